@@ -1,0 +1,157 @@
+/* rmem_b200 -- C ABI of the B200-native RMem (restricted-memory VOS) propagation engine.
+ *
+ * The reference (Restricted-Memory/RMem, pure Python/PyTorch) has no FFI layer: its boundary for this
+ * path is the Python method surface of AOTInferEngine / AOTEngine plus the LSTT/GPM module forwards
+ * (SURVEY.md section 8b).  This header is what a ctypes binding under those Python classes calls.
+ * Conventions: plain `extern "C"`, every entry returns int (0 = ok, <0 = error; message via
+ * rmem_last_error(), thread-local), never throws, never calls exit(), never allocates device memory
+ * (the caller passes outputs and a workspace/arena it sized with the matching *_bytes query), takes an
+ * explicit cudaStream_t (as void*), holds no global mutable state.  Device pointers only unless a
+ * parameter is marked HOST.  All activations are token-major ("[pixels, channels]", i.e. NHWC); bf16 is
+ * the tensor-core operand type, fp32 the residual / statistics / logits type.
+ *
+ * Paths are relative to /root/reference/aot_plus/.
+ */
+#ifndef RMEM_B200_H
+#define RMEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMEM_MAX_BANK_FRAMES 16
+#define RMEM_ATTN_DENSE 0 /* materialised scores: generic GEMMs + row softmax */
+#define RMEM_ATTN_TC 1    /* fused tcgen05 + TMA flash kernel */
+
+int rmem_version(void);
+const char* rmem_last_error(void);
+
+/* ---------------------------------------------------------------- op level (module forwards) ---- */
+
+/* Generic bf16 GEMM / implicit-GEMM conv with fused epilogue: nn.Linear / nn.Conv2d(+FrozenBatchNorm2d+ReLU)
+ * call sites of networks/encoders/resnet.py:48-68,178-195, networks/decoders/fpn.py:36-68,
+ * networks/layers/transformer.py:1104-1123, attention.py:151-172.  See rmem_b200/csrc/gemm.cuh. */
+typedef struct rmem_gemm_desc {
+  const void* A; long long lda;      /* bf16 [M,K] row-major, or NHWC map when conv != 0 */
+  const void* B; long long ldb;      /* bf16 [N,K] row-major weight (K ordered ky,kx,ci for conv) */
+  int M, N, K;
+  int conv, Hin, Win, Cin, Wout, kw, stride, pad;
+  float alpha;
+  const float* bias; int bias_along_m;
+  int act; int act_from_col;         /* 0 none, 1 relu, 2 silu; applied to columns >= act_from_col */
+  const void* residual; long long ldr;  /* bf16, added before the activation */
+  const void* gate; long long ldg;      /* bf16, multiplied after the activation */
+  int accumulate;                    /* C += result (fp32 destinations only) */
+  void* C; long long ldc; int c_is_f32;
+  void* C2; long long ldc2; int c2_is_f32; int n_split; /* columns >= n_split go to C2 */
+} rmem_gemm_desc;
+int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream);
+
+/* Long-term / self attention over the restricted bank with per-frame attention mass and the temporal
+ * positional embedding applied as a per-(query,frame) score bias.
+ * Replaces GatedPropagation.forward's QK^T -> softmax -> .V (networks/layers/attention.py:174-193), the
+ * mass record of transformer.py:1185-1192 and the temporal-PE add of transformer.py:1140-1175. */
+int rmem_long_attn_workspace_bytes(int impl, int HW, int HWp, int nslots, int Dv, size_t* bytes);
+int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void* kbank, const void* vtbank,
+                       int nslots, int T, const int* slots /*HOST [T]*/, int HW, int HWp, int Dk, int Dv,
+                       float scale, const void* gate, long long ldg, void* out, long long ldo, float* mass,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Qt = bf16(Q + cur_pos_emb); qbias[i,t] = scale * <Qt_i, pe_mem[t]>          (transformer.py:1140-1175) */
+/* pe_mem = mem_pos_emb [n_slots, C]; pe_slot HOST [T] = slot of each memory frame (rmem_temporal_pe_slots). */
+int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+                   float scale, void* qt, float* qbias, int P, int C, void* stream);
+/* Slot map of transformer.py:1140-1170 (identity for T<=4, flip-nearest-flip above): HOST out [T]. */
+int rmem_temporal_pe_slots(int T, int n_slots, int* out);
+
+/* Windowed short-term attention: LocalGatedPropagation.forward core (attention.py:289-353, 363-413). */
+int rmem_local_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                        const float* rel, long long ldrel, const void* gate, long long ldg, void* out,
+                        long long ldo, int h, int w, int Dv, float scale, void* stream);
+
+/* nn.LayerNorm (transformer.py:1104,1119,1222), GroupNorm (basic.py:6-12, 62-70), DWConv2d (basic.py:38-59). */
+int rmem_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
+                       int P, int C, void* stream);
+int rmem_groupnorm_fwd(const void* x, int x_is_f32, const float* gamma, const float* beta, void* y, int P, int C,
+                       int G, int relu, double* stats /* 2*G doubles scratch */, void* stream);
+int rmem_dwconv5x5_fwd(const void* x, const float* w /* [25,C] */, void* y, int h, int w_, int C, void* stream);
+
+/* F.interpolate(bilinear, align_corners=True) on NHWC bf16 (fpn.py:50,58). */
+int rmem_upsample_bilinear_fwd(const void* x, void* y, int hin, int win, int hout, int wout, int C, void* stream);
+int rmem_transpose_fwd(const void* x, long long ldx, void* y, long long ldy, int P, int C, void* stream);
+int rmem_maxpool3x3s2_fwd(const void* x, void* y, int Hin, int Win, int C, int Hout, int Wout, void* stream);
+int rmem_pack_image_fwd(const float* img_nchw, void* out_nhwc8, int H, int W, void* stream);
+
+/* ID bank: one_hot_mask (utils/image.py:69-74) + assign_identity (networks/engines/aot_engine.py:208-232) +
+ * patch_wise_id_bank Conv2d(12->256,k17,s16,p8) (networks/models/aot.py:63-74,111-114) + id_norm
+ * (networks/models/deaot.py:65-69), as a gather-sum indexed by the uint8 label. */
+int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed /* [289,12,C] */,
+                    const float* bias, const float* ln_gamma, const float* ln_beta, void* out_bf16, long long ldo,
+                    float* out_f32, int h, int w, int C, void* stream);
+
+/* Mask-ID assignment: bilinear(align_corners=True) upsample of the 1/4-res logits (aot_engine.py:457-463),
+ * soft_logit_aggregation over k object groups (aot_engine.py:650-673), softmax -> argmax
+ * (networks/managers/evaluator.py:430-441).  logits4: HOST array of k device pointers, each planar [11,h4,w4]. */
+int rmem_mask_head_fwd(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits,
+                       uint8_t* out_label, void* stream);
+
+/* Relevance term of the evict score: fg-prob from the low-res logits (aot_engine.py:355-362) times the layer-0
+ * attention mass, summed over tokens (transformer.py:891-906).  rel[T] un-normalised. */
+int rmem_evict_relevance_fwd(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w,
+                             float* rel, void* stream);
+/* EMA + UCB freshness + argmin (transformer.py:907-964).  HOST arithmetic on T_old floats.  idx = long_memories_indexes
+ * after the append (T_old+1 entries).  ema_keys/ema_vals/times_keys/times_vals are the engine's dictionaries
+ * (capacity RMEM_MAX_BANK_FRAMES+1, counts in/out).  Returns the logical index to drop in *drop. */
+int rmem_evict_pick(const float* rel_host, int T_old, const int* idx, int former, int* ema_keys, float* ema_vals,
+                    int* n_ema, int* times_keys, int* times_vals, int* n_times, int* drop);
+
+/* ---------------------------------------------------------------- engine level ---- */
+/* Per-clip state machine: AOTInferEngine.{add_reference_frame, match_propogate_one_frame, update_memory,
+ * restart_engine} (networks/engines/aot_engine.py:571-725, deaot_engine.py:20-56) over DeAOT
+ * (networks/models/deaot.py) = ResNet-50 encoder + DualBranchGPM (networks/layers/transformer.py:700-1249) +
+ * FPN decoder, with the restricted long-term bank (transformer.py:880-991) held in a caller-provided arena. */
+typedef struct rmem_engine_config {
+  int model;            /* 0 = r50_deaotl */
+  int H, W;             /* snapped input size (16k+1), dataloaders/video_transforms.py:607-615 */
+  int former_mem_len;   /* FORMER_MEM_LEN */
+  int latter_mem_len;   /* LATTER_MEM_LEN */
+  int max_engines;      /* ceil(max objects / 10) object groups */
+  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC */
+  int long_term_mem_gap;
+} rmem_engine_config;
+
+typedef struct rmem_weight_entry {
+  const char* name;     /* packed tensor name (see rmem_b200/weights.py) */
+  size_t offset;        /* byte offset into the weight blob */
+  size_t nbytes;
+} rmem_weight_entry;
+
+typedef struct rmem_engine rmem_engine; /* opaque, host-side */
+
+int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes);
+int rmem_engine_create(const rmem_engine_config* cfg, const void* weight_blob, const rmem_weight_entry* entries,
+                       int n_entries, void* arena, size_t arena_bytes, rmem_engine** out);
+void rmem_engine_destroy(rmem_engine* e);
+int rmem_engine_restart(rmem_engine* e);
+int rmem_engine_set_gap(rmem_engine* e, int long_term_mem_gap);
+/* label: device, fp32 (label_is_f32) or uint8, [H,W] integer object ids (255 = ignore). */
+int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void* label, int label_is_f32,
+                                    int n_objects, int frame_step, void* stream);
+/* out_logits [1+10k, Ho, Wo] fp32 (nullable), out_label uint8 [Ho, Wo] (nullable). */
+int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, float* out_logits, uint8_t* out_label,
+                          void* stream);
+int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f32, void* stream);
+/* introspection (parity tests): */
+int rmem_engine_num_groups(const rmem_engine* e);
+int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx /*HOST, cap 17*/, int* n);
+int rmem_engine_pred_logits(const rmem_engine* e, int group, const float** logits4, int* h4, int* w4);
+int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel /*HOST cap 16*/, int* n, int* drop);
+long long rmem_engine_launch_count(const rmem_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMEM_B200_H */

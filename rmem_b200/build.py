@@ -1,0 +1,77 @@
+"""Builds rmem_b200/lib/librmem_b200.so (hand-written sm_100a CUDA + the C ABI) with nvcc, in-tree.
+
+    python -m rmem_b200.build [--force] [--verbose]
+
+nvcc cross-compiles sm_100a without a GPU; the .so travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "librmem_b200.so")
+SOURCES = ["capi.cu", "gemm.cu", "ops.cu", "attn_dense.cu", "attn_tc.cu", "engine.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+# --use_fast_math only affects non-parity-critical kernels: the mask head / bilinear paths use explicit
+# __fmul_rn/__fadd_rn/__fdiv_rn and expf is called where exactness matters (see ops.cu).
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for root, _, files in os.walk(CSRC):
+        for f in sorted(files):
+            with open(os.path.join(root, f), "rb") as fh:
+                h.update(f.encode()); h.update(fh.read())
+    with open(os.path.join(HERE, "..", "include", "rmem_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, "build.sha256")
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return LIB
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"nvcc not found at {NVCC} and no up-to-date {LIB}; cannot build the CUDA extension")
+
+    def compile_one(src):
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    objs = []
+    log = []
+    for src, obj, r in results:
+        log.append(f"==== {src}\n{r.stdout}\n{r.stderr}")
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    with open(os.path.join(LIBDIR, "build.log"), "w") as fh:
+        fh.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,164 @@
+// C-ABI glue: error state, op-level entry points declared in include/rmem_b200.h.
+#include <cstdarg>
+#include <map>
+
+#include "../../include/rmem_b200.h"
+#include "attn.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+namespace rmem {
+
+static thread_local char g_err[1024] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+long long& launch_counter() { return g_launches; }
+
+int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former, std::map<int, float>& ema,
+                    std::map<int, int>& times, int* drop, float* rel_norm_out);
+
+}  // namespace rmem
+
+using namespace rmem;
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int rmem_version(void) { return 100; }
+const char* rmem_last_error(void) { return get_error(); }
+
+int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream) {
+  RMEM_REQUIRE(d, "null desc");
+  GemmParams p;
+  p.A = (const bf16*)d->A; p.lda = d->lda; p.B = (const bf16*)d->B; p.ldb = d->ldb;
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.conv = d->conv; p.Hin = d->Hin; p.Win = d->Win; p.Cin = d->Cin; p.Wout = d->Wout; p.kw = d->kw;
+  p.stride = d->stride; p.pad = d->pad;
+  p.alpha = d->alpha; p.bias = d->bias; p.bias_m = d->bias_along_m; p.act = d->act; p.act_from = d->act_from_col;
+  p.res = (const bf16*)d->residual; p.ldr = d->ldr; p.gate = (const bf16*)d->gate; p.ldg = d->ldg;
+  p.accumulate = d->accumulate;
+  p.C = d->C; p.ldc = d->ldc; p.c_fp32 = d->c_is_f32;
+  p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_fp32 = d->c2_is_f32;
+  p.n_split = d->C2 ? d->n_split : (1 << 30);
+  return gemm_launch(p, STREAM(stream));
+}
+
+int rmem_long_attn_workspace_bytes(int impl, int HW, int HWp, int nslots, int Dv, size_t* bytes) {
+  RMEM_REQUIRE(bytes, "null bytes");
+  *bytes = impl == RMEM_ATTN_TC ? long_attn_tc_workspace(HW, HWp, nslots, Dv) : long_attn_dense_workspace(HW, HWp, nslots);
+  return RMEM_OK;
+}
+
+int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void* kbank, const void* vtbank, int nslots,
+                       int T, const int* slots, int HW, int HWp, int Dk, int Dv, float scale, const void* gate,
+                       long long ldg, void* out, long long ldo, float* mass, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  RMEM_REQUIRE(qt && kbank && vtbank && out && slots && workspace, "null argument");
+  RMEM_REQUIRE(T >= 1 && T <= kMaxBankFrames, "T=%d out of range", T);
+  LongAttnArgs a;
+  a.qt = (const bf16*)qt; a.qbias = qbias; a.kbank = (const bf16*)kbank; a.vtbank = (const bf16*)vtbank;
+  a.nslots = nslots; a.T = T;
+  for (int t = 0; t < T; ++t) a.slot[t] = slots[t];
+  a.HW = HW; a.HWp = HWp; a.Dk = Dk; a.Dv = Dv; a.scale = scale;
+  a.gate = (const bf16*)gate; a.ldg = ldg; a.out = (bf16*)out; a.ldo = ldo; a.mass = mass;
+  if (impl == RMEM_ATTN_TC) return long_attn_tc(a, workspace, workspace_bytes, STREAM(stream));
+  return long_attn_dense(a, workspace, workspace_bytes, STREAM(stream));
+}
+
+int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+                   float scale, void* qt, float* qbias, int P, int C, void* stream) {
+  return qprep((const bf16*)q, ldq, pe_cur, pe_mem, pe_slot, T, scale, (bf16*)qt, qbias, P, C, STREAM(stream));
+}
+
+int rmem_temporal_pe_slots(int T, int n_slots, int* out) {
+  RMEM_REQUIRE(out && T >= 1 && T <= kMaxBankFrames && n_slots >= 1, "bad argument");
+  temporal_pe_slots(T, n_slots, out);
+  return RMEM_OK;
+}
+
+int rmem_local_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                        const float* rel, long long ldrel, const void* gate, long long ldg, void* out, long long ldo,
+                        int h, int w, int Dv, float scale, void* stream) {
+  return local_attn((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, rel, ldrel, (const bf16*)gate, ldg,
+                    (bf16*)out, ldo, h, w, Dv, scale, STREAM(stream));
+}
+
+int rmem_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
+                       int P, int C, void* stream) {
+  return layernorm(x, ldx, gamma, beta, (bf16*)y, ldy, nullptr, 0, P, C, STREAM(stream));
+}
+
+int rmem_groupnorm_fwd(const void* x, int x_is_f32, const float* gamma, const float* beta, void* y, int P, int C, int G,
+                       int relu, double* stats, void* stream) {
+  if (x_is_f32) return groupnorm_f32((const float*)x, gamma, beta, (bf16*)y, P, C, G, relu, stats, STREAM(stream));
+  return groupnorm_bf16((const bf16*)x, gamma, beta, (bf16*)y, P, C, G, relu, stats, STREAM(stream));
+}
+
+int rmem_dwconv5x5_fwd(const void* x, const float* w, void* y, int h, int w_, int C, void* stream) {
+  return dwconv5x5((const bf16*)x, w, (bf16*)y, h, w_, C, STREAM(stream));
+}
+
+int rmem_upsample_bilinear_fwd(const void* x, void* y, int hin, int win, int hout, int wout, int C, void* stream) {
+  return upsample_bilinear_bf16((const bf16*)x, (bf16*)y, hin, win, hout, wout, C, STREAM(stream));
+}
+
+int rmem_transpose_fwd(const void* x, long long ldx, void* y, long long ldy, int P, int C, void* stream) {
+  return transpose_bf16((const bf16*)x, ldx, (bf16*)y, ldy, P, C, STREAM(stream));
+}
+
+int rmem_maxpool3x3s2_fwd(const void* x, void* y, int Hin, int Win, int C, int Hout, int Wout, void* stream) {
+  return maxpool3x3s2((const bf16*)x, (bf16*)y, Hin, Win, C, Hout, Wout, STREAM(stream));
+}
+
+int rmem_pack_image_fwd(const float* img, void* out, int H, int W, void* stream) {
+  return pack_image(img, (bf16*)out, H, W, STREAM(stream));
+}
+
+int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
+                    const float* ln_gamma, const float* ln_beta, void* out_bf16, long long ldo, float* out_f32, int h,
+                    int w, int C, void* stream) {
+  RMEM_REQUIRE(label && w_packed && bias && (out_bf16 || out_f32), "null argument");
+  return idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_gamma, ln_beta, (bf16*)out_bf16, ldo, out_f32, h, w,
+                      C, STREAM(stream));
+}
+
+int rmem_mask_head_fwd(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits,
+                       uint8_t* out_label, void* stream) {
+  RMEM_REQUIRE(logits4, "null argument");
+  return mask_head(logits4, k, h4, w4, Ho, Wo, out_logits, out_label, STREAM(stream));
+}
+
+int rmem_evict_relevance_fwd(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel,
+                             void* stream) {
+  return evict_relevance(mass, T, logits4, h4, w4, h, w, rel, STREAM(stream));
+}
+
+int rmem_evict_pick(const float* rel_host, int T_old, const int* idx, int former, int* ema_keys, float* ema_vals,
+                    int* n_ema, int* times_keys, int* times_vals, int* n_times, int* drop) {
+  RMEM_REQUIRE(rel_host && idx && ema_keys && ema_vals && n_ema && times_keys && times_vals && n_times && drop,
+               "null argument");
+  RMEM_REQUIRE(T_old >= 1 && T_old <= kMaxBankFrames, "T_old=%d out of range", T_old);
+  std::map<int, float> ema;
+  std::map<int, int> times;
+  for (int i = 0; i < *n_ema; ++i) ema[ema_keys[i]] = ema_vals[i];
+  for (int i = 0; i < *n_times; ++i) times[times_keys[i]] = times_vals[i];
+  RMEM_TRY(evict_pick_host(rel_host, T_old, idx, former, ema, times, drop, nullptr));
+  int i = 0;
+  for (auto& kv : ema) { ema_keys[i] = kv.first; ema_vals[i] = kv.second; ++i; }
+  *n_ema = i;
+  i = 0;
+  for (auto& kv : times) { times_keys[i] = kv.first; times_vals[i] = kv.second; ++i; }
+  *n_times = i;
+  return RMEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// Shared device/host helpers for the rmem_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+namespace rmem {
+
+// ---- error plumbing (C-ABI never throws / exits; see include/rmem_b200.h) ----
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define RMEM_OK 0
+#define RMEM_ERR_ARG (-1)
+#define RMEM_ERR_CUDA (-2)
+#define RMEM_ERR_WEIGHT (-3)
+#define RMEM_ERR_ARENA (-4)
+#define RMEM_ERR_STATE (-5)
+
+#define RMEM_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      rmem::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return RMEM_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+// Every kernel launch goes through this macro; the thread-local counter backs bench.py's gpu_launches.
+long long& launch_counter();
+#define RMEM_LAUNCH_CHECK()                 \
+  do {                                      \
+    ++rmem::launch_counter();               \
+    RMEM_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
+
+#define RMEM_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      rmem::set_error(__VA_ARGS__);    \
+      return RMEM_ERR_ARG;             \
+    }                                  \
+  } while (0)
+
+#define RMEM_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != RMEM_OK) return _rc; \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `red` needs 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+  if (w == 0) {
+    r = warp_max(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  bf162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  bf162 v = *reinterpret_cast<bf162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
+
+}  // namespace rmem

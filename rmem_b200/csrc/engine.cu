@@ -1,0 +1,774 @@
+// Host-side per-clip state machine + frame orchestration of the DeAOT+RMem propagation path.
+//
+// Mirrors (behaviour, not code) of the reference, paths relative to /root/reference/aot_plus/:
+//   AOTInferEngine / DeAOTInferEngine   networks/engines/aot_engine.py:571-725, deaot_engine.py:20-56
+//   AOTEngine.{add_reference_frame, match_propogate_one_frame, update_short_term_memory}
+//                                        networks/engines/aot_engine.py:241-436
+//   DeAOT.{encode_image, get_id_emb, LSTT_forward, decode_id_logits}   networks/models/{aot,deaot}.py
+//   DualBranchGPM / GatedPropagationModule                             networks/layers/transformer.py:700-1249
+//   restrict_long_memories                                             networks/layers/transformer.py:880-991
+//
+// B200-first differences from the reference's structure: the bank is a fixed ring of physical slots in
+// a caller-provided HBM arena (no torch.cat re-allocation), V / ID_V are stored value-major so the
+// P.V contraction is K-major on both operands, the temporal positional embedding is a score bias
+// instead of a re-materialised K bank, the encoder runs once per frame for all object groups, and the
+// only host<->device sync is the T-float relevance read-back on frames that append to the bank.
+#include <map>
+#include <string>
+#include <vector>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/rmem_b200.h"
+#include "attn.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+namespace rmem {
+
+int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former, std::map<int, float>& ema,
+                    std::map<int, int>& times, int* drop, float* rel_norm_out);
+
+namespace {
+
+constexpr int kLayers = 3;
+constexpr int kD = 256;      // d_model
+constexpr int kDk = 128;     // att dim
+constexpr int kDv = 1024;    // V (512) || ID_V (512)
+constexpr int kMaxObj = 10;
+
+struct Geo {
+  int H, W, H1, W1, H4, W4, H8, W8, h, w;
+  int P1, P4, P8, HW, HWp;
+};
+
+Geo make_geo(int H, int W) {
+  Geo g;
+  g.H = H; g.W = W;
+  g.H1 = (H - 1) / 2 + 1; g.W1 = (W - 1) / 2 + 1;      // conv1 k7 s2 p3
+  g.H4 = (g.H1 - 1) / 2 + 1; g.W4 = (g.W1 - 1) / 2 + 1;  // maxpool k3 s2 p1
+  g.H8 = (g.H4 - 1) / 2 + 1; g.W8 = (g.W4 - 1) / 2 + 1;  // layer2 stride 2
+  g.h = (g.H8 - 1) / 2 + 1; g.w = (g.W8 - 1) / 2 + 1;    // layer3 stride 2
+  g.P1 = g.H1 * g.W1; g.P4 = g.H4 * g.W4; g.P8 = g.H8 * g.W8;
+  g.HW = g.h * g.w;
+  g.HWp = round_up(g.HW, 128);
+  return g;
+}
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  bool dry = false;
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    if (dry) return nullptr;
+    return (o + bytes <= cap) ? reinterpret_cast<T*>(base + o) : nullptr;
+  }
+};
+
+struct LayerState {
+  bf16* kc[2];       // [HW,128]   current / previous frame K (= Q)
+  bf16* vid[2];      // [HW,1024]  V || ID_V, token-major (short-term memory + source of the bank append)
+  bf16* cat;         // [HW,512]   curr_ID_V || id_emb  (linear_ID_V input; layer 0 uses only the id half)
+  bf16* kbank;       // [nslots][HWp][128]
+  bf16* vtbank;      // [1024][nslots*HWp]
+};
+
+struct Group {       // one AOTEngine: <= 10 objects, own bank (reference + per-engine deepcopy)
+  LayerState L[kLayers];
+  float* mass0;      // [HW,16] layer-0 attention mass of the last propagate (logical frame order)
+  int mass_T = 0;
+  float* logits4;    // planar [11, P4] = pred_id_logits
+  int parity = 0;    // which of kc/vid is "current"
+  std::vector<int> slots;       // logical frame -> physical slot
+  std::vector<int> free_slots;
+  std::vector<int> long_idx;    // long_memories_indexes
+  std::map<int, float> ema;     // stored_attn_weight_dict
+  std::map<int, int> times;     // stored_frame_times
+  int frame_step = 0, last_mem_step = -1;
+  bool has_ref = false;
+  std::vector<float> last_rel;
+  int last_drop = -1;
+};
+
+}  // namespace
+}  // namespace rmem
+
+using namespace rmem;
+
+struct rmem_engine {
+  rmem_engine_config cfg;
+  Geo g;
+  int nslots = 0;
+  std::map<std::string, std::pair<const char*, size_t>> weights;
+  int n_groups = 0;
+  std::vector<Group> groups;
+  long long launches0 = 0;
+
+  // shared scratch
+  bf16 *img8, *c1, *x0, *x1, *t1, *t2, *ds, *feat4, *feat8, *feat16;
+  float* enc_tgt;     // [HW,256] projector output
+  float* res;         // [HW,512] tgt || tgt_id residual stream
+  bf16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
+  float *qbias, *rel, *rel_dev;
+  bf16 *d0, *d1, *d2;
+  double* stats;
+  uint8_t* label8;
+  void* attn_ws;
+  size_t attn_ws_bytes;
+  char* arena_base = nullptr;
+  size_t state_begin = 0, state_bytes = 0;   // region zeroed per clip (banks, short-term memory)
+  bool ones_ready = false;
+
+  // ---------------------------------------------------------------------------------------------
+  template <typename T>
+  const T* Wt(const std::string& name, size_t elems, int* rc) {
+    auto it = weights.find(name);
+    if (it == weights.end()) {
+      set_error("missing weight '%s'", name.c_str());
+      *rc = RMEM_ERR_WEIGHT;
+      return nullptr;
+    }
+    if (it->second.second != elems * sizeof(T)) {
+      set_error("weight '%s': expected %zu bytes, blob has %zu", name.c_str(), elems * sizeof(T), it->second.second);
+      *rc = RMEM_ERR_WEIGHT;
+      return nullptr;
+    }
+    return reinterpret_cast<const T*>(it->second.first);
+  }
+
+  int layout(Arena& a) {
+    const Geo& G = g;
+    img8 = a.take<bf16>((size_t)G.H * G.W * 8);
+    c1 = a.take<bf16>((size_t)G.P1 * 64);
+    x0 = a.take<bf16>((size_t)G.P4 * 256);
+    x1 = a.take<bf16>((size_t)G.P4 * 256);
+    t1 = a.take<bf16>((size_t)G.P4 * 128);
+    t2 = a.take<bf16>((size_t)G.P4 * 64);
+    ds = a.take<bf16>((size_t)G.P4 * 256);
+    feat4 = a.take<bf16>((size_t)G.P4 * 256);
+    feat8 = a.take<bf16>((size_t)G.P8 * 512);
+    feat16 = a.take<bf16>((size_t)G.HW * 1024);
+    enc_tgt = a.take<float>((size_t)G.HW * kD);
+    res = a.take<float>((size_t)G.HW * 2 * kD);
+    t_ln = a.take<bf16>((size_t)G.HW * kD);
+    qt = a.take<bf16>((size_t)G.HW * kDk);
+    cu = a.take<bf16>((size_t)G.HW * kDv);
+    cu0 = a.take<bf16>((size_t)G.HW * kDv);
+    attn_a = a.take<bf16>((size_t)G.HW * kDv);
+    dwo = a.take<bf16>((size_t)G.HW * kDv);
+    z = a.take<bf16>((size_t)G.HW * 2 * kD);
+    qk = a.take<bf16>((size_t)G.HWp * kDk);
+    vt_self = a.take<bf16>((size_t)kDv * G.HWp);
+    u_self = a.take<bf16>((size_t)G.HW * kDv);
+    gpm_out = a.take<bf16>((size_t)G.HW * 2 * kD);
+    idemb = a.take<bf16>((size_t)G.HW * kD);
+    qbias = a.take<float>((size_t)G.HW * kMaxBankFrames);
+    rel = a.take<float>((size_t)G.HW * 256);
+    rel_dev = a.take<float>(64);
+    d0 = a.take<bf16>((size_t)G.P4 * 128);
+    d1 = a.take<bf16>((size_t)G.P4 * 128);
+    d2 = a.take<bf16>((size_t)G.P4 * 128);
+    stats = a.take<double>(64);
+    label8 = a.take<uint8_t>((size_t)G.H * G.W);
+    size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
+    size_t ws_tc = long_attn_tc_workspace(G.HW, G.HWp, nslots, kDv);
+    attn_ws_bytes = ws_dense > ws_tc ? ws_dense : ws_tc;
+    attn_ws = a.take<char>(attn_ws_bytes);
+    state_begin = a.off;
+    groups.assign(cfg.max_engines, Group());
+    for (auto& gr : groups) {
+      for (int l = 0; l < kLayers; ++l) {
+        LayerState& L = gr.L[l];
+        for (int p = 0; p < 2; ++p) {
+          L.kc[p] = a.take<bf16>((size_t)G.HWp * kDk);
+          L.vid[p] = a.take<bf16>((size_t)G.HW * kDv);
+        }
+        L.cat = a.take<bf16>((size_t)G.HW * 2 * kD);
+        L.kbank = a.take<bf16>((size_t)nslots * G.HWp * kDk);
+        L.vtbank = a.take<bf16>((size_t)kDv * nslots * G.HWp);
+      }
+      gr.mass0 = a.take<float>((size_t)G.HW * kMaxBankFrames);
+      gr.logits4 = a.take<float>((size_t)11 * G.P4);
+    }
+    state_bytes = a.off - state_begin;
+    if (!a.dry && a.off > a.cap) {
+      set_error("arena too small: need %zu bytes, have %zu", a.off, a.cap);
+      return RMEM_ERR_ARENA;
+    }
+    return RMEM_OK;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // conv / linear helpers over the generic GEMM
+  int conv(const bf16* x, int Hin, int Win, int Cin, const std::string& wname, int Cout, int k, int stride, int pad,
+           int act, const bf16* resid, bf16* out, cudaStream_t s) {
+    int rc = RMEM_OK;
+    const bf16* w = Wt<bf16>(wname + ".w", (size_t)Cout * k * k * Cin, &rc);
+    const float* b = Wt<float>(wname + ".b", Cout, &rc);
+    if (rc) return rc;
+    int Hout = (Hin + 2 * pad - k) / stride + 1, Wout = (Win + 2 * pad - k) / stride + 1;
+    GemmParams p;
+    p.A = x; p.B = w; p.ldb = (long long)k * k * Cin;
+    p.M = Hout * Wout; p.N = Cout; p.K = k * k * Cin;
+    if (k == 1 && stride == 1) {
+      p.lda = Cin;
+    } else {
+      p.conv = 1; p.Hin = Hin; p.Win = Win; p.Cin = Cin; p.Wout = Wout; p.kw = k; p.stride = stride; p.pad = pad;
+    }
+    p.bias = b; p.act = act;
+    p.res = resid; p.ldr = Cout;
+    p.C = out; p.ldc = Cout;
+    return gemm_launch(p, s);
+  }
+
+  struct Lin {
+    const bf16* A; long long lda; int M; int K; int N;
+    std::string w;
+    int act = ACT_NONE; int act_from = 0;
+    void* C = nullptr; long long ldc = 0; int c_fp32 = 0;
+    void* C2 = nullptr; long long ldc2 = 0; int c2_fp32 = 0; int n_split = 1 << 30;
+    int accumulate = 0;
+    int n_weight_rows = -1;   // rows stored in the blob (>= N when padded)
+  };
+  int linear(const Lin& L, cudaStream_t s) {
+    int rc = RMEM_OK;
+    int rows = L.n_weight_rows > 0 ? L.n_weight_rows : L.N;
+    const bf16* w = Wt<bf16>(L.w + ".w", (size_t)rows * L.K, &rc);
+    const float* b = Wt<float>(L.w + ".b", rows, &rc);
+    if (rc) return rc;
+    GemmParams p;
+    p.A = L.A; p.lda = L.lda; p.B = w; p.ldb = L.K;
+    p.M = L.M; p.N = L.N; p.K = L.K;
+    p.bias = b; p.act = L.act; p.act_from = L.act_from;
+    p.C = L.C; p.ldc = L.ldc; p.c_fp32 = L.c_fp32;
+    p.C2 = L.C2; p.ldc2 = L.ldc2; p.c2_fp32 = L.c2_fp32; p.n_split = L.n_split;
+    p.accumulate = L.accumulate;
+    return gemm_launch(p, s);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // ResNet-50 stem + layer1..3 (FrozenBN folded) + encoder_projector.   resnet.py:178-195, aot.py:116-134
+  int bottleneck(const bf16* x, int Hin, int Win, int Cin, const std::string& pre, int planes, int stride, bool has_ds,
+                 bf16* out, cudaStream_t s) {
+    int Hout = (Hin - 1) / stride + 1, Wout = (Win - 1) / stride + 1;
+    RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".conv1", planes, 1, 1, 0, ACT_RELU, nullptr, t1, s));
+    RMEM_TRY(conv(t1, Hin, Win, planes, pre + ".conv2", planes, 3, stride, 1, ACT_RELU, nullptr, t2, s));
+    const bf16* idt = x;
+    if (has_ds) {
+      RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".ds", planes * 4, 1, stride, 0, ACT_NONE, nullptr, ds, s));
+      idt = ds;
+    }
+    RMEM_TRY(conv(t2, Hout, Wout, planes, pre + ".conv3", planes * 4, 1, 1, 0, ACT_RELU, idt, out, s));
+    return RMEM_OK;
+  }
+
+  int encode(const float* img, cudaStream_t s) {
+    const Geo& G = g;
+    RMEM_TRY(pack_image(img, img8, G.H, G.W, s));
+    RMEM_TRY(conv(img8, G.H, G.W, 8, "enc.conv1", 64, 7, 2, 3, ACT_RELU, nullptr, c1, s));
+    RMEM_TRY(maxpool3x3s2(c1, x0, G.H1, G.W1, 64, G.H4, G.W4, s));
+    bf16* cur = x0;
+    int Hc = G.H4, Wc = G.W4, Cc = 64;
+    const int planes[3] = {64, 128, 256}, nblk[3] = {3, 4, 6}, strides[3] = {1, 2, 2};
+    bf16* feats[3] = {feat4, feat8, feat16};
+    for (int li = 0; li < 3; ++li) {
+      for (int bi = 0; bi < nblk[li]; ++bi) {
+        int st = bi == 0 ? strides[li] : 1;
+        bool has_ds = bi == 0;
+        bf16* out = (bi == nblk[li] - 1) ? feats[li] : ((cur == x0) ? x1 : x0);
+        std::string pre = "enc.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+        RMEM_TRY(bottleneck(cur, Hc, Wc, Cc, pre, planes[li], st, has_ds, out, s));
+        Hc = (Hc - 1) / st + 1; Wc = (Wc - 1) / st + 1; Cc = planes[li] * 4;
+        cur = out;
+      }
+    }
+    Lin p;
+    p.A = feat16; p.lda = 1024; p.M = G.HW; p.K = 1024; p.N = kD; p.w = "proj";
+    p.C = enc_tgt; p.ldc = kD; p.c_fp32 = 1;
+    return linear(p, s);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  int id_embed(Group& gr, int gi, const void* label, int label_is_f32, int use_ignore, cudaStream_t s) {
+    const Geo& G = g;
+    int rc = RMEM_OK;
+    const float* w = Wt<float>("idbank.w", (size_t)289 * 12 * kD, &rc);
+    const float* b = Wt<float>("idbank.b", kD, &rc);
+    const float* lg = Wt<float>("id_norm.g", kD, &rc);
+    const float* lb = Wt<float>("id_norm.b", kD, &rc);
+    if (rc) return rc;
+    RMEM_TRY(separate_label(label, label_is_f32, label8, G.H, G.W, gi, n_groups, s));
+    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s));
+    for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_bf16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
+    return RMEM_OK;
+  }
+
+  // ID_V = silu(linear_ID_V(cat[curr_ID_V, id_emb]))  -> vid[cur][:, 512:]      transformer.py:1238-1244
+  int fuse_id(Group& gr, int l, cudaStream_t s) {
+    const Geo& G = g;
+    Lin p;
+    std::string pre = "gpm." + std::to_string(l);
+    if (l == 0) { p.A = idemb; p.lda = kD; p.K = kD; }
+    else { p.A = gr.L[l].cat; p.lda = 2 * kD; p.K = 2 * kD; }
+    p.M = G.HW; p.N = 2 * kD; p.w = pre + ".linear_ID_V"; p.act = ACT_SILU;
+    p.C = gr.L[l].vid[gr.parity] + 512; p.ldc = kDv;
+    return linear(p, s);
+  }
+
+  int append_long(Group& gr, cudaStream_t s) {
+    const Geo& G = g;
+    if (gr.free_slots.empty()) { set_error("bank overflow"); return RMEM_ERR_STATE; }
+    int slot = gr.free_slots.back();
+    gr.free_slots.pop_back();
+    for (int l = 0; l < kLayers; ++l) {
+      LayerState& L = gr.L[l];
+      RMEM_TRY(copy2d_bf16(L.kc[gr.parity], kDk, L.kbank + (size_t)slot * G.HWp * kDk, kDk, G.HW, kDk, s));
+      RMEM_TRY(transpose_bf16(L.vid[gr.parity], kDv, L.vtbank + (size_t)slot * G.HWp, (long long)nslots * G.HWp,
+                              G.HW, kDv, s));
+    }
+    gr.slots.push_back(slot);
+    return RMEM_OK;
+  }
+
+  int attention(const LongAttnArgs& a, cudaStream_t s) {
+    if (cfg.attn_impl == RMEM_ATTN_TC) return long_attn_tc(a, attn_ws, attn_ws_bytes, s);
+    return long_attn_dense(a, attn_ws, attn_ws_bytes, s);
+  }
+
+  // gated epilogue tail: DWConv5x5 -> Linear(1024->512) accumulated into the tgt || tgt_id residual stream
+  int gated_tail(const std::string& pre, cudaStream_t s) {
+    const Geo& G = g;
+    int rc = RMEM_OK;
+    const float* dw = Wt<float>(pre + ".dw", (size_t)25 * kDv, &rc);
+    if (rc) return rc;
+    RMEM_TRY(dwconv5x5(attn_a, dw, dwo, G.h, G.w, kDv, s));
+    Lin p;
+    p.A = dwo; p.lda = kDv; p.M = G.HW; p.K = kDv; p.N = 2 * kD; p.w = pre + ".proj";
+    p.C = res; p.ldc = 2 * kD; p.c_fp32 = 1; p.accumulate = 1;
+    return linear(p, s);
+  }
+
+  // One GatedPropagationModule.forward (transformer.py:1091-1236).  ref_mode: curr_id_emb given.
+  int gpm_layer(Group& gr, int l, bool ref_mode, cudaStream_t s) {
+    const Geo& G = g;
+    const std::string pre = "gpm." + std::to_string(l);
+    LayerState& L = gr.L[l];
+    const int cur = gr.parity, prev = gr.parity ^ 1;
+    int rc = RMEM_OK;
+    const float scale = 1.f / sqrtf((float)kDk);
+
+    // t = LN1(tgt); Q|V = linear_QV(t) (silu on V); U = linear_U(t)
+    const float* n1g = Wt<float>(pre + ".norm1.g", kD, &rc);
+    const float* n1b = Wt<float>(pre + ".norm1.b", kD, &rc);
+    if (rc) return rc;
+    RMEM_TRY(layernorm(res, 2 * kD, n1g, n1b, t_ln, kD, nullptr, 0, G.HW, kD, s));
+    {
+      Lin p;
+      p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = kDk + 2 * kD; p.w = pre + ".linear_QV";
+      p.act = ACT_SILU; p.act_from = kDk;
+      p.C = L.kc[cur]; p.ldc = kDk;
+      p.C2 = L.vid[cur]; p.ldc2 = kDv; p.n_split = kDk;
+      RMEM_TRY(linear(p, s));
+    }
+    bf16* gate = (l == 0) ? cu0 : cu;
+    {
+      Lin p;
+      p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_U";
+      p.act = ACT_SILU; p.C = gate; p.ldc = kDv;
+      RMEM_TRY(linear(p, s));
+    }
+    if (l > 0) {
+      const float* g1 = Wt<float>(pre + ".id_norm1.g", kD, &rc);
+      const float* b1 = Wt<float>(pre + ".id_norm1.b", kD, &rc);
+      if (rc) return rc;
+      // ti = id_LN1(tgt_id) -> curr_ID_V (first half of the linear_ID_V input), also A of linear_ID_U
+      RMEM_TRY(layernorm(res + kD, 2 * kD, g1, b1, L.cat, 2 * kD, nullptr, 0, G.HW, kD, s));
+      Lin p;
+      p.A = L.cat; p.lda = 2 * kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_ID_U";
+      p.act = ACT_SILU; p.C = gate + 512; p.ldc = kDv;
+      RMEM_TRY(linear(p, s));
+    }
+
+    // memories
+    LongAttnArgs a;
+    a.HW = G.HW; a.HWp = G.HWp; a.Dk = kDk; a.Dv = kDv; a.scale = scale;
+    a.gate = gate; a.ldg = kDv; a.out = attn_a; a.ldo = kDv;
+    const bf16 *sk, *sv;
+    int T;
+    if (ref_mode) {
+      RMEM_TRY(fuse_id(gr, l, s));                    // ID_V of the reference frame itself (:1125-1135)
+      // bank := this frame -> physical slot 0
+      RMEM_TRY(copy2d_bf16(L.kc[cur], kDk, L.kbank, kDk, G.HW, kDk, s));
+      RMEM_TRY(transpose_bf16(L.vid[cur], kDv, L.vtbank, (long long)nslots * G.HWp, G.HW, kDv, s));
+      T = 1;
+      a.slot[0] = 0;
+      sk = L.kc[cur]; sv = L.vid[cur];
+    } else {
+      T = (int)gr.slots.size();
+      for (int t = 0; t < T; ++t) a.slot[t] = gr.slots[t];
+      sk = L.kc[prev]; sv = L.vid[prev];
+    }
+    a.T = T; a.nslots = nslots; a.kbank = L.kbank; a.vtbank = L.vtbank;
+    {
+      const float* pc = Wt<float>("cur_pos_emb", kDk, &rc);
+      const float* pm = Wt<float>("mem_pos_emb", 4 * kDk, &rc);
+      if (rc) return rc;
+      int pe_slot[kMaxBankFrames];
+      temporal_pe_slots(T, 4, pe_slot);
+      RMEM_TRY(qprep(L.kc[cur], kDk, pc, pm, pe_slot, T, scale, qt, qbias, G.HW, kDk, s));
+    }
+    a.qt = qt; a.qbias = qbias;
+    a.mass = (l == 0 && !ref_mode) ? gr.mass0 : nullptr;
+    if (a.mass) gr.mass_T = T;
+    RMEM_TRY(attention(a, s));
+    RMEM_TRY(gated_tail(pre + ".long", s));
+
+    // short-term windowed attention over the previous frame
+    {
+      Lin p;
+      p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 225; p.n_weight_rows = 256;
+      p.w = pre + ".short.rel"; p.C = rel; p.ldc = 256; p.c_fp32 = 1;
+      RMEM_TRY(linear(p, s));
+      RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
+      RMEM_TRY(gated_tail(pre + ".short", s));
+    }
+
+    // self attention on cat(LN2(tgt), id_LN2(tgt_id))
+    {
+      const float* g2 = Wt<float>(pre + ".norm2.g", kD, &rc);
+      const float* b2 = Wt<float>(pre + ".norm2.b", kD, &rc);
+      const float* gi2 = Wt<float>(pre + ".id_norm2.g", kD, &rc);
+      const float* bi2 = Wt<float>(pre + ".id_norm2.b", kD, &rc);
+      if (rc) return rc;
+      RMEM_TRY(layernorm(res, 2 * kD, g2, b2, z, 2 * kD, nullptr, 0, G.HW, kD, s));
+      RMEM_TRY(layernorm(res + kD, 2 * kD, gi2, bi2, z + kD, 2 * kD, nullptr, 0, G.HW, kD, s));
+      Lin p;
+      p.A = z; p.lda = 2 * kD; p.M = G.HW; p.K = 2 * kD; p.N = kDk; p.w = pre + ".self.linear_QK";
+      p.C = qk; p.ldc = kDk;
+      RMEM_TRY(linear(p, s));
+      for (int half = 0; half < 2; ++half) {
+        // v^T = silu(W_V . z_half^T + b): computed directly value-major (bias along M)
+        const std::string wn = pre + ".self.linear_V" + std::to_string(half + 1);
+        const bf16* w = Wt<bf16>(wn + ".w", (size_t)2 * kD * kD, &rc);
+        const float* b = Wt<float>(wn + ".b", 2 * kD, &rc);
+        if (rc) return rc;
+        GemmParams q;
+        q.A = w; q.lda = kD; q.B = z + half * kD; q.ldb = 2 * kD;
+        q.M = 2 * kD; q.N = G.HW; q.K = kD;
+        q.bias = b; q.bias_m = 1; q.act = ACT_SILU;
+        q.C = vt_self + (size_t)half * 2 * kD * G.HWp; q.ldc = G.HWp;
+        RMEM_TRY(gemm_launch(q, s));
+        Lin u;
+        u.A = z + half * kD; u.lda = 2 * kD; u.M = G.HW; u.K = kD; u.N = 2 * kD;
+        u.w = pre + ".self.linear_U" + std::to_string(half + 1);
+        u.act = ACT_SILU; u.C = u_self + half * 2 * kD; u.ldc = kDv;
+        RMEM_TRY(linear(u, s));
+      }
+      LongAttnArgs sa;
+      sa.HW = G.HW; sa.HWp = G.HWp; sa.Dk = kDk; sa.Dv = kDv; sa.scale = scale;
+      sa.qt = qk; sa.kbank = qk; sa.vtbank = vt_self; sa.nslots = 1; sa.T = 1; sa.slot[0] = 0;
+      sa.gate = u_self; sa.ldg = kDv; sa.out = attn_a; sa.ldo = kDv;
+      RMEM_TRY(attention(sa, s));
+      RMEM_TRY(gated_tail(pre + ".self", s));
+    }
+    return RMEM_OK;
+  }
+
+  // DualBranchGPM.forward (transformer.py:765-824) + FPN decoder (fpn.py:36-68) for one object group.
+  int lstt_decode(Group& gr, bool ref_mode, cudaStream_t s) {
+    const Geo& G = g;
+    int rc = RMEM_OK;
+    // residual stream: tgt = projector output, tgt_id = 0
+    RMEM_CUDA_CHECK(cudaMemcpy2DAsync(res, 2 * kD * sizeof(float), enc_tgt, kD * sizeof(float), kD * sizeof(float),
+                                      G.HW, cudaMemcpyDeviceToDevice, s));
+    RMEM_CUDA_CHECK(cudaMemset2DAsync(res + kD, 2 * kD * sizeof(float), 0, kD * sizeof(float), G.HW, s));
+    if (!ones_ready) {
+      RMEM_TRY(fill_bf16(cu0 + 512, kDv, G.HW, 512, 1.0f, s));
+      ones_ready = true;
+    }
+    for (int l = 0; l < kLayers; ++l) RMEM_TRY(gpm_layer(gr, l, ref_mode, s));
+    const float* og = Wt<float>("gpm.out_norm.g", 2 * kD, &rc);
+    const float* ob = Wt<float>("gpm.out_norm.b", 2 * kD, &rc);
+    if (rc) return rc;
+    RMEM_TRY(groupnorm_f32(res, og, ob, gpm_out, G.HW, 2 * kD, 2, 0, stats, s));
+
+    // ---- FPN ----
+    auto gn = [&](const std::string& n, const bf16* x, bf16* y, int P, int C) -> int {
+      int r2 = RMEM_OK;
+      const float* gg = Wt<float>(n + ".gn.g", C, &r2);
+      const float* gb = Wt<float>(n + ".gn.b", C, &r2);
+      if (r2) return r2;
+      return groupnorm_bf16(x, gg, gb, y, P, C, 8, 1, stats, s);
+    };
+    RMEM_TRY(conv(gpm_out, G.h, G.w, 2 * kD, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s));
+    RMEM_TRY(gn("dec.conv_in", d0, d1, G.HW, 256));
+    RMEM_TRY(conv(feat16, G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, d1, d0, s));
+    RMEM_TRY(conv(d0, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s));
+    RMEM_TRY(gn("dec.conv_16x", d2, d1, G.HW, 256));
+    RMEM_TRY(upsample_bilinear_bf16(d1, d0, G.h, G.w, G.H8, G.W8, 256, s));
+    RMEM_TRY(conv(feat8, G.H8, G.W8, 512, "dec.adapter_8x", 256, 1, 1, 0, ACT_NONE, d0, d2, s));
+    RMEM_TRY(conv(d2, G.H8, G.W8, 256, "dec.conv_8x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
+    RMEM_TRY(gn("dec.conv_8x", d0, d1, G.P8, 128));
+    RMEM_TRY(upsample_bilinear_bf16(d1, d0, G.H8, G.W8, G.H4, G.W4, 128, s));
+    RMEM_TRY(conv(feat4, G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, d0, d2, s));
+    RMEM_TRY(conv(d2, G.H4, G.W4, 128, "dec.conv_4x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
+    RMEM_TRY(gn("dec.conv_4x", d0, d1, G.P4, 128));
+    const bf16* wo = Wt<bf16>("dec.conv_out.w", (size_t)11 * 128, &rc);
+    const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);
+    if (rc) return rc;
+    return conv_out_logits(d1, wo, bo, gr.logits4, G.P4, 128, 11, s);
+  }
+};
+
+// =================================================================================================
+namespace rmem {
+
+// transformer.py:907-964 -- EMA + UCB bonus + argmin, fp32 host arithmetic on T_old values.
+int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former, std::map<int, float>& ema,
+                    std::map<int, int>& times, int* drop, float* rel_norm_out) {
+  float sum = 0.f;
+  for (int t = 0; t < T_old; ++t) sum += rel_raw[t];
+  std::vector<float> rel(T_old);
+  for (int t = 0; t < T_old; ++t) {
+    rel[t] = rel_raw[t] / sum;
+    if (rel_norm_out) rel_norm_out[t] = rel[t];
+  }
+  std::map<int, float> new_ema;
+  for (int t = 0; t < T_old; ++t) {
+    auto it = ema.find(idx[t]);
+    float v = rel[t];
+    if (it != ema.end()) {
+      // (1 - 0.8) and 0.8 as fp32 scalars, two roundings then the add -- what torch does for `py_float * tensor`
+      float x = 0.2f * it->second;
+      float y = 0.8f * rel[t];
+      v = x + y;
+    }
+    new_ema[idx[t]] = v;
+  }
+  ema.swap(new_ema);
+  std::map<int, int> new_times;
+  for (int t = 0; t <= T_old; ++t) {
+    auto it = times.find(idx[t]);
+    new_times[idx[t]] = 1 + (it != times.end() ? it->second : 0);
+  }
+  times.swap(new_times);
+  std::vector<float> tt(T_old);
+  float tsum = 0.f;
+  for (int t = 0; t < T_old; ++t) tt[t] = (float)times[idx[t]];
+  tt[0] = (float)T_old;
+  for (int t = 0; t < T_old; ++t) tsum += tt[t];
+  const float lg = logf(tsum);
+  int best = former;
+  if (T_old > 1) {
+    float bs = INFINITY;
+    for (int t = 1; t < T_old; ++t) {
+      float q = lg / (tt[t] + 8.0f);
+      float bonus = 1.5f * sqrtf(q);
+      float score = ema[idx[t]] + bonus;
+      if (score < bs) { bs = score; best = t; }
+    }
+  }
+  *drop = best;
+  return RMEM_OK;
+}
+
+}  // namespace rmem
+
+// =================================================================================================
+extern "C" {
+
+int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
+  RMEM_REQUIRE(cfg && bytes, "null argument");
+  RMEM_REQUIRE(cfg->model == 0, "only model 0 (r50_deaotl) is built");
+  RMEM_REQUIRE(cfg->H > 16 && cfg->W > 16 && (cfg->H - 1) % 16 == 0 && (cfg->W - 1) % 16 == 0,
+               "input size %dx%d is not 16k+1 (snap with MultiRestrictSize first)", cfg->H, cfg->W);
+  RMEM_REQUIRE(cfg->max_engines >= 1 && cfg->max_engines <= 4, "max_engines=%d out of 1..4", cfg->max_engines);
+  RMEM_REQUIRE(cfg->former_mem_len >= 1 && cfg->former_mem_len + cfg->latter_mem_len + 1 <= kMaxBankFrames,
+               "bank capacity %d+%d(+1) exceeds %d", cfg->former_mem_len, cfg->latter_mem_len, kMaxBankFrames);
+  rmem_engine tmp;
+  tmp.cfg = *cfg;
+  tmp.g = make_geo(cfg->H, cfg->W);
+  tmp.nslots = cfg->former_mem_len + cfg->latter_mem_len + 1;
+  Arena a;
+  a.dry = true;
+  tmp.layout(a);
+  *bytes = a.off + 256;
+  return RMEM_OK;
+}
+
+int rmem_engine_create(const rmem_engine_config* cfg, const void* weight_blob, const rmem_weight_entry* entries,
+                       int n_entries, void* arena, size_t arena_bytes, rmem_engine** out) {
+  RMEM_REQUIRE(cfg && weight_blob && entries && arena && out, "null argument");
+  size_t need = 0;
+  RMEM_TRY(rmem_engine_arena_bytes(cfg, &need));
+  RMEM_REQUIRE((reinterpret_cast<uintptr_t>(arena) & 255) == 0, "arena must be 256-byte aligned");
+  RMEM_REQUIRE((reinterpret_cast<uintptr_t>(weight_blob) & 255) == 0, "weight blob must be 256-byte aligned");
+  rmem_engine* e = new rmem_engine();
+  e->cfg = *cfg;
+  e->g = make_geo(cfg->H, cfg->W);
+  e->nslots = cfg->former_mem_len + cfg->latter_mem_len + 1;
+  for (int i = 0; i < n_entries; ++i) {
+    if ((entries[i].offset & 15) != 0) {
+      set_error("weight '%s' is not 16-byte aligned in the blob", entries[i].name);
+      delete e;
+      return RMEM_ERR_WEIGHT;
+    }
+    e->weights[entries[i].name] = {reinterpret_cast<const char*>(weight_blob) + entries[i].offset, entries[i].nbytes};
+  }
+  Arena a;
+  a.base = reinterpret_cast<char*>(arena);
+  a.cap = arena_bytes;
+  int rc = e->layout(a);
+  if (rc) { delete e; return rc; }
+  e->arena_base = a.base;
+  // one-time clear (create is off the hot path): pad rows/columns of K / value-major buffers must be finite
+  if (cudaMemset(arena, 0, a.off) != cudaSuccess) {
+    set_error("arena clear failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete e;
+    return RMEM_ERR_CUDA;
+  }
+  e->launches0 = launch_counter();
+  *out = e;
+  return RMEM_OK;
+}
+
+void rmem_engine_destroy(rmem_engine* e) { delete e; }
+
+int rmem_engine_restart(rmem_engine* e) {
+  RMEM_REQUIRE(e, "null engine");
+  e->n_groups = 0;
+  for (auto& gr : e->groups) {
+    gr.slots.clear(); gr.free_slots.clear(); gr.long_idx.clear(); gr.ema.clear(); gr.times.clear();
+    gr.frame_step = 0; gr.last_mem_step = -1; gr.has_ref = false; gr.parity = 0; gr.mass_T = 0;
+    gr.last_rel.clear(); gr.last_drop = -1;
+  }
+  return RMEM_OK;
+}
+
+int rmem_engine_set_gap(rmem_engine* e, int gap) {
+  RMEM_REQUIRE(e && gap >= 1, "bad gap");
+  e->cfg.long_term_mem_gap = gap;
+  return RMEM_OK;
+}
+
+int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void* label, int label_is_f32,
+                                    int n_objects, int frame_step, void* stream) {
+  RMEM_REQUIRE(e && img && label, "null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int n = (n_objects + kMaxObj - 1) / kMaxObj;
+  if (n < 1) n = 1;
+  RMEM_REQUIRE(n <= e->cfg.max_engines, "%d objects need %d object groups, engine built for %d", n_objects, n,
+               e->cfg.max_engines);
+  if (n > e->n_groups) e->n_groups = n;
+  if (frame_step < 0) frame_step = 0;
+  // zero the bank/state region once per clip (pad columns of the value-major bank must stay finite)
+  RMEM_CUDA_CHECK(cudaMemsetAsync(e->arena_base + e->state_begin, 0, e->state_bytes, s));
+  RMEM_TRY(e->encode(img, s));
+  for (int gi = 0; gi < e->n_groups; ++gi) {
+    Group& gr = e->groups[gi];
+    RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/0, s));
+    gr.slots.clear(); gr.free_slots.clear();
+    for (int sl = e->nslots - 1; sl >= 1; --sl) gr.free_slots.push_back(sl);
+    gr.slots.push_back(0);
+    gr.ema.clear(); gr.times.clear();
+    RMEM_TRY(e->lstt_decode(gr, /*ref_mode=*/true, s));
+    gr.parity ^= 1;                      // this frame becomes the short-term memory
+    gr.last_mem_step = frame_step;
+    gr.long_idx.push_back(gr.frame_step);
+    gr.has_ref = true;
+  }
+  return RMEM_OK;
+}
+
+int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, float* out_logits, uint8_t* out_label,
+                          void* stream) {
+  RMEM_REQUIRE(e && img, "null argument");
+  RMEM_REQUIRE(e->n_groups >= 1 && e->groups[0].has_ref, "propagate before add_reference_frame");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  RMEM_TRY(e->encode(img, s));
+  const float* lg[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int gi = 0; gi < e->n_groups; ++gi) {
+    Group& gr = e->groups[gi];
+    gr.frame_step += 1;
+    RMEM_TRY(e->lstt_decode(gr, /*ref_mode=*/false, s));
+    lg[gi] = gr.logits4;
+  }
+  if (out_logits || out_label)
+    RMEM_TRY(mask_head(lg, e->n_groups, e->g.H4, e->g.W4, Ho, Wo, out_logits, out_label, s));
+  return RMEM_OK;
+}
+
+int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f32, void* stream) {
+  RMEM_REQUIRE(e && label, "null argument");
+  RMEM_REQUIRE(e->n_groups >= 1 && e->groups[0].has_ref, "update_memory before add_reference_frame");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const Geo& G = e->g;
+  const int cap = e->cfg.former_mem_len + e->cfg.latter_mem_len;
+  for (int gi = 0; gi < e->n_groups; ++gi) {
+    Group& gr = e->groups[gi];
+    RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/1, s));
+    bool is_long = (gr.frame_step - gr.last_mem_step) >= e->cfg.long_term_mem_gap;
+    if (is_long) gr.last_mem_step = gr.frame_step;
+    for (int l = 0; l < kLayers; ++l) RMEM_TRY(e->fuse_id(gr, l, s));      // transformer.py:826-857
+    if (is_long) {
+      RMEM_TRY(e->append_long(gr, s));
+      gr.long_idx.push_back(gr.frame_step);
+      // aot_engine.py:350-369 -> transformer.py:880-991
+      const int T_old = gr.mass_T;
+      RMEM_REQUIRE(T_old + 1 == (int)gr.slots.size(), "attention mass is stale (T_old=%d, bank=%zu)", T_old,
+                   gr.slots.size());
+      RMEM_TRY(evict_relevance(gr.mass0, T_old, gr.logits4, G.H4, G.W4, G.h, G.w, e->rel_dev, s));
+      float rel_host[kMaxBankFrames];
+      RMEM_CUDA_CHECK(cudaMemcpyAsync(rel_host, e->rel_dev, sizeof(float) * T_old, cudaMemcpyDeviceToHost, s));
+      RMEM_CUDA_CHECK(cudaStreamSynchronize(s));
+      int drop = e->cfg.former_mem_len;
+      gr.last_rel.assign(T_old, 0.f);
+      RMEM_TRY(evict_pick_host(rel_host, T_old, gr.long_idx.data(), e->cfg.former_mem_len, gr.ema, gr.times, &drop,
+                               gr.last_rel.data()));
+      gr.last_drop = drop;
+      if ((int)gr.slots.size() > cap) {
+        gr.free_slots.push_back(gr.slots[drop]);
+        gr.slots.erase(gr.slots.begin() + drop);
+        gr.long_idx.erase(gr.long_idx.begin() + drop);
+      }
+    }
+    gr.parity ^= 1;   // current frame -> short-term memory
+  }
+  return RMEM_OK;
+}
+
+int rmem_engine_num_groups(const rmem_engine* e) { return e ? e->n_groups : 0; }
+
+int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx, int* n) {
+  RMEM_REQUIRE(e && idx && n && group >= 0 && group < e->n_groups, "bad argument");
+  const Group& gr = e->groups[group];
+  *n = (int)gr.long_idx.size();
+  for (int i = 0; i < *n && i < kMaxBankFrames + 1; ++i) idx[i] = gr.long_idx[i];
+  return RMEM_OK;
+}
+
+int rmem_engine_pred_logits(const rmem_engine* e, int group, const float** logits4, int* h4, int* w4) {
+  RMEM_REQUIRE(e && logits4 && group >= 0 && group < e->n_groups, "bad argument");
+  *logits4 = e->groups[group].logits4;
+  if (h4) *h4 = e->g.H4;
+  if (w4) *w4 = e->g.W4;
+  return RMEM_OK;
+}
+
+int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel, int* n, int* drop) {
+  RMEM_REQUIRE(e && rel && n && drop && group >= 0 && group < e->n_groups, "bad argument");
+  const Group& gr = e->groups[group];
+  *n = (int)gr.last_rel.size();
+  for (int i = 0; i < *n; ++i) rel[i] = gr.last_rel[i];
+  *drop = gr.last_drop;
+  return RMEM_OK;
+}
+
+long long rmem_engine_launch_count(const rmem_engine* e) { return e ? launch_counter() - e->launches0 : 0; }
+
+}  // extern "C"

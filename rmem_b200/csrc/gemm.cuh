@@ -1,0 +1,43 @@
+// Generic bf16 GEMM / implicit-GEMM convolution with a fused epilogue.
+//   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )
+// A is either a row-major matrix (linear mode) or an NHWC activation map gathered on the fly
+// (conv mode, K ordered (ky,kx,ci)); B is always the [N,K] row-major weight (K-major both sides).
+// This is the general-purpose workhorse for the ResNet-50 encoder, FPN decoder and the GPM
+// projections; the attention contractions have their own kernels.
+#pragma once
+#include "common.cuh"
+
+namespace rmem {
+
+struct GemmParams {
+  const bf16* A = nullptr;
+  long long lda = 0;
+  const bf16* B = nullptr;
+  long long ldb = 0;
+  int M = 0, N = 0, K = 0;
+  // conv mode (A = NHWC [Hin,Win,Cin]); output pixel m -> (m / Wout, m % Wout)
+  int conv = 0, Hin = 0, Win = 0, Cin = 0, Wout = 0, kw = 1, stride = 1, pad = 0;
+  // epilogue
+  float alpha = 1.f;
+  const float* bias = nullptr;  // [N] (or [M] if bias_m)
+  int bias_m = 0;
+  int act = ACT_NONE;           // applied to columns >= act_from
+  int act_from = 0;
+  const bf16* res = nullptr;    // added before the activation
+  long long ldr = 0;
+  const bf16* gate = nullptr;   // multiplied after the activation
+  long long ldg = 0;
+  int accumulate = 0;           // C += (fp32 outputs only)
+  void* C = nullptr;
+  long long ldc = 0;
+  int c_fp32 = 0;
+  void* C2 = nullptr;           // columns >= n_split go to C2[:, col - n_split]
+  long long ldc2 = 0;
+  int c2_fp32 = 0;
+  int n_split = 1 << 30;
+};
+
+// Launches the best tile configuration for the shape.  Returns RMEM_OK or an error code.
+int gemm_launch(const GemmParams& p, cudaStream_t stream);
+
+}  // namespace rmem

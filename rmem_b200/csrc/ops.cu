@@ -1,0 +1,637 @@
+// HBM-bound kernels of the RMem propagation path: packing, pooling, norms, depthwise conv, resize,
+// ID-bank gather, mask head, evict relevance.  Coalesced along the channel (innermost) dimension,
+// 16-byte vector accesses where the layout allows.  See ops.cuh for the contracts.
+#include "ops.cuh"
+
+namespace rmem {
+
+namespace {
+
+__device__ __forceinline__ void load8(const bf16* p, float* v) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_image_kernel(const float* __restrict__ img, bf16* __restrict__ out, int HW) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  float v[8] = {img[i], img[HW + i], img[2 * HW + i], 0.f, 0.f, 0.f, 0.f, 0.f};
+  store8(out + (size_t)i * 8, v);
+}
+
+__global__ void maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int Hin, int Win, int C, int Hout,
+                               int Wout) {
+  const int cv = C / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Hout * Wout * cv) return;
+  int c8 = (int)(i % cv);
+  int ox = (int)((i / cv) % Wout), oy = (int)(i / ((long long)cv * Wout));
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+  for (int ky = 0; ky < 3; ++ky) {
+    int iy = oy * 2 - 1 + ky;
+    if ((unsigned)iy >= (unsigned)Hin) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      int ix = ox * 2 - 1 + kx;
+      if ((unsigned)ix >= (unsigned)Win) continue;
+      float v[8];
+      load8(x + ((size_t)iy * Win + ix) * C + c8 * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+    }
+  }
+  store8(y + ((size_t)oy * Wout + ox) * C + c8 * 8, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, two-pass statistics in registers.
+constexpr int LN_MAXV = 16;  // C <= 512
+__global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, bf16* __restrict__ y, long long ldy,
+                                 bf16* __restrict__ y2, long long ldy2, int P, int C) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= P) return;
+  const float* xr = x + (long long)row * ldx;
+  float v[LN_MAXV];
+  const int nv = C / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) { v[j] = xr[j * 32 + lane]; s += v[j]; }
+  float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) { float d = v[j] - mean; q += d * d; }
+  float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) {
+      int c = j * 32 + lane;
+      bf16 o = __float2bfloat16((v[j] - mean) * rstd * gamma[c] + beta[c]);
+      y[(long long)row * ldy + c] = o;
+      if (y2) y2[(long long)row * ldy2 + c] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm: stats (double atomics) + apply.
+template <typename T>
+__device__ __forceinline__ void gn_load8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void gn_load8<bf16>(const bf16* p, float* v) { load8(p, v); }
+template <>
+__device__ __forceinline__ void gn_load8<float>(const float* p, float* v) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, double* __restrict__ stats) {
+  // thread -> fixed 8-channel vector column; rows strided over the grid.
+  const int cv = C / 8;
+  const int col = threadIdx.x % cv;
+  const int rows_per_block = blockDim.x / cv;
+  const int r0 = threadIdx.x / cv;
+  float s = 0.f, q = 0.f;
+  for (int r = blockIdx.x * rows_per_block + r0; r < P; r += gridDim.x * rows_per_block) {
+    float v[8];
+    gn_load8<T>(x + (size_t)r * C + col * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += v[k]; q += v[k] * v[k]; }
+  }
+  __shared__ float sh[64];  // [G][2], G <= 32
+  if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int g = (col * 8) / (C / G);
+  atomicAdd(&sh[g * 2], s);
+  atomicAdd(&sh[g * 2 + 1], q);
+  __syncthreads();
+  if (threadIdx.x < 2 * G) atomicAdd(&stats[threadIdx.x], (double)sh[threadIdx.x]);
+}
+
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, bf16* __restrict__ y, int P, int C, int G, int relu,
+                                const double* __restrict__ stats) {
+  const int cv = C / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * cv) return;
+  int col = (int)(i % cv);
+  long long r = i / cv;
+  int g = (col * 8) / (C / G);
+  double n = (double)P * (C / G);
+  double mean = stats[g * 2] / n;
+  double var = stats[g * 2 + 1] / n - mean * mean;
+  float fm = (float)mean, rstd = rsqrtf(fmaxf((float)var, 0.f) + 1e-5f);
+  float v[8];
+  gn_load8<T>(x + (size_t)r * C + col * 8, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = col * 8 + k;
+    float o = (v[k] - fm) * rstd * gamma[c] + beta[c];
+    v[k] = relu ? fmaxf(o, 0.f) : o;
+  }
+  store8(y + (size_t)r * C + col * 8, v);
+}
+
+template <typename T>
+int groupnorm_impl(const T* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+                   double* stats, cudaStream_t s) {
+  RMEM_REQUIRE(C % 8 == 0 && G <= 32 && C % G == 0 && (C / G) % 8 == 0 && 256 % (C / 8) == 0,
+               "groupnorm: unsupported C=%d G=%d", C, G);
+  RMEM_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * G, s));
+  int rows_per_block = 256 / (C / 8);
+  int grid = min(cdiv(P, rows_per_block * 4), 148 * 8);
+  gn_stats_kernel<T><<<grid, 256, 0, s>>>(x, P, C, G, stats);
+  RMEM_LAUNCH_CHECK();
+  long long nvec = (long long)P * (C / 8);
+  gn_apply_kernel<T><<<(unsigned)((nvec + 255) / 256), 256, 0, s>>>(x, gamma, beta, y, P, C, G, relu, stats);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void dwconv5_kernel(const bf16* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int h,
+                               int wd, int C) {
+  const int cv = C / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)h * wd * cv) return;
+  int c8 = (int)(i % cv);
+  int px = (int)((i / cv) % wd), py = (int)(i / ((long long)cv * wd));
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int ky = 0; ky < 5; ++ky) {
+    int iy = py + ky - 2;
+    if ((unsigned)iy >= (unsigned)h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      int ix = px + kx - 2;
+      if ((unsigned)ix >= (unsigned)wd) continue;
+      float v[8];
+      load8(x + ((size_t)iy * wd + ix) * C + c8 * 8, v);
+      const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * 5 + kx) * C + c8 * 8);
+      float4 w0 = wp[0], w1 = wp[1];
+      acc[0] += v[0] * w0.x; acc[1] += v[1] * w0.y; acc[2] += v[2] * w0.z; acc[3] += v[3] * w0.w;
+      acc[4] += v[4] * w1.x; acc[5] += v[5] * w1.y; acc[6] += v[6] * w1.z; acc[7] += v[7] * w1.w;
+    }
+  }
+  store8(y + ((size_t)py * wd + px) * C + c8 * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// align_corners=True source coordinate, as ATen's area_pixel_compute_source_index.
+__device__ __forceinline__ void src_index(int dst, int in_size, int out_size, int& i0, int& i1, float& l0, float& l1) {
+  if (in_size == out_size) { i0 = i1 = dst; l0 = 1.f; l1 = 0.f; return; }
+  float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  float real = __fmul_rn(scale, (float)dst);
+  i0 = min((int)real, in_size - 1);
+  float lam = fminf(fmaxf(__fsub_rn(real, (float)i0), 0.f), 1.f);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = lam;
+  l0 = __fsub_rn(1.f, lam);
+}
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, float wy0, float wy1, float wx0,
+                                        float wx1) {
+  float top = __fadd_rn(__fmul_rn(wx0, v00), __fmul_rn(wx1, v01));
+  float bot = __fadd_rn(__fmul_rn(wx0, v10), __fmul_rn(wx1, v11));
+  return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+}
+
+__global__ void upsample_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int hin, int win, int hout,
+                                     int wout, int C) {
+  const int cv = C / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)hout * wout * cv) return;
+  int c8 = (int)(i % cv);
+  int ox = (int)((i / cv) % wout), oy = (int)(i / ((long long)cv * wout));
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  src_index(oy, hin, hout, y0, y1, wy0, wy1);
+  src_index(ox, win, wout, x0, x1, wx0, wx1);
+  float a[8], b[8], c[8], d[8], o[8];
+  load8(x + ((size_t)y0 * win + x0) * C + c8 * 8, a);
+  load8(x + ((size_t)y0 * win + x1) * C + c8 * 8, b);
+  load8(x + ((size_t)y1 * win + x0) * C + c8 * 8, c);
+  load8(x + ((size_t)y1 * win + x1) * C + c8 * 8, d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = bilerp(a[k], b[k], c[k], d[k], wy0, wy1, wx0, wx1);
+  store8(y + ((size_t)oy * wout + ox) * C + c8 * 8, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_out: one warp per pixel, Cin <= 256, Cout <= 16.  Weights bf16 [Cout, Cin].
+__global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ out, int P, int Cin, int Cout) {
+  extern __shared__ float sw[];  // [Cout][Cin]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+  __syncthreads();
+  int lane = threadIdx.x & 31;
+  int warps = blockDim.x >> 5;
+  for (int p = blockIdx.x * warps + (threadIdx.x >> 5); p < P; p += gridDim.x * warps) {
+    float xv[8];
+    const int nv = Cin / 32;  // <= 8
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) xv[j] = __bfloat162float(x[(size_t)p * Cin + j * 32 + lane]);
+    for (int o = 0; o < Cout; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) s += xv[j] * sw[o * Cin + j * 32 + lane];
+      s = warp_sum(s);
+      if (lane == 0) out[(size_t)o * P + p] = s + b[o];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy, int P,
+                                 int C) {
+  __shared__ bf16 tile[64][66];
+  int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x * 2;
+    bf16 a = __float2bfloat16(0.f), b = a;
+    if (p < P && c < C) {
+      a = x[(long long)p * ldx + c];
+      if (c + 1 < C) b = x[(long long)p * ldx + c + 1];
+    }
+    tile[i][threadIdx.x * 2] = a;
+    tile[i][threadIdx.x * 2 + 1] = b;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    int c = c0 + i;
+    if (c >= C) continue;
+    int p = p0 + threadIdx.x * 2;
+    if (p < P) y[(long long)c * ldy + p] = tile[threadIdx.x * 2][i];
+    if (p + 1 < P) y[(long long)c * ldy + p + 1] = tile[threadIdx.x * 2 + 1][i];
+  }
+}
+
+__global__ void copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd, int P,
+                              int C) {
+  const int cv = C / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * cv) return;
+  int c8 = (int)(i % cv);
+  long long r = i / cv;
+  *reinterpret_cast<uint4*>(dst + r * ldd + c8 * 8) = *reinterpret_cast<const uint4*>(src + r * lds + c8 * 8);
+}
+__global__ void fill_kernel(bf16* __restrict__ dst, long long ldd, int P, int C, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * C) return;
+  dst[(i / C) * ldd + (i % C)] = __float2bfloat16(v);
+}
+
+__global__ void separate_label_kernel(const void* __restrict__ label, int is_f32, uint8_t* __restrict__ out, int n,
+                                      int engine, int n_engines) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = is_f32 ? (int)reinterpret_cast<const float*>(label)[i] : (int)reinterpret_cast<const uint8_t*>(label)[i];
+  if (n_engines > 1) {
+    int lo = engine * 10 + 1, hi = (engine + 1) * 10;
+    v = (v >= lo && v <= hi) ? (v - lo + 1) : 0;
+  }
+  out[i] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ID bank: one block per token, one thread per output channel.
+__global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, int use_ignore,
+                              const float* __restrict__ wp, const float* __restrict__ bias,
+                              const float* __restrict__ ln_g, const float* __restrict__ ln_b, bf16* __restrict__ out,
+                              long long ldo, float* __restrict__ out_f32, int w, int C) {
+  __shared__ int8_t ch[17 * 17];
+  __shared__ float red[32];
+  const int tok = blockIdx.x;
+  const int py = tok / w, px = tok - py * w;
+  for (int t = threadIdx.x; t < 289; t += blockDim.x) {
+    int ky = t / 17, kx = t - ky * 17;
+    int iy = py * 16 - 8 + ky, ix = px * 16 - 8 + kx;
+    int c = -1;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) {
+      int lab = label[(size_t)iy * W + ix];
+      if (lab <= 10) c = lab;
+      else if (lab == 255 && use_ignore) c = 11;
+    }
+    ch[t] = (int8_t)c;
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float acc = 0.f;
+  if (c < C) {
+    for (int t = 0; t < 289; ++t) {
+      int k = ch[t];
+      if (k >= 0) acc += wp[((size_t)t * 12 + k) * C + c];
+    }
+    acc += bias[c];
+  }
+  float o = acc;
+  if (ln_g) {
+    float mean = block_sum(c < C ? acc : 0.f, red) / (float)C;
+    float d = c < C ? acc - mean : 0.f;
+    float var = block_sum(d * d, red) / (float)C;
+    o = d * rsqrtf(var + 1e-5f) * (c < C ? ln_g[c] : 0.f) + (c < C ? ln_b[c] : 0.f);
+  }
+  if (c < C) {
+    if (out) out[(long long)tok * ldo + c] = __float2bfloat16(o);
+    if (out_f32) out_f32[(long long)tok * C + c] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct LogitPtrs { const float* p[4]; };
+
+__device__ __forceinline__ void softmax11(const float* x, float* p) {
+  float m = x[0];
+#pragma unroll
+  for (int c = 1; c < 11; ++c) m = fmaxf(m, x[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 11; ++c) { p[c] = expf(__fsub_rn(x[c], m)); s = __fadd_rn(s, p[c]); }
+#pragma unroll
+  for (int c = 0; c < 11; ++c) p[c] = __fdiv_rn(p[c], s);
+}
+
+__global__ void mask_head_kernel(LogitPtrs lp, int k, int h4, int w4, int Ho, int Wo, float* __restrict__ out_logits,
+                                 uint8_t* __restrict__ out_label) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ho * Wo) return;
+  int oy = i / Wo, ox = i - oy * Wo;
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  src_index(oy, h4, Ho, y0, y1, wy0, wy1);
+  src_index(ox, w4, Wo, x0, x1, wx0, wx1);
+  const size_t plane = (size_t)h4 * w4, oplane = (size_t)Ho * Wo;
+  const size_t i00 = (size_t)y0 * w4 + x0, i01 = (size_t)y0 * w4 + x1, i10 = (size_t)y1 * w4 + x0,
+               i11 = (size_t)y1 * w4 + x1;
+  if (k == 1) {
+    float lg[11], p[11];
+    const float* L = lp.p[0];
+#pragma unroll
+    for (int c = 0; c < 11; ++c) {
+      const float* pl = L + c * plane;
+      lg[c] = bilerp(pl[i00], pl[i01], pl[i10], pl[i11], wy0, wy1, wx0, wx1);
+      if (out_logits) out_logits[c * oplane + i] = lg[c];
+    }
+    softmax11(lg, p);
+    int best = 0;
+#pragma unroll
+    for (int c = 1; c < 11; ++c)
+      if (p[c] > p[best]) best = c;
+    if (out_label) out_label[i] = (uint8_t)best;
+    return;
+  }
+  // soft aggregation over k engines (aot_engine.py:650-673)
+  float merged[41];
+  float bg = 1.f;
+  for (int e = 0; e < k; ++e) {
+    float lg[11], p[11];
+    const float* L = lp.p[e];
+#pragma unroll
+    for (int c = 0; c < 11; ++c) {
+      const float* pl = L + c * plane;
+      lg[c] = bilerp(pl[i00], pl[i01], pl[i10], pl[i11], wy0, wy1, wx0, wx1);
+    }
+    softmax11(lg, p);
+    bg = (e == 0) ? p[0] : __fmul_rn(bg, p[0]);
+    for (int c = 1; c < 11; ++c) merged[1 + e * 10 + (c - 1)] = p[c];
+  }
+  merged[0] = bg;
+  const int nc = 1 + 10 * k;
+  float mx = -INFINITY;
+  for (int c = 0; c < nc; ++c) {
+    float m = fminf(fmaxf(merged[c], 1e-5f), 1.f - 1e-5f);
+    float lg = logf(__fdiv_rn(m, __fsub_rn(1.f, m)));
+    merged[c] = lg;
+    if (out_logits) out_logits[c * oplane + i] = lg;
+    mx = fmaxf(mx, lg);
+  }
+  float s = 0.f;
+  for (int c = 0; c < nc; ++c) { merged[c] = expf(__fsub_rn(merged[c], mx)); s = __fadd_rn(s, merged[c]); }
+  int best = 0;
+  float bp = __fdiv_rn(merged[0], s);
+  for (int c = 1; c < nc; ++c) {
+    float p = __fdiv_rn(merged[c], s);
+    if (p > bp) { bp = p; best = c; }
+  }
+  if (out_label) out_label[i] = (uint8_t)best;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void evict_rel_kernel(const float* __restrict__ mass, int T, const float* __restrict__ logits4, int h4,
+                                 int w4, int h, int w, float* __restrict__ rel) {
+  __shared__ float red[32];
+  float acc[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t] = 0.f;
+  const size_t plane = (size_t)h4 * w4;
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+    int oy = i / w, ox = i - oy * w;
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    src_index(oy, h4, h, y0, y1, wy0, wy1);
+    src_index(ox, w4, w, x0, x1, wx0, wx1);
+    float lg[11], p[11];
+#pragma unroll
+    for (int c = 0; c < 11; ++c) {
+      const float* pl = logits4 + c * plane;
+      lg[c] = bilerp(pl[(size_t)y0 * w4 + x0], pl[(size_t)y0 * w4 + x1], pl[(size_t)y1 * w4 + x0],
+                     pl[(size_t)y1 * w4 + x1], wy0, wy1, wx0, wx1);
+    }
+    softmax11(lg, p);
+    float fg = 1.f - p[0];
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (t < T) acc[t] += mass[(size_t)i * T + t] * fg;
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < T) {
+      float v = block_sum(acc[t], red);
+      if (threadIdx.x == 0) rel[t] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PeSlots { int s[16]; };
+__global__ void qprep_kernel(const bf16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
+                             const float* __restrict__ pe_mem, PeSlots ps, int T, float scale, bf16* __restrict__ qt,
+                             float* __restrict__ qbias, int P, int C) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= P) return;
+  float v[8];
+  const int nv = C / 32;  // <= 8
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      int c = j * 32 + lane;
+      float x = __bfloat162float(q[(long long)row * ldq + c]) + (pe_cur ? pe_cur[c] : 0.f);
+      bf16 r = __float2bfloat16(x);
+      qt[(long long)row * C + c] = r;
+      v[j] = __bfloat162float(r);
+    }
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) s += v[j] * pe_mem[ps.s[t] * C + j * 32 + lane];
+    s = warp_sum(s);
+    if (lane == 0) qbias[(long long)row * T + t] = s * scale;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+int pack_image(const float* img, bf16* out, int H, int W, cudaStream_t s) {
+  pack_image_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(img, out, H * W);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int maxpool3x3s2(const bf16* x, bf16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s) {
+  RMEM_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
+  long long n = (long long)Hout * Wout * (C / 8);
+  maxpool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, Hin, Win, C, Hout, Wout);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, bf16* y, long long ldy, bf16* y2,
+              long long ldy2, int P, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm: unsupported C=%d", C);
+  layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(x, ldx, gamma, beta, y, ldy, y2, ldy2, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int groupnorm_bf16(const bf16* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+                   double* stats, cudaStream_t s) {
+  return groupnorm_impl<bf16>(x, gamma, beta, y, P, C, G, relu, stats, s);
+}
+int groupnorm_f32(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+                  double* stats, cudaStream_t s) {
+  return groupnorm_impl<float>(x, gamma, beta, y, P, C, G, relu, stats, s);
+}
+
+int dwconv5x5(const bf16* x, const float* w, bf16* y, int h, int wd, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 8 == 0, "dwconv: C %% 8");
+  long long n = (long long)h * wd * (C / 8);
+  dwconv5_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, w, y, h, wd, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int upsample_bilinear_bf16(const bf16* x, bf16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 8 == 0, "upsample: C %% 8");
+  long long n = (long long)hout * wout * (C / 8);
+  upsample_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, hin, win, hout, wout, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int conv_out_logits(const bf16* x, const bf16* w, const float* b, float* out, int P, int Cin, int Cout,
+                    cudaStream_t s) {
+  RMEM_REQUIRE(Cin % 32 == 0 && Cin <= 256 && Cout <= 16, "conv_out: unsupported Cin=%d Cout=%d", Cin, Cout);
+  int grid = min(cdiv(P, 8), 148 * 8);
+  conv_out_kernel<<<grid, 256, Cout * Cin * sizeof(float), s>>>(x, w, b, out, P, Cin, Cout);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int transpose_bf16(const bf16* x, long long ldx, bf16* y, long long ldy, int P, int C, cudaStream_t s) {
+  dim3 grid(cdiv(P, 64), cdiv(C, 64)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(x, ldx, y, ldy, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int copy2d_bf16(const bf16* src, long long lds, bf16* dst, long long ldd, int P, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "copy2d: alignment");
+  long long n = (long long)P * (C / 8);
+  copy2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, lds, dst, ldd, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+int fill_bf16(bf16* dst, long long ldd, int P, int C, float v, cudaStream_t s) {
+  long long n = (long long)P * C;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ldd, P, C, v);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int W, int engine, int n_engines,
+                   cudaStream_t s) {
+  separate_label_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(label, label_is_f32, out, H * W, engine, n_engines);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
+                 const float* ln_g, const float* ln_b, bf16* out, long long ldo, float* out_f32, int h, int w, int C,
+                 cudaStream_t s) {
+  RMEM_REQUIRE(C <= 256 && C % 32 == 0, "idbank: unsupported C=%d", C);
+  idbank_kernel<<<h * w, 256, 0, s>>>(label, H, W, use_ignore, w_packed, bias, ln_g, ln_b, out, ldo, out_f32, w, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits,
+              uint8_t* out_label, cudaStream_t s) {
+  RMEM_REQUIRE(k >= 1 && k <= 4, "mask_head: 1..4 engines supported, got %d", k);
+  LogitPtrs lp;
+  for (int e = 0; e < 4; ++e) lp.p[e] = e < k ? logits4[e] : nullptr;
+  mask_head_kernel<<<cdiv(Ho * Wo, 128), 128, 0, s>>>(lp, k, h4, w4, Ho, Wo, out_logits, out_label);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel,
+                    cudaStream_t s) {
+  RMEM_REQUIRE(T >= 1 && T <= 16, "evict_relevance: T=%d out of range", T);
+  evict_rel_kernel<<<1, 1024, 0, s>>>(mass, T, logits4, h4, w4, h, w, rel);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+void temporal_pe_slots(int T, int n_slots, int* out) {
+  if (T <= n_slots) {
+    for (int t = 0; t < T; ++t) out[t] = t;
+    return;
+  }
+  const float scale = (float)n_slots / (float)T;  // ATen nearest: src = min(floor(dst * scale), in - 1)
+  for (int t = 0; t < T; ++t) {
+    int i = T - 1 - t;
+    int src = (int)floorf((float)i * scale);
+    if (src > n_slots - 1) src = n_slots - 1;
+    out[t] = n_slots - 1 - src;
+  }
+}
+
+int qprep(const bf16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+          float scale, bf16* qt, float* qbias, int P, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 32 == 0 && C <= 256, "qprep: unsupported C=%d", C);
+  RMEM_REQUIRE(T >= 0 && T <= 16, "qprep: T=%d", T);
+  PeSlots ps;
+  for (int t = 0; t < 16; ++t) ps.s[t] = (t < T && pe_slot) ? pe_slot[t] : 0;
+  qprep_kernel<<<cdiv(P, 8), 256, 0, s>>>(q, ldq, pe_cur, pe_mem, ps, T, scale, qt, qbias, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+}  // namespace rmem

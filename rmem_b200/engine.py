@@ -1,0 +1,228 @@
+"""Python surface of the B200-native RMem engine -- a drop-in for the reference's
+
+    build_engine(...)                                        networks/engines/__init__.py:5-21
+    AOTInferEngine / DeAOTInferEngine                        networks/engines/aot_engine.py:571-725,
+      .restart_engine / .add_reference_frame /                 deaot_engine.py:20-56
+      .match_propogate_one_frame / .update_memory
+    AOTEngine.{long_memories_indexes, pred_id_logits}        networks/engines/aot_engine.py:533-569
+
+(same names, argument meaning and state attributes; paths relative to /root/reference/aot_plus/).  All the
+arithmetic runs in hand-written sm_100a CUDA behind the C ABI of include/rmem_b200.h; torch only owns device
+memory and the stream.  There is no CPU fallback: without the extension and a GPU these classes raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _capi
+from .weights import WeightBlob, pack_deaot
+
+MAX_OBJ = 10   # configs/models/default.py MODEL_MAX_OBJ_NUM
+
+
+@dataclass
+class RmemConfig:
+    """The frozen subset of configs/models/r50_deaotl.py + configs/pre_vost.py this path depends on."""
+    model: str = "r50_deaotl"
+    former_mem_len: int = 1          # FORMER_MEM_LEN
+    latter_mem_len: int = 7          # LATTER_MEM_LEN
+    max_obj_num: int = MAX_OBJ
+    attn_impl: int = _capi.ATTN_DENSE
+    max_engines: int = 4
+
+
+class DeAOTModel:
+    """Weights of R50_DeAOTL resident in HBM (stands in for `build_vos_model(...)` + `load_state_dict`)."""
+
+    def __init__(self, state_dict, cfg: Optional[RmemConfig] = None, device: Union[str, torch.device] = "cuda:0"):
+        self.cfg = cfg or RmemConfig()
+        if self.cfg.model != "r50_deaotl":
+            raise NotImplementedError(f"model {self.cfg.model!r}: only r50_deaotl is built so far")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _capi.RmemError("rmem_b200 runs on CUDA devices only (no CPU path)")
+        _capi.load()
+        self.weights = WeightBlob(pack_deaot(state_dict), self.device)
+
+    def eval(self):
+        return self
+
+
+def build_vos_model(name: str, cfg: RmemConfig, state_dict=None, device="cuda:0") -> DeAOTModel:
+    if name not in ("deaot", "r50_deaotl"):
+        raise NotImplementedError(name)
+    return DeAOTModel(state_dict, cfg, device)
+
+
+class _SubEngineView:
+    """Read-only view of one object group's state: mirrors the AOTEngine attributes callers/tests read."""
+
+    def __init__(self, owner: "DeAOTInferEngine", index: int):
+        self._o, self._i = owner, index
+
+    @property
+    def long_memories_indexes(self) -> List[int]:
+        lib = _capi.load()
+        idx = (C.c_int * (_capi.MAX_BANK_FRAMES + 1))()
+        n = C.c_int(0)
+        _capi.check(lib.rmem_engine_long_indexes(self._o._h, self._i, idx, C.byref(n)))
+        return [idx[i] for i in range(n.value)]
+
+    @property
+    def pred_id_logits(self) -> torch.Tensor:
+        """[1,11,H/4,W/4] fp32 logits of the last decode (a copy; the engine reuses its buffer)."""
+        lib = _capi.load()
+        p = C.c_void_p()
+        h4, w4 = C.c_int(), C.c_int()
+        _capi.check(lib.rmem_engine_pred_logits(self._o._h, self._i, C.byref(p), C.byref(h4), C.byref(w4)))
+        n = 11 * h4.value * w4.value
+        off = p.value - self._o._arena.data_ptr()
+        return self._o._arena[off:off + 4 * n].view(torch.float32).view(1, 11, h4.value, w4.value).clone()
+
+    @property
+    def last_evict(self) -> Tuple[List[float], int]:
+        lib = _capi.load()
+        rel = (C.c_float * _capi.MAX_BANK_FRAMES)()
+        n, drop = C.c_int(), C.c_int()
+        _capi.check(lib.rmem_engine_last_evict(self._o._h, self._i, rel, C.byref(n), C.byref(drop)))
+        return [rel[i] for i in range(n.value)], drop.value
+
+
+class DeAOTInferEngine:
+    def __init__(self, aot_model: DeAOTModel, gpu_id: int = 0, long_term_mem_gap: int = 9999,
+                 max_aot_obj_num: Optional[int] = None):
+        self.AOT = aot_model
+        self.cfg = aot_model.cfg
+        self.gpu_id = gpu_id
+        self.device = aot_model.device
+        self.long_term_mem_gap = long_term_mem_gap
+        self.max_aot_obj_num = max_aot_obj_num or self.cfg.max_obj_num
+        self._h = None
+        self._arena = None
+        self._size = None
+        self.restart_engine()
+
+    # ---- lifetime -----------------------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def __del__(self):
+        self._destroy()
+
+    def _destroy(self):
+        if getattr(self, "_h", None):
+            _capi.load().rmem_engine_destroy(self._h)
+            self._h = None
+
+    def _ensure(self, H: int, W: int):
+        if self._h is not None and self._size == (H, W):
+            return
+        self._destroy()
+        lib = _capi.load()
+        cc = _capi.EngineConfig(0, H, W, self.cfg.former_mem_len, self.cfg.latter_mem_len, self.cfg.max_engines,
+                                self.cfg.attn_impl, max(int(self.long_term_mem_gap), 1))
+        nbytes = C.c_size_t()
+        _capi.check(lib.rmem_engine_arena_bytes(C.byref(cc), C.byref(nbytes)))
+        self._arena = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        h = C.c_void_p()
+        w = self.AOT.weights
+        _capi.check(lib.rmem_engine_create(C.byref(cc), _capi.ptr(w.blob), w.entries, w.n_entries,
+                                           _capi.ptr(self._arena), C.c_size_t(nbytes.value), C.byref(h)))
+        self._h = h
+        self._size = (H, W)
+
+    # ---- reference API ------------------------------------------------------------------------
+    def restart_engine(self):
+        """aot_engine.py:598-602."""
+        if self._h is not None:
+            _capi.check(_capi.load().rmem_engine_restart(self._h))
+        self.aot_engines: List[_SubEngineView] = []
+        self.input_size_2d = None
+        self.enc_size_2d = None
+        self.enc_hw = None
+
+    def _dev(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    def _label_arg(self, mask: torch.Tensor):
+        """Reference callers pass int (reference frame) or float-valued (update_memory) label maps [1,1,H,W]."""
+        if mask.dtype == torch.uint8:
+            return self._dev(mask), 0
+        return self._dev(mask, torch.float32), 1
+
+    def add_reference_frame(self, img: torch.Tensor, mask: torch.Tensor, obj_nums, frame_step: int = -1):
+        """aot_engine.py:675-702 / deaot_engine.py:30-56."""
+        if isinstance(obj_nums, (list, tuple)):
+            obj_nums = obj_nums[0]
+        assert img.shape[0] == 1, "the inference engine runs batch 1 (transformer.py:1190 asserts the same)"
+        H, W = int(img.shape[-2]), int(img.shape[-1])
+        self._ensure(H, W)
+        lib = _capi.load()
+        _capi.check(lib.rmem_engine_set_gap(self._h, max(int(self.long_term_mem_gap), 1)))
+        img = self._dev(img, torch.float32)
+        lab, is_f32 = self._label_arg(mask)
+        assert lab.numel() == H * W, "label map must match the frame size"
+        _capi.check(lib.rmem_engine_add_reference_frame(self._h, _capi.ptr(img), _capi.ptr(lab), is_f32,
+                                                        int(obj_nums), int(frame_step), _capi.stream_ptr()))
+        n = lib.rmem_engine_num_groups(self._h)
+        self.aot_engines = [_SubEngineView(self, i) for i in range(n)]
+        self.input_size_2d = (H, W)
+        self.enc_size_2d = ((H - 1) // 16 + 1, (W - 1) // 16 + 1)
+        self.enc_hw = self.enc_size_2d[0] * self.enc_size_2d[1]
+
+    def match_propogate_one_frame(self, img: torch.Tensor = None, mask=None, output_size=None,
+                                  return_label: bool = False):
+        """aot_engine.py:704-712.  Returns logits [1, 1+10k, Ho, Wo] fp32 (and the uint8 argmax label map
+        [1,1,Ho,Wo] of evaluator.py:430-441 when return_label)."""
+        lib = _capi.load()
+        _capi.check(lib.rmem_engine_set_gap(self._h, max(int(self.long_term_mem_gap), 1)))
+        img = self._dev(img, torch.float32)
+        Ho, Wo = output_size if output_size is not None else self.input_size_2d
+        k = len(self.aot_engines)
+        logits = torch.empty(1, 1 + MAX_OBJ * k, Ho, Wo, dtype=torch.float32, device=self.device)
+        label = torch.empty(1, 1, Ho, Wo, dtype=torch.uint8, device=self.device) if return_label else None
+        _capi.check(lib.rmem_engine_propagate(self._h, _capi.ptr(img), int(Ho), int(Wo), _capi.ptr(logits),
+                                              _capi.ptr(label), _capi.stream_ptr()))
+        return (logits, label) if return_label else logits
+
+    def propagate_label(self, img: torch.Tensor, output_size=None) -> torch.Tensor:
+        """Fast path: mask IDs only (no full-resolution logits written).  uint8 [1,1,Ho,Wo]."""
+        lib = _capi.load()
+        _capi.check(lib.rmem_engine_set_gap(self._h, max(int(self.long_term_mem_gap), 1)))
+        img = self._dev(img, torch.float32)
+        Ho, Wo = output_size if output_size is not None else self.input_size_2d
+        label = torch.empty(1, 1, Ho, Wo, dtype=torch.uint8, device=self.device)
+        _capi.check(lib.rmem_engine_propagate(self._h, _capi.ptr(img), int(Ho), int(Wo), None, _capi.ptr(label),
+                                              _capi.stream_ptr()))
+        return label
+
+    def update_memory(self, label: torch.Tensor):
+        """aot_engine.py:714-720 -> AOTEngine.update_short_term_memory (:327-396)."""
+        lib = _capi.load()
+        lab, is_f32 = self._label_arg(label)
+        H, W = self.input_size_2d
+        assert lab.numel() == H * W, "update_memory expects the label at the input size (evaluator.py:518-523)"
+        _capi.check(lib.rmem_engine_update_memory(self._h, _capi.ptr(lab), is_f32, _capi.stream_ptr()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_capi.load().rmem_engine_launch_count(self._h)) if self._h else 0
+
+
+def build_engine(name: str, phase: str = "eval", aot_model: DeAOTModel = None, gpu_id: int = 0,
+                 long_term_mem_gap: int = 9999, **kwargs):
+    """networks/engines/__init__.py:5-21."""
+    if phase != "eval":
+        raise NotImplementedError("rmem_b200 builds the inference path only (training is out of scope)")
+    if name in ("deaotengine", "deaot_engine"):
+        return DeAOTInferEngine(aot_model, gpu_id=gpu_id, long_term_mem_gap=long_term_mem_gap, **kwargs)
+    raise NotImplementedError(f"engine {name!r}")

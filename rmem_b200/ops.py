@@ -1,0 +1,275 @@
+"""Op-level Python mirrors of the reference's module forwards on this path, each a thin
+call into the C ABI.  Tensors are CUDA torch tensors; activations token-major [pixels, channels].
+
+    GatedPropagation.forward core      networks/layers/attention.py:139-211   -> long_attention / self use
+    LocalGatedPropagation.forward core networks/layers/attention.py:289-361   -> local_attention
+    nn.Linear / nn.Conv2d call sites                                          -> gemm / conv2d_nhwc
+    LayerNorm / GroupNorm / DWConv2d   networks/layers/basic.py               -> layernorm / groupnorm / dwconv5x5
+    patch_wise_id_bank (+id_norm)      networks/models/aot.py:63-74,111-114   -> id_embedding
+    logits -> mask IDs                 networks/engines/aot_engine.py:457-463,650-673 -> mask_head
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+
+ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+
+
+def _bf(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).contiguous()
+
+
+def round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         act_from: int = 0, residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+         out_f32: bool = False, alpha: float = 1.0, bias_along_m: bool = False,
+         accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = epilogue(alpha * A[M,K] @ B[N,K]^T).  A, B bf16."""
+    lib = _capi.load()
+    M, K = A.shape
+    N = B.shape[0]
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and B.shape[1] == K
+    if accumulate_into is not None:
+        out = accumulate_into
+        assert out.dtype == torch.float32
+    else:
+        out = torch.empty(M, N, dtype=torch.float32 if out_f32 else torch.bfloat16, device=A.device)
+    d = _capi.GemmDesc()
+    d.A, d.lda, d.B, d.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+    d.M, d.N, d.K = M, N, K
+    d.alpha = alpha
+    d.bias = 0 if bias is None else bias.data_ptr()
+    d.bias_along_m = int(bias_along_m)
+    d.act, d.act_from_col = act, act_from
+    if residual is not None:
+        d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
+    if gate is not None:
+        d.gate, d.ldg = gate.data_ptr(), gate.stride(0)
+    d.accumulate = int(accumulate_into is not None)
+    d.C, d.ldc, d.c_is_f32 = out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
+    d.n_split = 1 << 30
+    _capi.check(lib.rmem_gemm_fwd(C.byref(d), _capi.stream_ptr()))
+    return out
+
+
+def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, act: int = ACT_NONE,
+                residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [Hin,Win,Cin]; w bf16 [Cout,kh,kw,Cin] -> bf16 [Hout,Wout,Cout]."""
+    lib = _capi.load()
+    Hin, Win, Cin = x.shape
+    Cout, kh, kw, _ = w.shape
+    Hout, Wout = (Hin + 2 * pad - kh) // stride + 1, (Win + 2 * pad - kw) // stride + 1
+    out = torch.empty(Hout, Wout, Cout, dtype=torch.bfloat16, device=x.device)
+    d = _capi.GemmDesc()
+    d.A, d.B, d.ldb = x.data_ptr(), w.data_ptr(), kh * kw * Cin
+    d.M, d.N, d.K = Hout * Wout, Cout, kh * kw * Cin
+    d.conv, d.Hin, d.Win, d.Cin, d.Wout, d.kw, d.stride, d.pad = 1, Hin, Win, Cin, Wout, kw, stride, pad
+    d.alpha = 1.0
+    d.bias = bias.data_ptr()
+    d.act = act
+    if residual is not None:
+        d.residual, d.ldr = residual.data_ptr(), Cout
+    d.C, d.ldc, d.c_is_f32 = out.data_ptr(), Cout, 0
+    d.n_split = 1 << 30
+    _capi.check(lib.rmem_gemm_fwd(C.byref(d), _capi.stream_ptr()))
+    return out
+
+
+def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    lib = _capi.load()
+    P, Cc = x.shape
+    y = torch.empty(P, Cc, dtype=torch.bfloat16, device=x.device)
+    _capi.check(lib.rmem_layernorm_fwd(_capi.ptr(x), C.c_longlong(x.stride(0)), _capi.ptr(g), _capi.ptr(b),
+                                       _capi.ptr(y), C.c_longlong(Cc), P, Cc, _capi.stream_ptr()))
+    return y
+
+
+def groupnorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, groups: int, relu: bool) -> torch.Tensor:
+    lib = _capi.load()
+    P, Cc = x.shape
+    y = torch.empty(P, Cc, dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty(64, dtype=torch.float64, device=x.device)
+    _capi.check(lib.rmem_groupnorm_fwd(_capi.ptr(x), int(x.dtype == torch.float32), _capi.ptr(g), _capi.ptr(b),
+                                       _capi.ptr(y), P, Cc, groups, int(relu), _capi.ptr(stats), _capi.stream_ptr()))
+    return y
+
+
+def dwconv5x5(x: torch.Tensor, w25: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    lib = _capi.load()
+    y = torch.empty_like(x)
+    _capi.check(lib.rmem_dwconv5x5_fwd(_capi.ptr(x), _capi.ptr(w25), _capi.ptr(y), h, w, x.shape[1],
+                                       _capi.stream_ptr()))
+    return y
+
+
+def upsample_bilinear(x: torch.Tensor, hout: int, wout: int) -> torch.Tensor:
+    lib = _capi.load()
+    hin, win, Cc = x.shape
+    y = torch.empty(hout, wout, Cc, dtype=torch.bfloat16, device=x.device)
+    _capi.check(lib.rmem_upsample_bilinear_fwd(_capi.ptr(x), _capi.ptr(y), hin, win, hout, wout, Cc,
+                                               _capi.stream_ptr()))
+    return y
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    lib = _capi.load()
+    Hin, Win, Cc = x.shape
+    Hout, Wout = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
+    y = torch.empty(Hout, Wout, Cc, dtype=torch.bfloat16, device=x.device)
+    _capi.check(lib.rmem_maxpool3x3s2_fwd(_capi.ptr(x), _capi.ptr(y), Hin, Win, Cc, Hout, Wout, _capi.stream_ptr()))
+    return y
+
+
+def transpose(x: torch.Tensor, ldy: int) -> torch.Tensor:
+    lib = _capi.load()
+    P, Cc = x.shape
+    y = torch.zeros(Cc, ldy, dtype=torch.bfloat16, device=x.device)
+    _capi.check(lib.rmem_transpose_fwd(_capi.ptr(x), C.c_longlong(x.stride(0)), _capi.ptr(y), C.c_longlong(ldy), P, Cc,
+                                       _capi.stream_ptr()))
+    return y
+
+
+def id_embedding(label_u8: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, ln_g, ln_b,
+                 use_ignore: bool) -> torch.Tensor:
+    """label uint8 [H,W] -> fp32 [hw, C]."""
+    lib = _capi.load()
+    H, W = label_u8.shape
+    h, w = (H - 1) // 16 + 1, (W - 1) // 16 + 1
+    Cc = bias.numel()
+    out = torch.empty(h * w, Cc, dtype=torch.float32, device=label_u8.device)
+    _capi.check(lib.rmem_idbank_fwd(_capi.ptr(label_u8), H, W, int(use_ignore), _capi.ptr(w_packed), _capi.ptr(bias),
+                                    _capi.ptr(ln_g), _capi.ptr(ln_b), None, C.c_longlong(0), _capi.ptr(out), h, w, Cc,
+                                    _capi.stream_ptr()))
+    return out
+
+
+def mask_head(logits4: Sequence[torch.Tensor], Ho: int, Wo: int, want_logits: bool = True):
+    """k x fp32 [11,h4,w4] -> (logits fp32 [1+10k,Ho,Wo] | None, label uint8 [Ho,Wo])."""
+    lib = _capi.load()
+    k = len(logits4)
+    _, h4, w4 = logits4[0].shape
+    ptrs = (C.c_void_p * k)(*[t.data_ptr() for t in logits4])
+    dev = logits4[0].device
+    out = torch.empty(1 + 10 * k, Ho, Wo, dtype=torch.float32, device=dev) if want_logits else None
+    lab = torch.empty(Ho, Wo, dtype=torch.uint8, device=dev)
+    _capi.check(lib.rmem_mask_head_fwd(ptrs, k, h4, w4, Ho, Wo, _capi.ptr(out), _capi.ptr(lab), _capi.stream_ptr()))
+    return out, lab
+
+
+def evict_relevance(mass: torch.Tensor, logits4: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    lib = _capi.load()
+    T = mass.shape[1]
+    _, h4, w4 = logits4.shape
+    rel = torch.empty(T, dtype=torch.float32, device=mass.device)
+    _capi.check(lib.rmem_evict_relevance_fwd(_capi.ptr(mass), T, _capi.ptr(logits4), h4, w4, h, w, _capi.ptr(rel),
+                                             _capi.stream_ptr()))
+    return rel
+
+
+def evict_pick(rel: Sequence[float], idx: Sequence[int], former: int, ema: dict, times: dict) -> int:
+    """Host EMA/UCB/argmin (transformer.py:907-964).  Updates `ema` / `times` in place, returns drop index."""
+    lib = _capi.load()
+    T_old = len(rel)
+    cap = _capi.MAX_BANK_FRAMES + 1
+    relc = (C.c_float * T_old)(*rel)
+    idxc = (C.c_int * len(idx))(*idx)
+    ek, ev = (C.c_int * cap)(*ema.keys()), (C.c_float * cap)(*ema.values())
+    tk, tv = (C.c_int * cap)(*times.keys()), (C.c_int * cap)(*times.values())
+    ne, nt, drop = C.c_int(len(ema)), C.c_int(len(times)), C.c_int(-1)
+    _capi.check(lib.rmem_evict_pick(relc, T_old, idxc, former, ek, ev, C.byref(ne), tk, tv, C.byref(nt),
+                                    C.byref(drop)))
+    ema.clear(); times.clear()
+    for i in range(ne.value):
+        ema[ek[i]] = ev[i]
+    for i in range(nt.value):
+        times[tk[i]] = tv[i]
+    return drop.value
+
+
+def temporal_pe_slots(T: int, n_slots: int = 4) -> List[int]:
+    lib = _capi.load()
+    out = (C.c_int * T)()
+    _capi.check(lib.rmem_temporal_pe_slots(T, n_slots, out))
+    return list(out)
+
+
+def build_bank(k_frames: torch.Tensor, v_frames: torch.Tensor, nslots: int, slots: Sequence[int]):
+    """Lay T frames out the way the engine's ring bank does.  k [T,HW,Dk], v [T,HW,Dv] (any float dtype) ->
+    (kbank bf16 [nslots,HWp,Dk], vtbank bf16 [Dv, nslots*HWp], HWp)."""
+    T, HW, Dk = k_frames.shape
+    Dv = v_frames.shape[-1]
+    HWp = round_up(HW, 128)
+    dev = k_frames.device
+    kbank = torch.zeros(nslots, HWp, Dk, dtype=torch.bfloat16, device=dev)
+    vtbank = torch.zeros(Dv, nslots * HWp, dtype=torch.bfloat16, device=dev)
+    lib = _capi.load()
+    for t, s in enumerate(slots):
+        kbank[s, :HW] = k_frames[t].to(torch.bfloat16)
+        vt = _bf(v_frames[t])
+        _capi.check(lib.rmem_transpose_fwd(_capi.ptr(vt), C.c_longlong(Dv), C.c_void_p(vtbank.data_ptr() + 2 * s * HWp),
+                                           C.c_longlong(nslots * HWp), HW, Dv, _capi.stream_ptr()))
+    return kbank, vtbank, HWp
+
+
+def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, slots: Sequence[int], HW: int,
+                   pe_cur: Optional[torch.Tensor] = None, mem_pos_emb: Optional[torch.Tensor] = None,
+                   gate: Optional[torch.Tensor] = None, impl: int = _capi.ATTN_DENSE,
+                   want_mass: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """q bf16 [HW,Dk] (no PE, unscaled).  Returns (out bf16 [HW,Dv], mass fp32 [HW,T])."""
+    lib = _capi.load()
+    nslots, HWp, Dk = kbank.shape
+    Dv = vtbank.shape[0]
+    T = len(slots)
+    dev = q.device
+    scale = 1.0 / math.sqrt(Dk)
+    qt = torch.empty(HW, Dk, dtype=torch.bfloat16, device=dev)
+    qbias = torch.zeros(HW, max(T, 1), dtype=torch.float32, device=dev)
+    if mem_pos_emb is not None:
+        pes = (C.c_int * T)(*temporal_pe_slots(T, mem_pos_emb.shape[0]))
+        _capi.check(lib.rmem_qprep_fwd(_capi.ptr(q), C.c_longlong(q.stride(0)), _capi.ptr(pe_cur),
+                                       _capi.ptr(mem_pos_emb), pes, T, C.c_float(scale), _capi.ptr(qt),
+                                       _capi.ptr(qbias), HW, Dk, _capi.stream_ptr()))
+    else:
+        qt.copy_(q)
+    nbytes = C.c_size_t()
+    _capi.check(lib.rmem_long_attn_workspace_bytes(impl, HW, HWp, nslots, Dv, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    out = torch.empty(HW, Dv, dtype=torch.bfloat16, device=dev)
+    mass = torch.empty(HW, T, dtype=torch.float32, device=dev) if want_mass else None
+    sl = (C.c_int * T)(*slots)
+    _capi.check(lib.rmem_long_attn_fwd(impl, _capi.ptr(qt), _capi.ptr(qbias) if mem_pos_emb is not None else None,
+                                       _capi.ptr(kbank), _capi.ptr(vtbank), nslots, T, sl, HW, HWp, Dk, Dv,
+                                       C.c_float(scale), _capi.ptr(gate), C.c_longlong(gate.stride(0) if gate is not None else 0),
+                                       _capi.ptr(out), C.c_longlong(Dv), _capi.ptr(mass), _capi.ptr(ws),
+                                       C.c_size_t(nbytes.value), _capi.stream_ptr()))
+    return out, mass
+
+
+def local_attention(q: torch.Tensor, k_prev: torch.Tensor, v_prev: torch.Tensor, rel_w: torch.Tensor,
+                    rel_b: torch.Tensor, h: int, w: int, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q,k bf16 [HW,128]; v bf16 [HW,Dv]; rel_w fp32/bf16 [225,128]; rel_b [225] -> bf16 [HW,Dv]."""
+    lib = _capi.load()
+    HW, Dk = q.shape
+    Dv = v_prev.shape[1]
+    wpad = torch.zeros(256, Dk, dtype=torch.bfloat16, device=q.device)
+    wpad[:225] = rel_w.to(torch.bfloat16)
+    bpad = torch.zeros(256, dtype=torch.float32, device=q.device)
+    bpad[:225] = rel_b.float()
+    rel = gemm(q, wpad, bpad, out_f32=True)
+    out = torch.empty(HW, Dv, dtype=torch.bfloat16, device=q.device)
+    _capi.check(lib.rmem_local_attn_fwd(_capi.ptr(q), C.c_longlong(q.stride(0)), _capi.ptr(k_prev),
+                                        C.c_longlong(k_prev.stride(0)), _capi.ptr(v_prev),
+                                        C.c_longlong(v_prev.stride(0)), _capi.ptr(rel), C.c_longlong(256),
+                                        _capi.ptr(gate), C.c_longlong(gate.stride(0) if gate is not None else 0),
+                                        _capi.ptr(out), C.c_longlong(Dv), h, w, Dv, C.c_float(1.0 / math.sqrt(Dk)),
+                                        _capi.stream_ptr()))
+    return out

@@ -1,0 +1,140 @@
+"""Pack a reference `state_dict` (DeAOT, key names of networks/models/deaot.py -- SURVEY.md section 8b) into
+the flat device blob the C++ engine reads: FrozenBatchNorm2d folded into the conv weights
+(networks/layers/normalization.py:19-43), conv weights re-ordered to [Cout, ky, kx, Cin] (the K order of the
+implicit GEMM), GEMM operands in bf16, norm / bias / depthwise / positional parameters in fp32, the ID-bank
+conv (networks/models/aot.py:63-74) re-ordered to [17*17, 12, C] for the label-indexed gather.
+`module.` prefixes are stripped like utils/checkpoint.py:75-101 does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _capi
+
+BN_EPS = 1e-5
+
+
+def _resnet_blocks():
+    out = []
+    inplanes = 64
+    for li, (planes, nblk, stride) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2)], start=1):
+        for bi in range(nblk):
+            s = stride if bi == 0 else 1
+            out.append((li, bi, inplanes, planes, s, bi == 0))
+            inplanes = planes * 4
+    return out
+
+
+def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """name -> packed CPU tensor (bf16 or fp32, contiguous)."""
+    sd = {(k[7:] if k.startswith("module.") else k): v.detach().float().cpu() for k, v in sd.items()}
+    out: Dict[str, torch.Tensor] = {}
+
+    def conv_bn(dst, conv, bn, cin_pad=None):
+        w = sd[conv + ".weight"]
+        scale = sd[bn + ".weight"] / torch.sqrt(sd[bn + ".running_var"] + BN_EPS)
+        b = sd[bn + ".bias"] - sd[bn + ".running_mean"] * scale
+        w = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1)             # [Cout, ky, kx, Cin]
+        if cin_pad is not None and cin_pad > w.shape[-1]:
+            w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
+        out[dst + ".w"] = w.contiguous().to(torch.bfloat16)
+        out[dst + ".b"] = b.contiguous()
+
+    def conv(dst, src):
+        w = sd[src + ".weight"].permute(0, 2, 3, 1)
+        out[dst + ".w"] = w.contiguous().to(torch.bfloat16)
+        out[dst + ".b"] = sd[src + ".bias"].contiguous()
+
+    def linear(dst, src, pad_rows=None):
+        w, b = sd[src + ".weight"], sd[src + ".bias"]
+        w = w.reshape(w.shape[0], -1)
+        if pad_rows is not None and pad_rows > w.shape[0]:
+            w = torch.nn.functional.pad(w, (0, 0, 0, pad_rows - w.shape[0]))
+            b = torch.nn.functional.pad(b, (0, pad_rows - b.shape[0]))
+        out[dst + ".w"] = w.contiguous().to(torch.bfloat16)
+        out[dst + ".b"] = b.contiguous()
+
+    def norm(dst, src):
+        out[dst + ".g"] = sd[src + ".weight"].contiguous()
+        out[dst + ".b"] = sd[src + ".bias"].contiguous()
+
+    def dw(dst, src):
+        w = sd[src + ".dw_conv.conv.weight"]                                # [C,1,5,5]
+        out[dst] = w.view(w.shape[0], 25).t().contiguous()                  # [25, C]
+
+    conv_bn("enc.conv1", "encoder.conv1", "encoder.bn1", cin_pad=8)
+    for li, bi, inpl, pl, s, ds in _resnet_blocks():
+        p, q = f"encoder.layer{li}.{bi}", f"enc.layer{li}.{bi}"
+        for i in (1, 2, 3):
+            conv_bn(f"{q}.conv{i}", f"{p}.conv{i}", f"{p}.bn{i}")
+        if ds:
+            conv_bn(f"{q}.ds", f"{p}.downsample.0", f"{p}.downsample.1")
+    linear("proj", "encoder_projector")
+
+    wb = sd["patch_wise_id_bank.weight"]                                    # [C,12,17,17]
+    out["idbank.w"] = wb.permute(2, 3, 1, 0).reshape(17 * 17, wb.shape[1], wb.shape[0]).contiguous()
+    out["idbank.b"] = sd["patch_wise_id_bank.bias"].contiguous()
+    norm("id_norm", "id_norm")
+    out["cur_pos_emb"] = sd["cur_pos_emb"].reshape(-1).contiguous()
+    out["mem_pos_emb"] = sd["mem_pos_emb"].contiguous()
+
+    for l in range(3):
+        p, q = f"LSTT.layers.{l}", f"gpm.{l}"
+        norm(q + ".norm1", p + ".norm1")
+        linear(q + ".linear_QV", p + ".linear_QV")
+        linear(q + ".linear_U", p + ".linear_U")
+        linear(q + ".linear_ID_V", p + ".linear_ID_V")
+        if l > 0:
+            norm(q + ".id_norm1", p + ".id_norm1")
+            linear(q + ".linear_ID_U", p + ".linear_ID_U")
+        for dst, src in (("long", "long_term_attn"), ("short", "short_term_attn"), ("self", "self_attn")):
+            dw(f"{q}.{dst}.dw", f"{p}.{src}")
+            linear(f"{q}.{dst}.proj", f"{p}.{src}.projection")
+        linear(q + ".short.rel", p + ".short_term_attn.relative_emb_k", pad_rows=256)
+        norm(q + ".norm2", p + ".norm2")
+        norm(q + ".id_norm2", p + ".id_norm2")
+        linear(q + ".self.linear_QK", p + ".self_attn.linear_QK")
+        for nm in ("linear_V1", "linear_V2", "linear_U1", "linear_U2"):
+            linear(f"{q}.self.{nm}", f"{p}.self_attn.{nm}")
+    norm("gpm.out_norm", "LSTT.decoder_norms.0.gn")
+
+    for nm in ("conv_in", "conv_16x", "conv_8x", "conv_4x"):
+        conv("dec." + nm, f"decoder.{nm}.conv")
+        out[f"dec.{nm}.gn.g"] = sd[f"decoder.{nm}.gn.weight"].contiguous()
+        out[f"dec.{nm}.gn.b"] = sd[f"decoder.{nm}.gn.bias"].contiguous()
+    for nm in ("adapter_16x", "adapter_8x", "adapter_4x", "conv_out"):
+        conv("dec." + nm, "decoder." + nm)
+    return out
+
+
+class WeightBlob:
+    """Packed weights resident in HBM + the (name, offset, nbytes) table handed to rmem_engine_create."""
+
+    def __init__(self, packed: Dict[str, torch.Tensor], device):
+        offs: List[Tuple[str, int, int]] = []
+        total = 0
+        for name, t in packed.items():
+            nbytes = t.numel() * t.element_size()
+            offs.append((name, total, nbytes))
+            total += (nbytes + 255) // 256 * 256
+        host = torch.zeros(total, dtype=torch.uint8)
+        for (name, off, nbytes), t in zip(offs, packed.values()):
+            host[off:off + nbytes] = t.contiguous().view(torch.uint8).view(-1)
+        self.blob = host.to(device)
+        self.offsets = {n: (o, b) for n, o, b in offs}
+        self._names = [n.encode() for n, _, _ in offs]      # keep the byte strings alive
+        self.entries = (_capi.WeightEntry * len(offs))()
+        for i, (n, o, b) in enumerate(offs):
+            self.entries[i].name = self._names[i]
+            self.entries[i].offset = o
+            self.entries[i].nbytes = b
+        self.n_entries = len(offs)
+        self.nbytes = total
+
+    def view(self, name: str, dtype, shape):
+        """Typed device view of one packed tensor (op-level tests)."""
+        o, b = self.offsets[name]
+        return self.blob[o:o + b].view(dtype).view(*shape)
