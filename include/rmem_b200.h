@@ -23,6 +23,7 @@ extern "C" {
 #endif
 
 #define RMEM_MAX_BANK_FRAMES 16
+#define RMEM_GN_SCRATCH_DOUBLES (72 + 148 * 4 * 64)
 #define RMEM_ATTN_DENSE 0 /* materialised scores: generic GEMMs + row softmax */
 #define RMEM_ATTN_TC 1    /* fused tcgen05 + TMA flash kernel */
 
@@ -76,7 +77,8 @@ int rmem_local_attn_fwd(const void* q, long long ldq, const void* k, long long l
 int rmem_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
                        int P, int C, void* stream);
 int rmem_groupnorm_fwd(const void* x, int x_is_f32, const float* gamma, const float* beta, void* y, int P, int C,
-                       int G, int relu, double* stats /* 2*G doubles scratch */, void* stream);
+                       int G, int relu, double* stats /* RMEM_GN_SCRATCH_DOUBLES doubles, zero-initialised once */,
+                       void* stream);
 int rmem_dwconv5x5_fwd(const void* x, const float* w /* [25,C] */, void* y, int h, int w_, int C, void* stream);
 
 /* F.interpolate(bilinear, align_corners=True) on NHWC bf16 (fpn.py:50,58). */

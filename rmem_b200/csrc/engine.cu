@@ -173,7 +173,7 @@ struct rmem_engine {
     d0 = a.take<bf16>((size_t)G.P4 * 128);
     d1 = a.take<bf16>((size_t)G.P4 * 128);
     d2 = a.take<bf16>((size_t)G.P4 * 128);
-    stats = a.take<double>(64);
+    stats = a.take<double>(kGnScratchDoubles);
     label8 = a.take<uint8_t>((size_t)G.H * G.W);
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
     size_t ws_tc = long_attn_tc_workspace(G.HW, G.HWp, nslots, kDv);

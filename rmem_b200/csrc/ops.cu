@@ -96,8 +96,11 @@ __device__ __forceinline__ void gn_load8<float>(const float* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// Deterministic two-level reduction: fixed-order per-block partials, the last block to finish folds them in
+// block order (no floating-point atomics, so run-to-run results are bit-identical).
 template <typename T>
-__global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, double* __restrict__ stats) {
+__global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, double* __restrict__ stats,
+                                double* __restrict__ partials, unsigned int* __restrict__ counter) {
   // thread -> fixed 8-channel vector column; rows strided over the grid.
   const int cv = C / 8;
   const int col = threadIdx.x % cv;
@@ -110,14 +113,33 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, do
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s += v[k]; q += v[k] * v[k]; }
   }
-  __shared__ float sh[64];  // [G][2], G <= 32
-  if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0.f;
+  __shared__ float sh_s[256], sh_q[256];
+  __shared__ bool is_last;
+  sh_s[threadIdx.x] = s;
+  sh_q[threadIdx.x] = q;
   __syncthreads();
-  const int g = (col * 8) / (C / G);
-  atomicAdd(&sh[g * 2], s);
-  atomicAdd(&sh[g * 2 + 1], q);
+  if (threadIdx.x < 2 * G) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int cpg = cv / G;              // vector columns per group
+    const float* src = which ? sh_q : sh_s;
+    double a = 0.0;
+    for (int r = 0; r < rows_per_block; ++r)
+      for (int c = 0; c < cpg; ++c) a += (double)src[r * cv + g * cpg + c];
+    partials[(size_t)blockIdx.x * 2 * G + threadIdx.x] = a;
+  }
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x < 2 * G) atomicAdd(&stats[threadIdx.x], (double)sh[threadIdx.x]);
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 2 * G) {
+      double a = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) a += partials[(size_t)b * 2 * G + threadIdx.x];
+      stats[threadIdx.x] = a;
+    }
+    if (threadIdx.x == 0) *counter = 0u;   // re-arm for the next call on this stream
+  }
 }
 
 template <typename T>
@@ -145,15 +167,17 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict
   store8(y + (size_t)r * C + col * 8, v);
 }
 
+constexpr int kGnMaxBlocks = 148 * 4;
+
 template <typename T>
 int groupnorm_impl(const T* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
                    double* stats, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0 && G <= 32 && C % G == 0 && (C / G) % 8 == 0 && 256 % (C / 8) == 0,
                "groupnorm: unsupported C=%d G=%d", C, G);
-  RMEM_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * G, s));
+  // scratch layout (doubles): [0,64) stats | [64] counter (zero-initialised once, self re-arming) | [72,..) partials
   int rows_per_block = 256 / (C / 8);
-  int grid = min(cdiv(P, rows_per_block * 4), 148 * 8);
-  gn_stats_kernel<T><<<grid, 256, 0, s>>>(x, P, C, G, stats);
+  int grid = min(cdiv(P, rows_per_block * 4), kGnMaxBlocks);
+  gn_stats_kernel<T><<<grid, 256, 0, s>>>(x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64));
   RMEM_LAUNCH_CHECK();
   long long nvec = (long long)P * (C / 8);
   gn_apply_kernel<T><<<(unsigned)((nvec + 255) / 256), 256, 0, s>>>(x, gamma, beta, y, P, C, G, relu, stats);

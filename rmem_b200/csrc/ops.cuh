@@ -15,7 +15,9 @@ int maxpool3x3s2(const bf16* x, bf16* y, int Hin, int Win, int C, int Hout, int 
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, bf16* y, long long ldy,
               bf16* y2, long long ldy2, int P, int C, cudaStream_t s);
 
-// GroupNorm over (pixels x C/G) per group, eps 1e-5, optional ReLU.  `stats` = 2*G doubles scratch.
+// GroupNorm over (pixels x C/G) per group, eps 1e-5, optional ReLU.  `stats` = kGnScratchDoubles doubles of
+// scratch whose element [64] (the block counter) must be zero before the first call; it re-arms itself.
+constexpr int kGnScratchDoubles = 72 + 148 * 4 * 64;
 int groupnorm_bf16(const bf16* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
                    double* stats, cudaStream_t s);
 int groupnorm_f32(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,

@@ -97,7 +97,7 @@ def groupnorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, groups: int, re
     lib = _capi.load()
     P, Cc = x.shape
     y = torch.empty(P, Cc, dtype=torch.bfloat16, device=x.device)
-    stats = torch.empty(64, dtype=torch.float64, device=x.device)
+    stats = torch.zeros(72 + 148 * 4 * 64, dtype=torch.float64, device=x.device)
     _capi.check(lib.rmem_groupnorm_fwd(_capi.ptr(x), int(x.dtype == torch.float32), _capi.ptr(g), _capi.ptr(b),
                                        _capi.ptr(y), P, Cc, groups, int(relu), _capi.ptr(stats), _capi.stream_ptr()))
     return y

@@ -1,0 +1,26 @@
+"""Parity of the fused tcgen05/TMA long-term attention kernel (rmem_b200/csrc/attn_tc.cu) against the CPU oracle
+and the dense CUDA path, through the C ABI.  Tolerance: rel-Frobenius <= 8e-3 on the attention output (bf16
+operands and bf16 P, fp32 accumulate), per-frame mass max-abs <= 2e-3."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_tc_attention_matches_oracle(cuda_device):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "tc_attn_check.py")], capture_output=True, text=True,
+                       timeout=600)
+    print(r.stdout)
+    print(r.stderr[-2000:])
+    recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(recs) == 5, "tcgen05 attention check crashed"
+    for rec in recs:
+        assert rec["ok"], rec
+        assert rec["finite"], rec
+        assert rec["tc_vs_oracle"] < 8e-3, rec
+        assert rec["mass_err"] < 2e-3 and rec["mass_sum_err"] < 2e-3, rec

@@ -77,7 +77,7 @@ def test_engine_matches_reference_goldens(cuda_device, name):
         full = torch.from_numpy(z[f"logits4_{kf}"].astype(np.float32))
         e = float((rec["logits4"][kf][0] - full).abs().max())
         worst = max(worst, (e - 2e-3 * float(full.abs().max())) / float(full.abs().max()))   # fixture is fp16
-    print(f"[{name}] worst relative logit error = {worst:.3e}")
+    print(f"[{name}] worst relative logit error = {worst:.3e}", flush=True)
     assert worst < LOGIT_TOL
     # (b) labels
     ours = torch.stack(rec["labels"])

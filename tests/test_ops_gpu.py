@@ -190,16 +190,27 @@ def test_local_attention(ops, cuda_device):
 
 
 def test_mask_head_bit_exact_labels(ops, cuda_device):
+    """Integer mask IDs must be bit-exact given identical 1/4-res logits.  Full-res logits: tight for one object
+    group; for k > 1 the reference's logit(clamp(p)) is ill-conditioned near p -> 1 (1 ulp of p moves the logit by
+    ~6e-3), so those are compared in probability space."""
     g = torch.Generator().manual_seed(7)
     for k, (h4, w4, Ho, Wo) in [(1, (65, 81, 257, 321)), (1, (121, 213, 480, 854)), (2, (49, 65, 193, 257)),
-                                (3, (33, 41, 129, 161))]:
+                                (3, (33, 41, 129, 161)), (1, (65, 81, 65, 81))]:
         lgs = [torch.randn(1, 11, h4, w4, generator=g) * 3 for _ in range(k)]
         up = [F.interpolate(l, size=(Ho, Wo), mode="bilinear", align_corners=True) for l in lgs]
         ref_logit = O.soft_logit_aggregation(up)
         ref_label = O.logits_to_label(ref_logit)[0, 0].to(torch.uint8)
         out, lab = ops.mask_head([l[0].contiguous().to(cuda_device) for l in lgs], Ho, Wo)
-        assert float((out.cpu() - ref_logit[0]).abs().max()) < 1e-4
+        if k == 1:
+            err = float((out.cpu() - ref_logit[0]).abs().max())
+            print(f"mask_head k=1 {h4}x{w4}->{Ho}x{Wo}: max |dlogit| = {err:.3e}")
+            assert err < 2e-5
+        else:
+            err = float((torch.sigmoid(out.cpu()) - torch.sigmoid(ref_logit[0])).abs().max())
+            print(f"mask_head k={k}: max |dprob| = {err:.3e}")
+            assert err < 2e-6
         mism = int((lab.cpu() != ref_label).sum())
+        print(f"mask_head k={k}: label mismatches = {mism}/{lab.numel()}")
         assert mism == 0, f"k={k}: {mism} label mismatches"
 
 
