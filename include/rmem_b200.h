@@ -7,8 +7,9 @@
  * rmem_last_error(), thread-local), never throws, never calls exit(), never allocates device memory
  * (the caller passes outputs and a workspace/arena it sized with the matching *_bytes query), takes an
  * explicit cudaStream_t (as void*), holds no global mutable state.  Device pointers only unless a
- * parameter is marked HOST.  All activations are token-major ("[pixels, channels]", i.e. NHWC); bf16 is
- * the tensor-core operand type, fp32 the residual / statistics / logits type.
+ * parameter is marked HOST.  All activations are token-major ("[pixels, channels]", i.e. NHWC); "t16" below is
+ * the 16-bit tensor-core operand type (fp16 by default, see rmem_operand_dtype), fp32 the residual / statistics /
+ * logits type.
  *
  * Paths are relative to /root/reference/aot_plus/.
  */
@@ -29,22 +30,24 @@ extern "C" {
 
 int rmem_version(void);
 const char* rmem_last_error(void);
+/* "fp16" (default build) or "t16": the 16-bit tensor-core operand / activation type every `void*` half tensor uses. */
+const char* rmem_operand_dtype(void);
 
 /* ---------------------------------------------------------------- op level (module forwards) ---- */
 
-/* Generic bf16 GEMM / implicit-GEMM conv with fused epilogue: nn.Linear / nn.Conv2d(+FrozenBatchNorm2d+ReLU)
+/* Generic t16 GEMM / implicit-GEMM conv with fused epilogue: nn.Linear / nn.Conv2d(+FrozenBatchNorm2d+ReLU)
  * call sites of networks/encoders/resnet.py:48-68,178-195, networks/decoders/fpn.py:36-68,
  * networks/layers/transformer.py:1104-1123, attention.py:151-172.  See rmem_b200/csrc/gemm.cuh. */
 typedef struct rmem_gemm_desc {
-  const void* A; long long lda;      /* bf16 [M,K] row-major, or NHWC map when conv != 0 */
-  const void* B; long long ldb;      /* bf16 [N,K] row-major weight (K ordered ky,kx,ci for conv) */
+  const void* A; long long lda;      /* t16 [M,K] row-major, or NHWC map when conv != 0 */
+  const void* B; long long ldb;      /* t16 [N,K] row-major weight (K ordered ky,kx,ci for conv) */
   int M, N, K;
   int conv, Hin, Win, Cin, Wout, kw, stride, pad;
   float alpha;
   const float* bias; int bias_along_m;
   int act; int act_from_col;         /* 0 none, 1 relu, 2 silu; applied to columns >= act_from_col */
-  const void* residual; long long ldr;  /* bf16, added before the activation */
-  const void* gate; long long ldg;      /* bf16, multiplied after the activation */
+  const void* residual; long long ldr;  /* t16, added before the activation */
+  const void* gate; long long ldg;      /* t16, multiplied after the activation */
   int accumulate;                    /* C += result (fp32 destinations only) */
   void* C; long long ldc; int c_is_f32;
   void* C2; long long ldc2; int c2_is_f32; int n_split; /* columns >= n_split go to C2 */
@@ -61,7 +64,7 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
                        float scale, const void* gate, long long ldg, void* out, long long ldo, float* mass,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* Qt = bf16(Q + cur_pos_emb); qbias[i,t] = scale * <Qt_i, pe_mem[t]>          (transformer.py:1140-1175) */
+/* Qt = t16(Q + cur_pos_emb); qbias[i,t] = scale * <Qt_i, pe_mem[t]>          (transformer.py:1140-1175) */
 /* pe_mem = mem_pos_emb [n_slots, C]; pe_slot HOST [T] = slot of each memory frame (rmem_temporal_pe_slots). */
 int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
                    float scale, void* qt, float* qbias, int P, int C, void* stream);
@@ -81,7 +84,7 @@ int rmem_groupnorm_fwd(const void* x, int x_is_f32, const float* gamma, const fl
                        void* stream);
 int rmem_dwconv5x5_fwd(const void* x, const float* w /* [25,C] */, void* y, int h, int w_, int C, void* stream);
 
-/* F.interpolate(bilinear, align_corners=True) on NHWC bf16 (fpn.py:50,58). */
+/* F.interpolate(bilinear, align_corners=True) on NHWC t16 (fpn.py:50,58). */
 int rmem_upsample_bilinear_fwd(const void* x, void* y, int hin, int win, int hout, int wout, int C, void* stream);
 int rmem_transpose_fwd(const void* x, long long ldx, void* y, long long ldy, int P, int C, void* stream);
 int rmem_maxpool3x3s2_fwd(const void* x, void* y, int Hin, int Win, int C, int Hout, int Wout, void* stream);
@@ -91,7 +94,7 @@ int rmem_pack_image_fwd(const float* img_nchw, void* out_nhwc8, int H, int W, vo
  * patch_wise_id_bank Conv2d(12->256,k17,s16,p8) (networks/models/aot.py:63-74,111-114) + id_norm
  * (networks/models/deaot.py:65-69), as a gather-sum indexed by the uint8 label. */
 int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed /* [289,12,C] */,
-                    const float* bias, const float* ln_gamma, const float* ln_beta, void* out_bf16, long long ldo,
+                    const float* bias, const float* ln_gamma, const float* ln_beta, void* out_t16, long long ldo,
                     float* out_f32, int h, int w, int C, void* stream);
 
 /* Mask-ID assignment: bilinear(align_corners=True) upsample of the 1/4-res logits (aot_engine.py:457-463),

@@ -44,7 +44,7 @@ class WeightEntry(C.Structure):
 
 # every symbol include/rmem_b200.h declares (tests/test_capi_symbols.py checks header <-> this list <-> .so)
 SYMBOLS = [
-    "rmem_version", "rmem_last_error", "rmem_gemm_fwd", "rmem_long_attn_workspace_bytes", "rmem_long_attn_fwd",
+    "rmem_version", "rmem_last_error", "rmem_operand_dtype", "rmem_gemm_fwd", "rmem_long_attn_workspace_bytes", "rmem_long_attn_fwd",
     "rmem_qprep_fwd", "rmem_temporal_pe_slots", "rmem_local_attn_fwd", "rmem_layernorm_fwd", "rmem_groupnorm_fwd",
     "rmem_dwconv5x5_fwd", "rmem_upsample_bilinear_fwd", "rmem_transpose_fwd", "rmem_maxpool3x3s2_fwd",
     "rmem_pack_image_fwd", "rmem_idbank_fwd", "rmem_mask_head_fwd", "rmem_evict_relevance_fwd", "rmem_evict_pick",
@@ -73,12 +73,19 @@ def load(build_if_missing: bool = True):
         raise RmemError(f"rmem_b200 CUDA extension not found at {LIB_PATH}; run `python -m rmem_b200.build`")
     lib = C.CDLL(LIB_PATH)
     lib.rmem_last_error.restype = C.c_char_p
+    lib.rmem_operand_dtype.restype = C.c_char_p
     lib.rmem_engine_launch_count.restype = C.c_longlong
     lib.rmem_engine_destroy.restype = None
     for s in SYMBOLS:
         getattr(lib, s)  # AttributeError if the .so does not export it
     _lib = lib
     return lib
+
+
+def op_dtype():
+    """torch dtype of the 16-bit tensor-core operands the extension was built for (fp16 default)."""
+    import torch
+    return torch.float16 if load().rmem_operand_dtype() == b"fp16" else torch.bfloat16
 
 
 def check(rc: int):

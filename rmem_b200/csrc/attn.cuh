@@ -9,26 +9,26 @@ constexpr int kMaxBankFrames = 16;
 // Long-term (and self) attention over the restricted bank:
 //   P = softmax_j( scale * <qt_i, K_j> + qbias[i, t(j)] )   over all live frames' tokens
 //   out[i,:] = (sum_j P_ij * V_j) * gate[i,:] ;   mass[i,t] = sum_{j in frame t} P_ij
-// Bank layout (ours, ring of physical slots):  kbank [nslots][HWp][Dk] bf16 (token-major),
-// vtbank [Dv][nslots*HWp] bf16 (value-major = K-major for the PV contraction, frame `s` at columns s*HWp..).
+// Bank layout (ours, ring of physical slots):  kbank [nslots][HWp][Dk] t16 (token-major),
+// vtbank [Dv][nslots*HWp] t16 (value-major = K-major for the PV contraction, frame `s` at columns s*HWp..).
 struct LongAttnArgs {
-  const bf16* qt = nullptr;      // [HW, Dk]
+  const t16* qt = nullptr;      // [HW, Dk]
   const float* qbias = nullptr;  // [HW, T] or null
-  const bf16* kbank = nullptr;
-  const bf16* vtbank = nullptr;
+  const t16* kbank = nullptr;
+  const t16* vtbank = nullptr;
   int nslots = 1;
   int T = 1;
   int slot[kMaxBankFrames] = {0};  // logical frame t -> physical slot
   int HW = 0, HWp = 0, Dk = 128, Dv = 1024;
   float scale = 1.f;
-  const bf16* gate = nullptr;    // [HW, Dv] or null
+  const t16* gate = nullptr;    // [HW, Dv] or null
   long long ldg = 0;
-  bf16* out = nullptr;           // [HW, Dv]
+  t16* out = nullptr;           // [HW, Dv]
   long long ldo = 0;
   float* mass = nullptr;         // [HW, T] or null
 };
 
-// Materialised-score implementation (generic GEMM + row softmax).  Workspace: S fp32 + P bf16.
+// Materialised-score implementation (generic GEMM + row softmax).  Workspace: S fp32 + P t16.
 size_t long_attn_dense_workspace(int HW, int HWp, int nslots);
 int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
@@ -39,8 +39,8 @@ int long_attn_tc(const LongAttnArgs& a, void* workspace, size_t workspace_bytes,
 // Windowed short-term attention (LocalGatedPropagation core, attention.py:289-353), 15x15 window:
 //   s[i,d] = scale*<q_i, k_{i+d}> + rel[i,d] ; p = softmax_d ; out_i = (sum_d p[i,d] v_{i+d}) * gate_i
 // q,k [HW,128]; v [HW,Dv]; rel fp32 [HW, ldrel] (first 225 columns); all token-major with row strides.
-int local_attn(const bf16* q, long long ldq, const bf16* k, long long ldk, const bf16* v, long long ldv,
-               const float* rel, long long ldrel, const bf16* gate, long long ldg, bf16* out, long long ldo, int h,
+int local_attn(const t16* q, long long ldq, const t16* k, long long ldk, const t16* v, long long ldv,
+               const float* rel, long long ldrel, const t16* gate, long long ldg, t16* out, long long ldo, int h,
                int w, int Dv, float scale, cudaStream_t s);
 
 }  // namespace rmem

@@ -11,14 +11,14 @@ namespace {
 struct SlotMap { int slot[kMaxBankFrames]; };
 
 // One block per query row.  S row layout: [nslots][HWp] fp32 (only live slots / first HW columns valid).
-__global__ void softmax_mass_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long ld, int HW, int HWp,
+__global__ void softmax_mass_kernel(const float* __restrict__ S, t16* __restrict__ P, long long ld, int HW, int HWp,
                                     int nslots, int T, SlotMap sm, const float* __restrict__ qbias,
                                     float* __restrict__ mass) {
   __shared__ float red[32];
   __shared__ float s_mass[kMaxBankFrames];
   const int row = blockIdx.x;
   const float* Sr = S + (long long)row * ld;
-  bf16* Pr = P + (long long)row * ld;
+  t16* Pr = P + (long long)row * ld;
   float bias[kMaxBankFrames];
 #pragma unroll
   for (int t = 0; t < kMaxBankFrames; ++t) bias[t] = (t < T && qbias) ? qbias[(long long)row * T + t] : 0.f;
@@ -47,17 +47,17 @@ __global__ void softmax_mass_kernel(const float* __restrict__ S, bf16* __restric
     bool live = false;
 #pragma unroll
     for (int t = 0; t < kMaxBankFrames; ++t) live = live || (t < T && sm.slot[t] == s);
-    if (!live || c >= HW) Pr[j] = __float2bfloat16(0.f);
+    if (!live || c >= HW) Pr[j] = f2t(0.f);
   }
 #pragma unroll
   for (int t = 0; t < kMaxBankFrames; ++t) {
     if (t >= T) break;
     const float* St = Sr + (long long)sm.slot[t] * HWp;
-    bf16* Pt = Pr + (long long)sm.slot[t] * HWp;
+    t16* Pt = Pr + (long long)sm.slot[t] * HWp;
     float m = 0.f;
     for (int j = threadIdx.x; j < HW; j += blockDim.x) {
       float p = __expf(St[j] + bias[t] - mx) * inv;
-      Pt[j] = __float2bfloat16(p);
+      Pt[j] = f2t(p);
       m += p;
     }
     if (mass) {
@@ -74,12 +74,12 @@ __global__ void softmax_mass_kernel(const float* __restrict__ S, bf16* __restric
 // ------------------------------------------------------------------------------------------------
 // Local attention, one warp per query (CUDA cores; 0.87 GFLOP at 480p).
 template <int NCH>  // Dv = NCH * 256
-__global__ void __launch_bounds__(128) local_attn_kernel(const bf16* __restrict__ q, long long ldq,
-                                                         const bf16* __restrict__ k, long long ldk,
-                                                         const bf16* __restrict__ v, long long ldv,
+__global__ void __launch_bounds__(128) local_attn_kernel(const t16* __restrict__ q, long long ldq,
+                                                         const t16* __restrict__ k, long long ldk,
+                                                         const t16* __restrict__ v, long long ldv,
                                                          const float* __restrict__ rel, long long ldrel,
-                                                         const bf16* __restrict__ gate, long long ldg,
-                                                         bf16* __restrict__ out, long long ldo, int h, int w,
+                                                         const t16* __restrict__ gate, long long ldg,
+                                                         t16* __restrict__ out, long long ldo, int h, int w,
                                                          float scale) {
   __shared__ float s_q[4][128];
   __shared__ float s_p[4][256];
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) local_attn_kernel(const bf16* __restrict_
   const int py = i / w, px = i - py * w;
   {
     uint2 u = *reinterpret_cast<const uint2*>(q + (long long)i * ldq + lane * 4);
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    float2 a = unpack2(u.x), b = unpack2(u.y);
     s_q[warp][lane * 4 + 0] = a.x; s_q[warp][lane * 4 + 1] = a.y;
     s_q[warp][lane * 4 + 2] = b.x; s_q[warp][lane * 4 + 3] = b.y;
   }
@@ -104,12 +104,12 @@ __global__ void __launch_bounds__(128) local_attn_kernel(const bf16* __restrict_
       int dy = d / 15 - 7, dx = d % 15 - 7;
       int ny = py + dy, nx = px + dx;
       if ((unsigned)ny < (unsigned)h && (unsigned)nx < (unsigned)w) {
-        const bf16* kr = k + (long long)(ny * w + nx) * ldk;
+        const t16* kr = k + (long long)(ny * w + nx) * ldk;
         float dot = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
-          float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), f = unpack_bf16x2(u.w);
+          float2 a = unpack2(u.x), b = unpack2(u.y), e = unpack2(u.z), f = unpack2(u.w);
           const float* qq = &s_q[warp][c * 8];
           dot += a.x * qq[0] + a.y * qq[1] + b.x * qq[2] + b.y * qq[3] + e.x * qq[4] + e.y * qq[5] + f.x * qq[6] +
                  f.y * qq[7];
@@ -142,11 +142,11 @@ __global__ void __launch_bounds__(128) local_attn_kernel(const bf16* __restrict_
   for (int ny = y_lo; ny <= y_hi; ++ny) {
     for (int nx = x_lo; nx <= x_hi; ++nx) {
       const float p = s_p[warp][(ny - py + 7) * 15 + (nx - px + 7)];
-      const bf16* vr = v + (long long)(ny * w + nx) * ldv + lane * 8;
+      const t16* vr = v + (long long)(ny * w + nx) * ldv + lane * 8;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         uint4 u = *reinterpret_cast<const uint4*>(vr + c * 256);
-        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), f = unpack_bf16x2(u.w);
+        float2 a = unpack2(u.x), b = unpack2(u.y), e = unpack2(u.z), f = unpack2(u.w);
         acc[c][0] += p * a.x; acc[c][1] += p * a.y; acc[c][2] += p * b.x; acc[c][3] += p * b.y;
         acc[c][4] += p * e.x; acc[c][5] += p * e.y; acc[c][6] += p * f.x; acc[c][7] += p * f.y;
       }
@@ -157,13 +157,13 @@ __global__ void __launch_bounds__(128) local_attn_kernel(const bf16* __restrict_
     const int col = c * 256 + lane * 8;
     if (gate) {
       uint4 u = *reinterpret_cast<const uint4*>(gate + (long long)i * ldg + col);
-      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), f = unpack_bf16x2(u.w);
+      float2 a = unpack2(u.x), b = unpack2(u.y), e = unpack2(u.z), f = unpack2(u.w);
       acc[c][0] *= a.x; acc[c][1] *= a.y; acc[c][2] *= b.x; acc[c][3] *= b.y;
       acc[c][4] *= e.x; acc[c][5] *= e.y; acc[c][6] *= f.x; acc[c][7] *= f.y;
     }
     uint4 o;
-    o.x = pack_bf16x2(acc[c][0], acc[c][1]); o.y = pack_bf16x2(acc[c][2], acc[c][3]);
-    o.z = pack_bf16x2(acc[c][4], acc[c][5]); o.w = pack_bf16x2(acc[c][6], acc[c][7]);
+    o.x = pack2(acc[c][0], acc[c][1]); o.y = pack2(acc[c][2], acc[c][3]);
+    o.z = pack2(acc[c][4], acc[c][5]); o.w = pack2(acc[c][6], acc[c][7]);
     *reinterpret_cast<uint4*>(out + (long long)i * ldo + col) = o;
   }
 }
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) local_attn_kernel(const bf16* __restrict_
 
 size_t long_attn_dense_workspace(int HW, int HWp, int nslots) {
   size_t cols = (size_t)nslots * HWp;
-  return (size_t)HW * cols * (sizeof(float) + sizeof(bf16)) + 256;
+  return (size_t)HW * cols * (sizeof(float) + sizeof(t16)) + 256;
 }
 
 int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s) {
@@ -181,7 +181,7 @@ int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_byt
   RMEM_REQUIRE(workspace_bytes >= long_attn_dense_workspace(a.HW, a.HWp, a.nslots), "long_attn: workspace too small");
   const long long ld = (long long)a.nslots * a.HWp;
   float* S = reinterpret_cast<float*>(workspace);
-  bf16* P = reinterpret_cast<bf16*>(S + (size_t)a.HW * ld);
+  t16* P = reinterpret_cast<t16*>(S + (size_t)a.HW * ld);
   for (int t = 0; t < a.T; ++t) {
     RMEM_REQUIRE(a.slot[t] >= 0 && a.slot[t] < a.nslots, "long_attn: bad slot");
     GemmParams g;
@@ -205,8 +205,8 @@ int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_byt
   return gemm_launch(g, s);
 }
 
-int local_attn(const bf16* q, long long ldq, const bf16* k, long long ldk, const bf16* v, long long ldv,
-               const float* rel, long long ldrel, const bf16* gate, long long ldg, bf16* out, long long ldo, int h,
+int local_attn(const t16* q, long long ldq, const t16* k, long long ldk, const t16* v, long long ldv,
+               const float* rel, long long ldrel, const t16* gate, long long ldg, t16* out, long long ldo, int h,
                int w, int Dv, float scale, cudaStream_t s) {
   RMEM_REQUIRE(Dv == 1024 || Dv == 512 || Dv == 256, "local_attn: Dv=%d unsupported", Dv);
   RMEM_REQUIRE(ldq % 4 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && (!gate || ldg % 8 == 0),

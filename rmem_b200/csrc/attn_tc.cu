@@ -104,7 +104,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
+// D[tmem] (+)= A[smem] . B[smem]^T, t16 x t16 -> fp32
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                         uint32_t accumulate) {
   asm volatile(
@@ -126,9 +126,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: bf16 A/B (K-major), fp32 D.
+// kind::f16 instruction descriptor: fp16/bf16 A/B (K-major), fp32 D.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | (RMEM_UMMA_FORMAT << 7) | (RMEM_UMMA_FORMAT << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -329,10 +330,10 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
       for (int c = 0; c < BN / 8; ++c) {
         uint4 u;
-        u.x = pack_bf16x2(s[c * 8 + 0], s[c * 8 + 1]);
-        u.y = pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]);
-        u.z = pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]);
-        u.w = pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]);
+        u.x = pack2(s[c * 8 + 0], s[c * 8 + 1]);
+        u.y = pack2(s[c * 8 + 2], s[c * 8 + 3]);
+        u.z = pack2(s[c * 8 + 4], s[c * 8 + 5]);
+        u.w = pack2(s[c * 8 + 6], s[c * 8 + 7]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;
       }
       fence_async_smem();
@@ -370,8 +371,8 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // Merge the split partials: out = (sum_s 2^(m_s-M) O_s) / L * gate ; mass[i,t] = sum_{s in t} l_s 2^(m_s-M) / L.
 __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ part_o,
                                                       const float* __restrict__ part_ml, int nsplit, int nsub, int T,
-                                                      int HW, int Dv, const bf16* __restrict__ gate, long long ldg,
-                                                      bf16* __restrict__ out, long long ldo,
+                                                      int HW, int Dv, const t16* __restrict__ gate, long long ldg,
+                                                      t16* __restrict__ out, long long ldo,
                                                       float* __restrict__ mass) {
   __shared__ float w[kMaxBankFrames * 8];
   __shared__ float s_inv;
@@ -410,15 +411,21 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
     acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     if (gate) {
       const uint2 g = *reinterpret_cast<const uint2*>(gate + (long long)i * ldg + c);
-      const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+      const float2 g0 = unpack2(g.x), g1 = unpack2(g.y);
       acc.x *= g0.x; acc.y *= g0.y; acc.z *= g1.x; acc.w *= g1.y;
     }
     uint2 o;
-    o.x = pack_bf16x2(acc.x, acc.y);
-    o.y = pack_bf16x2(acc.z, acc.w);
+    o.x = pack2(acc.x, acc.y);
+    o.y = pack2(acc.z, acc.w);
     *reinterpret_cast<uint2*>(out + (long long)i * ldo + c) = o;
   }
 }
+
+#ifdef RMEM_OPERAND_BF16
+constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
 
 int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
               uint32_t box_inner, uint32_t box_outer) {
@@ -426,13 +433,27 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  // The driver entry point is resolved at run time so the library links (and loads on a GPU-less build box)
+  // without libcuda.so.
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      return RMEM_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  CUresult r = encode(map, kTmaType, 2, const_cast<void*>(base), dims, strides,
                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    const char* msg = nullptr;
-    cuGetErrorString(r, &msg);
-    set_error("cuTensorMapEncodeTiled failed: %s (inner=%llu outer=%llu stride=%llu box=%ux%u)", msg ? msg : "?",
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)", (int)r,
               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
               box_outer);
     return RMEM_ERR_CUDA;

@@ -34,17 +34,18 @@ using namespace rmem;
 extern "C" {
 
 int rmem_version(void) { return 100; }
+const char* rmem_operand_dtype(void) { return RMEM_OPERAND_NAME; }
 const char* rmem_last_error(void) { return get_error(); }
 
 int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream) {
   RMEM_REQUIRE(d, "null desc");
   GemmParams p;
-  p.A = (const bf16*)d->A; p.lda = d->lda; p.B = (const bf16*)d->B; p.ldb = d->ldb;
+  p.A = (const t16*)d->A; p.lda = d->lda; p.B = (const t16*)d->B; p.ldb = d->ldb;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.conv = d->conv; p.Hin = d->Hin; p.Win = d->Win; p.Cin = d->Cin; p.Wout = d->Wout; p.kw = d->kw;
   p.stride = d->stride; p.pad = d->pad;
   p.alpha = d->alpha; p.bias = d->bias; p.bias_m = d->bias_along_m; p.act = d->act; p.act_from = d->act_from_col;
-  p.res = (const bf16*)d->residual; p.ldr = d->ldr; p.gate = (const bf16*)d->gate; p.ldg = d->ldg;
+  p.res = (const t16*)d->residual; p.ldr = d->ldr; p.gate = (const t16*)d->gate; p.ldg = d->ldg;
   p.accumulate = d->accumulate;
   p.C = d->C; p.ldc = d->ldc; p.c_fp32 = d->c_is_f32;
   p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_fp32 = d->c2_is_f32;
@@ -65,18 +66,18 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
   RMEM_REQUIRE(qt && kbank && vtbank && out && slots && workspace, "null argument");
   RMEM_REQUIRE(T >= 1 && T <= kMaxBankFrames, "T=%d out of range", T);
   LongAttnArgs a;
-  a.qt = (const bf16*)qt; a.qbias = qbias; a.kbank = (const bf16*)kbank; a.vtbank = (const bf16*)vtbank;
+  a.qt = (const t16*)qt; a.qbias = qbias; a.kbank = (const t16*)kbank; a.vtbank = (const t16*)vtbank;
   a.nslots = nslots; a.T = T;
   for (int t = 0; t < T; ++t) a.slot[t] = slots[t];
   a.HW = HW; a.HWp = HWp; a.Dk = Dk; a.Dv = Dv; a.scale = scale;
-  a.gate = (const bf16*)gate; a.ldg = ldg; a.out = (bf16*)out; a.ldo = ldo; a.mass = mass;
+  a.gate = (const t16*)gate; a.ldg = ldg; a.out = (t16*)out; a.ldo = ldo; a.mass = mass;
   if (impl == RMEM_ATTN_TC) return long_attn_tc(a, workspace, workspace_bytes, STREAM(stream));
   return long_attn_dense(a, workspace, workspace_bytes, STREAM(stream));
 }
 
 int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
                    float scale, void* qt, float* qbias, int P, int C, void* stream) {
-  return qprep((const bf16*)q, ldq, pe_cur, pe_mem, pe_slot, T, scale, (bf16*)qt, qbias, P, C, STREAM(stream));
+  return qprep((const t16*)q, ldq, pe_cur, pe_mem, pe_slot, T, scale, (t16*)qt, qbias, P, C, STREAM(stream));
 }
 
 int rmem_temporal_pe_slots(int T, int n_slots, int* out) {
@@ -88,46 +89,46 @@ int rmem_temporal_pe_slots(int T, int n_slots, int* out) {
 int rmem_local_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                         const float* rel, long long ldrel, const void* gate, long long ldg, void* out, long long ldo,
                         int h, int w, int Dv, float scale, void* stream) {
-  return local_attn((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, rel, ldrel, (const bf16*)gate, ldg,
-                    (bf16*)out, ldo, h, w, Dv, scale, STREAM(stream));
+  return local_attn((const t16*)q, ldq, (const t16*)k, ldk, (const t16*)v, ldv, rel, ldrel, (const t16*)gate, ldg,
+                    (t16*)out, ldo, h, w, Dv, scale, STREAM(stream));
 }
 
 int rmem_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
                        int P, int C, void* stream) {
-  return layernorm(x, ldx, gamma, beta, (bf16*)y, ldy, nullptr, 0, P, C, STREAM(stream));
+  return layernorm(x, ldx, gamma, beta, (t16*)y, ldy, nullptr, 0, P, C, STREAM(stream));
 }
 
 int rmem_groupnorm_fwd(const void* x, int x_is_f32, const float* gamma, const float* beta, void* y, int P, int C, int G,
                        int relu, double* stats, void* stream) {
-  if (x_is_f32) return groupnorm_f32((const float*)x, gamma, beta, (bf16*)y, P, C, G, relu, stats, STREAM(stream));
-  return groupnorm_bf16((const bf16*)x, gamma, beta, (bf16*)y, P, C, G, relu, stats, STREAM(stream));
+  if (x_is_f32) return groupnorm_f32((const float*)x, gamma, beta, (t16*)y, P, C, G, relu, stats, STREAM(stream));
+  return groupnorm_t16((const t16*)x, gamma, beta, (t16*)y, P, C, G, relu, stats, STREAM(stream));
 }
 
 int rmem_dwconv5x5_fwd(const void* x, const float* w, void* y, int h, int w_, int C, void* stream) {
-  return dwconv5x5((const bf16*)x, w, (bf16*)y, h, w_, C, STREAM(stream));
+  return dwconv5x5((const t16*)x, w, (t16*)y, h, w_, C, STREAM(stream));
 }
 
 int rmem_upsample_bilinear_fwd(const void* x, void* y, int hin, int win, int hout, int wout, int C, void* stream) {
-  return upsample_bilinear_bf16((const bf16*)x, (bf16*)y, hin, win, hout, wout, C, STREAM(stream));
+  return upsample_bilinear_t16((const t16*)x, (t16*)y, hin, win, hout, wout, C, STREAM(stream));
 }
 
 int rmem_transpose_fwd(const void* x, long long ldx, void* y, long long ldy, int P, int C, void* stream) {
-  return transpose_bf16((const bf16*)x, ldx, (bf16*)y, ldy, P, C, STREAM(stream));
+  return transpose_t16((const t16*)x, ldx, (t16*)y, ldy, P, C, STREAM(stream));
 }
 
 int rmem_maxpool3x3s2_fwd(const void* x, void* y, int Hin, int Win, int C, int Hout, int Wout, void* stream) {
-  return maxpool3x3s2((const bf16*)x, (bf16*)y, Hin, Win, C, Hout, Wout, STREAM(stream));
+  return maxpool3x3s2((const t16*)x, (t16*)y, Hin, Win, C, Hout, Wout, STREAM(stream));
 }
 
 int rmem_pack_image_fwd(const float* img, void* out, int H, int W, void* stream) {
-  return pack_image(img, (bf16*)out, H, W, STREAM(stream));
+  return pack_image(img, (t16*)out, H, W, STREAM(stream));
 }
 
 int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
-                    const float* ln_gamma, const float* ln_beta, void* out_bf16, long long ldo, float* out_f32, int h,
+                    const float* ln_gamma, const float* ln_beta, void* out_t16, long long ldo, float* out_f32, int h,
                     int w, int C, void* stream) {
-  RMEM_REQUIRE(label && w_packed && bias && (out_bf16 || out_f32), "null argument");
-  return idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_gamma, ln_beta, (bf16*)out_bf16, ldo, out_f32, h, w,
+  RMEM_REQUIRE(label && w_packed && bias && (out_t16 || out_f32), "null argument");
+  return idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_gamma, ln_beta, (t16*)out_t16, ldo, out_f32, h, w,
                       C, STREAM(stream));
 }
 

@@ -71,11 +71,11 @@ struct Arena {
 };
 
 struct LayerState {
-  bf16* kc[2];       // [HW,128]   current / previous frame K (= Q)
-  bf16* vid[2];      // [HW,1024]  V || ID_V, token-major (short-term memory + source of the bank append)
-  bf16* cat;         // [HW,512]   curr_ID_V || id_emb  (linear_ID_V input; layer 0 uses only the id half)
-  bf16* kbank;       // [nslots][HWp][128]
-  bf16* vtbank;      // [1024][nslots*HWp]
+  t16* kc[2];       // [HW,128]   current / previous frame K (= Q)
+  t16* vid[2];      // [HW,1024]  V || ID_V, token-major (short-term memory + source of the bank append)
+  t16* cat;         // [HW,512]   curr_ID_V || id_emb  (linear_ID_V input; layer 0 uses only the id half)
+  t16* kbank;       // [nslots][HWp][128]
+  t16* vtbank;      // [1024][nslots*HWp]
 };
 
 struct Group {       // one AOTEngine: <= 10 objects, own bank (reference + per-engine deepcopy)
@@ -110,12 +110,12 @@ struct rmem_engine {
   long long launches0 = 0;
 
   // shared scratch
-  bf16 *img8, *c1, *x0, *x1, *t1, *t2, *ds, *feat4, *feat8, *feat16;
+  t16 *img8, *c1, *x0, *x1, *t1, *t2, *ds, *feat4, *feat8, *feat16;
   float* enc_tgt;     // [HW,256] projector output
   float* res;         // [HW,512] tgt || tgt_id residual stream
-  bf16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
+  t16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
   float *qbias, *rel, *rel_dev;
-  bf16 *d0, *d1, *d2;
+  t16 *d0, *d1, *d2;
   double* stats;
   uint8_t* label8;
   void* attn_ws;
@@ -143,36 +143,36 @@ struct rmem_engine {
 
   int layout(Arena& a) {
     const Geo& G = g;
-    img8 = a.take<bf16>((size_t)G.H * G.W * 8);
-    c1 = a.take<bf16>((size_t)G.P1 * 64);
-    x0 = a.take<bf16>((size_t)G.P4 * 256);
-    x1 = a.take<bf16>((size_t)G.P4 * 256);
-    t1 = a.take<bf16>((size_t)G.P4 * 128);
-    t2 = a.take<bf16>((size_t)G.P4 * 64);
-    ds = a.take<bf16>((size_t)G.P4 * 256);
-    feat4 = a.take<bf16>((size_t)G.P4 * 256);
-    feat8 = a.take<bf16>((size_t)G.P8 * 512);
-    feat16 = a.take<bf16>((size_t)G.HW * 1024);
+    img8 = a.take<t16>((size_t)G.H * G.W * 8);
+    c1 = a.take<t16>((size_t)G.P1 * 64);
+    x0 = a.take<t16>((size_t)G.P4 * 256);
+    x1 = a.take<t16>((size_t)G.P4 * 256);
+    t1 = a.take<t16>((size_t)G.P4 * 128);
+    t2 = a.take<t16>((size_t)G.P4 * 64);
+    ds = a.take<t16>((size_t)G.P4 * 256);
+    feat4 = a.take<t16>((size_t)G.P4 * 256);
+    feat8 = a.take<t16>((size_t)G.P8 * 512);
+    feat16 = a.take<t16>((size_t)G.HW * 1024);
     enc_tgt = a.take<float>((size_t)G.HW * kD);
     res = a.take<float>((size_t)G.HW * 2 * kD);
-    t_ln = a.take<bf16>((size_t)G.HW * kD);
-    qt = a.take<bf16>((size_t)G.HW * kDk);
-    cu = a.take<bf16>((size_t)G.HW * kDv);
-    cu0 = a.take<bf16>((size_t)G.HW * kDv);
-    attn_a = a.take<bf16>((size_t)G.HW * kDv);
-    dwo = a.take<bf16>((size_t)G.HW * kDv);
-    z = a.take<bf16>((size_t)G.HW * 2 * kD);
-    qk = a.take<bf16>((size_t)G.HWp * kDk);
-    vt_self = a.take<bf16>((size_t)kDv * G.HWp);
-    u_self = a.take<bf16>((size_t)G.HW * kDv);
-    gpm_out = a.take<bf16>((size_t)G.HW * 2 * kD);
-    idemb = a.take<bf16>((size_t)G.HW * kD);
+    t_ln = a.take<t16>((size_t)G.HW * kD);
+    qt = a.take<t16>((size_t)G.HW * kDk);
+    cu = a.take<t16>((size_t)G.HW * kDv);
+    cu0 = a.take<t16>((size_t)G.HW * kDv);
+    attn_a = a.take<t16>((size_t)G.HW * kDv);
+    dwo = a.take<t16>((size_t)G.HW * kDv);
+    z = a.take<t16>((size_t)G.HW * 2 * kD);
+    qk = a.take<t16>((size_t)G.HWp * kDk);
+    vt_self = a.take<t16>((size_t)kDv * G.HWp);
+    u_self = a.take<t16>((size_t)G.HW * kDv);
+    gpm_out = a.take<t16>((size_t)G.HW * 2 * kD);
+    idemb = a.take<t16>((size_t)G.HW * kD);
     qbias = a.take<float>((size_t)G.HW * kMaxBankFrames);
     rel = a.take<float>((size_t)G.HW * 256);
     rel_dev = a.take<float>(64);
-    d0 = a.take<bf16>((size_t)G.P4 * 128);
-    d1 = a.take<bf16>((size_t)G.P4 * 128);
-    d2 = a.take<bf16>((size_t)G.P4 * 128);
+    d0 = a.take<t16>((size_t)G.P4 * 128);
+    d1 = a.take<t16>((size_t)G.P4 * 128);
+    d2 = a.take<t16>((size_t)G.P4 * 128);
     stats = a.take<double>(kGnScratchDoubles);
     label8 = a.take<uint8_t>((size_t)G.H * G.W);
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
@@ -185,12 +185,12 @@ struct rmem_engine {
       for (int l = 0; l < kLayers; ++l) {
         LayerState& L = gr.L[l];
         for (int p = 0; p < 2; ++p) {
-          L.kc[p] = a.take<bf16>((size_t)G.HWp * kDk);
-          L.vid[p] = a.take<bf16>((size_t)G.HW * kDv);
+          L.kc[p] = a.take<t16>((size_t)G.HWp * kDk);
+          L.vid[p] = a.take<t16>((size_t)G.HW * kDv);
         }
-        L.cat = a.take<bf16>((size_t)G.HW * 2 * kD);
-        L.kbank = a.take<bf16>((size_t)nslots * G.HWp * kDk);
-        L.vtbank = a.take<bf16>((size_t)kDv * nslots * G.HWp);
+        L.cat = a.take<t16>((size_t)G.HW * 2 * kD);
+        L.kbank = a.take<t16>((size_t)nslots * G.HWp * kDk);
+        L.vtbank = a.take<t16>((size_t)kDv * nslots * G.HWp);
       }
       gr.mass0 = a.take<float>((size_t)G.HW * kMaxBankFrames);
       gr.logits4 = a.take<float>((size_t)11 * G.P4);
@@ -205,10 +205,10 @@ struct rmem_engine {
 
   // ---------------------------------------------------------------------------------------------
   // conv / linear helpers over the generic GEMM
-  int conv(const bf16* x, int Hin, int Win, int Cin, const std::string& wname, int Cout, int k, int stride, int pad,
-           int act, const bf16* resid, bf16* out, cudaStream_t s) {
+  int conv(const t16* x, int Hin, int Win, int Cin, const std::string& wname, int Cout, int k, int stride, int pad,
+           int act, const t16* resid, t16* out, cudaStream_t s) {
     int rc = RMEM_OK;
-    const bf16* w = Wt<bf16>(wname + ".w", (size_t)Cout * k * k * Cin, &rc);
+    const t16* w = Wt<t16>(wname + ".w", (size_t)Cout * k * k * Cin, &rc);
     const float* b = Wt<float>(wname + ".b", Cout, &rc);
     if (rc) return rc;
     int Hout = (Hin + 2 * pad - k) / stride + 1, Wout = (Win + 2 * pad - k) / stride + 1;
@@ -227,7 +227,7 @@ struct rmem_engine {
   }
 
   struct Lin {
-    const bf16* A; long long lda; int M; int K; int N;
+    const t16* A; long long lda; int M; int K; int N;
     std::string w;
     int act = ACT_NONE; int act_from = 0;
     void* C = nullptr; long long ldc = 0; int c_fp32 = 0;
@@ -238,7 +238,7 @@ struct rmem_engine {
   int linear(const Lin& L, cudaStream_t s) {
     int rc = RMEM_OK;
     int rows = L.n_weight_rows > 0 ? L.n_weight_rows : L.N;
-    const bf16* w = Wt<bf16>(L.w + ".w", (size_t)rows * L.K, &rc);
+    const t16* w = Wt<t16>(L.w + ".w", (size_t)rows * L.K, &rc);
     const float* b = Wt<float>(L.w + ".b", rows, &rc);
     if (rc) return rc;
     GemmParams p;
@@ -253,12 +253,12 @@ struct rmem_engine {
 
   // ---------------------------------------------------------------------------------------------
   // ResNet-50 stem + layer1..3 (FrozenBN folded) + encoder_projector.   resnet.py:178-195, aot.py:116-134
-  int bottleneck(const bf16* x, int Hin, int Win, int Cin, const std::string& pre, int planes, int stride, bool has_ds,
-                 bf16* out, cudaStream_t s) {
+  int bottleneck(const t16* x, int Hin, int Win, int Cin, const std::string& pre, int planes, int stride, bool has_ds,
+                 t16* out, cudaStream_t s) {
     int Hout = (Hin - 1) / stride + 1, Wout = (Win - 1) / stride + 1;
     RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".conv1", planes, 1, 1, 0, ACT_RELU, nullptr, t1, s));
     RMEM_TRY(conv(t1, Hin, Win, planes, pre + ".conv2", planes, 3, stride, 1, ACT_RELU, nullptr, t2, s));
-    const bf16* idt = x;
+    const t16* idt = x;
     if (has_ds) {
       RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".ds", planes * 4, 1, stride, 0, ACT_NONE, nullptr, ds, s));
       idt = ds;
@@ -272,15 +272,15 @@ struct rmem_engine {
     RMEM_TRY(pack_image(img, img8, G.H, G.W, s));
     RMEM_TRY(conv(img8, G.H, G.W, 8, "enc.conv1", 64, 7, 2, 3, ACT_RELU, nullptr, c1, s));
     RMEM_TRY(maxpool3x3s2(c1, x0, G.H1, G.W1, 64, G.H4, G.W4, s));
-    bf16* cur = x0;
+    t16* cur = x0;
     int Hc = G.H4, Wc = G.W4, Cc = 64;
     const int planes[3] = {64, 128, 256}, nblk[3] = {3, 4, 6}, strides[3] = {1, 2, 2};
-    bf16* feats[3] = {feat4, feat8, feat16};
+    t16* feats[3] = {feat4, feat8, feat16};
     for (int li = 0; li < 3; ++li) {
       for (int bi = 0; bi < nblk[li]; ++bi) {
         int st = bi == 0 ? strides[li] : 1;
         bool has_ds = bi == 0;
-        bf16* out = (bi == nblk[li] - 1) ? feats[li] : ((cur == x0) ? x1 : x0);
+        t16* out = (bi == nblk[li] - 1) ? feats[li] : ((cur == x0) ? x1 : x0);
         std::string pre = "enc.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
         RMEM_TRY(bottleneck(cur, Hc, Wc, Cc, pre, planes[li], st, has_ds, out, s));
         Hc = (Hc - 1) / st + 1; Wc = (Wc - 1) / st + 1; Cc = planes[li] * 4;
@@ -304,7 +304,7 @@ struct rmem_engine {
     if (rc) return rc;
     RMEM_TRY(separate_label(label, label_is_f32, label8, G.H, G.W, gi, n_groups, s));
     RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s));
-    for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_bf16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
+    for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_t16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
     return RMEM_OK;
   }
 
@@ -327,8 +327,8 @@ struct rmem_engine {
     gr.free_slots.pop_back();
     for (int l = 0; l < kLayers; ++l) {
       LayerState& L = gr.L[l];
-      RMEM_TRY(copy2d_bf16(L.kc[gr.parity], kDk, L.kbank + (size_t)slot * G.HWp * kDk, kDk, G.HW, kDk, s));
-      RMEM_TRY(transpose_bf16(L.vid[gr.parity], kDv, L.vtbank + (size_t)slot * G.HWp, (long long)nslots * G.HWp,
+      RMEM_TRY(copy2d_t16(L.kc[gr.parity], kDk, L.kbank + (size_t)slot * G.HWp * kDk, kDk, G.HW, kDk, s));
+      RMEM_TRY(transpose_t16(L.vid[gr.parity], kDv, L.vtbank + (size_t)slot * G.HWp, (long long)nslots * G.HWp,
                               G.HW, kDv, s));
     }
     gr.slots.push_back(slot);
@@ -375,7 +375,7 @@ struct rmem_engine {
       p.C2 = L.vid[cur]; p.ldc2 = kDv; p.n_split = kDk;
       RMEM_TRY(linear(p, s));
     }
-    bf16* gate = (l == 0) ? cu0 : cu;
+    t16* gate = (l == 0) ? cu0 : cu;
     {
       Lin p;
       p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_U";
@@ -398,13 +398,13 @@ struct rmem_engine {
     LongAttnArgs a;
     a.HW = G.HW; a.HWp = G.HWp; a.Dk = kDk; a.Dv = kDv; a.scale = scale;
     a.gate = gate; a.ldg = kDv; a.out = attn_a; a.ldo = kDv;
-    const bf16 *sk, *sv;
+    const t16 *sk, *sv;
     int T;
     if (ref_mode) {
       RMEM_TRY(fuse_id(gr, l, s));                    // ID_V of the reference frame itself (:1125-1135)
       // bank := this frame -> physical slot 0
-      RMEM_TRY(copy2d_bf16(L.kc[cur], kDk, L.kbank, kDk, G.HW, kDk, s));
-      RMEM_TRY(transpose_bf16(L.vid[cur], kDv, L.vtbank, (long long)nslots * G.HWp, G.HW, kDv, s));
+      RMEM_TRY(copy2d_t16(L.kc[cur], kDk, L.kbank, kDk, G.HW, kDk, s));
+      RMEM_TRY(transpose_t16(L.vid[cur], kDv, L.vtbank, (long long)nslots * G.HWp, G.HW, kDv, s));
       T = 1;
       a.slot[0] = 0;
       sk = L.kc[cur]; sv = L.vid[cur];
@@ -454,7 +454,7 @@ struct rmem_engine {
       for (int half = 0; half < 2; ++half) {
         // v^T = silu(W_V . z_half^T + b): computed directly value-major (bias along M)
         const std::string wn = pre + ".self.linear_V" + std::to_string(half + 1);
-        const bf16* w = Wt<bf16>(wn + ".w", (size_t)2 * kD * kD, &rc);
+        const t16* w = Wt<t16>(wn + ".w", (size_t)2 * kD * kD, &rc);
         const float* b = Wt<float>(wn + ".b", 2 * kD, &rc);
         if (rc) return rc;
         GemmParams q;
@@ -488,7 +488,7 @@ struct rmem_engine {
                                       G.HW, cudaMemcpyDeviceToDevice, s));
     RMEM_CUDA_CHECK(cudaMemset2DAsync(res + kD, 2 * kD * sizeof(float), 0, kD * sizeof(float), G.HW, s));
     if (!ones_ready) {
-      RMEM_TRY(fill_bf16(cu0 + 512, kDv, G.HW, 512, 1.0f, s));
+      RMEM_TRY(fill_t16(cu0 + 512, kDv, G.HW, 512, 1.0f, s));
       ones_ready = true;
     }
     for (int l = 0; l < kLayers; ++l) RMEM_TRY(gpm_layer(gr, l, ref_mode, s));
@@ -498,27 +498,27 @@ struct rmem_engine {
     RMEM_TRY(groupnorm_f32(res, og, ob, gpm_out, G.HW, 2 * kD, 2, 0, stats, s));
 
     // ---- FPN ----
-    auto gn = [&](const std::string& n, const bf16* x, bf16* y, int P, int C) -> int {
+    auto gn = [&](const std::string& n, const t16* x, t16* y, int P, int C) -> int {
       int r2 = RMEM_OK;
       const float* gg = Wt<float>(n + ".gn.g", C, &r2);
       const float* gb = Wt<float>(n + ".gn.b", C, &r2);
       if (r2) return r2;
-      return groupnorm_bf16(x, gg, gb, y, P, C, 8, 1, stats, s);
+      return groupnorm_t16(x, gg, gb, y, P, C, 8, 1, stats, s);
     };
     RMEM_TRY(conv(gpm_out, G.h, G.w, 2 * kD, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s));
     RMEM_TRY(gn("dec.conv_in", d0, d1, G.HW, 256));
     RMEM_TRY(conv(feat16, G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, d1, d0, s));
     RMEM_TRY(conv(d0, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s));
     RMEM_TRY(gn("dec.conv_16x", d2, d1, G.HW, 256));
-    RMEM_TRY(upsample_bilinear_bf16(d1, d0, G.h, G.w, G.H8, G.W8, 256, s));
+    RMEM_TRY(upsample_bilinear_t16(d1, d0, G.h, G.w, G.H8, G.W8, 256, s));
     RMEM_TRY(conv(feat8, G.H8, G.W8, 512, "dec.adapter_8x", 256, 1, 1, 0, ACT_NONE, d0, d2, s));
     RMEM_TRY(conv(d2, G.H8, G.W8, 256, "dec.conv_8x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
     RMEM_TRY(gn("dec.conv_8x", d0, d1, G.P8, 128));
-    RMEM_TRY(upsample_bilinear_bf16(d1, d0, G.H8, G.W8, G.H4, G.W4, 128, s));
+    RMEM_TRY(upsample_bilinear_t16(d1, d0, G.H8, G.W8, G.H4, G.W4, 128, s));
     RMEM_TRY(conv(feat4, G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, d0, d2, s));
     RMEM_TRY(conv(d2, G.H4, G.W4, 128, "dec.conv_4x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
     RMEM_TRY(gn("dec.conv_4x", d0, d1, G.P4, 128));
-    const bf16* wo = Wt<bf16>("dec.conv_out.w", (size_t)11 * 128, &rc);
+    const t16* wo = Wt<t16>("dec.conv_out.w", (size_t)11 * 128, &rc);
     const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);
     if (rc) return rc;
     return conv_out_logits(d1, wo, bo, gr.logits4, G.P4, 128, 11, s);

@@ -1,4 +1,4 @@
-// bf16 GEMM / implicit-GEMM conv, mma.sync.m16n8k16 + ldmatrix + 3-stage cp.async pipeline.
+// t16 GEMM / implicit-GEMM conv, mma.sync.m16n8k16 + ldmatrix + 3-stage cp.async pipeline.
 // See gemm.cuh for the contract.
 #include "gemm.cuh"
 
@@ -25,9 +25,9 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(s));
 }
-__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint32_t* b) {
+__device__ __forceinline__ void mma_t16(float* c, const uint32_t* a, const uint32_t* b) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      "mma.sync.aligned.m16n8k16.row.col.f32." RMEM_MMA_TYPE "." RMEM_MMA_TYPE ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
   static_assert(NI % 2 == 0, "NI must be even");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sA = reinterpret_cast<bf16*>(smem_raw);              // [STAGES][BM][BKP]
-  bf16* sB = sA + STAGES * BM * BKP;                         // [STAGES][BN][BKP]
+  t16* sA = reinterpret_cast<t16*>(smem_raw);              // [STAGES][BM][BKP]
+  t16* sB = sA + STAGES * BM * BKP;                         // [STAGES][BN][BKP]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
   const int row0 = tid >> 2;           // first tile row handled by this thread
 
   // per-thread A row bookkeeping (fixed across k)
-  const bf16* a_base[A_ITERS];
+  const t16* a_base[A_ITERS];
   int a_iy0[A_ITERS], a_ix0[A_ITERS];
   bool a_ok[A_ITERS];
 #pragma unroll
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
       a_base[j] = p.A + (long long)(a_ok[j] ? m : 0) * p.lda;
     }
   }
-  const bf16* b_base[B_ITERS];
+  const t16* b_base[B_ITERS];
   bool b_ok[B_ITERS];
 #pragma unroll
   for (int j = 0; j < B_ITERS; ++j) {
@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
     }
 #pragma unroll
     for (int j = 0; j < A_ITERS; ++j) {
-      bf16* dst = sA + ((stage * BM) + row0 + j * (NT / 4)) * BKP + vec * 8;
-      const bf16* src = p.A;
+      t16* dst = sA + ((stage * BM) + row0 + j * (NT / 4)) * BKP + vec * 8;
+      const t16* src = p.A;
       bool ok = a_ok[j] && k_ok;
       if (p.conv) {
         int iy = a_iy0[j] + ky, ix = a_ix0[j] + kx;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
     }
 #pragma unroll
     for (int j = 0; j < B_ITERS; ++j) {
-      bf16* dst = sB + ((stage * BN) + row0 + j * (NT / 4)) * BKP + vec * 8;
+      t16* dst = sB + ((stage * BN) + row0 + j * (NT / 4)) * BKP + vec * 8;
       bool ok = b_ok[j] && k_ok;
       cp_async16(dst, ok ? (b_base[j] + k) : p.B, ok ? 16 : 0);
     }
@@ -134,25 +134,25 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
       cp_async_commit();
     }
     const int stage = kt % STAGES;
-    const bf16* tA = sA + stage * BM * BKP;
-    const bf16* tB = sB + stage * BN * BKP;
+    const t16* tA = sA + stage * BM * BKP;
+    const t16* tB = sB + stage * BN * BKP;
 #pragma unroll
     for (int ks = 0; ks < BK / 16; ++ks) {
       uint32_t af[MI][4], bfr[NI][2];
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
-        const bf16* ptr = tA + (wm * WM + i * 16 + (lane & 15)) * BKP + ks * 16 + (lane >> 4) * 8;
+        const t16* ptr = tA + (wm * WM + i * 16 + (lane & 15)) * BKP + ks * 16 + (lane >> 4) * 8;
         ldmatrix_x4(af[i][0], af[i][1], af[i][2], af[i][3], ptr);
       }
 #pragma unroll
       for (int j = 0; j < NI; j += 2) {
-        const bf16* ptr = tB + (wn * WN + j * 8 + (lane & 7) + (lane >> 4) * 8) * BKP + ks * 16 + ((lane >> 3) & 1) * 8;
+        const t16* ptr = tB + (wn * WN + j * 8 + (lane & 7) + (lane >> 4) * 8) * BKP + ks * 16 + ((lane >> 3) & 1) * 8;
         ldmatrix_x4(bfr[j][0], bfr[j][1], bfr[j + 1][0], bfr[j + 1][1], ptr);
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NI; ++j) mma_bf16(acc[i][j], af[i], bfr[j]);
+        for (int j = 0; j < NI; ++j) mma_t16(acc[i][j], af[i], bfr[j]);
     }
   }
   cp_async_wait<0>();
@@ -178,9 +178,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
           if (two) v1 += p.bias[n + 1];
         }
         if (p.res) {
-          const bf16* r = p.res + (long long)m * p.ldr + n;
-          v0 += __bfloat162float(r[0]);
-          if (two) v1 += __bfloat162float(r[1]);
+          const t16* r = p.res + (long long)m * p.ldr + n;
+          v0 += t2f(r[0]);
+          if (two) v1 += t2f(r[1]);
         }
         if (p.act == ACT_RELU) {
           if (n >= p.act_from) v0 = fmaxf(v0, 0.f);
@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
           if (n + 1 >= p.act_from) v1 = silu_f(v1);
         }
         if (p.gate) {
-          const bf16* gp = p.gate + (long long)m * p.ldg + n;
-          v0 *= __bfloat162float(gp[0]);
-          if (two) v1 *= __bfloat162float(gp[1]);
+          const t16* gp = p.gate + (long long)m * p.ldg + n;
+          v0 *= t2f(gp[0]);
+          if (two) v1 *= t2f(gp[1]);
         }
         // destination (n and n+1 never straddle n_split: n is even, n_split is even)
         void* base = p.C;
@@ -210,12 +210,12 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
           o[0] = v0;
           if (two) o[1] = v1;
         } else {
-          bf16* o = reinterpret_cast<bf16*>(base) + (long long)m * ld + nn;
+          t16* o = reinterpret_cast<t16*>(base) + (long long)m * ld + nn;
           if (two && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
-            *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
+            *reinterpret_cast<uint32_t*>(o) = pack2(v0, v1);
           } else {
-            o[0] = __float2bfloat16(v0);
-            if (two) o[1] = __float2bfloat16(v1);
+            o[0] = f2t(v0);
+            if (two) o[1] = f2t(v1);
           }
         }
       }
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
 
 template <int BM, int BN, int WARPS_M, int WARPS_N>
 int launch_cfg(const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (BM + BN) * BKP * (int)sizeof(bf16);
+  constexpr int smem = STAGES * (BM + BN) * BKP * (int)sizeof(t16);
   static bool attr_done = false;
   if (!attr_done) {
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BM, BN, WARPS_M, WARPS_N>,

@@ -1,4 +1,4 @@
-// Generic bf16 GEMM / implicit-GEMM convolution with a fused epilogue.
+// Generic t16 GEMM / implicit-GEMM convolution with a fused epilogue.
 //   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )
 // A is either a row-major matrix (linear mode) or an NHWC activation map gathered on the fly
 // (conv mode, K ordered (ky,kx,ci)); B is always the [N,K] row-major weight (K-major both sides).
@@ -10,9 +10,9 @@
 namespace rmem {
 
 struct GemmParams {
-  const bf16* A = nullptr;
+  const t16* A = nullptr;
   long long lda = 0;
-  const bf16* B = nullptr;
+  const t16* B = nullptr;
   long long ldb = 0;
   int M = 0, N = 0, K = 0;
   // conv mode (A = NHWC [Hin,Win,Cin]); output pixel m -> (m / Wout, m % Wout)
@@ -23,9 +23,9 @@ struct GemmParams {
   int bias_m = 0;
   int act = ACT_NONE;           // applied to columns >= act_from
   int act_from = 0;
-  const bf16* res = nullptr;    // added before the activation
+  const t16* res = nullptr;    // added before the activation
   long long ldr = 0;
-  const bf16* gate = nullptr;   // multiplied after the activation
+  const t16* gate = nullptr;   // multiplied after the activation
   long long ldg = 0;
   int accumulate = 0;           // C += (fp32 outputs only)
   void* C = nullptr;

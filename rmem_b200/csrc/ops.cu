@@ -7,27 +7,27 @@ namespace rmem {
 
 namespace {
 
-__device__ __forceinline__ void load8(const bf16* p, float* v) {
+__device__ __forceinline__ void load8(const t16* p, float* v) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
-__device__ __forceinline__ void store8(bf16* p, const float* v) {
+__device__ __forceinline__ void store8(t16* p, const float* v) {
   uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]);
+  u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_image_kernel(const float* __restrict__ img, bf16* __restrict__ out, int HW) {
+__global__ void pack_image_kernel(const float* __restrict__ img, t16* __restrict__ out, int HW) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   float v[8] = {img[i], img[HW + i], img[2 * HW + i], 0.f, 0.f, 0.f, 0.f, 0.f};
   store8(out + (size_t)i * 8, v);
 }
 
-__global__ void maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int Hin, int Win, int C, int Hout,
+__global__ void maxpool_kernel(const t16* __restrict__ x, t16* __restrict__ y, int Hin, int Win, int C, int Hout,
                                int Wout) {
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,8 +56,8 @@ __global__ void maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 // LayerNorm: one warp per row, two-pass statistics in registers.
 constexpr int LN_MAXV = 16;  // C <= 512
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, bf16* __restrict__ y, long long ldy,
-                                 bf16* __restrict__ y2, long long ldy2, int P, int C) {
+                                 const float* __restrict__ beta, t16* __restrict__ y, long long ldy,
+                                 t16* __restrict__ y2, long long ldy2, int P, int C) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -78,7 +78,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
   for (int j = 0; j < LN_MAXV; ++j)
     if (j < nv) {
       int c = j * 32 + lane;
-      bf16 o = __float2bfloat16((v[j] - mean) * rstd * gamma[c] + beta[c]);
+      t16 o = f2t((v[j] - mean) * rstd * gamma[c] + beta[c]);
       y[(long long)row * ldy + c] = o;
       if (y2) y2[(long long)row * ldy2 + c] = o;
     }
@@ -89,7 +89,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
 template <typename T>
 __device__ __forceinline__ void gn_load8(const T* p, float* v);
 template <>
-__device__ __forceinline__ void gn_load8<bf16>(const bf16* p, float* v) { load8(p, v); }
+__device__ __forceinline__ void gn_load8<t16>(const t16* p, float* v) { load8(p, v); }
 template <>
 __device__ __forceinline__ void gn_load8<float>(const float* p, float* v) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -144,7 +144,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, do
 
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, bf16* __restrict__ y, int P, int C, int G, int relu,
+                                const float* __restrict__ beta, t16* __restrict__ y, int P, int C, int G, int relu,
                                 const double* __restrict__ stats) {
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +170,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict
 constexpr int kGnMaxBlocks = 148 * 4;
 
 template <typename T>
-int groupnorm_impl(const T* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                    double* stats, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0 && G <= 32 && C % G == 0 && (C / G) % 8 == 0 && 256 % (C / 8) == 0,
                "groupnorm: unsupported C=%d G=%d", C, G);
@@ -186,7 +186,7 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, bf16* y, i
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void dwconv5_kernel(const bf16* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int h,
+__global__ void dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w, t16* __restrict__ y, int h,
                                int wd, int C) {
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,7 +217,7 @@ __global__ void dwconv5_kernel(const bf16* __restrict__ x, const float* __restri
 // align_corners=True source coordinate, as ATen's area_pixel_compute_source_index.
 __device__ __forceinline__ void src_index(int dst, int in_size, int out_size, int& i0, int& i1, float& l0, float& l1) {
   if (in_size == out_size) { i0 = i1 = dst; l0 = 1.f; l1 = 0.f; return; }
-  float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  float scale = out_size > 1 ? __fdiv_rn((float)(in_size - 1), (float)(out_size - 1)) : 0.f;  // exact: --use_fast_math
   float real = __fmul_rn(scale, (float)dst);
   i0 = min((int)real, in_size - 1);
   float lam = fminf(fmaxf(__fsub_rn(real, (float)i0), 0.f), 1.f);
@@ -232,7 +232,7 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
   return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
 }
 
-__global__ void upsample_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int hin, int win, int hout,
+__global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__ y, int hin, int win, int hout,
                                      int wout, int C) {
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,11 +254,11 @@ __global__ void upsample_bf16_kernel(const bf16* __restrict__ x, bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv_out: one warp per pixel, Cin <= 256, Cout <= 16.  Weights bf16 [Cout, Cin].
-__global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ b,
+// conv_out: one warp per pixel, Cin <= 256, Cout <= 16.  Weights t16 [Cout, Cin].
+__global__ void conv_out_kernel(const t16* __restrict__ x, const t16* __restrict__ w, const float* __restrict__ b,
                                 float* __restrict__ out, int P, int Cin, int Cout) {
   extern __shared__ float sw[];  // [Cout][Cin]
-  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = t2f(w[i]);
   __syncthreads();
   int lane = threadIdx.x & 31;
   int warps = blockDim.x >> 5;
@@ -267,7 +267,7 @@ __global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restri
     const int nv = Cin / 32;  // <= 8
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (j < nv) xv[j] = __bfloat162float(x[(size_t)p * Cin + j * 32 + lane]);
+      if (j < nv) xv[j] = t2f(x[(size_t)p * Cin + j * 32 + lane]);
     for (int o = 0; o < Cout; ++o) {
       float s = 0.f;
 #pragma unroll
@@ -280,13 +280,13 @@ __global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void transpose_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy, int P,
+__global__ void transpose_kernel(const t16* __restrict__ x, long long ldx, t16* __restrict__ y, long long ldy, int P,
                                  int C) {
-  __shared__ bf16 tile[64][66];
+  __shared__ t16 tile[64][66];
   int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   for (int i = threadIdx.y; i < 64; i += blockDim.y) {
     int p = p0 + i, c = c0 + threadIdx.x * 2;
-    bf16 a = __float2bfloat16(0.f), b = a;
+    t16 a = f2t(0.f), b = a;
     if (p < P && c < C) {
       a = x[(long long)p * ldx + c];
       if (c + 1 < C) b = x[(long long)p * ldx + c + 1];
@@ -304,7 +304,7 @@ __global__ void transpose_kernel(const bf16* __restrict__ x, long long ldx, bf16
   }
 }
 
-__global__ void copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd, int P,
+__global__ void copy2d_kernel(const t16* __restrict__ src, long long lds, t16* __restrict__ dst, long long ldd, int P,
                               int C) {
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,10 +313,10 @@ __global__ void copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16*
   long long r = i / cv;
   *reinterpret_cast<uint4*>(dst + r * ldd + c8 * 8) = *reinterpret_cast<const uint4*>(src + r * lds + c8 * 8);
 }
-__global__ void fill_kernel(bf16* __restrict__ dst, long long ldd, int P, int C, float v) {
+__global__ void fill_kernel(t16* __restrict__ dst, long long ldd, int P, int C, float v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * C) return;
-  dst[(i / C) * ldd + (i % C)] = __float2bfloat16(v);
+  dst[(i / C) * ldd + (i % C)] = f2t(v);
 }
 
 __global__ void separate_label_kernel(const void* __restrict__ label, int is_f32, uint8_t* __restrict__ out, int n,
@@ -335,7 +335,7 @@ __global__ void separate_label_kernel(const void* __restrict__ label, int is_f32
 // ID bank: one block per token, one thread per output channel.
 __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, int use_ignore,
                               const float* __restrict__ wp, const float* __restrict__ bias,
-                              const float* __restrict__ ln_g, const float* __restrict__ ln_b, bf16* __restrict__ out,
+                              const float* __restrict__ ln_g, const float* __restrict__ ln_b, t16* __restrict__ out,
                               long long ldo, float* __restrict__ out_f32, int w, int C) {
   __shared__ int8_t ch[17 * 17];
   __shared__ float red[32];
@@ -370,7 +370,7 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
     o = d * rsqrtf(var + 1e-5f) * (c < C ? ln_g[c] : 0.f) + (c < C ? ln_b[c] : 0.f);
   }
   if (c < C) {
-    if (out) out[(long long)tok * ldo + c] = __float2bfloat16(o);
+    if (out) out[(long long)tok * ldo + c] = f2t(o);
     if (out_f32) out_f32[(long long)tok * C + c] = o;
   }
 }
@@ -492,8 +492,8 @@ __global__ void evict_rel_kernel(const float* __restrict__ mass, int T, const fl
 
 // ------------------------------------------------------------------------------------------------
 struct PeSlots { int s[16]; };
-__global__ void qprep_kernel(const bf16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
-                             const float* __restrict__ pe_mem, PeSlots ps, int T, float scale, bf16* __restrict__ qt,
+__global__ void qprep_kernel(const t16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
+                             const float* __restrict__ pe_mem, PeSlots ps, int T, float scale, t16* __restrict__ qt,
                              float* __restrict__ qbias, int P, int C) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
@@ -504,10 +504,10 @@ __global__ void qprep_kernel(const bf16* __restrict__ q, long long ldq, const fl
   for (int j = 0; j < 8; ++j)
     if (j < nv) {
       int c = j * 32 + lane;
-      float x = __bfloat162float(q[(long long)row * ldq + c]) + (pe_cur ? pe_cur[c] : 0.f);
-      bf16 r = __float2bfloat16(x);
+      float x = t2f(q[(long long)row * ldq + c]) + (pe_cur ? pe_cur[c] : 0.f);
+      t16 r = f2t(x);
       qt[(long long)row * C + c] = r;
-      v[j] = __bfloat162float(r);
+      v[j] = t2f(r);
     }
   for (int t = 0; t < T; ++t) {
     float s = 0.f;
@@ -522,13 +522,13 @@ __global__ void qprep_kernel(const bf16* __restrict__ q, long long ldq, const fl
 }  // namespace
 
 // ================================================================================================
-int pack_image(const float* img, bf16* out, int H, int W, cudaStream_t s) {
+int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s) {
   pack_image_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(img, out, H * W);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
-int maxpool3x3s2(const bf16* x, bf16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s) {
+int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
   long long n = (long long)Hout * Wout * (C / 8);
   maxpool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, Hin, Win, C, Hout, Wout);
@@ -536,7 +536,7 @@ int maxpool3x3s2(const bf16* x, bf16* y, int Hin, int Win, int C, int Hout, int 
   return RMEM_OK;
 }
 
-int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, bf16* y, long long ldy, bf16* y2,
+int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy, t16* y2,
               long long ldy2, int P, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm: unsupported C=%d", C);
   layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(x, ldx, gamma, beta, y, ldy, y2, ldy2, P, C);
@@ -544,16 +544,16 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
   return RMEM_OK;
 }
 
-int groupnorm_bf16(const bf16* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                    double* stats, cudaStream_t s) {
-  return groupnorm_impl<bf16>(x, gamma, beta, y, P, C, G, relu, stats, s);
+  return groupnorm_impl<t16>(x, gamma, beta, y, P, C, G, relu, stats, s);
 }
-int groupnorm_f32(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s) {
   return groupnorm_impl<float>(x, gamma, beta, y, P, C, G, relu, stats, s);
 }
 
-int dwconv5x5(const bf16* x, const float* w, bf16* y, int h, int wd, int C, cudaStream_t s) {
+int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "dwconv: C %% 8");
   long long n = (long long)h * wd * (C / 8);
   dwconv5_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, w, y, h, wd, C);
@@ -561,15 +561,15 @@ int dwconv5x5(const bf16* x, const float* w, bf16* y, int h, int wd, int C, cuda
   return RMEM_OK;
 }
 
-int upsample_bilinear_bf16(const bf16* x, bf16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s) {
+int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "upsample: C %% 8");
   long long n = (long long)hout * wout * (C / 8);
-  upsample_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, hin, win, hout, wout, C);
+  upsample_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, hin, win, hout, wout, C);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
-int conv_out_logits(const bf16* x, const bf16* w, const float* b, float* out, int P, int Cin, int Cout,
+int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int P, int Cin, int Cout,
                     cudaStream_t s) {
   RMEM_REQUIRE(Cin % 32 == 0 && Cin <= 256 && Cout <= 16, "conv_out: unsupported Cin=%d Cout=%d", Cin, Cout);
   int grid = min(cdiv(P, 8), 148 * 8);
@@ -578,21 +578,21 @@ int conv_out_logits(const bf16* x, const bf16* w, const float* b, float* out, in
   return RMEM_OK;
 }
 
-int transpose_bf16(const bf16* x, long long ldx, bf16* y, long long ldy, int P, int C, cudaStream_t s) {
+int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s) {
   dim3 grid(cdiv(P, 64), cdiv(C, 64)), block(32, 8);
   transpose_kernel<<<grid, block, 0, s>>>(x, ldx, y, ldy, P, C);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
-int copy2d_bf16(const bf16* src, long long lds, bf16* dst, long long ldd, int P, int C, cudaStream_t s) {
+int copy2d_t16(const t16* src, long long lds, t16* dst, long long ldd, int P, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "copy2d: alignment");
   long long n = (long long)P * (C / 8);
   copy2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, lds, dst, ldd, P, C);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
-int fill_bf16(bf16* dst, long long ldd, int P, int C, float v, cudaStream_t s) {
+int fill_t16(t16* dst, long long ldd, int P, int C, float v, cudaStream_t s) {
   long long n = (long long)P * C;
   fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ldd, P, C, v);
   RMEM_LAUNCH_CHECK();
@@ -607,7 +607,7 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 }
 
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
-                 const float* ln_g, const float* ln_b, bf16* out, long long ldo, float* out_f32, int h, int w, int C,
+                 const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
                  cudaStream_t s) {
   RMEM_REQUIRE(C <= 256 && C % 32 == 0, "idbank: unsupported C=%d", C);
   idbank_kernel<<<h * w, 256, 0, s>>>(label, H, W, use_ignore, w_packed, bias, ln_g, ln_b, out, ldo, out_f32, w, C);
@@ -647,8 +647,8 @@ void temporal_pe_slots(int T, int n_slots, int* out) {
   }
 }
 
-int qprep(const bf16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
-          float scale, bf16* qt, float* qbias, int P, int C, cudaStream_t s) {
+int qprep(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+          float scale, t16* qt, float* qbias, int P, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 256, "qprep: unsupported C=%d", C);
   RMEM_REQUIRE(T >= 0 && T <= 16, "qprep: T=%d", T);
   PeSlots ps;

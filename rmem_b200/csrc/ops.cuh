@@ -5,48 +5,48 @@
 
 namespace rmem {
 
-// img NCHW fp32 [3,H,W] -> NHWC bf16 [H,W,8] (channels 3..7 zero).              (encoder input)
-int pack_image(const float* img, bf16* out, int H, int W, cudaStream_t s);
+// img NCHW fp32 [3,H,W] -> NHWC t16 [H,W,8] (channels 3..7 zero).              (encoder input)
+int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s);
 
-// 3x3 stride-2 pad-1 max pooling on NHWC bf16 (resnet.py:186).
-int maxpool3x3s2(const bf16* x, bf16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s);
+// 3x3 stride-2 pad-1 max pooling on NHWC t16 (resnet.py:186).
+int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s);
 
-// LayerNorm over C (eps 1e-5): x fp32 [P, ldx] -> y bf16 [P, ldy] (+ optional second copy y2).
-int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, bf16* y, long long ldy,
-              bf16* y2, long long ldy2, int P, int C, cudaStream_t s);
+// LayerNorm over C (eps 1e-5): x fp32 [P, ldx] -> y t16 [P, ldy] (+ optional second copy y2).
+int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy,
+              t16* y2, long long ldy2, int P, int C, cudaStream_t s);
 
 // GroupNorm over (pixels x C/G) per group, eps 1e-5, optional ReLU.  `stats` = kGnScratchDoubles doubles of
 // scratch whose element [64] (the block counter) must be zero before the first call; it re-arms itself.
 constexpr int kGnScratchDoubles = 72 + 148 * 4 * 64;
-int groupnorm_bf16(const bf16* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                    double* stats, cudaStream_t s);
-int groupnorm_f32(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, int G, int relu,
+int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s);
 
-// Depthwise 5x5 (pad 2) on a token-major map: x bf16 [h*w, C], w fp32 [25, C] -> y bf16.   (basic.py:38-59)
-int dwconv5x5(const bf16* x, const float* w, bf16* y, int h, int wd, int C, cudaStream_t s);
+// Depthwise 5x5 (pad 2) on a token-major map: x t16 [h*w, C], w fp32 [25, C] -> y t16.   (basic.py:38-59)
+int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s);
 
-// Bilinear resize, align_corners=True, NHWC bf16.                                         (fpn.py:50,58)
-int upsample_bilinear_bf16(const bf16* x, bf16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s);
+// Bilinear resize, align_corners=True, NHWC t16.                                         (fpn.py:50,58)
+int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s);
 
 // 1x1 conv to the 11 ID logits, planar fp32 output [11, P].                                (fpn.py:66)
-int conv_out_logits(const bf16* x, const bf16* w, const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
+int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
 
 // [P, C] (row stride ldx) -> [C, ldy] transposed copy.
-int transpose_bf16(const bf16* x, long long ldx, bf16* y, long long ldy, int P, int C, cudaStream_t s);
+int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s);
 
-// dst[p, 0:C] = src[p, 0:C] with independent row strides (bf16).
-int copy2d_bf16(const bf16* src, long long lds, bf16* dst, long long ldd, int P, int C, cudaStream_t s);
-int fill_bf16(bf16* dst, long long ldd, int P, int C, float v, cudaStream_t s);
+// dst[p, 0:C] = src[p, 0:C] with independent row strides (t16).
+int copy2d_t16(const t16* src, long long lds, t16* dst, long long ldd, int P, int C, cudaStream_t s);
+int fill_t16(t16* dst, long long ldd, int P, int C, float v, cudaStream_t s);
 
 // Per-engine label map (aot_engine.py:604-618): label fp32/uint8 [H,W] -> uint8 [H,W].
 int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int W, int engine, int n_engines,
                    cudaStream_t s);
 
 // ID bank (aot.py:111-114, deaot.py:65-69): gather-sum of Conv2d(12->C,k17,s16,p8) weight slices indexed by the
-// label, + bias, optional LayerNorm.  w_packed fp32 [17*17][12][C].  out bf16 [h*w, ldo].
+// label, + bias, optional LayerNorm.  w_packed fp32 [17*17][12][C].  out t16 [h*w, ldo].
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
-                 const float* ln_g, const float* ln_b, bf16* out, long long ldo, float* out_f32, int h, int w, int C,
+                 const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
                  cudaStream_t s);
 
 // Mask head (aot_engine.py:457-463, 650-673; evaluator.py:430-441): k engines' planar logits [11,h4,w4] ->
@@ -59,10 +59,10 @@ int mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo
 int evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel,
                     cudaStream_t s);
 
-// Qt = bf16(Q + pe_cur);  qbias[i,t] = scale * <Qt_i, pe_mem[t]>        (temporal PE as a score bias, K8)
+// Qt = t16(Q + pe_cur);  qbias[i,t] = scale * <Qt_i, pe_mem[t]>        (temporal PE as a score bias, K8)
 // pe_mem = mem_pos_emb [n_slots, C]; pe_slot[t] = slot used by memory frame t (temporal_pe_slots).
-int qprep(const bf16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
-          float scale, bf16* qt, float* qbias, int P, int C, cudaStream_t s);
+int qprep(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+          float scale, t16* qt, float* qbias, int P, int C, cudaStream_t s);
 // transformer.py:1140-1170: identity for T <= n_slots, flip -> nearest -> flip above.
 void temporal_pe_slots(int T, int n_slots, int* out);
 

@@ -22,7 +22,7 @@ ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 
 
 def _bf(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).contiguous()
+    return t.to(_capi.op_dtype()).contiguous()
 
 
 def round_up(a: int, b: int) -> int:
@@ -37,12 +37,12 @@ def gemm(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     lib = _capi.load()
     M, K = A.shape
     N = B.shape[0]
-    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and B.shape[1] == K
+    assert A.dtype == _capi.op_dtype() and B.dtype == _capi.op_dtype() and B.shape[1] == K
     if accumulate_into is not None:
         out = accumulate_into
         assert out.dtype == torch.float32
     else:
-        out = torch.empty(M, N, dtype=torch.float32 if out_f32 else torch.bfloat16, device=A.device)
+        out = torch.empty(M, N, dtype=torch.float32 if out_f32 else _capi.op_dtype(), device=A.device)
     d = _capi.GemmDesc()
     d.A, d.lda, d.B, d.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
     d.M, d.N, d.K = M, N, K
@@ -63,12 +63,12 @@ def gemm(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, act: int = ACT_NONE,
                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x bf16 [Hin,Win,Cin]; w bf16 [Cout,kh,kw,Cin] -> bf16 [Hout,Wout,Cout]."""
+    """x t16 [Hin,Win,Cin]; w t16 [Cout,kh,kw,Cin] -> t16 [Hout,Wout,Cout]."""
     lib = _capi.load()
     Hin, Win, Cin = x.shape
     Cout, kh, kw, _ = w.shape
     Hout, Wout = (Hin + 2 * pad - kh) // stride + 1, (Win + 2 * pad - kw) // stride + 1
-    out = torch.empty(Hout, Wout, Cout, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(Hout, Wout, Cout, dtype=_capi.op_dtype(), device=x.device)
     d = _capi.GemmDesc()
     d.A, d.B, d.ldb = x.data_ptr(), w.data_ptr(), kh * kw * Cin
     d.M, d.N, d.K = Hout * Wout, Cout, kh * kw * Cin
@@ -87,7 +87,7 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: in
 def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = _capi.load()
     P, Cc = x.shape
-    y = torch.empty(P, Cc, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(P, Cc, dtype=_capi.op_dtype(), device=x.device)
     _capi.check(lib.rmem_layernorm_fwd(_capi.ptr(x), C.c_longlong(x.stride(0)), _capi.ptr(g), _capi.ptr(b),
                                        _capi.ptr(y), C.c_longlong(Cc), P, Cc, _capi.stream_ptr()))
     return y
@@ -96,7 +96,7 @@ def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> torch.Tensor
 def groupnorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, groups: int, relu: bool) -> torch.Tensor:
     lib = _capi.load()
     P, Cc = x.shape
-    y = torch.empty(P, Cc, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(P, Cc, dtype=_capi.op_dtype(), device=x.device)
     stats = torch.zeros(72 + 148 * 4 * 64, dtype=torch.float64, device=x.device)
     _capi.check(lib.rmem_groupnorm_fwd(_capi.ptr(x), int(x.dtype == torch.float32), _capi.ptr(g), _capi.ptr(b),
                                        _capi.ptr(y), P, Cc, groups, int(relu), _capi.ptr(stats), _capi.stream_ptr()))
@@ -114,7 +114,7 @@ def dwconv5x5(x: torch.Tensor, w25: torch.Tensor, h: int, w: int) -> torch.Tenso
 def upsample_bilinear(x: torch.Tensor, hout: int, wout: int) -> torch.Tensor:
     lib = _capi.load()
     hin, win, Cc = x.shape
-    y = torch.empty(hout, wout, Cc, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(hout, wout, Cc, dtype=_capi.op_dtype(), device=x.device)
     _capi.check(lib.rmem_upsample_bilinear_fwd(_capi.ptr(x), _capi.ptr(y), hin, win, hout, wout, Cc,
                                                _capi.stream_ptr()))
     return y
@@ -124,7 +124,7 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     lib = _capi.load()
     Hin, Win, Cc = x.shape
     Hout, Wout = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
-    y = torch.empty(Hout, Wout, Cc, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(Hout, Wout, Cc, dtype=_capi.op_dtype(), device=x.device)
     _capi.check(lib.rmem_maxpool3x3s2_fwd(_capi.ptr(x), _capi.ptr(y), Hin, Win, Cc, Hout, Wout, _capi.stream_ptr()))
     return y
 
@@ -132,7 +132,7 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
 def transpose(x: torch.Tensor, ldy: int) -> torch.Tensor:
     lib = _capi.load()
     P, Cc = x.shape
-    y = torch.zeros(Cc, ldy, dtype=torch.bfloat16, device=x.device)
+    y = torch.zeros(Cc, ldy, dtype=_capi.op_dtype(), device=x.device)
     _capi.check(lib.rmem_transpose_fwd(_capi.ptr(x), C.c_longlong(x.stride(0)), _capi.ptr(y), C.c_longlong(ldy), P, Cc,
                                        _capi.stream_ptr()))
     return y
@@ -204,16 +204,16 @@ def temporal_pe_slots(T: int, n_slots: int = 4) -> List[int]:
 
 def build_bank(k_frames: torch.Tensor, v_frames: torch.Tensor, nslots: int, slots: Sequence[int]):
     """Lay T frames out the way the engine's ring bank does.  k [T,HW,Dk], v [T,HW,Dv] (any float dtype) ->
-    (kbank bf16 [nslots,HWp,Dk], vtbank bf16 [Dv, nslots*HWp], HWp)."""
+    (kbank t16 [nslots,HWp,Dk], vtbank t16 [Dv, nslots*HWp], HWp)."""
     T, HW, Dk = k_frames.shape
     Dv = v_frames.shape[-1]
     HWp = round_up(HW, 128)
     dev = k_frames.device
-    kbank = torch.zeros(nslots, HWp, Dk, dtype=torch.bfloat16, device=dev)
-    vtbank = torch.zeros(Dv, nslots * HWp, dtype=torch.bfloat16, device=dev)
+    kbank = torch.zeros(nslots, HWp, Dk, dtype=_capi.op_dtype(), device=dev)
+    vtbank = torch.zeros(Dv, nslots * HWp, dtype=_capi.op_dtype(), device=dev)
     lib = _capi.load()
     for t, s in enumerate(slots):
-        kbank[s, :HW] = k_frames[t].to(torch.bfloat16)
+        kbank[s, :HW] = k_frames[t].to(_capi.op_dtype())
         vt = _bf(v_frames[t])
         _capi.check(lib.rmem_transpose_fwd(_capi.ptr(vt), C.c_longlong(Dv), C.c_void_p(vtbank.data_ptr() + 2 * s * HWp),
                                            C.c_longlong(nslots * HWp), HW, Dv, _capi.stream_ptr()))
@@ -224,14 +224,14 @@ def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, s
                    pe_cur: Optional[torch.Tensor] = None, mem_pos_emb: Optional[torch.Tensor] = None,
                    gate: Optional[torch.Tensor] = None, impl: int = _capi.ATTN_DENSE,
                    want_mass: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """q bf16 [HW,Dk] (no PE, unscaled).  Returns (out bf16 [HW,Dv], mass fp32 [HW,T])."""
+    """q t16 [HW,Dk] (no PE, unscaled).  Returns (out t16 [HW,Dv], mass fp32 [HW,T])."""
     lib = _capi.load()
     nslots, HWp, Dk = kbank.shape
     Dv = vtbank.shape[0]
     T = len(slots)
     dev = q.device
     scale = 1.0 / math.sqrt(Dk)
-    qt = torch.empty(HW, Dk, dtype=torch.bfloat16, device=dev)
+    qt = torch.empty(HW, Dk, dtype=_capi.op_dtype(), device=dev)
     qbias = torch.zeros(HW, max(T, 1), dtype=torch.float32, device=dev)
     if mem_pos_emb is not None:
         pes = (C.c_int * T)(*temporal_pe_slots(T, mem_pos_emb.shape[0]))
@@ -243,7 +243,7 @@ def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, s
     nbytes = C.c_size_t()
     _capi.check(lib.rmem_long_attn_workspace_bytes(impl, HW, HWp, nslots, Dv, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-    out = torch.empty(HW, Dv, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(HW, Dv, dtype=_capi.op_dtype(), device=dev)
     mass = torch.empty(HW, T, dtype=torch.float32, device=dev) if want_mass else None
     sl = (C.c_int * T)(*slots)
     _capi.check(lib.rmem_long_attn_fwd(impl, _capi.ptr(qt), _capi.ptr(qbias) if mem_pos_emb is not None else None,
@@ -256,16 +256,16 @@ def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, s
 
 def local_attention(q: torch.Tensor, k_prev: torch.Tensor, v_prev: torch.Tensor, rel_w: torch.Tensor,
                     rel_b: torch.Tensor, h: int, w: int, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q,k bf16 [HW,128]; v bf16 [HW,Dv]; rel_w fp32/bf16 [225,128]; rel_b [225] -> bf16 [HW,Dv]."""
+    """q,k t16 [HW,128]; v t16 [HW,Dv]; rel_w fp32/t16 [225,128]; rel_b [225] -> t16 [HW,Dv]."""
     lib = _capi.load()
     HW, Dk = q.shape
     Dv = v_prev.shape[1]
-    wpad = torch.zeros(256, Dk, dtype=torch.bfloat16, device=q.device)
-    wpad[:225] = rel_w.to(torch.bfloat16)
+    wpad = torch.zeros(256, Dk, dtype=_capi.op_dtype(), device=q.device)
+    wpad[:225] = rel_w.to(_capi.op_dtype())
     bpad = torch.zeros(256, dtype=torch.float32, device=q.device)
     bpad[:225] = rel_b.float()
     rel = gemm(q, wpad, bpad, out_f32=True)
-    out = torch.empty(HW, Dv, dtype=torch.bfloat16, device=q.device)
+    out = torch.empty(HW, Dv, dtype=_capi.op_dtype(), device=q.device)
     _capi.check(lib.rmem_local_attn_fwd(_capi.ptr(q), C.c_longlong(q.stride(0)), _capi.ptr(k_prev),
                                         C.c_longlong(k_prev.stride(0)), _capi.ptr(v_prev),
                                         C.c_longlong(v_prev.stride(0)), _capi.ptr(rel), C.c_longlong(256),

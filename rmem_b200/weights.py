@@ -1,7 +1,7 @@
 """Pack a reference `state_dict` (DeAOT, key names of networks/models/deaot.py -- SURVEY.md section 8b) into
 the flat device blob the C++ engine reads: FrozenBatchNorm2d folded into the conv weights
 (networks/layers/normalization.py:19-43), conv weights re-ordered to [Cout, ky, kx, Cin] (the K order of the
-implicit GEMM), GEMM operands in bf16, norm / bias / depthwise / positional parameters in fp32, the ID-bank
+implicit GEMM), GEMM operands in the 16-bit operand type (fp16 default), norm / bias / depthwise / positional parameters in fp32, the ID-bank
 conv (networks/models/aot.py:63-74) re-ordered to [17*17, 12, C] for the label-indexed gather.
 `module.` prefixes are stripped like utils/checkpoint.py:75-101 does.
 """
@@ -29,7 +29,7 @@ def _resnet_blocks():
 
 
 def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """name -> packed CPU tensor (bf16 or fp32, contiguous)."""
+    """name -> packed CPU tensor (t16 or fp32, contiguous)."""
     sd = {(k[7:] if k.startswith("module.") else k): v.detach().float().cpu() for k, v in sd.items()}
     out: Dict[str, torch.Tensor] = {}
 
@@ -40,12 +40,12 @@ def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         w = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1)             # [Cout, ky, kx, Cin]
         if cin_pad is not None and cin_pad > w.shape[-1]:
             w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
-        out[dst + ".w"] = w.contiguous().to(torch.bfloat16)
+        out[dst + ".w"] = w.contiguous().to(_capi.op_dtype())
         out[dst + ".b"] = b.contiguous()
 
     def conv(dst, src):
         w = sd[src + ".weight"].permute(0, 2, 3, 1)
-        out[dst + ".w"] = w.contiguous().to(torch.bfloat16)
+        out[dst + ".w"] = w.contiguous().to(_capi.op_dtype())
         out[dst + ".b"] = sd[src + ".bias"].contiguous()
 
     def linear(dst, src, pad_rows=None):
@@ -54,7 +54,7 @@ def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         if pad_rows is not None and pad_rows > w.shape[0]:
             w = torch.nn.functional.pad(w, (0, 0, 0, pad_rows - w.shape[0]))
             b = torch.nn.functional.pad(b, (0, pad_rows - b.shape[0]))
-        out[dst + ".w"] = w.contiguous().to(torch.bfloat16)
+        out[dst + ".w"] = w.contiguous().to(_capi.op_dtype())
         out[dst + ".b"] = b.contiguous()
 
     def norm(dst, src):

@@ -15,9 +15,11 @@ import torch  # noqa: E402
 from oracle import rmem_oracle as O  # noqa: E402
 from rmem_b200 import _capi, ops as K  # noqa: E402
 
+OP = _capi.op_dtype()
+
 
 def bfr(t):
-    return t.to(torch.bfloat16).float()
+    return t.to(OP).float()
 
 
 def relfro(a, b):
@@ -59,11 +61,11 @@ def main():
             ref = ref * gate
         kb, vtb, HWp = K.build_bank(k.to(dev), v.to(dev), nslots, slots)
         args = dict(pe_cur=pe_cur.to(dev) if use_pe else None, mem_pos_emb=pe_mem.to(dev) if use_pe else None,
-                    gate=gate.to(dev).bfloat16() if gate is not None else None)
+                    gate=gate.to(dev).to(OP) if gate is not None else None)
         rec = dict(case=name)
         try:
-            od, md = K.long_attention(q.to(dev).bfloat16(), kb, vtb, slots, HW, impl=_capi.ATTN_DENSE, **args)
-            ot, mt = K.long_attention(q.to(dev).bfloat16(), kb, vtb, slots, HW, impl=_capi.ATTN_TC, **args)
+            od, md = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=_capi.ATTN_DENSE, **args)
+            ot, mt = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=_capi.ATTN_TC, **args)
             torch.cuda.synchronize()
             rec.update(ok=True, tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
                        tc_vs_dense=relfro(ot, od), mass_err=float((mt.cpu() - ref_mass).abs().max()),

@@ -1,6 +1,6 @@
 """Parity of the fused tcgen05/TMA long-term attention kernel (rmem_b200/csrc/attn_tc.cu) against the CPU oracle
-and the dense CUDA path, through the C ABI.  Tolerance: rel-Frobenius <= 8e-3 on the attention output (bf16
-operands and bf16 P, fp32 accumulate), per-frame mass max-abs <= 2e-3."""
+and the dense CUDA path, through the C ABI.  Tolerance: rel-Frobenius <= 8e-3 on the attention output (16-bit
+operands and P, fp32 accumulate), per-frame mass max-abs <= 2e-3."""
 import json
 import os
 import subprocess

@@ -1,9 +1,9 @@
 """Op-level parity: every CUDA kernel on the path, called through the C ABI, against the CPU oracle
 (oracle/rmem_oracle.py, itself pinned to the reference) on the same seeded inputs.
 
-Tolerances: tensor-core operands are bf16 with fp32 accumulation, the oracle is fp32.  rel-Frobenius
-<= 6e-3 per op for GEMM-like ops (bf16 operand rounding 2^-9 on both operands and the bf16 output),
-integer / index outputs bit-exact.
+Tolerances: tensor-core operands are 16-bit (fp16 by default, 2^-11 rounding; bf16 build 2^-9) with fp32
+accumulation, the oracle is fp32 fed the same operand-rounded inputs.  rel-Frobenius <= 6e-3 per op for GEMM-like
+ops (covers the bf16 build too), integer / index outputs bit-exact.
 """
 import math
 
@@ -15,14 +15,18 @@ from oracle import rmem_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+from rmem_b200 import _capi  # noqa: E402
+
+OP = _capi.op_dtype()        # 16-bit tensor-core operand type of the build (fp16 default)
+
 
 def relfro(a, b):
     a, b = a.float().cpu(), b.float().cpu()
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def bfr(t):  # round to bf16 like the kernels' operands
-    return t.to(torch.bfloat16).float()
+def bfr(t):  # round to the kernels' 16-bit operand type
+    return t.to(OP).float()
 
 
 @pytest.fixture(scope="module")
@@ -38,16 +42,16 @@ def test_gemm_linear_epilogues(ops, cuda_device):
         W = torch.randn(N, K, generator=g) / math.sqrt(K)
         b = torch.randn(N, generator=g)
         ref = F.linear(bfr(A), bfr(W), b)
-        out = ops.gemm(A.to(cuda_device).bfloat16(), W.to(cuda_device).bfloat16(), b.to(cuda_device), out_f32=True)
+        out = ops.gemm(A.to(cuda_device).to(OP), W.to(cuda_device).to(OP), b.to(cuda_device), out_f32=True)
         assert relfro(out, ref) < 2e-5 * math.sqrt(K), (M, N, K)
         # silu from a column + bf16 output + gate + residual
         gate = torch.randn(M, N, generator=g)
         res = torch.randn(M, N, generator=g)
         ref2 = F.linear(bfr(A), bfr(W), b) + bfr(res)
         ref2 = torch.cat([ref2[:, : N // 2 // 2 * 2], O.silu(ref2[:, N // 2 // 2 * 2:])], 1) * bfr(gate)
-        out2 = ops.gemm(A.to(cuda_device).bfloat16(), W.to(cuda_device).bfloat16(), b.to(cuda_device),
-                        act=ops.ACT_SILU, act_from=N // 2 // 2 * 2, residual=res.to(cuda_device).bfloat16(),
-                        gate=gate.to(cuda_device).bfloat16())
+        out2 = ops.gemm(A.to(cuda_device).to(OP), W.to(cuda_device).to(OP), b.to(cuda_device),
+                        act=ops.ACT_SILU, act_from=N // 2 // 2 * 2, residual=res.to(cuda_device).to(OP),
+                        gate=gate.to(cuda_device).to(OP))
         assert relfro(out2, ref2) < 6e-3, (M, N, K)
 
 
@@ -58,12 +62,12 @@ def test_gemm_bias_along_m_and_accumulate(ops, cuda_device):
     Bm = torch.randn(N, K, generator=g)
     b = torch.randn(M, generator=g)
     ref = O.silu(bfr(A) @ bfr(Bm).t() + b[:, None])
-    out = ops.gemm(A.to(cuda_device).bfloat16(), Bm.to(cuda_device).bfloat16(), b.to(cuda_device), act=ops.ACT_SILU,
+    out = ops.gemm(A.to(cuda_device).to(OP), Bm.to(cuda_device).to(OP), b.to(cuda_device), act=ops.ACT_SILU,
                    bias_along_m=True, out_f32=True)
     assert relfro(out, ref) < 1e-3
     acc = torch.randn(M, N, generator=g)
     acc_d = acc.to(cuda_device).clone()
-    ops.gemm(A.to(cuda_device).bfloat16(), Bm.to(cuda_device).bfloat16(), None, accumulate_into=acc_d)
+    ops.gemm(A.to(cuda_device).to(OP), Bm.to(cuda_device).to(OP), None, accumulate_into=acc_d)
     assert relfro(acc_d, acc + bfr(A) @ bfr(Bm).t()) < 1e-4
 
 
@@ -76,8 +80,8 @@ def test_conv_implicit_gemm(ops, cuda_device, cfg):
     w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
     b = torch.randn(Cout, generator=g)
     ref = F.relu(F.conv2d(bfr(x), bfr(w), b, stride=s, padding=p))[0].permute(1, 2, 0)
-    out = ops.conv2d_nhwc(x[0].permute(1, 2, 0).contiguous().to(cuda_device).bfloat16(),
-                          w.permute(0, 2, 3, 1).contiguous().to(cuda_device).bfloat16(), b.to(cuda_device), s, p,
+    out = ops.conv2d_nhwc(x[0].permute(1, 2, 0).contiguous().to(cuda_device).to(OP),
+                          w.permute(0, 2, 3, 1).contiguous().to(cuda_device).to(OP), b.to(cuda_device), s, p,
                           act=ops.ACT_RELU)
     assert tuple(out.shape) == tuple(ref.shape)
     assert relfro(out, ref) < 6e-3
@@ -98,7 +102,7 @@ def test_layernorm_groupnorm(ops, cuda_device):
     x = bfr(torch.randn(61 * 107, 128, generator=g) + 0.1)
     gm, bt = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
     ref = F.relu(O.group_norm_tokens(x, gm, bt, 8))
-    out = ops.groupnorm(x.to(cuda_device).bfloat16(), gm.to(cuda_device), bt.to(cuda_device), 8, True)
+    out = ops.groupnorm(x.to(cuda_device).to(OP), gm.to(cuda_device), bt.to(cuda_device), 8, True)
     assert relfro(out, ref) < 4e-3
 
 
@@ -108,18 +112,18 @@ def test_dwconv_upsample_maxpool_transpose(ops, cuda_device):
     x = bfr(torch.randn(h * w, C, generator=g))
     wt = torch.randn(C, 1, 5, 5, generator=g) / 5
     ref = O.dwconv5(x, wt, h, w)
-    out = ops.dwconv5x5(x.to(cuda_device).bfloat16(), wt.view(C, 25).t().contiguous().to(cuda_device), h, w)
+    out = ops.dwconv5x5(x.to(cuda_device).to(OP), wt.view(C, 25).t().contiguous().to(cuda_device), h, w)
     assert relfro(out, ref) < 4e-3
     xm = bfr(torch.randn(1, 256, h, w, generator=g))
     ref = F.interpolate(xm, size=(61, 107), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
-    out = ops.upsample_bilinear(xm[0].permute(1, 2, 0).contiguous().to(cuda_device).bfloat16(), 61, 107)
+    out = ops.upsample_bilinear(xm[0].permute(1, 2, 0).contiguous().to(cuda_device).to(OP), 61, 107)
     assert relfro(out, ref) < 4e-3
     xp = bfr(torch.randn(1, 64, 65, 81, generator=g))
     ref = F.max_pool2d(xp, 3, 2, 1)[0].permute(1, 2, 0)
-    out = ops.maxpool3x3s2(xp[0].permute(1, 2, 0).contiguous().to(cuda_device).bfloat16())
+    out = ops.maxpool3x3s2(xp[0].permute(1, 2, 0).contiguous().to(cuda_device).to(OP))
     assert torch.equal(out.float().cpu(), ref)
     xt = bfr(torch.randn(1674, 1024, generator=g))
-    out = ops.transpose(xt.to(cuda_device).bfloat16(), 1792)
+    out = ops.transpose(xt.to(cuda_device).to(OP), 1792)
     assert torch.equal(out[:, :1674].float().cpu(), xt.t())
     assert float(out[:, 1674:].abs().max()) == 0.0
 
@@ -159,8 +163,8 @@ def test_long_attention_dense(ops, cuda_device, T, HW, slots):
     kt = k + O.temporal_pe(pe_mem, T).view(T, 1, -1)
     ref, ref_mass = O.long_term_attention(qt, kt, v, 128)
     kb, vtb, HWp = ops.build_bank(k.to(cuda_device), v.to(cuda_device), nslots, slots)
-    out, mass = ops.long_attention(q.to(cuda_device).bfloat16(), kb, vtb, slots, HW, pe_cur.to(cuda_device),
-                                   pe_mem.to(cuda_device), gate.to(cuda_device).bfloat16())
+    out, mass = ops.long_attention(q.to(cuda_device).to(OP), kb, vtb, slots, HW, pe_cur.to(cuda_device),
+                                   pe_mem.to(cuda_device), gate.to(cuda_device).to(OP))
     assert relfro(out, ref * gate) < 8e-3
     assert float((mass.cpu() - ref_mass).abs().max()) < 2e-3
     assert float((mass.sum(1).cpu() - 1).abs().max()) < 2e-3
@@ -183,9 +187,9 @@ def test_local_attention(ops, cuda_device):
         rb = torch.randn(225, generator=g) * 0.1
         gate = bfr(torch.randn(HW, 1024, generator=g))
         ref = O.local_attention(q, k, v, rw, rb, h, w) * gate
-        out = ops.local_attention(q.to(cuda_device).bfloat16(), k.to(cuda_device).bfloat16(),
-                                  v.to(cuda_device).bfloat16(), rw.to(cuda_device), rb.to(cuda_device), h, w,
-                                  gate.to(cuda_device).bfloat16())
+        out = ops.local_attention(q.to(cuda_device).to(OP), k.to(cuda_device).to(OP),
+                                  v.to(cuda_device).to(OP), rw.to(cuda_device), rb.to(cuda_device), h, w,
+                                  gate.to(cuda_device).to(OP))
         assert relfro(out, ref) < 6e-3, (h, w)
 
 
