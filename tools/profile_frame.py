@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Profiling driver for ncu: fills the c3 bank (T=8), then runs `--frames` steady-state propagated frames inside a
+cudaProfilerStart/Stop bracket so `ncu --profile-from-start off` sees only those launches.
+
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/launches.csv python tools/profile_frame.py --frames 5
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from rmem_b200 import _capi  # noqa: E402
+from rmem_b200.engine import DeAOTModel, RmemConfig, build_engine  # noqa: E402
+from rmem_b200.synth import make_state_dict, synthetic_frames, synthetic_label  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=5)
+    ap.add_argument("--H", type=int, default=481)
+    ap.add_argument("--W", type=int, default=849)
+    ap.add_argument("--objects", type=int, default=10)
+    ap.add_argument("--latter", type=int, default=7)
+    ap.add_argument("--gap", type=int, default=5)
+    ap.add_argument("--attn", default="tc", choices=["tc", "dense"])
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    sd = make_state_dict("r50_deaotl", seed=0, sharpen=4.0)
+    cfg = RmemConfig(former_mem_len=1, latter_mem_len=a.latter,
+                     attn_impl=_capi.ATTN_TC if a.attn == "tc" else _capi.ATTN_DENSE,
+                     max_engines=(a.objects + 9) // 10)
+    eng = build_engine("deaotengine", aot_model=DeAOTModel(sd, cfg, dev), long_term_mem_gap=1)
+    frames = synthetic_frames(4, a.H, a.W, seed=1000).to(dev)
+    label0 = synthetic_label(a.H, a.W, a.objects)
+    eng.add_reference_frame(frames[0:1], label0.int().to(dev), obj_nums=[a.objects], frame_step=0)
+    for i in range(1 + a.latter + 2):            # gap=1: the bank is full after `latter` frames
+        lab = eng.propagate_label(frames[1 + i % 3:2 + i % 3], output_size=(a.H, a.W))
+        eng.update_memory(lab)
+    eng.long_term_mem_gap = a.gap
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for i in range(a.frames):
+        lab = eng.propagate_label(frames[1 + i % 3:2 + i % 3], output_size=(a.H, a.W))
+        eng.update_memory(lab)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print("profiled frames:", a.frames, "bank:", eng.aot_engines[0].long_memories_indexes)
+
+
+if __name__ == "__main__":
+    main()
