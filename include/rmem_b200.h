@@ -26,7 +26,8 @@ extern "C" {
 #define RMEM_MAX_BANK_FRAMES 16
 #define RMEM_GN_SCRATCH_DOUBLES (72 + 148 * 4 * 64)
 #define RMEM_ATTN_DENSE 0 /* materialised scores: generic GEMMs + row softmax */
-#define RMEM_ATTN_TC 1    /* fused tcgen05 + TMA flash kernel */
+#define RMEM_ATTN_TC 1    /* fused tcgen05 + TMA flash kernel, v1 (split per frame, P through shared memory) */
+#define RMEM_ATTN_TC2 2   /* v2: stream-K schedule, 8 softmax warps, P through TMEM, fp16 partials (default) */
 
 int rmem_version(void);
 const char* rmem_last_error(void);
@@ -53,6 +54,9 @@ typedef struct rmem_gemm_desc {
   void* C2; long long ldc2; int c2_is_f32; int n_split; /* columns >= n_split go to C2 */
 } rmem_gemm_desc;
 int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream);
+/* 0 = auto: the tcgen05/TMA kernel whenever its alignment rules hold (K % 64 == 0, 16-byte aligned operands), else the
+ * legacy mma.sync kernel; 1 = force legacy (parity tests compare the two).  Thread-local.  Returns the previous value. */
+int rmem_set_gemm_impl(int impl);
 
 /* Long-term / self attention over the restricted bank with per-frame attention mass and the temporal
  * positional embedding applied as a per-(query,frame) score bias.
@@ -124,7 +128,7 @@ typedef struct rmem_engine_config {
   int former_mem_len;   /* FORMER_MEM_LEN */
   int latter_mem_len;   /* LATTER_MEM_LEN */
   int max_engines;      /* ceil(max objects / 10) object groups */
-  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC */
+  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC | RMEM_ATTN_TC2 */
   int long_term_mem_gap;
 } rmem_engine_config;
 

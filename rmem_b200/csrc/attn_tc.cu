@@ -11,13 +11,14 @@
 //   TMEM: 512 columns = O[256] | S0[64] | S1[64] | spare.
 //   Each CTA writes un-normalised (O, m, l) partials; combine_kernel merges the splits, applies the gate and
 //   emits mass[i,t] = sum_{splits of frame t} l_s 2^(m_s - M) / L.
-#include <cuda.h>
-
 #include "attn.cuh"
+#include "tcgen05.cuh"
 
 namespace rmem {
 
 namespace {
+
+using namespace tc;
 
 constexpr int BM = 128;        // query rows per CTA
 constexpr int BN = 64;         // keys per KV tile
@@ -54,118 +55,6 @@ struct TcParams {
   int* err;                   // device error flag (deadlock watchdog)
 };
 
-// ---------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU box -- flag + trap instead.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      if (err) atomicExch(err, code);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// D[tmem] (+)= A[smem] . B[smem]^T, t16 x t16 -> fp32
-__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
-  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
-  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-  return d;
-}
-
-// kind::f16 instruction descriptor: fp16/bf16 A/B (K-major), fp32 D.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (RMEM_UMMA_FORMAT << 7) | (RMEM_UMMA_FORMAT << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-      "%30,%31,%32};"
-      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-      "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-      "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])),
-      "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
-      "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])),
-      "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])),
-      "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kThreads, 1)
 long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -201,16 +90,16 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
       mbar_init(&p_full[i], 128); mbar_init(&p_free[i], 1);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  tc_fence_before();
+  fence_before();
   __syncthreads();
-  tc_fence_after();
+  fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
@@ -245,23 +134,23 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const uint32_t bb = k_addr + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
           umma_ss(tmem + TMEM_S + b * BN, make_desc_sw128(a), make_desc_sw128(bb), idesc_s, kk > 0);
         }
-        tc_commit(&s_full[b]);
+        commit(&s_full[b]);
       };
       mbar_wait(q_full, 0, p.err, 2);
       mbar_wait(&kv_full[0], 0, p.err, 3);
-      tc_fence_after();
+      fence_after();
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) {
           const int jn = j + 1;
           mbar_wait(&kv_full[jn % STAGES], (jn / STAGES) & 1, p.err, 4);
           if (jn >= 2) mbar_wait(&s_free[jn & 1], ((jn - 2) >> 1) & 1, p.err, 5);
-          tc_fence_after();
+          fence_after();
           issue_s(jn);
         }
         const int st = j % STAGES, b = j & 1;
         mbar_wait(&p_full[b], (j >> 1) & 1, p.err, 6);
-        tc_fence_after();
+        fence_after();
         const uint32_t p_addr = smem_u32(smem + OFF_P + b * SMEM_P);
         const uint32_t v_addr = smem_u32(smem + OFF_V + st * SMEM_V);
 #pragma unroll
@@ -269,8 +158,8 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           umma_ss(tmem + TMEM_O, make_desc_sw128(p_addr + kk * 32), make_desc_sw128(v_addr + kk * 32), idesc_o,
                   (j > 0 || kk > 0) ? 1u : 0u);
         }
-        tc_commit(&kv_empty[st]);
-        tc_commit(&p_free[b]);
+        commit(&kv_empty[st]);
+        commit(&p_free[b]);
       }
     }
   } else {
@@ -283,11 +172,11 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1, p.err, 7);
-      tc_fence_after();
+      fence_after();
       float s[BN];
       tmem_ld32(lane_addr + TMEM_S + b * BN, s);
       tmem_ld32(lane_addr + TMEM_S + b * BN + 32, s + 32);
-      tc_fence_before();
+      fence_before();
       mbar_arrive(&s_free[b]);
       const int key0 = (tile_lo + j) * BN;            // key index inside the frame
       float mt = -INFINITY;
@@ -303,7 +192,7 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (__any_sync(0xffffffffu, need)) {
         if (j > 0) {
           mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1, p.err, 8);   // PV(j-1) retired
-          tc_fence_after();
+          fence_after();
           const float f = need ? exp2f(m_used - mt) : 1.f;
           l *= f;
 #pragma unroll 1
@@ -314,7 +203,7 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             for (int e = 0; e < 32; ++e) o[e] *= f;
             tmem_st32(lane_addr + TMEM_O + c, o);
           }
-          tc_fence_before();
+          fence_before();
         }
         if (need) m_used = mt;
       }
@@ -342,7 +231,7 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // epilogue: un-normalised partial O + (m, l)
     const int last = n_tiles - 1;
     mbar_wait(&p_free[last & 1], (last >> 1) & 1, p.err, 10);
-    tc_fence_after();
+    fence_after();
     float* po = p.part_o + ((long long)split * p.HW + qi) * p.Dv + dv0;
 #pragma unroll 1
     for (int c = 0; c < DVC; c += 32) {
@@ -359,11 +248,11 @@ long_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       ml[0] = m_used;
       ml[1] = l;
     }
-    tc_fence_before();
+    fence_before();
   }
   __syncthreads();
   if (warp == 5) {
-    tc_fence_after();
+    fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
   }
 }
@@ -421,44 +310,12 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   }
 }
 
-#ifdef RMEM_OPERAND_BF16
-constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-#else
-constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-#endif
-
 int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
               uint32_t box_inner, uint32_t box_outer) {
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  // The driver entry point is resolved at run time so the library links (and loads on a GPU-less build box)
-  // without libcuda.so.
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
-      return RMEM_ERR_CUDA;
-    }
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  CUresult r = encode(map, kTmaType, 2, const_cast<void*>(base), dims, strides,
-                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed: CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)", (int)r,
-              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
-              box_outer);
-    return RMEM_ERR_CUDA;
-  }
-  return RMEM_OK;
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {row_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return tma_encode(map, base, 2, dims, strides, box, nullptr);
 }
 
 int pick_nsub(int qtiles, int dvchunks, int T, int tiles_per_frame) {

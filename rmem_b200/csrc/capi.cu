@@ -53,9 +53,17 @@ int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream) {
   return gemm_launch(p, STREAM(stream));
 }
 
+int rmem_set_gemm_impl(int impl) {
+  int prev = gemm_impl_switch();
+  gemm_impl_switch() = impl;
+  return prev;
+}
+
 int rmem_long_attn_workspace_bytes(int impl, int HW, int HWp, int nslots, int Dv, size_t* bytes) {
   RMEM_REQUIRE(bytes, "null bytes");
-  *bytes = impl == RMEM_ATTN_TC ? long_attn_tc_workspace(HW, HWp, nslots, Dv) : long_attn_dense_workspace(HW, HWp, nslots);
+  *bytes = impl == RMEM_ATTN_TC2 ? long_attn_tc2_workspace(HW, HWp, nslots, Dv)
+           : impl == RMEM_ATTN_TC ? long_attn_tc_workspace(HW, HWp, nslots, Dv)
+                                  : long_attn_dense_workspace(HW, HWp, nslots);
   return RMEM_OK;
 }
 
@@ -71,6 +79,7 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
   for (int t = 0; t < T; ++t) a.slot[t] = slots[t];
   a.HW = HW; a.HWp = HWp; a.Dk = Dk; a.Dv = Dv; a.scale = scale;
   a.gate = (const t16*)gate; a.ldg = ldg; a.out = (t16*)out; a.ldo = ldo; a.mass = mass;
+  if (impl == RMEM_ATTN_TC2) return long_attn_tc2(a, workspace, workspace_bytes, STREAM(stream));
   if (impl == RMEM_ATTN_TC) return long_attn_tc(a, workspace, workspace_bytes, STREAM(stream));
   return long_attn_dense(a, workspace, workspace_bytes, STREAM(stream));
 }

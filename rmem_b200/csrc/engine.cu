@@ -177,7 +177,8 @@ struct rmem_engine {
     label8 = a.take<uint8_t>((size_t)G.H * G.W);
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
     size_t ws_tc = long_attn_tc_workspace(G.HW, G.HWp, nslots, kDv);
-    attn_ws_bytes = ws_dense > ws_tc ? ws_dense : ws_tc;
+    size_t ws_tc2 = long_attn_tc2_workspace(G.HW, G.HWp, nslots, kDv);
+    attn_ws_bytes = cfg.attn_impl == RMEM_ATTN_TC2 ? ws_tc2 : (cfg.attn_impl == RMEM_ATTN_TC ? ws_tc : ws_dense);
     attn_ws = a.take<char>(attn_ws_bytes);
     state_begin = a.off;
     groups.assign(cfg.max_engines, Group());
@@ -336,6 +337,7 @@ struct rmem_engine {
   }
 
   int attention(const LongAttnArgs& a, cudaStream_t s) {
+    if (cfg.attn_impl == RMEM_ATTN_TC2) return long_attn_tc2(a, attn_ws, attn_ws_bytes, s);
     if (cfg.attn_impl == RMEM_ATTN_TC) return long_attn_tc(a, attn_ws, attn_ws_bytes, s);
     return long_attn_dense(a, attn_ws, attn_ws_bytes, s);
   }

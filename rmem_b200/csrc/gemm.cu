@@ -240,7 +240,21 @@ int launch_cfg(const GemmParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+int& gemm_impl_switch() {
+  static thread_local int impl = 0;
+  return impl;
+}
+
 int gemm_launch(const GemmParams& p, cudaStream_t stream) {
+  RMEM_REQUIRE(p.A && p.B && p.C, "gemm: null operand");
+  RMEM_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty shape M=%d N=%d K=%d", p.M, p.N, p.K);
+  RMEM_REQUIRE(!(p.accumulate && !p.c_fp32), "gemm: accumulate needs an fp32 destination");
+  if (p.n_split < p.N) RMEM_REQUIRE(p.C2 != nullptr, "gemm: n_split without C2");
+  if (gemm_impl_switch() == 0 && gemm_tc_supported(p)) return gemm_tc_launch(p, stream);
+  return gemm_legacy_launch(p, stream);
+}
+
+int gemm_legacy_launch(const GemmParams& p, cudaStream_t stream) {
   RMEM_REQUIRE(p.A && p.B && p.C, "gemm: null operand");
   RMEM_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty shape M=%d N=%d K=%d", p.M, p.N, p.K);
   RMEM_REQUIRE(p.K % 8 == 0, "gemm: K=%d must be a multiple of 8", p.K);

@@ -37,7 +37,15 @@ struct GemmParams {
   int n_split = 1 << 30;
 };
 
-// Launches the best tile configuration for the shape.  Returns RMEM_OK or an error code.
+// Launches the best kernel for the shape: the tcgen05/TMA kernel (gemm_tc.cu) whenever its alignment rules hold,
+// else the legacy mma.sync kernel (gemm.cu).  Returns RMEM_OK or an error code.
 int gemm_launch(const GemmParams& p, cudaStream_t stream);
+
+// tcgen05 + TMA implementation (gemm_tc.cu): K % 64 == 0, 16-byte aligned operands / outputs, conv Cin % 64 == 0.
+bool gemm_tc_supported(const GemmParams& p);
+int gemm_tc_launch(const GemmParams& p, cudaStream_t stream);
+int gemm_legacy_launch(const GemmParams& p, cudaStream_t stream);
+// 0 = auto (tcgen05 when supported), 1 = force the legacy mma.sync kernel (parity tests).  Thread-local.
+int& gemm_impl_switch();
 
 }  // namespace rmem

@@ -1,0 +1,353 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a with the fused epilogue contract of gemm.cuh:
+//   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T ),  fp16 operands, fp32 accumulation in TMEM.
+//
+//   block = 192 threads:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
+//   tile  = 128 (M) x BN (64 | 128 | 256) x 64 (K, one 128-byte swizzle atom), STAGES-deep mbarrier ring
+//   A tile: linear mode  -> 2-D TMA box [64 k, 128 rows] of the row-major matrix
+//           conv mode    -> 3-D TMA box [64 ch, BW, BH] (BW*BH = 128 output pixels of a rectangular patch) of the
+//                           NHWC map at the tap's offset; out-of-bounds pixels (the padding halo and the ragged tile
+//                           edge) are zero-filled by TMA, the traversal stride is the conv stride.  One k-block per
+//                           (tap, 64-channel slice): the im2col matrix is never materialised.
+//   B tile: 2-D TMA box [64 k, BN rows] of the [N,K] weight.
+//   Epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / residual / activation / gate / split / accumulate -> global
+//   (each thread owns an output row: 64-128 contiguous bytes per store burst).
+#include "gemm.cuh"
+#include "tcgen05.cuh"
+
+namespace rmem {
+
+namespace {
+
+using namespace tc;
+
+constexpr int TBM = 128;
+constexpr int TBK = 64;
+constexpr int kTcThreads = 192;
+constexpr int SMEM_A_STAGE = TBM * TBK * 2;   // 16 KB
+
+struct TcGemmParams {
+  int M, N, nk;
+  int conv, taps_w, cin_blocks, pad, stride, BW, BH, tiles_x, Hout, Wout;
+  float alpha;
+  const float* bias;
+  int bias_m, act, act_from;
+  const t16* res;
+  long long ldr;
+  const t16* gate;
+  long long ldg;
+  int accumulate;
+  void* C;
+  long long ldc;
+  int c_fp32;
+  void* C2;
+  long long ldc2;
+  int c2_fp32, n_split;
+  int* err;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int kB = BN * TBK * 2;
+  static constexpr int kStage = SMEM_A_STAGE + kB;
+  static constexpr int kBar = STAGES * kStage;
+  static constexpr int kTotal = kBar + 256 + 1024;   // barriers + alignment slack
+};
+
+__device__ __forceinline__ void load8h(const t16* p, float* v) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcGemmParams p) {
+  using L = TcSmem<BN, STAGES>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  int m0 = blockIdx.y * TBM, x0 = 0, y0 = 0;
+  if (p.conv) {
+    const int ty = blockIdx.y / p.tiles_x, tx = blockIdx.y - ty * p.tiles_x;
+    x0 = tx * p.BW;
+    y0 = ty * p.BH;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    for (int kb = 0; kb < p.nk; ++kb) {
+      const int st = kb % STAGES;
+      if (kb >= STAGES) mbar_wait(&empty[st], ((kb / STAGES) - 1) & 1, p.err, 1);
+      if (elect_one()) {
+        unsigned char* sa = smem + st * L::kStage;
+        unsigned char* sb = sa + SMEM_A_STAGE;
+        mbar_expect_tx(&full[st], L::kStage);
+        if (p.conv) {
+          const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+          const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
+          tma_load_3d(sa, &map_a, &full[st], cb * TBK, x0 * p.stride - p.pad + kx, y0 * p.stride - p.pad + ky);
+        } else {
+          tma_load_2d(sa, &map_a, &full[st], kb * TBK, m0);
+        }
+        tma_load_2d(sb, &map_b, &full[st], kb * TBK, n0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = make_idesc(TBM, BN);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int kb = 0; kb < p.nk; ++kb) {
+      const int st = kb % STAGES;
+      mbar_wait(&full[st], (kb / STAGES) & 1, p.err, 2);
+      fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_base + st * L::kStage;
+        const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + SMEM_A_STAGE);
+#pragma unroll
+        for (int kk = 0; kk < TBK / 16; ++kk)
+          umma_ss(tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+        commit(&empty[st]);
+        if (kb == p.nk - 1) commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue (warps 2-5) ================================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;                  // tile row
+    long long gm;
+    bool valid;
+    if (p.conv) {
+      const int yy = y0 + r / p.BW, xx = x0 + r % p.BW;
+      valid = yy < p.Hout && xx < p.Wout;
+      gm = (long long)yy * p.Wout + xx;
+    } else {
+      gm = m0 + r;
+      valid = gm < p.M;
+    }
+    const float bias_row = (p.bias && p.bias_m && valid) ? p.bias[gm] : 0.f;
+    mbar_wait(acc_full, 0, p.err, 3);
+    fence_after();
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int n = n0 + c0;
+      if (n >= p.N) break;                           // warp-uniform
+      float v[32];
+      tmem_ld32(lane_addr + c0, v);
+      if (!valid) continue;
+      const bool full_chunk = (n + 32 <= p.N);
+      // destination of this 32-column chunk (n_split is a multiple of 32)
+      void* base = p.C;
+      long long ld = p.ldc;
+      int nn = n, f32 = p.c_fp32;
+      if (n >= p.n_split) { base = p.C2; ld = p.ldc2; nn = n - p.n_split; f32 = p.c2_fp32; }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.alpha, bias_row);
+      if (full_chunk) {
+        if (p.bias && !p.bias_m) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (p.res) {
+          const t16* rp = p.res + gm * p.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float t[8];
+            load8h(rp + j, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j + e] += t[e];
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (n + j >= p.act_from) ? fmaxf(v[j], 0.f) : v[j];
+        } else if (p.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (n + j >= p.act_from) ? silu_f(v[j]) : v[j];
+        }
+        if (p.gate) {
+          const t16* gp = p.gate + gm * p.ldg + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float t[8];
+            load8h(gp + j, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j + e] *= t[e];
+          }
+        }
+        if (f32) {
+          float* o = reinterpret_cast<float*>(base) + gm * ld + nn;
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(o + j);
+              v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          t16* o = reinterpret_cast<t16*>(base) + gm * ld + nn;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack2(v[j], v[j + 1]); u.y = pack2(v[j + 2], v[j + 3]);
+            u.z = pack2(v[j + 4], v[j + 5]); u.w = pack2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = u;
+          }
+        }
+      } else {
+        // ragged last chunk: scalar path
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (n + j >= p.N) continue;
+          float x = v[j];
+          if (p.bias && !p.bias_m) x += p.bias[n + j];
+          if (p.res) x += t2f(p.res[gm * p.ldr + n + j]);
+          if (n + j >= p.act_from) {
+            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+            else if (p.act == ACT_SILU) x = silu_f(x);
+          }
+          if (p.gate) x *= t2f(p.gate[gm * p.ldg + n + j]);
+          if (f32) {
+            float* o = reinterpret_cast<float*>(base) + gm * ld + nn + j;
+            *o = p.accumulate ? (*o + x) : x;
+          } else {
+            reinterpret_cast<t16*>(base)[gm * ld + nn + j] = f2t(x);
+          }
+        }
+      }
+    }
+    fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc<BN>(tmem);
+  }
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, const TcGemmParams& p, int m_tiles, cudaStream_t s) {
+  using L = TcSmem<BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    RMEM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kTotal));
+    attr_done = true;
+  }
+  dim3 grid(cdiv(p.N, BN), m_tiles);
+  gemm_tc_kernel<BN, STAGES><<<grid, kTcThreads, L::kTotal, s>>>(*ma, *mb, p);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmParams& p) {
+  if (p.K % TBK != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return false;
+  if (p.ldb % 8 != 0) return false;
+  if (p.n_split < p.N && p.n_split % 32 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(p.C) & 15) return false;
+  if (p.ldc % (p.c_fp32 ? 4 : 8) != 0) return false;
+  if (p.n_split < p.N && ((reinterpret_cast<uintptr_t>(p.C2) & 15) || p.ldc2 % (p.c2_fp32 ? 4 : 8) != 0)) return false;
+  if (p.res && ((reinterpret_cast<uintptr_t>(p.res) & 15) || p.ldr % 8 != 0)) return false;
+  if (p.gate && ((reinterpret_cast<uintptr_t>(p.gate) & 15) || p.ldg % 8 != 0)) return false;
+  if (p.bias && !p.bias_m && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
+  if (p.conv) {
+    if (p.Cin % TBK != 0) return false;
+    if (p.K % (p.kw * p.Cin) != 0) return false;
+    if (p.stride < 1 || p.stride > 2) return false;
+    if (p.M % p.Wout != 0) return false;
+  } else {
+    if (p.lda % 8 != 0) return false;
+  }
+  return true;
+}
+
+int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
+  RMEM_REQUIRE(gemm_tc_supported(g), "gemm_tc: unsupported shape/alignment (M=%d N=%d K=%d)", g.M, g.N, g.K);
+  TcGemmParams p;
+  p.M = g.M; p.N = g.N; p.nk = g.K / TBK;
+  p.conv = g.conv; p.taps_w = g.kw; p.cin_blocks = g.conv ? g.Cin / TBK : 1; p.pad = g.pad; p.stride = g.stride;
+  p.BW = 128; p.BH = 1; p.tiles_x = 1; p.Hout = 0; p.Wout = g.Wout;
+  p.alpha = g.alpha; p.bias = g.bias; p.bias_m = g.bias_m; p.act = g.act; p.act_from = g.act_from;
+  p.res = g.res; p.ldr = g.ldr; p.gate = g.gate; p.ldg = g.ldg; p.accumulate = g.accumulate;
+  p.C = g.C; p.ldc = g.ldc; p.c_fp32 = g.c_fp32; p.C2 = g.C2; p.ldc2 = g.ldc2; p.c2_fp32 = g.c2_fp32;
+  p.n_split = g.n_split;
+  p.err = nullptr;   // watchdog traps without a flag word (the library never allocates device memory)
+
+  // ---- tile width: fill the 148 SMs, then prefer wide tiles (fewer A re-reads) ----
+  int m_tiles;
+  const CUtensorMap *ma = nullptr, *mb = nullptr;
+  if (g.conv) {
+    const int Hout = g.M / g.Wout;
+    p.Hout = Hout;
+    // rectangular 128-pixel patch that wastes the fewest tile slots
+    int best = 1 << 30;
+    for (int bw = 128; bw >= 8; bw >>= 1) {
+      const int bh = 128 / bw;
+      if (bw * g.stride > 256 || bh * g.stride > 256) continue;
+      const int n = cdiv(g.Wout, bw) * cdiv(Hout, bh);
+      if (n < best) { best = n; p.BW = bw; p.BH = bh; }
+    }
+    p.tiles_x = cdiv(g.Wout, p.BW);
+    m_tiles = best;
+    uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Win, (uint64_t)g.Hin};
+    uint64_t strides[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Win * g.Cin * 2};
+    uint32_t box[3] = {(uint32_t)TBK, (uint32_t)(p.BW * g.stride), (uint32_t)(p.BH * g.stride)};
+    uint32_t estr[3] = {1, (uint32_t)g.stride, (uint32_t)g.stride};
+    RMEM_TRY(tma_encode_cached(&ma, g.A, 3, dims, strides, box, estr));
+  } else {
+    m_tiles = cdiv(g.M, TBM);
+    uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    uint64_t strides[1] = {(uint64_t)g.lda * 2};
+    uint32_t box[2] = {(uint32_t)TBK, (uint32_t)TBM};
+    RMEM_TRY(tma_encode_cached(&ma, g.A, 2, dims, strides, box, nullptr));
+  }
+  int BN = 128;
+  if (g.N <= 64 || m_tiles * cdiv(g.N, 128) < 120) BN = 64;
+  else if (g.N >= 256 && g.K >= 512 && m_tiles * cdiv(g.N, 256) >= 148) BN = 256;
+  {
+    uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    uint64_t strides[1] = {(uint64_t)g.ldb * 2};
+    uint32_t box[2] = {(uint32_t)TBK, (uint32_t)BN};
+    RMEM_TRY(tma_encode_cached(&mb, g.B, 2, dims, strides, box, nullptr));
+  }
+  if (BN == 64) return launch_tc<64, 4>(ma, mb, p, m_tiles, stream);
+  if (BN == 128) return launch_tc<128, 3>(ma, mb, p, m_tiles, stream);
+  return launch_tc<256, 4>(ma, mb, p, m_tiles, stream);
+}
+
+}  // namespace rmem

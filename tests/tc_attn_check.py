@@ -16,6 +16,7 @@ from oracle import rmem_oracle as O  # noqa: E402
 from rmem_b200 import _capi, ops as K  # noqa: E402
 
 OP = _capi.op_dtype()
+IMPL = int(os.environ.get("RMEM_ATTN_IMPL", str(_capi.ATTN_TC2)))
 
 
 def bfr(t):
@@ -36,6 +37,8 @@ def main():
         ("self_like", 1, 1674, [0], 1.0, False, True),
         ("c3_t8", 8, 1674, [0, 5, 1, 2, 8, 3, 4, 6], 2.0, True, True),
         ("c3_t8_sharp", 8, 1674, [0, 5, 1, 2, 8, 3, 4, 6], 6.0, True, False),
+        ("t9_720p", 9, 3726, [8, 0, 5, 1, 2, 7, 3, 4, 6], 2.0, True, True),
+        ("t2_tiny", 2, 70, [1, 0], 3.0, True, True),
     ]
     only = sys.argv[1:] or None
     for name, T, HW, slots, sharp, use_pe, use_gate in cases:
@@ -65,9 +68,9 @@ def main():
         rec = dict(case=name)
         try:
             od, md = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=_capi.ATTN_DENSE, **args)
-            ot, mt = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=_capi.ATTN_TC, **args)
+            ot, mt = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=IMPL, **args)
             torch.cuda.synchronize()
-            rec.update(ok=True, tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
+            rec.update(ok=True, impl=IMPL, tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
                        tc_vs_dense=relfro(ot, od), mass_err=float((mt.cpu() - ref_mass).abs().max()),
                        mass_sum_err=float((mt.sum(1).cpu() - 1).abs().max()),
                        finite=bool(torch.isfinite(ot.float()).all()))

@@ -12,13 +12,14 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_tc_attention_matches_oracle(cuda_device):
+@pytest.mark.parametrize("impl", [2, 1], ids=["tc2", "tc1"])
+def test_tc_attention_matches_oracle(cuda_device, impl):
     r = subprocess.run([sys.executable, os.path.join(HERE, "tc_attn_check.py")], capture_output=True, text=True,
-                       timeout=600)
+                       timeout=600, env=dict(os.environ, RMEM_ATTN_IMPL=str(impl)))
     print(r.stdout)
     print(r.stderr[-2000:])
     recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-    assert r.returncode == 0 and len(recs) == 5, "tcgen05 attention check crashed"
+    assert r.returncode == 0 and len(recs) == 7, "tcgen05 attention check crashed"
     for rec in recs:
         assert rec["ok"], rec
         assert rec["finite"], rec

@@ -1,0 +1,78 @@
+"""Parity of the tcgen05/TMA GEMM + implicit-GEMM conv kernel (rmem_b200/csrc/gemm_tc.cu) through the C ABI against
+(a) torch fp32 on the same fp16-rounded operands and (b) the legacy mma.sync kernel, at the shapes the engine launches.
+Tolerance: fp16 operands, fp32 accumulate -> rel-Frobenius <= 2e-5*sqrt(K) on fp32 outputs, <= 1e-3 on fp16 outputs."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rmem_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+
+
+def relfro(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def K(cuda_device):
+    from rmem_b200 import ops
+    return ops
+
+
+def both(fn):
+    lib = _capi.load()
+    outs = []
+    for impl in (0, 1):
+        prev = lib.rmem_set_gemm_impl(impl)
+        try:
+            outs.append(fn())
+        finally:
+            lib.rmem_set_gemm_impl(prev)
+    return outs
+
+
+@pytest.mark.parametrize("shape", [(1674, 640, 256), (1674, 512, 1024), (25773, 64, 256), (25773, 256, 64),
+                                   (6527, 512, 128), (129, 64, 64), (1674, 128, 512), (1674, 256, 128),
+                                   (512, 1674, 256)])
+def test_linear_matches_torch_and_legacy(K, cuda_device, shape):
+    M, N, Kd = shape
+    OP = _capi.op_dtype()
+    g = torch.Generator().manual_seed(M + N + Kd)
+    A = (torch.randn(M, Kd, generator=g)).to(cuda_device).to(OP)
+    W = (torch.randn(N, Kd, generator=g) / math.sqrt(Kd)).to(cuda_device).to(OP)
+    b = torch.randn(N, generator=g).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(cuda_device).to(OP)
+    ref = F.linear(A.float(), W.float(), b)
+    ldc_ok = N % 8 == 0
+    tc, leg = both(lambda: K.gemm(A, W, b, out_f32=True))
+    assert relfro(tc, ref) < 2e-5 * math.sqrt(Kd)
+    assert relfro(tc, leg) < 2e-5 * math.sqrt(Kd)
+    if ldc_ok:
+        ref2 = torch.relu(ref + res.float())
+        tc2, leg2 = both(lambda: K.gemm(A, W, b, act=K.ACT_RELU, residual=res))
+        assert relfro(tc2, ref2) < 1e-3
+        assert relfro(tc2, leg2) < 1e-3
+
+
+@pytest.mark.parametrize("cfg", [(31, 54, 256, 256, 3, 1, 1), (121, 213, 64, 64, 3, 1, 1), (61, 107, 128, 128, 3, 1, 1),
+                                 (121, 213, 128, 128, 3, 2, 1), (61, 107, 256, 256, 3, 2, 1),
+                                 (121, 213, 256, 512, 1, 2, 0), (61, 107, 512, 1024, 1, 2, 0),
+                                 (31, 54, 1024, 256, 1, 1, 0), (17, 17, 64, 64, 3, 1, 1), (9, 200, 64, 64, 3, 1, 1)])
+def test_conv_matches_torch_and_legacy(K, cuda_device, cfg):
+    H, W, Cin, Cout, k, stride, pad = cfg
+    OP = _capi.op_dtype()
+    g = torch.Generator().manual_seed(H * W + Cin)
+    x = torch.randn(H, W, Cin, generator=g).to(cuda_device).to(OP)
+    w = (torch.randn(Cout, k, k, Cin, generator=g) / math.sqrt(k * k * Cin)).to(cuda_device).to(OP)
+    b = torch.randn(Cout, generator=g).to(cuda_device)
+    ref = F.conv2d(x.float().permute(2, 0, 1)[None], w.float().permute(0, 3, 1, 2), b, stride=stride, padding=pad)
+    ref = torch.relu(ref)[0].permute(1, 2, 0)
+    tc, leg = both(lambda: K.conv2d_nhwc(x, w, b, stride, pad, act=K.ACT_RELU))
+    assert tc.shape == ref.shape
+    assert relfro(tc, ref) < 1.5e-3, cfg
+    assert relfro(tc, leg) < 1.5e-3, cfg

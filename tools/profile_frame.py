@@ -27,12 +27,12 @@ def main():
     ap.add_argument("--objects", type=int, default=10)
     ap.add_argument("--latter", type=int, default=7)
     ap.add_argument("--gap", type=int, default=5)
-    ap.add_argument("--attn", default="tc", choices=["tc", "dense"])
+    ap.add_argument("--attn", default="tc2", choices=["tc2", "tc", "dense"])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     sd = make_state_dict("r50_deaotl", seed=0, sharpen=4.0)
     cfg = RmemConfig(former_mem_len=1, latter_mem_len=a.latter,
-                     attn_impl=_capi.ATTN_TC if a.attn == "tc" else _capi.ATTN_DENSE,
+                     attn_impl={"dense": 0, "tc": 1, "tc2": 2}[a.attn],
                      max_engines=(a.objects + 9) // 10)
     eng = build_engine("deaotengine", aot_model=DeAOTModel(sd, cfg, dev), long_term_mem_gap=1)
     frames = synthetic_frames(4, a.H, a.W, seed=1000).to(dev)
