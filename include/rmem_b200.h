@@ -52,6 +52,7 @@ typedef struct rmem_gemm_desc {
   int accumulate;                    /* C += result (fp32 destinations only) */
   void* C; long long ldc; int c_is_f32;
   void* C2; long long ldc2; int c2_is_f32; int n_split; /* columns >= n_split go to C2 */
+  int pad_n_ok;                      /* N % 32 != 0: columns N..round_up(N,32)-1 of C are writable padding */
 } rmem_gemm_desc;
 int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream);
 /* 0 = auto: the tcgen05/TMA kernel whenever its alignment rules hold (K % 64 == 0, 16-byte aligned operands), else the
@@ -67,6 +68,9 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
                        int nslots, int T, const int* slots /*HOST [T]*/, int HW, int HWp, int Dk, int Dv,
                        float scale, const void* gate, long long ldg, void* out, long long ldo, float* mass,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug aid: per-event clock64 trace of CTA 0 of the RMEM_ATTN_TC2 kernel into dev_buf ([tiles][16] int64); NULL disables. */
+int rmem_debug_attn_trace(void* dev_buf);
 
 /* Qt = t16(Q + cur_pos_emb); qbias[i,t] = scale * <Qt_i, pe_mem[t]>          (transformer.py:1140-1175) */
 /* pe_mem = mem_pos_emb [n_slots, C]; pe_slot HOST [T] = slot of each memory frame (rmem_temporal_pe_slots). */

@@ -39,6 +39,8 @@ int long_attn_tc(const LongAttnArgs& a, void* workspace, size_t workspace_bytes,
 // v2 (attn_tc2.cu): stream-K schedule over the SMs, 8 softmax warps, P through TMEM, fp16 partials.
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv);
 int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
+// Debug: clock64 event trace of CTA 0 ([tile][16] long long, see attn_tc2.cu); nullptr disables.
+int long_attn_tc2_set_trace(long long* dev_buf);
 
 // Windowed short-term attention (LocalGatedPropagation core, attention.py:289-353), 15x15 window:
 //   s[i,d] = scale*<q_i, k_{i+d}> + rel[i,d] ; p = softmax_d ; out_i = (sum_d p[i,d] v_{i+d}) * gate_i

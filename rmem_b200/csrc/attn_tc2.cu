@@ -1,19 +1,28 @@
-// Long-term / self attention v2 for sm_100a  (K1 + K1b + K8 of SURVEY.md; attention.py:174-193, transformer.py:1140-1197).
+// Long-term / self attention for sm_100a, third iteration  (K1 + K1b + K8 of SURVEY.md; attention.py:174-193,
+// transformer.py:1140-1197).  RMEM_ATTN_TC2.
 //
-// What changed against attn_tc.cu (kept as RMEM_ATTN_TC for comparison), driven by the round-1 ncu capture:
-//   * stream-K style static schedule: the (query tile, Dv chunk, KV tile) space is cut into one contiguous range per
-//     SM (grid = #SMs), so there is no partial last wave and each CTA flushes at most two segments;
-//   * eight softmax warps (two per TMEM lane quadrant, splitting the 64 score columns) with a ~170-instruction tile
-//     body: scale, temporal-PE bias and the running max folded into one FFMA feeding EX2, no saturating packs, the
-//     ragged-tile mask only on the last tile of a frame;
-//   * P goes back to the tensor core through TMEM (tcgen05.st, A operand of the P.V MMA read from TMEM): no shared-memory
-//     round trip, no proxy fence, and the freed shared memory buys a 4th K/V stage;
-//   * partial results leave the CTA as normalised fp16 rows (64 B bursts per thread) + fp32 (m, l): 4x less partial
-//     traffic than the fp32 un-normalised partials of v1; per-frame (m, l) pieces give the attention mass.
+// Why it looks like this (profiles/r01_*): the first two versions were bound by the LATENCY of the dependency loop
+// S = Q.K^T -> softmax -> P.V, not by any pipe: tcgen05.mma groups take ~400 cycles from issue to a visible commit on
+// top of their throughput (tools/ubench/mma_rate.cu: 8 x N=64 MMAs = 757 cycles alone, 49 cycles each in a stream),
+// and one set of softmax warps needed ~1600 cycles per 64-key tile.  This version removes the loop:
+//   * S runs up to four tiles ahead of P.V in four TMEM score buffers, issued by its own warp (tcgen05.mma issue blocks
+//     the issuing thread for roughly the MMA's execution time, so one issuing warp per MMA stream), so softmax never
+//     waits for scores;
+//   * two softmax warp groups (4 warps each, one query row per thread) alternate KV tiles; the only value that has to
+//     travel from tile j to tile j+1 is the lazily-updated row maximum, handed over through 512 B of shared memory and
+//     a 64-thread named barrier per TMEM lane quadrant -- the exp / pack / store phase of tile j overlaps the load /
+//     max phase of tile j+1;
+//   * P is written back as packed fp16 over the first 32 columns of its own score buffer (each thread overwrites only
+//     the row it has already read) and is the TMEM A operand of the P.V MMA: no shared-memory round trip;
+//   * stream-K static schedule: the (query tile, Dv chunk, KV tile) space is cut into one contiguous range per SM, each
+//     CTA flushes at most two segments as normalised fp16 rows + fp32 (m, l); per-frame (m, l) pieces give the mass;
+//   * K and V^T tiles travel in separate TMA rings (K is needed three tiles earlier than V), Q is double-buffered for
+//     the two segments.
 //
-//   block = 320 threads: warps 0-7 softmax + epilogue, warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
-//   TMEM (512 cols): O[256] | S0[64] S1[64] | P0[32] P1[32] (fp16 pairs)
-//   smem: Q 32 KB + 4 x (K 16 KB + V^T 32 KB) + barriers + exchange
+//   block = 384 threads: warps 0-3 softmax group 0 (even tiles), 4-7 group 1 (odd tiles), 8 K/Q producer,
+//                        9 V producer, 10 S issuer + TMEM owner, 11 P.V issuer
+//   TMEM (512 cols): O[256] | 4 x S/P[64]
+//   smem: Q 2 x 32 KB | K 4 x 16 KB | V^T 3 x 32 KB | row-max hand-over | barriers
 #include "attn.cuh"
 #include "tcgen05.cuh"
 
@@ -27,28 +36,32 @@ constexpr int BM = 128;        // query rows per CTA
 constexpr int BN = 64;         // keys per KV tile
 constexpr int DK = 128;
 constexpr int DVC = 256;       // Dv columns per unit
-constexpr int STAGES = 4;
+constexpr int KS = 4;          // K ring depth
+constexpr int VS = 3;          // V ring depth
+constexpr int NSB = 4;         // score buffers in TMEM
 constexpr int kSoftmaxWarps = 8;
-constexpr int kThreads = (kSoftmaxWarps + 2) * 32;
+constexpr int kWarpK = 8, kWarpV = 9, kWarpMmaS = 10, kWarpMmaPV = 11;
+constexpr int kThreads = 12 * 32;
 
 constexpr int SMEM_Q = BM * DK * 2;            // 32 KB (two 64-col swizzle atoms)
 constexpr int SMEM_K = BN * DK * 2;            // 16 KB
 constexpr int SMEM_V = DVC * BN * 2;           // 32 KB
 constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + SMEM_Q;
-constexpr int OFF_V = OFF_K + STAGES * SMEM_K;
-constexpr int OFF_XCH = OFF_V + STAGES * SMEM_V;          // float [2][4][2][32]
-constexpr int OFF_BAR = OFF_XCH + 2 * 4 * 2 * 32 * 4;
-constexpr int SMEM_TOTAL = OFF_BAR + 256;   // no alignment slack: 4 stages only fit in 227 KB if the dynamic base is
+constexpr int OFF_K = OFF_Q + 2 * SMEM_Q;
+constexpr int OFF_V = OFF_K + KS * SMEM_K;
+constexpr int OFF_MSH = OFF_V + VS * SMEM_V;              // float [128]        row-max hand-over
+constexpr int OFF_LX = OFF_MSH + BM * 4;                  // float [2][128][2]  (m, l) exchange at segment end
+constexpr int OFF_BAR = OFF_LX + 2 * BM * 2 * 4;
+constexpr int SMEM_TOTAL = OFF_BAR + 256;   // no alignment slack: the rings only fit in 227 KB if the dynamic base is
                                             // 1024B-aligned already (it follows the 1 KB driver reservation); checked below
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_O = 0;
-constexpr int TMEM_S = 256;    // 2 x 64
-constexpr int TMEM_P = 384;    // 2 x 32 (packed fp16 pairs)
+constexpr int TMEM_S = 256;    // 4 x 64; P (packed fp16 pairs) aliases the first 32 columns of its buffer
 
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float RESCALE_THRESHOLD = 8.0f;      // log2 units: P <= 2^8 before a lazy rescale is forced
+constexpr float RESCALE_THRESHOLD = 12.0f;     // log2 units: P <= 2^12 (fp16 max 2^16) before a lazy rescale is forced
 
 struct Tc2Params {
   int HW, HWp, T, tpf, TPU, n_units, n_dv, nCTA, Dv;
@@ -56,9 +69,9 @@ struct Tc2Params {
   int slot[kMaxBankFrames];
   float scale_log2;            // scale * log2(e)
   const float* qbias;          // [HW, T] or null (already multiplied by scale)
-  t16* part_o;                 // [nCTA][2][BM][DVC]  normalised partial O
-  float* part_ml;              // [nCTA][2][BM][2]    (m in log2 units, l)
-  float* pieces;               // [nCTA][2][T][BM][2] per-frame (m, l) of the segment (Dv chunk 0 units only) or null
+  t16* part_o;                 // [nCTA][2][BM][DVC]     normalised partial O
+  float* part_ml;              // [nCTA][2][BM][2]       (m in log2 units, l)
+  float* pieces;               // [nCTA][2][T][2][BM][2] per-frame (m, l) of each softmax group (Dv chunk 0 units) or null
 };
 
 // D[tmem] (+)= A[tmem] . B[smem]^T   (A = P as packed fp16 pairs, one TMEM lane per row)
@@ -72,17 +85,24 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31,%32};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // unsaturated fp32x2 -> t16x2 (values are bounded by 2^8 here)
@@ -94,6 +114,13 @@ __device__ __forceinline__ uint32_t pack2_fast(float lo, float hi) {
 #endif
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+// Optional event trace of CTA 0 (clock64 per pipeline event, 16 slots per tile); null in production.
+__device__ long long* g_trace = nullptr;
+#define TRACE(j, k)                                                                  \
+  do {                                                                               \
+    if (trace && lane == 0) trace[(long long)(j) * 16 + (k)] = clock64();            \
+  } while (0)
 
 struct Seg { int unit, lo, hi; };   // tiles [lo, hi) of the unit
 
@@ -108,20 +135,23 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();       // 128B-swizzled TMA / UMMA tiles need 1024B alignment
-  float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
+  float* m_sh = reinterpret_cast<float*>(smem + OFF_MSH);
+  float* lx = reinterpret_cast<float*>(smem + OFF_LX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_free = bars + 1;
-  uint64_t* o_drained = bars + 2;
-  uint64_t* kv_full = bars + 3;                 // [STAGES]
-  uint64_t* kv_empty = kv_full + STAGES;        // [STAGES]
-  uint64_t* s_full = kv_empty + STAGES;         // [2]
-  uint64_t* s_free = s_full + 2;                // [2]
-  uint64_t* p_full = s_free + 2;                // [2]
-  uint64_t* p_free = p_full + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
+  uint64_t* q_full = bars;                      // [2]
+  uint64_t* k_full = q_full + 2;                // [KS]
+  uint64_t* k_empty = k_full + KS;              // [KS]
+  uint64_t* v_full = k_empty + KS;              // [VS]
+  uint64_t* v_empty = v_full + VS;              // [VS]
+  uint64_t* s_full = v_empty + VS;              // [NSB]  S(j) complete
+  uint64_t* p_full = s_full + NSB;              // [NSB]  P(j) stored by its softmax group
+  uint64_t* sp_free = p_full + NSB;             // [NSB]  P.V(j) complete: score buffer (and everything before) retired
+  uint64_t* o_drained = sp_free + NSB;          // segment epilogue has read O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_drained + 1);
+  static_assert((2 + 2 * KS + 2 * VS + 3 * NSB + 1) * 8 + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const trace = blockIdx.x == 0 ? g_trace : nullptr;
 
   // ---- this CTA's work: a contiguous range of (unit, tile) steps -> at most two segments ----
   long long lo, hi;
@@ -143,78 +173,96 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
   const int n0 = nseg > 0 ? seg[0].hi - seg[0].lo : 0;
   const int ntot = n0 + (nseg > 1 ? seg[1].hi - seg[1].lo : 0);
-  // units are ordered (query tile major, Dv chunk minor): the Q tile changes only when unit / n_dv changes
-  const bool q_reload1 = nseg > 1 && (seg[1].unit / p.n_dv != seg[0].unit / p.n_dv);
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_free, 1);
-    mbar_init(o_drained, kSoftmaxWarps);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], kSoftmaxWarps);
-      mbar_init(&p_full[i], kSoftmaxWarps); mbar_init(&p_free[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < NSB; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&sp_free[i], 1);
     }
+    mbar_init(o_drained, kSoftmaxWarps);
     mbar_fence_init();
   }
-  if (warp == kSoftmaxWarps + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == kWarpMmaS) tmem_alloc<TMEM_COLS>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kSoftmaxWarps) {
-    // ================================ TMA producer (converged warp, one elected lane issues) ================
+  if (warp == kWarpK) {
+    // ================================ Q + K producer ================================
     if (ntot > 0) {
       if (elect_one()) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
-        tma_prefetch_desc(&map_v);
+        for (int s = 0; s < nseg; ++s) {
+          const int qt = seg[s].unit / p.n_dv;
+          mbar_expect_tx(&q_full[s], SMEM_Q);
+          tma_load_2d(smem + OFF_Q + s * SMEM_Q, &map_q, &q_full[s], 0, qt * BM);
+          tma_load_2d(smem + OFF_Q + s * SMEM_Q + BM * 128, &map_q, &q_full[s], 64, qt * BM);
+        }
       }
       __syncwarp();
-      int j = 0;
+      int i = 0;
       for (int s = 0; s < nseg; ++s) {
-        const int qt = seg[s].unit / p.n_dv, dv0 = (seg[s].unit % p.n_dv) * DVC;
-        if (s == 0 || q_reload1) {
-          if (s > 0) mbar_wait(q_free, 0, nullptr, 1);
+        int t = seg[s].lo / p.tpf, jt = seg[s].lo - t * p.tpf;
+        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++i, ++jt) {
+          if (jt == p.tpf) { jt = 0; ++t; }
+          const int st = i % KS;
+          if (i >= KS) mbar_wait(&k_empty[st], ((i / KS) - 1) & 1, nullptr, 1);
           if (elect_one()) {
-            mbar_expect_tx(q_full, SMEM_Q);
-            tma_load_2d(smem + OFF_Q, &map_q, q_full, 0, qt * BM);
-            tma_load_2d(smem + OFF_Q + BM * 128, &map_q, q_full, 64, qt * BM);
-          }
-          __syncwarp();
-        }
-        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++j) {
-          const int st = j % STAGES;
-          if (j >= STAGES) mbar_wait(&kv_empty[st], ((j / STAGES) - 1) & 1, nullptr, 2);
-          const int t = g / p.tpf, jt = g - t * p.tpf;
-          const int key0 = p.slot[t] * p.HWp + jt * BN;
-          if (elect_one()) {
-            mbar_expect_tx(&kv_full[st], SMEM_K + SMEM_V);
+            const int key0 = p.slot[t] * p.HWp + jt * BN;
             unsigned char* sk = smem + OFF_K + st * SMEM_K;
-            tma_load_2d(sk, &map_k, &kv_full[st], 0, key0);
-            tma_load_2d(sk + BN * 128, &map_k, &kv_full[st], 64, key0);
-            tma_load_2d(smem + OFF_V + st * SMEM_V, &map_v, &kv_full[st], key0, dv0);
+            mbar_expect_tx(&k_full[st], SMEM_K);
+            tma_load_2d(sk, &map_k, &k_full[st], 0, key0);
+            tma_load_2d(sk + BN * 128, &map_k, &k_full[st], 64, key0);
           }
           __syncwarp();
         }
       }
     }
-  } else if (warp == kSoftmaxWarps + 1) {
-    // ================================ MMA issuer (converged warp, one elected lane issues) ==================
+  } else if (warp == kWarpV) {
+    // ================================ V^T producer ================================
+    if (ntot > 0) {
+      if (elect_one()) tma_prefetch_desc(&map_v);
+      __syncwarp();
+      int i = 0;
+      for (int s = 0; s < nseg; ++s) {
+        const int dv0 = (seg[s].unit % p.n_dv) * DVC;
+        int t = seg[s].lo / p.tpf, jt = seg[s].lo - t * p.tpf;
+        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++i, ++jt) {
+          if (jt == p.tpf) { jt = 0; ++t; }
+          const int st = i % VS;
+          if (i >= VS) mbar_wait(&v_empty[st], ((i / VS) - 1) & 1, nullptr, 2);
+          if (elect_one()) {
+            const int key0 = p.slot[t] * p.HWp + jt * BN;
+            mbar_expect_tx(&v_full[st], SMEM_V);
+            tma_load_2d(smem + OFF_V + st * SMEM_V, &map_v, &v_full[st], key0, dv0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kWarpMmaS) {
+    // ================================ S = Q.K^T issuer ================================
+    // tcgen05.mma issue blocks the issuing thread for about the MMA's execution time, and every mbarrier wait costs
+    // ~90 cycles even when already complete (trace in profiles/r01_attn_trace.txt), so the two MMA streams get one
+    // warp each: this one runs up to four score tiles ahead, bounded only by the K ring and the score buffers.
     if (ntot > 0) {
       constexpr uint32_t idesc_s = make_idesc(BM, BN);
-      constexpr uint32_t idesc_o = make_idesc(BM, DVC);
       const uint32_t smem_base = smem_u32(smem);
-      const uint64_t dq = make_desc_sw128(smem_base + OFF_Q);
-      auto issue_s = [&](int j) {
-        const int st = j % STAGES, b = j & 1;
-        if (j == 0) mbar_wait(q_full, 0, nullptr, 3);
-        if (j == n0 && q_reload1) mbar_wait(q_full, 1, nullptr, 4);
-        mbar_wait(&kv_full[st], (j / STAGES) & 1, nullptr, 5);
-        if (j >= 2) mbar_wait(&s_free[b], ((j - 2) >> 1) & 1, nullptr, 6);
+      for (int i = 0; i < ntot; ++i) {
+        const int st = i % KS, b = i % NSB;
+        const int sq = i >= n0 ? 1 : 0;
+        if (i == 0) mbar_wait(&q_full[0], 0, nullptr, 3);
+        if (i == n0) mbar_wait(&q_full[1], 0, nullptr, 4);
+        mbar_wait(&k_full[st], (i / KS) & 1, nullptr, 5);
+        if (i >= NSB) mbar_wait(&sp_free[b], ((i - NSB) / NSB) & 1, nullptr, 6);    // P.V(i-4) retired its buffer
         fence_after();
+        TRACE(i, 2);
         if (elect_one()) {
+          const uint64_t dq = make_desc_sw128(smem_base + OFF_Q + sq * SMEM_Q);
           const uint64_t dk = make_desc_sw128(smem_base + OFF_K + st * SMEM_K);
           const uint32_t d = tmem + TMEM_S + b * BN;
 #pragma unroll
@@ -224,152 +272,190 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const uint64_t ob = (uint64_t)(((kk >> 2) * (BN * 128) + (kk & 3) * 32) >> 4);
             umma_ss(d, dq + oa, dk + ob, idesc_s, kk > 0);
           }
+          commit(&k_empty[st]);
           commit(&s_full[b]);
-          if (j == n0 - 1 && q_reload1) commit(q_free);      // last read of the old Q tile
         }
         __syncwarp();
-      };
-      issue_s(0);
+        TRACE(i, 3);
+      }
+    }
+  } else if (warp == kWarpMmaPV) {
+    // ================================ O += P.V issuer ================================
+    if (ntot > 0) {
+      constexpr uint32_t idesc_o = make_idesc(BM, DVC);
+      const uint32_t smem_base = smem_u32(smem);
       for (int j = 0; j < ntot; ++j) {
-        const bool defer = (j + 1 == n0) && q_reload1;     // next S needs a new Q tile: do not block P.V(j) on it
-        if (j + 1 < ntot && !defer) issue_s(j + 1);
-        const int st = j % STAGES, b = j & 1;
-        mbar_wait(&p_full[b], (j >> 1) & 1, nullptr, 7);
+        const int b = j % NSB, sv = j % VS;
+        mbar_wait(&p_full[b], (j / NSB) & 1, nullptr, 7);
+        TRACE(j, 0);
         const bool first = (j == 0) || (j == n0);
-        if (j == n0 && n0 > 0 && nseg > 1) mbar_wait(o_drained, 0, nullptr, 8);
+        if (j == n0 && nseg > 1) mbar_wait(o_drained, 0, nullptr, 8);
+        mbar_wait(&v_full[sv], (j / VS) & 1, nullptr, 9);
         fence_after();
         if (elect_one()) {
-          const uint64_t dv = make_desc_sw128(smem_base + OFF_V + st * SMEM_V);
-          const uint32_t pa = tmem + TMEM_P + b * 32;
+          const uint64_t dv = make_desc_sw128(smem_base + OFF_V + sv * SMEM_V);
+          const uint32_t pa = tmem + TMEM_S + b * BN;
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk)
             umma_ts(tmem + TMEM_O, pa + kk * 8, dv + (uint64_t)(kk * 2), idesc_o, (first && kk == 0) ? 0u : 1u);
-          commit(&kv_empty[st]);
-          commit(&p_free[b]);
+          commit(&v_empty[sv]);
+          commit(&sp_free[b]);
         }
         __syncwarp();
-        if (j + 1 < ntot && defer) issue_s(j + 1);
+        TRACE(j, 1);
       }
     }
   } else if (ntot > 0) {
     // ================================ softmax + epilogue (warps 0-7) ================================
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, grp = warp >> 2;
     const int row = quad * 32 + lane;                       // tile row == TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const int bar_id = 1 + quad;
-    int j = 0, xp = 0;
-    // exchange slot of this thread / its partner (other half of the same row)
-    auto xslot = [&](int par, int h) { return xch + ((par * 4 + quad) * 2 + h) * 32 + lane; };
+    // named barriers: group 0 -> group 1 hand-over, group 1 -> group 0 hand-over, segment-end exchange
+    const int id_in = grp == 1 ? 1 + quad : 5 + quad;
+    const int id_out = grp == 0 ? 1 + quad : 5 + quad;
+    const int id_ex = 9 + quad;
+    int j = 0;
 
     for (int s = 0; s < nseg; ++s) {
       const int unit = seg[s].unit;
       const int qt = unit / p.n_dv, dvc = unit % p.n_dv;
       const int qi = qt * BM + row;
       const bool row_ok = qi < p.HW;
-      float m_used = -INFINITY, l_tot = 0.f, l_piece = 0.f, bias2 = 0.f;
+      // m_ref: the running maximum this group's l / l_piece are relative to
+      float m_ref = -INFINITY, l_tot = 0.f, l_piece = 0.f, bias2 = 0.f;
       int cur_t = -1;
       const int j_first = j;
       float* piece_base = (p.pieces && dvc == 0)
-                              ? p.pieces + ((long long)(blockIdx.x * 2 + s) * p.T) * (BM * 2) + row * 2
+                              ? p.pieces + (((long long)(blockIdx.x * 2 + s) * p.T) * 2 + grp) * (BM * 2) + row * 2
                               : nullptr;
       auto flush_piece = [&](int t) {
-        // l of this frame's piece, both column halves
-        *xslot(xp, half) = l_piece;
-        named_bar_sync(bar_id, 64);
-        const float other = *xslot(xp, half ^ 1);
-        xp ^= 1;
-        if (piece_base && half == 0) {
-          float* d = piece_base + (long long)t * (BM * 2);
-          d[0] = m_used;
-          d[1] = l_piece + other;
+        if (piece_base) {
+          float* d = piece_base + (long long)t * (2 * BM * 2);
+          d[0] = m_ref;
+          d[1] = l_piece;
         }
       };
-
-      for (int g = seg[s].lo; g < seg[s].hi; ++g, ++j) {
-        const int t = g / p.tpf, jt = g - t * p.tpf;
-        if (t != cur_t) {
+      int t = seg[s].lo / p.tpf, jt = seg[s].lo - t * p.tpf;
+      for (int g = seg[s].lo; g < seg[s].hi; ++g, ++j, ++jt) {
+        if (jt == p.tpf) { jt = 0; ++t; }
+        if (t != cur_t) {                                   // both groups walk every tile's frame index
           if (cur_t >= 0) flush_piece(cur_t);
           cur_t = t;
           l_piece = 0.f;
           bias2 = (p.qbias && row_ok) ? p.qbias[(long long)qi * p.T + t] * LOG2E : 0.f;
         }
-        const int b = j & 1;
-        mbar_wait(&s_full[b], (j >> 1) & 1, nullptr, 9);
+        if ((j & 1) != grp) continue;
+        const int b = j % NSB;
+        long long* const trace_s = quad == 0 ? trace : nullptr;
+#define TRACE_S(k) do { if (trace_s && lane == 0) trace_s[(long long)j * 16 + (k)] = clock64(); } while (0)
+        TRACE_S(4);
+        mbar_wait(&s_full[b], (j / NSB) & 1, nullptr, 10);
         fence_after();
-        float sc[32];
-        tmem_ld32(lane_addr + TMEM_S + b * BN + half * 32, sc);
-        fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[b]);
-        if (jt == p.tpf - 1) {                               // ragged last tile of the frame
-          const int key0 = jt * BN + half * 32;
+        TRACE_S(5);
+        float sc[64];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(lane_addr + TMEM_S + b * BN, r0);
+          tmem_ld32_nowait(lane_addr + TMEM_S + b * BN + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) sc[c] = (key0 + c < p.HW) ? sc[c] : -INFINITY;
+          for (int c = 0; c < 32; ++c) { sc[c] = __uint_as_float(r0[c]); sc[32 + c] = __uint_as_float(r1[c]); }
         }
-        float mx = sc[0];
+        if (jt == p.tpf - 1) {                               // ragged last tile of the frame
+          const int key0 = jt * BN;
 #pragma unroll
-        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, sc[c]);
-        *xslot(xp, half) = mx;
-        named_bar_sync(bar_id, 64);
-        mx = fmaxf(mx, *xslot(xp, half ^ 1));
-        xp ^= 1;
+          for (int c = 0; c < 64; ++c) sc[c] = (key0 + c < p.HW) ? sc[c] : -INFINITY;
+        }
+        // row maximum: balanced tree
+        float mx;
+        {
+          float a[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) a[c] = fmaxf(fmaxf(sc[c], sc[16 + c]), fmaxf(sc[32 + c], sc[48 + c]));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a[c] = fmaxf(fmaxf(a[c], a[4 + c]), fmaxf(a[8 + c], a[12 + c]));
+          mx = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
+        }
         const float mt = fmaf(mx, p.scale_log2, bias2);      // scale > 0: max commutes with the affine map
-        // lazy rescale (the two warps of a quadrant see identical values -> identical decisions)
-        const bool need = mt > m_used + RESCALE_THRESHOLD;
+        TRACE_S(6);
+        // ---- hand-over of the lazily updated row maximum from the other group's tile j-1 ----
+        float m_prev = -INFINITY;
+        if (j > j_first) {
+          named_bar_sync(id_in, 64);
+          m_prev = m_sh[row];
+        }
+        const bool need = mt > m_prev + RESCALE_THRESHOLD;
+        float m_new = m_prev;
         if (__any_sync(0xffffffffu, need)) {
           if (j > j_first) {
-            mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1, nullptr, 10);   // P.V(j-1) retired
+            mbar_wait(&sp_free[(j - 1) % NSB], ((j - 1) / NSB) & 1, nullptr, 11);   // P.V(<= j-1) retired
             fence_after();
-            const float f = need ? exp2f(m_used - mt) : 1.f;
-            l_tot *= f;
-            l_piece *= f;
+            const float f = need ? exp2f(m_prev - mt) : 1.f;
 #pragma unroll 1
-            for (int c = 0; c < DVC / 2; c += 32) {
+            for (int c = 0; c < DVC; c += 32) {
               float o[32];
-              tmem_ld32(lane_addr + TMEM_O + half * (DVC / 2) + c, o);
+              tmem_ld32(lane_addr + TMEM_O + c, o);
 #pragma unroll
               for (int e = 0; e < 32; ++e) o[e] *= f;
-              tmem_st32(lane_addr + TMEM_O + half * (DVC / 2) + c, o);
+              tmem_st32(lane_addr + TMEM_O + c, o);
             }
             fence_before();
           }
-          if (need) m_used = mt;
+          if (need) m_new = mt;
         }
-        const float c0 = bias2 - m_used;
-        float lsum = 0.f;
-        uint32_t pk[16];
+        if (g + 1 < seg[s].hi) {
+          m_sh[row] = m_new;
+          named_bar_arrive(id_out, 64);
+        }
+        TRACE_S(7);
+        if (m_new != m_ref) {                                // bring this group's sums to the current reference
+          const float f2 = exp2f(m_ref - m_new);
+          l_tot *= f2;
+          l_piece *= f2;
+          m_ref = m_new;
+        }
+        const float c0 = bias2 - m_new;
+        uint32_t pk[32];
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
+        for (int c = 0; c < 64; c += 4) {
           const float e0 = exp2f(fmaf(sc[c], p.scale_log2, c0));
           const float e1 = exp2f(fmaf(sc[c + 1], p.scale_log2, c0));
-          lsum += e0 + e1;
+          const float e2 = exp2f(fmaf(sc[c + 2], p.scale_log2, c0));
+          const float e3 = exp2f(fmaf(sc[c + 3], p.scale_log2, c0));
+          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
           pk[c >> 1] = pack2_fast(e0, e1);
+          pk[(c >> 1) + 1] = pack2_fast(e2, e3);
         }
+        const float lsum = (ls0 + ls1) + (ls2 + ls3);
         l_tot += lsum;
         l_piece += lsum;
-        if (j >= 2) mbar_wait(&p_free[b], ((j - 2) >> 1) & 1, nullptr, 11);    // P.V(j-2) done reading P[b]
-        fence_after();
-        tmem_st16(lane_addr + TMEM_P + b * 32 + half * 16, pk);
+        // P(j) over the first 32 columns of S(j): this thread's row was fully read above
+        TRACE_S(8);
+        tmem_st32u(lane_addr + TMEM_S + b * BN, pk);
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[b]);
+        TRACE_S(9);
       }
       flush_piece(cur_t);
 
       // ---- segment epilogue: normalised fp16 partial O + (m, l) ----
-      *xslot(xp, half) = l_tot;
-      named_bar_sync(bar_id, 64);
-      const float l_row = l_tot + *xslot(xp, half ^ 1);
-      xp ^= 1;
+      lx[(grp * BM + row) * 2 + 0] = m_ref;
+      lx[(grp * BM + row) * 2 + 1] = l_tot;
+      named_bar_sync(id_ex, 64);
+      const float m_o = lx[((grp ^ 1) * BM + row) * 2 + 0], l_o = lx[((grp ^ 1) * BM + row) * 2 + 1];
+      const float M = fmaxf(m_ref, m_o);                    // == the maximum O is relative to (m is monotone)
+      const float l_row = l_tot * exp2f(m_ref - M) + l_o * exp2f(m_o - M);
       const float inv = 1.f / l_row;
       const int last = j - 1;
-      mbar_wait(&p_free[last & 1], (last >> 1) & 1, nullptr, 12);
+      mbar_wait(&sp_free[last % NSB], (last / NSB) & 1, nullptr, 12);
       fence_after();
-      t16* po = p.part_o + ((long long)(blockIdx.x * 2 + s) * BM + row) * DVC + half * (DVC / 2);
+      t16* po = p.part_o + ((long long)(blockIdx.x * 2 + s) * BM + row) * DVC + grp * (DVC / 2);
 #pragma unroll 1
       for (int c = 0; c < DVC / 2; c += 32) {
         float o[32];
-        tmem_ld32(lane_addr + TMEM_O + half * (DVC / 2) + c, o);
+        tmem_ld32(lane_addr + TMEM_O + grp * (DVC / 2) + c, o);
         if (row_ok) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
@@ -382,9 +468,9 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           }
         }
       }
-      if (half == 0) {
+      if (grp == 0) {
         float* ml = p.part_ml + ((long long)(blockIdx.x * 2 + s) * BM + row) * 2;
-        ml[0] = m_used;
+        ml[0] = M;
         ml[1] = l_row;
       }
       fence_before();
@@ -394,7 +480,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
   fence_before();
   __syncthreads();
-  if (warp == kSoftmaxWarps + 1) {
+  if (warp == kWarpMmaS) {
     fence_after();
     tmem_dealloc<TMEM_COLS>(tmem);
   }
@@ -402,43 +488,63 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
 // Merge the segments of every unit: out = (sum_s w_s O_s) * gate with w_s = l_s 2^(m_s - M) / L;
 // mass[i,t] = sum_{pieces of frame t} l_p 2^(m_p - M) / L  (from the Dv-chunk-0 units).
+// One block per query row; the (CTA, segment) list of the row's four units is resolved once per block.
+constexpr int kMaxSegsPerUnit = 24;
 __global__ void __launch_bounds__(256) combine2_kernel(const Tc2Params p, const t16* __restrict__ gate, long long ldg,
                                                        t16* __restrict__ out, long long ldo,
                                                        float* __restrict__ mass) {
+  __shared__ int s_n[4];
+  __shared__ int s_slot[4][kMaxSegsPerUnit];        // (cta * 2 + seg)
+  __shared__ float s_w[4][kMaxSegsPerUnit];         // l_s 2^(m_s - M) / L
+  __shared__ float s_M0, s_L0;
+  __shared__ int s_alo[kMaxSegsPerUnit], s_ahi[kMaxSegsPerUnit];   // unit-0 segments: tile range inside the unit
   const int i = blockIdx.x;
   const int qt = i / BM, r = i - qt * BM;
+  if (threadIdx.x < p.n_dv) {
+    const int k = threadIdx.x;
+    const int unit = qt * p.n_dv + k;
+    const long long u_lo = (long long)unit * p.TPU, u_hi = u_lo + p.TPU;
+    int c = (int)(((u_lo + 1) * p.nCTA - 1) / p.L);
+    int n = 0;
+    float M = -INFINITY;
+    for (; c < p.nCTA && n < kMaxSegsPerUnit; ++c) {
+      long long lo, hi;
+      cta_range(p, c, lo, hi);
+      if (lo >= u_hi) break;
+      if (hi <= lo) continue;
+      const int slot = c * 2 + (lo < u_lo ? 1 : 0);
+      s_slot[k][n] = slot;
+      if (k == 0) {
+        s_alo[n] = (int)((lo > u_lo ? lo : u_lo) - u_lo);
+        s_ahi[n] = (int)((hi < u_hi ? hi : u_hi) - u_lo);
+      }
+      M = fmaxf(M, p.part_ml[((long long)slot * BM + r) * 2]);
+      ++n;
+    }
+    float L = 0.f;
+    for (int e = 0; e < n; ++e) {
+      const float* ml = p.part_ml + ((long long)s_slot[k][e] * BM + r) * 2;
+      const float w = exp2f(ml[0] - M) * ml[1];
+      s_w[k][e] = w;
+      L += w;
+    }
+    const float inv = 1.f / L;
+    for (int e = 0; e < n; ++e) s_w[k][e] *= inv;
+    s_n[k] = n;
+    if (k == 0) { s_M0 = M; s_L0 = L; }
+  }
+  __syncthreads();
   const int col = threadIdx.x * 4;
   if (col < p.Dv) {
     const int k = col / DVC, cc = col - k * DVC;
-    const int unit = qt * p.n_dv + k;
-    const long long u_lo = (long long)unit * p.TPU, u_hi = u_lo + p.TPU;
-    const int c_first = (int)(((u_lo + 1) * p.nCTA - 1) / p.L);
-    float M = -INFINITY;
-    for (int c = c_first; c < p.nCTA; ++c) {
-      long long lo, hi;
-      cta_range(p, c, lo, hi);
-      if (lo >= u_hi) break;
-      if (hi <= lo) continue;
-      const int s = lo < u_lo ? 1 : 0;
-      M = fmaxf(M, p.part_ml[((long long)(c * 2 + s) * BM + r) * 2]);
-    }
-    float L = 0.f;
+    const int n = s_n[k];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = c_first; c < p.nCTA; ++c) {
-      long long lo, hi;
-      cta_range(p, c, lo, hi);
-      if (lo >= u_hi) break;
-      if (hi <= lo) continue;
-      const int s = lo < u_lo ? 1 : 0;
-      const float* ml = p.part_ml + ((long long)(c * 2 + s) * BM + r) * 2;
-      const float w = exp2f(ml[0] - M) * ml[1];
-      L += w;
-      const uint2 u = *reinterpret_cast<const uint2*>(p.part_o + ((long long)(c * 2 + s) * BM + r) * DVC + cc);
+    for (int e = 0; e < n; ++e) {
+      const float w = s_w[k][e];
+      const uint2 u = *reinterpret_cast<const uint2*>(p.part_o + ((long long)s_slot[k][e] * BM + r) * DVC + cc);
       const float2 a = unpack2(u.x), b = unpack2(u.y);
       acc.x += w * a.x; acc.y += w * a.y; acc.z += w * b.x; acc.w += w * b.y;
     }
-    const float inv = 1.f / L;
-    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     if (gate) {
       const uint2 g = *reinterpret_cast<const uint2*>(gate + (long long)i * ldg + col);
       const float2 g0 = unpack2(g.x), g1 = unpack2(g.y);
@@ -451,35 +557,16 @@ __global__ void __launch_bounds__(256) combine2_kernel(const Tc2Params p, const 
   }
   if (mass && threadIdx.x < p.T) {
     const int t = threadIdx.x;
-    const int unit = qt * p.n_dv;
-    const long long u_lo = (long long)unit * p.TPU, u_hi = u_lo + p.TPU;
-    const int c_first = (int)(((u_lo + 1) * p.nCTA - 1) / p.L);
-    float M = -INFINITY;
-    for (int c = c_first; c < p.nCTA; ++c) {
-      long long lo, hi;
-      cta_range(p, c, lo, hi);
-      if (lo >= u_hi) break;
-      if (hi <= lo) continue;
-      const int s = lo < u_lo ? 1 : 0;
-      M = fmaxf(M, p.part_ml[((long long)(c * 2 + s) * BM + r) * 2]);
-    }
-    float L = 0.f, a = 0.f;
-    const long long f_lo = u_lo + (long long)t * p.tpf, f_hi = f_lo + p.tpf;
-    for (int c = c_first; c < p.nCTA; ++c) {
-      long long lo, hi;
-      cta_range(p, c, lo, hi);
-      if (lo >= u_hi) break;
-      if (hi <= lo) continue;
-      const int s = lo < u_lo ? 1 : 0;
-      const float* ml = p.part_ml + ((long long)(c * 2 + s) * BM + r) * 2;
-      L += exp2f(ml[0] - M) * ml[1];
-      const long long a_lo = lo > u_lo ? lo : u_lo, a_hi = hi < u_hi ? hi : u_hi;   // this CTA's tiles of the unit
-      if (a_lo < f_hi && f_lo < a_hi) {
-        const float* pc = p.pieces + (((long long)(c * 2 + s) * p.T + t) * BM + r) * 2;
-        a += exp2f(pc[0] - M) * pc[1];
+    const int f_lo = t * p.tpf, f_hi = f_lo + p.tpf;
+    const float M = s_M0, invL = 1.f / s_L0;
+    float a = 0.f;
+    for (int e = 0; e < s_n[0]; ++e) {
+      if (s_alo[e] < f_hi && f_lo < s_ahi[e]) {
+        const float* pc = p.pieces + ((((long long)s_slot[0][e] * p.T + t) * 2) * BM + r) * 2;
+        a += exp2f(pc[0] - M) * pc[1] + exp2f(pc[BM * 2] - M) * pc[BM * 2 + 1];
       }
     }
-    mass[(long long)i * p.T + t] = a / L;
+    mass[(long long)i * p.T + t] = a * invL;
   }
 }
 
@@ -500,7 +587,10 @@ void schedule(int HW, int T, int Dv, int* n_units, int* tpf, int* TPU, int* nCTA
   *TPU = T * *tpf;
   const long long L = (long long)*n_units * *TPU;
   int n = sm_count();
-  if (n < *n_units) n = *n_units;          // a CTA never spans more than two units
+  if ((long long)n > L / 4) n = (int)(L / 4);                    // at least ~4 tiles per CTA
+  const int cap = (kMaxSegsPerUnit - 2) * *n_units;             // combine2 resolves <= kMaxSegsPerUnit segments per unit
+  if (n > cap) n = cap;
+  if (n < *n_units) n = *n_units;                               // a CTA never spans more than two units
   if ((long long)n > L) n = (int)L;
   *nCTA = n;
 }
@@ -512,11 +602,16 @@ size_t part_bytes(int nCTA, int T, size_t* off_ml, size_t* off_pieces) {
   o += (size_t)nCTA * 2 * BM * 2 * sizeof(float);
   o = (o + 255) & ~size_t(255);
   *off_pieces = o;
-  o += (size_t)nCTA * 2 * T * BM * 2 * sizeof(float);
+  o += (size_t)nCTA * 2 * T * 2 * BM * 2 * sizeof(float);
   return o + 256;
 }
 
 }  // namespace
+
+int long_attn_tc2_set_trace(long long* dev_buf) {
+  RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)));
+  return RMEM_OK;
+}
 
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv) {
   (void)HWp;

@@ -50,6 +50,7 @@ int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream) {
   p.C = d->C; p.ldc = d->ldc; p.c_fp32 = d->c_is_f32;
   p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_fp32 = d->c2_is_f32;
   p.n_split = d->C2 ? d->n_split : (1 << 30);
+  p.pad_n_ok = d->pad_n_ok;
   return gemm_launch(p, STREAM(stream));
 }
 
@@ -83,6 +84,8 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
   if (impl == RMEM_ATTN_TC) return long_attn_tc(a, workspace, workspace_bytes, STREAM(stream));
   return long_attn_dense(a, workspace, workspace_bytes, STREAM(stream));
 }
+
+int rmem_debug_attn_trace(void* dev_buf) { return long_attn_tc2_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 
 int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
                    float scale, void* qt, float* qbias, int P, int C, void* stream) {

@@ -433,7 +433,7 @@ struct rmem_engine {
     // short-term windowed attention over the previous frame
     {
       Lin p;
-      p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 225; p.n_weight_rows = 256;
+      p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
       p.w = pre + ".short.rel"; p.C = rel; p.ldc = 256; p.c_fp32 = 1;
       RMEM_TRY(linear(p, s));
       RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
@@ -462,7 +462,7 @@ struct rmem_engine {
         GemmParams q;
         q.A = w; q.lda = kD; q.B = z + half * kD; q.ldb = 2 * kD;
         q.M = 2 * kD; q.N = G.HW; q.K = kD;
-        q.bias = b; q.bias_m = 1; q.act = ACT_SILU;
+        q.bias = b; q.bias_m = 1; q.act = ACT_SILU; q.pad_n_ok = 1;   // pad key columns are masked by the attention
         q.C = vt_self + (size_t)half * 2 * kD * G.HWp; q.ldc = G.HWp;
         RMEM_TRY(gemm_launch(q, s));
         Lin u;

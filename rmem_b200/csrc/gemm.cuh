@@ -35,6 +35,9 @@ struct GemmParams {
   long long ldc2 = 0;
   int c2_fp32 = 0;
   int n_split = 1 << 30;
+  // N % 32 != 0 only: columns N .. round_up(N,32)-1 of C may be written with padding values (no residual / gate /
+  // per-column bias in that case).  Lets the tcgen05 kernel store whole 32-column chunks.
+  int pad_n_ok = 0;
 };
 
 // Launches the best kernel for the shape: the tcgen05/TMA kernel (gemm_tc.cu) whenever its alignment rules hold,

@@ -26,7 +26,7 @@ constexpr int kTcThreads = 192;
 constexpr int SMEM_A_STAGE = TBM * TBK * 2;   // 16 KB
 
 struct TcGemmParams {
-  int M, N, nk;
+  int M, N, nk, stages;
   int conv, taps_w, cin_blocks, pad, stride, BW, BH, tiles_x, Hout, Wout;
   float alpha;
   const float* bias;
@@ -45,12 +45,13 @@ struct TcGemmParams {
   int* err;
 };
 
-template <int BN, int STAGES>
+constexpr int kMaxStages = 6;
+template <int BN>
 struct TcSmem {
   static constexpr int kB = BN * TBK * 2;
   static constexpr int kStage = SMEM_A_STAGE + kB;
-  static constexpr int kBar = STAGES * kStage;
-  static constexpr int kTotal = kBar + 256 + 1024;   // barriers + alignment slack
+  // [1024B-aligned] stages x (A | B) tiles, then the barriers
+  static constexpr int total(int stages) { return stages * kStage + 256 + 1024; }   // + barriers + alignment slack
 };
 
 __device__ __forceinline__ void load8h(const t16* p, float* v) {
@@ -59,15 +60,16 @@ __device__ __forceinline__ void load8h(const t16* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
-template <int BN, int STAGES>
+template <int BN>
 __global__ void __launch_bounds__(kTcThreads)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcGemmParams p) {
-  using L = TcSmem<BN, STAGES>;
+  using L = TcSmem<BN>;
+  const int STAGES = p.stages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage);
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES;
@@ -96,6 +98,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Programmatic dependent launch: the next kernel in the stream may start its own prologue now (this CTA already
+  // holds its TMEM), and nothing above touched global memory, so the previous kernel's tail overlapped our prologue.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -151,17 +157,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       valid = gm < p.M;
     }
     const float bias_row = (p.bias && p.bias_m && valid) ? p.bias[gm] : 0.f;
+    // Prefetch this row's residual for the whole tile while the main loop runs (full 32-column chunks only): the
+    // epilogue would otherwise serialise one L2 round trip per chunk.
+    constexpr bool kPre = BN == 128;
+    uint4 rpre[kPre ? BN / 8 : 1];
+    const bool res_pre = kPre && p.res != nullptr && valid;
+    if (res_pre) {
+      const t16* rp = p.res + gm * p.ldr + n0;
+#pragma unroll
+      for (int c = 0; c < BN / 8; ++c)
+        if (n0 + c * 8 < p.N) rpre[c] = *reinterpret_cast<const uint4*>(rp + c * 8);
+    }
     mbar_wait(acc_full, 0, p.err, 3);
     fence_after();
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    auto chunk = [&](const int c0) {
       const int n = n0 + c0;
-      if (n >= p.N) break;                           // warp-uniform
+      if (n >= p.N) return;                          // warp-uniform
       float v[32];
       tmem_ld32(lane_addr + c0, v);
-      if (!valid) continue;
-      const bool full_chunk = (n + 32 <= p.N);
+      if (!valid) return;
       // destination of this 32-column chunk (n_split is a multiple of 32)
       void* base = p.C;
       long long ld = p.ldc;
@@ -169,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (n >= p.n_split) { base = p.C2; ld = p.ldc2; nn = n - p.n_split; f32 = p.c2_fp32; }
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.alpha, bias_row);
-      if (full_chunk) {
+      {
         if (p.bias && !p.bias_m) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -178,13 +193,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         if (p.res) {
-          const t16* rp = p.res + gm * p.ldr + n;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            float t[8];
-            load8h(rp + j, t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[j + e] += t[e];
+            const uint4 u = kPre ? rpre[kPre ? (c0 + j) / 8 : 0]
+                                 : *reinterpret_cast<const uint4*>(p.res + gm * p.ldr + n + j);
+            const float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
+            v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
+            v[j + 4] += c.x; v[j + 5] += c.y; v[j + 6] += d.x; v[j + 7] += d.y;
           }
         }
         if (p.act == ACT_RELU) {
@@ -226,27 +241,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             *reinterpret_cast<uint4*>(o + j) = u;
           }
         }
-      } else {
-        // ragged last chunk: scalar path
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (n + j >= p.N) continue;
-          float x = v[j];
-          if (p.bias && !p.bias_m) x += p.bias[n + j];
-          if (p.res) x += t2f(p.res[gm * p.ldr + n + j]);
-          if (n + j >= p.act_from) {
-            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-            else if (p.act == ACT_SILU) x = silu_f(x);
-          }
-          if (p.gate) x *= t2f(p.gate[gm * p.ldg + n + j]);
-          if (f32) {
-            float* o = reinterpret_cast<float*>(base) + gm * ld + nn + j;
-            *o = p.accumulate ? (*o + x) : x;
-          } else {
-            reinterpret_cast<t16*>(base)[gm * ld + nn + j] = f2t(x);
-          }
-        }
       }
+    };
+    if constexpr (kPre) {
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) chunk(c0);
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) chunk(c0);
     }
     fence_before();
   }
@@ -257,17 +259,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-template <int BN, int STAGES>
-int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, const TcGemmParams& p, int m_tiles, cudaStream_t s) {
-  using L = TcSmem<BN, STAGES>;
+template <int BN>
+int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int m_tiles, int max_stages,
+              cudaStream_t s) {
+  using L = TcSmem<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    RMEM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kTotal));
+    RMEM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::total(kMaxStages)));
     attr_done = true;
   }
-  dim3 grid(cdiv(p.N, BN), m_tiles);
-  gemm_tc_kernel<BN, STAGES><<<grid, kTcThreads, L::kTotal, s>>>(*ma, *mb, p);
+  // Only as many stages as there are k-blocks: short-K GEMMs (most of the encoder) are latency-bound, and a small
+  // shared-memory footprint lets several CTAs share an SM so one CTA's epilogue overlaps another's loads.
+  p.stages = p.nk < max_stages ? p.nk : max_stages;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(p.N, BN), m_tiles);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = L::total(p.stages);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RMEM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, *ma, *mb, static_cast<const TcGemmParams&>(p)));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -276,6 +291,10 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, const TcGemmParams& 
 
 bool gemm_tc_supported(const GemmParams& p) {
   if (p.K % TBK != 0) return false;
+  // the epilogue stores whole 32-column chunks: ragged N only when the caller says the padding columns are writable
+  if (p.N % 32 != 0 && !(p.pad_n_ok && p.n_split >= p.N && p.ldc >= round_up(p.N, 32) && !p.res && !p.gate &&
+                         (!p.bias || p.bias_m)))
+    return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return false;
   if (p.ldb % 8 != 0) return false;
   if (p.n_split < p.N && p.n_split % 32 != 0) return false;
@@ -299,7 +318,7 @@ bool gemm_tc_supported(const GemmParams& p) {
 int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
   RMEM_REQUIRE(gemm_tc_supported(g), "gemm_tc: unsupported shape/alignment (M=%d N=%d K=%d)", g.M, g.N, g.K);
   TcGemmParams p;
-  p.M = g.M; p.N = g.N; p.nk = g.K / TBK;
+  p.M = g.M; p.N = round_up(g.N, 32); p.nk = g.K / TBK;
   p.conv = g.conv; p.taps_w = g.kw; p.cin_blocks = g.conv ? g.Cin / TBK : 1; p.pad = g.pad; p.stride = g.stride;
   p.BW = 128; p.BH = 1; p.tiles_x = 1; p.Hout = 0; p.Wout = g.Wout;
   p.alpha = g.alpha; p.bias = g.bias; p.bias_m = g.bias_m; p.act = g.act; p.act_from = g.act_from;
@@ -345,9 +364,9 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
     uint32_t box[2] = {(uint32_t)TBK, (uint32_t)BN};
     RMEM_TRY(tma_encode_cached(&mb, g.B, 2, dims, strides, box, nullptr));
   }
-  if (BN == 64) return launch_tc<64, 4>(ma, mb, p, m_tiles, stream);
-  if (BN == 128) return launch_tc<128, 3>(ma, mb, p, m_tiles, stream);
-  return launch_tc<256, 4>(ma, mb, p, m_tiles, stream);
+  if (BN == 64) return launch_tc<64>(ma, mb, p, m_tiles, 4, stream);
+  if (BN == 128) return launch_tc<128>(ma, mb, p, m_tiles, 3, stream);
+  return launch_tc<256>(ma, mb, p, m_tiles, 4, stream);
 }
 
 }  // namespace rmem
