@@ -127,13 +127,20 @@ CASES = {
     "deaot_small_10obj": ("r50_deaotl", 0, 4.0, 257, 321, 10, 14, 1, 3, 2, (256, 320)),
     "deaot_small_xavier": ("r50_deaotl", 1, 1.0, 257, 321, 3, 8, 1, 2, 2, (257, 321)),
     "deaot_13obj_2engines": ("r50_deaotl", 2, 4.0, 193, 257, 13, 7, 1, 2, 2, (193, 257)),
+    # BASELINE.json configs[0] (c1): R50_AOTL, 256x256 -> 257x257, 1 object, T = 1 (reference frame only)
+    "aot_c1_256_t1": ("r50_aotl", 3, 1.0, 257, 257, 1, 3, 1, 1, 9999, (256, 256)),
+    # AOT + RMem: restricted bank (1 + 2), eviction active, sharpened attention
+    "aot_small_rmem": ("r50_aotl", 4, 4.0, 193, 257, 3, 11, 1, 2, 2, (193, 257)),
 }
 
 
 def main():
     torch.set_num_threads(8)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    only = sys.argv[1:]
     for name, (model, seed, sharpen, H, W, n_obj, nfr, former, latter, gap, out_size) in CASES.items():
+        if only and name not in only:
+            continue
         sd = O.make_state_dict(model, seed=seed, sharpen=sharpen)
         frames = O.synthetic_frames(nfr, H, W, seed=seed + 1)
         label0 = O.synthetic_label(H, W, n_obj)

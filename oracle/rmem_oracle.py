@@ -365,6 +365,7 @@ class Bank:
     long: List[List[LayerMem]] = field(default_factory=list)     # [layer][t]
     short: List[LayerMem] = field(default_factory=list)          # [layer]
     curr: List[LayerMem] = field(default_factory=list)           # [layer] from last forward
+    short_next: list = field(default_factory=list)               # AOT: [layer] [linear_QMem(o3), o3] of the last forward
     mass0: Optional[Tensor] = None                               # layer-0 [HW,T]
     evict: EvictState = field(default_factory=EvictState)
 
@@ -459,6 +460,110 @@ def gpm_forward(sd, tgt: Tensor, bank: Bank, id_emb: Optional[Tensor], h: int, w
                              sd["LSTT.decoder_norms.0.gn.bias"], 2)
 
 
+
+# --------------------------------------------------------------------------------------
+# AOT LSTT layer (transformer.py:553-692) -- stage pre_vost (MODEL_LINEAR_Q = False)
+# --------------------------------------------------------------------------------------
+N_HEAD = 8            # configs/models/default.py:19-20  MODEL_SELF_HEADS / MODEL_ATT_HEADS
+
+
+@dataclass
+class AotMem:
+    K: Tensor                 # [HW,256]
+    V: Tensor                 # [HW,256]
+
+
+def mha(sd, prefix: str, Q: Tensor, K: Tensor, V: Tensor, use_linear: bool, n_head: int = N_HEAD
+        ) -> Tuple[Tensor, Tensor]:
+    """MultiheadAttention.forward (attention.py:28-81) on [L, C] tensors (bs = 1).
+    Returns (projection(concat_h softmax(Q_h K_h^T / sqrt(d)) V_h), attn [h, Lq, Lk])."""
+    if use_linear:
+        Q, K, V = lin(sd, prefix + ".linear_Q", Q), lin(sd, prefix + ".linear_K", K), lin(sd, prefix + ".linear_V", V)
+    C = Q.shape[1]
+    d = C // n_head
+    qh = (Q / math.sqrt(d)).view(-1, n_head, d).permute(1, 0, 2)
+    kh = K.view(-1, n_head, d).permute(1, 2, 0)
+    vh = V.view(-1, n_head, d).permute(1, 0, 2)
+    attn = torch.softmax(qh @ kh, dim=-1)
+    out = (attn @ vh).permute(1, 0, 2).reshape(Q.shape[0], C)
+    return lin(sd, prefix + ".projection", out), attn
+
+
+def gn_gelu_dwconv(sd, prefix: str, x: Tensor, h: int, w: int) -> Tensor:
+    """GNActDWConv2d (basic.py:15-35): GroupNorm(32) -> GELU -> depthwise 5x5, token-major [HW, C]."""
+    m = tokens_to_map(x, h, w)
+    m = F.group_norm(m, 32, sd[prefix + ".gn.weight"], sd[prefix + ".gn.bias"], 1e-5)
+    m = F.gelu(m)
+    m = F.conv2d(m, sd[prefix + ".conv.weight"], None, padding=2, groups=m.shape[1])
+    return map_to_tokens(m)
+
+
+def aot_layer(sd, l: int, tgt: Tensor, bank: "Bank", id_emb: Optional[Tensor], pos: Tensor, h: int, w: int
+              ) -> Tuple[Tensor, AotMem, AotMem, dict]:
+    """SimplifiedTransformerBlock.forward.  Returns (tgt', curr=[K, V], short'=[local_K, local_V], dbg)."""
+    p = f"LSTT.layers.{l}"
+    # self-attention with sine PE on q, k (:566-571)
+    t = ln(sd, p + ".norm1", tgt)
+    qk = t + pos
+    o1, _ = mha(sd, p + ".self_attn", qk, qk, t, use_linear=True)
+    tgt = tgt + o1
+    # long / short term attention (:574-680)
+    t = ln(sd, p + ".norm2", tgt)
+    Q = lin(sd, p + ".linear_Q", t)
+    K, V = Q, t
+    if id_emb is not None:                                        # reference frame (:582-588)
+        gV = lin(sd, p + ".linear_V", V + id_emb)
+        longs = [AotMem(K, gV)]
+        short = AotMem(K, gV)
+    else:
+        longs, short = bank.long[l], bank.short[l]
+    T = len(longs)
+    pe = temporal_pe(sd["mem_pos_emb"], T)                        # [T,256]
+    Kt = torch.stack([m.K for m in longs]) + pe.view(T, 1, -1)
+    Vt = torch.stack([m.V for m in longs])
+    Qt = Q + sd["cur_pos_emb"].view(1, -1)
+    o2, attn = mha(sd, p + ".long_term_attn", Qt, Kt.flatten(0, 1), Vt.flatten(0, 1), use_linear=False)
+    HW = Q.shape[0]
+    mass = attn.view(N_HEAD, HW, T, HW).mean(0).sum(-1)           # [HW, T]  (:636-643)
+    o3, _ = mha(sd, p + ".short_term_attn", Q, ln(sd, p + ".norm4", short.K + K),
+                ln(sd, p + ".norm4", short.V + V), use_linear=False)        # (:656-662)
+    local_K = lin(sd, p + ".linear_QMem", o3)
+    local_V = o3
+    if id_emb is not None:
+        local_V = lin(sd, p + ".linear_VMem", local_V + id_emb)   # (:677-678)
+    tgt = tgt + o2 + o3
+    # feed-forward (:683-687)
+    t = ln(sd, p + ".norm3", tgt)
+    ff = lin(sd, p + ".linear2", gn_gelu_dwconv(sd, p + ".activation", lin(sd, p + ".linear1", t), h, w))
+    tgt = tgt + ff
+    dbg = dict(Q=Q, V=V, o1=o1, o2=o2, o3=o3, mass=mass, ff=ff)
+    if id_emb is not None:
+        dbg["ref_long"] = longs[0]
+    return tgt, AotMem(K, V), AotMem(local_K, local_V), dbg
+
+
+def lstt_forward(sd, tgt: Tensor, bank: "Bank", id_emb: Optional[Tensor], pos: Tensor, h: int, w: int,
+                 collect: Optional[list] = None) -> List[Tensor]:
+    """LongShortTermTransformer.forward (transformer.py:199-267): three LayerNormed layer outputs."""
+    bank.curr, bank.short_next = [], []
+    outs, ref_long = [], []
+    for l in range(3):
+        tgt, curr, short_next, dbg = aot_layer(sd, l, tgt, bank, id_emb, pos, h, w)
+        bank.curr.append(curr)
+        bank.short_next.append(short_next)
+        if l == 0 and id_emb is None:
+            bank.mass0 = dbg["mass"]
+        if id_emb is not None:
+            ref_long.append(dbg["ref_long"])
+        if collect is not None:
+            collect.append(dbg)
+        outs.append(ln(sd, f"LSTT.decoder_norms.{l}", tgt))
+    if id_emb is not None:                                        # init_memory (:438-443)
+        bank.long = [[m] for m in ref_long]
+        bank.short = list(bank.short_next)
+        bank.evict = EvictState()
+    return outs
+
 # --------------------------------------------------------------------------------------
 # engine state machine
 # --------------------------------------------------------------------------------------
@@ -474,12 +579,19 @@ class OracleSubEngine:
         self.pred_id_logits: Optional[Tensor] = None
         self.hw: Tuple[int, int] = (0, 0)
         self.dbg: Optional[list] = None
+        self.pos: Optional[Tensor] = None
 
     def _lstt(self, feats, id_emb):
         h, w = feats[-1].shape[-2:]
         self.hw = (h, w)
         tgt = map_to_tokens(feats[-1])
-        out = gpm_forward(self.sd, tgt, self.bank, id_emb, h, w, collect=self.dbg)
+        if self.cfg.is_deaot:
+            out = gpm_forward(self.sd, tgt, self.bank, id_emb, h, w, collect=self.dbg)
+        else:                                                     # aot.py:136-142: cat(proj16x, l0, l1, l2)
+            if self.pos is None or self.pos.shape[0] != h * w:
+                self.pos = sine_pos_emb(h, w, self.cfg.d_model)   # aot_engine.py:289-292 (once per clip)
+            outs = lstt_forward(self.sd, tgt, self.bank, id_emb, self.pos, h, w, collect=self.dbg)
+            out = torch.cat([tgt] + outs, dim=1)
         self.pred_id_logits = decode_logits(self.sd, tokens_to_map(out, h, w), feats)
         return self.pred_id_logits
 
@@ -505,15 +617,24 @@ class OracleSubEngine:
         is_long = self.frame_step - self.last_mem_step >= self.gap
         if is_long:
             self.last_mem_step = self.frame_step
-        for l in range(3):                                        # transformer.py:826-857
-            c = bank.curr[l]
-            c.ID_V = fuse_id(sd, l, c.curr_ID_V, id_emb)
-        bank.short = [LayerMem(c.K, c.V, c.ID_V) for c in bank.curr]
+        if cfg.is_deaot:
+            for l in range(3):                                    # transformer.py:826-857
+                c = bank.curr[l]
+                c.ID_V = fuse_id(sd, l, c.curr_ID_V, id_emb)
+            bank.short = [LayerMem(c.K, c.V, c.ID_V) for c in bank.curr]
+        else:
+            for l in range(3):                                    # transformer.py:269-304
+                p = f"LSTT.layers.{l}"
+                bank.curr[l].V = lin(sd, p + ".linear_V", bank.curr[l].V + id_emb)
+                bank.short_next[l].V = lin(sd, p + ".linear_VMem", bank.short_next[l].V + id_emb)
+            bank.short = list(bank.short_next)
         if is_long:
             for l in range(3):
                 c = bank.curr[l]
-                bank.long[l].append(LayerMem(c.K, c.V, c.ID_V))
+                bank.long[l].append(LayerMem(c.K, c.V, c.ID_V) if cfg.is_deaot else AotMem(c.K, c.V))
             self.long_memories_indexes.append(self.frame_step)
+            if (not cfg.is_deaot) and len(bank.long[0]) <= cfg.former_mem_len + cfg.latter_mem_len:
+                return                                            # AOT only: early return, no state change (:332-334)
             lg = F.interpolate(self.pred_id_logits, size=(h, w), mode="bilinear", align_corners=True)
             fg = 1 - torch.softmax(lg, dim=1)[0, 0].flatten()     # aot_engine.py:355-362
             rel = evict_scores(bank.mass0, fg)
@@ -529,7 +650,6 @@ class OracleEngine:
     """Mirror of DeAOTInferEngine (deaot_engine.py:20-56 + aot_engine.py:571-725)."""
 
     def __init__(self, sd, cfg: OracleConfig, long_term_mem_gap: int = 9999):
-        assert cfg.is_deaot, "oracle engine currently restates the DeAOT path"
         self.sd, self.cfg = sd, cfg
         self.long_term_mem_gap = long_term_mem_gap
         self.restart_engine()

@@ -36,6 +36,25 @@ int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_byt
 size_t long_attn_tc_workspace(int HW, int HWp, int nslots, int Dv);
 int long_attn_tc(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
+// Multi-head attention over a bank (AOT: 8 heads x 32): q [HW, H*dh] (row stride ldq), kbank [nslots][HWp][H*dh],
+// vtbank [H*dh][nslots*HWp], qbias [H][HW][T] or null, out [HW, H*dh] (row stride ldo), mass [HW, T] = head mean or null.
+struct MhaArgs {
+  const t16* q = nullptr;
+  long long ldq = 0;
+  const t16* kbank = nullptr;
+  const t16* vtbank = nullptr;
+  int nslots = 1, T = 1;
+  int slot[kMaxBankFrames] = {0};
+  int HW = 0, HWp = 0, H = 8, dh = 32;
+  float scale = 1.f;
+  const float* qbias = nullptr;
+  t16* out = nullptr;
+  long long ldo = 0;
+  float* mass = nullptr;
+};
+size_t mha_dense_workspace(int HW, int HWp, int nslots, int H);
+int mha_dense(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
 // v2 (attn_tc2.cu): stream-K schedule over the SMs, 8 softmax warps, P through TMEM, fp16 partials.
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv);
 int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);

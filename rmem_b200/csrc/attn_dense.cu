@@ -3,6 +3,7 @@
 // the fused tcgen05 kernel in attn_tc.cu is the fast one and is checked against it on the GPU.
 #include "attn.cuh"
 #include "gemm.cuh"
+#include "ops.cuh"
 
 namespace rmem {
 
@@ -17,11 +18,13 @@ __global__ void softmax_mass_kernel(const float* __restrict__ S, t16* __restrict
   __shared__ float red[32];
   __shared__ float s_mass[kMaxBankFrames];
   const int row = blockIdx.x;
-  const float* Sr = S + (long long)row * ld;
-  t16* Pr = P + (long long)row * ld;
+  // multi-head (AOT): blockIdx.y = head; S / P / qbias / mass are laid out [head][row][...]
+  const long long hrow = (long long)blockIdx.y * HW + row;
+  const float* Sr = S + hrow * ld;
+  t16* Pr = P + hrow * ld;
   float bias[kMaxBankFrames];
 #pragma unroll
-  for (int t = 0; t < kMaxBankFrames; ++t) bias[t] = (t < T && qbias) ? qbias[(long long)row * T + t] : 0.f;
+  for (int t = 0; t < kMaxBankFrames; ++t) bias[t] = (t < T && qbias) ? qbias[hrow * T + t] : 0.f;
 
   float mx = -INFINITY;
 #pragma unroll
@@ -67,7 +70,7 @@ __global__ void softmax_mass_kernel(const float* __restrict__ S, t16* __restrict
   }
   if (mass) {
     __syncthreads();
-    if (threadIdx.x < T) mass[(long long)row * T + threadIdx.x] = s_mass[threadIdx.x];
+    if (threadIdx.x < T) mass[hrow * T + threadIdx.x] = s_mass[threadIdx.x];
   }
 }
 
@@ -202,6 +205,49 @@ int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_byt
   g.M = a.HW; g.N = a.Dv; g.K = (int)ld;
   g.gate = a.gate; g.ldg = a.ldg;
   g.C = a.out; g.ldc = a.ldo; g.c_fp32 = 0;
+  return gemm_launch(g, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-head attention over the bank, materialised scores (AOT MultiheadAttention, attention.py:28-81 and the mass
+// record of transformer.py:636-643): head-batched legacy GEMMs (head dim 32 is below the tcgen05 kernel's K = 64 atom).
+size_t mha_dense_workspace(int HW, int HWp, int nslots, int H) {
+  size_t cols = (size_t)nslots * HWp;
+  return (size_t)H * HW * cols * (sizeof(float) + sizeof(t16)) + (size_t)H * HW * kMaxBankFrames * sizeof(float) + 512;
+}
+
+int mha_dense(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  RMEM_REQUIRE(a.T >= 1 && a.T <= kMaxBankFrames && a.T <= a.nslots, "mha: T=%d nslots=%d", a.T, a.nslots);
+  RMEM_REQUIRE(a.HWp % 8 == 0 && a.HWp >= a.HW && a.dh % 8 == 0, "mha: HWp=%d HW=%d dh=%d", a.HWp, a.HW, a.dh);
+  RMEM_REQUIRE(workspace_bytes >= mha_dense_workspace(a.HW, a.HWp, a.nslots, a.H), "mha: workspace too small");
+  const int C = a.H * a.dh;
+  const long long ld = (long long)a.nslots * a.HWp;
+  float* S = reinterpret_cast<float*>(workspace);
+  t16* P = reinterpret_cast<t16*>(S + (size_t)a.H * a.HW * ld);
+  float* mass_h = reinterpret_cast<float*>(reinterpret_cast<char*>(P) + (((size_t)a.H * a.HW * ld * sizeof(t16) + 255) & ~size_t(255)));
+  for (int t = 0; t < a.T; ++t) {
+    RMEM_REQUIRE(a.slot[t] >= 0 && a.slot[t] < a.nslots, "mha: bad slot");
+    GemmParams g;
+    g.A = a.q; g.lda = a.ldq;
+    g.B = a.kbank + (size_t)a.slot[t] * a.HWp * C; g.ldb = C;
+    g.M = a.HW; g.N = a.HW; g.K = a.dh;
+    g.alpha = a.scale;
+    g.C = S + (size_t)a.slot[t] * a.HWp; g.ldc = ld; g.c_fp32 = 1;
+    g.batch = a.H; g.sA = a.dh; g.sB = a.dh; g.sC = (long long)a.HW * ld;
+    RMEM_TRY(gemm_launch(g, s));
+  }
+  SlotMap sm;
+  for (int t = 0; t < kMaxBankFrames; ++t) sm.slot[t] = t < a.T ? a.slot[t] : -1;
+  softmax_mass_kernel<<<dim3(a.HW, a.H), 256, 0, s>>>(S, P, ld, a.HW, a.HWp, a.nslots, a.T, sm, a.qbias,
+                                                      a.mass ? mass_h : nullptr);
+  RMEM_LAUNCH_CHECK();
+  if (a.mass) RMEM_TRY(mean_heads(mass_h, a.mass, a.H, (long long)a.HW * a.T, s));
+  GemmParams g;
+  g.A = P; g.lda = ld;
+  g.B = a.vtbank; g.ldb = ld;
+  g.M = a.HW; g.N = a.dh; g.K = (int)ld;
+  g.C = a.out; g.ldc = a.ldo; g.c_fp32 = 0;
+  g.batch = a.H; g.sA = (long long)a.HW * ld; g.sB = (long long)a.dh * ld; g.sC = a.dh;
   return gemm_launch(g, s);
 }
 

@@ -78,8 +78,19 @@ struct LayerState {
   t16* vtbank;      // [1024][nslots*HWp]
 };
 
+struct LayerStateA {  // AOT (SimplifiedTransformerBlock) per-layer memories, transformer.py:438-441, 689-692
+  t16* k_cur;       // [HWp,256]  Q = K of the current frame
+  t16* v_cur;       // [HW,256]   LN2(tgt) = V of the current frame
+  t16* v_lin;       // [HW,256]   linear_V(V + id): what the long bank stores
+  t16* sk[2];       // [HWp,256]  short-term K = linear_QMem(o3)
+  t16* sv[2];       // [HW,256]   short-term V = linear_VMem(o3 + id)
+  t16* kbank;       // [nslots][HWp][256]
+  t16* vtbank;      // [256][nslots*HWp]
+};
+
 struct Group {       // one AOTEngine: <= 10 objects, own bank (reference + per-engine deepcopy)
   LayerState L[kLayers];
+  LayerStateA A[kLayers];
   float* mass0;      // [HW,16] layer-0 attention mass of the last propagate (logical frame order)
   int mass_T = 0;
   float* logits4;    // planar [11, P4] = pred_id_logits
@@ -123,6 +134,12 @@ struct rmem_engine {
   char* arena_base = nullptr;
   size_t state_begin = 0, state_bytes = 0;   // region zeroed per clip (banks, short-term memory)
   bool ones_ready = false;
+  // AOT scratch (model 1)
+  float *a_pos = nullptr, *a_tgt = nullptr, *a_qbias = nullptr;
+  t16 *a_tln, *a_qkpos, *a_q, *a_k, *a_vt, *a_att, *a_o3, *a_sum, *a_n4k, *a_n4v, *a_n4vt, *a_ff1, *a_ff2, *a_decin, *a_qt;
+  void* mha_ws = nullptr;
+  size_t mha_ws_bytes = 0;
+  bool pos_ready = false;
 
   // ---------------------------------------------------------------------------------------------
   template <typename T>
@@ -175,6 +192,28 @@ struct rmem_engine {
     d2 = a.take<t16>((size_t)G.P4 * 128);
     stats = a.take<double>(kGnScratchDoubles);
     label8 = a.take<uint8_t>((size_t)G.H * G.W);
+    if (cfg.model == 1) {
+      a_pos = a.take<float>((size_t)G.HW * kD);
+      a_tgt = a.take<float>((size_t)G.HW * kD);
+      a_qbias = a.take<float>((size_t)8 * G.HW * kMaxBankFrames);
+      a_tln = a.take<t16>((size_t)G.HW * kD);
+      a_qkpos = a.take<t16>((size_t)G.HW * kD);
+      a_q = a.take<t16>((size_t)G.HWp * kD);
+      a_k = a.take<t16>((size_t)G.HWp * kD);
+      a_vt = a.take<t16>((size_t)kD * G.HWp);
+      a_att = a.take<t16>((size_t)G.HW * kD);
+      a_o3 = a.take<t16>((size_t)G.HW * kD);
+      a_sum = a.take<t16>((size_t)G.HW * kD);
+      a_n4k = a.take<t16>((size_t)G.HWp * kD);
+      a_n4v = a.take<t16>((size_t)G.HW * kD);
+      a_n4vt = a.take<t16>((size_t)kD * G.HWp);
+      a_ff1 = a.take<t16>((size_t)G.HW * 4 * kD);
+      a_ff2 = a.take<t16>((size_t)G.HW * 4 * kD);
+      a_decin = a.take<t16>((size_t)G.HW * 4 * kD);
+      a_qt = a.take<t16>((size_t)G.HW * kD);
+      mha_ws_bytes = mha_dense_workspace(G.HW, G.HWp, nslots, 8);
+      mha_ws = a.take<char>(mha_ws_bytes);
+    }
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
     size_t ws_tc = long_attn_tc_workspace(G.HW, G.HWp, nslots, kDv);
     size_t ws_tc2 = long_attn_tc2_workspace(G.HW, G.HWp, nslots, kDv);
@@ -183,7 +222,19 @@ struct rmem_engine {
     state_begin = a.off;
     groups.assign(cfg.max_engines, Group());
     for (auto& gr : groups) {
-      for (int l = 0; l < kLayers; ++l) {
+      for (int l = 0; l < kLayers && cfg.model == 1; ++l) {
+        LayerStateA& L = gr.A[l];
+        L.k_cur = a.take<t16>((size_t)G.HWp * kD);
+        L.v_cur = a.take<t16>((size_t)G.HW * kD);
+        L.v_lin = a.take<t16>((size_t)G.HW * kD);
+        for (int p = 0; p < 2; ++p) {
+          L.sk[p] = a.take<t16>((size_t)G.HWp * kD);
+          L.sv[p] = a.take<t16>((size_t)G.HW * kD);
+        }
+        L.kbank = a.take<t16>((size_t)nslots * G.HWp * kD);
+        L.vtbank = a.take<t16>((size_t)kD * nslots * G.HWp);
+      }
+      for (int l = 0; l < kLayers && cfg.model == 0; ++l) {
         LayerState& L = gr.L[l];
         for (int p = 0; p < 2; ++p) {
           L.kc[p] = a.take<t16>((size_t)G.HWp * kDk);
@@ -300,12 +351,13 @@ struct rmem_engine {
     int rc = RMEM_OK;
     const float* w = Wt<float>("idbank.w", (size_t)289 * 12 * kD, &rc);
     const float* b = Wt<float>("idbank.b", kD, &rc);
-    const float* lg = Wt<float>("id_norm.g", kD, &rc);
-    const float* lb = Wt<float>("id_norm.b", kD, &rc);
+    const float* lg = cfg.model == 0 ? Wt<float>("id_norm.g", kD, &rc) : nullptr;   // deaot.py:65-69 only
+    const float* lb = cfg.model == 0 ? Wt<float>("id_norm.b", kD, &rc) : nullptr;
     if (rc) return rc;
     RMEM_TRY(separate_label(label, label_is_f32, label8, G.H, G.W, gi, n_groups, s));
     RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s));
-    for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_t16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
+    if (cfg.model == 0)
+      for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_t16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
     return RMEM_OK;
   }
 
@@ -498,8 +550,13 @@ struct rmem_engine {
     const float* ob = Wt<float>("gpm.out_norm.b", 2 * kD, &rc);
     if (rc) return rc;
     RMEM_TRY(groupnorm_f32(res, og, ob, gpm_out, G.HW, 2 * kD, 2, 0, stats, s));
+    return fpn_decode(gr, gpm_out, 2 * kD, s);
+  }
 
-    // ---- FPN ----
+  // FPNSegmentationHead.forward (fpn.py:36-68): x16 [HW, cin] -> planar fp32 logits [11, P4].
+  int fpn_decode(Group& gr, const t16* x16, int cin, cudaStream_t s) {
+    const Geo& G = g;
+    int rc = RMEM_OK;
     auto gn = [&](const std::string& n, const t16* x, t16* y, int P, int C) -> int {
       int r2 = RMEM_OK;
       const float* gg = Wt<float>(n + ".gn.g", C, &r2);
@@ -507,7 +564,7 @@ struct rmem_engine {
       if (r2) return r2;
       return groupnorm_t16(x, gg, gb, y, P, C, 8, 1, stats, s);
     };
-    RMEM_TRY(conv(gpm_out, G.h, G.w, 2 * kD, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s));
+    RMEM_TRY(conv(x16, G.h, G.w, cin, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s));
     RMEM_TRY(gn("dec.conv_in", d0, d1, G.HW, 256));
     RMEM_TRY(conv(feat16, G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, d1, d0, s));
     RMEM_TRY(conv(d0, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s));
@@ -524,6 +581,182 @@ struct rmem_engine {
     const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);
     if (rc) return rc;
     return conv_out_logits(d1, wo, bo, gr.logits4, G.P4, 128, 11, s);
+  }
+
+  // =============================================================================================
+  // AOT (model 1): SimplifiedTransformerBlock / LongShortTermTransformer  (transformer.py:199-267, 553-692)
+  // =============================================================================================
+  int mha(const MhaArgs& a, cudaStream_t s) { return mha_dense(a, mha_ws, mha_ws_bytes, s); }
+
+  // y[HW,N] (t16 or fp32 accumulate) = x[HW,K] W^T + b
+  int lin_t16(const t16* x, long long ldx, int K, const std::string& w, int N, t16* y, long long ldy, cudaStream_t s) {
+    Lin p;
+    p.A = x; p.lda = ldx; p.M = g.HW; p.K = K; p.N = N; p.w = w; p.C = y; p.ldc = ldy;
+    return linear(p, s);
+  }
+  int lin_acc(const t16* x, long long ldx, int K, const std::string& w, int N, float* y, long long ldy, cudaStream_t s) {
+    Lin p;
+    p.A = x; p.lda = ldx; p.M = g.HW; p.K = K; p.N = N; p.w = w; p.C = y; p.ldc = ldy; p.c_fp32 = 1; p.accumulate = 1;
+    return linear(p, s);
+  }
+
+  int aot_layer(Group& gr, int l, bool ref_mode, cudaStream_t s) {
+    const Geo& G = g;
+    const std::string pre = "lstt." + std::to_string(l);
+    LayerStateA& L = gr.A[l];
+    const int cur = gr.parity, prev = gr.parity ^ 1;
+    const float scale = 1.f / sqrtf(32.f);
+    int rc = RMEM_OK;
+    auto normw = [&](const std::string& n, const float** gg, const float** bb) {
+      *gg = Wt<float>(pre + "." + n + ".g", kD, &rc);
+      *bb = Wt<float>(pre + "." + n + ".b", kD, &rc);
+    };
+    const float *g1, *b1, *g2, *b2, *g3, *b3, *g4, *b4;
+    normw("norm1", &g1, &b1); normw("norm2", &g2, &b2); normw("norm3", &g3, &b3); normw("norm4", &g4, &b4);
+    if (rc) return rc;
+
+    // ---- self-attention with sine PE on q, k (:566-571) ----
+    RMEM_TRY(layernorm(a_tgt, kD, g1, b1, a_tln, kD, a_qkpos, kD, G.HW, kD, s, a_pos));
+    RMEM_TRY(lin_t16(a_qkpos, kD, kD, pre + ".self.linear_Q", kD, a_q, kD, s));
+    RMEM_TRY(lin_t16(a_qkpos, kD, kD, pre + ".self.linear_K", kD, a_k, kD, s));
+    {
+      // v^T = W_V . t^T + b, value-major for the P.V contraction (bias along M)
+      const t16* w = Wt<t16>(pre + ".self.linear_V.w", (size_t)kD * kD, &rc);
+      const float* b = Wt<float>(pre + ".self.linear_V.b", kD, &rc);
+      if (rc) return rc;
+      GemmParams q;
+      q.A = w; q.lda = kD; q.B = a_tln; q.ldb = kD;
+      q.M = kD; q.N = G.HW; q.K = kD;
+      q.bias = b; q.bias_m = 1; q.pad_n_ok = 1;
+      q.C = a_vt; q.ldc = G.HWp;
+      RMEM_TRY(gemm_launch(q, s));
+    }
+    {
+      MhaArgs a;
+      a.q = a_q; a.ldq = kD; a.kbank = a_k; a.vtbank = a_vt; a.nslots = 1; a.T = 1; a.slot[0] = 0;
+      a.HW = G.HW; a.HWp = G.HWp; a.scale = scale; a.out = a_att; a.ldo = kD;
+      RMEM_TRY(mha(a, s));
+    }
+    RMEM_TRY(lin_acc(a_att, kD, kD, pre + ".self.proj", kD, a_tgt, kD, s));
+
+    // ---- long / short-term attention (:574-680) ----
+    RMEM_TRY(layernorm(a_tgt, kD, g2, b2, L.v_cur, kD, nullptr, 0, G.HW, kD, s));       // V = LN2(tgt)
+    RMEM_TRY(lin_t16(L.v_cur, kD, kD, pre + ".linear_Q", kD, L.k_cur, kD, s));            // Q = K
+    const t16 *sk, *sv;
+    int T;
+    MhaArgs la;
+    if (ref_mode) {
+      RMEM_TRY(add_t16(L.v_cur, kD, idemb, kD, a_sum, kD, G.HW, kD, s));
+      RMEM_TRY(lin_t16(a_sum, kD, kD, pre + ".linear_V", kD, L.v_lin, kD, s));            // global_V (:584)
+      RMEM_TRY(copy2d_t16(L.k_cur, kD, L.kbank, kD, G.HW, kD, s));                        // bank := this frame, slot 0
+      RMEM_TRY(transpose_t16(L.v_lin, kD, L.vtbank, (long long)nslots * G.HWp, G.HW, kD, s));
+      T = 1;
+      la.slot[0] = 0;
+      sk = L.k_cur; sv = L.v_lin;
+    } else {
+      T = (int)gr.slots.size();
+      for (int t = 0; t < T; ++t) la.slot[t] = gr.slots[t];
+      sk = L.sk[prev]; sv = L.sv[prev];
+    }
+    {
+      const float* pc = Wt<float>("cur_pos_emb", kD, &rc);
+      const float* pm = Wt<float>("mem_pos_emb", 4 * kD, &rc);
+      if (rc) return rc;
+      int pe_slot[kMaxBankFrames];
+      temporal_pe_slots(T, 4, pe_slot);
+      RMEM_TRY(qprep_heads(L.k_cur, kD, pc, pm, pe_slot, T, scale, a_qt, a_qbias, G.HW, 8, s));
+    }
+    la.q = a_qt; la.ldq = kD; la.kbank = L.kbank; la.vtbank = L.vtbank; la.nslots = nslots; la.T = T;
+    la.HW = G.HW; la.HWp = G.HWp; la.scale = scale; la.qbias = a_qbias; la.out = a_att; la.ldo = kD;
+    la.mass = (l == 0 && !ref_mode) ? gr.mass0 : nullptr;
+    if (la.mass) gr.mass_T = T;
+    RMEM_TRY(mha(la, s));
+    RMEM_TRY(lin_acc(a_att, kD, kD, pre + ".long.proj", kD, a_tgt, kD, s));               // tgt += tgt2
+
+    // short-term: MHA(Q, LN4(local_K + K), LN4(local_V + V))  (:656-662) -- dense over the previous frame
+    RMEM_TRY(add_layernorm_t16(sk, kD, L.k_cur, kD, g4, b4, a_n4k, kD, G.HW, kD, s));
+    RMEM_TRY(add_layernorm_t16(sv, kD, L.v_cur, kD, g4, b4, a_n4v, kD, G.HW, kD, s));
+    RMEM_TRY(transpose_t16(a_n4v, kD, a_n4vt, G.HWp, G.HW, kD, s));
+    {
+      MhaArgs a;
+      a.q = L.k_cur; a.ldq = kD; a.kbank = a_n4k; a.vtbank = a_n4vt; a.nslots = 1; a.T = 1; a.slot[0] = 0;
+      a.HW = G.HW; a.HWp = G.HWp; a.scale = scale; a.out = a_att; a.ldo = kD;
+      RMEM_TRY(mha(a, s));
+    }
+    RMEM_TRY(lin_t16(a_att, kD, kD, pre + ".short.proj", kD, a_o3, kD, s));                // tgt3
+    RMEM_TRY(accum_t16_into_f32(a_o3, kD, a_tgt, kD, G.HW, kD, s));                        // tgt += tgt3
+    // next frame's short-term memory: [linear_QMem(tgt3), tgt3] (:675-678)
+    RMEM_TRY(lin_t16(a_o3, kD, kD, pre + ".linear_QMem", kD, L.sk[cur], kD, s));
+    if (ref_mode) {
+      RMEM_TRY(add_t16(a_o3, kD, idemb, kD, a_sum, kD, G.HW, kD, s));
+      RMEM_TRY(lin_t16(a_sum, kD, kD, pre + ".linear_VMem", kD, L.sv[cur], kD, s));
+    } else {
+      RMEM_TRY(copy2d_t16(a_o3, kD, L.sv[cur], kD, G.HW, kD, s));
+    }
+
+    // ---- feed-forward: LN3 -> linear1 -> GroupNorm(32) -> GELU -> DWConv5x5 -> linear2 (:683-687) ----
+    RMEM_TRY(layernorm(a_tgt, kD, g3, b3, a_tln, kD, nullptr, 0, G.HW, kD, s));
+    RMEM_TRY(lin_t16(a_tln, kD, kD, pre + ".linear1", 4 * kD, a_ff1, 4 * kD, s));
+    {
+      const float* gg = Wt<float>(pre + ".act.gn.g", 4 * kD, &rc);
+      const float* gb = Wt<float>(pre + ".act.gn.b", 4 * kD, &rc);
+      const float* dw = Wt<float>(pre + ".act.dw", (size_t)25 * 4 * kD, &rc);
+      if (rc) return rc;
+      RMEM_TRY(groupnorm_t16(a_ff1, gg, gb, a_ff2, G.HW, 4 * kD, 32, /*act=gelu*/ 2, stats, s));
+      RMEM_TRY(dwconv5x5(a_ff2, dw, a_ff1, G.h, G.w, 4 * kD, s));
+    }
+    RMEM_TRY(lin_acc(a_ff1, 4 * kD, 4 * kD, pre + ".linear2", kD, a_tgt, kD, s));
+
+    // decoder_norms[l] (:248-259) -> decoder input columns 256(l+1)..
+    const float* dg = Wt<float>("lstt.dec_norm." + std::to_string(l) + ".g", kD, &rc);
+    const float* db = Wt<float>("lstt.dec_norm." + std::to_string(l) + ".b", kD, &rc);
+    if (rc) return rc;
+    return layernorm(a_tgt, kD, dg, db, a_decin + (size_t)(l + 1) * kD, 4 * kD, nullptr, 0, G.HW, kD, s);
+  }
+
+  // LongShortTermTransformer.forward + AOT.decode_id_logits (aot.py:136-142): decoder input = cat(proj16x, l0, l1, l2)
+  int lstt_decode_aot(Group& gr, bool ref_mode, cudaStream_t s) {
+    const Geo& G = g;
+    if (!pos_ready) {
+      RMEM_TRY(sine_pos_emb(a_pos, G.h, G.w, kD, s));              // aot_engine.py:289-292, once per engine size
+      pos_ready = true;
+    }
+    RMEM_CUDA_CHECK(cudaMemcpyAsync(a_tgt, enc_tgt, sizeof(float) * G.HW * kD, cudaMemcpyDeviceToDevice, s));
+    RMEM_TRY(cvt_f32_t16(enc_tgt, kD, a_decin, 4 * kD, G.HW, kD, s));
+    for (int l = 0; l < kLayers; ++l) RMEM_TRY(aot_layer(gr, l, ref_mode, s));
+    return fpn_decode(gr, a_decin, 4 * kD, s);
+  }
+
+  // LongShortTermTransformer.update_short_memories (transformer.py:269-304)
+  int aot_refresh(Group& gr, cudaStream_t s) {
+    const Geo& G = g;
+    for (int l = 0; l < kLayers; ++l) {
+      const std::string pre = "lstt." + std::to_string(l);
+      LayerStateA& L = gr.A[l];
+      RMEM_TRY(add_t16(L.v_cur, kD, idemb, kD, a_sum, kD, G.HW, kD, s));
+      RMEM_TRY(lin_t16(a_sum, kD, kD, pre + ".linear_V", kD, L.v_lin, kD, s));
+      RMEM_TRY(add_t16(L.sv[gr.parity], kD, idemb, kD, a_sum, kD, G.HW, kD, s));
+      RMEM_TRY(lin_t16(a_sum, kD, kD, pre + ".linear_VMem", kD, L.sv[gr.parity], kD, s));
+    }
+    return RMEM_OK;
+  }
+
+  int append_long_aot(Group& gr, cudaStream_t s) {
+    const Geo& G = g;
+    if (gr.free_slots.empty()) { set_error("bank overflow"); return RMEM_ERR_STATE; }
+    int slot = gr.free_slots.back();
+    gr.free_slots.pop_back();
+    for (int l = 0; l < kLayers; ++l) {
+      LayerStateA& L = gr.A[l];
+      RMEM_TRY(copy2d_t16(L.k_cur, kD, L.kbank + (size_t)slot * G.HWp * kD, kD, G.HW, kD, s));
+      RMEM_TRY(transpose_t16(L.v_lin, kD, L.vtbank + (size_t)slot * G.HWp, (long long)nslots * G.HWp, G.HW, kD, s));
+    }
+    gr.slots.push_back(slot);
+    return RMEM_OK;
+  }
+
+  int frame_forward(Group& gr, bool ref_mode, cudaStream_t s) {
+    return cfg.model == 1 ? lstt_decode_aot(gr, ref_mode, s) : lstt_decode(gr, ref_mode, s);
   }
 };
 
@@ -586,7 +819,7 @@ extern "C" {
 
 int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
   RMEM_REQUIRE(cfg && bytes, "null argument");
-  RMEM_REQUIRE(cfg->model == 0, "only model 0 (r50_deaotl) is built");
+  RMEM_REQUIRE(cfg->model == 0 || cfg->model == 1, "model %d: 0 = r50_deaotl, 1 = r50_aotl", cfg->model);
   RMEM_REQUIRE(cfg->H > 16 && cfg->W > 16 && (cfg->H - 1) % 16 == 0 && (cfg->W - 1) % 16 == 0,
                "input size %dx%d is not 16k+1 (snap with MultiRestrictSize first)", cfg->H, cfg->W);
   RMEM_REQUIRE(cfg->max_engines >= 1 && cfg->max_engines <= 4, "max_engines=%d out of 1..4", cfg->max_engines);
@@ -678,7 +911,7 @@ int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void
     for (int sl = e->nslots - 1; sl >= 1; --sl) gr.free_slots.push_back(sl);
     gr.slots.push_back(0);
     gr.ema.clear(); gr.times.clear();
-    RMEM_TRY(e->lstt_decode(gr, /*ref_mode=*/true, s));
+    RMEM_TRY(e->frame_forward(gr, /*ref_mode=*/true, s));
     gr.parity ^= 1;                      // this frame becomes the short-term memory
     gr.last_mem_step = frame_step;
     gr.long_idx.push_back(gr.frame_step);
@@ -697,7 +930,7 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
   for (int gi = 0; gi < e->n_groups; ++gi) {
     Group& gr = e->groups[gi];
     gr.frame_step += 1;
-    RMEM_TRY(e->lstt_decode(gr, /*ref_mode=*/false, s));
+    RMEM_TRY(e->frame_forward(gr, /*ref_mode=*/false, s));
     lg[gi] = gr.logits4;
   }
   if (out_logits || out_label)
@@ -716,10 +949,18 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
     RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/1, s));
     bool is_long = (gr.frame_step - gr.last_mem_step) >= e->cfg.long_term_mem_gap;
     if (is_long) gr.last_mem_step = gr.frame_step;
-    for (int l = 0; l < kLayers; ++l) RMEM_TRY(e->fuse_id(gr, l, s));      // transformer.py:826-857
+    if (e->cfg.model == 1) {
+      RMEM_TRY(e->aot_refresh(gr, s));                                     // transformer.py:269-304
+    } else {
+      for (int l = 0; l < kLayers; ++l) RMEM_TRY(e->fuse_id(gr, l, s));    // transformer.py:826-857
+    }
     if (is_long) {
-      RMEM_TRY(e->append_long(gr, s));
+      RMEM_TRY(e->cfg.model == 1 ? e->append_long_aot(gr, s) : e->append_long(gr, s));
       gr.long_idx.push_back(gr.frame_step);
+      if (e->cfg.model == 1 && (int)gr.slots.size() <= cap) {              // AOT only: early return before any
+        gr.parity ^= 1;                                                    // statistics update (transformer.py:332-334)
+        continue;
+      }
       // aot_engine.py:350-369 -> transformer.py:880-991
       const int T_old = gr.mass_T;
       RMEM_REQUIRE(T_old + 1 == (int)gr.slots.size(), "attention mass is stale (T_old=%d, bank=%zu)", T_old,

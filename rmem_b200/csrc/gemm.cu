@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const t16* const Ab = p.A + (long long)blockIdx.z * p.sA;     // batched mode: one problem per blockIdx.z
+  const t16* const Bb = p.B + (long long)blockIdx.z * p.sB;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int vec = tid & 3;             // which 8-element k vector of the 32-wide stage
   const int row0 = tid >> 2;           // first tile row handled by this thread
@@ -63,10 +65,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
       int oy = m / p.Wout, ox = m - oy * p.Wout;
       a_iy0[j] = oy * p.stride - p.pad;
       a_ix0[j] = ox * p.stride - p.pad;
-      a_base[j] = p.A;
+      a_base[j] = Ab;
     } else {
       a_iy0[j] = a_ix0[j] = 0;
-      a_base[j] = p.A + (long long)(a_ok[j] ? m : 0) * p.lda;
+      a_base[j] = Ab + (long long)(a_ok[j] ? m : 0) * p.lda;
     }
   }
   const t16* b_base[B_ITERS];
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
   for (int j = 0; j < B_ITERS; ++j) {
     int n = n0 + row0 + j * (NT / 4);
     b_ok[j] = n < p.N;
-    b_base[j] = p.B + (long long)(b_ok[j] ? n : 0) * p.ldb;
+    b_base[j] = Bb + (long long)(b_ok[j] ? n : 0) * p.ldb;
   }
 
   auto load_tile = [&](int kt, int stage) {
@@ -91,12 +93,12 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
 #pragma unroll
     for (int j = 0; j < A_ITERS; ++j) {
       t16* dst = sA + ((stage * BM) + row0 + j * (NT / 4)) * BKP + vec * 8;
-      const t16* src = p.A;
+      const t16* src = Ab;
       bool ok = a_ok[j] && k_ok;
       if (p.conv) {
         int iy = a_iy0[j] + ky, ix = a_ix0[j] + kx;
         ok = ok && (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;
-        if (ok) src = p.A + ((long long)iy * p.Win + ix) * p.Cin + ci;
+        if (ok) src = Ab + ((long long)iy * p.Win + ix) * p.Cin + ci;
       } else if (ok) {
         src = a_base[j] + k;
       }
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
     for (int j = 0; j < B_ITERS; ++j) {
       t16* dst = sB + ((stage * BN) + row0 + j * (NT / 4)) * BKP + vec * 8;
       bool ok = b_ok[j] && k_ok;
-      cp_async16(dst, ok ? (b_base[j] + k) : p.B, ok ? 16 : 0);
+      cp_async16(dst, ok ? (b_base[j] + k) : Bb, ok ? 16 : 0);
     }
   };
 
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
           base = p.C2; ld = p.ldc2; nn = n - p.n_split; f32 = p.c2_fp32;
         }
         if (f32) {
-          float* o = reinterpret_cast<float*>(base) + (long long)m * ld + nn;
+          float* o = reinterpret_cast<float*>(base) + (long long)blockIdx.z * p.sC + (long long)m * ld + nn;
           if (p.accumulate) {
             v0 += o[0];
             if (two) v1 += o[1];
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmP
           o[0] = v0;
           if (two) o[1] = v1;
         } else {
-          t16* o = reinterpret_cast<t16*>(base) + (long long)m * ld + nn;
+          t16* o = reinterpret_cast<t16*>(base) + (long long)blockIdx.z * p.sC + (long long)m * ld + nn;
           if (two && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
             *reinterpret_cast<uint32_t*>(o) = pack2(v0, v1);
           } else {
@@ -232,7 +234,7 @@ int launch_cfg(const GemmParams& p, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM));
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.batch > 1 ? p.batch : 1);
   gemm_kernel<BM, BN, WARPS_M, WARPS_N><<<grid, WARPS_M * WARPS_N * 32, smem, stream>>>(p);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
@@ -250,7 +252,7 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   RMEM_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty shape M=%d N=%d K=%d", p.M, p.N, p.K);
   RMEM_REQUIRE(!(p.accumulate && !p.c_fp32), "gemm: accumulate needs an fp32 destination");
   if (p.n_split < p.N) RMEM_REQUIRE(p.C2 != nullptr, "gemm: n_split without C2");
-  if (gemm_impl_switch() == 0 && gemm_tc_supported(p)) return gemm_tc_launch(p, stream);
+  if (gemm_impl_switch() == 0 && p.batch <= 1 && gemm_tc_supported(p)) return gemm_tc_launch(p, stream);
   return gemm_legacy_launch(p, stream);
 }
 
@@ -271,8 +273,9 @@ int gemm_legacy_launch(const GemmParams& p, cudaStream_t stream) {
   if (p.n_split < p.N) RMEM_REQUIRE(p.C2 != nullptr, "gemm: n_split without C2");
 
   // Tile choice: fill the 148 SMs.  Large problems take 128x128, mid 128x64, small 64x64.
-  const long long t128 = (long long)cdiv(p.M, 128) * cdiv(p.N, 128);
-  const long long t12864 = (long long)cdiv(p.M, 128) * cdiv(p.N, 64);
+  const int nb = p.batch > 1 ? p.batch : 1;
+  const long long t128 = (long long)cdiv(p.M, 128) * cdiv(p.N, 128) * nb;
+  const long long t12864 = (long long)cdiv(p.M, 128) * cdiv(p.N, 64) * nb;
   if (t128 >= 2 * 148 && p.N >= 128) return launch_cfg<128, 128, 2, 4>(p, stream);
   if (t12864 >= 2 * 148) return launch_cfg<128, 64, 4, 2>(p, stream);
   return launch_cfg<64, 64, 2, 2>(p, stream);

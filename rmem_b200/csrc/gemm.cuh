@@ -38,6 +38,9 @@ struct GemmParams {
   // N % 32 != 0 only: columns N .. round_up(N,32)-1 of C may be written with padding values (no residual / gate /
   // per-column bias in that case).  Lets the tcgen05 kernel store whole 32-column chunks.
   int pad_n_ok = 0;
+  // batched mode (legacy kernel only): blockIdx.z selects a problem; element strides between problems
+  int batch = 1;
+  long long sA = 0, sB = 0, sC = 0;
 };
 
 // Launches the best kernel for the shape: the tcgen05/TMA kernel (gemm_tc.cu) whenever its alignment rules hold,

@@ -57,7 +57,7 @@ __global__ void maxpool_kernel(const t16* __restrict__ x, t16* __restrict__ y, i
 constexpr int LN_MAXV = 16;  // C <= 512
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, t16* __restrict__ y, long long ldy,
-                                 t16* __restrict__ y2, long long ldy2, int P, int C) {
+                                 t16* __restrict__ y2, long long ldy2, const float* __restrict__ add2, int P, int C) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -78,9 +78,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
   for (int j = 0; j < LN_MAXV; ++j)
     if (j < nv) {
       int c = j * 32 + lane;
-      t16 o = f2t((v[j] - mean) * rstd * gamma[c] + beta[c]);
+      const float of = (v[j] - mean) * rstd * gamma[c] + beta[c];
+      t16 o = f2t(of);
       y[(long long)row * ldy + c] = o;
-      if (y2) y2[(long long)row * ldy2 + c] = o;
+      if (y2) y2[(long long)row * ldy2 + c] = add2 ? f2t(of + add2[(long long)row * C + c]) : o;
     }
 }
 
@@ -162,7 +163,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict
   for (int k = 0; k < 8; ++k) {
     int c = col * 8 + k;
     float o = (v[k] - fm) * rstd * gamma[c] + beta[c];
-    v[k] = relu ? fmaxf(o, 0.f) : o;
+    v[k] = relu == 1 ? fmaxf(o, 0.f) : (relu == 2 ? 0.5f * o * (1.f + erff(o * 0.70710678118654752f)) : o);
   }
   store8(y + (size_t)r * C + col * 8, v);
 }
@@ -491,7 +492,118 @@ __global__ void evict_rel_kernel(const float* __restrict__ mass, int T, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// ---- small elementwise kernels of the AOT block (transformer.py:553-692) ----
+__global__ void add_t16_kernel(const t16* __restrict__ a, long long lda, const t16* __restrict__ b, long long ldb,
+                               t16* __restrict__ y, long long ldy, int P, int C) {
+  const int cv = C / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * cv) return;
+  int c8 = (int)(i % cv);
+  long long r = i / cv;
+  float u[8], v[8];
+  load8(a + r * lda + c8 * 8, u);
+  load8(b + r * ldb + c8 * 8, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) u[k] += v[k];
+  store8(y + r * ldy + c8 * 8, u);
+}
+
+// y = LayerNorm(a + b): one warp per row, C <= 512
+__global__ void add_layernorm_kernel(const t16* __restrict__ a, long long lda, const t16* __restrict__ b,
+                                     long long ldb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     t16* __restrict__ y, long long ldy, int P, int C) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= P) return;
+  float v[LN_MAXV];
+  const int nv = C / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) {
+      v[j] = t2f(a[(long long)row * lda + j * 32 + lane]) + t2f(b[(long long)row * ldb + j * 32 + lane]);
+      s += v[j];
+    }
+  float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) { float d = v[j] - mean; q += d * d; }
+  float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) {
+      int c = j * 32 + lane;
+      y[(long long)row * ldy + c] = f2t((v[j] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+__global__ void accum_t16_kernel(const t16* __restrict__ x, long long ldx, float* __restrict__ y, long long ldy, int P,
+                                 int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * C) return;
+  long long r = i / C;
+  int c = (int)(i - r * C);
+  y[r * ldy + c] += t2f(x[r * ldx + c]);
+}
+
+__global__ void cvt_f32_t16_kernel(const float* __restrict__ x, long long ldx, t16* __restrict__ y, long long ldy,
+                                   int P, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * C) return;
+  long long r = i / C;
+  int c = (int)(i - r * C);
+  y[r * ldy + c] = f2t(x[r * ldx + c]);
+}
+
+// PositionEmbeddingSine(num_pos_feats = C/2, normalize = True)  (position.py:35-77) -> fp32 [h*w, C]
+__global__ void sine_pe_kernel(float* __restrict__ out, int h, int w, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)h * w * C) return;
+  const int c = (int)(i % C);
+  const int tok = (int)(i / C);
+  const int py = tok / w, px = tok - py * w;
+  const int npf = C / 2;
+  const bool is_x = c >= npf;
+  const int k = is_x ? c - npf : c;
+  const float pos = is_x ? (float)px / ((float)(w - 1) + 1e-6f) : (float)py / ((float)(h - 1) + 1e-6f);
+  const float e = pos * 6.283185307179586f;
+  const float dim_t = powf(10000.f, (float)(2 * (k / 2)) / (float)npf);
+  const float a = e / dim_t;
+  out[i] = (k & 1) ? cosf(a) : sinf(a);
+}
+
+// mean over heads of the per-head attention mass: in [H][P][T] -> out [P][T]
+__global__ void mean_heads_kernel(const float* __restrict__ in, float* __restrict__ out, int H, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) s += in[(long long)h * n + i];
+  out[i] = s / (float)H;
+}
+
 struct PeSlots { int s[16]; };
+// AOT: qt = t16(q + pe_cur); qbias[h][i][t] = scale * <qt_i[h*dh .. (h+1)*dh), pe_mem[slot(t)][h*dh ..]>
+// one warp per row, C = 256, H = 8 heads of 32: lane j of chunk h covers channel h*32 + lane
+__global__ void qprep_heads_kernel(const t16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
+                                   const float* __restrict__ pe_mem, PeSlots ps, int T, float scale,
+                                   t16* __restrict__ qt, float* __restrict__ qbias, int P, int H) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= P) return;
+  const int C = H * 32;
+  for (int h = 0; h < H; ++h) {
+    const int c = h * 32 + lane;
+    t16 r = f2t(t2f(q[(long long)row * ldq + c]) + pe_cur[c]);
+    qt[(long long)row * C + c] = r;
+    const float v = t2f(r);
+    for (int t = 0; t < T; ++t) {
+      float s = warp_sum(v * pe_mem[ps.s[t] * C + c]);
+      if (lane == 0) qbias[((long long)h * P + row) * T + t] = s * scale;
+    }
+  }
+}
+
 __global__ void qprep_kernel(const t16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
                              const float* __restrict__ pe_mem, PeSlots ps, int T, float scale, t16* __restrict__ qt,
                              float* __restrict__ qbias, int P, int C) {
@@ -537,9 +649,9 @@ int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wo
 }
 
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy, t16* y2,
-              long long ldy2, int P, int C, cudaStream_t s) {
+              long long ldy2, int P, int C, cudaStream_t s, const float* add2) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm: unsupported C=%d", C);
-  layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(x, ldx, gamma, beta, y, ldy, y2, ldy2, P, C);
+  layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(x, ldx, gamma, beta, y, ldy, y2, ldy2, add2, P, C);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -629,6 +741,61 @@ int evict_relevance(const float* mass, int T, const float* logits4, int h4, int 
                     cudaStream_t s) {
   RMEM_REQUIRE(T >= 1 && T <= 16, "evict_relevance: T=%d out of range", T);
   evict_rel_kernel<<<1, 1024, 0, s>>>(mass, T, logits4, h4, w4, h, w, rel);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int add_t16(const t16* a, long long lda, const t16* b, long long ldb, t16* y, long long ldy, int P, int C,
+            cudaStream_t s) {
+  RMEM_REQUIRE(C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0, "add_t16: alignment");
+  long long n = (long long)P * (C / 8);
+  add_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, lda, b, ldb, y, ldy, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int add_layernorm_t16(const t16* a, long long lda, const t16* b, long long ldb, const float* gamma, const float* beta,
+                      t16* y, long long ldy, int P, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "add_layernorm: unsupported C=%d", C);
+  add_layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(a, lda, b, ldb, gamma, beta, y, ldy, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int accum_t16_into_f32(const t16* x, long long ldx, float* y, long long ldy, int P, int C, cudaStream_t s) {
+  long long n = (long long)P * C;
+  accum_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, y, ldy, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int cvt_f32_t16(const float* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s) {
+  long long n = (long long)P * C;
+  cvt_f32_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, y, ldy, P, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int sine_pos_emb(float* out, int h, int w, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 4 == 0 && h > 1 && w > 1, "sine_pos_emb: unsupported geometry");
+  long long n = (long long)h * w * C;
+  sine_pe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, h, w, C);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int mean_heads(const float* in, float* out, int H, long long n, cudaStream_t s) {
+  mean_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, H, n);
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int qprep_heads(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+                float scale, t16* qt, float* qbias, int P, int H, cudaStream_t s) {
+  RMEM_REQUIRE(T >= 1 && T <= 16 && H >= 1 && H <= 16, "qprep_heads: T=%d H=%d", T, H);
+  PeSlots ps;
+  for (int t = 0; t < 16; ++t) ps.s[t] = (t < T && pe_slot) ? pe_slot[t] : 0;
+  qprep_heads_kernel<<<cdiv(P, 8), 256, 0, s>>>(q, ldq, pe_cur, pe_mem, ps, T, scale, qt, qbias, P, H);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -12,8 +12,9 @@ int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s);
 int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s);
 
 // LayerNorm over C (eps 1e-5): x fp32 [P, ldx] -> y t16 [P, ldy] (+ optional second copy y2).
+// `add2` (fp32 [P, C], optional): y2 = t16(LN(x) + add2) instead of a plain copy (AOT sine PE on q, k).
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy,
-              t16* y2, long long ldy2, int P, int C, cudaStream_t s);
+              t16* y2, long long ldy2, int P, int C, cudaStream_t s, const float* add2 = nullptr);
 
 // GroupNorm over (pixels x C/G) per group, eps 1e-5, optional ReLU.  `stats` = kGnScratchDoubles doubles of
 // scratch whose element [64] (the block counter) must be zero before the first call; it re-arms itself.
@@ -22,6 +23,19 @@ int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, i
                    double* stats, cudaStream_t s);
 int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s);
+
+// AOT block helpers (transformer.py:553-692, basic.py:15-35, position.py:35-77).  groupnorm_*'s `relu` argument is an
+// activation code: 0 none, 1 ReLU, 2 exact GELU.
+int add_t16(const t16* a, long long lda, const t16* b, long long ldb, t16* y, long long ldy, int P, int C,
+            cudaStream_t s);
+int add_layernorm_t16(const t16* a, long long lda, const t16* b, long long ldb, const float* gamma, const float* beta,
+                      t16* y, long long ldy, int P, int C, cudaStream_t s);
+int accum_t16_into_f32(const t16* x, long long ldx, float* y, long long ldy, int P, int C, cudaStream_t s);
+int cvt_f32_t16(const float* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s);
+int sine_pos_emb(float* out, int h, int w, int C, cudaStream_t s);
+int mean_heads(const float* in, float* out, int H, long long n, cudaStream_t s);
+int qprep_heads(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+                float scale, t16* qt, float* qbias, int P, int H, cudaStream_t s);
 
 // Depthwise 5x5 (pad 2) on a token-major map: x t16 [h*w, C], w fp32 [25, C] -> y t16.   (basic.py:38-59)
 int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s);

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import _capi
-from .weights import WeightBlob, pack_deaot
+from .weights import WeightBlob, pack_model
 
 MAX_OBJ = 10   # configs/models/default.py MODEL_MAX_OBJ_NUM
 
@@ -36,27 +36,45 @@ class RmemConfig:
     max_engines: int = 4
 
 
-class DeAOTModel:
-    """Weights of R50_DeAOTL resident in HBM (stands in for `build_vos_model(...)` + `load_state_dict`)."""
+MODEL_IDS = {"r50_deaotl": 0, "r50_aotl": 1}
+
+
+class RmemModel:
+    """Weights of R50_DeAOTL / R50_AOTL resident in HBM (stands in for `build_vos_model(...)` + `load_state_dict`,
+    networks/models/__init__.py:5, networks/models/{aot,deaot}.py)."""
 
     def __init__(self, state_dict, cfg: Optional[RmemConfig] = None, device: Union[str, torch.device] = "cuda:0"):
         self.cfg = cfg or RmemConfig()
-        if self.cfg.model != "r50_deaotl":
-            raise NotImplementedError(f"model {self.cfg.model!r}: only r50_deaotl is built so far")
+        if self.cfg.model not in MODEL_IDS:
+            raise NotImplementedError(f"model {self.cfg.model!r}: r50_deaotl and r50_aotl are built")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _capi.RmemError("rmem_b200 runs on CUDA devices only (no CPU path)")
         _capi.load()
-        self.weights = WeightBlob(pack_deaot(state_dict), self.device)
+        self.weights = WeightBlob(pack_model(state_dict, self.cfg.model), self.device)
 
     def eval(self):
         return self
 
 
-def build_vos_model(name: str, cfg: RmemConfig, state_dict=None, device="cuda:0") -> DeAOTModel:
-    if name not in ("deaot", "r50_deaotl"):
+DeAOTModel = RmemModel
+
+
+def AOTModel(state_dict, cfg: Optional[RmemConfig] = None, device="cuda:0") -> RmemModel:
+    cfg = cfg or RmemConfig(model="r50_aotl")
+    cfg.model = "r50_aotl"
+    return RmemModel(state_dict, cfg, device)
+
+
+def build_vos_model(name: str, cfg: RmemConfig, state_dict=None, device="cuda:0") -> RmemModel:
+    """networks/models/__init__.py:5-13: 'aot' | 'deaot'."""
+    if name in ("deaot", "r50_deaotl"):
+        cfg.model = "r50_deaotl"
+    elif name in ("aot", "r50_aotl"):
+        cfg.model = "r50_aotl"
+    else:
         raise NotImplementedError(name)
-    return DeAOTModel(state_dict, cfg, device)
+    return RmemModel(state_dict, cfg, device)
 
 
 class _SubEngineView:
@@ -124,7 +142,7 @@ class DeAOTInferEngine:
             return
         self._destroy()
         lib = _capi.load()
-        cc = _capi.EngineConfig(0, H, W, self.cfg.former_mem_len, self.cfg.latter_mem_len, self.cfg.max_engines,
+        cc = _capi.EngineConfig(MODEL_IDS[self.cfg.model], H, W, self.cfg.former_mem_len, self.cfg.latter_mem_len, self.cfg.max_engines,
                                 self.cfg.attn_impl, max(int(self.long_term_mem_gap), 1))
         nbytes = C.c_size_t()
         _capi.check(lib.rmem_engine_arena_bytes(C.byref(cc), C.byref(nbytes)))
@@ -218,11 +236,19 @@ class DeAOTInferEngine:
         return int(_capi.load().rmem_engine_launch_count(self._h)) if self._h else 0
 
 
+class AOTInferEngine(DeAOTInferEngine):
+    """aot_engine.py:571-725 over R50_AOTL (same per-clip state machine; the reference's DeAOTInferEngine derives from it)."""
+
+
 def build_engine(name: str, phase: str = "eval", aot_model: DeAOTModel = None, gpu_id: int = 0,
                  long_term_mem_gap: int = 9999, **kwargs):
     """networks/engines/__init__.py:5-21."""
     if phase != "eval":
         raise NotImplementedError("rmem_b200 builds the inference path only (training is out of scope)")
     if name in ("deaotengine", "deaot_engine"):
+        assert aot_model.cfg.model == "r50_deaotl", "deaotengine needs a DeAOT model"
         return DeAOTInferEngine(aot_model, gpu_id=gpu_id, long_term_mem_gap=long_term_mem_gap, **kwargs)
+    if name in ("aotengine", "aot_engine"):
+        assert aot_model.cfg.model == "r50_aotl", "aotengine needs an AOT model"
+        return AOTInferEngine(aot_model, gpu_id=gpu_id, long_term_mem_gap=long_term_mem_gap, **kwargs)
     raise NotImplementedError(f"engine {name!r}")

@@ -28,8 +28,9 @@ def _resnet_blocks():
     return out
 
 
-def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """name -> packed CPU tensor (t16 or fp32, contiguous)."""
+def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[str, torch.Tensor]:
+    """name -> packed CPU tensor (t16 or fp32, contiguous).  model: "r50_deaotl" | "r50_aotl"."""
+    deaot = model == "r50_deaotl"
     sd = {(k[7:] if k.startswith("module.") else k): v.detach().float().cpu() for k, v in sd.items()}
     out: Dict[str, torch.Tensor] = {}
 
@@ -77,11 +78,29 @@ def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     wb = sd["patch_wise_id_bank.weight"]                                    # [C,12,17,17]
     out["idbank.w"] = wb.permute(2, 3, 1, 0).reshape(17 * 17, wb.shape[1], wb.shape[0]).contiguous()
     out["idbank.b"] = sd["patch_wise_id_bank.bias"].contiguous()
-    norm("id_norm", "id_norm")
+    if deaot:
+        norm("id_norm", "id_norm")
     out["cur_pos_emb"] = sd["cur_pos_emb"].reshape(-1).contiguous()
     out["mem_pos_emb"] = sd["mem_pos_emb"].contiguous()
 
-    for l in range(3):
+    # ---- AOT LSTT (transformer.py:466-697; linear_KMem is never used by the reference) ----
+    for l in range(0 if deaot else 3):
+        p, q = f"LSTT.layers.{l}", f"lstt.{l}"
+        for nm in ("norm1", "norm2", "norm3", "norm4"):
+            norm(f"{q}.{nm}", f"{p}.{nm}")
+        for nm in ("linear_Q", "linear_K", "linear_V"):
+            linear(f"{q}.self.{nm}", f"{p}.self_attn.{nm}")
+        linear(f"{q}.self.proj", f"{p}.self_attn.projection")
+        for nm in ("linear_Q", "linear_V", "linear_QMem", "linear_VMem", "linear1", "linear2"):
+            linear(f"{q}.{nm}", f"{p}.{nm}")
+        linear(f"{q}.long.proj", f"{p}.long_term_attn.projection")
+        linear(f"{q}.short.proj", f"{p}.short_term_attn.projection")
+        norm(f"{q}.act.gn", f"{p}.activation.gn")
+        w = sd[f"{p}.activation.conv.weight"]                               # [C,1,5,5]
+        out[f"{q}.act.dw"] = w.view(w.shape[0], 25).t().contiguous()
+        norm(f"lstt.dec_norm.{l}", f"LSTT.decoder_norms.{l}")
+
+    for l in range(3 if deaot else 0):
         p, q = f"LSTT.layers.{l}", f"gpm.{l}"
         norm(q + ".norm1", p + ".norm1")
         linear(q + ".linear_QV", p + ".linear_QV")
@@ -99,7 +118,8 @@ def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         linear(q + ".self.linear_QK", p + ".self_attn.linear_QK")
         for nm in ("linear_V1", "linear_V2", "linear_U1", "linear_U2"):
             linear(f"{q}.self.{nm}", f"{p}.self_attn.{nm}")
-    norm("gpm.out_norm", "LSTT.decoder_norms.0.gn")
+    if deaot:
+        norm("gpm.out_norm", "LSTT.decoder_norms.0.gn")
 
     for nm in ("conv_in", "conv_16x", "conv_8x", "conv_4x"):
         conv("dec." + nm, f"decoder.{nm}.conv")
@@ -108,6 +128,14 @@ def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     for nm in ("adapter_16x", "adapter_8x", "adapter_4x", "conv_out"):
         conv("dec." + nm, "decoder." + nm)
     return out
+
+
+def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    return pack_model(sd, "r50_deaotl")
+
+
+def pack_aot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    return pack_model(sd, "r50_aotl")
 
 
 class WeightBlob:

@@ -33,14 +33,16 @@ def load_case(name):
 
 
 def run_engine_lockstep(meta, z, device, attn_impl=0):
-    from rmem_b200.engine import DeAOTModel, RmemConfig, build_engine
+    from rmem_b200.engine import RmemModel, RmemConfig, build_engine
     sd = O.make_state_dict(meta["model"], seed=meta["seed"], sharpen=meta["sharpen"])
     H, W, n_obj = meta["H"], meta["W"], meta["n_obj"]
     frames = O.synthetic_frames(meta["n_frames"], H, W, seed=meta["seed"] + 1)
     label0 = O.synthetic_label(H, W, n_obj)
-    cfg = RmemConfig(former_mem_len=meta["former"], latter_mem_len=meta["latter"], attn_impl=attn_impl)
-    model = DeAOTModel(sd, cfg, device)
-    eng = build_engine("deaotengine", phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=meta["gap"])
+    cfg = RmemConfig(model=meta["model"], former_mem_len=meta["former"], latter_mem_len=meta["latter"],
+                     attn_impl=attn_impl)
+    model = RmemModel(sd, cfg, device)
+    eng = build_engine("deaotengine" if meta["model"] == "r50_deaotl" else "aotengine", phase="eval", aot_model=model,
+                       gpu_id=0, long_term_mem_gap=meta["gap"])
     out_size = tuple(meta["out_size"])
     forced = torch.from_numpy(z["labels"])                      # [F-1,Ho,Wo] uint8
     eng.restart_engine()
@@ -85,6 +87,12 @@ def test_engine_matches_reference_goldens(cuda_device, name, impl):
     agree = float((ours == torch.from_numpy(z["labels"])).float().mean())
     print(f"[{name}] label agreement = {agree:.5f}")
     assert agree >= LABEL_AGREE
+
+
+@pytest.mark.parametrize("name", ["aot_c1_256_t1", "aot_small_rmem"])
+def test_aot_engine_matches_reference_goldens(cuda_device, name):
+    """R50_AOTL (+RMem): BASELINE.json configs[0] (c1) and a restricted-bank clip with eviction."""
+    test_engine_matches_reference_goldens(cuda_device, name, 0)
 
 
 def test_engine_restart_is_deterministic(cuda_device):

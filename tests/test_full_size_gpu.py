@@ -1,0 +1,61 @@
+"""BASELINE.json configs c2 / c3 / c4 at FULL size on the GPU, lock-step against the CPU oracle for a few frames plus
+size-independent invariants of the restricted memory bank:
+  * 1/4-res logits within 5e-2 * max|logit| of the fp32 oracle, labels >= 99 % equal (teacher forcing on the oracle's labels)
+  * long_memories_indexes identical after every update; frame 0 and the newest frame are never evicted; len <= cap
+  * labels are valid object ids
+c2: R50_AOTL+RMem 480p 1 object T=4; c3: R50_DeAOTL+RMem 480p 10 objects T=8; c4: R50_DeAOTL+RMem 720p 30 objects (3 engines).
+Bank depth is reached with long_term_mem_gap=1 so the clip stays short (the oracle runs ~1-10 s per frame on CPU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rmem_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: (model, H, W, n_obj, former, latter, n_frames, sharpen)
+    "c2_aotl_480p_1obj_T4": ("r50_aotl", 481, 849, 1, 1, 3, 7, 2.0),
+    "c3_deaotl_480p_10obj_T8": ("r50_deaotl", 481, 849, 10, 1, 7, 11, 4.0),
+    "c4_deaotl_720p_30obj_3engines": ("r50_deaotl", 721, 1281, 30, 1, 2, 5, 4.0),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_full_size_lockstep(cuda_device, name):
+    from rmem_b200.engine import RmemConfig, RmemModel, build_engine
+    model, H, W, n_obj, former, latter, n_frames, sharpen = CASES[name]
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    sd = O.make_state_dict(model, seed=7, sharpen=sharpen)
+    frames = O.synthetic_frames(n_frames, H, W, seed=8)
+    label0 = O.synthetic_label(H, W, n_obj)
+    cap = former + latter
+    cfg = RmemConfig(model=model, former_mem_len=former, latter_mem_len=latter, max_engines=(n_obj + 9) // 10)
+    eng = build_engine("deaotengine" if model == "r50_deaotl" else "aotengine", aot_model=RmemModel(sd, cfg, cuda_device),
+                       long_term_mem_gap=1)
+    orc = O.OracleEngine(sd, O.OracleConfig(model=model, former_mem_len=former, latter_mem_len=latter),
+                         long_term_mem_gap=1)
+    worst, agree_min = 0.0, 1.0
+    with torch.no_grad():
+        eng.restart_engine(); orc.restart_engine()
+        eng.add_reference_frame(frames[0:1].to(cuda_device), label0.int().to(cuda_device), obj_nums=[n_obj], frame_step=0)
+        orc.add_reference_frame(frames[0:1], label0, obj_nums=[n_obj], frame_step=0)
+        for f in range(1, n_frames):
+            lg, lab = eng.match_propogate_one_frame(frames[f:f + 1].to(cuda_device), output_size=(H, W),
+                                                    return_label=True)
+            ref = orc.match_propogate_one_frame(frames[f:f + 1], output_size=(H, W))
+            for k, (a, b) in enumerate(zip(eng.aot_engines, orc.aot_engines)):
+                e = float((a.pred_id_logits.cpu() - b.pred_id_logits).abs().max() / b.pred_id_logits.abs().max())
+                worst = max(worst, e)
+            ref_lab = O.logits_to_label(ref)
+            agree_min = min(agree_min, float((lab.cpu().float() == ref_lab).float().mean()))
+            assert int(lab.max()) <= n_obj + (10 - n_obj % 10) % 10        # eval never masks unused id channels
+            eng.update_memory(ref_lab.to(cuda_device)); orc.update_memory(ref_lab)
+            for a, b in zip(eng.aot_engines, orc.aot_engines):
+                idx = a.long_memories_indexes
+                assert idx == b.long_memories_indexes, (f, idx, b.long_memories_indexes)
+                assert idx[0] == 0 and len(idx) <= cap and idx == sorted(idx)
+                if len(idx) > 1:
+                    assert idx[-1] == f                                    # gap 1: the newest frame is always kept
+    print(f"[{name}] worst relative 1/4-res logit error {worst:.3e}, min label agreement {agree_min:.5f}")
+    assert worst < 5e-2 and agree_min >= 0.99

@@ -12,7 +12,8 @@ from oracle import rmem_oracle as O
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["deaot_small_xavier", "deaot_13obj_2engines", "deaot_small_10obj"])
+@pytest.mark.parametrize("name", ["deaot_small_xavier", "deaot_13obj_2engines", "deaot_small_10obj",
+                                  "aot_c1_256_t1", "aot_small_rmem"])
 def test_oracle_reproduces_reference_goldens(name):
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 1))
     z = np.load(os.path.join(GOLD, name + ".npz"))
