@@ -71,6 +71,8 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
 
 /* Debug aid: per-event clock64 trace of CTA 0 of the RMEM_ATTN_TC2 kernel into dev_buf ([tiles][16] int64); NULL disables. */
 int rmem_debug_attn_trace(void* dev_buf);
+/* Same for the tcgen05 GEMM: first 64 CTAs of every launch, [cta][8] int64. */
+int rmem_debug_gemm_trace(void* dev_buf);
 
 /* Qt = t16(Q + cur_pos_emb); qbias[i,t] = scale * <Qt_i, pe_mem[t]>          (transformer.py:1140-1175) */
 /* pe_mem = mem_pos_emb [n_slots, C]; pe_slot HOST [T] = slot of each memory frame (rmem_temporal_pe_slots). */
@@ -101,9 +103,11 @@ int rmem_pack_image_fwd(const float* img_nchw, void* out_nhwc8, int H, int W, vo
 /* ID bank: one_hot_mask (utils/image.py:69-74) + assign_identity (networks/engines/aot_engine.py:208-232) +
  * patch_wise_id_bank Conv2d(12->256,k17,s16,p8) (networks/models/aot.py:63-74,111-114) + id_norm
  * (networks/models/deaot.py:65-69), as a gather-sum indexed by the uint8 label. */
+/* prefix (nullable): fp32 [12][18][18][C] inclusive 2-D prefix sums of the weight over (ky, kx) per class; a patch whose
+ * in-bounds pixels share one class then costs four reads instead of up to 289 weight rows. */
 int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed /* [289,12,C] */,
-                    const float* bias, const float* ln_gamma, const float* ln_beta, void* out_t16, long long ldo,
-                    float* out_f32, int h, int w, int C, void* stream);
+                    const float* prefix, const float* bias, const float* ln_gamma, const float* ln_beta, void* out_t16,
+                    long long ldo, float* out_f32, int h, int w, int C, void* stream);
 
 /* Mask-ID assignment: bilinear(align_corners=True) upsample of the 1/4-res logits (aot_engine.py:457-463),
  * soft_logit_aggregation over k object groups (aot_engine.py:650-673), softmax -> argmax
@@ -163,6 +167,10 @@ int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx /*HOST, c
 int rmem_engine_pred_logits(const rmem_engine* e, int group, const float** logits4, int* h4, int* w4);
 int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel /*HOST cap 16*/, int* n, int* drop);
 long long rmem_engine_launch_count(const rmem_engine* e);
+/* Profiling aid: CUDA events between pipeline stages (adds a stream sync per call while on).  get_timing writes
+ * "stage total_ms count" lines into buf. */
+int rmem_engine_set_timing(rmem_engine* e, int on);
+int rmem_engine_get_timing(rmem_engine* e, char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

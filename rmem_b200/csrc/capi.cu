@@ -85,6 +85,7 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
   return long_attn_dense(a, workspace, workspace_bytes, STREAM(stream));
 }
 
+int rmem_debug_gemm_trace(void* dev_buf) { return gemm_tc_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 int rmem_debug_attn_trace(void* dev_buf) { return long_attn_tc2_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 
 int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
@@ -136,12 +137,12 @@ int rmem_pack_image_fwd(const float* img, void* out, int H, int W, void* stream)
   return pack_image(img, (t16*)out, H, W, STREAM(stream));
 }
 
-int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
-                    const float* ln_gamma, const float* ln_beta, void* out_t16, long long ldo, float* out_f32, int h,
-                    int w, int C, void* stream) {
+int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* prefix,
+                    const float* bias, const float* ln_gamma, const float* ln_beta, void* out_t16, long long ldo,
+                    float* out_f32, int h, int w, int C, void* stream) {
   RMEM_REQUIRE(label && w_packed && bias && (out_t16 || out_f32), "null argument");
   return idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_gamma, ln_beta, (t16*)out_t16, ldo, out_f32, h, w,
-                      C, STREAM(stream));
+                      C, STREAM(stream), prefix);
 }
 
 int rmem_mask_head_fwd(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits,

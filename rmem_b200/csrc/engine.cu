@@ -140,6 +140,36 @@ struct rmem_engine {
   void* mha_ws = nullptr;
   size_t mha_ws_bytes = 0;
   bool pos_ready = false;
+  // optional stage timing (debug / profiling aid): CUDA events between pipeline stages, accumulated per name
+  bool timing = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::map<std::string, std::pair<double, long long>> stage_ms;
+  void mark(const char* name, cudaStream_t s) {
+    if (!timing) return;
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    cudaEvent_t e = ev_pool[ev_used++];
+    cudaEventRecord(e, s);
+    marks.emplace_back(name, e);
+  }
+  void flush_marks(cudaStream_t s) {
+    if (!timing || marks.empty()) return;
+    cudaStreamSynchronize(s);
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      auto& acc = stage_ms[marks[i].first];
+      acc.first += ms;
+      acc.second += 1;
+    }
+    marks.clear();
+    ev_used = 0;
+  }
 
   // ---------------------------------------------------------------------------------------------
   template <typename T>
@@ -321,9 +351,11 @@ struct rmem_engine {
 
   int encode(const float* img, cudaStream_t s) {
     const Geo& G = g;
+    mark("begin", s);
     RMEM_TRY(pack_image(img, img8, G.H, G.W, s));
     RMEM_TRY(conv(img8, G.H, G.W, 8, "enc.conv1", 64, 7, 2, 3, ACT_RELU, nullptr, c1, s));
     RMEM_TRY(maxpool3x3s2(c1, x0, G.H1, G.W1, 64, G.H4, G.W4, s));
+    mark("enc.stem", s);
     t16* cur = x0;
     int Hc = G.H4, Wc = G.W4, Cc = 64;
     const int planes[3] = {64, 128, 256}, nblk[3] = {3, 4, 6}, strides[3] = {1, 2, 2};
@@ -338,11 +370,14 @@ struct rmem_engine {
         Hc = (Hc - 1) / st + 1; Wc = (Wc - 1) / st + 1; Cc = planes[li] * 4;
         cur = out;
       }
+      mark(li == 0 ? "enc.layer1" : (li == 1 ? "enc.layer2" : "enc.layer3"), s);
     }
     Lin p;
     p.A = feat16; p.lda = 1024; p.M = G.HW; p.K = 1024; p.N = kD; p.w = "proj";
     p.C = enc_tgt; p.ldc = kD; p.c_fp32 = 1;
-    return linear(p, s);
+    RMEM_TRY(linear(p, s));
+    mark("enc.proj", s);
+    return RMEM_OK;
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -351,11 +386,12 @@ struct rmem_engine {
     int rc = RMEM_OK;
     const float* w = Wt<float>("idbank.w", (size_t)289 * 12 * kD, &rc);
     const float* b = Wt<float>("idbank.b", kD, &rc);
+    const float* pf = Wt<float>("idbank.prefix", (size_t)12 * 18 * 18 * kD, &rc);
     const float* lg = cfg.model == 0 ? Wt<float>("id_norm.g", kD, &rc) : nullptr;   // deaot.py:65-69 only
     const float* lb = cfg.model == 0 ? Wt<float>("id_norm.b", kD, &rc) : nullptr;
     if (rc) return rc;
     RMEM_TRY(separate_label(label, label_is_f32, label8, G.H, G.W, gi, n_groups, s));
-    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s));
+    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s, pf));
     if (cfg.model == 0)
       for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_t16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
     return RMEM_OK;
@@ -448,6 +484,7 @@ struct rmem_engine {
       RMEM_TRY(linear(p, s));
     }
 
+    mark("gpm.proj_in", s);
     // memories
     LongAttnArgs a;
     a.HW = G.HW; a.HWp = G.HWp; a.Dk = kDk; a.Dv = kDv; a.scale = scale;
@@ -479,8 +516,11 @@ struct rmem_engine {
     a.qt = qt; a.qbias = qbias;
     a.mass = (l == 0 && !ref_mode) ? gr.mass0 : nullptr;
     if (a.mass) gr.mass_T = T;
+    mark("gpm.long.prep", s);
     RMEM_TRY(attention(a, s));
+    mark("gpm.long.attn", s);
     RMEM_TRY(gated_tail(pre + ".long", s));
+    mark("gpm.long.tail", s);
 
     // short-term windowed attention over the previous frame
     {
@@ -488,8 +528,11 @@ struct rmem_engine {
       p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
       p.w = pre + ".short.rel"; p.C = rel; p.ldc = 256; p.c_fp32 = 1;
       RMEM_TRY(linear(p, s));
+      mark("gpm.short.rel", s);
       RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
+      mark("gpm.short.attn", s);
       RMEM_TRY(gated_tail(pre + ".short", s));
+      mark("gpm.short.tail", s);
     }
 
     // self attention on cat(LN2(tgt), id_LN2(tgt_id))
@@ -527,8 +570,11 @@ struct rmem_engine {
       sa.HW = G.HW; sa.HWp = G.HWp; sa.Dk = kDk; sa.Dv = kDv; sa.scale = scale;
       sa.qt = qk; sa.kbank = qk; sa.vtbank = vt_self; sa.nslots = 1; sa.T = 1; sa.slot[0] = 0;
       sa.gate = u_self; sa.ldg = kDv; sa.out = attn_a; sa.ldo = kDv;
+      mark("gpm.self.proj", s);
       RMEM_TRY(attention(sa, s));
+      mark("gpm.self.attn", s);
       RMEM_TRY(gated_tail(pre + ".self", s));
+      mark("gpm.self.tail", s);
     }
     return RMEM_OK;
   }
@@ -550,6 +596,7 @@ struct rmem_engine {
     const float* ob = Wt<float>("gpm.out_norm.b", 2 * kD, &rc);
     if (rc) return rc;
     RMEM_TRY(groupnorm_f32(res, og, ob, gpm_out, G.HW, 2 * kD, 2, 0, stats, s));
+    mark("gpm.out_norm", s);
     return fpn_decode(gr, gpm_out, 2 * kD, s);
   }
 
@@ -580,7 +627,9 @@ struct rmem_engine {
     const t16* wo = Wt<t16>("dec.conv_out.w", (size_t)11 * 128, &rc);
     const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);
     if (rc) return rc;
-    return conv_out_logits(d1, wo, bo, gr.logits4, G.P4, 128, 11, s);
+    RMEM_TRY(conv_out_logits(d1, wo, bo, gr.logits4, G.P4, 128, 11, s));
+    mark("decoder", s);
+    return RMEM_OK;
   }
 
   // =============================================================================================
@@ -935,6 +984,8 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
   }
   if (out_logits || out_label)
     RMEM_TRY(mask_head(lg, e->n_groups, e->g.H4, e->g.W4, Ho, Wo, out_logits, out_label, s));
+  e->mark("mask_head", s);
+  e->flush_marks(s);
   return RMEM_OK;
 }
 
@@ -944,9 +995,11 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const Geo& G = e->g;
   const int cap = e->cfg.former_mem_len + e->cfg.latter_mem_len;
+  e->mark("begin", s);
   for (int gi = 0; gi < e->n_groups; ++gi) {
     Group& gr = e->groups[gi];
     RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/1, s));
+    e->mark("upd.id_embed", s);
     bool is_long = (gr.frame_step - gr.last_mem_step) >= e->cfg.long_term_mem_gap;
     if (is_long) gr.last_mem_step = gr.frame_step;
     if (e->cfg.model == 1) {
@@ -982,6 +1035,8 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
     }
     gr.parity ^= 1;   // current frame -> short-term memory
   }
+  e->mark("upd.refresh+bank", s);
+  e->flush_marks(s);
   return RMEM_OK;
 }
 
@@ -1009,6 +1064,27 @@ int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel, int* n, 
   *n = (int)gr.last_rel.size();
   for (int i = 0; i < *n; ++i) rel[i] = gr.last_rel[i];
   *drop = gr.last_drop;
+  return RMEM_OK;
+}
+
+int rmem_engine_set_timing(rmem_engine* e, int on) {
+  RMEM_REQUIRE(e, "null engine");
+  e->timing = on != 0;
+  e->stage_ms.clear();
+  e->marks.clear();
+  e->ev_used = 0;
+  return RMEM_OK;
+}
+
+int rmem_engine_get_timing(rmem_engine* e, char* buf, size_t cap) {
+  RMEM_REQUIRE(e && buf && cap > 0, "bad argument");
+  std::string out;
+  for (auto& kv : e->stage_ms) {
+    char line[160];
+    snprintf(line, sizeof(line), "%s %.6f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  snprintf(buf, cap, "%s", out.c_str());
   return RMEM_OK;
 }
 

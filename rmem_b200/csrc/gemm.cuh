@@ -51,6 +51,8 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream);
 bool gemm_tc_supported(const GemmParams& p);
 int gemm_tc_launch(const GemmParams& p, cudaStream_t stream);
 int gemm_legacy_launch(const GemmParams& p, cudaStream_t stream);
+// Debug: clock64 event trace of the first 64 CTAs of every gemm_tc launch ([cta][8] long long); nullptr disables.
+int gemm_tc_set_trace(long long* dev_buf);
 // 0 = auto (tcgen05 when supported), 1 = force the legacy mma.sync kernel (parity tests).  Thread-local.
 int& gemm_impl_switch();
 

@@ -1,7 +1,7 @@
 // tcgen05 GEMM / implicit-GEMM convolution for sm_100a with the fused epilogue contract of gemm.cuh:
 //   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T ),  fp16 operands, fp32 accumulation in TMEM.
 //
-//   block = 192 threads:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
+//   block = 320 threads:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue
 //   tile  = 128 (M) x BN (64 | 128 | 256) x 64 (K, one 128-byte swizzle atom), STAGES-deep mbarrier ring
 //   A tile: linear mode  -> 2-D TMA box [64 k, 128 rows] of the row-major matrix
 //           conv mode    -> 3-D TMA box [64 ch, BW, BH] (BW*BH = 128 output pixels of a rectangular patch) of the
@@ -22,7 +22,8 @@ using namespace tc;
 
 constexpr int TBM = 128;
 constexpr int TBK = 64;
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant, splitting the tile's columns
+constexpr int kTcThreads = (2 + kEpiWarps) * 32;
 constexpr int SMEM_A_STAGE = TBM * TBK * 2;   // 16 KB
 
 struct TcGemmParams {
@@ -46,6 +47,12 @@ struct TcGemmParams {
 };
 
 constexpr int kMaxStages = 6;
+// Optional per-CTA event trace (clock64; 8 slots per CTA, first 64 CTAs); null in production.
+__device__ long long* g_gemm_trace = nullptr;
+#define GTRACE(k)                                                                                  \
+  do {                                                                                             \
+    if (gtrace && (threadIdx.x & 31) == 0) gtrace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = clock64(); \
+  } while (0)
 template <int BN>
 struct TcSmem {
   static constexpr int kB = BN * TBK * 2;
@@ -61,7 +68,7 @@ __device__ __forceinline__ void load8h(const t16* p, float* v) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, BN <= 128 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcGemmParams p) {
   using L = TcSmem<BN>;
@@ -76,6 +83,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const gtrace = (blockIdx.y * gridDim.x + blockIdx.x) < 64 ? g_gemm_trace : nullptr;
+  if (warp == 0) GTRACE(0);
   const int n0 = blockIdx.x * BN;
   int m0 = blockIdx.y * TBM, x0 = 0, y0 = 0;
   if (p.conv) {
@@ -94,6 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
   }
   if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  __shared__ __align__(16) float s_bias[BN];
   fence_before();
   __syncthreads();
   fence_after();
@@ -102,6 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // holds its TMEM), and nothing above touched global memory, so the previous kernel's tail overlapped our prologue.
   pdl_launch_dependents();
   pdl_wait();
+  if (warp == 0) GTRACE(1);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -131,6 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int st = kb % STAGES;
       mbar_wait(&full[st], (kb / STAGES) & 1, p.err, 2);
       fence_after();
+      if (kb == 0) GTRACE(2);
+      if (kb == p.nk - 1) GTRACE(3);
       if (elect_one()) {
         const uint32_t a_addr = smem_base + st * L::kStage;
         const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + SMEM_A_STAGE);
@@ -143,8 +156,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
     }
   } else {
-    // ================================ epilogue (warps 2-5) ================================
+    // ================================ epilogue (warps 2-9) ================================
+    // A single warp per scheduler runs the ~150-instruction chunk body at ~6 cycles per instruction (event trace,
+    // profiles/r01), so the tile's columns are split over two warps per TMEM lane quadrant.
+    // per-column bias of this tile -> shared memory, read back as a broadcast (weights are not produced by the
+    // preceding kernel, but the PDL wait has passed anyway)
+    for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32)
+      s_bias[i] = (p.bias && !p.bias_m && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                // which half of the tile's columns
     const int r = quad * 32 + lane;                  // tile row
     long long gm;
     bool valid;
@@ -160,95 +181,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Prefetch this row's residual for the whole tile while the main loop runs (full 32-column chunks only): the
     // epilogue would otherwise serialise one L2 round trip per chunk.
     constexpr bool kPre = BN == 128;
-    uint4 rpre[kPre ? BN / 8 : 1];
+    constexpr int kHalfCols = BN / 2;
+    const int cbeg = half * kHalfCols;
+    uint4 rpre[kPre ? kHalfCols / 8 : 1];
     const bool res_pre = kPre && p.res != nullptr && valid;
     if (res_pre) {
-      const t16* rp = p.res + gm * p.ldr + n0;
+      const t16* rp = p.res + gm * p.ldr + n0 + cbeg;
 #pragma unroll
-      for (int c = 0; c < BN / 8; ++c)
-        if (n0 + c * 8 < p.N) rpre[c] = *reinterpret_cast<const uint4*>(rp + c * 8);
+      for (int c = 0; c < kHalfCols / 8; ++c)
+        if (n0 + cbeg + c * 8 < p.N) rpre[c] = *reinterpret_cast<const uint4*>(rp + c * 8);
     }
     mbar_wait(acc_full, 0, p.err, 3);
     fence_after();
+    if (warp == 2) GTRACE(4);
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     auto chunk = [&](const int c0) {
       const int n = n0 + c0;
       if (n >= p.N) return;                          // warp-uniform
-      float v[32];
-      tmem_ld32(lane_addr + c0, v);
-      if (!valid) return;
       // destination of this 32-column chunk (n_split is a multiple of 32)
       void* base = p.C;
       long long ld = p.ldc;
       int nn = n, f32 = p.c_fp32;
       if (n >= p.n_split) { base = p.C2; ld = p.ldc2; nn = n - p.n_split; f32 = p.c2_fp32; }
+      // ---- issue every global load of the chunk first, so their L2 round trips overlap ----
+      uint4 rr[4], gg[4];
+      const bool do_res = p.res != nullptr && valid, do_gate = p.gate != nullptr && valid;
+      const bool do_acc = f32 && p.accumulate && valid;
+      if (do_res && !kPre) {
+        const t16* rp = p.res + gm * p.ldr + n;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.alpha, bias_row);
-      {
-        if (p.bias && !p.bias_m) {
+        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
+      }
+      if (do_gate) {
+        const t16* gp = p.gate + gm * p.ldg + n;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (p.res) {
+        for (int j = 0; j < 4; ++j) gg[j] = *reinterpret_cast<const uint4*>(gp + j * 8);
+      }
+      float v[32];
+      tmem_ld32(lane_addr + c0, v);
+      if (warp == 2 && c0 == 0) GTRACE(5);
+      if (!valid) return;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 u = kPre ? rpre[kPre ? (c0 + j) / 8 : 0]
-                                 : *reinterpret_cast<const uint4*>(p.res + gm * p.ldr + n + j);
-            const float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
-            v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
-            v[j + 4] += c.x; v[j + 5] += c.y; v[j + 6] += d.x; v[j + 7] += d.y;
-          }
-        }
-        if (p.act == ACT_RELU) {
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&s_bias[c0 + j]);
+        v[j] = fmaf(v[j], p.alpha, bias_row) + b.x;
+        v[j + 1] = fmaf(v[j + 1], p.alpha, bias_row) + b.y;
+        v[j + 2] = fmaf(v[j + 2], p.alpha, bias_row) + b.z;
+        v[j + 3] = fmaf(v[j + 3], p.alpha, bias_row) + b.w;
+      }
+      if (do_res) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (n + j >= p.act_from) ? fmaxf(v[j], 0.f) : v[j];
-        } else if (p.act == ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (n + j >= p.act_from) ? silu_f(v[j]) : v[j];
-        }
-        if (p.gate) {
-          const t16* gp = p.gate + gm * p.ldg + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float t[8];
-            load8h(gp + j, t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[j + e] *= t[e];
-          }
-        }
-        if (f32) {
-          float* o = reinterpret_cast<float*>(base) + gm * ld + nn;
-          if (p.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a = *reinterpret_cast<const float4*>(o + j);
-              v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          t16* o = reinterpret_cast<t16*>(base) + gm * ld + nn;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            u.x = pack2(v[j], v[j + 1]); u.y = pack2(v[j + 2], v[j + 3]);
-            u.z = pack2(v[j + 4], v[j + 5]); u.w = pack2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = u;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = kPre ? rpre[kPre ? (c0 - cbeg) / 8 + j : 0] : rr[j];
+          const float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
+          v[j * 8] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b.x; v[j * 8 + 3] += b.y;
+          v[j * 8 + 4] += c.x; v[j * 8 + 5] += c.y; v[j * 8 + 6] += d.x; v[j * 8 + 7] += d.y;
         }
       }
+      if (n >= p.act_from) {                         // act_from is a multiple of 32 (gemm_tc_supported)
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        }
+      }
+      if (do_gate) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = gg[j];
+          const float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
+          v[j * 8] *= a.x; v[j * 8 + 1] *= a.y; v[j * 8 + 2] *= b.x; v[j * 8 + 3] *= b.y;
+          v[j * 8 + 4] *= c.x; v[j * 8 + 5] *= c.y; v[j * 8 + 6] *= d.x; v[j * 8 + 7] *= d.y;
+        }
+      }
+      if (warp == 2 && c0 == 0) GTRACE(6);
+      if (f32) {
+        float* o = reinterpret_cast<float*>(base) + gm * ld + nn;
+        if (do_acc) {                                // one batch of 8 loads = one L2 round trip
+          float4 aa[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) aa[j] = *reinterpret_cast<const float4*>(o + j * 4);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j * 4] += aa[j].x; v[j * 4 + 1] += aa[j].y; v[j * 4 + 2] += aa[j].z; v[j * 4 + 3] += aa[j].w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        t16* o = reinterpret_cast<t16*>(base) + gm * ld + nn;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          u.x = pack2(v[j], v[j + 1]); u.y = pack2(v[j + 2], v[j + 3]);
+          u.z = pack2(v[j + 4], v[j + 5]); u.w = pack2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = u;
+        }
+      }
+      if (warp == 2 && c0 == 0) GTRACE(7);
     };
     if constexpr (kPre) {
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) chunk(c0);
+      for (int cc = 0; cc < kHalfCols; cc += 32) chunk(cbeg + cc);
     } else {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) chunk(c0);
+      for (int cc = 0; cc < kHalfCols; cc += 32) chunk(cbeg + cc);
     }
     fence_before();
   }
@@ -289,6 +329,11 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
 
 }  // namespace
 
+int gemm_tc_set_trace(long long* dev_buf) {
+  RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_gemm_trace, &dev_buf, sizeof(dev_buf)));
+  return RMEM_OK;
+}
+
 bool gemm_tc_supported(const GemmParams& p) {
   if (p.K % TBK != 0) return false;
   // the epilogue stores whole 32-column chunks: ragged N only when the caller says the padding columns are writable
@@ -298,6 +343,7 @@ bool gemm_tc_supported(const GemmParams& p) {
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return false;
   if (p.ldb % 8 != 0) return false;
   if (p.n_split < p.N && p.n_split % 32 != 0) return false;
+  if (p.act != ACT_NONE && p.act_from % 32 != 0) return false;
   if (reinterpret_cast<uintptr_t>(p.C) & 15) return false;
   if (p.ldc % (p.c_fp32 ? 4 : 8) != 0) return false;
   if (p.n_split < p.N && ((reinterpret_cast<uintptr_t>(p.C2) & 15) || p.ldc2 % (p.c2_fp32 ? 4 : 8) != 0)) return false;

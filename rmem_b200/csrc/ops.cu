@@ -187,31 +187,52 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w, t16* __restrict__ y, int h,
-                               int wd, int C) {
+// 8 channels x DW_PX consecutive pixels of one row per thread: the 5 x (DW_PX + 4) input window and the 25 weight
+// vectors are loaded once and shared by the DW_PX outputs (4.5x fewer loads than one pixel per thread).
+constexpr int DW_PX = 6;
+__global__ void __launch_bounds__(128) dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w,
+                                                      t16* __restrict__ y, int h, int wd, int C) {
   const int cv = C / 8;
+  const int xt = (wd + DW_PX - 1) / DW_PX;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)h * wd * cv) return;
-  int c8 = (int)(i % cv);
-  int px = (int)((i / cv) % wd), py = (int)(i / ((long long)cv * wd));
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (i >= (long long)h * xt * cv) return;
+  const int c8 = (int)(i % cv);
+  const int px0 = (int)((i / cv) % xt) * DW_PX, py = (int)(i / ((long long)cv * xt));
+  float acc[DW_PX][8];
 #pragma unroll
+  for (int p = 0; p < DW_PX; ++p)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[p][k] = 0.f;
+#pragma unroll 1
   for (int ky = 0; ky < 5; ++ky) {
-    int iy = py + ky - 2;
+    const int iy = py + ky - 2;
     if ((unsigned)iy >= (unsigned)h) continue;
+    float col[DW_PX + 4][8];
+#pragma unroll
+    for (int j = 0; j < DW_PX + 4; ++j) {
+      const int ix = px0 + j - 2;
+      if ((unsigned)ix < (unsigned)wd) {
+        load8(x + ((size_t)iy * wd + ix) * C + c8 * 8, col[j]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) col[j][k] = 0.f;
+      }
+    }
 #pragma unroll
     for (int kx = 0; kx < 5; ++kx) {
-      int ix = px + kx - 2;
-      if ((unsigned)ix >= (unsigned)wd) continue;
-      float v[8];
-      load8(x + ((size_t)iy * wd + ix) * C + c8 * 8, v);
       const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * 5 + kx) * C + c8 * 8);
-      float4 w0 = wp[0], w1 = wp[1];
-      acc[0] += v[0] * w0.x; acc[1] += v[1] * w0.y; acc[2] += v[2] * w0.z; acc[3] += v[3] * w0.w;
-      acc[4] += v[4] * w1.x; acc[5] += v[5] * w1.y; acc[6] += v[6] * w1.z; acc[7] += v[7] * w1.w;
+      const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+      for (int p = 0; p < DW_PX; ++p) {
+        const float* v = col[p + kx];
+        acc[p][0] += v[0] * w0.x; acc[p][1] += v[1] * w0.y; acc[p][2] += v[2] * w0.z; acc[p][3] += v[3] * w0.w;
+        acc[p][4] += v[4] * w1.x; acc[p][5] += v[5] * w1.y; acc[p][6] += v[6] * w1.z; acc[p][7] += v[7] * w1.w;
+      }
     }
   }
-  store8(y + ((size_t)py * wd + px) * C + c8 * 8, acc);
+#pragma unroll
+  for (int p = 0; p < DW_PX; ++p)
+    if (px0 + p < wd) store8(y + ((size_t)py * wd + px0 + p) * C + c8 * 8, acc[p]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -333,15 +354,22 @@ __global__ void separate_label_kernel(const void* __restrict__ label, int is_f32
 }
 
 // ------------------------------------------------------------------------------------------------
-// ID bank: one block per token, one thread per output channel.
+// ID bank: one block per token, one thread per output channel.  A 17x17 patch whose in-bounds pixels all carry the
+// same class (the common case away from object boundaries) is a rectangle sum over that class' weight plane: four
+// reads of the per-class 2-D prefix table instead of up to 289 weight rows.  Mixed patches take the tap loop.
 __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, int use_ignore,
-                              const float* __restrict__ wp, const float* __restrict__ bias,
-                              const float* __restrict__ ln_g, const float* __restrict__ ln_b, t16* __restrict__ out,
-                              long long ldo, float* __restrict__ out_f32, int w, int C) {
+                              const float* __restrict__ wp, const float* __restrict__ prefix,
+                              const float* __restrict__ bias, const float* __restrict__ ln_g,
+                              const float* __restrict__ ln_b, t16* __restrict__ out, long long ldo,
+                              float* __restrict__ out_f32, int w, int C) {
   __shared__ int8_t ch[17 * 17];
   __shared__ float red[32];
+  __shared__ int s_lo, s_hi;
   const int tok = blockIdx.x;
   const int py = tok / w, px = tok - py * w;
+  if (threadIdx.x == 0) { s_lo = 127; s_hi = -1; }
+  __syncthreads();
+  int lo = 127, hi = -1;
   for (int t = threadIdx.x; t < 289; t += blockDim.x) {
     int ky = t / 17, kx = t - ky * 17;
     int iy = py * 16 - 8 + ky, ix = px * 16 - 8 + kx;
@@ -350,16 +378,30 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
       int lab = label[(size_t)iy * W + ix];
       if (lab <= 10) c = lab;
       else if (lab == 255 && use_ignore) c = 11;
+      else c = 12;                      // in bounds but in no one-hot channel: contributes nothing
+      lo = min(lo, c);
+      hi = max(hi, c);
     }
     ch[t] = (int8_t)c;
   }
+  if (lo <= hi) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
   __syncthreads();
   const int c = threadIdx.x;
   float acc = 0.f;
   if (c < C) {
-    for (int t = 0; t < 289; ++t) {
-      int k = ch[t];
-      if (k >= 0) acc += wp[((size_t)t * 12 + k) * C + c];
+    const int klo = s_lo, khi = s_hi;
+    if (prefix && klo == khi && klo < 12) {
+      // uniform patch: in-bounds taps form the rectangle [ky0, ky1) x [kx0, kx1)
+      const int ky0 = max(0, 8 - py * 16), ky1 = min(17, H + 8 - py * 16);
+      const int kx0 = max(0, 8 - px * 16), kx1 = min(17, W + 8 - px * 16);
+      const float* P = prefix + (size_t)klo * 18 * 18 * C + c;      // P[ky][kx] = sum over taps [0,ky) x [0,kx)
+      acc = P[((size_t)ky1 * 18 + kx1) * C] - P[((size_t)ky0 * 18 + kx1) * C] - P[((size_t)ky1 * 18 + kx0) * C] +
+            P[((size_t)ky0 * 18 + kx0) * C];
+    } else {
+      for (int t = 0; t < 289; ++t) {
+        int k = ch[t];
+        if (k >= 0 && k < 12) acc += wp[((size_t)t * 12 + k) * C + c];
+      }
     }
     acc += bias[c];
   }
@@ -667,8 +709,8 @@ int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y,
 
 int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "dwconv: C %% 8");
-  long long n = (long long)h * wd * (C / 8);
-  dwconv5_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, w, y, h, wd, C);
+  long long n = (long long)h * ((wd + DW_PX - 1) / DW_PX) * (C / 8);
+  dwconv5_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(x, w, y, h, wd, C);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -720,9 +762,10 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
-                 cudaStream_t s) {
+                 cudaStream_t s, const float* prefix) {
   RMEM_REQUIRE(C <= 256 && C % 32 == 0, "idbank: unsupported C=%d", C);
-  idbank_kernel<<<h * w, 256, 0, s>>>(label, H, W, use_ignore, w_packed, bias, ln_g, ln_b, out, ldo, out_f32, w, C);
+  idbank_kernel<<<h * w, 256, 0, s>>>(label, H, W, use_ignore, w_packed, prefix, bias, ln_g, ln_b, out, ldo, out_f32,
+                                      w, C);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -59,9 +59,11 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 
 // ID bank (aot.py:111-114, deaot.py:65-69): gather-sum of Conv2d(12->C,k17,s16,p8) weight slices indexed by the
 // label, + bias, optional LayerNorm.  w_packed fp32 [17*17][12][C].  out t16 [h*w, ldo].
+// `prefix` (optional) fp32 [12][18][18][C]: per-class inclusive 2-D prefix sums of the weight over (ky, kx), lets a patch
+// of uniform class be a 4-read rectangle sum.
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
-                 cudaStream_t s);
+                 cudaStream_t s, const float* prefix = nullptr);
 
 // Mask head (aot_engine.py:457-463, 650-673; evaluator.py:430-441): k engines' planar logits [11,h4,w4] ->
 // bilinear(align_corners=True) -> soft aggregation -> out_logits [1+10k, Ho, Wo] (optional) and uint8 label.

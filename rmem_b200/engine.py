@@ -231,6 +231,20 @@ class DeAOTInferEngine:
         assert lab.numel() == H * W, "update_memory expects the label at the input size (evaluator.py:518-523)"
         _capi.check(lib.rmem_engine_update_memory(self._h, _capi.ptr(lab), is_f32, _capi.stream_ptr()))
 
+    def set_timing(self, on: bool):
+        """Profiling aid: per-stage CUDA-event timing inside the engine (adds a sync per call while on)."""
+        _capi.check(_capi.load().rmem_engine_set_timing(self._h, int(on)))
+
+    def get_timing(self):
+        """{stage: (mean_ms, count)} accumulated since set_timing(True)."""
+        buf = C.create_string_buffer(16384)
+        _capi.check(_capi.load().rmem_engine_get_timing(self._h, buf, C.c_size_t(16384)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, tot, n = line.split()
+            out[name] = (float(tot) / max(int(n), 1), int(n))
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(_capi.load().rmem_engine_launch_count(self._h)) if self._h else 0

@@ -139,14 +139,16 @@ def transpose(x: torch.Tensor, ldy: int) -> torch.Tensor:
 
 
 def id_embedding(label_u8: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, ln_g, ln_b,
-                 use_ignore: bool) -> torch.Tensor:
-    """label uint8 [H,W] -> fp32 [hw, C]."""
+                 use_ignore: bool, prefix: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """label uint8 [H,W] -> fp32 [hw, C].  prefix: optional [12,18,18,C] table (weights.py) enabling the uniform-patch
+    shortcut."""
     lib = _capi.load()
     H, W = label_u8.shape
     h, w = (H - 1) // 16 + 1, (W - 1) // 16 + 1
     Cc = bias.numel()
     out = torch.empty(h * w, Cc, dtype=torch.float32, device=label_u8.device)
-    _capi.check(lib.rmem_idbank_fwd(_capi.ptr(label_u8), H, W, int(use_ignore), _capi.ptr(w_packed), _capi.ptr(bias),
+    _capi.check(lib.rmem_idbank_fwd(_capi.ptr(label_u8), H, W, int(use_ignore), _capi.ptr(w_packed),
+                                    _capi.ptr(prefix), _capi.ptr(bias),
                                     _capi.ptr(ln_g), _capi.ptr(ln_b), None, C.c_longlong(0), _capi.ptr(out), h, w, Cc,
                                     _capi.stream_ptr()))
     return out

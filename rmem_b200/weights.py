@@ -78,6 +78,10 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
     wb = sd["patch_wise_id_bank.weight"]                                    # [C,12,17,17]
     out["idbank.w"] = wb.permute(2, 3, 1, 0).reshape(17 * 17, wb.shape[1], wb.shape[0]).contiguous()
     out["idbank.b"] = sd["patch_wise_id_bank.bias"].contiguous()
+    # per-class inclusive 2-D prefix sums over (ky, kx): P[k][ky][kx][c] = sum_{y<ky, x<kx} w[c, k, y, x]  (fp64 -> fp32)
+    pre = torch.zeros(wb.shape[1], 18, 18, wb.shape[0], dtype=torch.float64)
+    pre[:, 1:, 1:, :] = wb.double().permute(1, 2, 3, 0).cumsum(1).cumsum(2)
+    out["idbank.prefix"] = pre.float().contiguous()
     if deaot:
         norm("id_norm", "id_norm")
     out["cur_pos_emb"] = sd["cur_pos_emb"].reshape(-1).contiguous()

@@ -138,10 +138,11 @@ def test_id_embedding_matches_conv_of_one_hot(ops, cuda_device):
     pk = pack_deaot(sd)
     for use_ignore in (False, True):
         ref = O.id_embedding(sd, cfg, O.one_hot_with_ignore(lab, use_ignore))
-        out = ops.id_embedding(lab[0, 0].to(torch.uint8).to(cuda_device), pk["idbank.w"].to(cuda_device),
-                               pk["idbank.b"].to(cuda_device), pk["id_norm.g"].to(cuda_device),
-                               pk["id_norm.b"].to(cuda_device), use_ignore)
-        assert relfro(out, ref) < 2e-4, use_ignore
+        for prefix in (None, pk["idbank.prefix"].to(cuda_device)):      # tap loop only / uniform-patch shortcut
+            out = ops.id_embedding(lab[0, 0].to(torch.uint8).to(cuda_device), pk["idbank.w"].to(cuda_device),
+                                   pk["idbank.b"].to(cuda_device), pk["id_norm.g"].to(cuda_device),
+                                   pk["id_norm.b"].to(cuda_device), use_ignore, prefix=prefix)
+            assert relfro(out, ref) < 2e-4, (use_ignore, prefix is not None)
 
 
 def _attn_inputs(T, HW, g, sharp=1.0, Dv=1024):

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--latter", type=int, default=7)
     ap.add_argument("--gap", type=int, default=5)
     ap.add_argument("--attn", default="tc2", choices=["tc2", "tc", "dense"])
+    ap.add_argument("--stages", action="store_true", help="print per-stage CUDA-event times instead of profiling")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     sd = make_state_dict("r50_deaotl", seed=0, sharpen=4.0)
@@ -43,6 +44,18 @@ def main():
         eng.update_memory(lab)
     eng.long_term_mem_gap = a.gap
     torch.cuda.synchronize()
+    if a.stages:
+        eng.set_timing(True)
+        for i in range(a.frames):
+            lab = eng.propagate_label(frames[1 + i % 3:2 + i % 3], output_size=(a.H, a.W))
+            eng.update_memory(lab)
+        t = eng.get_timing()
+        per_frame = {k: v[0] * v[1] / a.frames for k, v in t.items()}
+        tot = sum(per_frame.values())
+        for k, v in sorted(per_frame.items(), key=lambda kv: -kv[1]):
+            print(f"{k:20s} {v * 1e3:9.1f} us/frame  {100 * v / tot:5.1f}%   ({t[k][1] / a.frames:.1f} x {t[k][0] * 1e3:.1f} us)")
+        print(f"{'total':20s} {tot * 1e3:9.1f} us/frame")
+        return
     torch.cuda.profiler.start()
     for i in range(a.frames):
         lab = eng.propagate_label(frames[1 + i % 3:2 + i % 3], output_size=(a.H, a.W))
