@@ -105,6 +105,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from rmem_b200 import _capi
     from rmem_b200.engine import DeAOTModel, RmemConfig, build_engine
@@ -141,15 +142,42 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # End-to-end leg: every frame starts in PINNED HOST memory and every label map ends in pinned host memory.  The
+    # host->device copy of frame i+1 is issued on a copy stream while frame i computes (what a prefetching loader does,
+    # evaluator.py:308,372 uses pin_memory + non_blocking); both copies are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty(1, 3, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i, src):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])           # frame i-2 has finished reading this staging buffer
+            stage[b].copy_(src[1 + i % ring: 2 + i % ring], non_blocking=True)
+            staged[b].record(copy_stream)
+
     def timed(src, steps, e2e):
-        host_lab = torch.empty(1, 1, H, W, dtype=torch.uint8).pin_memory()
+        host_lab = torch.empty(2, 1, 1, H, W, dtype=torch.uint8).pin_memory()
+        main = torch.cuda.current_stream()
+        for b in range(2):
+            consumed[b].record(main)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if e2e:
+            prefetch(0, src)
         for i in range(steps):
-            lab = step(i, src)
             if e2e:
-                host_lab.copy_(lab, non_blocking=True)
+                if i + 1 < steps:
+                    prefetch(i + 1, src)
+                main.wait_event(staged[i % 2])
+                lab = eng.propagate_label(stage[i % 2], output_size=(H, W))
+                consumed[i % 2].record(main)
+                eng.update_memory(lab)
+                host_lab[i % 2].copy_(lab, non_blocking=True)
+            else:
+                lab = step(i, src)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -194,7 +222,7 @@ def run_ours(args):
                              "exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
                     "d2h_bytes_per_step": H * W},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
@@ -267,7 +295,20 @@ def measure_attention_roofline(eng, dev, args):
             "peak_source": pk["source"] + " burst (op timed alone)", "ms_per_launch": round(ms, 4),
             "timing": f"{iters} back-to-back launches between two CUDA events, 4 banks (148 MB) cycled so operands "
                       "are never L2-resident from the previous launch",
-            "algorithmic_flops_per_launch": LT_FLOPS_PER_LAUNCH, "traffic": None}
+            "algorithmic_flops_per_launch": LT_FLOPS_PER_LAUNCH, "traffic": ncu_traffic()}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the attention kernel, from the committed
+    `ncu --set full` capture (profiles/attn_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        return {"bytes_per_launch": d["dram_bytes_per_launch"], "source": d["source"]}
+    except Exception:
+        return None
 
 
 def cpu_baseline(sample_frames: int):
