@@ -106,6 +106,20 @@ int rmem_local_attn_fwd(const void* q, long long ldq, const void* k, long long l
                     (t16*)out, ldo, h, w, Dv, scale, STREAM(stream));
 }
 
+int rmem_local_attn_tc_workspace_bytes(int h, int w, int Dv, size_t* bytes) {
+  RMEM_REQUIRE(bytes, "null bytes");
+  *bytes = local_attn_tc_workspace(h, w, Dv);
+  return RMEM_OK;
+}
+
+int rmem_local_attn_tc_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                           const float* rel, long long ldrel, const void* gate, long long ldg, void* out,
+                           long long ldo, int h, int w, int Dv, float scale, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  return local_attn_tc((const t16*)q, ldq, (const t16*)k, ldk, (const t16*)v, ldv, rel, ldrel, (const t16*)gate, ldg,
+                       (t16*)out, ldo, h, w, Dv, scale, workspace, workspace_bytes, STREAM(stream));
+}
+
 int rmem_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
                        int P, int C, void* stream) {
   return layernorm(x, ldx, gamma, beta, (t16*)y, ldy, nullptr, 0, P, C, STREAM(stream));

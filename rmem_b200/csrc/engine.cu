@@ -131,6 +131,8 @@ struct rmem_engine {
   uint8_t* label8;
   void* attn_ws;
   size_t attn_ws_bytes;
+  void* local_ws = nullptr;
+  size_t local_ws_bytes = 0;
   char* arena_base = nullptr;
   size_t state_begin = 0, state_bytes = 0;   // region zeroed per clip (banks, short-term memory)
   bool ones_ready = false;
@@ -249,6 +251,8 @@ struct rmem_engine {
     size_t ws_tc2 = long_attn_tc2_workspace(G.HW, G.HWp, nslots, kDv);
     attn_ws_bytes = cfg.attn_impl == RMEM_ATTN_TC2 ? ws_tc2 : (cfg.attn_impl == RMEM_ATTN_TC ? ws_tc : ws_dense);
     attn_ws = a.take<char>(attn_ws_bytes);
+    local_ws_bytes = local_attn_tc_workspace(G.h, G.w, kDv);
+    local_ws = a.take<char>(local_ws_bytes);
     state_begin = a.off;
     groups.assign(cfg.max_engines, Group());
     for (auto& gr : groups) {
@@ -529,7 +533,11 @@ struct rmem_engine {
       p.w = pre + ".short.rel"; p.C = rel; p.ldc = 256; p.c_fp32 = 1;
       RMEM_TRY(linear(p, s));
       mark("gpm.short.rel", s);
-      RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
+      if (cfg.attn_impl == RMEM_ATTN_DENSE)
+        RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
+      else
+        RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale,
+                               local_ws, local_ws_bytes, s));
       mark("gpm.short.attn", s);
       RMEM_TRY(gated_tail(pre + ".short", s));
       mark("gpm.short.tail", s);

@@ -177,9 +177,10 @@ def test_temporal_pe_slots_match_oracle(ops, cuda_device):
         assert ops.temporal_pe_slots(T) == ref, T
 
 
-def test_local_attention(ops, cuda_device):
+@pytest.mark.parametrize("impl", ["tc", "cuda_core"])
+def test_local_attention(ops, cuda_device, impl):
     g = torch.Generator().manual_seed(6)
-    for (h, w) in [(17, 21), (31, 54)]:
+    for (h, w) in [(17, 21), (31, 54), (9, 70), (46, 81)]:
         HW = h * w
         q = bfr(torch.randn(HW, 128, generator=g))
         k = bfr(torch.randn(HW, 128, generator=g))
@@ -190,8 +191,9 @@ def test_local_attention(ops, cuda_device):
         ref = O.local_attention(q, k, v, rw, rb, h, w) * gate
         out = ops.local_attention(q.to(cuda_device).to(OP), k.to(cuda_device).to(OP),
                                   v.to(cuda_device).to(OP), rw.to(cuda_device), rb.to(cuda_device), h, w,
-                                  gate.to(cuda_device).to(OP))
-        assert relfro(out, ref) < 6e-3, (h, w)
+                                  gate.to(cuda_device).to(OP), impl=impl)
+        assert torch.isfinite(out.float()).all()
+        assert relfro(out, ref) < 6e-3, (h, w, impl)
 
 
 def test_mask_head_bit_exact_labels(ops, cuda_device):
