@@ -15,6 +15,7 @@ struct SlotMap { int slot[kMaxBankFrames]; };
 __global__ void softmax_mass_kernel(const float* __restrict__ S, t16* __restrict__ P, long long ld, int HW, int HWp,
                                     int nslots, int T, SlotMap sm, const float* __restrict__ qbias,
                                     float* __restrict__ mass) {
+  pdl_prologue();
   __shared__ float red[32];
   __shared__ float s_mass[kMaxBankFrames];
   const int row = blockIdx.x;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(128) local_attn_kernel(const t16* __restrict__
                                                          const t16* __restrict__ gate, long long ldg,
                                                          t16* __restrict__ out, long long ldo, int h, int w,
                                                          float scale) {
+  pdl_prologue();
   __shared__ float s_q[4][128];
   __shared__ float s_p[4][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,7 +199,7 @@ int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_byt
   }
   SlotMap sm;
   for (int t = 0; t < kMaxBankFrames; ++t) sm.slot[t] = t < a.T ? a.slot[t] : -1;
-  softmax_mass_kernel<<<a.HW, 256, 0, s>>>(S, P, ld, a.HW, a.HWp, a.nslots, a.T, sm, a.qbias, a.mass);
+  RMEM_CUDA_CHECK(launch_pdl(softmax_mass_kernel, dim3(a.HW), dim3(256), 0, s, S, P, ld, a.HW, a.HWp, a.nslots, a.T, sm, a.qbias, a.mass));
   RMEM_LAUNCH_CHECK();
   GemmParams g;
   g.A = P; g.lda = ld;
@@ -238,8 +240,7 @@ int mha_dense(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStr
   }
   SlotMap sm;
   for (int t = 0; t < kMaxBankFrames; ++t) sm.slot[t] = t < a.T ? a.slot[t] : -1;
-  softmax_mass_kernel<<<dim3(a.HW, a.H), 256, 0, s>>>(S, P, ld, a.HW, a.HWp, a.nslots, a.T, sm, a.qbias,
-                                                      a.mass ? mass_h : nullptr);
+  RMEM_CUDA_CHECK(launch_pdl(softmax_mass_kernel, dim3(dim3(a.HW, a.H)), dim3(256), 0, s, S, P, ld, a.HW, a.HWp, a.nslots, a.T, sm, a.qbias, a.mass ? mass_h : nullptr));
   RMEM_LAUNCH_CHECK();
   if (a.mass) RMEM_TRY(mean_heads(mass_h, a.mass, a.H, (long long)a.HW * a.T, s));
   GemmParams g;
@@ -259,11 +260,11 @@ int local_attn(const t16* q, long long ldq, const t16* k, long long ldk, const t
                "local_attn: row strides must keep 16B alignment");
   const int grid = cdiv(h * w, 4);
   if (Dv == 1024)
-    local_attn_kernel<4><<<grid, 128, 0, s>>>(q, ldq, k, ldk, v, ldv, rel, ldrel, gate, ldg, out, ldo, h, w, scale);
+    RMEM_CUDA_CHECK(launch_pdl(local_attn_kernel<4>, dim3(grid), dim3(128), 0, s, q, ldq, k, ldk, v, ldv, rel, ldrel, gate, ldg, out, ldo, h, w, scale));
   else if (Dv == 512)
-    local_attn_kernel<2><<<grid, 128, 0, s>>>(q, ldq, k, ldk, v, ldv, rel, ldrel, gate, ldg, out, ldo, h, w, scale);
+    RMEM_CUDA_CHECK(launch_pdl(local_attn_kernel<2>, dim3(grid), dim3(128), 0, s, q, ldq, k, ldk, v, ldv, rel, ldrel, gate, ldg, out, ldo, h, w, scale));
   else
-    local_attn_kernel<1><<<grid, 128, 0, s>>>(q, ldq, k, ldk, v, ldv, rel, ldrel, gate, ldg, out, ldo, h, w, scale);
+    RMEM_CUDA_CHECK(launch_pdl(local_attn_kernel<1>, dim3(grid), dim3(128), 0, s, q, ldq, k, ldk, v, ldv, rel, ldrel, gate, ldg, out, ldo, h, w, scale));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -189,6 +189,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_prologue();   // barriers, TMEM and descriptors are set up; global memory is touched only from here on
 
   if (warp == kWarpK) {
     // ================================ Q + K producer ================================
@@ -493,6 +494,7 @@ constexpr int kMaxSegsPerUnit = 24;
 __global__ void __launch_bounds__(256) combine2_kernel(const Tc2Params p, const t16* __restrict__ gate, long long ldg,
                                                        t16* __restrict__ out, long long ldo,
                                                        float* __restrict__ mass) {
+  pdl_prologue();
   __shared__ int s_n[4];
   __shared__ int s_slot[4][kMaxSegsPerUnit];        // (cta * 2 + seg)
   __shared__ float s_w[4][kMaxSegsPerUnit];         // l_s 2^(m_s - M) / L
@@ -672,9 +674,9 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(long_attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_done = true;
   }
-  long_attn_tc2_kernel<<<p.nCTA, kThreads, SMEM_TOTAL, s>>>(*mq, *mk, *mv, p);
+  RMEM_CUDA_CHECK(launch_pdl(long_attn_tc2_kernel, dim3(p.nCTA), dim3(kThreads), SMEM_TOTAL, s, *mq, *mk, *mv, p));
   RMEM_LAUNCH_CHECK();
-  combine2_kernel<<<a.HW, 256, 0, s>>>(p, a.gate, a.ldg, a.out, a.ldo, a.mass);
+  RMEM_CUDA_CHECK(launch_pdl(combine2_kernel, dim3(a.HW), dim3(256), 0, s, p, a.gate, a.ldg, a.out, a.ldo, a.mass));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -149,4 +149,33 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
 
+// ---- programmatic dependent launch (sm_90+) ----
+// Every kernel of the path starts with pdl_prologue(): it lets the NEXT kernel in the stream be scheduled early (its
+// launch latency and prologue overlap this kernel), then blocks until the PREVIOUS kernel has completed and its memory
+// is visible.  Nothing may touch global memory before it.  Kernels are launched with launch_pdl() (the PDL attribute);
+// a kernel launched without it simply behaves as usual.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace rmem

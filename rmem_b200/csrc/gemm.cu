@@ -34,6 +34,7 @@ __device__ __forceinline__ void mma_t16(float* c, const uint32_t* a, const uint3
 
 template <int BM, int BN, int WARPS_M, int WARPS_N>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_kernel(const GemmParams p) {
+  pdl_prologue();
   constexpr int NT = WARPS_M * WARPS_N * 32;
   constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
   constexpr int MI = WM / 16, NI = WN / 8;
@@ -235,7 +236,7 @@ int launch_cfg(const GemmParams& p, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.batch > 1 ? p.batch : 1);
-  gemm_kernel<BM, BN, WARPS_M, WARPS_N><<<grid, WARPS_M * WARPS_N * 32, smem, stream>>>(p);
+  RMEM_CUDA_CHECK(launch_pdl(gemm_kernel<BM, BN, WARPS_M, WARPS_N>, dim3(grid), dim3(WARPS_M * WARPS_N * 32), smem, stream, p));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -110,8 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
   // Programmatic dependent launch: the next kernel in the stream may start its own prologue now (this CTA already
   // holds its TMEM), and nothing above touched global memory, so the previous kernel's tail overlapped our prologue.
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_prologue();
   if (warp == 0) GTRACE(1);
 
   if (warp == 0) {

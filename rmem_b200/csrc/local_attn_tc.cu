@@ -143,6 +143,7 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_prologue();   // barriers, TMEM and descriptors are set up; global memory is touched only from here on
 
   if (warp == kWarpK) {
     // ================================ Q + K producer ================================
@@ -373,6 +374,7 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // v token-major [h*w, Dv] (row stride ldv) -> value-major, row-padded [Dv][h][wp] (pad columns zero)
 __global__ void transpose_pad_kernel(const t16* __restrict__ x, long long ldx, t16* __restrict__ y, int h, int w, int wp,
                                      int C) {
+  pdl_prologue();
   __shared__ t16 tile[64][66];
   const int yy = blockIdx.z;                       // frame row
   const int x0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
@@ -417,7 +419,7 @@ int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, cons
   t16* vt = reinterpret_cast<t16*>(workspace);
   {
     dim3 grid(cdiv(wp, 64), cdiv(Dv, 64), h), block(32, 8);
-    transpose_pad_kernel<<<grid, block, 0, s>>>(v, ldv, vt, h, w, wp, Dv);
+    RMEM_CUDA_CHECK(launch_pdl(transpose_pad_kernel, dim3(grid), dim3(block), 0, s, v, ldv, vt, h, w, wp, Dv));
     RMEM_LAUNCH_CHECK();
   }
   const CUtensorMap *mq, *mk, *mv;
@@ -449,7 +451,7 @@ int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, cons
     attr_done = true;
   }
   const int patches = cdiv(h, QH) * p.tiles_x;
-  local_attn_tc_kernel<<<patches * p.n_dv, kThreads, SMEM_TOTAL, s>>>(*mq, *mk, *mv, p);
+  RMEM_CUDA_CHECK(launch_pdl(local_attn_tc_kernel, dim3(patches * p.n_dv), dim3(kThreads), SMEM_TOTAL, s, *mq, *mk, *mv, p));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -21,6 +21,7 @@ __device__ __forceinline__ void store8(t16* p, const float* v) {
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_image_kernel(const float* __restrict__ img, t16* __restrict__ out, int HW) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   float v[8] = {img[i], img[HW + i], img[2 * HW + i], 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -29,6 +30,7 @@ __global__ void pack_image_kernel(const float* __restrict__ img, t16* __restrict
 
 __global__ void maxpool_kernel(const t16* __restrict__ x, t16* __restrict__ y, int Hin, int Win, int C, int Hout,
                                int Wout) {
+  pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Hout * Wout * cv) return;
@@ -58,6 +60,7 @@ constexpr int LN_MAXV = 16;  // C <= 512
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, t16* __restrict__ y, long long ldy,
                                  t16* __restrict__ y2, long long ldy2, const float* __restrict__ add2, int P, int C) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -102,6 +105,7 @@ __device__ __forceinline__ void gn_load8<float>(const float* p, float* v) {
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, double* __restrict__ stats,
                                 double* __restrict__ partials, unsigned int* __restrict__ counter) {
+  pdl_prologue();
   // thread -> fixed 8-channel vector column; rows strided over the grid.
   const int cv = C / 8;
   const int col = threadIdx.x % cv;
@@ -147,6 +151,7 @@ template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, t16* __restrict__ y, int P, int C, int G, int relu,
                                 const double* __restrict__ stats) {
+  pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * cv) return;
@@ -178,10 +183,10 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
   // scratch layout (doubles): [0,64) stats | [64] counter (zero-initialised once, self re-arming) | [72,..) partials
   int rows_per_block = 256 / (C / 8);
   int grid = min(cdiv(P, rows_per_block * 4), kGnMaxBlocks);
-  gn_stats_kernel<T><<<grid, 256, 0, s>>>(x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64));
+  RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<T>, dim3(grid), dim3(256), 0, s, x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
   RMEM_LAUNCH_CHECK();
   long long nvec = (long long)P * (C / 8);
-  gn_apply_kernel<T><<<(unsigned)((nvec + 255) / 256), 256, 0, s>>>(x, gamma, beta, y, P, C, G, relu, stats);
+  RMEM_CUDA_CHECK(launch_pdl(gn_apply_kernel<T>, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, s, x, gamma, beta, y, P, C, G, relu, stats));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -192,6 +197,7 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
 constexpr int DW_PX = 6;
 __global__ void __launch_bounds__(128) dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w,
                                                       t16* __restrict__ y, int h, int wd, int C) {
+  pdl_prologue();
   const int cv = C / 8;
   const int xt = (wd + DW_PX - 1) / DW_PX;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,6 +262,7 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
 
 __global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__ y, int hin, int win, int hout,
                                      int wout, int C) {
+  pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)hout * wout * cv) return;
@@ -279,6 +286,7 @@ __global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__
 // conv_out: one warp per pixel, Cin <= 256, Cout <= 16.  Weights t16 [Cout, Cin].
 __global__ void conv_out_kernel(const t16* __restrict__ x, const t16* __restrict__ w, const float* __restrict__ b,
                                 float* __restrict__ out, int P, int Cin, int Cout) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [Cout][Cin]
   for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = t2f(w[i]);
   __syncthreads();
@@ -304,6 +312,7 @@ __global__ void conv_out_kernel(const t16* __restrict__ x, const t16* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void transpose_kernel(const t16* __restrict__ x, long long ldx, t16* __restrict__ y, long long ldy, int P,
                                  int C) {
+  pdl_prologue();
   __shared__ t16 tile[64][66];
   int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   for (int i = threadIdx.y; i < 64; i += blockDim.y) {
@@ -328,6 +337,7 @@ __global__ void transpose_kernel(const t16* __restrict__ x, long long ldx, t16* 
 
 __global__ void copy2d_kernel(const t16* __restrict__ src, long long lds, t16* __restrict__ dst, long long ldd, int P,
                               int C) {
+  pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * cv) return;
@@ -336,6 +346,7 @@ __global__ void copy2d_kernel(const t16* __restrict__ src, long long lds, t16* _
   *reinterpret_cast<uint4*>(dst + r * ldd + c8 * 8) = *reinterpret_cast<const uint4*>(src + r * lds + c8 * 8);
 }
 __global__ void fill_kernel(t16* __restrict__ dst, long long ldd, int P, int C, float v) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * C) return;
   dst[(i / C) * ldd + (i % C)] = f2t(v);
@@ -343,6 +354,7 @@ __global__ void fill_kernel(t16* __restrict__ dst, long long ldd, int P, int C, 
 
 __global__ void separate_label_kernel(const void* __restrict__ label, int is_f32, uint8_t* __restrict__ out, int n,
                                       int engine, int n_engines) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int v = is_f32 ? (int)reinterpret_cast<const float*>(label)[i] : (int)reinterpret_cast<const uint8_t*>(label)[i];
@@ -362,6 +374,7 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
                               const float* __restrict__ bias, const float* __restrict__ ln_g,
                               const float* __restrict__ ln_b, t16* __restrict__ out, long long ldo,
                               float* __restrict__ out_f32, int w, int C) {
+  pdl_prologue();
   __shared__ int8_t ch[17 * 17];
   __shared__ float red[32];
   __shared__ int s_lo, s_hi;
@@ -434,6 +447,7 @@ __device__ __forceinline__ void softmax11(const float* x, float* p) {
 
 __global__ void mask_head_kernel(LogitPtrs lp, int k, int h4, int w4, int Ho, int Wo, float* __restrict__ out_logits,
                                  uint8_t* __restrict__ out_label) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ho * Wo) return;
   int oy = i / Wo, ox = i - oy * Wo;
@@ -500,6 +514,7 @@ __global__ void mask_head_kernel(LogitPtrs lp, int k, int h4, int w4, int Ho, in
 // ------------------------------------------------------------------------------------------------
 __global__ void evict_rel_kernel(const float* __restrict__ mass, int T, const float* __restrict__ logits4, int h4,
                                  int w4, int h, int w, float* __restrict__ rel) {
+  pdl_prologue();
   __shared__ float red[32];
   float acc[16];
 #pragma unroll
@@ -537,6 +552,7 @@ __global__ void evict_rel_kernel(const float* __restrict__ mass, int T, const fl
 // ---- small elementwise kernels of the AOT block (transformer.py:553-692) ----
 __global__ void add_t16_kernel(const t16* __restrict__ a, long long lda, const t16* __restrict__ b, long long ldb,
                                t16* __restrict__ y, long long ldy, int P, int C) {
+  pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * cv) return;
@@ -554,6 +570,7 @@ __global__ void add_t16_kernel(const t16* __restrict__ a, long long lda, const t
 __global__ void add_layernorm_kernel(const t16* __restrict__ a, long long lda, const t16* __restrict__ b,
                                      long long ldb, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      t16* __restrict__ y, long long ldy, int P, int C) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -582,6 +599,7 @@ __global__ void add_layernorm_kernel(const t16* __restrict__ a, long long lda, c
 
 __global__ void accum_t16_kernel(const t16* __restrict__ x, long long ldx, float* __restrict__ y, long long ldy, int P,
                                  int C) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * C) return;
   long long r = i / C;
@@ -591,6 +609,7 @@ __global__ void accum_t16_kernel(const t16* __restrict__ x, long long ldx, float
 
 __global__ void cvt_f32_t16_kernel(const float* __restrict__ x, long long ldx, t16* __restrict__ y, long long ldy,
                                    int P, int C) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * C) return;
   long long r = i / C;
@@ -600,6 +619,7 @@ __global__ void cvt_f32_t16_kernel(const float* __restrict__ x, long long ldx, t
 
 // PositionEmbeddingSine(num_pos_feats = C/2, normalize = True)  (position.py:35-77) -> fp32 [h*w, C]
 __global__ void sine_pe_kernel(float* __restrict__ out, int h, int w, int C) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)h * w * C) return;
   const int c = (int)(i % C);
@@ -617,6 +637,7 @@ __global__ void sine_pe_kernel(float* __restrict__ out, int h, int w, int C) {
 
 // mean over heads of the per-head attention mass: in [H][P][T] -> out [P][T]
 __global__ void mean_heads_kernel(const float* __restrict__ in, float* __restrict__ out, int H, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
@@ -630,6 +651,7 @@ struct PeSlots { int s[16]; };
 __global__ void qprep_heads_kernel(const t16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
                                    const float* __restrict__ pe_mem, PeSlots ps, int T, float scale,
                                    t16* __restrict__ qt, float* __restrict__ qbias, int P, int H) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -649,6 +671,7 @@ __global__ void qprep_heads_kernel(const t16* __restrict__ q, long long ldq, con
 __global__ void qprep_kernel(const t16* __restrict__ q, long long ldq, const float* __restrict__ pe_cur,
                              const float* __restrict__ pe_mem, PeSlots ps, int T, float scale, t16* __restrict__ qt,
                              float* __restrict__ qbias, int P, int C) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -677,7 +700,7 @@ __global__ void qprep_kernel(const t16* __restrict__ q, long long ldq, const flo
 
 // ================================================================================================
 int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s) {
-  pack_image_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(img, out, H * W);
+  RMEM_CUDA_CHECK(launch_pdl(pack_image_kernel, dim3(cdiv(H * W, 256)), dim3(256), 0, s, img, out, H * W));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -685,7 +708,7 @@ int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s) {
 int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
   long long n = (long long)Hout * Wout * (C / 8);
-  maxpool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, Hin, Win, C, Hout, Wout);
+  RMEM_CUDA_CHECK(launch_pdl(maxpool_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, y, Hin, Win, C, Hout, Wout));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -693,7 +716,7 @@ int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wo
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy, t16* y2,
               long long ldy2, int P, int C, cudaStream_t s, const float* add2) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm: unsupported C=%d", C);
-  layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(x, ldx, gamma, beta, y, ldy, y2, ldy2, add2, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, x, ldx, gamma, beta, y, ldy, y2, ldy2, add2, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -710,7 +733,7 @@ int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y,
 int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "dwconv: C %% 8");
   long long n = (long long)h * ((wd + DW_PX - 1) / DW_PX) * (C / 8);
-  dwconv5_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(x, w, y, h, wd, C);
+  RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, s, x, w, y, h, wd, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -718,7 +741,7 @@ int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaSt
 int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "upsample: C %% 8");
   long long n = (long long)hout * wout * (C / 8);
-  upsample_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, hin, win, hout, wout, C);
+  RMEM_CUDA_CHECK(launch_pdl(upsample_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, y, hin, win, hout, wout, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -727,14 +750,14 @@ int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int 
                     cudaStream_t s) {
   RMEM_REQUIRE(Cin % 32 == 0 && Cin <= 256 && Cout <= 16, "conv_out: unsupported Cin=%d Cout=%d", Cin, Cout);
   int grid = min(cdiv(P, 8), 148 * 8);
-  conv_out_kernel<<<grid, 256, Cout * Cin * sizeof(float), s>>>(x, w, b, out, P, Cin, Cout);
+  RMEM_CUDA_CHECK(launch_pdl(conv_out_kernel, dim3(grid), dim3(256), Cout * Cin * sizeof(float), s, x, w, b, out, P, Cin, Cout));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
 int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s) {
   dim3 grid(cdiv(P, 64), cdiv(C, 64)), block(32, 8);
-  transpose_kernel<<<grid, block, 0, s>>>(x, ldx, y, ldy, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(transpose_kernel, dim3(grid), dim3(block), 0, s, x, ldx, y, ldy, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -742,20 +765,20 @@ int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int
 int copy2d_t16(const t16* src, long long lds, t16* dst, long long ldd, int P, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "copy2d: alignment");
   long long n = (long long)P * (C / 8);
-  copy2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, lds, dst, ldd, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(copy2d_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, src, lds, dst, ldd, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 int fill_t16(t16* dst, long long ldd, int P, int C, float v, cudaStream_t s) {
   long long n = (long long)P * C;
-  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ldd, P, C, v);
+  RMEM_CUDA_CHECK(launch_pdl(fill_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dst, ldd, P, C, v));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
 int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int W, int engine, int n_engines,
                    cudaStream_t s) {
-  separate_label_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(label, label_is_f32, out, H * W, engine, n_engines);
+  RMEM_CUDA_CHECK(launch_pdl(separate_label_kernel, dim3(cdiv(H * W, 256)), dim3(256), 0, s, label, label_is_f32, out, H * W, engine, n_engines));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -764,8 +787,7 @@ int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
                  cudaStream_t s, const float* prefix) {
   RMEM_REQUIRE(C <= 256 && C % 32 == 0, "idbank: unsupported C=%d", C);
-  idbank_kernel<<<h * w, 256, 0, s>>>(label, H, W, use_ignore, w_packed, prefix, bias, ln_g, ln_b, out, ldo, out_f32,
-                                      w, C);
+  RMEM_CUDA_CHECK(launch_pdl(idbank_kernel, dim3(h * w), dim3(256), 0, s, label, H, W, use_ignore, w_packed, prefix, bias, ln_g, ln_b, out, ldo, out_f32, w, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -775,7 +797,7 @@ int mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo
   RMEM_REQUIRE(k >= 1 && k <= 4, "mask_head: 1..4 engines supported, got %d", k);
   LogitPtrs lp;
   for (int e = 0; e < 4; ++e) lp.p[e] = e < k ? logits4[e] : nullptr;
-  mask_head_kernel<<<cdiv(Ho * Wo, 128), 128, 0, s>>>(lp, k, h4, w4, Ho, Wo, out_logits, out_label);
+  RMEM_CUDA_CHECK(launch_pdl(mask_head_kernel, dim3(cdiv(Ho * Wo, 128)), dim3(128), 0, s, lp, k, h4, w4, Ho, Wo, out_logits, out_label));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -783,7 +805,7 @@ int mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo
 int evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel,
                     cudaStream_t s) {
   RMEM_REQUIRE(T >= 1 && T <= 16, "evict_relevance: T=%d out of range", T);
-  evict_rel_kernel<<<1, 1024, 0, s>>>(mass, T, logits4, h4, w4, h, w, rel);
+  RMEM_CUDA_CHECK(launch_pdl(evict_rel_kernel, dim3(1), dim3(1024), 0, s, mass, T, logits4, h4, w4, h, w, rel));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -792,7 +814,7 @@ int add_t16(const t16* a, long long lda, const t16* b, long long ldb, t16* y, lo
             cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0, "add_t16: alignment");
   long long n = (long long)P * (C / 8);
-  add_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, lda, b, ldb, y, ldy, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(add_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a, lda, b, ldb, y, ldy, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -800,21 +822,21 @@ int add_t16(const t16* a, long long lda, const t16* b, long long ldb, t16* y, lo
 int add_layernorm_t16(const t16* a, long long lda, const t16* b, long long ldb, const float* gamma, const float* beta,
                       t16* y, long long ldy, int P, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "add_layernorm: unsupported C=%d", C);
-  add_layernorm_kernel<<<cdiv(P, 8), 256, 0, s>>>(a, lda, b, ldb, gamma, beta, y, ldy, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(add_layernorm_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, a, lda, b, ldb, gamma, beta, y, ldy, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
 int accum_t16_into_f32(const t16* x, long long ldx, float* y, long long ldy, int P, int C, cudaStream_t s) {
   long long n = (long long)P * C;
-  accum_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, y, ldy, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(accum_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, ldx, y, ldy, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
 int cvt_f32_t16(const float* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s) {
   long long n = (long long)P * C;
-  cvt_f32_t16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, y, ldy, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(cvt_f32_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, ldx, y, ldy, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -822,13 +844,13 @@ int cvt_f32_t16(const float* x, long long ldx, t16* y, long long ldy, int P, int
 int sine_pos_emb(float* out, int h, int w, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 4 == 0 && h > 1 && w > 1, "sine_pos_emb: unsupported geometry");
   long long n = (long long)h * w * C;
-  sine_pe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, h, w, C);
+  RMEM_CUDA_CHECK(launch_pdl(sine_pe_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, h, w, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
 int mean_heads(const float* in, float* out, int H, long long n, cudaStream_t s) {
-  mean_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, H, n);
+  RMEM_CUDA_CHECK(launch_pdl(mean_heads_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, in, out, H, n));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -838,7 +860,7 @@ int qprep_heads(const t16* q, long long ldq, const float* pe_cur, const float* p
   RMEM_REQUIRE(T >= 1 && T <= 16 && H >= 1 && H <= 16, "qprep_heads: T=%d H=%d", T, H);
   PeSlots ps;
   for (int t = 0; t < 16; ++t) ps.s[t] = (t < T && pe_slot) ? pe_slot[t] : 0;
-  qprep_heads_kernel<<<cdiv(P, 8), 256, 0, s>>>(q, ldq, pe_cur, pe_mem, ps, T, scale, qt, qbias, P, H);
+  RMEM_CUDA_CHECK(launch_pdl(qprep_heads_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, q, ldq, pe_cur, pe_mem, ps, T, scale, qt, qbias, P, H));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -863,7 +885,7 @@ int qprep(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem,
   RMEM_REQUIRE(T >= 0 && T <= 16, "qprep: T=%d", T);
   PeSlots ps;
   for (int t = 0; t < 16; ++t) ps.s[t] = (t < T && pe_slot) ? pe_slot[t] : 0;
-  qprep_kernel<<<cdiv(P, 8), 256, 0, s>>>(q, ldq, pe_cur, pe_mem, ps, T, scale, qt, qbias, P, C);
+  RMEM_CUDA_CHECK(launch_pdl(qprep_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, q, ldq, pe_cur, pe_mem, ps, T, scale, qt, qbias, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

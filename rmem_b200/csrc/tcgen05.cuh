@@ -33,11 +33,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Programmatic dependent launch (sm_90+): `wait` blocks until the preceding kernel in the stream has completed and its
-// memory is visible; `launch_dependents` lets the following kernel (if launched with the PDL attribute) start early.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
