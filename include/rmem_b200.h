@@ -71,6 +71,9 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
 
 /* Debug aid: per-event clock64 trace of CTA 0 of the RMEM_ATTN_TC2 kernel into dev_buf ([tiles][16] int64); NULL disables. */
 int rmem_debug_attn_trace(void* dev_buf);
+/* Measurement aid: cudaEvent_t handles recorded immediately before / after the RMEM_ATTN_TC2 main kernel launch inside
+ * rmem_long_attn_fwd (NULL, NULL clears).  Thread-local. */
+int rmem_debug_attn_events(void* ev0, void* ev1);
 /* Same for the tcgen05 GEMM: first 64 CTAs of every launch, [cta][8] int64. */
 int rmem_debug_gemm_trace(void* dev_buf);
 

@@ -60,6 +60,8 @@ size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv);
 int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 // Debug: clock64 event trace of CTA 0 ([tile][16] long long, see attn_tc2.cu); nullptr disables.
 int long_attn_tc2_set_trace(long long* dev_buf);
+// Measurement aid: record these CUDA events around the main kernel launch only (null clears).  Thread-local.
+void long_attn_tc2_set_events(void* ev0, void* ev1);
 
 // Windowed short-term attention (LocalGatedPropagation core, attention.py:289-353), 15x15 window:
 //   s[i,d] = scale*<q_i, k_{i+d}> + rel[i,d] ; p = softmax_d ; out_i = (sum_d p[i,d] v_{i+d}) * gate_i

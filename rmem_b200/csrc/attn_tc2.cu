@@ -610,6 +610,13 @@ size_t part_bytes(int nCTA, int T, size_t* off_ml, size_t* off_pieces) {
 
 }  // namespace
 
+// Optional CUDA events recorded right before / after the main kernel (bench.py times the dominant kernel alone with them).
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+void long_attn_tc2_set_events(void* ev0, void* ev1) {
+  g_ev0 = reinterpret_cast<cudaEvent_t>(ev0);
+  g_ev1 = reinterpret_cast<cudaEvent_t>(ev1);
+}
+
 int long_attn_tc2_set_trace(long long* dev_buf) {
   RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)));
   return RMEM_OK;
@@ -674,7 +681,9 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(long_attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_done = true;
   }
+  if (g_ev0) RMEM_CUDA_CHECK(cudaEventRecord(g_ev0, s));
   RMEM_CUDA_CHECK(launch_pdl(long_attn_tc2_kernel, dim3(p.nCTA), dim3(kThreads), SMEM_TOTAL, s, *mq, *mk, *mv, p));
+  if (g_ev1) RMEM_CUDA_CHECK(cudaEventRecord(g_ev1, s));
   RMEM_LAUNCH_CHECK();
   RMEM_CUDA_CHECK(launch_pdl(combine2_kernel, dim3(a.HW), dim3(256), 0, s, p, a.gate, a.ldg, a.out, a.ldo, a.mass));
   RMEM_LAUNCH_CHECK();
