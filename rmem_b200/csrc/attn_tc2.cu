@@ -16,13 +16,16 @@
 //     the row it has already read) and is the TMEM A operand of the P.V MMA: no shared-memory round trip;
 //   * stream-K static schedule: the (query tile, Dv chunk, KV tile) space is cut into one contiguous range per SM, each
 //     CTA flushes at most two segments as normalised fp16 rows + fp32 (m, l); per-frame (m, l) pieces give the mass;
-//   * K and V^T tiles travel in separate TMA rings (K is needed three tiles earlier than V), Q is double-buffered for
-//     the two segments.
+//   * shared-memory bandwidth (MMA operand reads + TMA fills, 128 B/cycle) turned out to be the binding resource, so the
+//     query tile is kept in TMEM as the A operand of S (tcgen05.mma with A in TMEM): S reads only K from shared memory;
+//   * K and V^T tiles travel in separate TMA rings (6 x 16 KB, 4 x 32 KB; K is needed earlier than V).
 //
 //   block = 384 threads: warps 0-3 softmax group 0 (even tiles), 4-7 group 1 (odd tiles), 8 K/Q producer,
 //                        9 V producer, 10 S issuer + TMEM owner, 11 P.V issuer
-//   TMEM (512 cols): O[256] | 4 x S/P[64]
-//   smem: Q 2 x 32 KB | K 4 x 16 KB | V^T 3 x 32 KB | row-max hand-over | barriers
+//   TMEM (512 cols): O[256] | 3 x S/P[64] | Q[64]
+//   smem: K 6 x 16 KB | V^T 4 x 32 KB | row-max hand-over | barriers
+#include <cstdlib>
+
 #include "attn.cuh"
 #include "tcgen05.cuh"
 
@@ -36,18 +39,16 @@ constexpr int BM = 128;        // query rows per CTA
 constexpr int BN = 64;         // keys per KV tile
 constexpr int DK = 128;
 constexpr int DVC = 256;       // Dv columns per unit
-constexpr int KS = 4;          // K ring depth
-constexpr int VS = 3;          // V ring depth
-constexpr int NSB = 4;         // score buffers in TMEM
+constexpr int KS = 6;          // K ring depth
+constexpr int VS = 4;          // V ring depth
+constexpr int NSB = 3;         // score buffers in TMEM; P (packed fp16) aliases the first 32 columns of its S buffer
 constexpr int kSoftmaxWarps = 8;
 constexpr int kWarpK = 8, kWarpV = 9, kWarpMmaS = 10, kWarpMmaPV = 11;
 constexpr int kThreads = 12 * 32;
 
-constexpr int SMEM_Q = BM * DK * 2;            // 32 KB (two 64-col swizzle atoms)
 constexpr int SMEM_K = BN * DK * 2;            // 16 KB
 constexpr int SMEM_V = DVC * BN * 2;           // 32 KB
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + 2 * SMEM_Q;
+constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + KS * SMEM_K;
 constexpr int OFF_MSH = OFF_V + VS * SMEM_V;              // float [128]        row-max hand-over
 constexpr int OFF_LX = OFF_MSH + BM * 4;                  // float [2][128][2]  (m, l) exchange at segment end
@@ -58,7 +59,8 @@ static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_O = 0;
-constexpr int TMEM_S = 256;    // 4 x 64; P (packed fp16 pairs) aliases the first 32 columns of its buffer
+constexpr int TMEM_S = 256;    // 3 x 64 fp32 score columns; P(j) overwrites the first 32 of S(j) = A operand of O += P.V
+constexpr int TMEM_Q = 448;    // 64 columns: the 128 x 128 fp16 query tile as packed pairs = TMEM A operand of S = Q.K^T
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 12.0f;     // log2 units: P <= 2^12 (fp16 max 2^16) before a lazy rescale is forced
@@ -68,6 +70,7 @@ struct Tc2Params {
   long long L;                 // n_units * TPU
   int slot[kMaxBankFrames];
   float scale_log2;            // scale * log2(e)
+  const t16* q;                // [HW, 128] query (cur PE already added), row-major
   const float* qbias;          // [HW, T] or null (already multiplied by scale)
   t16* part_o;                 // [nCTA][2][BM][DVC]     normalised partial O
   float* part_ml;              // [nCTA][2][BM][2]       (m in log2 units, l)
@@ -117,6 +120,7 @@ __device__ __forceinline__ uint32_t pack2_fast(float lo, float hi) {
 
 // Optional event trace of CTA 0 (clock64 per pipeline event, 16 slots per tile); null in production.
 __device__ long long* g_trace = nullptr;
+__device__ int g_trace_cta = 0;
 #define TRACE(j, k)                                                                  \
   do {                                                                               \
     if (trace && lane == 0) trace[(long long)(j) * 16 + (k)] = clock64();            \
@@ -130,16 +134,16 @@ __device__ __forceinline__ void cta_range(const Tc2Params& p, int cta, long long
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                     const __grid_constant__ CUtensorMap map_v, const Tc2Params p) {
+long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                     const Tc2Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();       // 128B-swizzled TMA / UMMA tiles need 1024B alignment
   float* m_sh = reinterpret_cast<float*>(smem + OFF_MSH);
   float* lx = reinterpret_cast<float*>(smem + OFF_LX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars;                      // [2]
-  uint64_t* k_full = q_full + 2;                // [KS]
+  uint64_t* q_ready = bars;                     // Q tile stored to TMEM (one phase per segment that (re)loads it)
+  uint64_t* k_full = q_ready + 1;               // [KS]
   uint64_t* k_empty = k_full + KS;              // [KS]
   uint64_t* v_full = k_empty + KS;              // [VS]
   uint64_t* v_empty = v_full + VS;              // [VS]
@@ -148,10 +152,10 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* sp_free = p_full + NSB;             // [NSB]  P.V(j) complete: score buffer (and everything before) retired
   uint64_t* o_drained = sp_free + NSB;          // segment epilogue has read O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_drained + 1);
-  static_assert((2 + 2 * KS + 2 * VS + 3 * NSB + 1) * 8 + 4 <= 256, "barrier area");
+  static_assert((1 + 2 * KS + 2 * VS + 3 * NSB + 1) * 8 + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* const trace = blockIdx.x == 0 ? g_trace : nullptr;
+  long long* const trace = (int)blockIdx.x == g_trace_cta ? g_trace : nullptr;
 
   // ---- this CTA's work: a contiguous range of (unit, tile) steps -> at most two segments ----
   long long lo, hi;
@@ -173,9 +177,11 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
   const int n0 = nseg > 0 ? seg[0].hi - seg[0].lo : 0;
   const int ntot = n0 + (nseg > 1 ? seg[1].hi - seg[1].lo : 0);
+  // units are ordered (query tile major, Dv chunk minor): the Q tile changes only when unit / n_dv changes
+  const bool q_reload1 = nseg > 1 && (seg[1].unit / p.n_dv != seg[0].unit / p.n_dv);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
+    mbar_init(q_ready, 4);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < NSB; ++i) {
@@ -195,14 +201,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // ================================ Q + K producer ================================
     if (ntot > 0) {
       if (elect_one()) {
-        tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
-        for (int s = 0; s < nseg; ++s) {
-          const int qt = seg[s].unit / p.n_dv;
-          mbar_expect_tx(&q_full[s], SMEM_Q);
-          tma_load_2d(smem + OFF_Q + s * SMEM_Q, &map_q, &q_full[s], 0, qt * BM);
-          tma_load_2d(smem + OFF_Q + s * SMEM_Q + BM * 128, &map_q, &q_full[s], 64, qt * BM);
-        }
       }
       __syncwarp();
       int i = 0;
@@ -255,23 +254,21 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const uint32_t smem_base = smem_u32(smem);
       for (int i = 0; i < ntot; ++i) {
         const int st = i % KS, b = i % NSB;
-        const int sq = i >= n0 ? 1 : 0;
-        if (i == 0) mbar_wait(&q_full[0], 0, nullptr, 3);
-        if (i == n0) mbar_wait(&q_full[1], 0, nullptr, 4);
+        if (i == 0) mbar_wait(q_ready, 0, nullptr, 3);
+        if (i == n0 && q_reload1) mbar_wait(q_ready, 1, nullptr, 4);
         mbar_wait(&k_full[st], (i / KS) & 1, nullptr, 5);
-        if (i >= NSB) mbar_wait(&sp_free[b], ((i - NSB) / NSB) & 1, nullptr, 6);    // P.V(i-4) retired its buffer
+        if (i >= NSB) mbar_wait(&sp_free[b], ((i - NSB) / NSB) & 1, nullptr, 6);    // P.V(i-3) retired its buffer
         fence_after();
         TRACE(i, 2);
         if (elect_one()) {
-          const uint64_t dq = make_desc_sw128(smem_base + OFF_Q + sq * SMEM_Q);
           const uint64_t dk = make_desc_sw128(smem_base + OFF_K + st * SMEM_K);
           const uint32_t d = tmem + TMEM_S + b * BN;
 #pragma unroll
           for (int kk = 0; kk < DK / 16; ++kk) {
-            // 16 k-elements = 32 B inside the 128 B swizzle atom; the second 64-wide atom starts one tile-half later
-            const uint64_t oa = (uint64_t)(((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4);
+            // A = Q from TMEM (16 k-elements = 8 packed columns); B: 32 B inside the 128 B swizzle atom, the second
+            // 64-wide atom of the K tile starts one tile-half later
             const uint64_t ob = (uint64_t)(((kk >> 2) * (BN * 128) + (kk & 3) * 32) >> 4);
-            umma_ss(d, dq + oa, dk + ob, idesc_s, kk > 0);
+            umma_ts(d, tmem + TMEM_Q + kk * 8, dk + ob, idesc_s, kk > 0);
           }
           commit(&k_empty[st]);
           commit(&s_full[b]);
@@ -316,6 +313,29 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int id_out = grp == 0 ? 1 + quad : 5 + quad;
     const int id_ex = 9 + quad;
     int j = 0;
+    // The 128 x 128 fp16 query tile lives in TMEM as the A operand of S = Q.K^T (one row per lane, packed pairs): the
+    // score MMAs then read only K from shared memory, whose bandwidth (operand reads + TMA fills) bounds this kernel.
+    auto store_q = [&](int qt) {
+      const int qr = qt * BM + row;
+      uint32_t w[64];
+      if (qr < p.HW) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + (long long)qr * DK);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const uint4 u = src[c];
+          w[c * 4] = u.x; w[c * 4 + 1] = u.y; w[c * 4 + 2] = u.z; w[c * 4 + 3] = u.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) w[c] = 0u;
+      }
+      tmem_st32u(lane_addr + TMEM_Q, w);
+      tmem_st32u(lane_addr + TMEM_Q + 32, w + 32);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+    };
+    if (grp == 0) store_q(seg[0].unit / p.n_dv);
 
     for (int s = 0; s < nseg; ++s) {
       const int unit = seg[s].unit;
@@ -362,6 +382,8 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
           for (int c = 0; c < 32; ++c) { sc[c] = __uint_as_float(r0[c]); sc[32 + c] = __uint_as_float(r1[c]); }
         }
+        // S(n0-1) is complete, hence every score MMA of the first segment: the next segment's query tile may go in
+        if (q_reload1 && j == n0 - 1) store_q(seg[1].unit / p.n_dv);
         if (jt == p.tpf - 1) {                               // ragged last tile of the frame
           const int key0 = jt * BN;
 #pragma unroll
@@ -431,8 +453,8 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const float lsum = (ls0 + ls1) + (ls2 + ls3);
         l_tot += lsum;
         l_piece += lsum;
-        // P(j) over the first 32 columns of S(j): this thread's row was fully read above
         TRACE_S(8);
+        // P(j) over the first 32 columns of S(j): this thread's row was fully read above
         tmem_st32u(lane_addr + TMEM_S + b * BN, pk);
         fence_before();
         __syncwarp();
@@ -442,6 +464,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       flush_piece(cur_t);
 
       // ---- segment epilogue: normalised fp16 partial O + (m, l) ----
+      if (quad == 0 && grp == 0 && trace && lane == 0) trace[(long long)(j - 1) * 16 + 10] = clock64();
       lx[(grp * BM + row) * 2 + 0] = m_ref;
       lx[(grp * BM + row) * 2 + 1] = l_tot;
       named_bar_sync(id_ex, 64);
@@ -476,6 +499,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       fence_before();
       __syncwarp();
+      if (quad == 0 && grp == 0 && trace && lane == 0) trace[(long long)(j - 1) * 16 + 11] = clock64();
       if (lane == 0 && s + 1 < nseg) mbar_arrive(o_drained);
     }
   }
@@ -618,6 +642,12 @@ void long_attn_tc2_set_events(void* ev0, void* ev1) {
 }
 
 int long_attn_tc2_set_trace(long long* dev_buf) {
+  static int cta = -1;
+  if (cta < 0) {
+    const char* e = getenv("RMEM_TRACE_CTA");
+    cta = e ? atoi(e) : 0;
+    RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_cta, &cta, sizeof(cta)));
+  }
   RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)));
   return RMEM_OK;
 }
@@ -657,13 +687,9 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   p.part_ml = reinterpret_cast<float*>(ws + off_ml);
   p.pieces = a.mass ? reinterpret_cast<float*>(ws + off_pieces) : nullptr;
 
-  const CUtensorMap *mq, *mk, *mv;
-  {
-    uint64_t dims[2] = {(uint64_t)DK, (uint64_t)a.HW};
-    uint64_t str[1] = {(uint64_t)DK * 2};
-    uint32_t box[2] = {64, (uint32_t)BM};
-    RMEM_TRY(tma_encode_cached(&mq, a.qt, 2, dims, str, box, nullptr));
-  }
+  RMEM_REQUIRE((reinterpret_cast<uintptr_t>(a.qt) & 15) == 0, "long_attn_tc2: q alignment");
+  p.q = a.qt;
+  const CUtensorMap *mk, *mv;
   {
     uint64_t dims[2] = {(uint64_t)DK, (uint64_t)a.nslots * a.HWp};
     uint64_t str[1] = {(uint64_t)DK * 2};
@@ -682,7 +708,7 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
     attr_done = true;
   }
   if (g_ev0) RMEM_CUDA_CHECK(cudaEventRecord(g_ev0, s));
-  RMEM_CUDA_CHECK(launch_pdl(long_attn_tc2_kernel, dim3(p.nCTA), dim3(kThreads), SMEM_TOTAL, s, *mq, *mk, *mv, p));
+  RMEM_CUDA_CHECK(launch_pdl(long_attn_tc2_kernel, dim3(p.nCTA), dim3(kThreads), SMEM_TOTAL, s, *mk, *mv, p));
   if (g_ev1) RMEM_CUDA_CHECK(cudaEventRecord(g_ev1, s));
   RMEM_LAUNCH_CHECK();
   RMEM_CUDA_CHECK(launch_pdl(combine2_kernel, dim3(a.HW), dim3(256), 0, s, p, a.gate, a.ldg, a.out, a.ldo, a.mass));

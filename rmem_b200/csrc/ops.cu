@@ -192,53 +192,56 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// 8 channels x DW_PX consecutive pixels of one row per thread: the 5 x (DW_PX + 4) input window and the 25 weight
-// vectors are loaded once and shared by the DW_PX outputs (4.5x fewer loads than one pixel per thread).
-constexpr int DW_PX = 6;
+// 5x5 depthwise convolution, NHWC.  One thread owns a channel pair and slides a 5x5 register window along a strip of
+// DW_SL output pixels of one row: each new output costs 5 loads (the entering column) instead of 25, the 25 weight
+// pairs live in registers (fetched before the PDL wait: they are not produced by the preceding kernel), and a warp
+// covers 64 consecutive channels, so every access is one 128-byte line.  fp32 accumulation in (ky, kx) order.
+constexpr int DW_SL = 9;
 __global__ void __launch_bounds__(128) dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w,
                                                       t16* __restrict__ y, int h, int wd, int C) {
+  const int cp = C / 2;
+  const int xs = (wd + DW_SL - 1) / DW_SL;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < (long long)h * xs * cp;
+  const int c2 = active ? (int)(i % cp) : 0;
+  float2 wt[25];
+#pragma unroll
+  for (int k = 0; k < 25; ++k) wt[k] = *reinterpret_cast<const float2*>(w + (size_t)k * C + c2 * 2);
   pdl_prologue();
-  const int cv = C / 8;
-  const int xt = (wd + DW_PX - 1) / DW_PX;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)h * xt * cv) return;
-  const int c8 = (int)(i % cv);
-  const int px0 = (int)((i / cv) % xt) * DW_PX, py = (int)(i / ((long long)cv * xt));
-  float acc[DW_PX][8];
+  if (!active) return;
+  const int x_begin = (int)((i / cp) % xs) * DW_SL, py = (int)(i / ((long long)cp * xs));
+  const uint32_t* xin = reinterpret_cast<const uint32_t*>(x) + c2;
+  uint32_t* yout = reinterpret_cast<uint32_t*>(y) + c2;
+  auto load_col = [&](int ix, uint32_t (&col)[5]) {
 #pragma unroll
-  for (int p = 0; p < DW_PX; ++p)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[p][k] = 0.f;
-#pragma unroll 1
-  for (int ky = 0; ky < 5; ++ky) {
-    const int iy = py + ky - 2;
-    if ((unsigned)iy >= (unsigned)h) continue;
-    float col[DW_PX + 4][8];
-#pragma unroll
-    for (int j = 0; j < DW_PX + 4; ++j) {
-      const int ix = px0 + j - 2;
-      if ((unsigned)ix < (unsigned)wd) {
-        load8(x + ((size_t)iy * wd + ix) * C + c8 * 8, col[j]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) col[j][k] = 0.f;
-      }
+    for (int ky = 0; ky < 5; ++ky) {
+      const int iy = py + ky - 2;
+      col[ky] = ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)wd) ? xin[((size_t)iy * wd + ix) * cp] : 0u;
     }
+  };
+  uint32_t win[5][5];                                     // [kx][ky]: columns x-2 .. x+2 of the current output
 #pragma unroll
-    for (int kx = 0; kx < 5; ++kx) {
-      const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * 5 + kx) * C + c8 * 8);
-      const float4 w0 = wp[0], w1 = wp[1];
+  for (int kx = 1; kx < 5; ++kx) load_col(x_begin + kx - 3, win[kx]);
 #pragma unroll
-      for (int p = 0; p < DW_PX; ++p) {
-        const float* v = col[p + kx];
-        acc[p][0] += v[0] * w0.x; acc[p][1] += v[1] * w0.y; acc[p][2] += v[2] * w0.z; acc[p][3] += v[3] * w0.w;
-        acc[p][4] += v[4] * w1.x; acc[p][5] += v[5] * w1.y; acc[p][6] += v[6] * w1.z; acc[p][7] += v[7] * w1.w;
+  for (int px = 0; px < DW_SL; ++px) {
+    const int ox = x_begin + px;
+    if (ox >= wd) break;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) win[kx][ky] = win[kx + 1][ky];
+    load_col(ox + 2, win[4]);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const float2 v = unpack2(win[kx][ky]);
+        a0 = fmaf(v.x, wt[ky * 5 + kx].x, a0);
+        a1 = fmaf(v.y, wt[ky * 5 + kx].y, a1);
       }
-    }
+    yout[((size_t)py * wd + ox) * cp] = pack2(a0, a1);
   }
-#pragma unroll
-  for (int p = 0; p < DW_PX; ++p)
-    if (px0 + p < wd) store8(y + ((size_t)py * wd + px0 + p) * C + c8 * 8, acc[p]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -411,8 +414,20 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
       acc = P[((size_t)ky1 * 18 + kx1) * C] - P[((size_t)ky0 * 18 + kx1) * C] - P[((size_t)ky1 * 18 + kx0) * C] +
             P[((size_t)ky0 * 18 + kx0) * C];
     } else {
-      for (int t = 0; t < 289; ++t) {
-        int k = ch[t];
+      // predicated loads, eight taps in flight (the tap loop is L2-latency bound otherwise); summed in tap order
+      int t = 0;
+      for (; t + 8 <= 289; t += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = ch[t + u];
+          v[u] = (k >= 0 && k < 12) ? wp[((size_t)(t + u) * 12 + k) * C + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      for (; t < 289; ++t) {
+        const int k = ch[t];
         if (k >= 0 && k < 12) acc += wp[((size_t)t * 12 + k) * C + c];
       }
     }
@@ -732,7 +747,7 @@ int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y,
 
 int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "dwconv: C %% 8");
-  long long n = (long long)h * ((wd + DW_PX - 1) / DW_PX) * (C / 8);
+  long long n = (long long)h * ((wd + DW_SL - 1) / DW_SL) * (C / 2);
   RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, s, x, w, y, h, wd, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;

@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 RMEM_ATTN_IMPL=2 timeout 600 python tests/tc_attn_check.py > gpurun_out/attn2_check.log 2>&1; echo "rc=$?" >> gpurun_out/attn2_check.log
-cut -c1-160 gpurun_out/attn2_check.log | tail -9
-timeout 300 python bench.py --steps 60 --warmup 10 --no-cpu-baseline --attn tc2 > gpurun_out/bench_tc2.json 2> gpurun_out/bench_tc2.err; echo "bench rc=$?"
+cut -c1-170 gpurun_out/attn2_check.log | tail -9
+python tools/trace_attn.py > gpurun_out/attn_trace.txt 2>&1; sed -n 56,62p gpurun_out/attn_trace.txt
+timeout 300 python bench.py --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/bench_tc2.json 2> gpurun_out/bench_tc2.err; echo "bench rc=$?"
 python -c "
-import json;d=json.load(open('gpurun_out/bench_tc2.json'));print(d['value'],d['e2e']['value'],d['roofline']['ms_per_launch'],d['roofline']['frac'])"; tail -5 gpurun_out/bench_tc2.err
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-    --log-file gpurun_out/launches.csv python tools/profile_frame.py --frames 5 > gpurun_out/launches.log 2>&1
-tail -1 gpurun_out/launches.log
+import json;d=json.load(open('gpurun_out/bench_tc2.json'));r=d['roofline'];print('fps',d['value'],'e2e',d['e2e']['value'],'kernel ms',r['ms_per_launch'],r['frac'],'op',r['op_ms_per_launch'],r['op_frac'])"; tail -5 gpurun_out/bench_tc2.err

@@ -21,9 +21,9 @@ torch.cuda.synchronize()
 _capi.check(lib.rmem_debug_attn_trace(C.c_void_p(0)))
 t = tr.cpu().view(256, 16)
 t0 = int(t[t > 0].min())
-names = ["pfull_seen", "pv_issued", "s_waits_done", "s_issued", "sm_start", "sfull_seen", "max_done", "handoff_done", "exp_done", "p_arrived"]
+names = ["pfull_seen", "pv_issued", "s_waits_done", "s_issued", "sm_start", "sfull_seen", "max_done", "handoff_done", "exp_done", "p_arrived", "epi_start", "epi_end"]
 print("tile " + " ".join(n.rjust(12) for n in names))
 for j in range(90):
     if int(t[j].max()) == 0:
         break
-    print(f"{j:4d} " + " ".join((str(int(x) - t0) if int(x) > 0 else "-").rjust(12) for x in t[j, :10]))
+    print(f"{j:4d} " + " ".join((str(int(x) - t0) if int(x) > 0 else "-").rjust(12) for x in t[j, :12]))
