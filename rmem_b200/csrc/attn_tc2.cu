@@ -88,6 +88,20 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5 -- below the fp16
+// rounding of P).  The MUFU unit evaluates 16 ex2 per cycle and SM: 8192 per 64-key tile = 512 cycles, more than the
+// tile's MMA time; a quarter of the exponentials can bypass it (kPolyExp).
+constexpr bool kPolyExp = false;   // measured: no gain (the tile period is set by the MMA pipe, not by MUFU)
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                         // 1.5 * 2^23: nearest integer lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);                   // [-0.5, 0.5]
+  float r = fmaf(f, 0.0551716648f, 0.2426111251f);
+  r = fmaf(r, f, 0.6932609677f);
+  r = fmaf(r, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
+}
+
 __device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -156,6 +170,14 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const trace = (int)blockIdx.x == g_trace_cta ? g_trace : nullptr;
+  // per-CTA wall times (rows 100.. of the trace buffer): globaltimer start/end, tiles, segments, SM id
+  long long* const cta_times = (g_trace && blockIdx.x < 148) ? g_trace + (100 + blockIdx.x) * 16 : nullptr;
+  if (cta_times && threadIdx.x == 0) {
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cta_times[0] = (long long)gt; cta_times[4] = smid; cta_times[5] = clock64();
+  }
 
   // ---- this CTA's work: a contiguous range of (unit, tile) steps -> at most two segments ----
   long long lo, hi;
@@ -315,7 +337,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
     int j = 0;
     // The 128 x 128 fp16 query tile lives in TMEM as the A operand of S = Q.K^T (one row per lane, packed pairs): the
     // score MMAs then read only K from shared memory, whose bandwidth (operand reads + TMA fills) bounds this kernel.
-    auto store_q = [&](int qt) {
+    auto store_q = [&](int qt, uint64_t* after, uint32_t parity) {
       const int qr = qt * BM + row;
       uint32_t w[64];
       if (qr < p.HW) {
@@ -329,13 +351,17 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 #pragma unroll
         for (int c = 0; c < 64; ++c) w[c] = 0u;
       }
+      if (after) {                                          // the rows are in registers; now wait until Q may be replaced
+        mbar_wait(after, parity, nullptr, 14);
+        fence_after();
+      }
       tmem_st32u(lane_addr + TMEM_Q, w);
       tmem_st32u(lane_addr + TMEM_Q + 32, w + 32);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(q_ready);
     };
-    if (grp == 0) store_q(seg[0].unit / p.n_dv);
+    if (grp == 0) store_q(seg[0].unit / p.n_dv, nullptr, 0);
 
     for (int s = 0; s < nseg; ++s) {
       const int unit = seg[s].unit;
@@ -365,7 +391,13 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
           l_piece = 0.f;
           bias2 = (p.qbias && row_ok) ? p.qbias[(long long)qi * p.T + t] * LOG2E : 0.f;
         }
-        if ((j & 1) != grp) continue;
+        if ((j & 1) != grp) {
+          // The other group owns the first segment's last tile; this one is idle until the epilogue, so it brings in
+          // the next segment's query tile: rows to registers, wait for S(n0-1) (= every score MMA of the segment has
+          // read Q), then into TMEM.  Off the critical path of the last tile.
+          if (q_reload1 && j == n0 - 1) store_q(seg[1].unit / p.n_dv, &s_full[j % NSB], (j / NSB) & 1);
+          continue;
+        }
         const int b = j % NSB;
         long long* const trace_s = quad == 0 ? trace : nullptr;
 #define TRACE_S(k) do { if (trace_s && lane == 0) trace_s[(long long)j * 16 + (k)] = clock64(); } while (0)
@@ -382,8 +414,6 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 #pragma unroll
           for (int c = 0; c < 32; ++c) { sc[c] = __uint_as_float(r0[c]); sc[32 + c] = __uint_as_float(r1[c]); }
         }
-        // S(n0-1) is complete, hence every score MMA of the first segment: the next segment's query tile may go in
-        if (q_reload1 && j == n0 - 1) store_q(seg[1].unit / p.n_dv);
         if (jt == p.tpf - 1) {                               // ragged last tile of the frame
           const int key0 = jt * BN;
 #pragma unroll
@@ -445,7 +475,8 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
           const float e0 = exp2f(fmaf(sc[c], p.scale_log2, c0));
           const float e1 = exp2f(fmaf(sc[c + 1], p.scale_log2, c0));
           const float e2 = exp2f(fmaf(sc[c + 2], p.scale_log2, c0));
-          const float e3 = exp2f(fmaf(sc[c + 3], p.scale_log2, c0));
+          const float a3 = fmaf(sc[c + 3], p.scale_log2, c0);
+          const float e3 = kPolyExp ? exp2_poly(a3) : exp2f(a3);
           ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
           pk[c >> 1] = pack2_fast(e0, e1);
           pk[(c >> 1) + 1] = pack2_fast(e2, e3);
@@ -468,6 +499,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       lx[(grp * BM + row) * 2 + 0] = m_ref;
       lx[(grp * BM + row) * 2 + 1] = l_tot;
       named_bar_sync(id_ex, 64);
+      if (quad == 0 && grp == 0 && trace && lane == 0) trace[(long long)(j - 1) * 16 + 12] = clock64();
       const float m_o = lx[((grp ^ 1) * BM + row) * 2 + 0], l_o = lx[((grp ^ 1) * BM + row) * 2 + 1];
       const float M = fmaxf(m_ref, m_o);                    // == the maximum O is relative to (m is monotone)
       const float l_row = l_tot * exp2f(m_ref - M) + l_o * exp2f(m_o - M);
@@ -475,7 +507,10 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       const int last = j - 1;
       mbar_wait(&sp_free[last % NSB], (last / NSB) & 1, nullptr, 12);
       fence_after();
-      t16* po = p.part_o + ((long long)(blockIdx.x * 2 + s) * BM + row) * DVC + grp * (DVC / 2);
+      if (quad == 0 && grp == 0 && trace && lane == 0) trace[(long long)(j - 1) * 16 + 13] = clock64();
+      // part_o: [slot][16-column group][row][16] -- the 32 rows of a warp are contiguous per group, so every store
+      // instruction covers whole lines (row-major rows 512 B apart cost one line per lane and ~5000 cycles per segment)
+      t16* po = p.part_o + (((long long)(blockIdx.x * 2 + s) * (DVC / 16) + grp * (DVC / 32)) * BM + row) * 16;
 #pragma unroll 1
       for (int c = 0; c < DVC / 2; c += 32) {
         float o[32];
@@ -488,7 +523,7 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
             u.y = pack2(o[e + 2] * inv, o[e + 3] * inv);
             u.z = pack2(o[e + 4] * inv, o[e + 5] * inv);
             u.w = pack2(o[e + 6] * inv, o[e + 7] * inv);
-            *reinterpret_cast<uint4*>(po + c + e) = u;
+            *reinterpret_cast<uint4*>(po + (long long)((c + e) >> 4) * (BM * 16) + ((c + e) & 8)) = u;
           }
         }
       }
@@ -505,6 +540,11 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
   }
   fence_before();
   __syncthreads();
+  if (cta_times && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cta_times[1] = (long long)gt; cta_times[2] = ntot; cta_times[3] = nseg; cta_times[6] = clock64();
+  }
   if (warp == kWarpMmaS) {
     fence_after();
     tmem_dealloc<TMEM_COLS>(tmem);
@@ -513,21 +553,27 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
 
 // Merge the segments of every unit: out = (sum_s w_s O_s) * gate with w_s = l_s 2^(m_s - M) / L;
 // mass[i,t] = sum_{pieces of frame t} l_p 2^(m_p - M) / L  (from the Dv-chunk-0 units).
-// One block per query row; the (CTA, segment) list of the row's four units is resolved once per block.
+// Four query rows per block, 64 threads x 16 columns per row: part_o is stored as [slot][16-column group][row][16], so
+// a thread reads one full 32-byte sector per segment (and the attention epilogue's row-per-lane stores coalesce).
 constexpr int kMaxSegsPerUnit = 24;
+constexpr int kCombRows = 4;
+constexpr int kColGroups = DVC / 16;
+static_assert(BM % kCombRows == 0, "the rows of a combine block share a query tile");
 __global__ void __launch_bounds__(256) combine2_kernel(const Tc2Params p, const t16* __restrict__ gate, long long ldg,
                                                        t16* __restrict__ out, long long ldo,
                                                        float* __restrict__ mass) {
   pdl_prologue();
-  __shared__ int s_n[4];
-  __shared__ int s_slot[4][kMaxSegsPerUnit];        // (cta * 2 + seg)
-  __shared__ float s_w[4][kMaxSegsPerUnit];         // l_s 2^(m_s - M) / L
-  __shared__ float s_M0, s_L0;
-  __shared__ int s_alo[kMaxSegsPerUnit], s_ahi[kMaxSegsPerUnit];   // unit-0 segments: tile range inside the unit
-  const int i = blockIdx.x;
-  const int qt = i / BM, r = i - qt * BM;
-  if (threadIdx.x < p.n_dv) {
-    const int k = threadIdx.x;
+  __shared__ int s_n[kCombRows][4];
+  __shared__ int s_slot[kCombRows][4][kMaxSegsPerUnit];        // (cta * 2 + seg)
+  __shared__ float s_w[kCombRows][4][kMaxSegsPerUnit];         // l_s 2^(m_s - M) / L
+  __shared__ float s_M0[kCombRows], s_L0[kCombRows];
+  __shared__ int s_alo[kCombRows][kMaxSegsPerUnit], s_ahi[kCombRows][kMaxSegsPerUnit];   // unit-0 tile ranges
+  const int rr = threadIdx.x >> 6, tc = threadIdx.x & 63;
+  const int i = blockIdx.x * kCombRows + rr;
+  const bool live = i < p.HW;
+  const int qt = (blockIdx.x * kCombRows) / BM, r = i - qt * BM;
+  if (live && tc < p.n_dv) {
+    const int k = tc;
     const int unit = qt * p.n_dv + k;
     const long long u_lo = (long long)unit * p.TPU, u_hi = u_lo + p.TPU;
     int c = (int)(((u_lo + 1) * p.nCTA - 1) / p.L);
@@ -539,56 +585,73 @@ __global__ void __launch_bounds__(256) combine2_kernel(const Tc2Params p, const 
       if (lo >= u_hi) break;
       if (hi <= lo) continue;
       const int slot = c * 2 + (lo < u_lo ? 1 : 0);
-      s_slot[k][n] = slot;
+      s_slot[rr][k][n] = slot;
       if (k == 0) {
-        s_alo[n] = (int)((lo > u_lo ? lo : u_lo) - u_lo);
-        s_ahi[n] = (int)((hi < u_hi ? hi : u_hi) - u_lo);
+        s_alo[rr][n] = (int)((lo > u_lo ? lo : u_lo) - u_lo);
+        s_ahi[rr][n] = (int)((hi < u_hi ? hi : u_hi) - u_lo);
       }
       M = fmaxf(M, p.part_ml[((long long)slot * BM + r) * 2]);
       ++n;
     }
     float L = 0.f;
     for (int e = 0; e < n; ++e) {
-      const float* ml = p.part_ml + ((long long)s_slot[k][e] * BM + r) * 2;
+      const float* ml = p.part_ml + ((long long)s_slot[rr][k][e] * BM + r) * 2;
       const float w = exp2f(ml[0] - M) * ml[1];
-      s_w[k][e] = w;
+      s_w[rr][k][e] = w;
       L += w;
     }
     const float inv = 1.f / L;
-    for (int e = 0; e < n; ++e) s_w[k][e] *= inv;
-    s_n[k] = n;
-    if (k == 0) { s_M0 = M; s_L0 = L; }
+    for (int e = 0; e < n; ++e) s_w[rr][k][e] *= inv;
+    s_n[rr][k] = n;
+    if (k == 0) { s_M0[rr] = M; s_L0[rr] = L; }
   }
   __syncthreads();
-  const int col = threadIdx.x * 4;
-  if (col < p.Dv) {
-    const int k = col / DVC, cc = col - k * DVC;
-    const int n = s_n[k];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int col = tc * 16;
+  if (live && col < p.Dv) {
+    const int k = col / DVC, cg = (col - k * DVC) >> 4;
+    const int n = s_n[rr][k];
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
     for (int e = 0; e < n; ++e) {
-      const float w = s_w[k][e];
-      const uint2 u = *reinterpret_cast<const uint2*>(p.part_o + ((long long)s_slot[k][e] * BM + r) * DVC + cc);
-      const float2 a = unpack2(u.x), b = unpack2(u.y);
-      acc.x += w * a.x; acc.y += w * a.y; acc.z += w * b.x; acc.w += w * b.y;
+      const float w = s_w[rr][k][e];
+      const uint4* src = reinterpret_cast<const uint4*>(
+          p.part_o + (((long long)s_slot[rr][k][e] * kColGroups + cg) * BM + r) * 16);
+      const uint4 u0 = src[0], u1 = src[1];
+      const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 f = unpack2(uu[c]);
+        acc[c * 2] = fmaf(w, f.x, acc[c * 2]);
+        acc[c * 2 + 1] = fmaf(w, f.y, acc[c * 2 + 1]);
+      }
     }
     if (gate) {
-      const uint2 g = *reinterpret_cast<const uint2*>(gate + (long long)i * ldg + col);
-      const float2 g0 = unpack2(g.x), g1 = unpack2(g.y);
-      acc.x *= g0.x; acc.y *= g0.y; acc.z *= g1.x; acc.w *= g1.y;
+      const uint4* gp = reinterpret_cast<const uint4*>(gate + (long long)i * ldg + col);
+      const uint4 g0 = gp[0], g1 = gp[1];
+      const uint32_t gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 f = unpack2(gg[c]);
+        acc[c * 2] *= f.x;
+        acc[c * 2 + 1] *= f.y;
+      }
     }
-    uint2 o;
-    o.x = pack2(acc.x, acc.y);
-    o.y = pack2(acc.z, acc.w);
-    *reinterpret_cast<uint2*>(out + (long long)i * ldo + col) = o;
+    uint4 o0, o1;
+    o0.x = pack2(acc[0], acc[1]); o0.y = pack2(acc[2], acc[3]); o0.z = pack2(acc[4], acc[5]); o0.w = pack2(acc[6], acc[7]);
+    o1.x = pack2(acc[8], acc[9]); o1.y = pack2(acc[10], acc[11]); o1.z = pack2(acc[12], acc[13]); o1.w = pack2(acc[14], acc[15]);
+    uint4* op = reinterpret_cast<uint4*>(out + (long long)i * ldo + col);
+    op[0] = o0;
+    op[1] = o1;
   }
-  if (mass && threadIdx.x < p.T) {
-    const int t = threadIdx.x;
+  if (mass && live && tc < p.T) {
+    const int t = tc;
     const int f_lo = t * p.tpf, f_hi = f_lo + p.tpf;
-    const float M = s_M0, invL = 1.f / s_L0;
+    const float M = s_M0[rr], invL = 1.f / s_L0[rr];
     float a = 0.f;
-    for (int e = 0; e < s_n[0]; ++e) {
-      if (s_alo[e] < f_hi && f_lo < s_ahi[e]) {
-        const float* pc = p.pieces + ((((long long)s_slot[0][e] * p.T + t) * 2) * BM + r) * 2;
+    for (int e = 0; e < s_n[rr][0]; ++e) {
+      if (s_alo[rr][e] < f_hi && f_lo < s_ahi[rr][e]) {
+        const float* pc = p.pieces + ((((long long)s_slot[rr][0][e] * p.T + t) * 2) * BM + r) * 2;
         a += exp2f(pc[0] - M) * pc[1] + exp2f(pc[BM * 2] - M) * pc[BM * 2 + 1];
       }
     }
@@ -711,7 +774,7 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   RMEM_CUDA_CHECK(launch_pdl(long_attn_tc2_kernel, dim3(p.nCTA), dim3(kThreads), SMEM_TOTAL, s, *mk, *mv, p));
   if (g_ev1) RMEM_CUDA_CHECK(cudaEventRecord(g_ev1, s));
   RMEM_LAUNCH_CHECK();
-  RMEM_CUDA_CHECK(launch_pdl(combine2_kernel, dim3(a.HW), dim3(256), 0, s, p, a.gate, a.ldg, a.out, a.ldo, a.mass));
+  RMEM_CUDA_CHECK(launch_pdl(combine2_kernel, dim3(cdiv(a.HW, kCombRows)), dim3(256), 0, s, p, a.gate, a.ldg, a.out, a.ldo, a.mass));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
