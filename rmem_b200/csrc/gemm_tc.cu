@@ -11,8 +11,15 @@
 //   B tile: 2-D TMA box [64 k, BN rows] of the [N,K] weight.
 //   Epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / residual / activation / gate / split / accumulate -> global
 //   (each thread owns an output row: 64-128 contiguous bytes per store burst).
+//   Split-K: a GEMM with few output tiles and a long K (layer3's 3x3 convolutions: 56 tiles x 36 k-blocks) is bound by
+//   the ~40 B/clk one SM can pull from L2, not by the tensor pipe.  Such a launch runs as clusters of S = 2 | 4 CTAs
+//   along K: every CTA accumulates its k-range in its own TMEM, ranks 1.. push their fp32 partial tile into rank 0's
+//   shared memory (DSMEM stores, column-major so lanes are contiguous) and rank 0 reduces in rank order inside its
+//   normal epilogue -- no global workspace, no atomics, bit-reproducible.
 #include "gemm.cuh"
 #include "tcgen05.cuh"
+
+#include <cstdlib>
 
 namespace rmem {
 
@@ -28,6 +35,7 @@ constexpr int SMEM_A_STAGE = TBM * TBK * 2;   // 16 KB
 
 struct TcGemmParams {
   int M, N, nk, stages;
+  int splitk;                 // CTAs per cluster along K (1 = no split)
   int conv, taps_w, cin_blocks, pad, stride, BW, BH, tiles_x, Hout, Wout;
   float alpha;
   const float* bias;
@@ -58,8 +66,43 @@ struct TcSmem {
   static constexpr int kB = BN * TBK * 2;
   static constexpr int kStage = SMEM_A_STAGE + kB;
   // [1024B-aligned] stages x (A | B) tiles, then the barriers
-  static constexpr int total(int stages) { return stages * kStage + 256 + 1024; }   // + barriers + alignment slack
+  static constexpr int kRecv = TBM * BN * 4;     // one fp32 partial tile (split-K)
+  // + barriers + alignment slack; split-K adds (S-1) receive tiles behind the barrier area
+  static constexpr int total(int stages, int splitk = 1) { return stages * kStage + 256 + 1024 + (splitk - 1) * kRecv; }
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  long long spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (!done && ++spins > (1ll << 26)) __trap();
+  }
+}
 
 __device__ __forceinline__ void load8h(const t16* p, float* v) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -80,7 +123,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* recv_full = bars + 2 * STAGES + 1;   // split-K: every epilogue warp of every peer has pushed its partial
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  float* recv = reinterpret_cast<float*>(smem + STAGES * L::kStage + 256);   // [(S-1)][BN][128] fp32, rank 0 only
+  const int S = BN == 64 ? p.splitk : 1;         // split-K exists for the narrow tile only (compiled out elsewhere)
+  const uint32_t krank = S > 1 ? cluster_ctarank() : 0u;
+  // this CTA's k-blocks: [kb0, kb0 + nkl)
+  const int kq = p.nk / S, kr = p.nk - kq * S;
+  const int kb0 = (int)krank * kq + ((int)krank < kr ? (int)krank : kr);
+  const int nkl = kq + ((int)krank < kr ? 1 : 0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const gtrace = (blockIdx.y * gridDim.x + blockIdx.x) < 64 ? g_gemm_trace : nullptr;
@@ -96,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(recv_full, (S - 1) * kEpiWarps);
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -107,6 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   fence_before();
   __syncthreads();
   fence_after();
+  if (S > 1) cluster_sync_all();   // rank 0's receive barrier is initialised before any peer can signal it
   const uint32_t tmem = *tmem_slot;
   // Programmatic dependent launch: the next kernel in the stream may start its own prologue now (this CTA already
   // holds its TMEM), and nothing above touched global memory, so the previous kernel's tail overlapped our prologue.
@@ -115,9 +168,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    for (int kb = 0; kb < p.nk; ++kb) {
-      const int st = kb % STAGES;
-      if (kb >= STAGES) mbar_wait(&empty[st], ((kb / STAGES) - 1) & 1, p.err, 1);
+    for (int kl = 0; kl < nkl; ++kl) {
+      const int st = kl % STAGES, kb = kb0 + kl;
+      if (kl >= STAGES) mbar_wait(&empty[st], ((kl / STAGES) - 1) & 1, p.err, 1);
       if (elect_one()) {
         unsigned char* sa = smem + st * L::kStage;
         unsigned char* sb = sa + SMEM_A_STAGE;
@@ -137,12 +190,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = make_idesc(TBM, BN);
     const uint32_t smem_base = smem_u32(smem);
-    for (int kb = 0; kb < p.nk; ++kb) {
+    for (int kb = 0; kb < nkl; ++kb) {
       const int st = kb % STAGES;
       mbar_wait(&full[st], (kb / STAGES) & 1, p.err, 2);
       fence_after();
       if (kb == 0) GTRACE(2);
-      if (kb == p.nk - 1) GTRACE(3);
+      if (kb == nkl - 1) GTRACE(3);
       if (elect_one()) {
         const uint32_t a_addr = smem_base + st * L::kStage;
         const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + SMEM_A_STAGE);
@@ -150,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kk = 0; kk < TBK / 16; ++kk)
           umma_ss(tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
         commit(&empty[st]);
-        if (kb == p.nk - 1) commit(acc_full);
+        if (kb == nkl - 1) commit(acc_full);
       }
       __syncwarp();
     }
@@ -194,6 +247,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     fence_after();
     if (warp == 2) GTRACE(4);
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    if (krank != 0) {
+      // ---- split-K peer: fp32 partial tile -> rank 0's receive buffer [BN][128] (lanes = consecutive rows) ----
+      const uint32_t dst0 = map_to_cta(smem_u32(recv + ((size_t)(krank - 1) * BN) * TBM + r), 0);
+#pragma unroll 1
+      for (int cc = 0; cc < kHalfCols; cc += 32) {
+        const int c0 = cbeg + cc;
+        if (n0 + c0 >= p.N) break;
+        float v[32];
+        tmem_ld32(lane_addr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st_cluster_f32(dst0 + (uint32_t)((c0 + j) * TBM * 4), v[j]);
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(recv_full), 0));
+    } else {
+    if (S > 1) mbar_wait_cluster(recv_full, 0);
     auto chunk = [&](const int c0) {
       const int n = n0 + c0;
       if (n >= p.N) return;                          // warp-uniform
@@ -219,6 +289,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float v[32];
       tmem_ld32(lane_addr + c0, v);
       if (warp == 2 && c0 == 0) GTRACE(5);
+      for (int sp = 1; sp < S; ++sp) {               // peers' partials, in rank order
+        const float* rv = recv + ((size_t)(sp - 1) * BN + c0) * TBM + r;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += rv[j * TBM];
+      }
       if (!valid) return;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -289,6 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
       for (int cc = 0; cc < kHalfCols; cc += 32) chunk(cbeg + cc);
     }
+    }
     fence_before();
   }
   __syncthreads();
@@ -298,29 +374,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+constexpr int kMaxSplitK = 4;
+int tc_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+// RMEM_GEMM_SPLITK=0 disables the split (A/B measurements)
+bool gemm_splitk_switch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RMEM_GEMM_SPLITK"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <int BN>
 int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int m_tiles, int max_stages,
               cudaStream_t s) {
   using L = TcSmem<BN>;
   static bool attr_done = false;
   if (!attr_done) {
+    const int a = L::total(kMaxStages), b = BN == 64 ? L::total(4, kMaxSplitK) : 0;
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::total(kMaxStages)));
+                                         a > b ? a : b));
     attr_done = true;
   }
+  // Split-K (BN = 64 only): few output tiles and a long K -> spread the k-blocks over a cluster of S CTAs so that
+  // every SM pulls a share of the operands (the per-SM L2 ingest rate is the bound, see the header).
+  const int tiles = cdiv(p.N, BN) * m_tiles;
+  int S = 1;
+  if (BN == 64 && gemm_splitk_switch() && tiles * 2 <= tc_sm_count() && p.nk >= 8) {
+    S = tc_sm_count() / tiles;
+    if (S > kMaxSplitK) S = kMaxSplitK;
+    if (S > p.nk / 4) S = p.nk / 4;
+    if (S < 2) S = 1;
+  }
+  p.splitk = S;
   // Only as many stages as there are k-blocks: short-K GEMMs (most of the encoder) are latency-bound, and a small
   // shared-memory footprint lets several CTAs share an SM so one CTA's epilogue overlaps another's loads.
-  p.stages = p.nk < max_stages ? p.nk : max_stages;
+  const int nkl = cdiv(p.nk, S);
+  p.stages = nkl < max_stages ? nkl : max_stages;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(p.N, BN), m_tiles);
+  cfg.gridDim = dim3(cdiv(p.N, BN), m_tiles, S);
   cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = L::total(p.stages);
+  cfg.dynamicSmemBytes = L::total(p.stages, S);
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (S > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 1;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = (unsigned)S;
+    cfg.numAttrs = 2;
+  }
   RMEM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, *ma, *mb, static_cast<const TcGemmParams&>(p)));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;

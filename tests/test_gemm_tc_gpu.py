@@ -38,7 +38,9 @@ def both(fn):
 
 @pytest.mark.parametrize("shape", [(1674, 640, 256), (1674, 512, 1024), (25773, 64, 256), (25773, 256, 64),
                                    (6527, 512, 128), (129, 64, 64), (1674, 128, 512), (1674, 256, 128),
-                                   (512, 1674, 256)])
+                                   (512, 1674, 256),
+                                   # split-K clusters (few tiles, long K): S = 4, S = 4 with 2 tiles, odd k-block count
+                                   (1674, 128, 1024), (200, 64, 2304), (300, 64, 576), (1674, 256, 2304)])
 def test_linear_matches_torch_and_legacy(K, cuda_device, shape):
     M, N, Kd = shape
     OP = _capi.op_dtype()
@@ -76,3 +78,18 @@ def test_conv_matches_torch_and_legacy(K, cuda_device, cfg):
     assert tc.shape == ref.shape
     assert relfro(tc, ref) < 1.5e-3, cfg
     assert relfro(tc, leg) < 1.5e-3, cfg
+
+
+def test_splitk_is_bit_reproducible_and_matches_unsplit(K, cuda_device, monkeypatch):
+    """The cluster split-K reduction adds the partial tiles in rank order: two runs give identical bits, and the
+    result agrees with torch fp32 like the unsplit kernel does."""
+    OP = _capi.op_dtype()
+    g = torch.Generator().manual_seed(7)
+    M, N, Kd = 1620, 256, 2304
+    A = torch.randn(M, Kd, generator=g).to(cuda_device).to(OP)
+    W = (torch.randn(N, Kd, generator=g) / math.sqrt(Kd)).to(cuda_device).to(OP)
+    b = torch.randn(N, generator=g).to(cuda_device)
+    o1 = K.gemm(A, W, b, out_f32=True)
+    o2 = K.gemm(A, W, b, out_f32=True)
+    assert torch.equal(o1, o2)
+    assert relfro(o1, F.linear(A.float(), W.float(), b)) < 2e-5 * math.sqrt(Kd)
