@@ -181,6 +181,7 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        print(f"[bench] rank {rank}/{world} {'e2e' if e2e else 'device'}: {ms / steps:.4f} ms/step", file=sys.stderr, flush=True)
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms], device=dev)

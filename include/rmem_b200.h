@@ -89,12 +89,14 @@ int rmem_local_attn_fwd(const void* q, long long ldq, const void* k, long long l
                         const float* rel, long long ldrel, const void* gate, long long ldg, void* out,
                         long long ldo, int h, int w, int Dv, float scale, void* stream);
 
-/* Same op on tensor cores (tcgen05 + 3-D TMA boxes over the key halo of an 8x16 query patch). */
+/* Same op on tensor cores (tcgen05 + 3-D TMA boxes over the key halo of a 4x32 query patch).  rel_pitch = floats per
+ * window row of `rel`: 15 = the reference's relative_emb_k order (225 columns), 16 = one aligned 64-byte line per window
+ * row (240 columns, what the engine's packed weights produce; ~3x faster bias fetch). */
 int rmem_local_attn_tc_workspace_bytes(int h, int w, int Dv, size_t* bytes);
 int rmem_local_attn_tc_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                           const float* rel, long long ldrel, const void* gate, long long ldg, void* out,
-                           long long ldo, int h, int w, int Dv, float scale, void* workspace, size_t workspace_bytes,
-                           void* stream);
+                           const float* rel, long long ldrel, int rel_pitch, const void* gate, long long ldg,
+                           void* out, long long ldo, int h, int w, int Dv, float scale, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* nn.LayerNorm (transformer.py:1104,1119,1222), GroupNorm (basic.py:6-12, 62-70), DWConv2d (basic.py:38-59). */
 int rmem_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,

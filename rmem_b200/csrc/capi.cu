@@ -117,10 +117,11 @@ int rmem_local_attn_tc_workspace_bytes(int h, int w, int Dv, size_t* bytes) {
 }
 
 int rmem_local_attn_tc_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                           const float* rel, long long ldrel, const void* gate, long long ldg, void* out,
-                           long long ldo, int h, int w, int Dv, float scale, void* workspace, size_t workspace_bytes,
-                           void* stream) {
-  return local_attn_tc((const t16*)q, ldq, (const t16*)k, ldk, (const t16*)v, ldv, rel, ldrel, (const t16*)gate, ldg,
+                           const float* rel, long long ldrel, int rel_pitch, const void* gate, long long ldg,
+                           void* out, long long ldo, int h, int w, int Dv, float scale, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return local_attn_tc((const t16*)q, ldq, (const t16*)k, ldk, (const t16*)v, ldv, rel, ldrel, rel_pitch,
+                       (const t16*)gate, ldg,
                        (t16*)out, ldo, h, w, Dv, scale, workspace, workspace_bytes, STREAM(stream));
 }
 

@@ -530,14 +530,15 @@ struct rmem_engine {
     {
       Lin p;
       p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
-      p.w = pre + ".short.rel"; p.C = rel; p.ldc = 256; p.c_fp32 = 1;
+      // the tensor-core kernel reads one aligned 16-float line per window row (".short.rel16": rows re-ordered at pack time)
+      p.w = pre + (cfg.attn_impl == RMEM_ATTN_DENSE ? ".short.rel" : ".short.rel16"); p.C = rel; p.ldc = 256; p.c_fp32 = 1;
       RMEM_TRY(linear(p, s));
       mark("gpm.short.rel", s);
       if (cfg.attn_impl == RMEM_ATTN_DENSE)
         RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
       else
-        RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale,
-                               local_ws, local_ws_bytes, s));
+        RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, 16, gate, kDv, attn_a, kDv, G.h, G.w, kDv,
+                               scale, local_ws, local_ws_bytes, s));
       mark("gpm.short.attn", s);
       RMEM_TRY(gated_tail(pre + ".short", s));
       mark("gpm.short.tail", s);

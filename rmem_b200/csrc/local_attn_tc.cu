@@ -60,8 +60,9 @@ constexpr float M_FLOOR = -1.0e30f;   // finite stand-in for "no key seen yet" (
 struct LocalParams {
   int h, w, n_dv, tiles_x;
   float scale_log2;
-  const float* rel;      // [HW, ldrel] fp32, first 225 columns
-  long long ldrel;
+  const float* rel;      // [HW, ldrel] fp32: 15 window rows of rel_pitch floats (15 = reference order, 16 = one aligned
+  long long ldrel;       //   64-byte line per window row, last float unused)
+  int rel_pitch;
   const t16* gate;       // [HW, ldg] or null
   long long ldg;
   t16* out;              // [HW, ldo]
@@ -241,6 +242,19 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int c_lo = max(qx - MD, 0) - kx_base, c_hi = min(qx + MD, p.w - 1) - kx_base;      // inclusive, in [0, 31]
     const int dx0 = kx_base - qx + MD;                                                     // window column of c = 0
     float m_ref = M_FLOOR, l_tot = 0.f;
+    // rel_pitch 16: the 15 biases of one window row are one 64-byte line per query: four 16-byte loads, issued one
+    // own-tile ahead.  (One scalar load per (query, key) -- 32 different lines per instruction -- made this kernel
+    // LSU-bound at ~4300 cycles per key tile.)
+    const bool rel16 = p.rel_pitch == 16;
+    float4 rnext[4];
+    auto load_rel = [&](int jj) {
+      const int dy = ky_base + KR * jj - qy + MD;
+      const bool in = jj < NT && row_ok && (unsigned)dy <= (unsigned)(2 * MD);
+      const float4* src = reinterpret_cast<const float4*>(relrow + (in ? dy : 0) * 16);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) rnext[e] = in ? src[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (rel16) load_rel(grp);
 
     for (int j = 0; j < NT; ++j) {
       if ((j & 1) != grp) continue;
@@ -258,12 +272,45 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       // x = scale*s + rel (log2 units) inside the window, -inf outside; rows of the patch beyond the frame see x = 0
       float mt = -INFINITY;
+      if (rel16) {
+        static_assert(KR == 1, "one key row per tile");
+        float R[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          R[4 * e] = rnext[e].x * LOG2E; R[4 * e + 1] = rnext[e].y * LOG2E;
+          R[4 * e + 2] = rnext[e].z * LOG2E; R[4 * e + 3] = rnext[e].w * LOG2E;
+        }
+        load_rel(j + 2);
+        // key column c of the tile is window column c + dx0: rotate so that R[c & 15] is that column's bias (the <= 15
+        // valid columns of a query are consecutive, hence distinct mod 16); four select stages, all in registers
+        const int rot = dx0 & 15;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const bool on = (rot >> b) & 1;
+          float T[16];
+#pragma unroll
+          for (int m = 0; m < 16; ++m) T[m] = on ? R[(m + (1 << b)) & 15] : R[m];
+#pragma unroll
+          for (int m = 0; m < 16; ++m) R[m] = T[m];
+        }
+        const int ky = ky_base + j;
+        const int dy = ky - qy + MD;
+        const bool row_in = row_ok && (unsigned)dy <= (unsigned)(2 * MD) && (unsigned)ky < (unsigned)p.h;
+#pragma unroll
+        for (int c = 0; c < KW; ++c) {
+          const bool ok = row_in && c >= c_lo && c <= c_hi;
+          float x = ok ? fmaf(sc[c], p.scale_log2, R[c & 15]) : -INFINITY;
+          if (!row_ok) x = 0.f;
+          sc[c] = x;
+          mt = fmaxf(mt, x);
+        }
+      } else
 #pragma unroll
       for (int kr = 0; kr < KR; ++kr) {
         const int ky = ky_base + KR * j + kr;
         const int dy = ky - qy + MD;
         const bool row_in = row_ok && (unsigned)dy <= (unsigned)(2 * MD) && (unsigned)ky < (unsigned)p.h;
-        const float* rr = relrow + dy * (2 * MD + 1) + dx0;
+        const float* rr = relrow + dy * p.rel_pitch + dx0;
 #pragma unroll
         for (int c = 0; c < KW; ++c) {
           const bool ok = row_in && c >= c_lo && c <= c_hi;
@@ -408,7 +455,7 @@ size_t local_attn_tc_workspace(int h, int w, int Dv) {
 }
 
 int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, const t16* v, long long ldv,
-                  const float* rel, long long ldrel, const t16* gate, long long ldg, t16* out, long long ldo, int h,
+                  const float* rel, long long ldrel, int rel_pitch, const t16* gate, long long ldg, t16* out, long long ldo, int h,
                   int w, int Dv, float scale, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   RMEM_REQUIRE(Dv % DVC == 0, "local_attn_tc: Dv=%d must be a multiple of 256", Dv);
   RMEM_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && (!gate || ldg % 8 == 0),
@@ -444,7 +491,9 @@ int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, cons
   LocalParams p;
   p.h = h; p.w = w; p.n_dv = Dv / DVC; p.tiles_x = cdiv(w, QW);
   p.scale_log2 = scale * LOG2E;
-  p.rel = rel; p.ldrel = ldrel; p.gate = gate; p.ldg = ldg; p.out = out; p.ldo = ldo;
+  RMEM_REQUIRE(rel_pitch == 15 || (rel_pitch == 16 && ldrel % 4 == 0 && (reinterpret_cast<uintptr_t>(rel) & 15) == 0),
+               "local_attn_tc: rel_pitch must be 15, or 16 with 16-byte aligned rows");
+  p.rel = rel; p.ldrel = ldrel; p.rel_pitch = rel_pitch; p.gate = gate; p.ldg = ldg; p.out = out; p.ldo = ldo;
   static bool attr_done = false;
   if (!attr_done) {
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(local_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));

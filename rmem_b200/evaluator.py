@@ -1,0 +1,300 @@
+"""Per-clip evaluation shell over the engine API ("real-clip evaluator shell").
+
+Host-side mirror of the reference's production caller:
+  * clip dataset ............ aot_plus/dataloaders/eval_datasets.py:14-118  (VOSTest: object bookkeeping, label squeeze)
+  * test-time resize ........ aot_plus/dataloaders/video_transforms.py:559-643 (MultiRestrictSize, single scale, no flip)
+  * tensor conversion ....... aot_plus/dataloaders/video_transforms.py:646-666 (MultiToTensor: /255, ImageNet mean/std)
+  * per-clip frame loop ..... aot_plus/networks/managers/evaluator.py:300-556  (reference frame, propagate, argmax,
+                              new-object merge + re-reference, update_memory, long-term gap = max(round(N/30), 5))
+  * mask writer ............. aot_plus/utils/image.py:89-105                   (un-squeeze object ids, palette PNG)
+  * clip -> rank queue ...... aot_plus/networks/managers/evaluator.py:276-295  (dynamic queue; here an atomic counter in
+                              the torch.distributed key-value store -- still no per-frame collective)
+
+The engine is anything with the reference's method surface (`restart_engine`, `add_reference_frame`,
+`match_propogate_one_frame`, `update_memory`, `long_term_mem_gap`, `input_size_2d`): the CUDA engine of
+rmem_b200.engine in production, the CPU oracle in the host-logic tests.  Test-time augmentation (flip / multi-scale
+engines, evaluator.py:338-352) is not part of the measured path and is rejected loudly rather than silently ignored.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def davis_palette() -> List[int]:
+    """The 256-entry palette of utils/image.py:6-74: the PASCAL-VOC bit-shuffle colours (with 191 where VOC has 192) for
+    ids 0..21, a grey ramp (i, i, i) above."""
+    pal: List[int] = []
+    for i in range(256):
+        if i >= 22:
+            pal += [i, i, i]
+            continue
+        r = g = b = 0
+        c = i
+        for j in range(8):
+            r |= ((c >> 0) & 1) << (7 - j)
+            g |= ((c >> 1) & 1) << (7 - j)
+            b |= ((c >> 2) & 1) << (7 - j)
+            c >>= 3
+        pal += [191 if v == 192 else v for v in (r, g, b)]
+    return pal
+
+
+def restrict_size(h: int, w: int, min_size: Optional[int] = None, max_size: Optional[float] = 800 * 1.3,
+                  scale: float = 1.0, align_corners: bool = True, max_stride: int = 16) -> Tuple[int, int]:
+    """Network input size for an h x w frame (video_transforms.py:575-623; defaults = configs/default.py:110-112).
+    480 x 854 -> 481 x 849, 720 x 1280 -> 721 x 1281 after the 1040-pixel long-edge cap ...."""
+    assert (min_size is None) or (max_size is None)
+    sc = None
+    if min_size is not None:
+        short_edge = w if h > w else h
+        if short_edge > min_size:
+            sc = float(min_size) / short_edge
+    else:
+        long_edge = h if h > w else w
+        if long_edge > max_size:
+            sc = float(max_size) / long_edge
+    new_h, new_w = (h, w) if sc is None else (sc * h, sc * w)
+    new_h, new_w = int(new_h * scale), int(new_w * scale)
+    if align_corners:
+        if (new_h - 1) % max_stride != 0:
+            new_h = int(np.around((new_h - 1) / max_stride) * max_stride + 1)
+        if (new_w - 1) % max_stride != 0:
+            new_w = int(np.around((new_w - 1) / max_stride) * max_stride + 1)
+    else:
+        if new_h % max_stride != 0:
+            new_h = int(np.around(new_h / max_stride) * max_stride)
+        if new_w % max_stride != 0:
+            new_w = int(np.around(new_w / max_stride) * max_stride)
+    return new_h, new_w
+
+
+def long_term_gap(num_frames: int, no_memory_gap: bool = False) -> int:
+    """evaluator.py:329-333: one long-term frame every max(round(N / 30), 5) frames."""
+    gap = max(int(round(num_frames / 30)), 5)
+    if no_memory_gap:
+        gap = int(round(gap / 4))
+    return gap
+
+
+class ClipDataset:
+    """One clip = a directory of frames plus label PNGs for the frames that introduce objects (VOSTest,
+    eval_datasets.py:14-118).  `obj_indices[i]` lists the dataset object ids known up to frame i (0 = background);
+    labels are squeezed to 0..n in order of first appearance, exactly like `read_label(..., squeeze_idx)`."""
+
+    def __init__(self, image_dir: str, label_dir: str, images: Optional[Sequence[str]] = None,
+                 labels: Optional[Sequence[str]] = None, rgb: bool = True, resolution: Optional[int] = None,
+                 min_size: Optional[int] = None, max_size: Optional[float] = 800 * 1.3, seq_name: Optional[str] = None):
+        self.image_dir, self.label_dir = image_dir, label_dir
+        self.seq_name = seq_name or os.path.basename(os.path.normpath(image_dir))
+        self.images = sorted(images if images is not None else
+                             [f for f in os.listdir(image_dir) if f.lower().endswith((".jpg", ".jpeg", ".png"))])
+        self.labels = set(labels if labels is not None else
+                          [f for f in os.listdir(label_dir) if f.lower().endswith(".png")])
+        self.rgb, self.resolution = rgb, resolution
+        self.min_size, self.max_size = min_size, max_size
+        assert len(self.images) >= 2, "a clip needs a reference frame and at least one frame to propagate to"
+        self.obj_nums: List[int] = []
+        self.obj_indices: List[List[int]] = []
+        curr_objs = [0]
+        for img_name in self.images:
+            self.obj_nums.append(len(curr_objs) - 1)
+            lab = os.path.splitext(img_name)[0] + ".png"
+            if lab in self.labels:
+                for obj in list(np.unique(self._read_png(lab))):
+                    if int(obj) not in curr_objs:
+                        curr_objs.append(int(obj))
+            self.obj_indices.append(curr_objs.copy())
+        self.obj_nums[0] = self.obj_nums[1]
+
+    def __len__(self):
+        return len(self.images)
+
+    def _read_png(self, name: str) -> np.ndarray:
+        from PIL import Image
+        return np.array(Image.open(os.path.join(self.label_dir, name)), dtype=np.uint8)
+
+    def read_label(self, name: str, squeeze_idx: Sequence[int]) -> np.ndarray:
+        label = self._read_png(name)
+        out = label * 0
+        for idx, obj_id in enumerate(squeeze_idx):
+            if obj_id == 0:
+                continue
+            out += ((label == obj_id) * idx).astype(np.uint8)
+        return out
+
+    def read_image(self, idx: int) -> np.ndarray:
+        import cv2
+        img = cv2.imread(os.path.join(self.image_dir, self.images[idx]))
+        if img is None:
+            raise FileNotFoundError(os.path.join(self.image_dir, self.images[idx]))
+        img = np.array(img, dtype=np.float32)
+        return img[:, :, [2, 1, 0]] if self.rgb else img
+
+    def __getitem__(self, idx: int) -> Dict:
+        img = self.read_image(idx)
+        height, width = img.shape[:2]
+        if self.resolution is not None:          # output size only (eval_datasets.py:87-90); the frame is not resized here
+            width = int(np.ceil(float(width) * self.resolution / float(height)))
+            height = int(self.resolution)
+        nh, nw = restrict_size(img.shape[0], img.shape[1], self.min_size, self.max_size)
+        if (nh, nw) != img.shape[:2]:
+            import cv2
+            img = cv2.resize(img, dsize=(nw, nh), interpolation=cv2.INTER_CUBIC)
+        img = img / 255.
+        img -= IMAGENET_MEAN
+        img /= IMAGENET_STD
+        sample = {"current_img": torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))).float()[None]}
+        lab = os.path.splitext(self.images[idx])[0] + ".png"
+        if lab in self.labels:
+            sample["current_label"] = torch.from_numpy(self.read_label(lab, self.obj_indices[idx])).int()[None, None]
+        sample["meta"] = {"seq_name": self.seq_name, "frame_num": len(self.images), "obj_num": self.obj_nums[idx],
+                          "current_name": self.images[idx], "height": height, "width": width, "flip": False,
+                          "obj_idx": self.obj_indices[idx]}
+        return sample
+
+
+def save_mask(mask: np.ndarray, path: str, squeeze_idx: Optional[Sequence[int]] = None, background: bool = True):
+    """utils/image.py:89-105: map 0..n back to the dataset's object ids, write a palettised PNG (on a writer thread
+    when `background`, like the reference's fire-and-forget thread)."""
+    mask = np.asarray(mask).astype(np.uint8)
+
+    def _write():
+        from PIL import Image
+        m = mask
+        if squeeze_idx is not None:
+            un = m * 0
+            for idx in range(1, len(squeeze_idx)):
+                un += ((m == idx) * squeeze_idx[idx]).astype(np.uint8)
+            m = un
+        im = Image.fromarray(m).convert("P")
+        im.putpalette(davis_palette())
+        im.save(path)
+
+    if background:
+        t = threading.Thread(target=_write)
+        t.start()
+        return t
+    _write()
+    return None
+
+
+@dataclass
+class ClipResult:
+    seq_name: str
+    frames: int = 0                       # propagated frames (the reference frame is not timed, evaluator.py:399-404)
+    seconds: float = 0.0
+    labels: List[torch.Tensor] = field(default_factory=list)      # uint8 [Ho, Wo] per propagated frame (if keep_labels)
+    paths: List[str] = field(default_factory=list)
+
+
+def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, device=None, keep_labels: bool = False,
+                  no_memory_gap: bool = False, timer: Optional[Callable[[], float]] = None,
+                  on_frame: Optional[Callable[[int, torch.Tensor], None]] = None) -> ClipResult:
+    """evaluator.py:300-556 for one clip and one (un-augmented) engine.  Frame 0 must carry a label."""
+    res = ClipResult(dataset.seq_name)
+    engine.restart_engine()
+    engine.long_term_mem_gap = long_term_gap(len(dataset), no_memory_gap)
+    if out_dir is not None:
+        os.makedirs(os.path.join(out_dir, dataset.seq_name), exist_ok=True)
+    use_cuda = device is not None and torch.device(device).type == "cuda"
+    writers = []
+    now = timer or time.perf_counter
+    for frame_idx in range(len(dataset)):
+        sample = dataset[frame_idx]
+        meta = sample["meta"]
+        img = sample["current_img"]
+        label = sample.get("current_label")
+        if device is not None:
+            img = img.to(device, non_blocking=True)
+            label = label.to(device, non_blocking=True) if label is not None else None
+        label = label.float() if label is not None else None
+        if frame_idx == 0:
+            if label is None:
+                raise ValueError(f"{dataset.seq_name}: the first frame has no label")
+            ref = F.interpolate(label, size=img.shape[2:], mode="nearest").int()
+            engine.add_reference_frame(img, ref, obj_nums=[int(meta["obj_num"])], frame_step=0)
+            continue
+        if use_cuda:
+            torch.cuda.synchronize()
+        t0 = now()
+        out_size = (int(meta["height"]), int(meta["width"]))
+        logit = engine.match_propogate_one_frame(img, output_size=out_size)
+        prob = torch.softmax(logit, dim=1)
+        pred = torch.argmax(prob, dim=1, keepdim=True).float()
+        if label is not None:              # a frame that introduces objects: paste them in and re-reference
+            keep = (label == 0).float()
+            pred = pred * keep + label * (1 - keep)
+            new_obj_nums = [int(pred.max().item())]
+            cur = F.interpolate(pred, size=engine.input_size_2d, mode="nearest")
+            engine.add_reference_frame(img, cur, obj_nums=new_obj_nums, frame_step=frame_idx)
+        else:
+            cur = F.interpolate(pred, size=engine.input_size_2d, mode="nearest")
+            engine.update_memory(cur)
+        if use_cuda:
+            torch.cuda.synchronize()
+        res.seconds += now() - t0
+        res.frames += 1
+        lab8 = pred[0, 0].to(torch.uint8).cpu()
+        if on_frame is not None:
+            on_frame(frame_idx, lab8)
+        if keep_labels:
+            res.labels.append(lab8)
+        if out_dir is not None:
+            path = os.path.join(out_dir, dataset.seq_name, os.path.splitext(meta["current_name"])[0] + ".png")
+            writers.append(save_mask(lab8.numpy(), path, meta["obj_idx"]))
+            res.paths.append(path)
+    for t in writers:
+        if t is not None:
+            t.join()
+    return res
+
+
+class ClipQueue:
+    """Clip -> rank assignment.  With a torch.distributed store every rank draws the next clip index from one atomic
+    counter (the reference's dynamic multiprocessing queue, evaluator.py:276-295); without one, static round-robin."""
+
+    def __init__(self, n_clips: int, rank: int = 0, world: int = 1, store=None, key: str = "rmem_next_clip"):
+        self.n, self.rank, self.world, self.store, self.key = n_clips, rank, world, store, key
+        self._static = iter(range(rank, n_clips, world))
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> int:
+        if self.store is None:
+            return next(self._static)
+        i = int(self.store.add(self.key, 1)) - 1
+        if i >= self.n:
+            raise StopIteration
+        return i
+
+
+def evaluate_clips(engine, clips: Sequence[ClipDataset], out_dir: Optional[str] = None, device=None, rank: int = 0,
+                   world: int = 1, store=None, log: Optional[Callable[[str], None]] = print) -> Dict:
+    """evaluator.py:265-613: every rank pulls clips until the queue is empty; (frames, seconds) are gathered once at
+    the end.  Returns this rank's per-clip results and the job-wide all-frame FPS."""
+    from .sharding import gather_stats
+    results: List[ClipResult] = []
+    for i in ClipQueue(len(clips), rank, world, store):
+        r = evaluate_clip(engine, clips[i], out_dir=out_dir, device=device)
+        results.append(r)
+        if log:
+            log(f"rank {rank} - Seq {r.seq_name} [{i + 1}/{len(clips)}] - FPS: {r.frames / max(r.seconds, 1e-9):.2f}")
+    frames = sum(r.frames for r in results)
+    seconds = sum(r.seconds for r in results)
+    stats = gather_stats(frames, seconds, device if device is not None else "cpu", world)
+    tot_f = sum(f for f, _ in stats)
+    tot_s = sum(s for _, s in stats)
+    return {"results": results, "frames": frames, "seconds": seconds, "all_frames": tot_f,
+            "all_frame_fps": tot_f / max(tot_s, 1e-9), "per_rank": stats}

@@ -258,15 +258,19 @@ def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, s
 
 def local_attention(q: torch.Tensor, k_prev: torch.Tensor, v_prev: torch.Tensor, rel_w: torch.Tensor,
                     rel_b: torch.Tensor, h: int, w: int, gate: Optional[torch.Tensor] = None,
-                    impl: str = "tc") -> torch.Tensor:
-    """q,k t16 [HW,128]; v t16 [HW,Dv]; rel_w fp32/t16 [225,128]; rel_b [225] -> t16 [HW,Dv]."""
+                    impl: str = "tc", rel_pitch: int = 16) -> torch.Tensor:
+    """q,k t16 [HW,128]; v t16 [HW,Dv]; rel_w fp32/t16 [225,128]; rel_b [225] -> t16 [HW,Dv].
+    impl "tc" lays the 225 offsets out as 15 window rows of `rel_pitch` floats (16 = what the engine's packed weights
+    use, 15 = the reference order); the CUDA-core kernel always reads the reference order."""
     lib = _capi.load()
     HW, Dk = q.shape
     Dv = v_prev.shape[1]
+    pitch = rel_pitch if impl == "tc" else 15
     wpad = torch.zeros(256, Dk, dtype=_capi.op_dtype(), device=q.device)
-    wpad[:225] = rel_w.to(_capi.op_dtype())
     bpad = torch.zeros(256, dtype=torch.float32, device=q.device)
-    bpad[:225] = rel_b.float()
+    for dy in range(15):
+        wpad[dy * pitch: dy * pitch + 15] = rel_w[dy * 15: dy * 15 + 15].to(_capi.op_dtype())
+        bpad[dy * pitch: dy * pitch + 15] = rel_b[dy * 15: dy * 15 + 15].float()
     rel = gemm(q, wpad, bpad, out_f32=True)
     out = torch.empty(HW, Dv, dtype=_capi.op_dtype(), device=q.device)
     if impl == "tc":
@@ -275,9 +279,9 @@ def local_attention(q: torch.Tensor, k_prev: torch.Tensor, v_prev: torch.Tensor,
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=q.device)
         _capi.check(lib.rmem_local_attn_tc_fwd(
             _capi.ptr(q), C.c_longlong(q.stride(0)), _capi.ptr(k_prev), C.c_longlong(k_prev.stride(0)),
-            _capi.ptr(v_prev), C.c_longlong(v_prev.stride(0)), _capi.ptr(rel), C.c_longlong(256), _capi.ptr(gate),
-            C.c_longlong(gate.stride(0) if gate is not None else 0), _capi.ptr(out), C.c_longlong(Dv), h, w, Dv,
-            C.c_float(1.0 / math.sqrt(Dk)), _capi.ptr(ws), C.c_size_t(nbytes.value), _capi.stream_ptr()))
+            _capi.ptr(v_prev), C.c_longlong(v_prev.stride(0)), _capi.ptr(rel), C.c_longlong(256), int(pitch),
+            _capi.ptr(gate), C.c_longlong(gate.stride(0) if gate is not None else 0), _capi.ptr(out), C.c_longlong(Dv),
+            h, w, Dv, C.c_float(1.0 / math.sqrt(Dk)), _capi.ptr(ws), C.c_size_t(nbytes.value), _capi.stream_ptr()))
         return out
     _capi.check(lib.rmem_local_attn_fwd(_capi.ptr(q), C.c_longlong(q.stride(0)), _capi.ptr(k_prev),
                                         C.c_longlong(k_prev.stride(0)), _capi.ptr(v_prev),

@@ -117,6 +117,14 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
             dw(f"{q}.{dst}.dw", f"{p}.{src}")
             linear(f"{q}.{dst}.proj", f"{p}.{src}.projection")
         linear(q + ".short.rel", p + ".short_term_attn.relative_emb_k", pad_rows=256)
+        # the same 225 offsets as 15 window rows of 16 (last one zero): one aligned 64-byte line per row for the
+        # tensor-core kernel (local_attn_tc.cu, rel_pitch 16)
+        for sfx in (".w", ".b"):
+            src = out[q + ".short.rel" + sfx]
+            dst = torch.zeros_like(src)
+            for dy in range(15):
+                dst[dy * 16: dy * 16 + 15] = src[dy * 15: dy * 15 + 15]
+            out[q + ".short.rel16" + sfx] = dst
         norm(q + ".norm2", p + ".norm2")
         norm(q + ".id_norm2", p + ".id_norm2")
         linear(q + ".self.linear_QK", p + ".self_attn.linear_QK")

@@ -177,8 +177,10 @@ def test_temporal_pe_slots_match_oracle(ops, cuda_device):
         assert ops.temporal_pe_slots(T) == ref, T
 
 
-@pytest.mark.parametrize("impl", ["tc", "cuda_core"])
+@pytest.mark.parametrize("impl", ["tc", "tc15", "cuda_core"])
 def test_local_attention(ops, cuda_device, impl):
+    """tc = tensor-core kernel with the packed 16-float window rows, tc15 = same kernel on the reference order."""
+    kw = {"impl": "tc", "rel_pitch": 15} if impl == "tc15" else {"impl": impl}
     g = torch.Generator().manual_seed(6)
     for (h, w) in [(17, 21), (31, 54), (9, 70), (46, 81)]:
         HW = h * w
@@ -191,7 +193,7 @@ def test_local_attention(ops, cuda_device, impl):
         ref = O.local_attention(q, k, v, rw, rb, h, w) * gate
         out = ops.local_attention(q.to(cuda_device).to(OP), k.to(cuda_device).to(OP),
                                   v.to(cuda_device).to(OP), rw.to(cuda_device), rb.to(cuda_device), h, w,
-                                  gate.to(cuda_device).to(OP), impl=impl)
+                                  gate.to(cuda_device).to(OP), **kw)
         assert torch.isfinite(out.float()).all()
         assert relfro(out, ref) < 6e-3, (h, w, impl)
 
