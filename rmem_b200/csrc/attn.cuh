@@ -73,6 +73,7 @@ int local_attn(const t16* q, long long ldq, const t16* k, long long ldk, const t
 // Tensor-core version (local_attn_tc.cu): 8x16 query patches x 256-column Dv chunks, key halo walked as 2x32 tiles via
 // 3-D TMA boxes; needs a value-major padded copy of v in `workspace` (local_attn_tc_workspace bytes, 256B aligned).
 size_t local_attn_tc_workspace(int h, int w, int Dv);
+int local_attn_tc_set_trace(long long* dev_buf);
 int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, const t16* v, long long ldv,
                   const float* rel, long long ldrel, int rel_pitch, const t16* gate, long long ldg, t16* out, long long ldo, int h,
                   int w, int Dv, float scale, void* workspace, size_t workspace_bytes, cudaStream_t s);

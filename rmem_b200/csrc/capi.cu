@@ -90,7 +90,10 @@ int rmem_debug_attn_events(void* ev0, void* ev1) {
   long_attn_tc2_set_events(ev0, ev1);
   return RMEM_OK;
 }
-int rmem_debug_attn_trace(void* dev_buf) { return long_attn_tc2_set_trace(reinterpret_cast<long long*>(dev_buf)); }
+int rmem_debug_attn_trace(void* dev_buf) {
+  RMEM_TRY(local_attn_tc_set_trace(reinterpret_cast<long long*>(dev_buf)));
+  return long_attn_tc2_set_trace(reinterpret_cast<long long*>(dev_buf));
+}
 
 int rmem_qprep_fwd(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
                    float scale, void* qt, float* qbias, int P, int C, void* stream) {

@@ -32,6 +32,9 @@ constexpr int BN = KW * KR;        // 64
 constexpr int DK = 128;
 constexpr int DVC = 256;
 constexpr int MD = 7;              // max displacement (15 x 15 window)
+// tile columns that can fall inside some query's window, widened to whole fp16 pairs
+constexpr int C_MIN = (KX_OFF - MD) & ~1, C_MAX = (KX_OFF + QW - 1 + MD) | 1;
+static_assert(C_MIN >= 0 && C_MAX < KW, "key tile covers every window");
 constexpr int NT = (QH + 2 * MD + KR - 1) / KR;   // 18 key tiles per patch
 constexpr int KS = 4, VS = 3, NSB = 4;
 constexpr int kWarpK = 8, kWarpV = 9, kWarpMmaS = 10, kWarpMmaPV = 11;
@@ -56,6 +59,8 @@ constexpr int TMEM_S = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 12.0f;
 constexpr float M_FLOOR = -1.0e30f;   // finite stand-in for "no key seen yet" (masked scores are -inf)
+
+__device__ long long* g_ltrace = nullptr;   // debug event trace (rmem_debug_attn_trace), null in production
 
 struct LocalParams {
   int h, w, n_dv, tiles_x;
@@ -127,6 +132,9 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp_free + NSB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const trace = blockIdx.x == 0 ? g_ltrace : nullptr;   // clock64 events of CTA 0 (debug), 16 slots per tile
+#define LTRACE(j, k) do { if (trace && lane == 0) trace[(long long)(j) * 16 + (k)] = clock64(); } while (0)
+  if (warp == 0) LTRACE(40, 0);
   const int patch = blockIdx.x / p.n_dv, dvc = blockIdx.x - patch * p.n_dv;
   const int ty = patch / p.tiles_x, tx = patch - ty * p.tiles_x;
   const int y0 = ty * QH, x0 = tx * QW;
@@ -191,6 +199,7 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_wait(&k_full[st], (i / KS) & 1, nullptr, 5);
       if (i >= NSB) mbar_wait(&sp_free[b], ((i - NSB) / NSB) & 1, nullptr, 6);
       fence_after();
+      LTRACE(i, 2);
       if (elect_one()) {
         const uint64_t dq = make_desc_sw128(smem_base + OFF_Q);
         const uint64_t dk = make_desc_sw128(smem_base + OFF_K + st * SMEM_K);
@@ -205,6 +214,7 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         commit(&s_full[b]);
       }
       __syncwarp();
+      LTRACE(i, 3);
     }
   } else if (warp == kWarpMmaPV) {
     // ================================ O += P.V issuer ================================
@@ -213,8 +223,10 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     for (int j = 0; j < NT; ++j) {
       const int b = j % NSB, sv = j % VS;
       mbar_wait(&p_full[b], (j / NSB) & 1, nullptr, 7);
+      LTRACE(j, 0);
       mbar_wait(&v_full[sv], (j / VS) & 1, nullptr, 9);
       fence_after();
+      LTRACE(j, 10);
       if (elect_one()) {
         const uint64_t dv = make_desc_sw128(smem_base + OFF_V + sv * SMEM_V);
         const uint32_t pa = tmem + TMEM_S + b * BN;
@@ -225,6 +237,7 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         commit(&sp_free[b]);
       }
       __syncwarp();
+      LTRACE(j, 1);
     }
   } else {
     // ================================ softmax + epilogue (warps 0-7) ================================
@@ -246,21 +259,27 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // own-tile ahead.  (One scalar load per (query, key) -- 32 different lines per instruction -- made this kernel
     // LSU-bound at ~4300 cycles per key tile.)
     const bool rel16 = p.rel_pitch == 16;
+    // Key column c of a tile is window column c + dx0, so the thread wants its 16-float line rotated left by
+    // rot = dx0 mod 16 (then bias(c) = line[c & 15], a compile-time register).  rot is fixed per thread: whole
+    // float4s are rotated for free by the load addresses, the remaining 0..3 floats by two select stages.
+    const int rot = dx0 & 15, rot4 = rot >> 2;
     float4 rnext[4];
     auto load_rel = [&](int jj) {
       const int dy = ky_base + KR * jj - qy + MD;
       const bool in = jj < NT && row_ok && (unsigned)dy <= (unsigned)(2 * MD);
       const float4* src = reinterpret_cast<const float4*>(relrow + (in ? dy : 0) * 16);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) rnext[e] = in ? src[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = 0; e < 4; ++e) rnext[e] = in ? src[(e + rot4) & 3] : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     if (rel16) load_rel(grp);
 
     for (int j = 0; j < NT; ++j) {
       if ((j & 1) != grp) continue;
       const int b = j % NSB;
+      if (quad == 0) LTRACE(j, 4);
       mbar_wait(&s_full[b], (j / NSB) & 1, nullptr, 10);
       fence_after();
+      if (quad == 0) LTRACE(j, 5);
       float sc[64];
       {
         uint32_t r0[32], r1[32];
@@ -281,11 +300,8 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           R[4 * e + 2] = rnext[e].z * LOG2E; R[4 * e + 3] = rnext[e].w * LOG2E;
         }
         load_rel(j + 2);
-        // key column c of the tile is window column c + dx0: rotate so that R[c & 15] is that column's bias (the <= 15
-        // valid columns of a query are consecutive, hence distinct mod 16); four select stages, all in registers
-        const int rot = dx0 & 15;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 2; ++b) {
           const bool on = (rot >> b) & 1;
           float T[16];
 #pragma unroll
@@ -296,11 +312,12 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int ky = ky_base + j;
         const int dy = ky - qy + MD;
         const bool row_in = row_ok && (unsigned)dy <= (unsigned)(2 * MD) && (unsigned)ky < (unsigned)p.h;
+        // Columns outside [C_MIN, C_MAX] are outside every query's window (the exp loop skips them as well).  Rows of
+        // the patch beyond the frame are fully masked: M_FLOOR keeps their exponentials at 0, nothing is stored.
 #pragma unroll
-        for (int c = 0; c < KW; ++c) {
+        for (int c = C_MIN; c <= C_MAX; ++c) {
           const bool ok = row_in && c >= c_lo && c <= c_hi;
-          float x = ok ? fmaf(sc[c], p.scale_log2, R[c & 15]) : -INFINITY;
-          if (!row_ok) x = 0.f;
+          const float x = ok ? fmaf(sc[c], p.scale_log2, R[c & 15]) : -INFINITY;
           sc[c] = x;
           mt = fmaxf(mt, x);
         }
@@ -321,6 +338,7 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           mt = fmaxf(mt, x);
         }
       }
+      if (quad == 0) LTRACE(j, 6);
       // ---- hand-over of the lazily updated row maximum from the other group's tile j-1 ----
       float m_prev = M_FLOOR;
       if (j > 0) {
@@ -354,23 +372,40 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         l_tot *= exp2f(m_ref - m_new);
         m_ref = m_new;
       }
+      if (quad == 0) LTRACE(j, 7);
       uint32_t pk[32];
       float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
+        if (c + 1 < C_MIN || c > C_MAX) { pk[c >> 1] = 0u; continue; }   // never inside a window (compile time)
         const float e0 = exp2f(sc[c] - m_new);          // exp2(-inf) = 0 for masked keys
         const float e1 = exp2f(sc[c + 1] - m_new);
         ls0 += e0; ls1 += e1;
         pk[c >> 1] = pack2_fast(e0, e1);
       }
       l_tot += ls0 + ls1;
+      if (quad == 0) LTRACE(j, 8);
       tmem_st32u(lane_addr + TMEM_S + b * BN, pk);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (quad == 0) LTRACE(j, 9);
     }
+    if (warp == 0) LTRACE(40, 1);
 
     // ---- epilogue: out = O / l * gate ----
+    // The gate rows this lane will write (two rows per store instruction, see below) are fetched now, all sixteen at
+    // once: their L2 latency overlaps the wait for the last P.V instead of being paid once per row pair.
+    const int ecol = dvc * DVC + grp * (DVC / 2) + (lane & 15) * 8;
+    uint4 gq[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int prow = quad * 32 + it * 2 + (lane >> 4);
+      const int oy = y0 + prow / QW, ox = x0 + prow % QW;
+      gq[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (p.gate && oy < p.h && ox < p.w)
+        gq[it] = *reinterpret_cast<const uint4*>(p.gate + ((long long)oy * p.w + ox) * p.ldg + ecol);
+    }
     lx[(grp * BM + row) * 2 + 0] = m_ref;
     lx[(grp * BM + row) * 2 + 1] = l_tot;
     named_bar_sync(id_ex, 64);
@@ -380,35 +415,47 @@ local_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const float inv = 1.f / l_row;
     mbar_wait(&sp_free[(NT - 1) % NSB], ((NT - 1) / NSB) & 1, nullptr, 12);
     fence_after();
+    if (warp == 0) LTRACE(40, 2);
     const int col0 = dvc * DVC + grp * (DVC / 2);
+    // Every MMA has retired and every TMA tile has been consumed: the K/V rings are free.  Each warp stages its
+    // 32 rows x 128 columns (fp32, normalised) there and writes them out two rows per instruction -- 16 lanes x 16 bytes
+    // per row, whole lines -- with the gate read the same way.  (One row per lane costs a line per lane per access:
+    // ~10000 cycles for this epilogue.)
+    constexpr int ROWP = (DVC / 2) * 4 + 16;                 // staged row pitch in bytes (+16: conflict-free float4 phases)
+    static_assert(8 * 32 * ROWP <= KS * SMEM_K + VS * SMEM_V, "staging fits in the rings");
+    unsigned char* stg = smem + OFF_K + warp * (32 * ROWP);
 #pragma unroll 1
     for (int c = 0; c < DVC / 2; c += 32) {
       float o[32];
       tmem_ld32(lane_addr + TMEM_O + grp * (DVC / 2) + c, o);
-      if (row_ok) {
-        uint4 g4[4];
+      float4* d = reinterpret_cast<float4*>(stg + lane * ROWP + c * 4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        d[e] = make_float4(o[4 * e] * inv, o[4 * e + 1] * inv, o[4 * e + 2] * inv, o[4 * e + 3] * inv);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int rr = it * 2 + (lane >> 4), cc = (lane & 15) * 8;
+      const int prow = quad * 32 + rr;
+      const int oy = y0 + prow / QW, ox = x0 + prow % QW;
+      if (oy < p.h && ox < p.w) {
+        const long long oi = (long long)oy * p.w + ox;
+        const float4* sp = reinterpret_cast<const float4*>(stg + rr * ROWP + cc * 4);
+        const float4 a = sp[0], b = sp[1];
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         if (p.gate) {
-          const t16* gp = p.gate + qi * p.ldg + col0 + c;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) g4[e] = *reinterpret_cast<const uint4*>(gp + e * 8);
+          const uint4 g = gq[it];
+          const float2 g0 = unpack2(g.x), g1 = unpack2(g.y), g2 = unpack2(g.z), g3 = unpack2(g.w);
+          v[0] *= g0.x; v[1] *= g0.y; v[2] *= g1.x; v[3] *= g1.y; v[4] *= g2.x; v[5] *= g2.y; v[6] *= g3.x; v[7] *= g3.y;
         }
-        t16* po = p.out + qi * p.ldo + col0 + c;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = o[e * 8 + k] * inv;
-          if (p.gate) {
-            const float2 a = unpack2(g4[e].x), bb = unpack2(g4[e].y), cc = unpack2(g4[e].z), dd = unpack2(g4[e].w);
-            v[0] *= a.x; v[1] *= a.y; v[2] *= bb.x; v[3] *= bb.y; v[4] *= cc.x; v[5] *= cc.y; v[6] *= dd.x; v[7] *= dd.y;
-          }
-          uint4 u;
-          u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(po + e * 8) = u;
-        }
+        uint4 u;
+        u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.out + oi * p.ldo + col0 + cc) = u;
       }
     }
     fence_before();
+    if (warp == 0) LTRACE(40, 3);
   }
   fence_before();
   __syncthreads();
@@ -502,6 +549,11 @@ int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, cons
   const int patches = cdiv(h, QH) * p.tiles_x;
   RMEM_CUDA_CHECK(launch_pdl(local_attn_tc_kernel, dim3(patches * p.n_dv), dim3(kThreads), SMEM_TOTAL, s, *mq, *mk, *mv, p));
   RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int local_attn_tc_set_trace(long long* dev_buf) {
+  RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_ltrace, &dev_buf, sizeof(dev_buf)));
   return RMEM_OK;
 }
 
