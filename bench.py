@@ -97,6 +97,9 @@ class ClockSampler:
                     samples=len(sm))
 
 
+PREFETCH = os.environ.get("RMEM_BENCH_PREFETCH", "1") != "0"
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -132,6 +135,9 @@ def run_ours(args):
         eng.add_reference_frame(src[0:1], label0.int().to(dev), obj_nums=[N_OBJ], frame_step=0)
 
     def step(i, src):
+        # software pipelining across frames: frame i+1 is encoded on the engine's side stream while frame i propagates
+        if PREFETCH:
+            eng.prefetch(src[1 + (i + 1) % ring: 2 + (i + 1) % ring])
         lab = eng.propagate_label(src[1 + i % ring: 2 + i % ring], output_size=(H, W))
         eng.update_memory(lab)        # 480p -> output size == input size, nearest resize is the identity
         return lab
@@ -171,6 +177,8 @@ def run_ours(args):
             if e2e:
                 if i + 1 < steps:
                     prefetch(i + 1, src)
+                    if PREFETCH:
+                        eng.prefetch(stage[(i + 1) % 2], stream=copy_stream)   # encode i+1 once its copy has landed
                 main.wait_event(staged[i % 2])
                 lab = eng.propagate_label(stage[i % 2], output_size=(H, W))
                 consumed[i % 2].record(main)

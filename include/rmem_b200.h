@@ -179,6 +179,10 @@ int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx /*HOST, c
 int rmem_engine_pred_logits(const rmem_engine* e, int group, const float** logits4, int* h4, int* w4);
 int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel /*HOST cap 16*/, int* n, int* drop);
 long long rmem_engine_launch_count(const rmem_engine* e);
+/* Software pipelining across frames: encode the NEXT frame (aot.py:116-134, no dependency on the memory bank) on the
+ * engine's side stream while the current frame is propagated.  `img` must be ready on `stream`; the following
+ * rmem_engine_propagate must be given the same pointer (otherwise the inline encoder runs).  Bit-identical results. */
+int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream);
 /* Profiling aid: CUDA events between pipeline stages (adds a stream sync per call while on).  get_timing writes
  * "stage total_ms count" lines into buf. */
 int rmem_engine_set_timing(rmem_engine* e, int on);

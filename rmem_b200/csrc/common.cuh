@@ -1,5 +1,6 @@
 // Shared device/host helpers for the rmem_b200 kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -161,6 +162,12 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_launch_dependents();
   pdl_wait();
 }
+// Per-thread switch: the engine issues the prefetched encoder (side stream) without the attribute -- an early-launched
+// grid holds shared memory and TMEM on its SMs while it waits, which starves the stream that owns the critical path.
+inline bool& pdl_enabled() {
+  static thread_local bool on = [] { const char* e = getenv("RMEM_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args&&... args) {
@@ -171,7 +178,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -123,6 +123,42 @@ struct rmem_engine {
   // shared scratch
   t16 *img8, *c1, *x0, *x1, *t1, *t2, *ds, *feat4, *feat8, *feat16;
   float* enc_tgt;     // [HW,256] projector output
+  // Encoder outputs are double-buffered: the image encoder does not depend on the memory state, so the NEXT frame can be
+  // encoded on a side stream (rmem_engine_prefetch) while this frame's propagation / decoder / memory update run.
+  // feat4/feat8/feat16/enc_tgt above always point at the set the current frame reads.
+  t16 *feat4s[2], *feat8s[2], *feat16s[2];
+  float* enc_tgts[2];
+  int fslot = 0;
+  cudaStream_t enc_stream = nullptr;
+  cudaEvent_t ev_img_ready = nullptr, ev_inline = nullptr, ev_done[2] = {nullptr, nullptr}, ev_feat_free[2] = {nullptr, nullptr};
+  bool feat_free_valid[2] = {false, false}, inline_valid = false;
+  bool pending[2] = {false, false};        // features of pf_img[sl] are (being) produced on enc_stream, not consumed yet
+  const float* pf_img[2] = {nullptr, nullptr};
+  long long pf_seq[2] = {0, 0}, pf_counter = 0;
+  int last_enc_slot = -1;                  // last slot encoded on enc_stream (its event orders the encoder temporaries)
+  void use_slot(int sl) { fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl]; }
+  int init_streams() {
+    RMEM_CUDA_CHECK(cudaStreamCreateWithFlags(&enc_stream, cudaStreamNonBlocking));
+    RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_ready, cudaEventDisableTiming));
+    RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_inline, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+      RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_feat_free[i], cudaEventDisableTiming));
+    }
+    return RMEM_OK;
+  }
+  ~rmem_engine() {
+    if (enc_stream) {
+      cudaStreamSynchronize(enc_stream);
+      cudaStreamDestroy(enc_stream);
+    }
+    if (ev_img_ready) cudaEventDestroy(ev_img_ready);
+    if (ev_inline) cudaEventDestroy(ev_inline);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      if (ev_feat_free[i]) cudaEventDestroy(ev_feat_free[i]);
+    }
+  }
   float* res;         // [HW,512] tgt || tgt_id residual stream
   t16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
   float *qbias, *rel, *rel_dev;
@@ -199,10 +235,13 @@ struct rmem_engine {
     t1 = a.take<t16>((size_t)G.P4 * 128);
     t2 = a.take<t16>((size_t)G.P4 * 64);
     ds = a.take<t16>((size_t)G.P4 * 256);
-    feat4 = a.take<t16>((size_t)G.P4 * 256);
-    feat8 = a.take<t16>((size_t)G.P8 * 512);
-    feat16 = a.take<t16>((size_t)G.HW * 1024);
-    enc_tgt = a.take<float>((size_t)G.HW * kD);
+    for (int sl = 0; sl < 2; ++sl) {
+      feat4s[sl] = a.take<t16>((size_t)G.P4 * 256);
+      feat8s[sl] = a.take<t16>((size_t)G.P8 * 512);
+      feat16s[sl] = a.take<t16>((size_t)G.HW * 1024);
+      enc_tgts[sl] = a.take<float>((size_t)G.HW * kD);
+    }
+    use_slot(0);
     res = a.take<float>((size_t)G.HW * 2 * kD);
     t_ln = a.take<t16>((size_t)G.HW * kD);
     qt = a.take<t16>((size_t)G.HW * kDk);
@@ -353,7 +392,34 @@ struct rmem_engine {
     return RMEM_OK;
   }
 
-  int encode(const float* img, cudaStream_t s) {
+  // Features of `img`: taken from a prefetch when one is outstanding for exactly this pointer, else encoded inline.
+  int features(const float* img, cudaStream_t s) {
+    for (int sl = 0; sl < 2; ++sl)
+      if (pending[sl] && pf_img[sl] == img) {
+        RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_done[sl], 0));
+        pending[sl] = false;
+        use_slot(sl);
+        return RMEM_OK;
+      }
+    // inline: the encoder's temporaries are shared with the side stream -> order after whatever is queued there; the
+    // current slot's readers were all issued on this stream before, so it can be overwritten in stream order
+    if (last_enc_slot >= 0) RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_done[last_enc_slot], 0));
+    // a pending entry may be the NEXT frame (prefetch issued before this call): keep it, encode into the other slot
+    const int sl = pending[fslot] ? (fslot ^ 1) : fslot;
+    pending[sl] = false;
+    use_slot(sl);
+    RMEM_TRY(encode_into(img, s, sl));
+    RMEM_CUDA_CHECK(cudaEventRecord(ev_inline, s));
+    inline_valid = true;
+    return RMEM_OK;
+  }
+  int release_features(cudaStream_t s) {     // every reader of the current feature set has been issued on s
+    RMEM_CUDA_CHECK(cudaEventRecord(ev_feat_free[fslot], s));
+    feat_free_valid[fslot] = true;
+    return RMEM_OK;
+  }
+
+  int encode_into(const float* img, cudaStream_t s, int sl) {
     const Geo& G = g;
     mark("begin", s);
     RMEM_TRY(pack_image(img, img8, G.H, G.W, s));
@@ -363,7 +429,7 @@ struct rmem_engine {
     t16* cur = x0;
     int Hc = G.H4, Wc = G.W4, Cc = 64;
     const int planes[3] = {64, 128, 256}, nblk[3] = {3, 4, 6}, strides[3] = {1, 2, 2};
-    t16* feats[3] = {feat4, feat8, feat16};
+    t16* feats[3] = {feat4s[sl], feat8s[sl], feat16s[sl]};
     for (int li = 0; li < 3; ++li) {
       for (int bi = 0; bi < nblk[li]; ++bi) {
         int st = bi == 0 ? strides[li] : 1;
@@ -377,8 +443,8 @@ struct rmem_engine {
       mark(li == 0 ? "enc.layer1" : (li == 1 ? "enc.layer2" : "enc.layer3"), s);
     }
     Lin p;
-    p.A = feat16; p.lda = 1024; p.M = G.HW; p.K = 1024; p.N = kD; p.w = "proj";
-    p.C = enc_tgt; p.ldc = kD; p.c_fp32 = 1;
+    p.A = feat16s[sl]; p.lda = 1024; p.M = G.HW; p.K = 1024; p.N = kD; p.w = "proj";
+    p.C = enc_tgts[sl]; p.ldc = kD; p.c_fp32 = 1;
     RMEM_TRY(linear(p, s));
     mark("enc.proj", s);
     return RMEM_OK;
@@ -925,6 +991,8 @@ int rmem_engine_create(const rmem_engine_config* cfg, const void* weight_blob, c
     delete e;
     return RMEM_ERR_CUDA;
   }
+  rc = e->init_streams();
+  if (rc) { delete e; return rc; }
   e->launches0 = launch_counter();
   *out = e;
   return RMEM_OK;
@@ -935,6 +1003,7 @@ void rmem_engine_destroy(rmem_engine* e) { delete e; }
 int rmem_engine_restart(rmem_engine* e) {
   RMEM_REQUIRE(e, "null engine");
   e->n_groups = 0;
+  e->pending[0] = e->pending[1] = false;
   for (auto& gr : e->groups) {
     gr.slots.clear(); gr.free_slots.clear(); gr.long_idx.clear(); gr.ema.clear(); gr.times.clear();
     gr.frame_step = 0; gr.last_mem_step = -1; gr.has_ref = false; gr.parity = 0; gr.mass_T = 0;
@@ -961,7 +1030,7 @@ int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void
   if (frame_step < 0) frame_step = 0;
   // zero the bank/state region once per clip (pad columns of the value-major bank must stay finite)
   RMEM_CUDA_CHECK(cudaMemsetAsync(e->arena_base + e->state_begin, 0, e->state_bytes, s));
-  RMEM_TRY(e->encode(img, s));
+  RMEM_TRY(e->features(img, s));
   for (int gi = 0; gi < e->n_groups; ++gi) {
     Group& gr = e->groups[gi];
     RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/0, s));
@@ -975,7 +1044,7 @@ int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void
     gr.long_idx.push_back(gr.frame_step);
     gr.has_ref = true;
   }
-  return RMEM_OK;
+  return e->release_features(s);
 }
 
 int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, float* out_logits, uint8_t* out_label,
@@ -983,7 +1052,7 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
   RMEM_REQUIRE(e && img, "null argument");
   RMEM_REQUIRE(e->n_groups >= 1 && e->groups[0].has_ref, "propagate before add_reference_frame");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  RMEM_TRY(e->encode(img, s));
+  RMEM_TRY(e->features(img, s));
   const float* lg[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int gi = 0; gi < e->n_groups; ++gi) {
     Group& gr = e->groups[gi];
@@ -995,6 +1064,34 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
     RMEM_TRY(mask_head(lg, e->n_groups, e->g.H4, e->g.W4, Ho, Wo, out_logits, out_label, s));
   e->mark("mask_head", s);
   e->flush_marks(s);
+  return e->release_features(s);            // the feature set of this frame may be overwritten from here on
+}
+
+// Encode the NEXT frame on the engine's side stream while the current frame is still being propagated (the encoder has
+// no dependency on the memory bank; aot.py:116-134 is a pure function of the image).  `img` must be ready on `stream`
+// and stay untouched until the rmem_engine_propagate call that consumes it has been issued; that call must pass the
+// same pointer (anything else falls back to the inline encoder).  Results are bit-identical to the unprefetched path.
+int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream) {
+  RMEM_REQUIRE(e && img, "null argument");
+  if (e->timing) return RMEM_OK;            // stage timing serialises the frame; keep it on one stream
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // the slot that does not hold an unconsumed prefetch; the current slot's readers have all been issued
+  int sl = e->pending[e->fslot ^ 1] ? e->fslot : (e->fslot ^ 1);
+  if (e->pending[sl]) sl = e->pf_seq[0] < e->pf_seq[1] ? 0 : 1;   // both unconsumed: the older one is stale, replace it
+  RMEM_CUDA_CHECK(cudaEventRecord(e->ev_img_ready, s));
+  RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_img_ready, 0));
+  if (e->feat_free_valid[sl]) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_feat_free[sl], 0));
+  if (e->inline_valid) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_inline, 0));
+  const bool pdl_was = pdl_enabled();
+  pdl_enabled() = false;                    // see common.cuh: no early-launched grids on the side stream
+  const int rc = e->encode_into(img, e->enc_stream, sl);
+  pdl_enabled() = pdl_was;
+  if (rc) return rc;
+  RMEM_CUDA_CHECK(cudaEventRecord(e->ev_done[sl], e->enc_stream));
+  e->pending[sl] = true;
+  e->pf_img[sl] = img;
+  e->pf_seq[sl] = ++e->pf_counter;
+  e->last_enc_slot = sl;
   return RMEM_OK;
 }
 

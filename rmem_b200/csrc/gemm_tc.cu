@@ -425,7 +425,7 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (S > 1) {

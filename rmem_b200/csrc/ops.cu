@@ -193,10 +193,11 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
 
 // ------------------------------------------------------------------------------------------------
 // 5x5 depthwise convolution, NHWC.  One thread owns a channel pair and slides a 5x5 register window along a strip of
-// DW_SL output pixels of one row: each new output costs 5 loads (the entering column) instead of 25, the 25 weight
+// DW_SL output pixels of one row: the strip's 5 x (DW_SL + 4) inputs are loaded once (up front, in one round trip) and
+// shared by its outputs instead of 25 loads per output, the 25 weight
 // pairs live in registers (fetched before the PDL wait: they are not produced by the preceding kernel), and a warp
 // covers 64 consecutive channels, so every access is one 128-byte line.  fp32 accumulation in (ky, kx) order.
-constexpr int DW_SL = 9;
+constexpr int DW_SL = 6;
 __global__ void __launch_bounds__(128) dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w,
                                                       t16* __restrict__ y, int h, int wd, int C) {
   const int cp = C / 2;
@@ -219,24 +220,26 @@ __global__ void __launch_bounds__(128) dwconv5_kernel(const t16* __restrict__ x,
       col[ky] = ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)wd) ? xin[((size_t)iy * wd + ix) * cp] : 0u;
     }
   };
-  uint32_t win[5][5];                                     // [kx][ky]: columns x-2 .. x+2 of the current output
+  // every input the strip needs, issued up front (one round trip instead of one per output): columns
+  // x_begin-2 .. x_begin+DW_SL+1, five rows each, converted to fp32 once
+  float2 win[DW_SL + 4][5];
 #pragma unroll
-  for (int kx = 1; kx < 5; ++kx) load_col(x_begin + kx - 3, win[kx]);
+  for (int j = 0; j < DW_SL + 4; ++j) {
+    uint32_t col[5];
+    load_col(x_begin + j - 2, col);
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) win[j][ky] = unpack2(col[ky]);
+  }
 #pragma unroll
   for (int px = 0; px < DW_SL; ++px) {
     const int ox = x_begin + px;
     if (ox >= wd) break;
-#pragma unroll
-    for (int kx = 0; kx < 4; ++kx)
-#pragma unroll
-      for (int ky = 0; ky < 5; ++ky) win[kx][ky] = win[kx + 1][ky];
-    load_col(ox + 2, win[4]);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
-        const float2 v = unpack2(win[kx][ky]);
+        const float2 v = win[px + kx][ky];
         a0 = fmaf(v.x, wt[ky * 5 + kx].x, a0);
         a1 = fmaf(v.y, wt[ky * 5 + kx].y, a1);
       }

@@ -223,6 +223,17 @@ class DeAOTInferEngine:
                                               _capi.stream_ptr()))
         return label
 
+    def prefetch(self, img: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """Encode the NEXT frame on the engine's side stream while the current one is propagated (the image encoder,
+        aot.py:116-134, does not depend on the memory bank).  `img` must be a contiguous fp32 CUDA tensor that is ready
+        on `stream` (default: the current stream) and is passed unchanged to the next match_propogate_one_frame /
+        propagate_label call.  Optional: results are bit-identical without it."""
+        if self._h is None:
+            return
+        assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous(), "prefetch needs the engine-ready tensor"
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else _capi.stream_ptr()
+        _capi.check(_capi.load().rmem_engine_prefetch(self._h, _capi.ptr(img), sp))
+
     def update_memory(self, label: torch.Tensor):
         """aot_engine.py:714-720 -> AOTEngine.update_short_term_memory (:327-396)."""
         lib = _capi.load()

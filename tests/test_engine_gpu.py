@@ -103,3 +103,46 @@ def test_engine_restart_is_deterministic(cuda_device):
     for a, b in zip(rec1["labels"], rec2["labels"]):
         assert torch.equal(a, b)
     assert eng.launch_count > 0
+
+
+def _free_run(eng, frames_dev, label0, n_obj, gap, mode):
+    """Self-fed clip (engine's own labels).  mode: None = no prefetch, 'before' = prefetch(i+1) issued before
+    propagate(i), 'after' = issued after it, 'wrong' = prefetch of a frame that is not the next one."""
+    eng.restart_engine()
+    eng.long_term_mem_gap = gap
+    eng.add_reference_frame(frames_dev[0:1], label0, obj_nums=[n_obj], frame_step=0)
+    n = frames_dev.shape[0]
+    labs, idx = [], []
+    for f in range(1, n):
+        nxt = frames_dev[f + 1:f + 2] if f + 1 < n else None
+        if mode == "before" and nxt is not None:
+            eng.prefetch(nxt)
+        if mode == "wrong":
+            eng.prefetch(frames_dev[0:1])
+        lab = eng.propagate_label(frames_dev[f:f + 1])
+        if mode == "after" and nxt is not None:
+            eng.prefetch(nxt)
+        eng.update_memory(lab)
+        labs.append(lab.clone())
+        idx.append(list(eng.aot_engines[0].long_memories_indexes))
+    torch.cuda.synchronize()
+    return torch.cat(labs), idx
+
+
+@pytest.mark.parametrize("model", ["r50_deaotl", "r50_aotl"])
+def test_prefetched_encoder_is_bit_identical(cuda_device, model):
+    """rmem_engine_prefetch only moves the encoder of the next frame onto a side stream: labels (integer, exact) and the
+    eviction index sequence must not change, whatever the call order, and a prefetch of the wrong frame is ignored."""
+    from rmem_b200.engine import RmemModel, RmemConfig, build_engine
+    H, W, n_obj = 257, 321, 3
+    sd = O.make_state_dict(model, seed=3, sharpen=4.0)
+    frames = O.synthetic_frames(12, H, W, seed=11).to(cuda_device)
+    label0 = O.synthetic_label(H, W, n_obj).int().to(cuda_device)
+    cfg = RmemConfig(model=model, former_mem_len=1, latter_mem_len=2)
+    eng = build_engine("deaotengine" if model == "r50_deaotl" else "aotengine", phase="eval",
+                       aot_model=RmemModel(sd, cfg, cuda_device), gpu_id=0, long_term_mem_gap=2)
+    base, idx0 = _free_run(eng, frames, label0, n_obj, 2, None)
+    for mode in ("before", "after", "wrong", "before"):
+        labs, idx = _free_run(eng, frames, label0, n_obj, 2, mode)
+        assert torch.equal(labs, base), mode
+        assert idx == idx0, mode
