@@ -1083,7 +1083,10 @@ int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream) {
   if (e->feat_free_valid[sl]) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_feat_free[sl], 0));
   if (e->inline_valid) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_inline, 0));
   const bool pdl_was = pdl_enabled();
-  pdl_enabled() = false;                    // see common.cuh: no early-launched grids on the side stream
+  {
+    static const bool side_pdl = [] { const char* e = getenv("RMEM_SIDE_PDL"); return e && e[0] == '1'; }();
+    pdl_enabled() = side_pdl && pdl_was;    // see common.cuh: no early-launched grids on the side stream
+  }
   const int rc = e->encode_into(img, e->enc_stream, sl);
   pdl_enabled() = pdl_was;
   if (rc) return rc;

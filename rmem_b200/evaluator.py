@@ -209,25 +209,38 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         os.makedirs(os.path.join(out_dir, dataset.seq_name), exist_ok=True)
     use_cuda = device is not None and torch.device(device).type == "cuda"
     writers = []
+    timers = []
     now = timer or time.perf_counter
-    for frame_idx in range(len(dataset)):
-        sample = dataset[frame_idx]
-        meta = sample["meta"]
-        img = sample["current_img"]
-        label = sample.get("current_label")
+    def fetch(i):
+        smp = dataset[i]
+        im, lb = smp["current_img"], smp.get("current_label")
         if device is not None:
-            img = img.to(device, non_blocking=True)
-            label = label.to(device, non_blocking=True) if label is not None else None
-        label = label.float() if label is not None else None
+            im = im.to(device, non_blocking=True).contiguous()
+            lb = lb.to(device, non_blocking=True) if lb is not None else None
+        return smp["meta"], im, (lb.float() if lb is not None else None)
+
+    can_prefetch = use_cuda and hasattr(engine, "prefetch")
+    nxt = fetch(0)
+    for frame_idx in range(len(dataset)):
+        meta, img, label = nxt
+        nxt = fetch(frame_idx + 1) if frame_idx + 1 < len(dataset) else None
+        # frames are known ahead of time: the next one is encoded on the engine's side stream while this one propagates
+        # (same-size frames only -- a size change rebuilds the engine)
+        if can_prefetch and frame_idx >= 1 and nxt is not None and nxt[1].shape == img.shape:
+            engine.prefetch(nxt[1])
         if frame_idx == 0:
             if label is None:
                 raise ValueError(f"{dataset.seq_name}: the first frame has no label")
             ref = F.interpolate(label, size=img.shape[2:], mode="nearest").int()
             engine.add_reference_frame(img, ref, obj_nums=[int(meta["obj_num"])], frame_step=0)
             continue
+        # per-frame timing like the reference (evaluator.py:399-404, 525-527): CUDA events around propagate + update,
+        # read after the clip -- no device-wide sync inside the loop, so the prefetched encoder really overlaps
         if use_cuda:
-            torch.cuda.synchronize()
-        t0 = now()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        else:
+            t0 = now()
         out_size = (int(meta["height"]), int(meta["width"]))
         logit = engine.match_propogate_one_frame(img, output_size=out_size)
         prob = torch.softmax(logit, dim=1)
@@ -242,8 +255,10 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
             cur = F.interpolate(pred, size=engine.input_size_2d, mode="nearest")
             engine.update_memory(cur)
         if use_cuda:
-            torch.cuda.synchronize()
-        res.seconds += now() - t0
+            ev1.record()
+            timers.append((ev0, ev1))
+        else:
+            res.seconds += now() - t0
         res.frames += 1
         lab8 = pred[0, 0].to(torch.uint8).cpu()
         if on_frame is not None:
@@ -254,6 +269,9 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
             path = os.path.join(out_dir, dataset.seq_name, os.path.splitext(meta["current_name"])[0] + ".png")
             writers.append(save_mask(lab8.numpy(), path, meta["obj_idx"]))
             res.paths.append(path)
+    if timers:
+        torch.cuda.synchronize()
+        res.seconds += sum(a.elapsed_time(b) for a, b in timers) / 1e3
     for t in writers:
         if t is not None:
             t.join()

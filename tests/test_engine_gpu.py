@@ -146,3 +146,38 @@ def test_prefetched_encoder_is_bit_identical(cuda_device, model):
         labs, idx = _free_run(eng, frames, label0, n_obj, 2, mode)
         assert torch.equal(labs, base), mode
         assert idx == idx0, mode
+
+
+def test_evaluator_shell_cuda_engine_vs_oracle_engine(cuda_device, tmp_path):
+    """The same clip directory through rmem_b200.evaluator with the CUDA engine and with the CPU oracle engine: decoded
+    frames, resize rule, reference frame, propagate / update loop, new-object re-reference and the PNG writer are shared;
+    only the engine differs.  Free-running (each engine feeds on its own labels), so a few near-tie pixels may differ."""
+    import cv2
+    from PIL import Image
+    from rmem_b200 import evaluator as E
+    from rmem_b200.engine import RmemModel, RmemConfig, build_engine
+    rng = np.random.RandomState(0)
+    H, W = 97, 129
+    img_dir, lab_dir = tmp_path / "JPEGImages" / "c", tmp_path / "Annotations" / "c"
+    os.makedirs(img_dir), os.makedirs(lab_dir)
+    base = cv2.GaussianBlur(rng.randint(0, 255, (H, W, 3)).astype(np.uint8), (0, 0), 3)
+    for f in range(5):
+        cv2.imwrite(str(img_dir / f"{f:05d}.png"), np.roll(base, 2 * f, axis=1))
+    l0 = np.zeros((H, W), np.uint8); l0[20:60, 20:70] = 4
+    Image.fromarray(l0).save(lab_dir / "00000.png")
+    l2 = np.zeros((H, W), np.uint8); l2[60:90, 80:120] = 9
+    Image.fromarray(l2).save(lab_dir / "00002.png")
+    ds = E.ClipDataset(str(img_dir), str(lab_dir))
+    sd = O.make_state_dict("r50_deaotl", seed=5, sharpen=4.0)
+    eng = build_engine("deaotengine", phase="eval",
+                       aot_model=RmemModel(sd, RmemConfig(model="r50_deaotl", former_mem_len=1, latter_mem_len=2),
+                                           cuda_device), gpu_id=0)
+    ours = E.evaluate_clip(eng, ds, out_dir=str(tmp_path / "ours"), device=cuda_device, keep_labels=True)
+    with torch.no_grad():
+        ref = E.evaluate_clip(O.OracleEngine(sd, O.OracleConfig(model="r50_deaotl", former_mem_len=1, latter_mem_len=2)),
+                              ds, keep_labels=True)
+    assert ours.frames == ref.frames == 4 and ours.seconds > 0
+    agree = np.mean([float((a == b).float().mean()) for a, b in zip(ours.labels, ref.labels)])
+    assert agree >= 0.97, agree
+    out2 = np.array(Image.open(ours.paths[1]))                   # frame 2: dataset ids, new object pasted in
+    assert (out2[60:90, 80:120] == 9).all() and set(np.unique(out2)) <= {0, 4, 9}
