@@ -129,6 +129,22 @@ struct rmem_engine {
   t16 *feat4s[2], *feat8s[2], *feat16s[2];
   float* enc_tgts[2];
   int fslot = 0;
+  // Independent GEMMs of one layer (U / ID_U next to QV, the self-attention projections, the three linear_ID_V of the
+  // memory update) are forked onto a second engine-owned stream: each is a ~3 us kernel behind ~5 us of launch latency.
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool use_aux() const { return aux_stream != nullptr && !timing && aux_on; }
+  bool aux_on = true;
+  int fork(cudaStream_t s) {
+    RMEM_CUDA_CHECK(cudaEventRecord(ev_fork, s));
+    RMEM_CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+    return RMEM_OK;
+  }
+  int join(cudaStream_t s) {
+    RMEM_CUDA_CHECK(cudaEventRecord(ev_join, aux_stream));
+    RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
+    return RMEM_OK;
+  }
   cudaStream_t enc_stream = nullptr;
   cudaEvent_t ev_img_ready = nullptr, ev_inline = nullptr, ev_done[2] = {nullptr, nullptr}, ev_feat_free[2] = {nullptr, nullptr};
   bool feat_free_valid[2] = {false, false}, inline_valid = false;
@@ -139,6 +155,10 @@ struct rmem_engine {
   void use_slot(int sl) { fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl]; }
   int init_streams() {
     RMEM_CUDA_CHECK(cudaStreamCreateWithFlags(&enc_stream, cudaStreamNonBlocking));
+    RMEM_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    { const char* e = getenv("RMEM_AUX_STREAM"); aux_on = !(e && e[0] == '0'); }
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_ready, cudaEventDisableTiming));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_inline, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
@@ -152,6 +172,12 @@ struct rmem_engine {
       cudaStreamSynchronize(enc_stream);
       cudaStreamDestroy(enc_stream);
     }
+    if (aux_stream) {
+      cudaStreamSynchronize(aux_stream);
+      cudaStreamDestroy(aux_stream);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     if (ev_img_ready) cudaEventDestroy(ev_img_ready);
     if (ev_inline) cudaEventDestroy(ev_inline);
     for (int i = 0; i < 2; ++i) {
@@ -536,23 +562,27 @@ struct rmem_engine {
       RMEM_TRY(linear(p, s));
     }
     t16* gate = (l == 0) ? cu0 : cu;
+    const bool par = use_aux();
+    cudaStream_t s2 = par ? aux_stream : s;          // U and ID_U do not depend on QV: second stream
+    if (par) RMEM_TRY(fork(s));
     {
       Lin p;
       p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_U";
       p.act = ACT_SILU; p.C = gate; p.ldc = kDv;
-      RMEM_TRY(linear(p, s));
+      RMEM_TRY(linear(p, s2));
     }
     if (l > 0) {
       const float* g1 = Wt<float>(pre + ".id_norm1.g", kD, &rc);
       const float* b1 = Wt<float>(pre + ".id_norm1.b", kD, &rc);
       if (rc) return rc;
       // ti = id_LN1(tgt_id) -> curr_ID_V (first half of the linear_ID_V input), also A of linear_ID_U
-      RMEM_TRY(layernorm(res + kD, 2 * kD, g1, b1, L.cat, 2 * kD, nullptr, 0, G.HW, kD, s));
+      RMEM_TRY(layernorm(res + kD, 2 * kD, g1, b1, L.cat, 2 * kD, nullptr, 0, G.HW, kD, s2));
       Lin p;
       p.A = L.cat; p.lda = 2 * kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_ID_U";
       p.act = ACT_SILU; p.C = gate + 512; p.ldc = kDv;
-      RMEM_TRY(linear(p, s));
+      RMEM_TRY(linear(p, s2));
     }
+    if (par) RMEM_TRY(join(s));
 
     mark("gpm.proj_in", s);
     // memories
@@ -622,6 +652,7 @@ struct rmem_engine {
       Lin p;
       p.A = z; p.lda = 2 * kD; p.M = G.HW; p.K = 2 * kD; p.N = kDk; p.w = pre + ".self.linear_QK";
       p.C = qk; p.ldc = kDk;
+      if (par) RMEM_TRY(fork(s));                    // U1 / U2 on the second stream, QK and the two V^T on this one
       RMEM_TRY(linear(p, s));
       for (int half = 0; half < 2; ++half) {
         // v^T = silu(W_V . z_half^T + b): computed directly value-major (bias along M)
@@ -639,8 +670,9 @@ struct rmem_engine {
         u.A = z + half * kD; u.lda = 2 * kD; u.M = G.HW; u.K = kD; u.N = 2 * kD;
         u.w = pre + ".self.linear_U" + std::to_string(half + 1);
         u.act = ACT_SILU; u.C = u_self + half * 2 * kD; u.ldc = kDv;
-        RMEM_TRY(linear(u, s));
+        RMEM_TRY(linear(u, s2));
       }
+      if (par) RMEM_TRY(join(s));
       LongAttnArgs sa;
       sa.HW = G.HW; sa.HWp = G.HWp; sa.Dk = kDk; sa.Dv = kDv; sa.scale = scale;
       sa.qt = qk; sa.kbank = qk; sa.vtbank = vt_self; sa.nslots = 1; sa.T = 1; sa.slot[0] = 0;
@@ -1114,7 +1146,10 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
     if (e->cfg.model == 1) {
       RMEM_TRY(e->aot_refresh(gr, s));                                     // transformer.py:269-304
     } else {
-      for (int l = 0; l < kLayers; ++l) RMEM_TRY(e->fuse_id(gr, l, s));    // transformer.py:826-857
+      const bool par = e->use_aux();                                       // three independent GEMMs: alternate streams
+      if (par) RMEM_TRY(e->fork(s));
+      for (int l = 0; l < kLayers; ++l) RMEM_TRY(e->fuse_id(gr, l, (par && l == 1) ? e->aux_stream : s));
+      if (par) RMEM_TRY(e->join(s));                                       // transformer.py:826-857
     }
     if (is_long) {
       RMEM_TRY(e->cfg.model == 1 ? e->append_long_aot(gr, s) : e->append_long(gr, s));
