@@ -647,8 +647,7 @@ struct rmem_engine {
       const float* gi2 = Wt<float>(pre + ".id_norm2.g", kD, &rc);
       const float* bi2 = Wt<float>(pre + ".id_norm2.b", kD, &rc);
       if (rc) return rc;
-      RMEM_TRY(layernorm(res, 2 * kD, g2, b2, z, 2 * kD, nullptr, 0, G.HW, kD, s));
-      RMEM_TRY(layernorm(res + kD, 2 * kD, gi2, bi2, z + kD, 2 * kD, nullptr, 0, G.HW, kD, s));
+      RMEM_TRY(layernorm_pair(res, 2 * kD, g2, b2, gi2, bi2, z, 2 * kD, G.HW, kD, s));
       Lin p;
       p.A = z; p.lda = 2 * kD; p.M = G.HW; p.K = 2 * kD; p.N = kDk; p.w = pre + ".self.linear_QK";
       p.C = qk; p.ldc = kDk;

@@ -88,6 +88,39 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
     }
 }
 
+// Two LayerNorms over the two C-wide halves of one [P, 2C] row (norm2 on tgt, id_norm2 on tgt_id, transformer.py:1222)
+// in one launch: warp -> (row, half).
+__global__ void layernorm_pair_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g0,
+                                      const float* __restrict__ b0, const float* __restrict__ g1,
+                                      const float* __restrict__ b1, t16* __restrict__ y, long long ldy, int P, int C) {
+  pdl_prologue();
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int row = w >> 1, half = w & 1;
+  if (row >= P) return;
+  const float* xr = x + (long long)row * ldx + half * C;
+  const float* gamma = half ? g1 : g0;
+  const float* beta = half ? b1 : b0;
+  float v[LN_MAXV];
+  const int nv = C / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) { v[j] = xr[j * 32 + lane]; s += v[j]; }
+  float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) { float d = v[j] - mean; q += d * d; }
+  float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+    if (j < nv) {
+      int c = j * 32 + lane;
+      y[(long long)row * ldy + half * C + c] = f2t((v[j] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm: stats (double atomics) + apply.
 template <typename T>
@@ -138,10 +171,20 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, do
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (threadIdx.x < 2 * G) {
-      double a = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) a += partials[(size_t)b * 2 * G + threadIdx.x];
-      stats[threadIdx.x] = a;
+    // fold the per-block partials with the whole block: thread -> (output o, slice j); slice j adds blocks j, j+J, ...
+    // in order, then the J slices are added in order -- still a fixed summation order, ~16x shorter serial chain
+    __shared__ double sh_d[256];
+    const int n_out = 2 * G, J = blockDim.x / n_out;
+    const int o = threadIdx.x % n_out, j = threadIdx.x / n_out;
+    double a = 0.0;
+    if (j < J)
+      for (unsigned b = j; b < gridDim.x; b += J) a += partials[(size_t)b * n_out + o];
+    sh_d[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < n_out) {
+      double t = 0.0;
+      for (int jj = 0; jj < J; ++jj) t += sh_d[jj * n_out + threadIdx.x];
+      stats[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *counter = 0u;   // re-arm for the next call on this stream
   }
@@ -182,7 +225,7 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
                "groupnorm: unsupported C=%d G=%d", C, G);
   // scratch layout (doubles): [0,64) stats | [64] counter (zero-initialised once, self re-arming) | [72,..) partials
   int rows_per_block = 256 / (C / 8);
-  int grid = min(cdiv(P, rows_per_block * 4), kGnMaxBlocks);
+  int grid = min(cdiv(P, rows_per_block), kGnMaxBlocks);     // one row group per block until the grid cap: parallelism first
   RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<T>, dim3(grid), dim3(256), 0, s, x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
   RMEM_LAUNCH_CHECK();
   long long nvec = (long long)P * (C / 8);
@@ -735,6 +778,14 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
               long long ldy2, int P, int C, cudaStream_t s, const float* add2) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm: unsupported C=%d", C);
   RMEM_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, x, ldx, gamma, beta, y, ldy, y2, ldy2, add2, P, C));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int layernorm_pair(const float* x, long long ldx, const float* g0, const float* b0, const float* g1, const float* b1,
+                   t16* y, long long ldy, int P, int C, cudaStream_t s) {
+  RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm_pair: unsupported C=%d", C);
+  RMEM_CUDA_CHECK(launch_pdl(layernorm_pair_kernel, dim3(cdiv(2 * P, 8)), dim3(256), 0, s, x, ldx, g0, b0, g1, b1, y, ldy, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
