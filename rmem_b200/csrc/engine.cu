@@ -134,7 +134,7 @@ struct rmem_engine {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_aux() const { return aux_stream != nullptr && !timing && aux_on; }
-  bool aux_on = true;
+  bool aux_on = true, branch_par = true;
   int fork(cudaStream_t s) {
     RMEM_CUDA_CHECK(cudaEventRecord(ev_fork, s));
     RMEM_CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
@@ -159,6 +159,7 @@ struct rmem_engine {
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     { const char* e = getenv("RMEM_AUX_STREAM"); aux_on = !(e && e[0] == '0'); }
+    { const char* e = getenv("RMEM_BRANCH_PAR"); branch_par = !(e && e[0] == '0'); }
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_ready, cudaEventDisableTiming));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_inline, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
@@ -186,6 +187,7 @@ struct rmem_engine {
     }
   }
   float* res;         // [HW,512] tgt || tgt_id residual stream
+  t16 *attn_b, *dwo_b;
   t16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
   float *qbias, *rel, *rel_dev;
   t16 *d0, *d1, *d2;
@@ -275,6 +277,8 @@ struct rmem_engine {
     cu0 = a.take<t16>((size_t)G.HW * kDv);
     attn_a = a.take<t16>((size_t)G.HW * kDv);
     dwo = a.take<t16>((size_t)G.HW * kDv);
+    attn_b = a.take<t16>((size_t)G.HW * kDv);     // short-term branch's own pair (it runs beside the long-term branch)
+    dwo_b = a.take<t16>((size_t)G.HW * kDv);
     z = a.take<t16>((size_t)G.HW * 2 * kD);
     qk = a.take<t16>((size_t)G.HWp * kDk);
     vt_self = a.take<t16>((size_t)kDv * G.HWp);
@@ -528,13 +532,20 @@ struct rmem_engine {
 
   // gated epilogue tail: DWConv5x5 -> Linear(1024->512) accumulated into the tgt || tgt_id residual stream
   int gated_tail(const std::string& pre, cudaStream_t s) {
+    RMEM_TRY(gated_tail_dw(pre, attn_a, dwo, s));
+    return gated_tail_proj(pre, dwo, s);
+  }
+  int gated_tail_dw(const std::string& pre, const t16* in, t16* out, cudaStream_t s) {
     const Geo& G = g;
     int rc = RMEM_OK;
     const float* dw = Wt<float>(pre + ".dw", (size_t)25 * kDv, &rc);
     if (rc) return rc;
-    RMEM_TRY(dwconv5x5(attn_a, dw, dwo, G.h, G.w, kDv, s));
+    return dwconv5x5(in, dw, out, G.h, G.w, kDv, s);
+  }
+  int gated_tail_proj(const std::string& pre, const t16* in, cudaStream_t s) {   // res += proj(in): fp32 read-modify-write
+    const Geo& G = g;
     Lin p;
-    p.A = dwo; p.lda = kDv; p.M = G.HW; p.K = kDv; p.N = 2 * kD; p.w = pre + ".proj";
+    p.A = in; p.lda = kDv; p.M = G.HW; p.K = kDv; p.N = 2 * kD; p.w = pre + ".proj";
     p.C = res; p.ldc = 2 * kD; p.c_fp32 = 1; p.accumulate = 1;
     return linear(p, s);
   }
@@ -617,28 +628,40 @@ struct rmem_engine {
     a.mass = (l == 0 && !ref_mode) ? gr.mass0 : nullptr;
     if (a.mass) gr.mass_T = T;
     mark("gpm.long.prep", s);
-    RMEM_TRY(attention(a, s));
-    mark("gpm.long.attn", s);
-    RMEM_TRY(gated_tail(pre + ".long", s));
-    mark("gpm.long.tail", s);
-
-    // short-term windowed attention over the previous frame
-    {
+    // The short-term branch (relative-bias GEMM, windowed attention, depthwise conv) does not depend on the long-term one:
+    // it runs on the second stream into its own buffers; only its final projection (an fp32 accumulate into the
+    // residual stream, like the long-term one) is issued after the join, in the reference's order.
+    const bool par2 = par && branch_par;
+    cudaStream_t sb = par2 ? aux_stream : s;
+    t16* sh_attn = par2 ? attn_b : attn_a;
+    t16* sh_dwo = par2 ? dwo_b : dwo;
+    auto short_branch = [&]() -> int {
       Lin p;
       p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
       // the tensor-core kernel reads one aligned 16-float line per window row (".short.rel16": rows re-ordered at pack time)
       p.w = pre + (cfg.attn_impl == RMEM_ATTN_DENSE ? ".short.rel" : ".short.rel16"); p.C = rel; p.ldc = 256; p.c_fp32 = 1;
-      RMEM_TRY(linear(p, s));
-      mark("gpm.short.rel", s);
+      RMEM_TRY(linear(p, sb));
+      mark("gpm.short.rel", sb);
       if (cfg.attn_impl == RMEM_ATTN_DENSE)
-        RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, attn_a, kDv, G.h, G.w, kDv, scale, s));
+        RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, sh_attn, kDv, G.h, G.w, kDv, scale, sb));
       else
-        RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, 16, gate, kDv, attn_a, kDv, G.h, G.w, kDv,
-                               scale, local_ws, local_ws_bytes, s));
-      mark("gpm.short.attn", s);
-      RMEM_TRY(gated_tail(pre + ".short", s));
-      mark("gpm.short.tail", s);
+        RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, 16, gate, kDv, sh_attn, kDv, G.h, G.w, kDv,
+                               scale, local_ws, local_ws_bytes, sb));
+      mark("gpm.short.attn", sb);
+      return gated_tail_dw(pre + ".short", sh_attn, sh_dwo, sb);
+    };
+    if (par2) {
+      RMEM_TRY(fork(s));
+      RMEM_TRY(short_branch());
     }
+    RMEM_TRY(attention(a, s));
+    mark("gpm.long.attn", s);
+    RMEM_TRY(gated_tail(pre + ".long", s));
+    mark("gpm.long.tail", s);
+    if (par2) RMEM_TRY(join(s));
+    else RMEM_TRY(short_branch());
+    RMEM_TRY(gated_tail_proj(pre + ".short", sh_dwo, s));
+    mark("gpm.short.tail", s);
 
     // self attention on cat(LN2(tgt), id_LN2(tgt_id))
     {
