@@ -75,6 +75,13 @@ struct Tc2Params {
   t16* part_o;                 // [nCTA][2][BM][DVC]     normalised partial O
   float* part_ml;              // [nCTA][2][BM][2]       (m in log2 units, l)
   float* pieces;               // [nCTA][2][T][2][BM][2] per-frame (m, l) of each softmax group (Dv chunk 0 units) or null
+  // direct mode (one CTA = one whole unit, e.g. the T = 1 self-attention): the kernel normalises, gates and writes the
+  // final rows itself; no partials, no combine launch
+  int direct;
+  const t16* gate;
+  long long ldg;
+  t16* out;
+  long long ldo;
 };
 
 // D[tmem] (+)= A[tmem] . B[smem]^T   (A = P as packed fp16 pairs, one TMEM lane per row)
@@ -508,6 +515,43 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
       mbar_wait(&sp_free[last % NSB], (last / NSB) & 1, nullptr, 12);
       fence_after();
       if (quad == 0 && grp == 0 && trace && lane == 0) trace[(long long)(j - 1) * 16 + 13] = clock64();
+      if (p.direct) {
+        // Whole unit in this CTA: out = O / l * gate, written here.  Every MMA has retired and every TMA tile has been
+        // consumed, so the K/V rings are free: each warp stages its 32 rows x 128 columns there (fp32) and writes two
+        // rows per instruction (16 lanes x 16 bytes per row = whole lines), the gate read the same way.
+        constexpr int ROWP = (DVC / 2) * 4 + 16;
+        static_assert(kSoftmaxWarps * 32 * ROWP <= KS * SMEM_K + VS * SMEM_V, "staging fits in the rings");
+        unsigned char* stg = smem + OFF_K + warp * (32 * ROWP);
+#pragma unroll 1
+        for (int c = 0; c < DVC / 2; c += 32) {
+          float o[32];
+          tmem_ld32(lane_addr + TMEM_O + grp * (DVC / 2) + c, o);
+          float4* d = reinterpret_cast<float4*>(stg + lane * ROWP + c * 4);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            d[e] = make_float4(o[4 * e] * inv, o[4 * e + 1] * inv, o[4 * e + 2] * inv, o[4 * e + 3] * inv);
+        }
+        __syncwarp();
+        const int ecol = dvc * DVC + grp * (DVC / 2) + (lane & 15) * 8;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rr = it * 2 + (lane >> 4);
+          const int oi = qt * BM + quad * 32 + rr;
+          if (oi < p.HW) {
+            const float4* sp = reinterpret_cast<const float4*>(stg + rr * ROWP + (lane & 15) * 32);
+            const float4 a = sp[0], b = sp[1];
+            float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            if (p.gate) {
+              const uint4 g = *reinterpret_cast<const uint4*>(p.gate + (long long)oi * p.ldg + ecol);
+              const float2 g0 = unpack2(g.x), g1 = unpack2(g.y), g2 = unpack2(g.z), g3 = unpack2(g.w);
+              v[0] *= g0.x; v[1] *= g0.y; v[2] *= g1.x; v[3] *= g1.y; v[4] *= g2.x; v[5] *= g2.y; v[6] *= g3.x; v[7] *= g3.y;
+            }
+            uint4 u;
+            u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(p.out + (long long)oi * p.ldo + ecol) = u;
+          }
+        }
+      } else {
       // part_o: [slot][16-column group][row][16] -- the 32 rows of a warp are contiguous per group, so every store
       // instruction covers whole lines (row-major rows 512 B apart cost one line per lane and ~5000 cycles per segment)
       t16* po = p.part_o + (((long long)(blockIdx.x * 2 + s) * (DVC / 16) + grp * (DVC / 32)) * BM + row) * 16;
@@ -527,7 +571,8 @@ long_attn_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_con
           }
         }
       }
-      if (grp == 0) {
+      }
+      if (grp == 0 && !p.direct) {
         float* ml = p.part_ml + ((long long)(blockIdx.x * 2 + s) * BM + row) * 2;
         ml[0] = M;
         ml[1] = l_row;
@@ -669,6 +714,20 @@ int sm_count() {
   return n;
 }
 
+// RMEM_ATTN_DIRECT=1 enables the one-CTA-per-unit path for single-frame launches.  Off by default: measured at c3 it
+// is slower (56 CTAs x 27 tiles leave 92 SMs idle: 1.496 vs 1.463 ms per frame) than stream-K + combine.
+bool direct_switch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RMEM_ATTN_DIRECT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+
+bool short_switch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RMEM_ATTN_SHORT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 void schedule(int HW, int T, int Dv, int* n_units, int* tpf, int* TPU, int* nCTA) {
   const int qtiles = cdiv(HW, BM), n_dv = Dv / DVC;
   *n_units = qtiles * n_dv;
@@ -679,6 +738,9 @@ void schedule(int HW, int T, int Dv, int* n_units, int* tpf, int* TPU, int* nCTA
   if ((long long)n > L / 4) n = (int)(L / 4);                    // at least ~4 tiles per CTA
   const int cap = (kMaxSegsPerUnit - 2) * *n_units;             // combine2 resolves <= kMaxSegsPerUnit segments per unit
   if (n > cap) n = cap;
+  // Short launches (the T = 1 self-attention: ~10 tiles per SM): a segment epilogue costs about six tiles, so a CTA that
+  // straddles two units pays more in epilogues than the last SMs are worth -- use k whole-segment CTAs per unit instead.
+  if (L / n < 16 && n / *n_units >= 2 && short_switch()) n = (n / *n_units) * *n_units;
   if (n < *n_units) n = *n_units;                               // a CTA never spans more than two units
   if ((long long)n > L) n = (int)L;
   *nCTA = n;
@@ -737,6 +799,14 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   Tc2Params p;
   p.HW = a.HW; p.HWp = a.HWp; p.T = a.T; p.Dv = a.Dv; p.n_dv = a.Dv / DVC;
   schedule(a.HW, a.T, a.Dv, &p.n_units, &p.tpf, &p.TPU, &p.nCTA);
+  // One frame of keys and no attention mass wanted (the self-attention): a unit is only tpf tiles long, so cutting it into
+  // stream-K segments costs more in segment epilogues + the combine launch than it balances.  One CTA per unit, final
+  // rows written by the kernel.
+  const bool vec_ok = a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                      (!a.gate || (a.ldg % 8 == 0 && (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0));
+  p.direct = (a.T == 1 && !a.mass && vec_ok && p.n_units <= sm_count() && direct_switch()) ? 1 : 0;
+  if (p.direct) p.nCTA = p.n_units;
+  p.gate = a.gate; p.ldg = a.ldg; p.out = a.out; p.ldo = a.ldo;
   p.L = (long long)p.n_units * p.TPU;
   size_t off_ml, off_pieces;
   const size_t need = part_bytes(p.nCTA, a.T, &off_ml, &off_pieces);
@@ -774,6 +844,7 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   RMEM_CUDA_CHECK(launch_pdl(long_attn_tc2_kernel, dim3(p.nCTA), dim3(kThreads), SMEM_TOTAL, s, *mk, *mv, p));
   if (g_ev1) RMEM_CUDA_CHECK(cudaEventRecord(g_ev1, s));
   RMEM_LAUNCH_CHECK();
+  if (p.direct) return RMEM_OK;
   RMEM_CUDA_CHECK(launch_pdl(combine2_kernel, dim3(cdiv(a.HW, kCombRows)), dim3(256), 0, s, p, a.gate, a.ldg, a.out, a.ldo, a.mass));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
