@@ -65,8 +65,10 @@ constexpr int TMEM_Q = 448;    // 64 columns: the 128 x 128 fp16 query tile as p
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 12.0f;     // log2 units: P <= 2^12 (fp16 max 2^16) before a lazy rescale is forced
 
+constexpr int kMaxCTA = 192;   // SMs a launch may use (B200: 148)
 struct Tc2Params {
   int HW, HWp, T, tpf, TPU, n_units, n_dv, nCTA, Dv;
+  int bounds[kMaxCTA + 1];     // CTA c owns steps [bounds[c], bounds[c+1]) of the (unit, tile) sequence, see make_bounds()
   long long L;                 // n_units * TPU
   int slot[kMaxBankFrames];
   float scale_log2;            // scale * log2(e)
@@ -150,8 +152,8 @@ __device__ int g_trace_cta = 0;
 struct Seg { int unit, lo, hi; };   // tiles [lo, hi) of the unit
 
 __device__ __forceinline__ void cta_range(const Tc2Params& p, int cta, long long& lo, long long& hi) {
-  lo = (p.L * cta) / p.nCTA;
-  hi = (p.L * (cta + 1)) / p.nCTA;
+  lo = p.bounds[cta];
+  hi = p.bounds[cta + 1];
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -621,7 +623,10 @@ __global__ void __launch_bounds__(256) combine2_kernel(const Tc2Params p, const 
     const int k = tc;
     const int unit = qt * p.n_dv + k;
     const long long u_lo = (long long)unit * p.TPU, u_hi = u_lo + p.TPU;
-    int c = (int)(((u_lo + 1) * p.nCTA - 1) / p.L);
+    int c = 0;                                       // first CTA whose range reaches past u_lo (bounds are ascending)
+    for (int step = 128; step > 0; step >>= 1)
+      if (c + step < p.nCTA && p.bounds[c + step] <= u_lo) c += step;
+    if (p.bounds[c + 1] <= u_lo) ++c;
     int n = 0;
     float M = -INFINITY;
     for (; c < p.nCTA && n < kMaxSegsPerUnit; ++c) {
@@ -722,6 +727,60 @@ bool direct_switch() {
   return v != 0;
 }
 
+// Static schedule.  Uniform cuts give every CTA the same number of tiles, but a CTA whose range crosses a unit boundary
+// pays a second segment epilogue (TMEM read-out of O is 64 B/clk: ~6 tile-times) plus a pipeline restart, and the kernel
+// ends with the slowest CTA (per-CTA wall times, profiles/r01_attn_trace_cta95.txt: 99k cycles with one segment, 112k with
+// two).  make_bounds() equalises tiles + kSegCost * segments (+ kRestartCost for a second segment) instead: smallest
+// budget for which a greedy walk covers all L steps with nCTA CTAs, at most two segments per CTA.
+constexpr int kSegCost = 6, kRestartCost = 1;
+bool balance_switch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RMEM_ATTN_BALANCE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+// CTAs [0, m) get `budget`, the rest budget - 1
+bool greedy_bounds(long long L, int TPU, int n, long long budget, int m, int* b) {
+  long long pos = 0;
+  for (int c = 0; c < n; ++c) {
+    b[c] = (int)pos;
+    long long room = budget - (c >= m ? 1 : 0) - kSegCost;
+    bool second = false;
+    while (room > 0 && pos < L) {
+      const long long unit_end = (pos / TPU + 1) * TPU;
+      const long long take = room < unit_end - pos ? room : unit_end - pos;
+      pos += take;
+      room -= take;
+      if (pos == unit_end && pos < L) {
+        if (second) break;
+        second = true;
+        room -= kSegCost + kRestartCost;
+      }
+    }
+  }
+  b[n] = (int)L;
+  return pos >= L;
+}
+void make_bounds(long long L, int TPU, int n, int* b) {
+  const long long uni = (L + n - 1) / n;
+  if (!balance_switch() || uni < 16) {                 // short launches keep the uniform cut (see schedule())
+    for (int c = 0; c <= n; ++c) b[c] = (int)((L * c) / n);
+    return;
+  }
+  long long lo = uni, hi = uni + 2 * kSegCost + kRestartCost + 2;
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if (greedy_bounds(L, TPU, n, mid, n, b)) hi = mid; else lo = mid + 1;
+  }
+  // with the minimal budget the walk usually ends a few CTAs early (idle SMs): give only the first m CTAs the full
+  // budget and the others one tile less, m minimal
+  int mlo = 0, mhi = n;
+  while (mlo < mhi) {
+    const int mid = (mlo + mhi) / 2;
+    if (greedy_bounds(L, TPU, n, lo, mid, b)) mhi = mid; else mlo = mid + 1;
+  }
+  greedy_bounds(L, TPU, n, lo, mlo, b);
+}
+
 bool short_switch() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RMEM_ATTN_SHORT"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -735,6 +794,7 @@ void schedule(int HW, int T, int Dv, int* n_units, int* tpf, int* TPU, int* nCTA
   *TPU = T * *tpf;
   const long long L = (long long)*n_units * *TPU;
   int n = sm_count();
+  if (n > kMaxCTA) n = kMaxCTA;
   if ((long long)n > L / 4) n = (int)(L / 4);                    // at least ~4 tiles per CTA
   const int cap = (kMaxSegsPerUnit - 2) * *n_units;             // combine2 resolves <= kMaxSegsPerUnit segments per unit
   if (n > cap) n = cap;
@@ -808,6 +868,8 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   if (p.direct) p.nCTA = p.n_units;
   p.gate = a.gate; p.ldg = a.ldg; p.out = a.out; p.ldo = a.ldo;
   p.L = (long long)p.n_units * p.TPU;
+  RMEM_REQUIRE(p.nCTA <= kMaxCTA, "long_attn_tc2: %d CTAs > %d", p.nCTA, kMaxCTA);
+  make_bounds(p.L, p.TPU, p.nCTA, p.bounds);
   size_t off_ml, off_pieces;
   const size_t need = part_bytes(p.nCTA, a.T, &off_ml, &off_pieces);
   RMEM_REQUIRE(workspace_bytes >= need, "long_attn_tc2: workspace %zu < %zu", workspace_bytes, need);
