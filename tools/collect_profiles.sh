@@ -6,7 +6,7 @@ cp gpurun_out/bench.json profiles/${R}_bench_final.json
 cp gpurun_out/bench_ref.json profiles/${R}_bench_reference_arm.json
 cp gpurun_out/stage_times.txt profiles/${R}_stage_times.txt
 cp gpurun_out/launches.csv profiles/${R}_launches_c3_final.csv
-python tools/summarize_launches.py gpurun_out/launches.csv > profiles/${R}_launches_c3_final_summary.txt
+python tools/summarize_launches.py gpurun_out/launches.csv 5 > profiles/${R}_launches_c3_final_summary.txt
 [ -f gpurun_out/bench_2gpu.json ] && grep '^{' gpurun_out/bench_2gpu.json > profiles/${R}_bench_2gpu.json
 ncu -i gpurun_out/attn.ncu-rep --page details --csv > profiles/${R}_attn_final_ncu_details.csv
 python tools/ncu_traffic.py gpurun_out/attn.ncu-rep long_attn_tc2_kernel profiles/attn_traffic.json
