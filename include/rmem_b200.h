@@ -71,6 +71,9 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
 
 /* Debug aid: per-event clock64 trace of CTA 0 of the RMEM_ATTN_TC2 kernel into dev_buf ([tiles][16] int64); NULL disables. */
 int rmem_debug_attn_trace(void* dev_buf);
+/* Host-only: the static (unit, tile)-step schedule the fused attention kernel uses for a launch of this shape: CTA c owns
+ * steps [bounds[c], bounds[c+1]) of n_units * tiles_per_unit.  `bounds` has room for `cap` ints (>= n_cta + 1). */
+int rmem_debug_attn_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds, int cap);
 /* Measurement aid: cudaEvent_t handles recorded immediately before / after the RMEM_ATTN_TC2 main kernel launch inside
  * rmem_long_attn_fwd (NULL, NULL clears).  Thread-local. */
 int rmem_debug_attn_events(void* ev0, void* ev1);

@@ -57,6 +57,7 @@ int mha_dense(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStr
 
 // v2 (attn_tc2.cu): stream-K schedule over the SMs, 8 softmax warps, P through TMEM, fp16 partials.
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv);
+int long_attn_tc2_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds, int cap);
 int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 // Debug: clock64 event trace of CTA 0 ([tile][16] long long, see attn_tc2.cu); nullptr disables.
 int long_attn_tc2_set_trace(long long* dev_buf);

@@ -837,6 +837,15 @@ int long_attn_tc2_set_trace(long long* dev_buf) {
   return RMEM_OK;
 }
 
+// Host-only view of the static schedule (tests): step range of every CTA for a launch of this shape.
+int long_attn_tc2_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds, int cap) {
+  int tpf = 0;
+  schedule(HW, T, Dv, n_units, &tpf, tiles_per_unit, n_cta);
+  RMEM_REQUIRE(*n_cta + 1 <= cap && *n_cta <= kMaxCTA, "schedule: %d CTAs do not fit the caller's table (%d)", *n_cta, cap);
+  make_bounds((long long)*n_units * *tiles_per_unit, *tiles_per_unit, *n_cta, bounds);
+  return RMEM_OK;
+}
+
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv) {
   (void)HWp;
   size_t best = 0;

@@ -90,6 +90,12 @@ int rmem_debug_attn_events(void* ev0, void* ev1) {
   long_attn_tc2_set_events(ev0, ev1);
   return RMEM_OK;
 }
+int rmem_debug_attn_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds,
+                             int cap) {
+  RMEM_REQUIRE(n_units && tiles_per_unit && n_cta && bounds, "null argument");
+  return long_attn_tc2_schedule(HW, T, Dv, n_units, tiles_per_unit, n_cta, bounds, cap);
+}
+
 int rmem_debug_attn_trace(void* dev_buf) {
   RMEM_TRY(local_attn_tc_set_trace(reinterpret_cast<long long*>(dev_buf)));
   return long_attn_tc2_set_trace(reinterpret_cast<long long*>(dev_buf));

@@ -64,3 +64,31 @@ def test_synthetic_shapes_follow_the_reference_size_rule():
     assert synth.snap_size(256) == 257
     lab = synth.synthetic_label(481, 849, 10)
     assert sorted(lab.unique().tolist()) == list(range(11))
+
+
+def test_attention_static_schedule_invariants():
+    """Host side of the fused attention kernel's stream-K schedule (attn_tc2.cu make_bounds): the cut points are
+    ascending, cover every (unit, tile) step exactly once, no CTA spans more than two units, and the modelled cost
+    (tiles + 6 per segment, +1 for a second one) is flat across CTAs for long launches.  No GPU involved."""
+    import ctypes as C
+    from rmem_b200 import _capi
+    lib = _capi.load()
+    for (HW, T, Dv) in [(1674, 8, 1024), (1674, 1, 1024), (1674, 5, 1024), (3726, 8, 1024), (289, 1, 1024),
+                        (289, 3, 256), (540, 9, 512), (65, 2, 1024)]:
+        n_units, tpu, n_cta = C.c_int(), C.c_int(), C.c_int()
+        b = (C.c_int * 256)()
+        _capi.check(lib.rmem_debug_attn_schedule(HW, T, Dv, C.byref(n_units), C.byref(tpu), C.byref(n_cta), b, 256))
+        n, L, TPU = n_cta.value, n_units.value * tpu.value, tpu.value
+        assert n_units.value == -(-HW // 128) * (Dv // 256) and TPU == T * -(-HW // 64)
+        bounds = [b[i] for i in range(n + 1)]
+        assert bounds[0] == 0 and bounds[-1] == L and all(x <= y for x, y in zip(bounds, bounds[1:])), (HW, T, Dv)
+        costs = []
+        for lo, hi in zip(bounds, bounds[1:]):
+            if hi == lo:
+                continue
+            segs = (hi - 1) // TPU - lo // TPU + 1
+            assert segs <= 2, (HW, T, Dv, lo, hi)
+            costs.append(hi - lo + 6 * segs + (1 if segs == 2 else 0))
+        if L // n >= 16:
+            assert max(costs) - min(costs) <= 8, (HW, T, Dv, min(costs), max(costs))
+            assert len(costs) == n                                   # no idle CTA
