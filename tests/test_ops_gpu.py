@@ -108,12 +108,13 @@ def test_layernorm_groupnorm(ops, cuda_device):
 
 def test_dwconv_upsample_maxpool_transpose(ops, cuda_device):
     g = torch.Generator().manual_seed(4)
-    h, w, C = 31, 54, 1024
-    x = bfr(torch.randn(h * w, C, generator=g))
-    wt = torch.randn(C, 1, 5, 5, generator=g) / 5
-    ref = O.dwconv5(x, wt, h, w)
-    out = ops.dwconv5x5(x.to(cuda_device).to(OP), wt.view(C, 25).t().contiguous().to(cuda_device), h, w)
-    assert relfro(out, ref) < 4e-3
+    for (h, w, C) in [(31, 54, 1024), (17, 21, 1024), (46, 81, 1024), (5, 3, 64), (8, 18, 128)]:   # ragged tiles too
+        x = bfr(torch.randn(h * w, C, generator=g))
+        wt = torch.randn(C, 1, 5, 5, generator=g) / 5
+        ref = O.dwconv5(x, wt, h, w)
+        out = ops.dwconv5x5(x.to(cuda_device).to(OP), wt.view(C, 25).t().contiguous().to(cuda_device), h, w)
+        assert relfro(out, ref) < 4e-3, (h, w, C)
+    h, w = 31, 54
     xm = bfr(torch.randn(1, 256, h, w, generator=g))
     ref = F.interpolate(xm, size=(61, 107), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
     out = ops.upsample_bilinear(xm[0].permute(1, 2, 0).contiguous().to(cuda_device).to(OP), 61, 107)
