@@ -137,13 +137,22 @@ def test_id_embedding_matches_conv_of_one_hot(ops, cuda_device):
     lab[0, 0, 5:30, 7:50] = 255
     from rmem_b200.weights import pack_deaot
     pk = pack_deaot(sd)
-    for use_ignore in (False, True):
-        ref = O.id_embedding(sd, cfg, O.one_hot_with_ignore(lab, use_ignore))
-        for prefix in (None, pk["idbank.prefix"].to(cuda_device)):      # tap loop only / uniform-patch shortcut
-            out = ops.id_embedding(lab[0, 0].to(torch.uint8).to(cuda_device), pk["idbank.w"].to(cuda_device),
-                                   pk["idbank.b"].to(cuda_device), pk["id_norm.g"].to(cuda_device),
-                                   pk["id_norm.b"].to(cuda_device), use_ignore, prefix=prefix)
-            assert relfro(out, ref) < 2e-4, (use_ignore, prefix is not None)
+    # a second label map with salt-and-pepper noise: mixed patches with a dominant class (prefix + minority correction),
+    # patches without one (plain tap loop), ids above 10 that fall in no one-hot channel, and ignore pixels
+    g = torch.Generator().manual_seed(9)
+    noisy = lab.clone()
+    m = torch.rand(lab.shape, generator=g) < 0.12
+    noisy[m] = torch.randint(0, 14, lab.shape, generator=g)[m].to(noisy.dtype)
+    noisy[0, 0, 100:140, 100:160] = torch.randint(0, 11, (40, 60), generator=g).to(noisy.dtype)
+    noisy[0, 0, 200:215, 10:40] = 255
+    for which, lb in (("blocks", lab), ("noisy", noisy)):
+        for use_ignore in (False, True):
+            ref = O.id_embedding(sd, cfg, O.one_hot_with_ignore(lb, use_ignore))
+            for prefix in (None, pk["idbank.prefix"].to(cuda_device)):      # tap loop only / prefix-table shortcuts
+                out = ops.id_embedding(lb[0, 0].to(torch.uint8).to(cuda_device), pk["idbank.w"].to(cuda_device),
+                                       pk["idbank.b"].to(cuda_device), pk["id_norm.g"].to(cuda_device),
+                                       pk["id_norm.b"].to(cuda_device), use_ignore, prefix=prefix)
+                assert relfro(out, ref) < 2e-4, (which, use_ignore, prefix is not None)
 
 
 def _attn_inputs(T, HW, g, sharp=1.0, Dv=1024):
