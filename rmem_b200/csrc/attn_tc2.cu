@@ -5,7 +5,7 @@
 // S = Q.K^T -> softmax -> P.V, not by any pipe: tcgen05.mma groups take ~400 cycles from issue to a visible commit on
 // top of their throughput (tools/ubench/mma_rate.cu: 8 x N=64 MMAs = 757 cycles alone, 49 cycles each in a stream),
 // and one set of softmax warps needed ~1600 cycles per 64-key tile.  This version removes the loop:
-//   * S runs up to four tiles ahead of P.V in four TMEM score buffers, issued by its own warp (tcgen05.mma issue blocks
+//   * S runs up to three tiles ahead of P.V in three TMEM score buffers, issued by its own warp (tcgen05.mma issue blocks
 //     the issuing thread for roughly the MMA's execution time, so one issuing warp per MMA stream), so softmax never
 //     waits for scores;
 //   * two softmax warp groups (4 warps each, one query row per thread) alternate KV tiles; the only value that has to
@@ -18,9 +18,13 @@
 //     CTA flushes at most two segments as normalised fp16 rows + fp32 (m, l); per-frame (m, l) pieces give the mass;
 //   * shared-memory bandwidth (MMA operand reads + TMA fills, 128 B/cycle) turned out to be the binding resource, so the
 //     query tile is kept in TMEM as the A operand of S (tcgen05.mma with A in TMEM): S reads only K from shared memory;
-//   * K and V^T tiles travel in separate TMA rings (6 x 16 KB, 4 x 32 KB; K is needed earlier than V).
+//   * K and V^T tiles travel in separate TMA rings (6 x 16 KB, 4 x 32 KB; K is needed earlier than V);
+//   * what bounds the steady state now is the ~48 B/clk one SM can pull from L2: 48 KB of K + V^T per 64-key step is
+//     ~1000 cycles, against ~780 cycles of tensor work -- the next step is cta_group::2;
+//   * the static schedule equalises tiles + segment epilogues across CTAs (make_bounds), partial O is stored in
+//     16-column groups so the row-per-lane TMEM read-out writes whole lines.
 //
-//   block = 384 threads: warps 0-3 softmax group 0 (even tiles), 4-7 group 1 (odd tiles), 8 K/Q producer,
+//   block = 384 threads: warps 0-3 softmax group 0 (even tiles), 4-7 group 1 (odd tiles), 8 K producer,
 //                        9 V producer, 10 S issuer + TMEM owner, 11 P.V issuer
 //   TMEM (512 cols): O[256] | 3 x S/P[64] | Q[64]
 //   smem: K 6 x 16 KB | V^T 4 x 32 KB | row-max hand-over | barriers
