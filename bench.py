@@ -228,7 +228,10 @@ def run_ours(args):
             "dtype": "fp16" if _capi.op_dtype() == torch.float16 else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"clip-sharded x{world}", "attn_impl": args.attn,
                        "l2": "per-frame working set (banks 3x37 MB + activations + 150 MB attention workspace) "
-                             "exceeds the 126 MB L2; no explicit flush"},
+                             "exceeds the 126 MB L2; no explicit flush",
+                       "pipeline": ("each step = prefetch(frame i+1: image encoder on the engine's side stream) + "
+                                    "propagate(frame i) + update_memory(frame i); every frame is encoded exactly once"
+                                    if PREFETCH else "no cross-frame prefetch")},
             "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
                     "d2h_bytes_per_step": H * W},
             "gpu_launches": int(launches) * world,
