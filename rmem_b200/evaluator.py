@@ -52,31 +52,21 @@ def davis_palette() -> List[int]:
 
 def restrict_size(h: int, w: int, min_size: Optional[int] = None, max_size: Optional[float] = 800 * 1.3,
                   scale: float = 1.0, align_corners: bool = True, max_stride: int = 16) -> Tuple[int, int]:
-    """Network input size for an h x w frame (video_transforms.py:575-623; defaults = configs/default.py:110-112).
-    480 x 854 -> 481 x 849, 720 x 1280 -> 721 x 1281 after the 1040-pixel long-edge cap ...."""
-    assert (min_size is None) or (max_size is None)
-    sc = None
-    if min_size is not None:
-        short_edge = w if h > w else h
-        if short_edge > min_size:
-            sc = float(min_size) / short_edge
-    else:
-        long_edge = h if h > w else w
-        if long_edge > max_size:
-            sc = float(max_size) / long_edge
-    new_h, new_w = (h, w) if sc is None else (sc * h, sc * w)
-    new_h, new_w = int(new_h * scale), int(new_w * scale)
-    if align_corners:
-        if (new_h - 1) % max_stride != 0:
-            new_h = int(np.around((new_h - 1) / max_stride) * max_stride + 1)
-        if (new_w - 1) % max_stride != 0:
-            new_w = int(np.around((new_w - 1) / max_stride) * max_stride + 1)
-    else:
-        if new_h % max_stride != 0:
-            new_h = int(np.around(new_h / max_stride) * max_stride)
-        if new_w % max_stride != 0:
-            new_w = int(np.around(new_w / max_stride) * max_stride)
-    return new_h, new_w
+    """Network input size for an h x w frame -- the rule of MultiRestrictSize (video_transforms.py:575-623; defaults =
+    configs/default.py:110-112): cap the short edge at `min_size` or the long edge at `max_size` (only ever shrinking),
+    apply `scale`, then snap each side to a multiple of the stride (+1 with align_corners).
+    480 x 854 -> 481 x 849."""
+    if min_size is not None and max_size is not None:
+        raise ValueError("give min_size or max_size, not both")
+    edge, limit = (min(h, w), min_size) if min_size is not None else (max(h, w), max_size)
+    shrink = float(limit) / edge if (limit is not None and edge > limit) else None
+
+    def side(v: int) -> int:
+        v = int((v if shrink is None else shrink * v) * scale)
+        off = 1 if align_corners else 0                 # sides are stride * k (+ 1): already-aligned values are fixed points
+        return int(np.around((v - off) / max_stride) * max_stride + off)
+
+    return side(h), side(w)
 
 
 def long_term_gap(num_frames: int, no_memory_gap: bool = False) -> int:
@@ -104,17 +94,17 @@ class ClipDataset:
         self.rgb, self.resolution = rgb, resolution
         self.min_size, self.max_size = min_size, max_size
         assert len(self.images) >= 2, "a clip needs a reference frame and at least one frame to propagate to"
+        # objects known before each frame (VOSTest, eval_datasets.py:37-52): ids enter in order of first appearance, a
+        # frame's own label only counts from that frame on, and frame 0 reports the count valid at frame 1
+        known: List[int] = [0]
         self.obj_nums: List[int] = []
         self.obj_indices: List[List[int]] = []
-        curr_objs = [0]
-        for img_name in self.images:
-            self.obj_nums.append(len(curr_objs) - 1)
-            lab = os.path.splitext(img_name)[0] + ".png"
-            if lab in self.labels:
-                for obj in list(np.unique(self._read_png(lab))):
-                    if int(obj) not in curr_objs:
-                        curr_objs.append(int(obj))
-            self.obj_indices.append(curr_objs.copy())
+        for name in self.images:
+            self.obj_nums.append(len(known) - 1)
+            png = os.path.splitext(name)[0] + ".png"
+            if png in self.labels:
+                known += [int(v) for v in np.unique(self._read_png(png)) if int(v) not in known]
+            self.obj_indices.append(list(known))
         self.obj_nums[0] = self.obj_nums[1]
 
     def __len__(self):
@@ -125,13 +115,12 @@ class ClipDataset:
         return np.array(Image.open(os.path.join(self.label_dir, name)), dtype=np.uint8)
 
     def read_label(self, name: str, squeeze_idx: Sequence[int]) -> np.ndarray:
-        label = self._read_png(name)
-        out = label * 0
-        for idx, obj_id in enumerate(squeeze_idx):
-            if obj_id == 0:
-                continue
-            out += ((label == obj_id) * idx).astype(np.uint8)
-        return out
+        """Dataset ids -> 0..n by position in `squeeze_idx` (ids not listed, and id 0, map to 0)."""
+        lut = np.zeros(256, np.uint8)
+        for pos, obj_id in enumerate(squeeze_idx):
+            if obj_id != 0:
+                lut[obj_id] = pos
+        return lut[self._read_png(name)]
 
     def read_image(self, idx: int) -> np.ndarray:
         import cv2
@@ -172,11 +161,10 @@ def save_mask(mask: np.ndarray, path: str, squeeze_idx: Optional[Sequence[int]] 
     def _write():
         from PIL import Image
         m = mask
-        if squeeze_idx is not None:
-            un = m * 0
-            for idx in range(1, len(squeeze_idx)):
-                un += ((m == idx) * squeeze_idx[idx]).astype(np.uint8)
-            m = un
+        if squeeze_idx is not None:                   # 0..n back to the dataset's ids; anything above n becomes 0
+            lut = np.zeros(256, np.uint8)
+            lut[1:len(squeeze_idx)] = np.asarray(squeeze_idx[1:], np.uint8)
+            m = lut[m]
         im = Image.fromarray(m).convert("P")
         im.putpalette(davis_palette())
         im.save(path)
