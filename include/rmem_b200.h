@@ -26,8 +26,10 @@ extern "C" {
 #define RMEM_MAX_BANK_FRAMES 16
 #define RMEM_GN_SCRATCH_DOUBLES (72 + 148 * 4 * 64)
 #define RMEM_ATTN_DENSE 0 /* materialised scores: generic GEMMs + row softmax */
-#define RMEM_ATTN_TC 1    /* fused tcgen05 + TMA flash kernel, v1 (split per frame, P through shared memory) */
-#define RMEM_ATTN_TC2 2   /* v2: stream-K schedule, 8 softmax warps, P through TMEM, fp16 partials (default) */
+#define RMEM_ATTN_TC 1    /* (removed: the first tcgen05 kernel of round 1; selecting it is an error) */
+#define RMEM_ATTN_TC2 2   /* stream-K schedule over single CTAs, 8 softmax warps, P through TMEM, fp16 partials */
+#define RMEM_ATTN_TC3 3   /* CTA pairs (tcgen05.mma.cta_group::2) sharing every K / V^T tile, 128-key score MMAs, seeded
+                             row maximum (default) */
 
 int rmem_version(void);
 const char* rmem_last_error(void);
@@ -68,13 +70,25 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
                        int nslots, int T, const int* slots /*HOST [T]*/, int HW, int HWp, int Dk, int Dv,
                        float scale, const void* gate, long long ldg, void* out, long long ldo, float* mass,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* Same op with the token grid of the queries / bank frames (grid_h * grid_w == HW).  RMEM_ATTN_TC3 uses it to seed the
+ * running row maximum of the online softmax with the scores against the 3x3 neighbourhood of the query's own position in
+ * every bank frame (a lower bound of the true maximum), which keeps the lazy-rescale path of the kernel rare on peaked
+ * score distributions; results are the same softmax either way.  grid_h = grid_w = 0: no seed (= rmem_long_attn_fwd). */
+int rmem_long_attn_grid_fwd(int impl, const void* qt, const float* qbias, const void* kbank, const void* vtbank,
+                            int nslots, int T, const int* slots /*HOST [T]*/, int HW, int HWp, int Dk, int Dv,
+                            float scale, const void* gate, long long ldg, void* out, long long ldo, float* mass,
+                            int grid_h, int grid_w, void* workspace, size_t workspace_bytes, void* stream);
+/* Debug aid (RMEM_ATTN_TC3): device int the kernel increments once per warp-level lazy-rescale event; NULL disables.
+ * Thread-local. */
+int rmem_debug_attn_rescale_counter(void* dev_int);
 
 /* Debug aid: per-event clock64 trace of CTA 0 of the RMEM_ATTN_TC2 kernel into dev_buf ([tiles][16] int64); NULL disables. */
 int rmem_debug_attn_trace(void* dev_buf);
 /* Host-only: the static (unit, tile)-step schedule the fused attention kernel uses for a launch of this shape: CTA c owns
- * steps [bounds[c], bounds[c+1]) of n_units * tiles_per_unit.  `bounds` has room for `cap` ints (>= n_cta + 1). */
-int rmem_debug_attn_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds, int cap);
-/* Measurement aid: cudaEvent_t handles recorded immediately before / after the RMEM_ATTN_TC2 main kernel launch inside
+ * steps [bounds[c], bounds[c+1]) of n_units * tiles_per_unit (impl RMEM_ATTN_TC2: CTAs and 64-key tiles; RMEM_ATTN_TC3:
+ * clusters of two CTAs and 128-key groups, a unit being a PAIR of query tiles x one Dv chunk).  `bounds` has room for `cap` ints (>= n_cta + 1). */
+int rmem_debug_attn_schedule(int impl, int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds, int cap);
+/* Measurement aid: cudaEvent_t handles recorded immediately before / after the main attention kernel launch (TC2 / TC3) inside
  * rmem_long_attn_fwd (NULL, NULL clears).  Thread-local. */
 int rmem_debug_attn_events(void* ev0, void* ev1);
 /* Same for the tcgen05 GEMM: first 64 CTAs of every launch, [cta][8] int64. */
@@ -151,7 +165,7 @@ typedef struct rmem_engine_config {
   int former_mem_len;   /* FORMER_MEM_LEN */
   int latter_mem_len;   /* LATTER_MEM_LEN */
   int max_engines;      /* ceil(max objects / 10) object groups */
-  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC | RMEM_ATTN_TC2 */
+  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC2 | RMEM_ATTN_TC3 */
   int long_term_mem_gap;
 } rmem_engine_config;
 

@@ -26,15 +26,14 @@ struct LongAttnArgs {
   t16* out = nullptr;           // [HW, Dv]
   long long ldo = 0;
   float* mass = nullptr;         // [HW, T] or null
+  // RMEM_ATTN_TC3 only: token grid (seed_h * seed_w == HW) for the row-maximum seed (scores against the 3x3 neighbourhood
+  // of the query's own position in every bank frame); 0 = no seed (the first key tile seeds the maximum)
+  int seed_h = 0, seed_w = 0;
 };
 
 // Materialised-score implementation (generic GEMM + row softmax).  Workspace: S fp32 + P t16.
 size_t long_attn_dense_workspace(int HW, int HWp, int nslots);
 int long_attn_dense(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
-
-// Fused tcgen05/TMA flash kernel (attn_tc.cu).  Workspace holds split partials.
-size_t long_attn_tc_workspace(int HW, int HWp, int nslots, int Dv);
-int long_attn_tc(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 // Multi-head attention over a bank (AOT: 8 heads x 32): q [HW, H*dh] (row stride ldq), kbank [nslots][HWp][H*dh],
 // vtbank [H*dh][nslots*HWp], qbias [H][HW][T] or null, out [HW, H*dh] (row stride ldo), mass [HW, T] = head mean or null.
@@ -59,6 +58,14 @@ int mha_dense(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStr
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv);
 int long_attn_tc2_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds, int cap);
 int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
+// v3 (attn_tc3.cu): CTA pairs (tcgen05.mma.cta_group::2) share every K / V^T tile, 128-key score MMAs, seeded row maximum.
+size_t long_attn_tc3_workspace(int HW, int HWp, int nslots, int Dv);
+int long_attn_tc3_schedule(int HW, int T, int Dv, int* n_units, int* groups_per_unit, int* n_clusters, int* bounds, int cap);
+int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int long_attn_tc3_set_trace(long long* dev_buf);
+void long_attn_tc3_set_events(void* ev0, void* ev1);
+// Debug: device int incremented once per warp-level lazy-rescale event (null disables).  Thread-local.
+void long_attn_tc3_set_rescale_counter(int* dev_counter);
 // Debug: clock64 event trace of CTA 0 ([tile][16] long long, see attn_tc2.cu); nullptr disables.
 int long_attn_tc2_set_trace(long long* dev_buf);
 // Measurement aid: record these CUDA events around the main kernel launch only (null clears).  Thread-local.

@@ -1,0 +1,978 @@
+// Long-term / self attention for sm_100a, CTA-pair version  (K1 + K1b + K8 of SURVEY.md; attention.py:174-193,
+// transformer.py:1140-1197).  RMEM_ATTN_TC3.
+//
+// What changed against attn_tc2.cu, and why (profiles/r01_*):
+//   * tc2 was bound by the ~48 B/clk ONE SM can pull from L2: 48 KB of K + V^T per 64-key step.  Here two CTAs of a
+//     cluster (one TPC) work on two neighbouring 128-query tiles and share every K / V^T tile:
+//     tcgen05.mma.cta_group::2 (M = 256) reads half of the B operand from each CTA's shared memory, so every SM ingests
+//     24 KB per 64 keys.  One thread of the leader CTA issues the MMAs for both; tcgen05.commit ... multicast::cluster
+//     releases the rings and score buffers of both CTAs; each CTA's TMA signals the leader's `full` barriers.
+//   * S = Q.K^T is computed 128 keys at a time (N = 128: ~68 cycles per K=16 step instead of 2 x 49 at N = 64); the
+//     query tile moved from TMEM to shared memory (TMA, once per segment) to make room for 2 x 128 score columns -- with
+//     the B traffic halved, shared-memory bandwidth (the reason it lived in TMEM) is no longer the binding resource.
+//   * The lazy rescale of O (tcgen05.ld/st round trip over 256 columns behind a drained P.V pipeline) was the
+//     data-dependent slow path: on peaked scores (sigma ~ 15-20 log2 units in GPM layers 1-2) ~45 % of the tiles hit it.
+//     The row maximum is now SEEDED with a lower bound of the true maximum computed by attn_seed_kernel (scores against
+//     the 3x3 neighbourhood of the query's own position in every bank frame): the true maximum stays within the fp16
+//     head-room (2^15) of the seed, so rescales become rare (tools/attn_rescale_sim.py); the rescale path itself stays as
+//     the always-correct fallback.
+//
+//   cluster = 2 CTAs x 384 threads: warps 0-3 softmax group 0 (even 64-key sub-tiles), 4-7 group 1 (odd sub-tiles),
+//                                   8 Q/K producer, 9 V producer, 10 S issuer (leader) + TMEM owner, 11 P.V issuer (leader)
+//   TMEM (512 cols per CTA): O[256] | 2 slots x (S[64] | S[64]);  P (packed fp16) aliases the first 32 columns of its S
+//   smem per CTA: Q 32 KB | K ring 3 x 16 KB (64 of a group's 128 keys) | V^T ring 8 x 16 KB (128 of 256 dv rows x 64 keys)
+//   Work: units = (query-tile pair, Dv chunk of 256); a unit is T * ceil(HW / 128) groups of 128 keys; the (unit, group)
+//   sequence is cut into one contiguous range per cluster (stream-K, cost-aware bounds), <= 2 segments per cluster, each
+//   flushed as normalised fp16 rows + fp32 (m, l); combine3_kernel merges, gates and emits the per-frame attention mass.
+#include <cstdlib>
+#include <type_traits>
+
+#include "attn.cuh"
+#include "tcgen05.cuh"
+
+namespace rmem {
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;        // query rows per CTA (256 per cluster)
+constexpr int BNS = 64;        // keys per sub-tile (one softmax step, one P.V MMA group)
+constexpr int BNG = 128;       // keys per group (one S MMA group)
+constexpr int DK = 128;
+constexpr int DVC = 256;       // Dv columns per unit
+constexpr int KS = 3;          // K ring depth (groups)
+constexpr int VS = 8;          // V ring depth (sub-tiles)
+constexpr int kSoftmaxWarps = 8;
+constexpr int kWarpK = 8, kWarpV = 9, kWarpMmaS = 10, kWarpMmaPV = 11;
+constexpr int kThreads = 12 * 32;
+
+constexpr int SMEM_Q = BM * DK * 2;              // 32 KB: [2 dk atoms][128 rows][128 B]
+constexpr int SMEM_K = (BNG / 2) * DK * 2;       // 16 KB: [2 dk atoms][64 keys][128 B]   (this CTA's half of the group)
+constexpr int SMEM_V = (DVC / 2) * BNS * 2;      // 16 KB: [128 dv rows][64 keys]         (this CTA's half of the chunk)
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + SMEM_Q;
+constexpr int OFF_V = OFF_K + KS * SMEM_K;
+constexpr int OFF_MSH = OFF_V + VS * SMEM_V;              // float [128]        row-max hand-over
+constexpr int OFF_LX = OFF_MSH + BM * 4;                  // float [2][128][2]  (m, l) exchange at segment end
+constexpr int OFF_BAR = OFF_LX + 2 * BM * 2 * 4;
+constexpr int SMEM_USED = OFF_BAR + 512;
+constexpr int SMEM_TOTAL = SMEM_USED + 1024;              // + alignment slack (the base is rounded up to 1024 B)
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_O = 0;
+constexpr int TMEM_S = 256;    // 2 slots x 128 fp32 score columns; sub-tile (slot, sub) at TMEM_S + slot*128 + sub*64
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 15.0f;     // log2 units: P <= 2^15 (fp16 max 2^16) before a lazy rescale is forced
+
+constexpr int kMaxCL = 96;     // clusters a launch may use (B200: 74)
+struct Tc3Params {
+  int HW, HWp, T, gpf, TPU, n_units, n_dv, nCL, Dv;
+  int bounds[kMaxCL + 1];      // cluster c owns steps [bounds[c], bounds[c+1]) of the (unit, group) sequence
+  int slot[kMaxBankFrames];
+  float scale_log2;            // scale * log2(e)
+  const float* qbias;          // [HW, T] or null (already multiplied by scale)
+  const float* mseed;          // [HW] lower bound of the row maximum in log2 units (scale and bias applied) or null
+  t16* part_o;                 // [nCTA][2][DVC/16][BM][16]  normalised partial O
+  float* part_ml;              // [nCTA][2][BM][2]           (m in log2 units, l)
+  float* pieces;               // [nCTA][2][T][2][BM][2]     per-frame (m, l) of each softmax group (Dv chunk 0) or null
+  int* rescales;               // debug counter (warp-level rescale events) or null
+  int exp_mode;                // exponentials per 4 that bypass MUFU through exp2_poly: 0, 1 or 2
+};
+
+// ---- cluster / pair primitives ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the LEADER CTA's copy of a barrier (works from either CTA of the pair).  Default semantics (release at CTA
+// scope), as CUTLASS's ClusterBarrier::arrive(cta_id): everything these barriers order lives in TMEM / the async proxy
+// and is fenced with tcgen05.fence::before/after_thread_sync.  A `.release.cluster` arrive costs the arriving warp
+// ~1000 cycles per sub-tile (profiles/r02_attn3_trace_first.txt: exp_done -> p_arrived 1200 cycles in the peer CTA
+// against 240 in the leader).
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, nullptr, 0); }
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, nullptr, 0); }
+
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5 -- below the fp16
+// rounding of P).  The MUFU unit evaluates 16 ex2 per cycle and SM; both softmax groups reach their exp phase at the
+// same time here (one 128-key score MMA feeds both), 16384 exponentials = 1024 MUFU cycles per group against 1580 cycles
+// of tensor work, and that phase sits on the S -> softmax -> P.V dependency chain of a score slot.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                         // 1.5 * 2^23: nearest integer lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);                   // [-0.5, 0.5]
+  float r = fmaf(f, 0.0551716648f, 0.2426111251f);
+  r = fmaf(r, f, 0.6932609677f);
+  r = fmaf(r, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
+}
+
+// TMA tile into THIS CTA's shared memory, transaction bytes counted on the LEADER CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+// MMA completion -> the same barrier in both CTAs of the pair
+__device__ __forceinline__ void commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D[tmem, 2 x 128 rows] (+)= A[smem of each CTA] . B[smem, half per CTA]^T
+__device__ __forceinline__ void umma2_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem of each CTA: packed fp16 pairs, one lane per row] . B[smem, half per CTA]^T
+__device__ __forceinline__ void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(TMEM_COLS));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(TMEM_COLS));
+}
+
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// unsaturated fp32x2 -> t16x2 (values are bounded by 2^15 here)
+__device__ __forceinline__ uint32_t pack2_fast(float lo, float hi) {
+#ifdef RMEM_OPERAND_BF16
+  t162 v = __floats2bfloat162_rn(lo, hi);
+#else
+  t162 v = __floats2half2_rn(lo, hi);
+#endif
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Optional event trace (null in production): clock64 per pipeline event of ONE cluster, [rank][256 sub-tiles][16] int64,
+// then per-CTA wall times in rows 600.. ([cta][16]: globaltimer start / end, groups, segments, SM id, clock64 start / end).
+__device__ long long* g_trace3 = nullptr;
+__device__ int g_trace3_cl = 0;
+#define TRACE3(j, k)                                                                         \
+  do {                                                                                       \
+    if (trace && lane == 0 && (j) < 256) trace[(long long)(j) * 16 + (k)] = clock64();        \
+  } while (0)
+
+struct Seg { int unit, lo, hi; };   // groups [lo, hi) of the unit
+
+__global__ void __launch_bounds__(kThreads, 1)
+long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, const Tc3Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 128B-swizzled TMA / UMMA tiles need 1024B alignment; the offset is the same in both CTAs of the pair
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* m_sh = reinterpret_cast<float*>(smem + OFF_MSH);
+  float* lx = reinterpret_cast<float*>(smem + OFF_LX);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;                      // leader: both CTAs' query tiles have landed (one phase per load)
+  uint64_t* q_free = q_full + 1;                // both:   every score MMA of the first segment has read Q
+  uint64_t* k_full = q_free + 1;                // [KS] leader
+  uint64_t* k_empty = k_full + KS;              // [KS] both
+  uint64_t* v_full = k_empty + KS;              // [VS] leader
+  uint64_t* v_empty = v_full + VS;              // [VS] both
+  uint64_t* s_full = v_empty + VS;              // [2]  both:   S(group) complete
+  uint64_t* p_full = s_full + 2;                // [4]  leader: P(sub-tile) stored by its softmax group in BOTH CTAs
+  uint64_t* sp_free = p_full + 4;               // [4]  both:   P.V(sub-tile) complete: score buffer (and all before) retired
+  uint64_t* o_drained = sp_free + 4;            // leader: both CTAs' segment epilogues have read O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_drained + 1);
+  static_assert((2 + 2 * KS + 2 * VS + 2 + 4 + 4 + 1) * 8 + 4 <= 512, "barrier area");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cl = (int)cluster_id_x();
+  const int cta = cl * 2 + (int)rank;           // partial-result slot owner
+  long long* const trace = (g_trace3 && cl == g_trace3_cl) ? g_trace3 + (long long)rank * 256 * 16 : nullptr;
+  long long* const cta_times = (g_trace3 && cta < 148) ? g_trace3 + (600 + cta) * 16 : nullptr;
+  if (cta_times && threadIdx.x == 0) {
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cta_times[0] = (long long)gt; cta_times[4] = smid; cta_times[5] = clock64();
+  }
+
+  // ---- this cluster's work: a contiguous range of (unit, group) steps -> at most two segments ----
+  const long long lo = p.bounds[cl], hi = p.bounds[cl + 1];
+  Seg seg[2];
+  int nseg = 0;
+  {
+    long long x = lo;
+    while (x < hi && nseg < 2) {
+      const int u = (int)(x / p.TPU);
+      const long long ue = (long long)(u + 1) * p.TPU;
+      const long long e = hi < ue ? hi : ue;
+      seg[nseg].unit = u;
+      seg[nseg].lo = (int)(x - (long long)u * p.TPU);
+      seg[nseg].hi = (int)(e - (long long)u * p.TPU);
+      ++nseg;
+      x = e;
+    }
+  }
+  const int n0 = nseg > 0 ? seg[0].hi - seg[0].lo : 0;                       // groups of the first segment
+  const int ntot = n0 + (nseg > 1 ? seg[1].hi - seg[1].lo : 0);
+  // units are ordered (query pair major, Dv chunk minor): the Q tiles change only when unit / n_dv changes
+  const bool q_reload1 = nseg > 1 && (seg[1].unit / p.n_dv != seg[0].unit / p.n_dv);
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 2);
+    mbar_init(q_free, 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 2); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 2); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&p_full[i], 8); mbar_init(&sp_free[i], 1); }
+    mbar_init(o_drained, 2 * kSoftmaxWarps);
+    mbar_fence_init();
+  }
+  if (warp == kWarpMmaS) tmem_alloc_pair(tmem_slot);
+  fence_before();
+  __syncthreads();
+  cluster_sync_all();           // the peer's barriers are initialised and both TMEM allocations are done
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_prologue();   // barriers, TMEM and descriptors are set up; global memory is touched only from here on
+
+  if (warp == kWarpK) {
+    // ================================ Q + K producer (both CTAs, own halves) ================================
+    if (ntot > 0) {
+      if (elect_one()) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+      }
+      __syncwarp();
+      int i = 0;
+      for (int s = 0; s < nseg; ++s) {
+        if (s == 0 || q_reload1) {
+          if (s == 1) mbar_wait_b(q_free, 0);                // the first segment's score MMAs are done with Q
+          if (elect_one()) {
+            const int row0 = ((seg[s].unit / p.n_dv) * 2 + (int)rank) * BM;
+            tma_load_2d_pair(smem + OFF_Q, &map_q, q_full, 0, row0);
+            tma_load_2d_pair(smem + OFF_Q + BM * 128, &map_q, q_full, 64, row0);
+            if (leader) mbar_expect_tx(q_full, 2 * SMEM_Q); else mbar_arrive_leader(q_full);
+          }
+          __syncwarp();
+        }
+        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++i) {
+          const int t = g / p.gpf, jg = g - t * p.gpf;
+          const int st = i % KS;
+          if (i >= KS) mbar_wait_b(&k_empty[st], ((i / KS) - 1) & 1);
+          if (elect_one()) {
+            const int key0 = p.slot[t] * p.HWp + jg * BNG + (int)rank * (BNG / 2);
+            unsigned char* sk = smem + OFF_K + st * SMEM_K;
+            tma_load_2d_pair(sk, &map_k, &k_full[st], 0, key0);
+            tma_load_2d_pair(sk + (BNG / 2) * 128, &map_k, &k_full[st], 64, key0);
+            if (leader) mbar_expect_tx(&k_full[st], 2 * SMEM_K); else mbar_arrive_leader(&k_full[st]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kWarpV) {
+    // ================================ V^T producer (both CTAs, own dv half) ================================
+    if (ntot > 0) {
+      if (elect_one()) tma_prefetch_desc(&map_v);
+      __syncwarp();
+      int i = 0;
+      for (int s = 0; s < nseg; ++s) {
+        const int dv0 = (seg[s].unit % p.n_dv) * DVC + (int)rank * (DVC / 2);
+        for (int g = seg[s].lo; g < seg[s].hi; ++g) {
+          const int t = g / p.gpf, jg = g - t * p.gpf;
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub, ++i) {
+            const int st = i % VS;
+            if (i >= VS) mbar_wait_b(&v_empty[st], ((i / VS) - 1) & 1);
+            if (elect_one()) {
+              const int key0 = p.slot[t] * p.HWp + jg * BNG + sub * BNS;
+              tma_load_2d_pair(smem + OFF_V + st * SMEM_V, &map_v, &v_full[st], key0, dv0);
+              if (leader) mbar_expect_tx(&v_full[st], 2 * SMEM_V); else mbar_arrive_leader(&v_full[st]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpMmaS) {
+    // ================================ S = Q.K^T issuer (leader only) ================================
+    if (ntot > 0 && leader) {
+      constexpr uint32_t idesc_s = make_idesc(2 * BM, BNG);
+      const uint32_t smem_base = smem_u32(smem);
+      for (int i = 0; i < ntot; ++i) {
+        const int st = i % KS, slot = i & 1;
+        if (i == 0) mbar_wait_cl(q_full, 0);
+        if (i == n0 && q_reload1) mbar_wait_cl(q_full, 1);
+        mbar_wait_cl(&k_full[st], (i / KS) & 1);
+        TRACE3(2 * i, 10);
+        if (i >= 2) mbar_wait_b(&sp_free[slot * 2 + 1], ((i - 2) >> 1) & 1);      // P.V of group i-2 retired the slot
+        fence_after();
+        TRACE3(2 * i, 2);
+        if (elect_one()) {
+          const uint64_t dq = make_desc_sw128(smem_base + OFF_Q);
+          const uint64_t dk = make_desc_sw128(smem_base + OFF_K + st * SMEM_K);
+          const uint32_t d = tmem + TMEM_S + slot * BNG;
+#pragma unroll
+          for (int kk = 0; kk < DK / 16; ++kk) {
+            // 32 B per k-step inside the 128 B swizzle atom; the second 64-wide dk atom starts one tile-half later
+            const uint64_t oa = (uint64_t)(((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4);
+            const uint64_t ob = (uint64_t)(((kk >> 2) * ((BNG / 2) * 128) + (kk & 3) * 32) >> 4);
+            umma2_ss(d, dq + oa, dk + ob, idesc_s, kk > 0);
+          }
+          commit_pair(&k_empty[st]);
+          commit_pair(&s_full[slot]);
+          if (i == n0 - 1 && q_reload1) commit_pair(q_free);
+        }
+        __syncwarp();
+        TRACE3(2 * i, 3);
+      }
+    }
+  } else if (warp == kWarpMmaPV) {
+    // ================================ O += P.V issuer (leader only) ================================
+    if (ntot > 0 && leader) {
+      constexpr uint32_t idesc_o = make_idesc(2 * BM, DVC);
+      const uint32_t smem_base = smem_u32(smem);
+      for (int j = 0; j < 2 * ntot; ++j) {
+        const int gi = j >> 1, b = (gi & 1) * 2 + (j & 1), sv = j % VS;
+        mbar_wait_cl(&p_full[b], (gi >> 1) & 1);
+        TRACE3(j, 0);
+        const bool first = (j == 0) || (j == 2 * n0);
+        if (j == 2 * n0 && nseg > 1) mbar_wait_cl(o_drained, 0);
+        mbar_wait_cl(&v_full[sv], (j / VS) & 1);
+        fence_after();
+        TRACE3(j, 13);
+        if (elect_one()) {
+          const uint64_t dv = make_desc_sw128(smem_base + OFF_V + sv * SMEM_V);
+          const uint32_t pa = tmem + TMEM_S + b * BNS;
+#pragma unroll
+          for (int kk = 0; kk < BNS / 16; ++kk)
+            umma2_ts(tmem + TMEM_O, pa + kk * 8, dv + (uint64_t)(kk * 2), idesc_o, (first && kk == 0) ? 0u : 1u);
+          commit_pair(&v_empty[sv]);
+          commit_pair(&sp_free[b]);
+        }
+        __syncwarp();
+        TRACE3(j, 1);
+      }
+    }
+  } else if (ntot > 0) {
+    // ================================ softmax + epilogue (warps 0-7, both CTAs) ================================
+    const int quad = warp & 3, grp = warp >> 2;
+    const int row = quad * 32 + lane;                       // tile row == TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    // named barriers: group 0 -> group 1 hand-over, group 1 -> group 0 hand-over, segment-end exchange
+    const int id_in = grp == 1 ? 1 + quad : 5 + quad;
+    const int id_out = grp == 0 ? 1 + quad : 5 + quad;
+    const int id_ex = 9 + quad;
+    int j = 0;                                              // sub-tile counter over both segments (grp == j & 1)
+
+    for (int s = 0; s < nseg; ++s) {
+      const int unit = seg[s].unit;
+      const int qt = (unit / p.n_dv) * 2 + (int)rank, dvc = unit % p.n_dv;
+      const int qi = qt * BM + row;
+      const bool row_ok = qi < p.HW;
+      const float seed = (p.mseed && row_ok) ? p.mseed[qi] : -INFINITY;
+      // m_ref: the running maximum this group's l / l_piece are relative to
+      float m_ref = -INFINITY, l_tot = 0.f, l_piece = 0.f, bias2 = 0.f;
+      int cur_t = -1;
+      const int j_first = j;
+      float* piece_base = (p.pieces && dvc == 0)
+                              ? p.pieces + (((long long)(cta * 2 + s) * p.T) * 2 + grp) * (BM * 2) + row * 2
+                              : nullptr;
+      auto flush_piece = [&](int t) {
+        if (piece_base) {
+          float* d = piece_base + (long long)t * (2 * BM * 2);
+          d[0] = m_ref;
+          d[1] = l_piece;
+        }
+      };
+      for (int g = seg[s].lo; g < seg[s].hi; ++g) {
+        const int t = g / p.gpf, jg = g - t * p.gpf;
+        if (t != cur_t) {                                   // both groups walk every group's frame index
+          if (cur_t >= 0) flush_piece(cur_t);
+          cur_t = t;
+          l_piece = 0.f;
+          bias2 = (p.qbias && row_ok) ? p.qbias[(long long)qi * p.T + t] * LOG2E : 0.f;
+        }
+        // this softmax group's sub-tile of the group: j = j_first + 2 * (g - lo) + grp
+        const int jj = j + grp;
+        const int gi = jj >> 1, b = (gi & 1) * 2 + grp;
+        const bool last_of_seg = (g + 1 == seg[s].hi) && grp == 1;
+        long long* const trace_s = quad == 0 ? trace : nullptr;
+#define TRACE3_S(k) do { if (trace_s && lane == 0 && jj < 256) trace_s[(long long)jj * 16 + (k)] = clock64(); } while (0)
+        TRACE3_S(4);
+        mbar_wait_b(&s_full[gi & 1], (gi >> 1) & 1);
+        fence_after();
+        TRACE3_S(5);
+        float sc[64];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(lane_addr + TMEM_S + b * BNS, r0);
+          tmem_ld32_nowait(lane_addr + TMEM_S + b * BNS + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { sc[c] = __uint_as_float(r0[c]); sc[32 + c] = __uint_as_float(r1[c]); }
+        }
+        const int key0 = jg * BNG + grp * BNS;
+        if (key0 + BNS > p.HW) {                             // ragged / padding sub-tile at the end of the frame
+#pragma unroll
+          for (int c = 0; c < 64; ++c) sc[c] = (key0 + c < p.HW) ? sc[c] : -INFINITY;
+        }
+        // row maximum: balanced tree
+        float mx;
+        {
+          float a[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) a[c] = fmaxf(fmaxf(sc[c], sc[16 + c]), fmaxf(sc[32 + c], sc[48 + c]));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a[c] = fmaxf(fmaxf(a[c], a[4 + c]), fmaxf(a[8 + c], a[12 + c]));
+          mx = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
+        }
+        const float mt = fmaf(mx, p.scale_log2, bias2);      // scale > 0: max commutes with the affine map
+        TRACE3_S(6);
+        // ---- hand-over of the lazily updated row maximum from the other group's sub-tile jj-1 ----
+        float m_prev = seed;
+        if (jj > j_first) {
+          named_bar_sync(id_in, 64);
+          m_prev = m_sh[row];
+        }
+        const bool need = mt > m_prev + RESCALE_THRESHOLD;
+        float m_new = m_prev;
+        if (__any_sync(0xffffffffu, need)) {
+          if (jj > j_first) {
+            const int jp = jj - 1, gp = jp >> 1, bp = (gp & 1) * 2 + (jp & 1);
+            mbar_wait_b(&sp_free[bp], (gp >> 1) & 1);        // P.V(<= jj-1) retired
+            fence_after();
+            const float f = need ? exp2f(m_prev - mt) : 1.f;
+#pragma unroll 1
+            for (int c = 0; c < DVC; c += 32) {
+              float o[32];
+              tmem_ld32(lane_addr + TMEM_O + c, o);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] *= f;
+              tmem_st32(lane_addr + TMEM_O + c, o);
+            }
+            fence_before();
+            if (p.rescales && lane == 0) atomicAdd(p.rescales, 1);
+          }
+          if (need) m_new = mt;
+        }
+        if (!last_of_seg) {
+          m_sh[row] = m_new;
+          named_bar_arrive(id_out, 64);
+        }
+        TRACE3_S(7);
+        if (m_new != m_ref) {                                // bring this group's sums to the current reference
+          const float f2 = exp2f(m_ref - m_new);
+          l_tot *= f2;
+          l_piece *= f2;
+          m_ref = m_new;
+        }
+        const float c0 = bias2 - m_new;
+        uint32_t pk[32];
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+        auto exp_phase = [&](auto mode) {
+          constexpr int kMode = decltype(mode)::value;
+#pragma unroll
+          for (int c = 0; c < 64; c += 4) {
+            const float a0 = fmaf(sc[c], p.scale_log2, c0), a1 = fmaf(sc[c + 1], p.scale_log2, c0);
+            const float a2 = fmaf(sc[c + 2], p.scale_log2, c0), a3 = fmaf(sc[c + 3], p.scale_log2, c0);
+            const float e0 = exp2f(a0);
+            const float e1 = kMode >= 2 ? exp2_poly(a1) : exp2f(a1);
+            const float e2 = exp2f(a2);
+            const float e3 = kMode >= 1 ? exp2_poly(a3) : exp2f(a3);
+            ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+            pk[c >> 1] = pack2_fast(e0, e1);
+            pk[(c >> 1) + 1] = pack2_fast(e2, e3);
+          }
+        };
+        if (p.exp_mode == 0) exp_phase(std::integral_constant<int, 0>{});
+        else if (p.exp_mode == 1) exp_phase(std::integral_constant<int, 1>{});
+        else exp_phase(std::integral_constant<int, 2>{});
+        const float lsum = (ls0 + ls1) + (ls2 + ls3);
+        l_tot += lsum;
+        l_piece += lsum;
+        TRACE3_S(8);
+        // P over the first 32 columns of its own score buffer: this thread's row was fully read above
+        tmem_st32u(lane_addr + TMEM_S + b * BNS, pk);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(&p_full[b]); else mbar_arrive_leader(&p_full[b]); }
+        TRACE3_S(9);
+        j += 2;
+      }
+      flush_piece(cur_t);
+
+      // ---- segment epilogue: normalised fp16 partial O + (m, l) ----
+      lx[(grp * BM + row) * 2 + 0] = m_ref;
+      lx[(grp * BM + row) * 2 + 1] = l_tot;
+      named_bar_sync(id_ex, 64);
+      const float m_o = lx[((grp ^ 1) * BM + row) * 2 + 0], l_o = lx[((grp ^ 1) * BM + row) * 2 + 1];
+      const float M = fmaxf(m_ref, m_o);                    // == the maximum O is relative to (m is monotone)
+      const float l_row = l_tot * exp2f(m_ref - M) + l_o * exp2f(m_o - M);
+      const float inv = l_row > 0.f ? 1.f / l_row : 0.f;    // a seed far above this segment's scores can leave l = 0
+      {
+        const int last = j - 1, gl = last >> 1, bl = (gl & 1) * 2 + 1;
+        mbar_wait_b(&sp_free[bl], (gl >> 1) & 1);
+        fence_after();
+      }
+      // part_o: [slot][16-column group][row][16] -- the 32 rows of a warp are contiguous per group, so every store
+      // instruction covers whole lines
+      t16* po = p.part_o + (((long long)(cta * 2 + s) * (DVC / 16) + grp * (DVC / 32)) * BM + row) * 16;
+#pragma unroll 1
+      for (int c = 0; c < DVC / 2; c += 32) {
+        float o[32];
+        tmem_ld32(lane_addr + TMEM_O + grp * (DVC / 2) + c, o);
+        if (row_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 u;
+            u.x = pack2(o[e] * inv, o[e + 1] * inv);
+            u.y = pack2(o[e + 2] * inv, o[e + 3] * inv);
+            u.z = pack2(o[e + 4] * inv, o[e + 5] * inv);
+            u.w = pack2(o[e + 6] * inv, o[e + 7] * inv);
+            *reinterpret_cast<uint4*>(po + (long long)((c + e) >> 4) * (BM * 16) + ((c + e) & 8)) = u;
+          }
+        }
+      }
+      if (grp == 0) {
+        float* ml = p.part_ml + ((long long)(cta * 2 + s) * BM + row) * 2;
+        ml[0] = M;
+        ml[1] = l_row;
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0 && s + 1 < nseg) mbar_arrive_leader(o_drained);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  cluster_sync_all();           // the leader's MMAs read the peer's shared memory and write its TMEM until here
+  if (cta_times && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cta_times[1] = (long long)gt; cta_times[2] = ntot; cta_times[3] = nseg; cta_times[6] = clock64();
+  }
+  if (warp == kWarpMmaS) {
+    fence_after();
+    tmem_dealloc_pair(tmem);
+  }
+}
+
+// Merge the segments of every unit: out = (sum_s w_s O_s) * gate with w_s = l_s 2^(m_s - M) / L;
+// mass[i,t] = sum_{pieces of frame t} l_p 2^(m_p - M) / L  (from the Dv-chunk-0 units).
+// Four query rows per block, 64 threads x 16 columns per row (see attn_tc2.cu's combine2_kernel; here a unit covers a
+// PAIR of query tiles and the partial slot is (cluster * 2 + rank) * 2 + segment).
+constexpr int kMaxSegsPerUnit = 24;
+constexpr int kCombRows = 4;
+constexpr int kColGroups = DVC / 16;
+static_assert(BM % kCombRows == 0, "the rows of a combine block share a query tile");
+__global__ void __launch_bounds__(256) combine3_kernel(const Tc3Params p, const t16* __restrict__ gate, long long ldg,
+                                                       t16* __restrict__ out, long long ldo,
+                                                       float* __restrict__ mass) {
+  pdl_prologue();
+  __shared__ int s_n[kCombRows][4];
+  __shared__ int s_slot[kCombRows][4][kMaxSegsPerUnit];        // (cta * 2 + seg)
+  __shared__ float s_w[kCombRows][4][kMaxSegsPerUnit];         // l_s 2^(m_s - M) / L
+  __shared__ float s_M0[kCombRows], s_L0[kCombRows];
+  __shared__ int s_alo[kCombRows][kMaxSegsPerUnit], s_ahi[kCombRows][kMaxSegsPerUnit];   // unit-0 group ranges
+  const int rr = threadIdx.x >> 6, tc = threadIdx.x & 63;
+  const int i = blockIdx.x * kCombRows + rr;
+  const bool live = i < p.HW;
+  const int qt = (blockIdx.x * kCombRows) / BM, r = i - qt * BM;
+  const int qp = qt >> 1, rank = qt & 1;
+  if (live && tc < p.n_dv) {
+    const int k = tc;
+    const int unit = qp * p.n_dv + k;
+    const long long u_lo = (long long)unit * p.TPU, u_hi = u_lo + p.TPU;
+    int c = 0;                                       // first cluster whose range reaches past u_lo (bounds ascend)
+    for (int step = 64; step > 0; step >>= 1)
+      if (c + step < p.nCL && p.bounds[c + step] <= u_lo) c += step;
+    if (p.bounds[c + 1] <= u_lo) ++c;
+    int n = 0;
+    float M = -INFINITY;
+    for (; c < p.nCL && n < kMaxSegsPerUnit; ++c) {
+      const long long lo = p.bounds[c], hi = p.bounds[c + 1];
+      if (lo >= u_hi) break;
+      if (hi <= lo) continue;
+      const int slot = (c * 2 + rank) * 2 + (lo < u_lo ? 1 : 0);
+      s_slot[rr][k][n] = slot;
+      if (k == 0) {
+        s_alo[rr][n] = (int)((lo > u_lo ? lo : u_lo) - u_lo);
+        s_ahi[rr][n] = (int)((hi < u_hi ? hi : u_hi) - u_lo);
+      }
+      const float* ml = p.part_ml + ((long long)slot * BM + r) * 2;
+      if (ml[1] > 0.f) M = fmaxf(M, ml[0]);
+      ++n;
+    }
+    float L = 0.f;
+    for (int e = 0; e < n; ++e) {
+      const float* ml = p.part_ml + ((long long)s_slot[rr][k][e] * BM + r) * 2;
+      const float w = ml[1] > 0.f ? exp2f(ml[0] - M) * ml[1] : 0.f;
+      s_w[rr][k][e] = w;
+      L += w;
+    }
+    const float inv = L > 0.f ? 1.f / L : 0.f;
+    for (int e = 0; e < n; ++e) s_w[rr][k][e] *= inv;
+    s_n[rr][k] = n;
+    if (k == 0) { s_M0[rr] = M; s_L0[rr] = L; }
+  }
+  __syncthreads();
+  const int col = tc * 16;
+  if (live && col < p.Dv) {
+    const int k = col / DVC, cg = (col - k * DVC) >> 4;
+    const int n = s_n[rr][k];
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int e = 0; e < n; ++e) {
+      const float w = s_w[rr][k][e];
+      const uint4* src = reinterpret_cast<const uint4*>(
+          p.part_o + (((long long)s_slot[rr][k][e] * kColGroups + cg) * BM + r) * 16);
+      const uint4 u0 = src[0], u1 = src[1];
+      const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 f = unpack2(uu[c]);
+        acc[c * 2] = fmaf(w, f.x, acc[c * 2]);
+        acc[c * 2 + 1] = fmaf(w, f.y, acc[c * 2 + 1]);
+      }
+    }
+    if (gate) {
+      const uint4* gp = reinterpret_cast<const uint4*>(gate + (long long)i * ldg + col);
+      const uint4 g0 = gp[0], g1 = gp[1];
+      const uint32_t gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 f = unpack2(gg[c]);
+        acc[c * 2] *= f.x;
+        acc[c * 2 + 1] *= f.y;
+      }
+    }
+    uint4 o0, o1;
+    o0.x = pack2(acc[0], acc[1]); o0.y = pack2(acc[2], acc[3]); o0.z = pack2(acc[4], acc[5]); o0.w = pack2(acc[6], acc[7]);
+    o1.x = pack2(acc[8], acc[9]); o1.y = pack2(acc[10], acc[11]); o1.z = pack2(acc[12], acc[13]); o1.w = pack2(acc[14], acc[15]);
+    uint4* op = reinterpret_cast<uint4*>(out + (long long)i * ldo + col);
+    op[0] = o0;
+    op[1] = o1;
+  }
+  if (mass && live && tc < p.T) {
+    const int t = tc;
+    const int f_lo = t * p.gpf, f_hi = f_lo + p.gpf;
+    const float M = s_M0[rr], invL = s_L0[rr] > 0.f ? 1.f / s_L0[rr] : 0.f;
+    float a = 0.f;
+    for (int e = 0; e < s_n[rr][0]; ++e) {
+      if (s_alo[rr][e] < f_hi && f_lo < s_ahi[rr][e]) {
+        const float* pc = p.pieces + ((((long long)s_slot[rr][0][e] * p.T + t) * 2) * BM + r) * 2;
+        // a piece whose sum is zero may carry m = -inf (no sub-tile of that frame seen by the group): skip it
+        if (pc[1] > 0.f) a += exp2f(pc[0] - M) * pc[1];
+        if (pc[BM * 2 + 1] > 0.f) a += exp2f(pc[BM * 2] - M) * pc[BM * 2 + 1];
+      }
+    }
+    mass[(long long)i * p.T + t] = a * invL;
+  }
+}
+
+// Seed of the running row maximum: the best score of query i against the keys at its own position and the 8 neighbours
+// in every bank frame (T x 9 dot products of 128) -- a LOWER bound of the true maximum that is close to it whenever the
+// match is local or the score distribution is broad.  One warp per query; lane l holds dk channels 4l..4l+3.
+__global__ void __launch_bounds__(256) attn_seed_kernel(const t16* __restrict__ qt, const float* __restrict__ qbias,
+                                                        const t16* __restrict__ kbank, Tc3Params p, int h, int w,
+                                                        float* __restrict__ mseed) {
+  pdl_prologue();
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= p.HW) return;
+  const uint2 qu = *reinterpret_cast<const uint2*>(qt + (long long)i * DK + lane * 4);
+  const float2 q0 = unpack2(qu.x), q1 = unpack2(qu.y);
+  const int y = i / w, x = i - y * w;
+  float best = -INFINITY;
+  for (int t = 0; t < p.T; ++t) {
+    const t16* kb = kbank + (long long)p.slot[t] * p.HWp * DK;
+    const float b2 = qbias ? qbias[(long long)i * p.T + t] * LOG2E : 0.f;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const uint2 ku = *reinterpret_cast<const uint2*>(kb + (long long)(yy * w + xx) * DK + lane * 4);
+        const float2 k0 = unpack2(ku.x), k1 = unpack2(ku.y);
+        float s = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+        s = warp_sum(s);
+        best = fmaxf(best, fmaf(s, p.scale_log2, b2));
+      }
+    }
+  }
+  if (lane == 0) mseed[i] = best;
+}
+
+int sm_count3() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// Static schedule in groups of 128 keys (see attn_tc2.cu make_bounds): equalise groups + kSegCost * segments
+// (+ kRestartCost for a second segment) over the clusters.  A segment epilogue (TMEM read-out of O at 64 B/clk) costs
+// about three group-times.
+constexpr int kSegCost = 3, kRestartCost = 1;
+bool greedy_bounds(long long L, int TPU, int n, long long budget, int m, int* b) {
+  long long pos = 0;
+  for (int c = 0; c < n; ++c) {
+    b[c] = (int)pos;
+    long long room = budget - (c >= m ? 1 : 0) - kSegCost;
+    bool second = false;
+    while (room > 0 && pos < L) {
+      const long long unit_end = (pos / TPU + 1) * TPU;
+      const long long take = room < unit_end - pos ? room : unit_end - pos;
+      pos += take;
+      room -= take;
+      if (pos == unit_end && pos < L) {
+        if (second) break;
+        second = true;
+        room -= kSegCost + kRestartCost;
+      }
+    }
+  }
+  b[n] = (int)L;
+  return pos >= L;
+}
+void make_bounds(long long L, int TPU, int n, int* b) {
+  const long long uni = (L + n - 1) / n;
+  if (uni < 8) {                                         // short launches keep the uniform cut
+    for (int c = 0; c <= n; ++c) b[c] = (int)((L * c) / n);
+    return;
+  }
+  long long lo = uni, hi = uni + 2 * kSegCost + kRestartCost + 2;
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if (greedy_bounds(L, TPU, n, mid, n, b)) hi = mid; else lo = mid + 1;
+  }
+  int mlo = 0, mhi = n;
+  while (mlo < mhi) {
+    const int mid = (mlo + mhi) / 2;
+    if (greedy_bounds(L, TPU, n, lo, mid, b)) mhi = mid; else mlo = mid + 1;
+  }
+  greedy_bounds(L, TPU, n, lo, mlo, b);
+}
+
+void schedule3(int HW, int T, int Dv, int* n_units, int* gpf, int* TPU, int* nCL) {
+  const int qpairs = cdiv(cdiv(HW, BM), 2), n_dv = Dv / DVC;
+  *n_units = qpairs * n_dv;
+  *gpf = cdiv(HW, BNG);
+  *TPU = T * *gpf;
+  const long long L = (long long)*n_units * *TPU;
+  int n = sm_count3() / 2;
+  if (n > kMaxCL) n = kMaxCL;
+  if ((long long)n > L / 2) n = (int)(L / 2);                   // at least ~2 groups per cluster
+  const int cap = (kMaxSegsPerUnit - 2) * *n_units;             // combine3 resolves <= kMaxSegsPerUnit segments per unit
+  if (n > cap) n = cap;
+  // Short launches (the T = 1 self-attention: ~5 groups per cluster): a segment epilogue costs about three groups, so a
+  // cluster that straddles two units pays more in epilogues than the last SMs are worth -- k whole-segment clusters per unit.
+  if (L / n < 8 && n / *n_units >= 2) n = (n / *n_units) * *n_units;
+  if (n < *n_units) n = *n_units;                               // a cluster never spans more than two units
+  if ((long long)n > L) n = (int)L;
+  if (n < 1) n = 1;
+  *nCL = n;
+}
+
+size_t part_bytes3(int nCL, int T, size_t* off_ml, size_t* off_pieces, size_t* off_seed, int HW) {
+  const size_t nCTA = (size_t)nCL * 2;
+  size_t o = nCTA * 2 * BM * DVC * sizeof(t16);
+  o = (o + 255) & ~size_t(255);
+  *off_ml = o;
+  o += nCTA * 2 * BM * 2 * sizeof(float);
+  o = (o + 255) & ~size_t(255);
+  *off_pieces = o;
+  o += nCTA * 2 * T * 2 * BM * 2 * sizeof(float);
+  o = (o + 255) & ~size_t(255);
+  *off_seed = o;
+  o += (size_t)HW * sizeof(float);
+  return o + 256;
+}
+
+}  // namespace
+
+static thread_local cudaEvent_t g3_ev0 = nullptr, g3_ev1 = nullptr;
+void long_attn_tc3_set_events(void* ev0, void* ev1) {
+  g3_ev0 = reinterpret_cast<cudaEvent_t>(ev0);
+  g3_ev1 = reinterpret_cast<cudaEvent_t>(ev1);
+}
+static thread_local int* g3_rescales = nullptr;
+void long_attn_tc3_set_rescale_counter(int* dev_counter) { g3_rescales = dev_counter; }
+
+int long_attn_tc3_set_trace(long long* dev_buf) {
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("RMEM_TRACE_CTA");
+    cl = e ? atoi(e) : 0;
+    RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace3_cl, &cl, sizeof(cl)));
+  }
+  RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace3, &dev_buf, sizeof(dev_buf)));
+  return RMEM_OK;
+}
+
+// Host-only view of the static schedule (tests): step range of every cluster for a launch of this shape.
+int long_attn_tc3_schedule(int HW, int T, int Dv, int* n_units, int* groups_per_unit, int* n_clusters, int* bounds,
+                           int cap) {
+  int gpf = 0;
+  schedule3(HW, T, Dv, n_units, &gpf, groups_per_unit, n_clusters);
+  RMEM_REQUIRE(*n_clusters + 1 <= cap && *n_clusters <= kMaxCL, "schedule: %d clusters do not fit the caller's table (%d)",
+               *n_clusters, cap);
+  make_bounds((long long)*n_units * *groups_per_unit, *groups_per_unit, *n_clusters, bounds);
+  return RMEM_OK;
+}
+
+size_t long_attn_tc3_workspace(int HW, int HWp, int nslots, int Dv) {
+  (void)HWp;
+  size_t best = 0;
+  for (int T = 1; T <= nslots && T <= kMaxBankFrames; ++T) {
+    int n_units, gpf, TPU, nCL;
+    schedule3(HW, T, Dv, &n_units, &gpf, &TPU, &nCL);
+    size_t a, b, c;
+    const size_t n = part_bytes3(nCL, T, &a, &b, &c, HW);
+    if (n > best) best = n;
+  }
+  return best;
+}
+
+int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  RMEM_REQUIRE(a.Dk == DK, "long_attn_tc3: Dk=%d (built for 128)", a.Dk);
+  RMEM_REQUIRE(a.Dv % DVC == 0 && a.Dv <= 1024, "long_attn_tc3: Dv=%d must be a multiple of 256, <= 1024", a.Dv);
+  RMEM_REQUIRE(a.HWp % BNG == 0 && a.HWp >= a.HW, "long_attn_tc3: HWp=%d must be a multiple of 128", a.HWp);
+  RMEM_REQUIRE(a.T >= 1 && a.T <= kMaxBankFrames && a.T <= a.nslots, "long_attn_tc3: T=%d nslots=%d", a.T, a.nslots);
+  RMEM_REQUIRE(a.ldo % 8 == 0 && (!a.gate || a.ldg % 8 == 0), "long_attn_tc3: ldo/ldg alignment");
+  RMEM_REQUIRE(a.seed_h * a.seed_w == a.HW || a.seed_h == 0, "long_attn_tc3: seed grid %dx%d != HW=%d", a.seed_h,
+               a.seed_w, a.HW);
+  Tc3Params p;
+  p.HW = a.HW; p.HWp = a.HWp; p.T = a.T; p.Dv = a.Dv; p.n_dv = a.Dv / DVC;
+  schedule3(a.HW, a.T, a.Dv, &p.n_units, &p.gpf, &p.TPU, &p.nCL);
+  RMEM_REQUIRE(p.nCL <= kMaxCL, "long_attn_tc3: %d clusters > %d", p.nCL, kMaxCL);
+  make_bounds((long long)p.n_units * p.TPU, p.TPU, p.nCL, p.bounds);
+  size_t off_ml, off_pieces, off_seed;
+  const size_t need = part_bytes3(p.nCL, a.T, &off_ml, &off_pieces, &off_seed, a.HW);
+  RMEM_REQUIRE(workspace_bytes >= need, "long_attn_tc3: workspace %zu < %zu", workspace_bytes, need);
+  RMEM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "long_attn_tc3: workspace alignment");
+  for (int t = 0; t < kMaxBankFrames; ++t) p.slot[t] = t < a.T ? a.slot[t] : 0;
+  p.scale_log2 = a.scale * LOG2E;
+  p.qbias = a.qbias;
+  char* ws = reinterpret_cast<char*>(workspace);
+  p.part_o = reinterpret_cast<t16*>(ws);
+  p.part_ml = reinterpret_cast<float*>(ws + off_ml);
+  p.pieces = a.mass ? reinterpret_cast<float*>(ws + off_pieces) : nullptr;
+  float* mseed = reinterpret_cast<float*>(ws + off_seed);
+  p.mseed = a.seed_h > 0 ? mseed : nullptr;
+  p.rescales = g3_rescales;
+  {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("RMEM_ATTN_EXP"); mode = e ? atoi(e) : 0; if (mode < 0 || mode > 2) mode = 0; }
+    p.exp_mode = mode;
+  }
+
+  RMEM_REQUIRE((reinterpret_cast<uintptr_t>(a.qt) & 15) == 0, "long_attn_tc3: q alignment");
+  const CUtensorMap *mq, *mk, *mv;
+  {
+    uint64_t dims[2] = {(uint64_t)DK, (uint64_t)a.HW};
+    uint64_t str[1] = {(uint64_t)DK * 2};
+    uint32_t box[2] = {64, (uint32_t)BM};
+    RMEM_TRY(tma_encode_cached(&mq, a.qt, 2, dims, str, box, nullptr));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)DK, (uint64_t)a.nslots * a.HWp};
+    uint64_t str[1] = {(uint64_t)DK * 2};
+    uint32_t box[2] = {64, (uint32_t)(BNG / 2)};
+    RMEM_TRY(tma_encode_cached(&mk, a.kbank, 2, dims, str, box, nullptr));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.nslots * a.HWp, (uint64_t)a.Dv};
+    uint64_t str[1] = {(uint64_t)a.nslots * a.HWp * 2};
+    uint32_t box[2] = {(uint32_t)BNS, (uint32_t)(DVC / 2)};
+    RMEM_TRY(tma_encode_cached(&mv, a.vtbank, 2, dims, str, box, nullptr));
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    RMEM_CUDA_CHECK(cudaFuncSetAttribute(long_attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_done = true;
+  }
+  if (p.mseed) {
+    RMEM_CUDA_CHECK(launch_pdl(attn_seed_kernel, dim3(cdiv(a.HW, 8)), dim3(256), 0, s, a.qt, a.qbias, a.kbank, p,
+                               a.seed_h, a.seed_w, mseed));
+    RMEM_LAUNCH_CHECK();
+  }
+  if (g3_ev0) RMEM_CUDA_CHECK(cudaEventRecord(g3_ev0, s));
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.nCL * 2);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    RMEM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, long_attn_tc3_kernel, *mq, *mk, *mv, static_cast<const Tc3Params&>(p)));
+  }
+  if (g3_ev1) RMEM_CUDA_CHECK(cudaEventRecord(g3_ev1, s));
+  RMEM_LAUNCH_CHECK();
+  RMEM_CUDA_CHECK(launch_pdl(combine3_kernel, dim3(cdiv(a.HW, kCombRows)), dim3(256), 0, s, p, a.gate, a.ldg, a.out,
+                             a.ldo, a.mass));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+}  // namespace rmem

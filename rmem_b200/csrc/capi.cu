@@ -62,9 +62,10 @@ int rmem_set_gemm_impl(int impl) {
 
 int rmem_long_attn_workspace_bytes(int impl, int HW, int HWp, int nslots, int Dv, size_t* bytes) {
   RMEM_REQUIRE(bytes, "null bytes");
-  *bytes = impl == RMEM_ATTN_TC2 ? long_attn_tc2_workspace(HW, HWp, nslots, Dv)
-           : impl == RMEM_ATTN_TC ? long_attn_tc_workspace(HW, HWp, nslots, Dv)
-                                  : long_attn_dense_workspace(HW, HWp, nslots);
+  RMEM_REQUIRE(impl == RMEM_ATTN_DENSE || impl == RMEM_ATTN_TC2 || impl == RMEM_ATTN_TC3, "attention impl %d", impl);
+  *bytes = impl == RMEM_ATTN_TC3 ? long_attn_tc3_workspace(HW, HWp, nslots, Dv)
+           : impl == RMEM_ATTN_TC2 ? long_attn_tc2_workspace(HW, HWp, nslots, Dv)
+                                   : long_attn_dense_workspace(HW, HWp, nslots);
   return RMEM_OK;
 }
 
@@ -72,32 +73,52 @@ int rmem_long_attn_fwd(int impl, const void* qt, const float* qbias, const void*
                        int T, const int* slots, int HW, int HWp, int Dk, int Dv, float scale, const void* gate,
                        long long ldg, void* out, long long ldo, float* mass, void* workspace, size_t workspace_bytes,
                        void* stream) {
+  return rmem_long_attn_grid_fwd(impl, qt, qbias, kbank, vtbank, nslots, T, slots, HW, HWp, Dk, Dv, scale, gate, ldg, out,
+                                 ldo, mass, 0, 0, workspace, workspace_bytes, stream);
+}
+
+int rmem_long_attn_grid_fwd(int impl, const void* qt, const float* qbias, const void* kbank, const void* vtbank,
+                            int nslots, int T, const int* slots, int HW, int HWp, int Dk, int Dv, float scale,
+                            const void* gate, long long ldg, void* out, long long ldo, float* mass, int grid_h,
+                            int grid_w, void* workspace, size_t workspace_bytes, void* stream) {
   RMEM_REQUIRE(qt && kbank && vtbank && out && slots && workspace, "null argument");
   RMEM_REQUIRE(T >= 1 && T <= kMaxBankFrames, "T=%d out of range", T);
+  RMEM_REQUIRE((grid_h == 0 && grid_w == 0) || (grid_h > 0 && grid_w > 0 && grid_h * grid_w == HW),
+               "token grid %dx%d does not match HW=%d", grid_h, grid_w, HW);
   LongAttnArgs a;
   a.qt = (const t16*)qt; a.qbias = qbias; a.kbank = (const t16*)kbank; a.vtbank = (const t16*)vtbank;
   a.nslots = nslots; a.T = T;
   for (int t = 0; t < T; ++t) a.slot[t] = slots[t];
   a.HW = HW; a.HWp = HWp; a.Dk = Dk; a.Dv = Dv; a.scale = scale;
   a.gate = (const t16*)gate; a.ldg = ldg; a.out = (t16*)out; a.ldo = ldo; a.mass = mass;
+  a.seed_h = grid_h; a.seed_w = grid_w;
+  if (impl == RMEM_ATTN_TC3) return long_attn_tc3(a, workspace, workspace_bytes, STREAM(stream));
   if (impl == RMEM_ATTN_TC2) return long_attn_tc2(a, workspace, workspace_bytes, STREAM(stream));
-  if (impl == RMEM_ATTN_TC) return long_attn_tc(a, workspace, workspace_bytes, STREAM(stream));
+  RMEM_REQUIRE(impl == RMEM_ATTN_DENSE, "attention impl %d (0 dense, 2 tc2, 3 tc3)", impl);
   return long_attn_dense(a, workspace, workspace_bytes, STREAM(stream));
 }
 
 int rmem_debug_gemm_trace(void* dev_buf) { return gemm_tc_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 int rmem_debug_attn_events(void* ev0, void* ev1) {
   long_attn_tc2_set_events(ev0, ev1);
+  long_attn_tc3_set_events(ev0, ev1);
   return RMEM_OK;
 }
-int rmem_debug_attn_schedule(int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds,
+int rmem_debug_attn_rescale_counter(void* dev_int) {
+  long_attn_tc3_set_rescale_counter(reinterpret_cast<int*>(dev_int));
+  return RMEM_OK;
+}
+int rmem_debug_attn_schedule(int impl, int HW, int T, int Dv, int* n_units, int* tiles_per_unit, int* n_cta, int* bounds,
                              int cap) {
   RMEM_REQUIRE(n_units && tiles_per_unit && n_cta && bounds, "null argument");
+  if (impl == RMEM_ATTN_TC3) return long_attn_tc3_schedule(HW, T, Dv, n_units, tiles_per_unit, n_cta, bounds, cap);
+  RMEM_REQUIRE(impl == RMEM_ATTN_TC2, "attention impl %d has no static schedule", impl);
   return long_attn_tc2_schedule(HW, T, Dv, n_units, tiles_per_unit, n_cta, bounds, cap);
 }
 
 int rmem_debug_attn_trace(void* dev_buf) {
   RMEM_TRY(local_attn_tc_set_trace(reinterpret_cast<long long*>(dev_buf)));
+  RMEM_TRY(long_attn_tc3_set_trace(reinterpret_cast<long long*>(dev_buf)));
   return long_attn_tc2_set_trace(reinterpret_cast<long long*>(dev_buf));
 }
 

@@ -316,9 +316,9 @@ struct rmem_engine {
       mha_ws = a.take<char>(mha_ws_bytes);
     }
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
-    size_t ws_tc = long_attn_tc_workspace(G.HW, G.HWp, nslots, kDv);
     size_t ws_tc2 = long_attn_tc2_workspace(G.HW, G.HWp, nslots, kDv);
-    attn_ws_bytes = cfg.attn_impl == RMEM_ATTN_TC2 ? ws_tc2 : (cfg.attn_impl == RMEM_ATTN_TC ? ws_tc : ws_dense);
+    size_t ws_tc3 = long_attn_tc3_workspace(G.HW, G.HWp, nslots, kDv);
+    attn_ws_bytes = cfg.attn_impl == RMEM_ATTN_TC3 ? ws_tc3 : (cfg.attn_impl == RMEM_ATTN_TC2 ? ws_tc2 : ws_dense);
     attn_ws = a.take<char>(attn_ws_bytes);
     local_ws_bytes = local_attn_tc_workspace(G.h, G.w, kDv);
     local_ws = a.take<char>(local_ws_bytes);
@@ -524,9 +524,10 @@ struct rmem_engine {
     return RMEM_OK;
   }
 
-  int attention(const LongAttnArgs& a, cudaStream_t s) {
+  int attention(LongAttnArgs& a, cudaStream_t s) {
+    a.seed_h = g.h; a.seed_w = g.w;      // token grid: tc3 seeds the row maximum from the query's own neighbourhood
+    if (cfg.attn_impl == RMEM_ATTN_TC3) return long_attn_tc3(a, attn_ws, attn_ws_bytes, s);
     if (cfg.attn_impl == RMEM_ATTN_TC2) return long_attn_tc2(a, attn_ws, attn_ws_bytes, s);
-    if (cfg.attn_impl == RMEM_ATTN_TC) return long_attn_tc(a, attn_ws, attn_ws_bytes, s);
     return long_attn_dense(a, attn_ws, attn_ws_bytes, s);
   }
 
@@ -998,6 +999,8 @@ extern "C" {
 int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
   RMEM_REQUIRE(cfg && bytes, "null argument");
   RMEM_REQUIRE(cfg->model == 0 || cfg->model == 1, "model %d: 0 = r50_deaotl, 1 = r50_aotl", cfg->model);
+  RMEM_REQUIRE(cfg->attn_impl == RMEM_ATTN_DENSE || cfg->attn_impl == RMEM_ATTN_TC2 || cfg->attn_impl == RMEM_ATTN_TC3,
+               "attn_impl %d: 0 = dense, 2 = tc2, 3 = tc3", cfg->attn_impl);
   RMEM_REQUIRE(cfg->H > 16 && cfg->W > 16 && (cfg->H - 1) % 16 == 0 && (cfg->W - 1) % 16 == 0,
                "input size %dx%d is not 16k+1 (snap with MultiRestrictSize first)", cfg->H, cfg->W);
   RMEM_REQUIRE(cfg->max_engines >= 1 && cfg->max_engines <= 4, "max_engines=%d out of 1..4", cfg->max_engines);

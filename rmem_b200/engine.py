@@ -32,7 +32,7 @@ class RmemConfig:
     former_mem_len: int = 1          # FORMER_MEM_LEN
     latter_mem_len: int = 7          # LATTER_MEM_LEN
     max_obj_num: int = MAX_OBJ
-    attn_impl: int = _capi.ATTN_TC2
+    attn_impl: int = _capi.ATTN_TC3
     max_engines: int = 4
 
 

@@ -225,8 +225,10 @@ def build_bank(k_frames: torch.Tensor, v_frames: torch.Tensor, nslots: int, slot
 def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, slots: Sequence[int], HW: int,
                    pe_cur: Optional[torch.Tensor] = None, mem_pos_emb: Optional[torch.Tensor] = None,
                    gate: Optional[torch.Tensor] = None, impl: int = _capi.ATTN_DENSE,
-                   want_mass: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """q t16 [HW,Dk] (no PE, unscaled).  Returns (out t16 [HW,Dv], mass fp32 [HW,T])."""
+                   want_mass: bool = True, grid: Optional[Tuple[int, int]] = None
+                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """q t16 [HW,Dk] (no PE, unscaled).  Returns (out t16 [HW,Dv], mass fp32 [HW,T]).
+    grid = (h, w) token grid (h*w == HW): lets ATTN_TC3 seed the row maximum from the query's own neighbourhood."""
     lib = _capi.load()
     nslots, HWp, Dk = kbank.shape
     Dv = vtbank.shape[0]
@@ -248,11 +250,13 @@ def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, s
     out = torch.empty(HW, Dv, dtype=_capi.op_dtype(), device=dev)
     mass = torch.empty(HW, T, dtype=torch.float32, device=dev) if want_mass else None
     sl = (C.c_int * T)(*slots)
-    _capi.check(lib.rmem_long_attn_fwd(impl, _capi.ptr(qt), _capi.ptr(qbias) if mem_pos_emb is not None else None,
-                                       _capi.ptr(kbank), _capi.ptr(vtbank), nslots, T, sl, HW, HWp, Dk, Dv,
-                                       C.c_float(scale), _capi.ptr(gate), C.c_longlong(gate.stride(0) if gate is not None else 0),
-                                       _capi.ptr(out), C.c_longlong(Dv), _capi.ptr(mass), _capi.ptr(ws),
-                                       C.c_size_t(nbytes.value), _capi.stream_ptr()))
+    gh, gw = grid if grid is not None else (0, 0)
+    _capi.check(lib.rmem_long_attn_grid_fwd(impl, _capi.ptr(qt), _capi.ptr(qbias) if mem_pos_emb is not None else None,
+                                            _capi.ptr(kbank), _capi.ptr(vtbank), nslots, T, sl, HW, HWp, Dk, Dv,
+                                            C.c_float(scale), _capi.ptr(gate),
+                                            C.c_longlong(gate.stride(0) if gate is not None else 0),
+                                            _capi.ptr(out), C.c_longlong(Dv), _capi.ptr(mass), int(gh), int(gw),
+                                            _capi.ptr(ws), C.c_size_t(nbytes.value), _capi.stream_ptr()))
     return out, mass
 
 

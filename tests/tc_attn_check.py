@@ -16,7 +16,9 @@ from oracle import rmem_oracle as O  # noqa: E402
 from rmem_b200 import _capi, ops as K  # noqa: E402
 
 OP = _capi.op_dtype()
-IMPL = int(os.environ.get("RMEM_ATTN_IMPL", str(_capi.ATTN_TC2)))
+IMPL = int(os.environ.get("RMEM_ATTN_IMPL", str(_capi.ATTN_TC3)))
+SEED = os.environ.get("RMEM_ATTN_SEED", "1") != "0"      # pass the token grid (tc3: seeded row maximum)
+GRIDS = {289: (17, 17), 357: (17, 21), 1674: (31, 54), 3726: (46, 81), 70: (7, 10)}
 
 
 def bfr(t):
@@ -68,9 +70,13 @@ def main():
         rec = dict(case=name)
         try:
             od, md = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=_capi.ATTN_DENSE, **args)
-            ot, mt = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=IMPL, **args)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            _capi.check(_capi.load().rmem_debug_attn_rescale_counter(_capi.ptr(cnt)))
+            ot, mt = K.long_attention(q.to(dev).to(OP), kb, vtb, slots, HW, impl=IMPL,
+                                      grid=GRIDS[HW] if SEED else None, **args)
             torch.cuda.synchronize()
-            rec.update(ok=True, impl=IMPL, tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
+            _capi.check(_capi.load().rmem_debug_attn_rescale_counter(None))
+            rec.update(ok=True, impl=IMPL, seeded=SEED, rescales=int(cnt.item()), tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
                        tc_vs_dense=relfro(ot, od), mass_err=float((mt.cpu() - ref_mass).abs().max()),
                        mass_sum_err=float((mt.sum(1).cpu() - 1).abs().max()),
                        finite=bool(torch.isfinite(ot.float()).all()))
