@@ -195,6 +195,14 @@ int rmem_engine_num_groups(const rmem_engine* e);
 int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx /*HOST, cap 17*/, int* n);
 int rmem_engine_pred_logits(const rmem_engine* e, int group, const float** logits4, int* h4, int* w4);
 int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel /*HOST cap 16*/, int* n, int* drop);
+/* One GPM layer's memories of an object group (DeAOT), valid after update_memory: the restricted long-term bank
+ * (LongShortTermTransformer long_term_memories, transformer.py:993-1007) as kbank t16 [nslots][HWp][128] and vtbank t16
+ * [1024][nslots*HWp] (V || ID_V, value-major), the logical->physical slot table (HOST out, cap 16, T entries), and the
+ * short-term memory = last propagated frame's K (= Q) [HW,128] and V || ID_V [HW,1024].  Device pointers into the arena;
+ * any out parameter may be NULL.  Used by the layer-level parity tests and by bench.py's per-layer roofline. */
+int rmem_engine_layer_memory(const rmem_engine* e, int group, int layer, const void** kbank, const void** vtbank,
+                             const void** q_last, const void** vid_last, int* nslots, int* HWp, int* T,
+                             int* slots /*HOST cap 16*/);
 long long rmem_engine_launch_count(const rmem_engine* e);
 /* Software pipelining across frames: encode the NEXT frame (aot.py:116-134, no dependency on the memory bank) on the
  * engine's side stream while the current frame is propagated.  `img` must be ready on `stream`; the following

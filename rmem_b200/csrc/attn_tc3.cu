@@ -7,9 +7,14 @@
 //     tcgen05.mma.cta_group::2 (M = 256) reads half of the B operand from each CTA's shared memory, so every SM ingests
 //     24 KB per 64 keys.  One thread of the leader CTA issues the MMAs for both; tcgen05.commit ... multicast::cluster
 //     releases the rings and score buffers of both CTAs; each CTA's TMA signals the leader's `full` barriers.
-//   * S = Q.K^T is computed 128 keys at a time (N = 128: ~68 cycles per K=16 step instead of 2 x 49 at N = 64); the
-//     query tile moved from TMEM to shared memory (TMA, once per segment) to make room for 2 x 128 score columns -- with
-//     the B traffic halved, shared-memory bandwidth (the reason it lived in TMEM) is no longer the binding resource.
+//   * The query tile moved from TMEM to shared memory (TMA, once per segment) -- with the B traffic halved, shared-memory
+//     bandwidth (the reason it lived in TMEM) is no longer the binding resource -- which frees TMEM for separate score and
+//     probability buffers.
+//   * Scores and probabilities no longer share TMEM columns.  With P written over its own score buffer a score slot was
+//     tied up for the whole S -> softmax -> P.V chain (~4300 cycles for two groups in flight, tensor pipe 74 % busy:
+//     profiles/r02_attn3_trace_2slots.txt).  Now there is ONE 128-column score slot that goes back to the S issuer as soon
+//     as every softmax warp holds its scores in registers (~300 cycles after the MMA), and four 32-column P buffers
+//     (two groups in flight) that are recycled when their P.V MMA retires.
 //   * The lazy rescale of O (tcgen05.ld/st round trip over 256 columns behind a drained P.V pipeline) was the
 //     data-dependent slow path: on peaked scores (sigma ~ 15-20 log2 units in GPM layers 1-2) ~45 % of the tiles hit it.
 //     The row maximum is now SEEDED with a lower bound of the true maximum computed by attn_seed_kernel (scores against
@@ -17,15 +22,15 @@
 //     head-room (2^15) of the seed, so rescales become rare (tools/attn_rescale_sim.py); the rescale path itself stays as
 //     the always-correct fallback.
 //
-//   cluster = 2 CTAs x 384 threads: warps 0-3 softmax group 0 (even 64-key sub-tiles), 4-7 group 1 (odd sub-tiles),
-//                                   8 Q/K producer, 9 V producer, 10 S issuer (leader) + TMEM owner, 11 P.V issuer (leader)
-//   TMEM (512 cols per CTA): O[256] | 2 slots x (S[64] | S[64]);  P (packed fp16) aliases the first 32 columns of its S
-//   smem per CTA: Q 32 KB | K ring 3 x 16 KB (64 of a group's 128 keys) | V^T ring 8 x 16 KB (128 of 256 dv rows x 64 keys)
+//   cluster = 2 CTAs x 512 threads: warps 0-11 = three softmax groups (64-key sub-tiles round-robin), 12 Q/K producer,
+//                                   13 V producer, 14 S issuer (leader) + TMEM owner, 15 P.V issuer (leader);
+//                                   setmaxnreg gives the softmax warpgroups 152 registers and the last warpgroup 40
+//   TMEM (512 cols per CTA): O[256] | S[128] (one group) | 4 x P[32] (packed fp16, two groups in flight)
+//   smem per CTA: Q 32 KB | K ring 6 x 8 KB (32 of a sub-tile's 64 keys) | V^T ring 8 x 16 KB (128 of 256 dv rows x 64 keys)
 //   Work: units = (query-tile pair, Dv chunk of 256); a unit is T * ceil(HW / 128) groups of 128 keys; the (unit, group)
 //   sequence is cut into one contiguous range per cluster (stream-K, cost-aware bounds), <= 2 segments per cluster, each
 //   flushed as normalised fp16 rows + fp32 (m, l); combine3_kernel merges, gates and emits the per-frame attention mass.
 #include <cstdlib>
-#include <type_traits>
 
 #include "attn.cuh"
 #include "tcgen05.cuh"
@@ -41,28 +46,33 @@ constexpr int BNS = 64;        // keys per sub-tile (one softmax step, one P.V M
 constexpr int BNG = 128;       // keys per group (one S MMA group)
 constexpr int DK = 128;
 constexpr int DVC = 256;       // Dv columns per unit
-constexpr int KS = 3;          // K ring depth (groups)
+constexpr int KS = 6;          // K ring depth (sub-tiles)
 constexpr int VS = 8;          // V ring depth (sub-tiles)
-constexpr int kSoftmaxWarps = 8;
-constexpr int kWarpK = 8, kWarpV = 9, kWarpMmaS = 10, kWarpMmaPV = 11;
-constexpr int kThreads = 12 * 32;
+constexpr int kGroups = 3;                       // softmax groups of four warps (one per TMEM lane quadrant)
+constexpr int kSoftmaxWarps = 4 * kGroups;
+constexpr int kWarpK = 12, kWarpV = 13, kWarpMmaS = 14, kWarpMmaPV = 15;
+constexpr int kThreads = 16 * 32;
+// Register budget (64 K per SM): the kernel starts at 128 per thread (512 threads); the producer / issuer warpgroup drops
+// to kRegsIssue and the three softmax warpgroups grow to kRegsSoftmax (setmaxnreg): 3*128*152 + 128*56 = 65536.
+constexpr int kRegsSoftmax = 152, kRegsIssue = 56;
 
 constexpr int SMEM_Q = BM * DK * 2;              // 32 KB: [2 dk atoms][128 rows][128 B]
-constexpr int SMEM_K = (BNG / 2) * DK * 2;       // 16 KB: [2 dk atoms][64 keys][128 B]   (this CTA's half of the group)
+constexpr int SMEM_K = (BNS / 2) * DK * 2;       // 8 KB: [2 dk atoms][32 keys][128 B]    (this CTA's half of the sub-tile)
 constexpr int SMEM_V = (DVC / 2) * BNS * 2;      // 16 KB: [128 dv rows][64 keys]         (this CTA's half of the chunk)
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + SMEM_Q;
 constexpr int OFF_V = OFF_K + KS * SMEM_K;
 constexpr int OFF_MSH = OFF_V + VS * SMEM_V;              // float [128]        row-max hand-over
-constexpr int OFF_LX = OFF_MSH + BM * 4;                  // float [2][128][2]  (m, l) exchange at segment end
-constexpr int OFF_BAR = OFF_LX + 2 * BM * 2 * 4;
+constexpr int OFF_LX = OFF_MSH + BM * 4;                  // float [3][128][2]  (m, l) exchange at segment end
+constexpr int OFF_BAR = OFF_LX + kGroups * BM * 2 * 4;
 constexpr int SMEM_USED = OFF_BAR + 512;
 constexpr int SMEM_TOTAL = SMEM_USED + 1024;              // + alignment slack (the base is rounded up to 1024 B)
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_O = 0;
-constexpr int TMEM_S = 256;    // 2 slots x 128 fp32 score columns; sub-tile (slot, sub) at TMEM_S + slot*128 + sub*64
+constexpr int TMEM_S = 256;    // ONE 128-key score slot: sub-tile `sub` at TMEM_S + sub*64 (fp32)
+constexpr int TMEM_P = 384;    // 4 P buffers of 32 columns (packed fp16 pairs): (group & 1) * 2 + sub
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 15.0f;     // log2 units: P <= 2^15 (fp16 max 2^16) before a lazy rescale is forced
@@ -77,9 +87,8 @@ struct Tc3Params {
   const float* mseed;          // [HW] lower bound of the row maximum in log2 units (scale and bias applied) or null
   t16* part_o;                 // [nCTA][2][DVC/16][BM][16]  normalised partial O
   float* part_ml;              // [nCTA][2][BM][2]           (m in log2 units, l)
-  float* pieces;               // [nCTA][2][T][2][BM][2]     per-frame (m, l) of each softmax group (Dv chunk 0) or null
+  float* pieces;               // [nCTA][2][T][3][BM][2]     per-frame (m, l) of each softmax group (Dv chunk 0) or null
   int* rescales;               // debug counter (warp-level rescale events) or null
-  int exp_mode;                // exponentials per 4 that bypass MUFU through exp2_poly: 0, 1 or 2
 };
 
 // ---- cluster / pair primitives ----
@@ -111,20 +120,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, nullptr, 0); }
 __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, nullptr, 0); }
 
-// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5 -- below the fp16
-// rounding of P).  The MUFU unit evaluates 16 ex2 per cycle and SM; both softmax groups reach their exp phase at the
-// same time here (one 128-key score MMA feeds both), 16384 exponentials = 1024 MUFU cycles per group against 1580 cycles
-// of tensor work, and that phase sits on the S -> softmax -> P.V dependency chain of a score slot.
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;                         // 1.5 * 2^23: nearest integer lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);                   // [-0.5, 0.5]
-  float r = fmaf(f, 0.0551716648f, 0.2426111251f);
-  r = fmaf(r, f, 0.6932609677f);
-  r = fmaf(r, f, 0.9999280572f);
-  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
-}
-
+// Tried and dropped (profiles/r02_attn3_experiments.txt): a polynomial 2^x on the FMA pipe for a quarter / half of the
+// exponentials (slower: 76-78 vs 73.7 us -- the added issue slots and registers cost more than the MUFU cycles saved), and
+// ex2.approx.f16x2 (two exponentials per MUFU instruction on fp16-rounded exponents: 86 us and 1.6x the error).
 // TMA tile into THIS CTA's shared memory, transaction bytes counted on the LEADER CTA's barrier (peer bit cleared)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -221,12 +219,15 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* k_empty = k_full + KS;              // [KS] both
   uint64_t* v_full = k_empty + KS;              // [VS] leader
   uint64_t* v_empty = v_full + VS;              // [VS] both
-  uint64_t* s_full = v_empty + VS;              // [2]  both:   S(group) complete
-  uint64_t* p_full = s_full + 2;                // [4]  leader: P(sub-tile) stored by its softmax group in BOTH CTAs
-  uint64_t* sp_free = p_full + 4;               // [4]  both:   P.V(sub-tile) complete: score buffer (and all before) retired
+  // S(sub-tile j) complete, both CTAs: six barriers in rotation (j % 6).  A softmax group owns every third sub-tile, so
+  // all uses of one barrier belong to the same group and no waiter ever skips a phase.
+  uint64_t* s_full = v_empty + VS;              // [6]
+  uint64_t* s_free = s_full + 6;                // [2] leader: the owner (both CTAs) of score half-slot `sub` holds its scores
+  uint64_t* p_full = s_free + 2;                // [4]  leader: P(sub-tile) stored by its softmax group in BOTH CTAs
+  uint64_t* sp_free = p_full + 4;               // [4]  both:   P.V(sub-tile) complete: P buffer (and all before) retired
   uint64_t* o_drained = sp_free + 4;            // leader: both CTAs' segment epilogues have read O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_drained + 1);
-  static_assert((2 + 2 * KS + 2 * VS + 2 + 4 + 4 + 1) * 8 + 4 <= 512, "barrier area");
+  static_assert((2 + 2 * KS + 2 * VS + 8 + 4 + 4 + 1) * 8 + 4 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -269,9 +270,10 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_init(q_free, 1);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 2); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 2); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&s_free[i], 2 * 4);   // the four warps of the owning group, both CTAs
     for (int i = 0; i < 4; ++i) { mbar_init(&p_full[i], 8); mbar_init(&sp_free[i], 1); }
-    mbar_init(o_drained, 2 * kSoftmaxWarps);
+    mbar_init(o_drained, 2 * kSoftmaxWarps);           // every softmax warp of both CTAs
     mbar_fence_init();
   }
   if (warp == kWarpMmaS) tmem_alloc_pair(tmem_slot);
@@ -282,6 +284,8 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t tmem = *tmem_slot;
   pdl_prologue();   // barriers, TMEM and descriptors are set up; global memory is touched only from here on
 
+  if (warp >= kSoftmaxWarps) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
   if (warp == kWarpK) {
     // ================================ Q + K producer (both CTAs, own halves) ================================
     if (ntot > 0) {
@@ -302,18 +306,21 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           }
           __syncwarp();
         }
-        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++i) {
+        for (int g = seg[s].lo; g < seg[s].hi; ++g) {
           const int t = g / p.gpf, jg = g - t * p.gpf;
-          const int st = i % KS;
-          if (i >= KS) mbar_wait_b(&k_empty[st], ((i / KS) - 1) & 1);
-          if (elect_one()) {
-            const int key0 = p.slot[t] * p.HWp + jg * BNG + (int)rank * (BNG / 2);
-            unsigned char* sk = smem + OFF_K + st * SMEM_K;
-            tma_load_2d_pair(sk, &map_k, &k_full[st], 0, key0);
-            tma_load_2d_pair(sk + (BNG / 2) * 128, &map_k, &k_full[st], 64, key0);
-            if (leader) mbar_expect_tx(&k_full[st], 2 * SMEM_K); else mbar_arrive_leader(&k_full[st]);
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub, ++i) {
+            const int st = i % KS;
+            if (i >= KS) mbar_wait_b(&k_empty[st], ((i / KS) - 1) & 1);
+            if (elect_one()) {
+              const int key0 = p.slot[t] * p.HWp + jg * BNG + sub * BNS + (int)rank * (BNS / 2);
+              unsigned char* sk = smem + OFF_K + st * SMEM_K;
+              tma_load_2d_pair(sk, &map_k, &k_full[st], 0, key0);
+              tma_load_2d_pair(sk + (BNS / 2) * 128, &map_k, &k_full[st], 64, key0);
+              if (leader) mbar_expect_tx(&k_full[st], 2 * SMEM_K); else mbar_arrive_leader(&k_full[st]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -344,53 +351,56 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   } else if (warp == kWarpMmaS) {
     // ================================ S = Q.K^T issuer (leader only) ================================
     if (ntot > 0 && leader) {
-      constexpr uint32_t idesc_s = make_idesc(2 * BM, BNG);
+      constexpr uint32_t idesc_s = make_idesc(2 * BM, BNS);
       const uint32_t smem_base = smem_u32(smem);
-      for (int i = 0; i < ntot; ++i) {
-        const int st = i % KS, slot = i & 1;
+      // One 64-key score MMA group per sub-tile into half-slot (j & 1).  The two half-slots are recycled independently, each
+      // as soon as its single owner group has the scores in registers (a 128-key MMA into one slot had to wait for BOTH
+      // owners: 2180 cycles per key group, profiles/r02_attn3_trace_3groups_1slot.txt).
+      for (int i = 0; i < 2 * ntot; ++i) {
+        const int st = i % KS, sub = i & 1;
         if (i == 0) mbar_wait_cl(q_full, 0);
-        if (i == n0 && q_reload1) mbar_wait_cl(q_full, 1);
+        if (i == 2 * n0 && q_reload1) mbar_wait_cl(q_full, 1);
         mbar_wait_cl(&k_full[st], (i / KS) & 1);
-        TRACE3(2 * i, 10);
-        if (i >= 2) mbar_wait_b(&sp_free[slot * 2 + 1], ((i - 2) >> 1) & 1);      // P.V of group i-2 retired the slot
+        TRACE3(i, 10);
+        if (i >= 2) mbar_wait_cl(&s_free[sub], ((i >> 1) - 1) & 1);   // the scores of sub-tile i-2 are in registers
         fence_after();
-        TRACE3(2 * i, 2);
+        TRACE3(i, 2);
         if (elect_one()) {
           const uint64_t dq = make_desc_sw128(smem_base + OFF_Q);
           const uint64_t dk = make_desc_sw128(smem_base + OFF_K + st * SMEM_K);
-          const uint32_t d = tmem + TMEM_S + slot * BNG;
+          const uint32_t d = tmem + TMEM_S + sub * BNS;
 #pragma unroll
           for (int kk = 0; kk < DK / 16; ++kk) {
             // 32 B per k-step inside the 128 B swizzle atom; the second 64-wide dk atom starts one tile-half later
             const uint64_t oa = (uint64_t)(((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4);
-            const uint64_t ob = (uint64_t)(((kk >> 2) * ((BNG / 2) * 128) + (kk & 3) * 32) >> 4);
+            const uint64_t ob = (uint64_t)(((kk >> 2) * ((BNS / 2) * 128) + (kk & 3) * 32) >> 4);
             umma2_ss(d, dq + oa, dk + ob, idesc_s, kk > 0);
           }
           commit_pair(&k_empty[st]);
-          commit_pair(&s_full[slot]);
-          if (i == n0 - 1 && q_reload1) commit_pair(q_free);
+          commit_pair(&s_full[i % 6]);
+          if (i == 2 * n0 - 1 && q_reload1) commit_pair(q_free);
         }
         __syncwarp();
-        TRACE3(2 * i, 3);
+        TRACE3(i, 3);
       }
     }
-  } else if (warp == kWarpMmaPV) {
+  } else {
     // ================================ O += P.V issuer (leader only) ================================
     if (ntot > 0 && leader) {
       constexpr uint32_t idesc_o = make_idesc(2 * BM, DVC);
       const uint32_t smem_base = smem_u32(smem);
       for (int j = 0; j < 2 * ntot; ++j) {
         const int gi = j >> 1, b = (gi & 1) * 2 + (j & 1), sv = j % VS;
-        mbar_wait_cl(&p_full[b], (gi >> 1) & 1);
-        TRACE3(j, 0);
+        mbar_wait_cl(&v_full[sv], (j / VS) & 1);             // long since complete: its latency hides behind the P wait
+        TRACE3(j, 13);
         const bool first = (j == 0) || (j == 2 * n0);
         if (j == 2 * n0 && nseg > 1) mbar_wait_cl(o_drained, 0);
-        mbar_wait_cl(&v_full[sv], (j / VS) & 1);
+        mbar_wait_cl(&p_full[b], (gi >> 1) & 1);
         fence_after();
-        TRACE3(j, 13);
+        TRACE3(j, 0);
         if (elect_one()) {
           const uint64_t dv = make_desc_sw128(smem_base + OFF_V + sv * SMEM_V);
-          const uint32_t pa = tmem + TMEM_S + b * BNS;
+          const uint32_t pa = tmem + TMEM_P + b * 32;
 #pragma unroll
           for (int kk = 0; kk < BNS / 16; ++kk)
             umma2_ts(tmem + TMEM_O, pa + kk * 8, dv + (uint64_t)(kk * 2), idesc_o, (first && kk == 0) ? 0u : 1u);
@@ -401,16 +411,25 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         TRACE3(j, 1);
       }
     }
-  } else if (ntot > 0) {
-    // ================================ softmax + epilogue (warps 0-7, both CTAs) ================================
+  }
+  } else {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+  if (ntot > 0) {
+    // ================================ softmax + epilogue (warps 0-11, both CTAs) ================================
+    // Three softmax groups of four warps (one warp per TMEM lane quadrant) take the 64-key sub-tiles round-robin.  Two
+    // groups could not keep up with the tensor pipe: a sub-tile costs a softmax warp ~2300 cycles (MUFU: 64 ex2 per thread
+    // at 8 cycles per warp instruction, shared by the warps of an SM sub-core, plus ~1100 cycles of barrier / TMEM
+    // latencies) against 1580 cycles of tensor work per 128-key group (profiles/r02_attn3_trace_1slot.txt).
     const int quad = warp & 3, grp = warp >> 2;
     const int row = quad * 32 + lane;                       // tile row == TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    // named barriers: group 0 -> group 1 hand-over, group 1 -> group 0 hand-over, segment-end exchange
-    const int id_in = grp == 1 ? 1 + quad : 5 + quad;
-    const int id_out = grp == 0 ? 1 + quad : 5 + quad;
-    const int id_ex = 9 + quad;
-    int j = 0;                                              // sub-tile counter over both segments (grp == j & 1)
+    // named barriers: hand-over of the running maximum from group a to group (a+1)%3 on id 1 + a*4 + quad (64 threads),
+    // segment-end exchange on id 13 (all softmax warps)
+    const int id_in = 1 + ((grp + kGroups - 1) % kGroups) * 4 + quad;
+    const int id_out = 1 + grp * 4 + quad;
+    constexpr int id_ex = 13;
+    int j = 0;                                              // sub-tile counter over both segments
+    int own = grp;                                          // next sub-tile this group handles (j % 3 == grp)
 
     for (int s = 0; s < nseg; ++s) {
       const int unit = seg[s].unit;
@@ -421,154 +440,167 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // m_ref: the running maximum this group's l / l_piece are relative to
       float m_ref = -INFINITY, l_tot = 0.f, l_piece = 0.f, bias2 = 0.f;
       int cur_t = -1;
-      const int j_first = j;
+      const int j_first = j, j_last = j + 2 * (seg[s].hi - seg[s].lo) - 1;
       float* piece_base = (p.pieces && dvc == 0)
-                              ? p.pieces + (((long long)(cta * 2 + s) * p.T) * 2 + grp) * (BM * 2) + row * 2
+                              ? p.pieces + (((long long)(cta * 2 + s) * p.T) * kGroups + grp) * (BM * 2) + row * 2
                               : nullptr;
       auto flush_piece = [&](int t) {
         if (piece_base) {
-          float* d = piece_base + (long long)t * (2 * BM * 2);
+          float* d = piece_base + (long long)t * (kGroups * BM * 2);
           d[0] = m_ref;
           d[1] = l_piece;
         }
       };
-      for (int g = seg[s].lo; g < seg[s].hi; ++g) {
-        const int t = g / p.gpf, jg = g - t * p.gpf;
-        if (t != cur_t) {                                   // both groups walk every group's frame index
+      int t = seg[s].lo / p.gpf, jg = seg[s].lo - t * p.gpf;
+      for (int g = seg[s].lo; g < seg[s].hi; ++g, ++jg, j += 2) {
+        if (jg == p.gpf) { jg = 0; ++t; }
+        if (t != cur_t) {                                   // every group walks every key group's frame index
           if (cur_t >= 0) flush_piece(cur_t);
           cur_t = t;
           l_piece = 0.f;
           bias2 = (p.qbias && row_ok) ? p.qbias[(long long)qi * p.T + t] * LOG2E : 0.f;
         }
-        // this softmax group's sub-tile of the group: j = j_first + 2 * (g - lo) + grp
-        const int jj = j + grp;
-        const int gi = jj >> 1, b = (gi & 1) * 2 + grp;
-        const bool last_of_seg = (g + 1 == seg[s].hi) && grp == 1;
-        long long* const trace_s = quad == 0 ? trace : nullptr;
-#define TRACE3_S(k) do { if (trace_s && lane == 0 && jj < 256) trace_s[(long long)jj * 16 + (k)] = clock64(); } while (0)
-        TRACE3_S(4);
-        mbar_wait_b(&s_full[gi & 1], (gi >> 1) & 1);
-        fence_after();
-        TRACE3_S(5);
-        float sc[64];
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(lane_addr + TMEM_S + b * BNS, r0);
-          tmem_ld32_nowait(lane_addr + TMEM_S + b * BNS + 32, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) { sc[c] = __uint_as_float(r0[c]); sc[32 + c] = __uint_as_float(r1[c]); }
-        }
-        const int key0 = jg * BNG + grp * BNS;
-        if (key0 + BNS > p.HW) {                             // ragged / padding sub-tile at the end of the frame
-#pragma unroll
-          for (int c = 0; c < 64; ++c) sc[c] = (key0 + c < p.HW) ? sc[c] : -INFINITY;
-        }
-        // row maximum: balanced tree
-        float mx;
-        {
-          float a[16];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) a[c] = fmaxf(fmaxf(sc[c], sc[16 + c]), fmaxf(sc[32 + c], sc[48 + c]));
-#pragma unroll
-          for (int c = 0; c < 4; ++c) a[c] = fmaxf(fmaxf(a[c], a[4 + c]), fmaxf(a[8 + c], a[12 + c]));
-          mx = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
-        }
-        const float mt = fmaf(mx, p.scale_log2, bias2);      // scale > 0: max commutes with the affine map
-        TRACE3_S(6);
-        // ---- hand-over of the lazily updated row maximum from the other group's sub-tile jj-1 ----
-        float m_prev = seed;
-        if (jj > j_first) {
-          named_bar_sync(id_in, 64);
-          m_prev = m_sh[row];
-        }
-        const bool need = mt > m_prev + RESCALE_THRESHOLD;
-        float m_new = m_prev;
-        if (__any_sync(0xffffffffu, need)) {
-          if (jj > j_first) {
-            const int jp = jj - 1, gp = jp >> 1, bp = (gp & 1) * 2 + (jp & 1);
-            mbar_wait_b(&sp_free[bp], (gp >> 1) & 1);        // P.V(<= jj-1) retired
-            fence_after();
-            const float f = need ? exp2f(m_prev - mt) : 1.f;
 #pragma unroll 1
-            for (int c = 0; c < DVC; c += 32) {
-              float o[32];
-              tmem_ld32(lane_addr + TMEM_O + c, o);
-#pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] *= f;
-              tmem_st32(lane_addr + TMEM_O + c, o);
+        for (int sub = 0; sub < 2; ++sub) {
+          const int jj = j + sub;
+          if (jj != own) continue;
+          own += kGroups;
+          const int gi = jj >> 1, b = (gi & 1) * 2 + sub;
+          long long* const trace_s = quad == 0 ? trace : nullptr;
+#define TRACE3_S(k) do { if (trace_s && lane == 0 && jj < 256) trace_s[(long long)jj * 16 + (k)] = clock64(); } while (0)
+          TRACE3_S(4);
+          mbar_wait_b(&s_full[jj % 6], (jj / 6) & 1);
+          fence_after();
+          TRACE3_S(5);
+          float sc[64];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld32_nowait(lane_addr + TMEM_S + sub * BNS, r0);
+            tmem_ld32_nowait(lane_addr + TMEM_S + sub * BNS + 32, r1);
+            // P buffer b was last read by P.V of group gi-2 (long retired in the steady state): the wait's own latency
+            // overlaps the TMEM load
+            if (gi >= 2) {
+              mbar_wait_b(&sp_free[b], ((gi - 2) >> 1) & 1);
+              fence_after();
             }
-            fence_before();
-            if (p.rescales && lane == 0) atomicAdd(p.rescales, 1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { sc[c] = __uint_as_float(r0[c]); sc[32 + c] = __uint_as_float(r1[c]); }
           }
-          if (need) m_new = mt;
-        }
-        if (!last_of_seg) {
-          m_sh[row] = m_new;
-          named_bar_arrive(id_out, 64);
-        }
-        TRACE3_S(7);
-        if (m_new != m_ref) {                                // bring this group's sums to the current reference
-          const float f2 = exp2f(m_ref - m_new);
-          l_tot *= f2;
-          l_piece *= f2;
-          m_ref = m_new;
-        }
-        const float c0 = bias2 - m_new;
-        uint32_t pk[32];
-        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-        auto exp_phase = [&](auto mode) {
-          constexpr int kMode = decltype(mode)::value;
+          // the scores are in registers: hand the slot back to the S issuer (the next group's scores are computed while
+          // this one goes through max / exp / P store)
+          fence_before();
+          __syncwarp();
+          if (lane == 0) { if (leader) mbar_arrive(&s_free[sub]); else mbar_arrive_leader(&s_free[sub]); }
+          const int key0 = jg * BNG + sub * BNS;
+          if (key0 + BNS > p.HW) {                             // ragged / padding sub-tile at the end of the frame
+#pragma unroll
+            for (int c = 0; c < 64; ++c) sc[c] = (key0 + c < p.HW) ? sc[c] : -INFINITY;
+          }
+          // row maximum: balanced tree
+          float mx;
+          {
+            float a[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a[c] = fmaxf(fmaxf(sc[c], sc[16 + c]), fmaxf(sc[32 + c], sc[48 + c]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[c] = fmaxf(fmaxf(a[c], a[4 + c]), fmaxf(a[8 + c], a[12 + c]));
+            mx = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
+          }
+          const float mt = fmaf(mx, p.scale_log2, bias2);      // scale > 0: max commutes with the affine map
+          TRACE3_S(6);
+          // ---- hand-over of the lazily updated row maximum from the previous group's sub-tile jj-1 ----
+          float m_prev = seed;
+          if (jj > j_first) {
+            named_bar_sync(id_in, 64);
+            m_prev = m_sh[row];
+          }
+          const bool need = mt > m_prev + RESCALE_THRESHOLD;
+          float m_new = m_prev;
+          if (__any_sync(0xffffffffu, need)) {
+            if (jj > j_first) {
+              const int jp = jj - 1, gp = jp >> 1, bp = (gp & 1) * 2 + (jp & 1);
+              mbar_wait_b(&sp_free[bp], (gp >> 1) & 1);        // P.V(<= jj-1) retired
+              fence_after();
+              const float f = need ? exp2f(m_prev - mt) : 1.f;
+#pragma unroll 1
+              for (int c = 0; c < DVC; c += 32) {
+                float o[32];
+                tmem_ld32(lane_addr + TMEM_O + c, o);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[e] *= f;
+                tmem_st32(lane_addr + TMEM_O + c, o);
+              }
+              fence_before();
+              if (p.rescales && lane == 0) atomicAdd(p.rescales, 1);
+            }
+            if (need) m_new = mt;
+          }
+          if (jj < j_last) {
+            m_sh[row] = m_new;
+            named_bar_arrive(id_out, 64);
+          }
+          TRACE3_S(7);
+          if (m_new != m_ref) {                                // bring this group's sums to the current reference
+            const float f2 = exp2f(m_ref - m_new);
+            l_tot *= f2;
+            l_piece *= f2;
+            m_ref = m_new;
+          }
+          const float c0 = bias2 - m_new;
+          uint32_t pk[32];
+          float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll
           for (int c = 0; c < 64; c += 4) {
-            const float a0 = fmaf(sc[c], p.scale_log2, c0), a1 = fmaf(sc[c + 1], p.scale_log2, c0);
-            const float a2 = fmaf(sc[c + 2], p.scale_log2, c0), a3 = fmaf(sc[c + 3], p.scale_log2, c0);
-            const float e0 = exp2f(a0);
-            const float e1 = kMode >= 2 ? exp2_poly(a1) : exp2f(a1);
-            const float e2 = exp2f(a2);
-            const float e3 = kMode >= 1 ? exp2_poly(a3) : exp2f(a3);
+            const float e0 = exp2f(fmaf(sc[c], p.scale_log2, c0));
+            const float e1 = exp2f(fmaf(sc[c + 1], p.scale_log2, c0));
+            const float e2 = exp2f(fmaf(sc[c + 2], p.scale_log2, c0));
+            const float e3 = exp2f(fmaf(sc[c + 3], p.scale_log2, c0));
             ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
             pk[c >> 1] = pack2_fast(e0, e1);
             pk[(c >> 1) + 1] = pack2_fast(e2, e3);
           }
-        };
-        if (p.exp_mode == 0) exp_phase(std::integral_constant<int, 0>{});
-        else if (p.exp_mode == 1) exp_phase(std::integral_constant<int, 1>{});
-        else exp_phase(std::integral_constant<int, 2>{});
-        const float lsum = (ls0 + ls1) + (ls2 + ls3);
-        l_tot += lsum;
-        l_piece += lsum;
-        TRACE3_S(8);
-        // P over the first 32 columns of its own score buffer: this thread's row was fully read above
-        tmem_st32u(lane_addr + TMEM_S + b * BNS, pk);
-        fence_before();
-        __syncwarp();
-        if (lane == 0) { if (leader) mbar_arrive(&p_full[b]); else mbar_arrive_leader(&p_full[b]); }
-        TRACE3_S(9);
-        j += 2;
+          const float lsum = (ls0 + ls1) + (ls2 + ls3);
+          l_tot += lsum;
+          l_piece += lsum;
+          TRACE3_S(8);
+          tmem_st32u(lane_addr + TMEM_P + b * 32, pk);
+          fence_before();
+          __syncwarp();
+          if (lane == 0) { if (leader) mbar_arrive(&p_full[b]); else mbar_arrive_leader(&p_full[b]); }
+          TRACE3_S(9);
+          if (trace && quad > 0 && lane == 0 && jj < 256) trace[(long long)jj * 16 + (quad == 1 ? 11 : quad == 2 ? 12 : 14)] = clock64();
+        }
       }
       flush_piece(cur_t);
 
       // ---- segment epilogue: normalised fp16 partial O + (m, l) ----
       lx[(grp * BM + row) * 2 + 0] = m_ref;
       lx[(grp * BM + row) * 2 + 1] = l_tot;
-      named_bar_sync(id_ex, 64);
-      const float m_o = lx[((grp ^ 1) * BM + row) * 2 + 0], l_o = lx[((grp ^ 1) * BM + row) * 2 + 1];
-      const float M = fmaxf(m_ref, m_o);                    // == the maximum O is relative to (m is monotone)
-      const float l_row = l_tot * exp2f(m_ref - M) + l_o * exp2f(m_o - M);
+      named_bar_sync(id_ex, kSoftmaxWarps * 32);
+      float M = -INFINITY;                                  // == the maximum O is relative to (m is monotone)
+#pragma unroll
+      for (int a = 0; a < kGroups; ++a) M = fmaxf(M, lx[(a * BM + row) * 2]);
+      float l_row = 0.f;
+#pragma unroll
+      for (int a = 0; a < kGroups; ++a) {
+        const float la = lx[(a * BM + row) * 2 + 1];
+        if (la > 0.f) l_row += la * exp2f(lx[(a * BM + row) * 2] - M);
+      }
       const float inv = l_row > 0.f ? 1.f / l_row : 0.f;    // a seed far above this segment's scores can leave l = 0
       {
-        const int last = j - 1, gl = last >> 1, bl = (gl & 1) * 2 + 1;
+        const int gl = j_last >> 1, bl = (gl & 1) * 2 + 1;
         mbar_wait_b(&sp_free[bl], (gl >> 1) & 1);
         fence_after();
       }
       // part_o: [slot][16-column group][row][16] -- the 32 rows of a warp are contiguous per group, so every store
-      // instruction covers whole lines
-      t16* po = p.part_o + (((long long)(cta * 2 + s) * (DVC / 16) + grp * (DVC / 32)) * BM + row) * 16;
+      // instruction covers whole lines.  32-column chunks 0-2 / 3-5 / 6-7 go to softmax groups 0 / 1 / 2.
+      t16* po = p.part_o + (((long long)(cta * 2 + s) * (DVC / 16)) * BM + row) * 16;
+      const int c_lo = grp * 96, c_hi = grp == 2 ? DVC : c_lo + 96;
 #pragma unroll 1
-      for (int c = 0; c < DVC / 2; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         float o[32];
-        tmem_ld32(lane_addr + TMEM_O + grp * (DVC / 2) + c, o);
+        tmem_ld32(lane_addr + TMEM_O + c, o);
         if (row_ok) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
@@ -589,7 +621,10 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       fence_before();
       __syncwarp();
       if (lane == 0 && s + 1 < nseg) mbar_arrive_leader(o_drained);
+      // the exchange area is reused by the next segment: every group must have read it before anyone writes again
+      if (s + 1 < nseg) named_bar_sync(id_ex, kSoftmaxWarps * 32);
     }
+  }
   }
   fence_before();
   __syncthreads();
@@ -709,10 +744,11 @@ __global__ void __launch_bounds__(256) combine3_kernel(const Tc3Params p, const 
     float a = 0.f;
     for (int e = 0; e < s_n[rr][0]; ++e) {
       if (s_alo[rr][e] < f_hi && f_lo < s_ahi[rr][e]) {
-        const float* pc = p.pieces + ((((long long)s_slot[rr][0][e] * p.T + t) * 2) * BM + r) * 2;
+        const float* pc = p.pieces + ((((long long)s_slot[rr][0][e] * p.T + t) * kGroups) * BM + r) * 2;
         // a piece whose sum is zero may carry m = -inf (no sub-tile of that frame seen by the group): skip it
-        if (pc[1] > 0.f) a += exp2f(pc[0] - M) * pc[1];
-        if (pc[BM * 2 + 1] > 0.f) a += exp2f(pc[BM * 2] - M) * pc[BM * 2 + 1];
+#pragma unroll
+        for (int gq = 0; gq < kGroups; ++gq)
+          if (pc[gq * BM * 2 + 1] > 0.f) a += exp2f(pc[gq * BM * 2] - M) * pc[gq * BM * 2 + 1];
       }
     }
     mass[(long long)i * p.T + t] = a * invL;
@@ -834,7 +870,7 @@ size_t part_bytes3(int nCL, int T, size_t* off_ml, size_t* off_pieces, size_t* o
   o += nCTA * 2 * BM * 2 * sizeof(float);
   o = (o + 255) & ~size_t(255);
   *off_pieces = o;
-  o += nCTA * 2 * T * 2 * BM * 2 * sizeof(float);
+  o += nCTA * 2 * T * kGroups * BM * 2 * sizeof(float);
   o = (o + 255) & ~size_t(255);
   *off_seed = o;
   o += (size_t)HW * sizeof(float);
@@ -913,11 +949,6 @@ int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   float* mseed = reinterpret_cast<float*>(ws + off_seed);
   p.mseed = a.seed_h > 0 ? mseed : nullptr;
   p.rescales = g3_rescales;
-  {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("RMEM_ATTN_EXP"); mode = e ? atoi(e) : 0; if (mode < 0 || mode > 2) mode = 0; }
-    p.exp_mode = mode;
-  }
 
   RMEM_REQUIRE((reinterpret_cast<uintptr_t>(a.qt) & 15) == 0, "long_attn_tc3: q alignment");
   const CUtensorMap *mq, *mk, *mv;
@@ -930,7 +961,7 @@ int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   {
     uint64_t dims[2] = {(uint64_t)DK, (uint64_t)a.nslots * a.HWp};
     uint64_t str[1] = {(uint64_t)DK * 2};
-    uint32_t box[2] = {64, (uint32_t)(BNG / 2)};
+    uint32_t box[2] = {64, (uint32_t)(BNS / 2)};
     RMEM_TRY(tma_encode_cached(&mk, a.kbank, 2, dims, str, box, nullptr));
   }
   {

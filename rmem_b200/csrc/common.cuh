@@ -1,6 +1,8 @@
 // Shared device/host helpers for the rmem_b200 kernels (sm_100a only).
 #pragma once
 #include <cstdlib>
+#include <exception>
+#include <new>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -61,6 +63,24 @@ long long& launch_counter();
       return RMEM_ERR_ARG;             \
     }                                  \
   } while (0)
+
+// Every multi-line entry point is wrapped: no C++ exception (std::bad_alloc from the host-side containers, ...) may cross
+// the extern "C" boundary; it becomes a status code + message like every other failure.
+#define RMEM_API_BEGIN try {
+#define RMEM_API_END                                                              \
+  }                                                                               \
+  catch (const std::bad_alloc&) {                                                 \
+    rmem::set_error("out of host memory");                                        \
+    return RMEM_ERR_STATE;                                                        \
+  }                                                                               \
+  catch (const std::exception& ex) {                                              \
+    rmem::set_error("unexpected C++ exception: %s", ex.what());                   \
+    return RMEM_ERR_STATE;                                                        \
+  }                                                                               \
+  catch (...) {                                                                   \
+    rmem::set_error("unexpected C++ exception");                                  \
+    return RMEM_ERR_STATE;                                                        \
+  }
 
 #define RMEM_TRY(expr)          \
   do {                          \

@@ -14,6 +14,7 @@
 // instead of a re-materialised K bank, the encoder runs once per frame for all object groups, and the
 // only host<->device sync is the T-float relevance read-back on frames that append to the bank.
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 #include <cmath>
@@ -151,6 +152,7 @@ struct rmem_engine {
   bool pending[2] = {false, false};        // features of pf_img[sl] are (being) produced on enc_stream, not consumed yet
   const float* pf_img[2] = {nullptr, nullptr};
   long long pf_seq[2] = {0, 0}, pf_counter = 0;
+  int pf_age[2] = {0, 0};                  // features() calls since the prefetch was issued (a live entry is consumed at <= 1)
   int last_enc_slot = -1;                  // last slot encoded on enc_stream (its event orders the encoder temporaries)
   void use_slot(int sl) { fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl]; }
   int init_streams() {
@@ -424,6 +426,14 @@ struct rmem_engine {
 
   // Features of `img`: taken from a prefetch when one is outstanding for exactly this pointer, else encoded inline.
   int features(const float* img, cudaStream_t s) {
+    // A prefetched frame is consumed by the very next propagate, or by the one after it when the prefetch was issued
+    // before the current frame's propagate (bench / evaluator order).  Anything older was never consumed (skipped frame,
+    // exception in the caller): drop it, so that a later tensor the allocator places at the same address cannot pick up
+    // stale features.
+    for (int sl = 0; sl < 2; ++sl)
+      if (pending[sl] && pf_age[sl] >= 2) pending[sl] = false;
+    for (int sl = 0; sl < 2; ++sl)
+      if (pending[sl]) ++pf_age[sl];
     for (int sl = 0; sl < 2; ++sl)
       if (pending[sl] && pf_img[sl] == img) {
         RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_done[sl], 0));
@@ -997,6 +1007,7 @@ int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former,
 extern "C" {
 
 int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(cfg && bytes, "null argument");
   RMEM_REQUIRE(cfg->model == 0 || cfg->model == 1, "model %d: 0 = r50_deaotl, 1 = r50_aotl", cfg->model);
   RMEM_REQUIRE(cfg->attn_impl == RMEM_ATTN_DENSE || cfg->attn_impl == RMEM_ATTN_TC2 || cfg->attn_impl == RMEM_ATTN_TC3,
@@ -1015,23 +1026,25 @@ int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
   tmp.layout(a);
   *bytes = a.off + 256;
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_create(const rmem_engine_config* cfg, const void* weight_blob, const rmem_weight_entry* entries,
                        int n_entries, void* arena, size_t arena_bytes, rmem_engine** out) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(cfg && weight_blob && entries && arena && out, "null argument");
   size_t need = 0;
   RMEM_TRY(rmem_engine_arena_bytes(cfg, &need));
   RMEM_REQUIRE((reinterpret_cast<uintptr_t>(arena) & 255) == 0, "arena must be 256-byte aligned");
   RMEM_REQUIRE((reinterpret_cast<uintptr_t>(weight_blob) & 255) == 0, "weight blob must be 256-byte aligned");
-  rmem_engine* e = new rmem_engine();
+  std::unique_ptr<rmem_engine> holder(new rmem_engine());   // freed on every early return / exception below
+  rmem_engine* e = holder.get();
   e->cfg = *cfg;
   e->g = make_geo(cfg->H, cfg->W);
   e->nslots = cfg->former_mem_len + cfg->latter_mem_len + 1;
   for (int i = 0; i < n_entries; ++i) {
     if ((entries[i].offset & 15) != 0) {
       set_error("weight '%s' is not 16-byte aligned in the blob", entries[i].name);
-      delete e;
       return RMEM_ERR_WEIGHT;
     }
     e->weights[entries[i].name] = {reinterpret_cast<const char*>(weight_blob) + entries[i].offset, entries[i].nbytes};
@@ -1040,24 +1053,25 @@ int rmem_engine_create(const rmem_engine_config* cfg, const void* weight_blob, c
   a.base = reinterpret_cast<char*>(arena);
   a.cap = arena_bytes;
   int rc = e->layout(a);
-  if (rc) { delete e; return rc; }
+  if (rc) return rc;
   e->arena_base = a.base;
   // one-time clear (create is off the hot path): pad rows/columns of K / value-major buffers must be finite
   if (cudaMemset(arena, 0, a.off) != cudaSuccess) {
     set_error("arena clear failed: %s", cudaGetErrorString(cudaGetLastError()));
-    delete e;
     return RMEM_ERR_CUDA;
   }
   rc = e->init_streams();
-  if (rc) { delete e; return rc; }
+  if (rc) return rc;
   e->launches0 = launch_counter();
-  *out = e;
+  *out = holder.release();
   return RMEM_OK;
+  RMEM_API_END
 }
 
 void rmem_engine_destroy(rmem_engine* e) { delete e; }
 
 int rmem_engine_restart(rmem_engine* e) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e, "null engine");
   e->n_groups = 0;
   e->pending[0] = e->pending[1] = false;
@@ -1067,16 +1081,20 @@ int rmem_engine_restart(rmem_engine* e) {
     gr.last_rel.clear(); gr.last_drop = -1;
   }
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_set_gap(rmem_engine* e, int gap) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && gap >= 1, "bad gap");
   e->cfg.long_term_mem_gap = gap;
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void* label, int label_is_f32,
                                     int n_objects, int frame_step, void* stream) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && img && label, "null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int n = (n_objects + kMaxObj - 1) / kMaxObj;
@@ -1084,7 +1102,6 @@ int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void
   RMEM_REQUIRE(n <= e->cfg.max_engines, "%d objects need %d object groups, engine built for %d", n_objects, n,
                e->cfg.max_engines);
   if (n > e->n_groups) e->n_groups = n;
-  if (frame_step < 0) frame_step = 0;
   // zero the bank/state region once per clip (pad columns of the value-major bank must stay finite)
   RMEM_CUDA_CHECK(cudaMemsetAsync(e->arena_base + e->state_begin, 0, e->state_bytes, s));
   RMEM_TRY(e->features(img, s));
@@ -1097,15 +1114,17 @@ int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void
     gr.ema.clear(); gr.times.clear();
     RMEM_TRY(e->frame_forward(gr, /*ref_mode=*/true, s));
     gr.parity ^= 1;                      // this frame becomes the short-term memory
-    gr.last_mem_step = frame_step;
+    gr.last_mem_step = frame_step < 0 ? gr.frame_step : frame_step;   // aot_engine.py:254-255: -1 = the engine's own step
     gr.long_idx.push_back(gr.frame_step);
     gr.has_ref = true;
   }
   return e->release_features(s);
+  RMEM_API_END
 }
 
 int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, float* out_logits, uint8_t* out_label,
                           void* stream) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && img, "null argument");
   RMEM_REQUIRE(e->n_groups >= 1 && e->groups[0].has_ref, "propagate before add_reference_frame");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1122,6 +1141,7 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
   e->mark("mask_head", s);
   e->flush_marks(s);
   return e->release_features(s);            // the feature set of this frame may be overwritten from here on
+  RMEM_API_END
 }
 
 // Encode the NEXT frame on the engine's side stream while the current frame is still being propagated (the encoder has
@@ -1129,6 +1149,7 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
 // and stay untouched until the rmem_engine_propagate call that consumes it has been issued; that call must pass the
 // same pointer (anything else falls back to the inline encoder).  Results are bit-identical to the unprefetched path.
 int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && img, "null argument");
   if (e->timing) return RMEM_OK;            // stage timing serialises the frame; keep it on one stream
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1151,11 +1172,14 @@ int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream) {
   e->pending[sl] = true;
   e->pf_img[sl] = img;
   e->pf_seq[sl] = ++e->pf_counter;
+  e->pf_age[sl] = 0;
   e->last_enc_slot = sl;
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f32, void* stream) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && label, "null argument");
   RMEM_REQUIRE(e->n_groups >= 1 && e->groups[0].has_ref, "update_memory before add_reference_frame");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1207,45 +1231,81 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
   e->mark("upd.refresh+bank", s);
   e->flush_marks(s);
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_num_groups(const rmem_engine* e) { return e ? e->n_groups : 0; }
 
 int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx, int* n) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && idx && n && group >= 0 && group < e->n_groups, "bad argument");
   const Group& gr = e->groups[group];
-  *n = (int)gr.long_idx.size();
-  for (int i = 0; i < *n && i < kMaxBankFrames + 1; ++i) idx[i] = gr.long_idx[i];
+  // A mid-clip add_reference_frame re-initialises the bank but (like aot_engine.py:321-323) keeps appending to this list,
+  // so it can outgrow the bank; the caller's buffer holds kMaxBankFrames + 1 entries: report the NEWEST ones.
+  const int total = (int)gr.long_idx.size();
+  const int cnt = total < kMaxBankFrames + 1 ? total : kMaxBankFrames + 1;
+  for (int i = 0; i < cnt; ++i) idx[i] = gr.long_idx[total - cnt + i];
+  *n = cnt;
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_pred_logits(const rmem_engine* e, int group, const float** logits4, int* h4, int* w4) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && logits4 && group >= 0 && group < e->n_groups, "bad argument");
   *logits4 = e->groups[group].logits4;
   if (h4) *h4 = e->g.H4;
   if (w4) *w4 = e->g.W4;
   return RMEM_OK;
+  RMEM_API_END
+}
+
+int rmem_engine_layer_memory(const rmem_engine* e, int group, int layer, const void** kbank, const void** vtbank,
+                             const void** q_last, const void** vid_last, int* nslots, int* HWp, int* T, int* slots) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(e && group >= 0 && group < e->n_groups && layer >= 0 && layer < kLayers, "bad argument");
+  RMEM_REQUIRE(e->cfg.model == 0, "layer memories are exposed for the DeAOT model only");
+  const Group& gr = e->groups[group];
+  const LayerState& L = gr.L[layer];
+  // update_memory flipped the parity: the last propagated frame's K / V||ID_V are the "previous frame" buffers now
+  const int last = gr.parity ^ 1;
+  if (kbank) *kbank = L.kbank;
+  if (vtbank) *vtbank = L.vtbank;
+  if (q_last) *q_last = L.kc[last];
+  if (vid_last) *vid_last = L.vid[last];
+  if (nslots) *nslots = e->nslots;
+  if (HWp) *HWp = e->g.HWp;
+  if (T) *T = (int)gr.slots.size();
+  if (slots)
+    for (size_t t = 0; t < gr.slots.size() && t < (size_t)kMaxBankFrames; ++t) slots[t] = gr.slots[t];
+  return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel, int* n, int* drop) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && rel && n && drop && group >= 0 && group < e->n_groups, "bad argument");
   const Group& gr = e->groups[group];
   *n = (int)gr.last_rel.size();
   for (int i = 0; i < *n; ++i) rel[i] = gr.last_rel[i];
   *drop = gr.last_drop;
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_set_timing(rmem_engine* e, int on) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e, "null engine");
   e->timing = on != 0;
   e->stage_ms.clear();
   e->marks.clear();
   e->ev_used = 0;
   return RMEM_OK;
+  RMEM_API_END
 }
 
 int rmem_engine_get_timing(rmem_engine* e, char* buf, size_t cap) {
+  RMEM_API_BEGIN
   RMEM_REQUIRE(e && buf && cap > 0, "bad argument");
   std::string out;
   for (auto& kv : e->stage_ms) {
@@ -1255,6 +1315,7 @@ int rmem_engine_get_timing(rmem_engine* e, char* buf, size_t cap) {
   }
   snprintf(buf, cap, "%s", out.c_str());
   return RMEM_OK;
+  RMEM_API_END
 }
 
 long long rmem_engine_launch_count(const rmem_engine* e) { return e ? launch_counter() - e->launches0 : 0; }

@@ -43,14 +43,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase flips (or ~kWaitHintNs pass) instead of
+// returning at once.  A warp that polls without the hint keeps taking issue slots from the other warps of its SM
+// sub-core: the MMA-issuer warps of the pair attention kernel slowed the softmax warps next to them by ~1500 cycles per
+// sub-tile (profiles/r02_attn3_trace_spin.txt).
+constexpr uint32_t kWaitHintNs = 100000;     // 0.1 ms per try
+constexpr uint32_t kWaitMaxTries = 20000;    // ~2 s before the watchdog traps
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
       : "memory");
   return ok != 0;
 }
@@ -58,7 +64,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > kWaitMaxTries) {
       if (err) atomicExch(err, code);
       __trap();
     }

@@ -102,6 +102,28 @@ class _SubEngineView:
         off = p.value - self._o._arena.data_ptr()
         return self._o._arena[off:off + 4 * n].view(torch.float32).view(1, 11, h4.value, w4.value).clone()
 
+    def layer_memory(self, layer: int) -> dict:
+        """Views (no copies) of one GPM layer's memories after update_memory: the restricted long-term bank in the
+        engine's layout (kbank [nslots,HWp,128], vtbank [1024,nslots*HWp]), the logical->physical slot list, and the
+        short-term memory (last frame's K = Q [HW,128], V||ID_V [HW,1024])."""
+        lib = _capi.load()
+        kb, vb, ql, vl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ns, hwp, T = C.c_int(), C.c_int(), C.c_int()
+        slots = (C.c_int * _capi.MAX_BANK_FRAMES)()
+        _capi.check(lib.rmem_engine_layer_memory(self._o._h, self._i, int(layer), C.byref(kb), C.byref(vb), C.byref(ql),
+                                                 C.byref(vl), C.byref(ns), C.byref(hwp), C.byref(T), slots))
+        arena, base = self._o._arena, self._o._arena.data_ptr()
+        HW = self._o.enc_hw
+        op = _capi.op_dtype()
+
+        def view(p, n, shape):
+            off = p.value - base
+            return arena[off:off + 2 * n].view(op).view(*shape)
+        return dict(kbank=view(kb, ns.value * hwp.value * 128, (ns.value, hwp.value, 128)),
+                    vtbank=view(vb, 1024 * ns.value * hwp.value, (1024, ns.value * hwp.value)),
+                    q_last=view(ql, HW * 128, (HW, 128)), vid_last=view(vl, HW * 1024, (HW, 1024)),
+                    slots=[slots[i] for i in range(T.value)], nslots=ns.value, HWp=hwp.value)
+
     @property
     def last_evict(self) -> Tuple[List[float], int]:
         lib = _capi.load()

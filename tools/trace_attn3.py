@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 _capi.check(lib.rmem_debug_attn_trace(C.c_void_p(0)))
 t = tr.cpu().view(ROWS, 16)
 names = ["pfull_seen", "pv_issued", "s_waits_done", "s_issued", "sm_start", "sfull_seen", "max_done", "handoff_done",
-         "exp_done", "p_arrived", "s_kfull_seen", "-", "-", "vfull_seen"]
+         "exp_done", "p_arrived", "s_kfull_seen", "p_arr_q1", "p_arr_q2", "vfull_seen", "p_arr_q3"]
 for rank in range(2):
     tt = t[rank * 256:(rank + 1) * 256]
     if int(tt.max()) == 0:
@@ -34,7 +34,7 @@ for rank in range(2):
     for j in range(96):
         if int(tt[j].max()) == 0:
             break
-        print(f"{j:4d} " + " ".join((str(int(x) - t0) if int(x) > 0 else "-").rjust(12) for x in tt[j, :14]))
+        print(f"{j:4d} " + " ".join((str(int(x) - t0) if int(x) > 0 else "-").rjust(12) for x in tt[j, :15]))
 ct = t[600:748]
 g0 = int(ct[:, 0][ct[:, 0] > 0].min())
 rows = [(c, int(ct[c, 0]) - g0, int(ct[c, 1]) - g0, int(ct[c, 2]), int(ct[c, 3]), int(ct[c, 4]), int(ct[c, 6] - ct[c, 5]))
