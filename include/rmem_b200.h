@@ -128,15 +128,24 @@ int rmem_upsample_bilinear_fwd(const void* x, void* y, int hin, int win, int hou
 int rmem_transpose_fwd(const void* x, long long ldx, void* y, long long ldy, int P, int C, void* stream);
 int rmem_maxpool3x3s2_fwd(const void* x, void* y, int Hin, int Win, int C, int Hout, int Wout, void* stream);
 int rmem_pack_image_fwd(const float* img_nchw, void* out_nhwc8, int H, int W, void* stream);
+/* Same into the zero-padded layout [H+6][W+8][8] (pixel (y,x) at (y+3, x+3)) that the stem convolution reads
+ * (rmem_gemm_desc.conv = 2: conv1 7x7 stride 2 pad 3 of networks/encoders/resnet.py:178-181 as a tcgen05 GEMM with one
+ * k-block per window row; B = [Cout][7][8 pixels][8 channels], zero weights for the 8th pixel).  Writes the interior
+ * only: the caller zeroes the buffer once. */
+int rmem_pack_image_padded_fwd(const float* img_nchw, void* out, int H, int W, void* stream);
 
 /* ID bank: one_hot_mask (utils/image.py:69-74) + assign_identity (networks/engines/aot_engine.py:208-232) +
  * patch_wise_id_bank Conv2d(12->256,k17,s16,p8) (networks/models/aot.py:63-74,111-114) + id_norm
  * (networks/models/deaot.py:65-69), as a gather-sum indexed by the uint8 label. */
 /* prefix (nullable): fp32 [12][18][18][C] inclusive 2-D prefix sums of the weight over (ky, kx) per class; a patch whose
- * in-bounds pixels share one class then costs four reads instead of up to 289 weight rows. */
+ * in-bounds pixels share one class then costs four reads instead of up to 289 weight rows, a patch with few pixels off
+ * its dominant class the rectangle plus two reads per such pixel.  prefix_rows (nullable, needs prefix): fp32
+ * [17][12][18][C] 1-D prefix sums over kx per (ky, class): every run of equal labels in a patch row costs two reads.
+ * The kernel picks the cheapest decomposition per patch; all of them compute the same sum (fp32 order differs). */
 int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed /* [289,12,C] */,
-                    const float* prefix, const float* bias, const float* ln_gamma, const float* ln_beta, void* out_t16,
-                    long long ldo, float* out_f32, int h, int w, int C, void* stream);
+                    const float* prefix, const float* prefix_rows, const float* bias, const float* ln_gamma,
+                    const float* ln_beta, void* out_t16, long long ldo, float* out_f32, int h, int w, int C,
+                    void* stream);
 
 /* Mask-ID assignment: bilinear(align_corners=True) upsample of the 1/4-res logits (aot_engine.py:457-463),
  * soft_logit_aggregation over k object groups (aot_engine.py:650-673), softmax -> argmax

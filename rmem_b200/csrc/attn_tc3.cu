@@ -757,34 +757,49 @@ __global__ void __launch_bounds__(256) combine3_kernel(const Tc3Params p, const 
 
 // Seed of the running row maximum: the best score of query i against the keys at its own position and the 8 neighbours
 // in every bank frame (T x 9 dot products of 128) -- a LOWER bound of the true maximum that is close to it whenever the
-// match is local or the score distribution is broad.  One warp per query; lane l holds dk channels 4l..4l+3.
+// match is local or the score distribution is broad.  One warp per query; eight lanes share a key (16 channels = two
+// 16-byte loads each, 3 shuffles to reduce), so a warp scores four keys per step.
 __global__ void __launch_bounds__(256) attn_seed_kernel(const t16* __restrict__ qt, const float* __restrict__ qbias,
                                                         const t16* __restrict__ kbank, Tc3Params p, int h, int w,
                                                         float* __restrict__ mseed) {
   pdl_prologue();
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= p.HW) return;
-  const uint2 qu = *reinterpret_cast<const uint2*>(qt + (long long)i * DK + lane * 4);
-  const float2 q0 = unpack2(qu.x), q1 = unpack2(qu.y);
+  const int sub = lane >> 3, part = lane & 7;            // key within the step, 16-channel block
+  float q[16];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qt + (long long)i * DK + part * 16);
+    const uint4 a = qp[0], b = qp[1];
+    const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const float2 f = unpack2(u[c]); q[2 * c] = f.x; q[2 * c + 1] = f.y; }
+  }
   const int y = i / w, x = i - y * w;
   float best = -INFINITY;
-  for (int t = 0; t < p.T; ++t) {
-    const t16* kb = kbank + (long long)p.slot[t] * p.HWp * DK;
-    const float b2 = qbias ? qbias[(long long)i * p.T + t] * LOG2E : 0.f;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= h) continue;
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= w) continue;
-        const uint2 ku = *reinterpret_cast<const uint2*>(kb + (long long)(yy * w + xx) * DK + lane * 4);
-        const float2 k0 = unpack2(ku.x), k1 = unpack2(ku.y);
-        float s = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
-        s = warp_sum(s);
-        best = fmaxf(best, fmaf(s, p.scale_log2, b2));
-      }
+  const int n = p.T * 9;
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const int k = k0 + sub;
+    const int t = k / 9, nb = k - t * 9;
+    const int yy = y + nb / 3 - 1, xx = x + nb % 3 - 1;
+    const bool ok = k < n && yy >= 0 && yy < h && xx >= 0 && xx < w;
+    float s = 0.f;
+    if (ok) {
+      const uint4* kp = reinterpret_cast<const uint4*>(kbank + ((long long)p.slot[t] * p.HWp + yy * w + xx) * DK + part * 16);
+      const uint4 a = kp[0], b = kp[1];
+      const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { const float2 f = unpack2(u[c]); s = fmaf(q[2 * c], f.x, s); s = fmaf(q[2 * c + 1], f.y, s); }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok) {
+      const float b2 = qbias ? qbias[(long long)i * p.T + t] * LOG2E : 0.f;
+      best = fmaxf(best, fmaf(s, p.scale_log2, b2));
     }
   }
+  best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 8));
+  best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
   if (lane == 0) mseed[i] = best;
 }
 

@@ -228,13 +228,18 @@ int rmem_pack_image_fwd(const float* img, void* out, int H, int W, void* stream)
   RMEM_API_END
 }
 
+int rmem_pack_image_padded_fwd(const float* img, void* out, int H, int W, void* stream) {
+  return pack_image_padded(img, (t16*)out, H, W, STREAM(stream));
+}
+
 int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* prefix,
+                    const float* prefix_rows,
                     const float* bias, const float* ln_gamma, const float* ln_beta, void* out_t16, long long ldo,
                     float* out_f32, int h, int w, int C, void* stream) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(label && w_packed && bias && (out_t16 || out_f32), "null argument");
   return idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_gamma, ln_beta, (t16*)out_t16, ldo, out_f32, h, w,
-                      C, STREAM(stream), prefix);
+                      C, STREAM(stream), prefix, prefix_rows);
   RMEM_API_END
 }
 

@@ -258,7 +258,7 @@ struct rmem_engine {
 
   int layout(Arena& a) {
     const Geo& G = g;
-    img8 = a.take<t16>((size_t)G.H * G.W * 8);
+    img8 = a.take<t16>((size_t)(G.H + 6) * (G.W + 8) * 8);   // zero-padded stem input (zeroed once at create)
     c1 = a.take<t16>((size_t)G.P1 * 64);
     x0 = a.take<t16>((size_t)G.P4 * 256);
     x1 = a.take<t16>((size_t)G.P4 * 256);
@@ -462,8 +462,21 @@ struct rmem_engine {
   int encode_into(const float* img, cudaStream_t s, int sl) {
     const Geo& G = g;
     mark("begin", s);
-    RMEM_TRY(pack_image(img, img8, G.H, G.W, s));
-    RMEM_TRY(conv(img8, G.H, G.W, 8, "enc.conv1", 64, 7, 2, 3, ACT_RELU, nullptr, c1, s));
+    RMEM_TRY(pack_image_padded(img, img8, G.H, G.W, s));
+    {
+      // conv1 (7x7, stride 2, pad 3; resnet.py:178-181) on the tcgen05 kernel: one k-block per window row (gemm.cuh conv = 2)
+      int rc = RMEM_OK;
+      const t16* w = Wt<t16>("enc.conv1.w", (size_t)64 * 7 * 8 * 8, &rc);
+      const float* b = Wt<float>("enc.conv1.b", 64, &rc);
+      if (rc) return rc;
+      GemmParams p;
+      p.A = img8; p.B = w; p.ldb = 7 * 64;
+      p.M = G.P1; p.N = 64; p.K = 7 * 64;
+      p.conv = 2; p.Hin = G.H + 6; p.Win = G.W + 8; p.Cin = 8; p.Wout = G.W1; p.kw = 7; p.stride = 2; p.pad = 3;
+      p.bias = b; p.act = ACT_RELU;
+      p.C = c1; p.ldc = 64;
+      RMEM_TRY(gemm_launch(p, s));
+    }
     RMEM_TRY(maxpool3x3s2(c1, x0, G.H1, G.W1, 64, G.H4, G.W4, s));
     mark("enc.stem", s);
     t16* cur = x0;
@@ -497,11 +510,12 @@ struct rmem_engine {
     const float* w = Wt<float>("idbank.w", (size_t)289 * 12 * kD, &rc);
     const float* b = Wt<float>("idbank.b", kD, &rc);
     const float* pf = Wt<float>("idbank.prefix", (size_t)12 * 18 * 18 * kD, &rc);
+    const float* pr = Wt<float>("idbank.prefix_rows", (size_t)17 * 12 * 18 * kD, &rc);
     const float* lg = cfg.model == 0 ? Wt<float>("id_norm.g", kD, &rc) : nullptr;   // deaot.py:65-69 only
     const float* lb = cfg.model == 0 ? Wt<float>("id_norm.b", kD, &rc) : nullptr;
     if (rc) return rc;
     RMEM_TRY(separate_label(label, label_is_f32, label8, G.H, G.W, gi, n_groups, s));
-    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s, pf));
+    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s, pf, pr));
     if (cfg.model == 0)
       for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_t16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
     return RMEM_OK;

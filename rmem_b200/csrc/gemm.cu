@@ -253,6 +253,10 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   RMEM_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty shape M=%d N=%d K=%d", p.M, p.N, p.K);
   RMEM_REQUIRE(!(p.accumulate && !p.c_fp32), "gemm: accumulate needs an fp32 destination");
   if (p.n_split < p.N) RMEM_REQUIRE(p.C2 != nullptr, "gemm: n_split without C2");
+  if (p.conv == 2) {      // stem mode exists on the tcgen05 kernel only
+    RMEM_REQUIRE(gemm_tc_supported(p), "gemm(stem): unsupported shape (Cin=%d kw=%d stride=%d K=%d)", p.Cin, p.kw, p.stride, p.K);
+    return gemm_tc_launch(p, stream);
+  }
   if (gemm_impl_switch() == 0 && p.batch <= 1 && gemm_tc_supported(p)) return gemm_tc_launch(p, stream);
   return gemm_legacy_launch(p, stream);
 }

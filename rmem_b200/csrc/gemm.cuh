@@ -16,6 +16,10 @@ struct GemmParams {
   long long ldb = 0;
   int M = 0, N = 0, K = 0;
   // conv mode (A = NHWC [Hin,Win,Cin]); output pixel m -> (m / Wout, m % Wout)
+  // conv = 2, "stem" mode (the 7x7 stride-2 first convolution on 3 -> 8 channels, tcgen05 kernel only): A is the
+  // zero-PADDED image [Hin][Win][8] (3 pad rows / pixels before the first real one, >= 5 pad pixels after the last), one
+  // k-block per window row: the 64 contiguous elements (8 pixels x 8 channels) starting at padded pixel (oy*2 + ky,
+  // ox*2); B = [N][kw rows][8 pixels][8 channels] with zero weights for the 8th pixel, K = kw * 64.
   int conv = 0, Hin = 0, Win = 0, Cin = 0, Wout = 0, kw = 1, stride = 1, pad = 0;
   // epilogue
   float alpha = 1.f;

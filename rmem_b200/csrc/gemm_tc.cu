@@ -37,6 +37,7 @@ struct TcGemmParams {
   int M, N, nk, stages;
   int splitk;                 // CTAs per cluster along K (1 = no split)
   int conv, taps_w, cin_blocks, pad, stride, BW, BH, tiles_x, Hout, Wout;
+  int sx, sy;                 // coordinate steps of the A tensor map per output pixel (conv: stride, stride; stem: 1, 2)
   float alpha;
   const float* bias;
   int bias_m, act, act_from;
@@ -178,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.conv) {
           const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
           const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
-          tma_load_3d(sa, &map_a, &full[st], cb * TBK, x0 * p.stride - p.pad + kx, y0 * p.stride - p.pad + ky);
+          tma_load_3d(sa, &map_a, &full[st], cb * TBK, x0 * p.sx - p.pad + kx, y0 * p.sy - p.pad + ky);
         } else {
           tma_load_2d(sa, &map_a, &full[st], kb * TBK, m0);
         }
@@ -463,7 +464,11 @@ bool gemm_tc_supported(const GemmParams& p) {
   if (p.res && ((reinterpret_cast<uintptr_t>(p.res) & 15) || p.ldr % 8 != 0)) return false;
   if (p.gate && ((reinterpret_cast<uintptr_t>(p.gate) & 15) || p.ldg % 8 != 0)) return false;
   if (p.bias && !p.bias_m && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
-  if (p.conv) {
+  if (p.conv == 2) {                       // stem mode (see gemm.cuh): K = kw rows of 64 contiguous elements
+    if (p.K != p.kw * TBK || p.stride != 2 || p.Cin != 8) return false;
+    if (p.M % p.Wout != 0) return false;
+    if ((long long)(p.Wout - 1) * 2 * p.Cin + TBK > (long long)p.Win * p.Cin) return false;   // last window inside the row
+  } else if (p.conv) {
     if (p.Cin % TBK != 0) return false;
     if (p.K % (p.kw * p.Cin) != 0) return false;
     if (p.stride < 1 || p.stride > 2) return false;
@@ -478,7 +483,9 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
   RMEM_REQUIRE(gemm_tc_supported(g), "gemm_tc: unsupported shape/alignment (M=%d N=%d K=%d)", g.M, g.N, g.K);
   TcGemmParams p;
   p.M = g.M; p.N = round_up(g.N, 32); p.nk = g.K / TBK;
-  p.conv = g.conv; p.taps_w = g.kw; p.cin_blocks = g.conv ? g.Cin / TBK : 1; p.pad = g.pad; p.stride = g.stride;
+  p.conv = g.conv; p.taps_w = g.kw; p.cin_blocks = g.conv == 1 ? g.Cin / TBK : 1; p.pad = g.pad; p.stride = g.stride;
+  p.sx = p.sy = g.stride;
+  if (g.conv == 2) { p.taps_w = 1; p.pad = 0; p.sx = 1; p.sy = 2; }   // k-block kb = window row ky; padding is physical
   p.BW = 128; p.BH = 1; p.tiles_x = 1; p.Hout = 0; p.Wout = g.Wout;
   p.alpha = g.alpha; p.bias = g.bias; p.bias_m = g.bias_m; p.act = g.act; p.act_from = g.act_from;
   p.res = g.res; p.ldr = g.ldr; p.gate = g.gate; p.ldg = g.ldg; p.accumulate = g.accumulate;
@@ -502,11 +509,22 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
     }
     p.tiles_x = cdiv(g.Wout, p.BW);
     m_tiles = best;
+    if (g.conv == 2) {
+      // Stem: the A row of output pixel (oy, ox) and window row ky is the 64 contiguous elements (8 pixels x 8 channels,
+      // the 8th pixel meets zero weights) that start at padded pixel (oy*2 + ky, ox*2): a tensor map whose second
+      // dimension steps by TWO pixels (32 bytes) while the first one spans 64 elements -- overlapping rows.
+      uint64_t dims[3] = {(uint64_t)TBK, (uint64_t)g.Wout, (uint64_t)g.Hin};
+      uint64_t strides[2] = {(uint64_t)2 * g.Cin * 2, (uint64_t)g.Win * g.Cin * 2};
+      uint32_t box[3] = {(uint32_t)TBK, (uint32_t)p.BW, (uint32_t)(p.BH * 2)};
+      uint32_t estr[3] = {1, 1, 2};
+      RMEM_TRY(tma_encode_cached(&ma, g.A, 3, dims, strides, box, estr));
+    } else {
     uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Win, (uint64_t)g.Hin};
     uint64_t strides[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Win * g.Cin * 2};
     uint32_t box[3] = {(uint32_t)TBK, (uint32_t)(p.BW * g.stride), (uint32_t)(p.BH * g.stride)};
     uint32_t estr[3] = {1, (uint32_t)g.stride, (uint32_t)g.stride};
     RMEM_TRY(tma_encode_cached(&ma, g.A, 3, dims, strides, box, estr));
+    }
   } else {
     m_tiles = cdiv(g.M, TBM);
     uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};

@@ -28,6 +28,18 @@ __global__ void pack_image_kernel(const float* __restrict__ img, t16* __restrict
   store8(out + (size_t)i * 8, v);
 }
 
+// Same into the zero-padded layout the stem convolution reads (gemm.cuh, conv = 2): [H + 6][W + 8][8], pixel (y, x) at
+// padded (y + 3, x + 3).  Only the interior is written: the caller zeroes the buffer once.
+__global__ void pack_image_padded_kernel(const float* __restrict__ img, t16* __restrict__ out, int H, int W) {
+  pdl_prologue();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (i >= HW) return;
+  const int y = i / W, x = i - y * W;
+  float v[8] = {img[i], img[HW + i], img[2 * HW + i], 0.f, 0.f, 0.f, 0.f, 0.f};
+  store8(out + ((size_t)(y + 3) * (W + 8) + x + 3) * 8, v);
+}
+
 __global__ void maxpool_kernel(const t16* __restrict__ x, t16* __restrict__ y, int Hin, int Win, int C, int Hout,
                                int Wout) {
   pdl_prologue();
@@ -444,23 +456,34 @@ __global__ void separate_label_kernel(const void* __restrict__ label, int is_f32
 }
 
 // ------------------------------------------------------------------------------------------------
-// ID bank: one block per token, one thread per output channel.  A 17x17 patch whose in-bounds pixels all carry the
-// same class (the common case away from object boundaries) is a rectangle sum over that class' weight plane: four
-// reads of the per-class 2-D prefix table instead of up to 289 weight rows.  Mixed patches take the tap loop.
+// ID bank: one block per token, one thread per output channel.  Summing one conv-weight row per pixel of the 17x17 label
+// patch is a 289 x 1 KB gather per token (484 MB of L2 reads per 480p frame: 47-72 us).  Three cheaper decompositions of
+// the same sum, picked per patch by their read count:
+//   RECT  the in-bounds pixels share one class: one rectangle of that class' 2-D prefix table (4 reads);
+//   RUNS  every image row of the patch is cut into runs of one class, each run is a difference of two entries of the
+//         per-(row, class) 1-D prefix table (2 reads per run; label maps are piecewise constant, ~2 runs per row);
+//   MINOR rectangle of the dominant class + (w[pixel, class] - w[pixel, dominant]) for the other pixels (salt-and-pepper);
+//   TAPS  the plain gather (also taken when no prefix table is given).
+// Steady-state c3 labels (argmax maps of the network): 59 reads per patch on average instead of 289.
 __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, int use_ignore,
                               const float* __restrict__ wp, const float* __restrict__ prefix,
-                              const float* __restrict__ bias, const float* __restrict__ ln_g,
-                              const float* __restrict__ ln_b, t16* __restrict__ out, long long ldo,
-                              float* __restrict__ out_f32, int w, int C) {
+                              const float* __restrict__ prefix_rows, const float* __restrict__ bias,
+                              const float* __restrict__ ln_g, const float* __restrict__ ln_b, t16* __restrict__ out,
+                              long long ldo, float* __restrict__ out_f32, int w, int C) {
   pdl_prologue();
   __shared__ int8_t ch[17 * 17];
   __shared__ float red[32];
-  __shared__ int s_lo, s_hi;
+  __shared__ int s_hist[13];                     // in-bounds pixels per class (12 = in no one-hot channel)
+  __shared__ int s_nruns, s_nlist;
+  __shared__ int s_rowruns[17];                  // valid-class runs per patch row
+  __shared__ unsigned short list[17 * 17];       // RUNS: ky | x0 << 5 | x1 << 10 (class from ch);  MINOR: tap index
+  // (both lists are built in a fixed order -- row-major -- so the fp32 sum, and with it the whole engine, stays
+  // bit-reproducible from run to run)
   const int tok = blockIdx.x;
   const int py = tok / w, px = tok - py * w;
-  if (threadIdx.x == 0) { s_lo = 127; s_hi = -1; }
+  if (threadIdx.x < 13) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 13) { s_nruns = 0; s_nlist = 0; }
   __syncthreads();
-  int lo = 127, hi = -1;
   for (int t = threadIdx.x; t < 289; t += blockDim.x) {
     int ky = t / 17, kx = t - ky * 17;
     int iy = py * 16 - 8 + ky, ix = px * 16 - 8 + kx;
@@ -470,24 +493,113 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
       if (lab <= 10) c = lab;
       else if (lab == 255 && use_ignore) c = 11;
       else c = 12;                      // in bounds but in no one-hot channel: contributes nothing
-      lo = min(lo, c);
-      hi = max(hi, c);
+      atomicAdd(&s_hist[c], 1);
     }
     ch[t] = (int8_t)c;
   }
-  if (lo <= hi) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
   __syncthreads();
+  // in-bounds taps form the rectangle [ky0, ky1) x [kx0, kx1)
+  const int ky0 = max(0, 8 - py * 16), ky1 = min(17, H + 8 - py * 16);
+  const int kx0 = max(0, 8 - px * 16), kx1 = min(17, W + 8 - px * 16);
+  enum { TAPS = 0, RECT = 1, RUNS = 2, MINOR = 3 };
+  int mode = TAPS, dom = 0;
+  if (prefix) {
+    int tot = 0, best = -1;
+    for (int k = 0; k < 13; ++k) { tot += s_hist[k]; if (k < 12 && s_hist[k] > best) { best = s_hist[k]; dom = k; } }
+    const int minor = tot - best;                            // pixels that are not of the dominant one-hot class
+    if (minor == 0) mode = RECT;
+    else {
+      int cost = 289;
+      if (4 + 2 * minor < cost) { cost = 4 + 2 * minor; mode = MINOR; }
+      if (prefix_rows) {
+        // valid-class runs of this patch (counted by 17 threads, one per row)
+        if (threadIdx.x < 17) {
+          const int ky = threadIdx.x;
+          int n = 0;
+          if (ky >= ky0 && ky < ky1)
+            for (int kx = kx0; kx < kx1; ++kx) {
+              const int k = ch[ky * 17 + kx];
+              if (k < 12 && (kx == kx0 || ch[ky * 17 + kx - 1] != k)) ++n;
+            }
+          s_rowruns[ky] = n;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int n = 0;
+          for (int ky = 0; ky < 17; ++ky) n += s_rowruns[ky];
+          s_nruns = n;
+        }
+        __syncthreads();
+        if (2 * s_nruns < cost) { cost = 2 * s_nruns; mode = RUNS; }
+      }
+    }
+  }
+  if (mode == RUNS) {
+    if (threadIdx.x < 17) {
+      const int ky = threadIdx.x;
+      int pos = 0;
+      for (int r = 0; r < ky; ++r) pos += s_rowruns[r];
+      if (ky >= ky0 && ky < ky1) {
+        int x0 = kx0;
+        for (int kx = kx0 + 1; kx <= kx1; ++kx)
+          if (kx == kx1 || ch[ky * 17 + kx] != ch[ky * 17 + x0]) {
+            if (ch[ky * 17 + x0] < 12) list[pos++] = (unsigned short)(ky | (x0 << 5) | (kx << 10));
+            x0 = kx;
+          }
+      }
+      if (ky == 16) s_nlist = pos;
+    }
+    __syncthreads();
+  } else if (mode == MINOR) {
+    if (threadIdx.x < 32) {                                    // ordered compaction by one warp
+      int pos = 0;
+      for (int t0 = 0; t0 < 289; t0 += 32) {
+        const int t = t0 + threadIdx.x;
+        const bool m = t < 289 && ch[t] >= 0 && ch[t] != dom;
+        const unsigned b = __ballot_sync(0xffffffffu, m);
+        if (m) list[pos + __popc(b & ((1u << threadIdx.x) - 1u))] = (unsigned short)t;
+        pos += __popc(b);
+      }
+      if (threadIdx.x == 0) s_nlist = pos;
+    }
+    __syncthreads();
+  }
   const int c = threadIdx.x;
   float acc = 0.f;
   if (c < C) {
-    const int klo = s_lo, khi = s_hi;
-    if (prefix && klo == khi && klo < 12) {
-      // uniform patch: in-bounds taps form the rectangle [ky0, ky1) x [kx0, kx1)
-      const int ky0 = max(0, 8 - py * 16), ky1 = min(17, H + 8 - py * 16);
-      const int kx0 = max(0, 8 - px * 16), kx1 = min(17, W + 8 - px * 16);
-      const float* P = prefix + (size_t)klo * 18 * 18 * C + c;      // P[ky][kx] = sum over taps [0,ky) x [0,kx)
-      acc = P[((size_t)ky1 * 18 + kx1) * C] - P[((size_t)ky0 * 18 + kx1) * C] - P[((size_t)ky1 * 18 + kx0) * C] +
-            P[((size_t)ky0 * 18 + kx0) * C];
+    if (mode == RECT || mode == MINOR) {
+      const float* P = prefix + (size_t)dom * 18 * 18 * C + c;      // P[ky][kx] = sum over taps [0,ky) x [0,kx)
+      acc = (P[((size_t)ky1 * 18 + kx1) * C] - P[((size_t)ky0 * 18 + kx1) * C]) -
+            (P[((size_t)ky1 * 18 + kx0) * C] - P[((size_t)ky0 * 18 + kx0) * C]);
+      if (mode == MINOR) {
+        const int n = s_nlist;
+        for (int i = 0; i < n; ++i) {
+          const int t = list[i], k = ch[t];
+          const float wd = wp[((size_t)t * 12 + dom) * C + c];
+          const float wk = k < 12 ? wp[((size_t)t * 12 + k) * C + c] : 0.f;
+          acc += wk - wd;
+        }
+      }
+    } else if (mode == RUNS) {
+      const int n = s_nlist;
+      int i = 0;
+      for (; i + 4 <= n; i += 4) {                               // four runs (eight reads) in flight
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = list[i + u], ky = r & 31, x0 = (r >> 5) & 31, x1 = r >> 10;
+          const float* P = prefix_rows + ((size_t)(ky * 12 + ch[ky * 17 + x0]) * 18) * C + c;
+          v[2 * u] = P[(size_t)x1 * C];
+          v[2 * u + 1] = P[(size_t)x0 * C];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[2 * u] - v[2 * u + 1];
+      }
+      for (; i < n; ++i) {
+        const int r = list[i], ky = r & 31, x0 = (r >> 5) & 31, x1 = r >> 10;
+        const float* P = prefix_rows + ((size_t)(ky * 12 + ch[ky * 17 + x0]) * 18) * C + c;
+        acc += P[(size_t)x1 * C] - P[(size_t)x0 * C];
+      }
     } else {
       // predicated loads, eight taps in flight (the tap loop is L2-latency bound otherwise); summed in tap order
       int t = 0;
@@ -795,6 +907,12 @@ int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s) {
   return RMEM_OK;
 }
 
+int pack_image_padded(const float* img, t16* out, int H, int W, cudaStream_t s) {
+  RMEM_CUDA_CHECK(launch_pdl(pack_image_padded_kernel, dim3(cdiv(H * W, 256)), dim3(256), 0, s, img, out, H, W));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
 int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s) {
   RMEM_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
   long long n = (long long)Hout * Wout * (C / 8);
@@ -883,9 +1001,10 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
-                 cudaStream_t s, const float* prefix) {
+                 cudaStream_t s, const float* prefix, const float* prefix_rows) {
   RMEM_REQUIRE(C <= 256 && C % 32 == 0, "idbank: unsupported C=%d", C);
-  RMEM_CUDA_CHECK(launch_pdl(idbank_kernel, dim3(h * w), dim3(256), 0, s, label, H, W, use_ignore, w_packed, prefix, bias, ln_g, ln_b, out, ldo, out_f32, w, C));
+  RMEM_REQUIRE(prefix || !prefix_rows, "idbank: the row-prefix table needs the 2-D prefix table as well");
+  RMEM_CUDA_CHECK(launch_pdl(idbank_kernel, dim3(h * w), dim3(256), 0, s, label, H, W, use_ignore, w_packed, prefix, prefix_rows, bias, ln_g, ln_b, out, ldo, out_f32, w, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -7,6 +7,8 @@ namespace rmem {
 
 // img NCHW fp32 [3,H,W] -> NHWC t16 [H,W,8] (channels 3..7 zero).              (encoder input)
 int pack_image(const float* img, t16* out, int H, int W, cudaStream_t s);
+// zero-padded [H+6][W+8][8] layout for the stem convolution (gemm.cuh conv = 2); writes the interior only
+int pack_image_padded(const float* img, t16* out, int H, int W, cudaStream_t s);
 
 // 3x3 stride-2 pad-1 max pooling on NHWC t16 (resnet.py:186).
 int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wout, cudaStream_t s);
@@ -65,7 +67,7 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 // of uniform class be a 4-read rectangle sum.
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
-                 cudaStream_t s, const float* prefix = nullptr);
+                 cudaStream_t s, const float* prefix = nullptr, const float* prefix_rows = nullptr);
 
 // Mask head (aot_engine.py:457-463, 650-673; evaluator.py:430-441): k engines' planar logits [11,h4,w4] ->
 // bilinear(align_corners=True) -> soft aggregation -> out_logits [1+10k, Ho, Wo] (optional) and uint8 label.

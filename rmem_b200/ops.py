@@ -84,6 +84,29 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: in
     return out
 
 
+def stem_conv(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_RELU) -> torch.Tensor:
+    """conv1 of the ResNet stem (7x7, stride 2, pad 3; resnet.py:178-181) on the tcgen05 GEMM: img fp32 [1,3,H,W] is
+    packed into the zero-padded NHWC8 layout, w t16 [Cout,7,8,8] (weights.py "enc.conv1.w") -> t16 [H1,W1,Cout]."""
+    lib = _capi.load()
+    H, W = int(img.shape[-2]), int(img.shape[-1])
+    H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    Cout = w.shape[0]
+    pad = torch.zeros(H + 6, W + 8, 8, dtype=_capi.op_dtype(), device=img.device)
+    _capi.check(lib.rmem_pack_image_padded_fwd(_capi.ptr(img.contiguous()), _capi.ptr(pad), H, W, _capi.stream_ptr()))
+    out = torch.empty(H1, W1, Cout, dtype=_capi.op_dtype(), device=img.device)
+    d = _capi.GemmDesc()
+    d.A, d.B, d.ldb = pad.data_ptr(), w.data_ptr(), 7 * 64
+    d.M, d.N, d.K = H1 * W1, Cout, 7 * 64
+    d.conv, d.Hin, d.Win, d.Cin, d.Wout, d.kw, d.stride, d.pad = 2, H + 6, W + 8, 8, W1, 7, 2, 3
+    d.alpha = 1.0
+    d.bias = bias.data_ptr()
+    d.act = act
+    d.C, d.ldc, d.c_is_f32 = out.data_ptr(), Cout, 0
+    d.n_split = 1 << 30
+    _capi.check(lib.rmem_gemm_fwd(C.byref(d), _capi.stream_ptr()))
+    return out
+
+
 def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = _capi.load()
     P, Cc = x.shape
@@ -139,16 +162,17 @@ def transpose(x: torch.Tensor, ldy: int) -> torch.Tensor:
 
 
 def id_embedding(label_u8: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, ln_g, ln_b,
-                 use_ignore: bool, prefix: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """label uint8 [H,W] -> fp32 [hw, C].  prefix: optional [12,18,18,C] table (weights.py) enabling the uniform-patch
-    shortcut."""
+                 use_ignore: bool, prefix: Optional[torch.Tensor] = None,
+                 prefix_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """label uint8 [H,W] -> fp32 [hw, C].  prefix / prefix_rows: optional [12,18,18,C] / [17,12,18,C] tables (weights.py)
+    enabling the rectangle / dominant-class / row-run decompositions of the per-pixel gather."""
     lib = _capi.load()
     H, W = label_u8.shape
     h, w = (H - 1) // 16 + 1, (W - 1) // 16 + 1
     Cc = bias.numel()
     out = torch.empty(h * w, Cc, dtype=torch.float32, device=label_u8.device)
     _capi.check(lib.rmem_idbank_fwd(_capi.ptr(label_u8), H, W, int(use_ignore), _capi.ptr(w_packed),
-                                    _capi.ptr(prefix), _capi.ptr(bias),
+                                    _capi.ptr(prefix), _capi.ptr(prefix_rows), _capi.ptr(bias),
                                     _capi.ptr(ln_g), _capi.ptr(ln_b), None, C.c_longlong(0), _capi.ptr(out), h, w, Cc,
                                     _capi.stream_ptr()))
     return out

@@ -67,6 +67,8 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
         out[dst] = w.view(w.shape[0], 25).t().contiguous()                  # [25, C]
 
     conv_bn("enc.conv1", "encoder.conv1", "encoder.bn1", cin_pad=8)
+    # stem layout (gemm.cuh conv = 2): [Cout][7 window rows][8 pixels][8 channels], zero weights for the 8th pixel
+    out["enc.conv1.w"] = torch.nn.functional.pad(out["enc.conv1.w"], (0, 0, 0, 1)).contiguous()
     for li, bi, inpl, pl, s, ds in _resnet_blocks():
         p, q = f"encoder.layer{li}.{bi}", f"enc.layer{li}.{bi}"
         for i in (1, 2, 3):
@@ -82,6 +84,10 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
     pre = torch.zeros(wb.shape[1], 18, 18, wb.shape[0], dtype=torch.float64)
     pre[:, 1:, 1:, :] = wb.double().permute(1, 2, 3, 0).cumsum(1).cumsum(2)
     out["idbank.prefix"] = pre.float().contiguous()
+    # per-(ky, class) 1-D prefix sums over kx: R[ky][k][kx][c] = sum_{x<kx} w[c, k, ky, x]
+    rows = torch.zeros(17, wb.shape[1], 18, wb.shape[0], dtype=torch.float64)
+    rows[:, :, 1:, :] = wb.double().permute(2, 1, 3, 0).cumsum(2)
+    out["idbank.prefix_rows"] = rows.float().contiguous()
     if deaot:
         norm("id_norm", "id_norm")
     out["cur_pos_emb"] = sd["cur_pos_emb"].reshape(-1).contiguous()

@@ -93,3 +93,23 @@ def test_splitk_is_bit_reproducible_and_matches_unsplit(K, cuda_device, monkeypa
     o2 = K.gemm(A, W, b, out_f32=True)
     assert torch.equal(o1, o2)
     assert relfro(o1, F.linear(A.float(), W.float(), b)) < 2e-5 * math.sqrt(Kd)
+
+
+@pytest.mark.parametrize("H,W", [(257, 321), (481, 849), (129, 161)])
+def test_stem_conv_matches_torch(K, cuda_device, H, W):
+    """conv1 (7x7 / stride 2 / pad 3, FrozenBN folded, ReLU) as the "stem" mode of the tcgen05 GEMM (one k-block per
+    window row over the zero-padded NHWC8 image) against F.conv2d in fp32; resnet.py:178-181."""
+    from oracle import rmem_oracle as O
+    from rmem_b200.weights import pack_deaot
+    from rmem_b200 import _capi
+    sd = O.make_state_dict("r50_deaotl", seed=1)
+    pk = pack_deaot(sd)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(1, 3, H, W, generator=g)
+    OP = _capi.op_dtype()
+    x16 = img.to(OP).float()                                  # what the kernel sees after packing
+    w = pk["enc.conv1.w"].float()[:, :, :7, :3].permute(0, 3, 1, 2).contiguous()     # [64,3,7,7] with BN folded
+    ref = F.relu(F.conv2d(x16, w, pk["enc.conv1.b"], stride=2, padding=3))[0].permute(1, 2, 0)
+    out = K.stem_conv(img.to(cuda_device), pk["enc.conv1.w"].to(cuda_device), pk["enc.conv1.b"].to(cuda_device))
+    err = float((out.float().cpu() - ref).abs().max() / ref.abs().max())
+    assert out.shape == ref.shape and err < 4e-3, err

@@ -44,7 +44,9 @@ def test_evict_pick_state_machine_matches_oracle():
 def test_weight_packing_shapes_and_bn_folding():
     sd = synth.make_state_dict("r50_deaotl", seed=0)
     pk = pack_deaot({"module." + k: v for k, v in sd.items()})         # checkpoint-style prefix is stripped
-    assert pk["enc.conv1.w"].shape == (64, 7, 7, 8) and float(pk["enc.conv1.w"][..., 3:].abs().max()) == 0.0
+    # stem layout: [Cout][7 window rows][8 pixels][8 channels]; channels 3.. and the 8th pixel carry zero weights
+    assert pk["enc.conv1.w"].shape == (64, 7, 8, 8) and float(pk["enc.conv1.w"][..., 3:].abs().max()) == 0.0
+    assert float(pk["enc.conv1.w"][:, :, 7].abs().max()) == 0.0
     assert pk["enc.layer3.0.ds.w"].shape == (1024, 1, 1, 512)
     assert pk["idbank.w"].shape == (289, 12, 256) and pk["gpm.1.linear_ID_V.w"].shape == (512, 512)
     assert pk["gpm.0.linear_ID_V.w"].shape == (512, 256) and pk["gpm.2.short.rel.w"].shape == (256, 128)

@@ -148,11 +148,13 @@ def test_id_embedding_matches_conv_of_one_hot(ops, cuda_device):
     for which, lb in (("blocks", lab), ("noisy", noisy)):
         for use_ignore in (False, True):
             ref = O.id_embedding(sd, cfg, O.one_hot_with_ignore(lb, use_ignore))
-            for prefix in (None, pk["idbank.prefix"].to(cuda_device)):      # tap loop only / prefix-table shortcuts
+            # tap loop only / rectangle + dominant-class shortcuts / + row runs
+            for prefix, rows in ((None, None), (pk["idbank.prefix"].to(cuda_device), None),
+                                 (pk["idbank.prefix"].to(cuda_device), pk["idbank.prefix_rows"].to(cuda_device))):
                 out = ops.id_embedding(lb[0, 0].to(torch.uint8).to(cuda_device), pk["idbank.w"].to(cuda_device),
                                        pk["idbank.b"].to(cuda_device), pk["id_norm.g"].to(cuda_device),
-                                       pk["id_norm.b"].to(cuda_device), use_ignore, prefix=prefix)
-                assert relfro(out, ref) < 2e-4, (which, use_ignore, prefix is not None)
+                                       pk["id_norm.b"].to(cuda_device), use_ignore, prefix=prefix, prefix_rows=rows)
+                assert relfro(out, ref) < 2e-4, (which, use_ignore, prefix is not None, rows is not None)
 
 
 def _attn_inputs(T, HW, g, sharp=1.0, Dv=1024):
