@@ -197,6 +197,12 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    # RMEM_BENCH_HIPRIO=1: run the propagation path on a high-priority stream (measured: worse, the overlap with the
+    # prefetched encoder is lost -- 1.52 vs 1.335 ms per frame; kept as a switch).
+    hp = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("RMEM_BENCH_HIPRIO", "0") != "0" else None
+    if hp is not None:
+        hp.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(hp)
     # ---- device-resident run ----
     clip_start(frames_dev)
     for i in range(max(fill, args.warmup)):

@@ -156,7 +156,14 @@ struct rmem_engine {
   int last_enc_slot = -1;                  // last slot encoded on enc_stream (its event orders the encoder temporaries)
   void use_slot(int sl) { fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl]; }
   int init_streams() {
-    RMEM_CUDA_CHECK(cudaStreamCreateWithFlags(&enc_stream, cudaStreamNonBlocking));
+    // Stream priorities were measured and do not help (c3, 1.335 ms per frame with equal priorities): a low-priority
+    // prefetch stream under a high-priority caller stream loses the overlap altogether (1.52 ms), a high-priority second
+    // stream alone costs 0.05 ms.  RMEM_ENC_PRIO = 1 / -1 gives the prefetch stream the highest / lowest priority.
+    int prio_least = 0, prio_greatest = 0;
+    RMEM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    int enc_prio = prio_least;
+    { const char* e = getenv("RMEM_ENC_PRIO"); if (e && e[0] == '1') enc_prio = prio_greatest; }
+    RMEM_CUDA_CHECK(cudaStreamCreateWithPriority(&enc_stream, cudaStreamNonBlocking, enc_prio));
     RMEM_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -189,7 +196,7 @@ struct rmem_engine {
     }
   }
   float* res;         // [HW,512] tgt || tgt_id residual stream
-  t16 *attn_b, *dwo_b;
+  t16 *attn_b, *dwo2;
   t16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
   float *qbias, *rel, *rel_dev;
   t16 *d0, *d1, *d2;
@@ -279,8 +286,9 @@ struct rmem_engine {
     cu0 = a.take<t16>((size_t)G.HW * kDv);
     attn_a = a.take<t16>((size_t)G.HW * kDv);
     dwo = a.take<t16>((size_t)G.HW * kDv);
-    attn_b = a.take<t16>((size_t)G.HW * kDv);     // short-term branch's own pair (it runs beside the long-term branch)
-    dwo_b = a.take<t16>((size_t)G.HW * kDv);
+    attn_b = a.take<t16>((size_t)G.HW * kDv);     // short-term branch's own input (it runs beside the long-term branch)
+    dwo2 = a.take<t16>((size_t)G.HW * 2 * kDv);   // [HW, 2048]: depthwise-conv outputs of the long | short branch = the
+                                                  // A operand of the merged tail projection
     z = a.take<t16>((size_t)G.HW * 2 * kD);
     qk = a.take<t16>((size_t)G.HWp * kDk);
     vt_self = a.take<t16>((size_t)kDv * G.HWp);
@@ -560,12 +568,21 @@ struct rmem_engine {
     RMEM_TRY(gated_tail_dw(pre, attn_a, dwo, s));
     return gated_tail_proj(pre, dwo, s);
   }
-  int gated_tail_dw(const std::string& pre, const t16* in, t16* out, cudaStream_t s) {
+  int gated_tail_dw(const std::string& pre, const t16* in, t16* out, cudaStream_t s, int ldy = 0) {
     const Geo& G = g;
     int rc = RMEM_OK;
     const float* dw = Wt<float>(pre + ".dw", (size_t)25 * kDv, &rc);
     if (rc) return rc;
-    return dwconv5x5(in, dw, out, G.h, G.w, kDv, s);
+    return dwconv5x5(in, dw, out, G.h, G.w, kDv, s, 0, ldy);
+  }
+  // tgt || tgt_id += long_term_attn.projection(dw_long) + short_term_attn.projection(dw_short) as ONE accumulate over the
+  // concatenated K = 2048 (transformer.py:1212-1220; weights.py "tail.proj")
+  int gated_tail_proj2(const std::string& pre, cudaStream_t s) {
+    const Geo& G = g;
+    Lin p;
+    p.A = dwo2; p.lda = 2 * kDv; p.M = G.HW; p.K = 2 * kDv; p.N = 2 * kD; p.w = pre + ".tail.proj";
+    p.C = res; p.ldc = 2 * kD; p.c_fp32 = 1; p.accumulate = 1;
+    return linear(p, s);
   }
   int gated_tail_proj(const std::string& pre, const t16* in, cudaStream_t s) {   // res += proj(in): fp32 read-modify-write
     const Geo& G = g;
@@ -659,7 +676,6 @@ struct rmem_engine {
     const bool par2 = par && branch_par;
     cudaStream_t sb = par2 ? aux_stream : s;
     t16* sh_attn = par2 ? attn_b : attn_a;
-    t16* sh_dwo = par2 ? dwo_b : dwo;
     auto short_branch = [&]() -> int {
       Lin p;
       p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
@@ -673,7 +689,7 @@ struct rmem_engine {
         RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, 16, gate, kDv, sh_attn, kDv, G.h, G.w, kDv,
                                scale, local_ws, local_ws_bytes, sb));
       mark("gpm.short.attn", sb);
-      return gated_tail_dw(pre + ".short", sh_attn, sh_dwo, sb);
+      return gated_tail_dw(pre + ".short", sh_attn, dwo2 + kDv, sb, 2 * kDv);
     };
     if (par2) {
       RMEM_TRY(fork(s));
@@ -681,11 +697,11 @@ struct rmem_engine {
     }
     RMEM_TRY(attention(a, s));
     mark("gpm.long.attn", s);
-    RMEM_TRY(gated_tail(pre + ".long", s));
+    RMEM_TRY(gated_tail_dw(pre + ".long", attn_a, dwo2, s, 2 * kDv));
     mark("gpm.long.tail", s);
     if (par2) RMEM_TRY(join(s));
     else RMEM_TRY(short_branch());
-    RMEM_TRY(gated_tail_proj(pre + ".short", sh_dwo, s));
+    RMEM_TRY(gated_tail_proj2(pre, s));
     mark("gpm.short.tail", s);
 
     // self attention on cat(LN2(tgt), id_LN2(tgt_id))
@@ -696,28 +712,28 @@ struct rmem_engine {
       const float* bi2 = Wt<float>(pre + ".id_norm2.b", kD, &rc);
       if (rc) return rc;
       RMEM_TRY(layernorm_pair(res, 2 * kD, g2, b2, gi2, bi2, z, 2 * kD, G.HW, kD, s));
-      Lin p;
-      p.A = z; p.lda = 2 * kD; p.M = G.HW; p.K = 2 * kD; p.N = kDk; p.w = pre + ".self.linear_QK";
-      p.C = qk; p.ldc = kDk;
-      if (par) RMEM_TRY(fork(s));                    // U1 / U2 on the second stream, QK and the two V^T on this one
-      RMEM_TRY(linear(p, s));
-      for (int half = 0; half < 2; ++half) {
-        // v^T = silu(W_V . z_half^T + b): computed directly value-major (bias along M)
-        const std::string wn = pre + ".self.linear_V" + std::to_string(half + 1);
-        const t16* w = Wt<t16>(wn + ".w", (size_t)2 * kD * kD, &rc);
-        const float* b = Wt<float>(wn + ".b", 2 * kD, &rc);
+      // Two launches instead of five (weights.py "self.QKU" / "self.V12"): [q=k | u] = z . [W_QK ; diag(W_U1, W_U2)]^T with
+      // SiLU from column 128 on the second stream, and v^T = silu(diag(W_V1, W_V2) . z^T + b) computed directly
+      // value-major (bias along M) on this one.
+      if (par) RMEM_TRY(fork(s));
+      {
+        Lin p;
+        p.A = z; p.lda = 2 * kD; p.M = G.HW; p.K = 2 * kD; p.N = kDk + kDv; p.w = pre + ".self.QKU";
+        p.act = ACT_SILU; p.act_from = kDk;
+        p.C = qk; p.ldc = kDk;
+        p.C2 = u_self; p.ldc2 = kDv; p.n_split = kDk;
+        RMEM_TRY(linear(p, s2));
+      }
+      {
+        const t16* w = Wt<t16>(pre + ".self.V12.w", (size_t)kDv * 2 * kD, &rc);
+        const float* b = Wt<float>(pre + ".self.V12.b", kDv, &rc);
         if (rc) return rc;
         GemmParams q;
-        q.A = w; q.lda = kD; q.B = z + half * kD; q.ldb = 2 * kD;
-        q.M = 2 * kD; q.N = G.HW; q.K = kD;
+        q.A = w; q.lda = 2 * kD; q.B = z; q.ldb = 2 * kD;
+        q.M = kDv; q.N = G.HW; q.K = 2 * kD;
         q.bias = b; q.bias_m = 1; q.act = ACT_SILU; q.pad_n_ok = 1;   // pad key columns are masked by the attention
-        q.C = vt_self + (size_t)half * 2 * kD * G.HWp; q.ldc = G.HWp;
+        q.C = vt_self; q.ldc = G.HWp;
         RMEM_TRY(gemm_launch(q, s));
-        Lin u;
-        u.A = z + half * kD; u.lda = 2 * kD; u.M = G.HW; u.K = kD; u.N = 2 * kD;
-        u.w = pre + ".self.linear_U" + std::to_string(half + 1);
-        u.act = ACT_SILU; u.C = u_self + half * 2 * kD; u.ldc = kDv;
-        RMEM_TRY(linear(u, s2));
       }
       if (par) RMEM_TRY(join(s));
       LongAttnArgs sa;

@@ -399,7 +399,8 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
   using L = TcSmem<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    const int a = L::total(kMaxStages), b = BN == 64 ? L::total(4, kMaxSplitK) : 0;
+    // most the launcher below can ask for: BN = 256 runs 4 stages (6 x 48 KB would not fit in 227 KB)
+    const int a = L::total(BN == 256 ? 4 : kMaxStages), b = BN == 64 ? L::total(4, kMaxSplitK) : 0;
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          a > b ? a : b));
     attr_done = true;

@@ -254,11 +254,11 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
 // fp32 accumulation in (ky, kx) order.  The register-only versions before it sat at ~13 us for 6.6 MB of traffic
 // (148 registers -> 2.4 waves of L2-latency-bound threads).
 constexpr int DW_TH = 8, DW_TW = 18;
-__global__ void __launch_bounds__(256) dwconv5_kernel(const t16* __restrict__ x, const float* __restrict__ w,
-                                                      t16* __restrict__ y, int h, int wd, int C) {
+__global__ void __launch_bounds__(256) dwconv5_kernel(const t16* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                      t16* __restrict__ y, int ldy, int h, int wd, int C) {
   __shared__ uint32_t tile[(DW_TH + 4) * (DW_TW + 4)][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cp = C / 2;
+  const int cp = ldx / 2, cpy = ldy / 2;                 // pixel pitch of input / output in channel pairs
   const int c2 = blockIdx.x * 32 + lane;                 // channel pair (C % 64 == 0)
   const int x0 = blockIdx.y * DW_TW, y0 = blockIdx.z * DW_TH;
   float2 wt[25];
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) dwconv5_kernel(const t16* __restrict__ x,
         a0 = fmaf(win[kx][ky].x, wt[ky * 5 + kx].x, a0);
         a1 = fmaf(win[kx][ky].y, wt[ky * 5 + kx].y, a1);
       }
-    yout[((size_t)oy * wd + x0 + px) * cp] = pack2(a0, a1);
+    yout[((size_t)oy * wd + x0 + px) * cpy] = pack2(a0, a1);
   }
 }
 
@@ -946,10 +946,13 @@ int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y,
   return groupnorm_impl<float>(x, gamma, beta, y, P, C, G, relu, stats, s);
 }
 
-int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s) {
+int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s, int ldx, int ldy) {
   RMEM_REQUIRE(C % 64 == 0, "dwconv: C %% 64");
+  if (ldx <= 0) ldx = C;
+  if (ldy <= 0) ldy = C;
+  RMEM_REQUIRE(ldx % 2 == 0 && ldy % 2 == 0 && ldx >= C && ldy >= C, "dwconv: ldx=%d ldy=%d", ldx, ldy);
   const dim3 grid(C / 64, cdiv(wd, DW_TW), cdiv(h, DW_TH));
-  RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel, grid, dim3(256), 0, s, x, w, y, h, wd, C));
+  RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel, grid, dim3(256), 0, s, x, ldx, w, y, ldy, h, wd, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

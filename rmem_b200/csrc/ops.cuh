@@ -42,7 +42,8 @@ int qprep_heads(const t16* q, long long ldq, const float* pe_cur, const float* p
                 float scale, t16* qt, float* qbias, int P, int H, cudaStream_t s);
 
 // Depthwise 5x5 (pad 2) on a token-major map: x t16 [h*w, C], w fp32 [25, C] -> y t16.   (basic.py:38-59)
-int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s);
+// ldx / ldy: pixel pitch of input / output in elements (<= 0: C)
+int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s, int ldx = 0, int ldy = 0);
 
 // Bilinear resize, align_corners=True, NHWC t16.                                         (fpn.py:50,58)
 int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s);

@@ -136,6 +136,22 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
         linear(q + ".self.linear_QK", p + ".self_attn.linear_QK")
         for nm in ("linear_V1", "linear_V2", "linear_U1", "linear_U2"):
             linear(f"{q}.self.{nm}", f"{p}.self_attn.{nm}")
+        # Fused launches of the engine (same arithmetic, fewer small GEMMs on the per-frame critical path):
+        #  * self.QKU  [128 + 1024, 512]: rows 0..127 = linear_QK (all 512 inputs), then linear_U1 on the tgt half and
+        #    linear_U2 on the tgt_id half of z = cat(LN2(tgt), id_LN2(tgt_id)) as a block-diagonal weight
+        #  * self.V12  [1024, 512]: block-diagonal linear_V1 / linear_V2 (computed value-major: W . z^T)
+        #  * tail.proj [512, 2048]: long_term_attn.projection | short_term_attn.projection along K, biases summed
+        #    (tgt += o2 + o3 is one accumulate of the concatenated depthwise-conv outputs, transformer.py:1212-1220)
+        od = _capi.op_dtype()
+        z = torch.zeros(512, 256, dtype=od)
+        u1, u2 = out[f"{q}.self.linear_U1.w"], out[f"{q}.self.linear_U2.w"]
+        out[f"{q}.self.QKU.w"] = torch.cat([out[f"{q}.self.linear_QK.w"], torch.cat([u1, z], 1), torch.cat([z, u2], 1)], 0).contiguous()
+        out[f"{q}.self.QKU.b"] = torch.cat([out[f"{q}.self.linear_QK.b"], out[f"{q}.self.linear_U1.b"], out[f"{q}.self.linear_U2.b"]]).contiguous()
+        v1, v2 = out[f"{q}.self.linear_V1.w"], out[f"{q}.self.linear_V2.w"]
+        out[f"{q}.self.V12.w"] = torch.cat([torch.cat([v1, z], 1), torch.cat([z, v2], 1)], 0).contiguous()
+        out[f"{q}.self.V12.b"] = torch.cat([out[f"{q}.self.linear_V1.b"], out[f"{q}.self.linear_V2.b"]]).contiguous()
+        out[f"{q}.tail.proj.w"] = torch.cat([out[f"{q}.long.proj.w"], out[f"{q}.short.proj.w"]], 1).contiguous()
+        out[f"{q}.tail.proj.b"] = (out[f"{q}.long.proj.b"] + out[f"{q}.short.proj.b"]).contiguous()
     if deaot:
         norm("gpm.out_norm", "LSTT.decoder_norms.0.gn")
 

@@ -37,6 +37,7 @@ def both(fn):
 
 
 @pytest.mark.parametrize("shape", [(1674, 640, 256), (1674, 512, 1024), (25773, 64, 256), (25773, 256, 64),
+                                   (25773, 256, 512), (3726, 1152, 512),     # wide tiles (BN = 256)
                                    (6527, 512, 128), (129, 64, 64), (1674, 128, 512), (1674, 256, 128),
                                    (512, 1674, 256),
                                    # split-K clusters (few tiles, long K): S = 4, S = 4 with 2 tiles, odd k-block count

@@ -10,7 +10,7 @@ from rmem_b200.synth import make_state_dict, synthetic_frames, synthetic_label
 
 dev = torch.device("cuda:0"); torch.cuda.set_device(dev)
 sd = make_state_dict("r50_deaotl", seed=0, sharpen=4.0)
-cfg = RmemConfig(former_mem_len=B.FORMER, latter_mem_len=B.LATTER, attn_impl=B.ATTN_IMPLS["tc2"], max_engines=1)
+cfg = RmemConfig(former_mem_len=B.FORMER, latter_mem_len=B.LATTER, attn_impl=B.ATTN_IMPLS["tc3"], max_engines=1)
 eng = build_engine("deaotengine", aot_model=DeAOTModel(sd, cfg, dev), long_term_mem_gap=B.GAP)
 frames = synthetic_frames(9, B.H, B.W, seed=1000).to(dev); label0 = synthetic_label(B.H, B.W, B.N_OBJ)
 eng.restart_engine(); eng.long_term_mem_gap = B.GAP
