@@ -54,7 +54,7 @@ class OracleConfig:
     """Frozen subset of configs/models/r50_deaotl.py + configs/pre_vost.py."""
     model: str = "r50_deaotl"           # "r50_deaotl" | "r50_aotl"
     former_mem_len: int = 1
-    latter_mem_len: int = 7
+    latter_mem_len: int = 8             # shipped setting (configs/models/r50_deaotl.py:8); the T=8 workloads pass 7
     d_model: int = 256                  # MODEL_ENCODER_EMBEDDING_DIM
     n_layers: int = 3                   # MODEL_LSTT_NUM
     max_obj: int = MAX_OBJ

@@ -30,7 +30,9 @@ class RmemConfig:
     """The frozen subset of configs/models/r50_deaotl.py + configs/pre_vost.py this path depends on."""
     model: str = "r50_deaotl"
     former_mem_len: int = 1          # FORMER_MEM_LEN
-    latter_mem_len: int = 7          # LATTER_MEM_LEN
+    # LATTER_MEM_LEN: 8 = what the reference ships (configs/models/r50_deaotl.py:8, eval_vost.sh `--latter_mem_len 8`:
+    # bank capacity 1 + 8 = 9 frames).  BASELINE.json's "T=8" workloads (bench.py, the c3 / c4 tests) pass 7 explicitly.
+    latter_mem_len: int = 8
     max_obj_num: int = MAX_OBJ
     attn_impl: int = _capi.ATTN_TC3
     max_engines: int = 4

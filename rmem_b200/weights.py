@@ -164,6 +164,55 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
     return out
 
 
+def load_checkpoint(ckpt, model: str = "r50_deaotl", template: Dict[str, torch.Tensor] = None,
+                    widened_init: str = "template") -> Tuple[Dict[str, torch.Tensor], List[str]]:
+    """`load_network` of the reference (utils/checkpoint.py:75-101) for this path: turn a released checkpoint into the
+    state_dict `pack_model` / `RmemModel` take.
+
+    ckpt      path (torch.load, CPU) or an already loaded dict.  `'state_dict'` / `'model'` wrappers are unwrapped (:78-83).
+    template  the freshly built model's state_dict (names -> tensors of the model's shapes; the reference calls it
+              `model_dict`, :84).  Default: rmem_b200.synth.make_state_dict(model, seed=0).
+    Per checkpoint entry, in the reference's order (:87-98):
+      * conv weight whose input-channel count is ONE LESS than the model's (`patch_wise_id_bank.weight` saved with 11
+        channels, the model built with MODEL_IGNORE_TOKEN has 12): copied into the first channels, the extra channel keeps
+        the template's value (`widened_init="template"`, what the reference does with its freshly initialised model) or is
+        zeroed (`"zeros"`: the ignore channel then contributes nothing);
+      * same name and shape: taken;  `module.`-prefixed name (DDP) whose stripped name and shape match: taken;
+      * anything else: reported in the returned list (the reference's `pretrained_dict_remove`), not loaded.
+    Returns (state_dict, dropped_keys)."""
+    from .synth import make_state_dict
+    if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+        ckpt = torch.load(ckpt, map_location="cpu")
+    if "state_dict" in ckpt:
+        pretrained = ckpt["state_dict"]
+    elif "model" in ckpt:
+        pretrained = ckpt["model"]
+    else:
+        pretrained = ckpt
+    model_dict = {k: v.detach().clone().float() for k, v in (template or make_state_dict(model, seed=0)).items()}
+    update, dropped = {}, []
+    for k, v in pretrained.items():
+        if not torch.is_tensor(v):
+            dropped.append(k)
+            continue
+        v = v.detach().float().cpu()
+        if (k in model_dict and v.dim() > 2 and v.shape[0] == model_dict[k].shape[0]
+                and v.shape[1] == model_dict[k].shape[1] - 1):
+            if widened_init == "zeros":
+                model_dict[k][:, -1:] = 0
+            model_dict[k][:, :-1] = v
+            continue
+        if k in model_dict and v.shape == model_dict[k].shape:
+            update[k] = v
+        elif k[:7] == "module.":
+            if k[7:] in model_dict and v.shape == model_dict[k[7:]].shape:
+                update[k[7:]] = v
+        else:
+            dropped.append(k)
+    model_dict.update(update)
+    return model_dict, dropped
+
+
 def pack_deaot(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return pack_model(sd, "r50_deaotl")
 

@@ -7,8 +7,9 @@ every frame and are compared on (a) 1/4-res logits, (b) argmax labels, (c) long_
 update (integer, exact).
 
 Tolerance (stated): tensor-core operands are fp16 (fp32 accumulate, fp32 residual stream / norms / logits);
-the reference is fp32.  1/4-res logits: max-abs error <= 5e-2 * max|logit|; label agreement
->= 99 %; eviction index sequence identical.
+the reference is fp32.  1/4-res logits: max-abs error <= 1.5e-2 * max|logit| (achieved: 2-4e-3; SURVEY.md 8c asked for
+5e-2); label agreement >= 99.5 %; eviction index sequence identical.  The achieved numbers of every case are appended
+to gpurun_out/r02_parity.json (committed under profiles/ by the round script).
 """
 import json
 import os
@@ -22,8 +23,10 @@ from oracle import rmem_oracle as O
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-LOGIT_TOL = 5e-2
-LABEL_AGREE = 0.99
+LOGIT_TOL = 1.5e-2
+LABEL_AGREE = 0.995
+
+from parity_report import report  # noqa: E402
 
 
 def load_case(name):
@@ -86,6 +89,8 @@ def test_engine_matches_reference_goldens(cuda_device, name, impl):
     ours = torch.stack(rec["labels"])
     agree = float((ours == torch.from_numpy(z["labels"])).float().mean())
     print(f"[{name}] label agreement = {agree:.5f}")
+    report(f"golden/{name}/attn_impl_{impl}", worst_rel_logit_err=worst, label_agreement=agree, idx_identical=True,
+           frames=len(rec["logits4"]), tolerances=dict(logit=LOGIT_TOL, label=LABEL_AGREE), vs="unmodified reference")
     assert agree >= LABEL_AGREE
 
 

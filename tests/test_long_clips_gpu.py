@@ -1,0 +1,84 @@
+"""Long clips and deep banks at BASELINE.json's full sizes against fixtures of the fp32 CPU oracle
+(oracle/make_long_golden.py; the oracle is pinned to the unmodified reference by oracle/make_golden.py):
+
+  long_c3_gap5 / long_c3_gap67   c3 (R50_DeAOTL+RMem, 481x849, 10 objects, T=8) over 320 propagated frames, one long-term
+                                 append + eviction every 5 / every 67 frames (67 = max(round(2000/30), 5), evaluator.py:330-332)
+  deep_c3_T9                     c3 at the shipped bank capacity 1 + 8
+  deep_c4_T8                     c4 (721x1281, 30 objects = 3 object groups) at T = 8
+
+Both sides are teacher-forced with the same procedural label history.  Checked on EVERY frame: long_memories_indexes
+after the update (identical), and on every eviction the dropped position (identical) and the normalised relevance vector
+(<= 2e-3); on the stored frames: 1/4-res logits within LOGIT_TOL * max|logit| of the oracle and label agreement
+>= LABEL_AGREE.  This is where fp16 drift of the fp32 residual stream / the fp16 bank over hundreds of frames would show.
+The achieved numbers go to gpurun_out/r02_parity.json (copied to profiles/ by the round script)."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_long_golden as G
+from oracle import rmem_oracle as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LOGIT_TOL = 1.5e-2
+LABEL_AGREE = 0.995
+REL_TOL = 2e-3
+
+
+@pytest.mark.parametrize("name", list(G.CASES))
+def test_long_clip_matches_oracle_fixture(cuda_device, name):
+    from rmem_b200.engine import DeAOTModel, RmemConfig, build_engine
+    path = os.path.join(HERE, "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"fixture {name}.npz not generated")
+    z = np.load(path)
+    H, W, n_obj, former, latter, gap, n_frames, every, seed = [int(x) for x in z["case"]]
+    assert (H, W, n_obj, former, latter, gap, n_frames, every, seed) == G.CASES[name], "fixture is stale"
+    sd = O.make_state_dict("r50_deaotl", seed=seed, sharpen=4.0)
+    frames, label0 = G.clip_inputs(name)
+    frames = frames.to(cuda_device)
+    cfg = RmemConfig(former_mem_len=former, latter_mem_len=latter, max_engines=(n_obj + 9) // 10)
+    eng = build_engine("deaotengine", aot_model=DeAOTModel(sd, cfg, cuda_device), long_term_mem_gap=gap)
+    logit_frames = {int(f): i for i, f in enumerate(z["logit_frames"])}
+    evict_at = {(int(f), int(g)): i for i, (f, g) in enumerate(z["evict_frames"])}
+    worst_logit, worst_rel, min_agree, n_evict = 0.0, 0.0, 1.0, 0
+    eng.restart_engine()
+    eng.add_reference_frame(G.frame_of(frames, 0), label0.int().to(cuda_device), obj_nums=[n_obj], frame_step=0)
+    for f in range(1, n_frames):
+        img = G.frame_of(frames, f)
+        if f + 1 < n_frames:
+            eng.prefetch(G.frame_of(frames, f + 1))
+        lg, lab = eng.match_propogate_one_frame(img, output_size=(H, W), return_label=True)
+        if f in logit_frames:
+            i = logit_frames[f]
+            ref = torch.from_numpy(z["logits"][i].astype(np.float32))            # [n_eng, 11, h4/S, w4/S]
+            for gi, e in enumerate(eng.aot_engines):
+                mine = e.pred_id_logits[0, :, ::G.SAMPLE, ::G.SAMPLE].cpu()
+                worst_logit = max(worst_logit, float((mine - ref[gi]).abs().max() / ref[gi].abs().max()))
+            blob = z["labels_blob"][int(z["labels_off"][i]):int(z["labels_off"][i + 1])].tobytes()
+            ref_lab = torch.from_numpy(np.frombuffer(zlib.decompress(blob), dtype=np.uint8).reshape(H, W).copy())
+            min_agree = min(min_agree, float((lab[0, 0].cpu() == ref_lab).float().mean()))
+        eng.update_memory(G.forced_label(label0, f).to(cuda_device))
+        for gi, e in enumerate(eng.aot_engines):
+            want = [int(v) for v in z["idx"][f - 1, gi] if v >= 0]
+            assert e.long_memories_indexes == want, (name, f, gi, e.long_memories_indexes, want)
+            if (f, gi) in evict_at:
+                k = evict_at[(f, gi)]
+                rel, drop = e.last_evict
+                assert drop == int(z["evict_drop"][k]), (name, f, gi, drop, int(z["evict_drop"][k]))
+                ref_rel = z["evict_rel"][k][:len(rel)]
+                worst_rel = max(worst_rel, float(np.abs(np.array(rel) - ref_rel).max()))
+                n_evict += 1
+    rec = dict(case=name, frames=n_frames - 1, evictions=n_evict, logit_samples=len(logit_frames),
+               worst_rel_logit_err=worst_logit, min_label_agreement=min_agree, worst_relevance_abs_err=worst_rel,
+               tolerances=dict(logit=LOGIT_TOL, label=LABEL_AGREE, relevance=REL_TOL))
+    print(json.dumps(rec))
+    from parity_report import report
+    report(f"long/{name}", **rec)
+    assert n_evict == len(evict_at)
+    assert worst_logit < LOGIT_TOL and min_agree >= LABEL_AGREE and worst_rel < REL_TOL, rec
