@@ -27,7 +27,7 @@
 //                                   setmaxnreg gives the softmax warpgroups 152 registers and the last warpgroup 40
 //   TMEM (512 cols per CTA): O[256] | S[128] (one group) | 4 x P[32] (packed fp16, two groups in flight)
 //   smem per CTA: Q 32 KB | K ring 6 x 8 KB (32 of a sub-tile's 64 keys) | V^T ring 8 x 16 KB (128 of 256 dv rows x 64 keys)
-//   Work: units = (query-tile pair, Dv chunk of 256); a unit is T * ceil(HW / 128) groups of 128 keys; the (unit, group)
+//   Work: units = (query-tile pair, Dv chunk of 256); a unit is T * ceil(HW / 64) sub-tiles of 64 keys; the (unit, sub-tile)
 //   sequence is cut into one contiguous range per cluster (stream-K, cost-aware bounds), <= 2 segments per cluster, each
 //   flushed as normalised fp16 rows + fp32 (m, l); combine3_kernel merges, gates and emits the per-frame attention mass.
 #include <cstdlib>
@@ -43,7 +43,6 @@ using namespace tc;
 
 constexpr int BM = 128;        // query rows per CTA (256 per cluster)
 constexpr int BNS = 64;        // keys per sub-tile (one softmax step, one P.V MMA group)
-constexpr int BNG = 128;       // keys per group (one S MMA group)
 constexpr int DK = 128;
 constexpr int DVC = 256;       // Dv columns per unit
 constexpr int KS = 6;          // K ring depth (sub-tiles)
@@ -79,8 +78,8 @@ constexpr float RESCALE_THRESHOLD = 15.0f;     // log2 units: P <= 2^15 (fp16 ma
 
 constexpr int kMaxCL = 96;     // clusters a launch may use (B200: 74)
 struct Tc3Params {
-  int HW, HWp, T, gpf, TPU, n_units, n_dv, nCL, Dv;
-  int bounds[kMaxCL + 1];      // cluster c owns steps [bounds[c], bounds[c+1]) of the (unit, group) sequence
+  int HW, HWp, T, tpf, TPU, n_units, n_dv, nCL, Dv;   // tpf = 64-key sub-tiles per frame, TPU = T * tpf per unit
+  int bounds[kMaxCL + 1];      // cluster c owns steps [bounds[c], bounds[c+1]) of the (unit, sub-tile) sequence
   int slot[kMaxBankFrames];
   float scale_log2;            // scale * log2(e)
   const float* qbias;          // [HW, T] or null (already multiplied by scale)
@@ -202,7 +201,7 @@ __device__ int g_trace3_cl = 0;
     if (trace && lane == 0 && (j) < 256) trace[(long long)(j) * 16 + (k)] = clock64();        \
   } while (0)
 
-struct Seg { int unit, lo, hi; };   // groups [lo, hi) of the unit
+struct Seg { int unit, lo, hi; };   // sub-tiles [lo, hi) of the unit
 
 __global__ void __launch_bounds__(kThreads, 1)
 long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -243,7 +242,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     cta_times[0] = (long long)gt; cta_times[4] = smid; cta_times[5] = clock64();
   }
 
-  // ---- this cluster's work: a contiguous range of (unit, group) steps -> at most two segments ----
+  // ---- this cluster's work: a contiguous range of (unit, sub-tile) steps -> at most two segments ----
   const long long lo = p.bounds[cl], hi = p.bounds[cl + 1];
   Seg seg[2];
   int nseg = 0;
@@ -260,7 +259,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       x = e;
     }
   }
-  const int n0 = nseg > 0 ? seg[0].hi - seg[0].lo : 0;                       // groups of the first segment
+  const int n0 = nseg > 0 ? seg[0].hi - seg[0].lo : 0;                       // sub-tiles of the first segment
   const int ntot = n0 + (nseg > 1 ? seg[1].hi - seg[1].lo : 0);
   // units are ordered (query pair major, Dv chunk minor): the Q tiles change only when unit / n_dv changes
   const bool q_reload1 = nseg > 1 && (seg[1].unit / p.n_dv != seg[0].unit / p.n_dv);
@@ -306,21 +305,19 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           }
           __syncwarp();
         }
-        for (int g = seg[s].lo; g < seg[s].hi; ++g) {
-          const int t = g / p.gpf, jg = g - t * p.gpf;
-#pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub, ++i) {
-            const int st = i % KS;
-            if (i >= KS) mbar_wait_b(&k_empty[st], ((i / KS) - 1) & 1);
-            if (elect_one()) {
-              const int key0 = p.slot[t] * p.HWp + jg * BNG + sub * BNS + (int)rank * (BNS / 2);
-              unsigned char* sk = smem + OFF_K + st * SMEM_K;
-              tma_load_2d_pair(sk, &map_k, &k_full[st], 0, key0);
-              tma_load_2d_pair(sk + (BNS / 2) * 128, &map_k, &k_full[st], 64, key0);
-              if (leader) mbar_expect_tx(&k_full[st], 2 * SMEM_K); else mbar_arrive_leader(&k_full[st]);
-            }
-            __syncwarp();
+        int t = seg[s].lo / p.tpf, jt = seg[s].lo - t * p.tpf;
+        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++i, ++jt) {
+          if (jt == p.tpf) { jt = 0; ++t; }
+          const int st = i % KS;
+          if (i >= KS) mbar_wait_b(&k_empty[st], ((i / KS) - 1) & 1);
+          if (elect_one()) {
+            const int key0 = p.slot[t] * p.HWp + jt * BNS + (int)rank * (BNS / 2);
+            unsigned char* sk = smem + OFF_K + st * SMEM_K;
+            tma_load_2d_pair(sk, &map_k, &k_full[st], 0, key0);
+            tma_load_2d_pair(sk + (BNS / 2) * 128, &map_k, &k_full[st], 64, key0);
+            if (leader) mbar_expect_tx(&k_full[st], 2 * SMEM_K); else mbar_arrive_leader(&k_full[st]);
           }
+          __syncwarp();
         }
       }
     }
@@ -332,19 +329,17 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       int i = 0;
       for (int s = 0; s < nseg; ++s) {
         const int dv0 = (seg[s].unit % p.n_dv) * DVC + (int)rank * (DVC / 2);
-        for (int g = seg[s].lo; g < seg[s].hi; ++g) {
-          const int t = g / p.gpf, jg = g - t * p.gpf;
-#pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub, ++i) {
-            const int st = i % VS;
-            if (i >= VS) mbar_wait_b(&v_empty[st], ((i / VS) - 1) & 1);
-            if (elect_one()) {
-              const int key0 = p.slot[t] * p.HWp + jg * BNG + sub * BNS;
-              tma_load_2d_pair(smem + OFF_V + st * SMEM_V, &map_v, &v_full[st], key0, dv0);
-              if (leader) mbar_expect_tx(&v_full[st], 2 * SMEM_V); else mbar_arrive_leader(&v_full[st]);
-            }
-            __syncwarp();
+        int t = seg[s].lo / p.tpf, jt = seg[s].lo - t * p.tpf;
+        for (int g = seg[s].lo; g < seg[s].hi; ++g, ++i, ++jt) {
+          if (jt == p.tpf) { jt = 0; ++t; }
+          const int st = i % VS;
+          if (i >= VS) mbar_wait_b(&v_empty[st], ((i / VS) - 1) & 1);
+          if (elect_one()) {
+            const int key0 = p.slot[t] * p.HWp + jt * BNS;
+            tma_load_2d_pair(smem + OFF_V + st * SMEM_V, &map_v, &v_full[st], key0, dv0);
+            if (leader) mbar_expect_tx(&v_full[st], 2 * SMEM_V); else mbar_arrive_leader(&v_full[st]);
           }
+          __syncwarp();
         }
       }
     }
@@ -356,10 +351,10 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // One 64-key score MMA group per sub-tile into half-slot (j & 1).  The two half-slots are recycled independently, each
       // as soon as its single owner group has the scores in registers (a 128-key MMA into one slot had to wait for BOTH
       // owners: 2180 cycles per key group, profiles/r02_attn3_trace_3groups_1slot.txt).
-      for (int i = 0; i < 2 * ntot; ++i) {
+      for (int i = 0; i < ntot; ++i) {
         const int st = i % KS, sub = i & 1;
         if (i == 0) mbar_wait_cl(q_full, 0);
-        if (i == 2 * n0 && q_reload1) mbar_wait_cl(q_full, 1);
+        if (i == n0 && q_reload1) mbar_wait_cl(q_full, 1);
         mbar_wait_cl(&k_full[st], (i / KS) & 1);
         TRACE3(i, 10);
         if (i >= 2) mbar_wait_cl(&s_free[sub], ((i >> 1) - 1) & 1);   // the scores of sub-tile i-2 are in registers
@@ -378,7 +373,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           }
           commit_pair(&k_empty[st]);
           commit_pair(&s_full[i % 6]);
-          if (i == 2 * n0 - 1 && q_reload1) commit_pair(q_free);
+          if (i == n0 - 1 && q_reload1) commit_pair(q_free);
         }
         __syncwarp();
         TRACE3(i, 3);
@@ -389,13 +384,13 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (ntot > 0 && leader) {
       constexpr uint32_t idesc_o = make_idesc(2 * BM, DVC);
       const uint32_t smem_base = smem_u32(smem);
-      for (int j = 0; j < 2 * ntot; ++j) {
-        const int gi = j >> 1, b = (gi & 1) * 2 + (j & 1), sv = j % VS;
+      for (int j = 0; j < ntot; ++j) {
+        const int b = j & 3, sv = j % VS;
         mbar_wait_cl(&v_full[sv], (j / VS) & 1);             // long since complete: its latency hides behind the P wait
         TRACE3(j, 13);
-        const bool first = (j == 0) || (j == 2 * n0);
-        if (j == 2 * n0 && nseg > 1) mbar_wait_cl(o_drained, 0);
-        mbar_wait_cl(&p_full[b], (gi >> 1) & 1);
+        const bool first = (j == 0) || (j == n0);
+        if (j == n0 && nseg > 1) mbar_wait_cl(o_drained, 0);
+        mbar_wait_cl(&p_full[b], (j >> 2) & 1);
         fence_after();
         TRACE3(j, 0);
         if (elect_one()) {
@@ -440,7 +435,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // m_ref: the running maximum this group's l / l_piece are relative to
       float m_ref = -INFINITY, l_tot = 0.f, l_piece = 0.f, bias2 = 0.f;
       int cur_t = -1;
-      const int j_first = j, j_last = j + 2 * (seg[s].hi - seg[s].lo) - 1;
+      const int j_first = j, j_last = j + (seg[s].hi - seg[s].lo) - 1;
       float* piece_base = (p.pieces && dvc == 0)
                               ? p.pieces + (((long long)(cta * 2 + s) * p.T) * kGroups + grp) * (BM * 2) + row * 2
                               : nullptr;
@@ -451,21 +446,20 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           d[1] = l_piece;
         }
       };
-      int t = seg[s].lo / p.gpf, jg = seg[s].lo - t * p.gpf;
-      for (int g = seg[s].lo; g < seg[s].hi; ++g, ++jg, j += 2) {
-        if (jg == p.gpf) { jg = 0; ++t; }
-        if (t != cur_t) {                                   // every group walks every key group's frame index
+      int t = seg[s].lo / p.tpf, jt = seg[s].lo - t * p.tpf;
+      for (int g = seg[s].lo; g < seg[s].hi; ++g, ++jt, ++j) {
+        if (jt == p.tpf) { jt = 0; ++t; }
+        if (t != cur_t) {                                   // every group walks every sub-tile's frame index
           if (cur_t >= 0) flush_piece(cur_t);
           cur_t = t;
           l_piece = 0.f;
           bias2 = (p.qbias && row_ok) ? p.qbias[(long long)qi * p.T + t] * LOG2E : 0.f;
         }
-#pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
-          const int jj = j + sub;
+        {
+          const int jj = j;
           if (jj != own) continue;
           own += kGroups;
-          const int gi = jj >> 1, b = (gi & 1) * 2 + sub;
+          const int sub = jj & 1, b = jj & 3;               // score half-slot, P buffer
           long long* const trace_s = quad == 0 ? trace : nullptr;
 #define TRACE3_S(k) do { if (trace_s && lane == 0 && jj < 256) trace_s[(long long)jj * 16 + (k)] = clock64(); } while (0)
           TRACE3_S(4);
@@ -477,10 +471,10 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             uint32_t r0[32], r1[32];
             tmem_ld32_nowait(lane_addr + TMEM_S + sub * BNS, r0);
             tmem_ld32_nowait(lane_addr + TMEM_S + sub * BNS + 32, r1);
-            // P buffer b was last read by P.V of group gi-2 (long retired in the steady state): the wait's own latency
+            // P buffer b was last read by P.V of sub-tile jj-4 (long retired in the steady state): the wait's own latency
             // overlaps the TMEM load
-            if (gi >= 2) {
-              mbar_wait_b(&sp_free[b], ((gi - 2) >> 1) & 1);
+            if (jj >= 4) {
+              mbar_wait_b(&sp_free[b], ((jj >> 2) - 1) & 1);
               fence_after();
             }
             tmem_ld_wait();
@@ -492,7 +486,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           fence_before();
           __syncwarp();
           if (lane == 0) { if (leader) mbar_arrive(&s_free[sub]); else mbar_arrive_leader(&s_free[sub]); }
-          const int key0 = jg * BNG + sub * BNS;
+          const int key0 = jt * BNS;
           if (key0 + BNS > p.HW) {                             // ragged / padding sub-tile at the end of the frame
 #pragma unroll
             for (int c = 0; c < 64; ++c) sc[c] = (key0 + c < p.HW) ? sc[c] : -INFINITY;
@@ -519,8 +513,8 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           float m_new = m_prev;
           if (__any_sync(0xffffffffu, need)) {
             if (jj > j_first) {
-              const int jp = jj - 1, gp = jp >> 1, bp = (gp & 1) * 2 + (jp & 1);
-              mbar_wait_b(&sp_free[bp], (gp >> 1) & 1);        // P.V(<= jj-1) retired
+              const int jp = jj - 1;
+              mbar_wait_b(&sp_free[jp & 3], (jp >> 2) & 1);    // P.V(<= jj-1) retired
               fence_after();
               const float f = need ? exp2f(m_prev - mt) : 1.f;
 #pragma unroll 1
@@ -588,11 +582,8 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (la > 0.f) l_row += la * exp2f(lx[(a * BM + row) * 2] - M);
       }
       const float inv = l_row > 0.f ? 1.f / l_row : 0.f;    // a seed far above this segment's scores can leave l = 0
-      {
-        const int gl = j_last >> 1, bl = (gl & 1) * 2 + 1;
-        mbar_wait_b(&sp_free[bl], (gl >> 1) & 1);
-        fence_after();
-      }
+      mbar_wait_b(&sp_free[j_last & 3], (j_last >> 2) & 1);
+      fence_after();
       // part_o: [slot][16-column group][row][16] -- the 32 rows of a warp are contiguous per group, so every store
       // instruction covers whole lines.  32-column chunks 0-2 / 3-5 / 6-7 go to softmax groups 0 / 1 / 2.
       t16* po = p.part_o + (((long long)(cta * 2 + s) * (DVC / 16)) * BM + row) * 16;
@@ -739,7 +730,7 @@ __global__ void __launch_bounds__(256) combine3_kernel(const Tc3Params p, const 
   }
   if (mass && live && tc < p.T) {
     const int t = tc;
-    const int f_lo = t * p.gpf, f_hi = f_lo + p.gpf;
+    const int f_lo = t * p.tpf, f_hi = f_lo + p.tpf;
     const float M = s_M0[rr], invL = s_L0[rr] > 0.f ? 1.f / s_L0[rr] : 0.f;
     float a = 0.f;
     for (int e = 0; e < s_n[rr][0]; ++e) {
@@ -813,10 +804,11 @@ int sm_count3() {
   return n;
 }
 
-// Static schedule in groups of 128 keys (see attn_tc2.cu make_bounds): equalise groups + kSegCost * segments
-// (+ kRestartCost for a second segment) over the clusters.  A segment epilogue (TMEM read-out of O at 64 B/clk) costs
-// about three group-times.
-constexpr int kSegCost = 3, kRestartCost = 1;
+// Static schedule in 64-key sub-tiles (see attn_tc2.cu make_bounds): equalise sub-tiles + kSegCost * segments over the
+// clusters.  Measured on the per-CTA wall times of profiles/r02_attn3_trace_3groups.txt: a cluster with 40 groups and
+// two segments ends 4 us BEFORE one with 43 groups and one segment, i.e. a segment epilogue is nearly free here (three
+// softmax groups share the TMEM read-out and the score MMAs of the next segment run meanwhile): two sub-tiles.
+constexpr int kSegCost = 2, kRestartCost = 0;
 bool greedy_bounds(long long L, int TPU, int n, long long budget, int m, int* b) {
   long long pos = 0;
   for (int c = 0; c < n; ++c) {
@@ -840,7 +832,7 @@ bool greedy_bounds(long long L, int TPU, int n, long long budget, int m, int* b)
 }
 void make_bounds(long long L, int TPU, int n, int* b) {
   const long long uni = (L + n - 1) / n;
-  if (uni < 8) {                                         // short launches keep the uniform cut
+  if (uni < 16) {                                        // short launches keep the uniform cut
     for (int c = 0; c <= n; ++c) b[c] = (int)((L * c) / n);
     return;
   }
@@ -857,20 +849,20 @@ void make_bounds(long long L, int TPU, int n, int* b) {
   greedy_bounds(L, TPU, n, lo, mlo, b);
 }
 
-void schedule3(int HW, int T, int Dv, int* n_units, int* gpf, int* TPU, int* nCL) {
+void schedule3(int HW, int T, int Dv, int* n_units, int* tpf, int* TPU, int* nCL) {
   const int qpairs = cdiv(cdiv(HW, BM), 2), n_dv = Dv / DVC;
   *n_units = qpairs * n_dv;
-  *gpf = cdiv(HW, BNG);
-  *TPU = T * *gpf;
+  *tpf = cdiv(HW, BNS);
+  *TPU = T * *tpf;
   const long long L = (long long)*n_units * *TPU;
   int n = sm_count3() / 2;
   if (n > kMaxCL) n = kMaxCL;
-  if ((long long)n > L / 2) n = (int)(L / 2);                   // at least ~2 groups per cluster
+  if ((long long)n > L / 4) n = (int)(L / 4);                   // at least ~4 sub-tiles per cluster
   const int cap = (kMaxSegsPerUnit - 2) * *n_units;             // combine3 resolves <= kMaxSegsPerUnit segments per unit
   if (n > cap) n = cap;
-  // Short launches (the T = 1 self-attention: ~5 groups per cluster): a segment epilogue costs about three groups, so a
-  // cluster that straddles two units pays more in epilogues than the last SMs are worth -- k whole-segment clusters per unit.
-  if (L / n < 8 && n / *n_units >= 2) n = (n / *n_units) * *n_units;
+  // Short launches (the T = 1 self-attention: ~10 sub-tiles per cluster): a cluster that straddles two units pays a
+  // pipeline restart for a handful of tiles -- k whole-segment clusters per unit instead.
+  if (L / n < 16 && n / *n_units >= 2) n = (n / *n_units) * *n_units;
   if (n < *n_units) n = *n_units;                               // a cluster never spans more than two units
   if ((long long)n > L) n = (int)L;
   if (n < 1) n = 1;
@@ -916,8 +908,8 @@ int long_attn_tc3_set_trace(long long* dev_buf) {
 // Host-only view of the static schedule (tests): step range of every cluster for a launch of this shape.
 int long_attn_tc3_schedule(int HW, int T, int Dv, int* n_units, int* groups_per_unit, int* n_clusters, int* bounds,
                            int cap) {
-  int gpf = 0;
-  schedule3(HW, T, Dv, n_units, &gpf, groups_per_unit, n_clusters);
+  int tpf = 0;
+  schedule3(HW, T, Dv, n_units, &tpf, groups_per_unit, n_clusters);
   RMEM_REQUIRE(*n_clusters + 1 <= cap && *n_clusters <= kMaxCL, "schedule: %d clusters do not fit the caller's table (%d)",
                *n_clusters, cap);
   make_bounds((long long)*n_units * *groups_per_unit, *groups_per_unit, *n_clusters, bounds);
@@ -928,8 +920,8 @@ size_t long_attn_tc3_workspace(int HW, int HWp, int nslots, int Dv) {
   (void)HWp;
   size_t best = 0;
   for (int T = 1; T <= nslots && T <= kMaxBankFrames; ++T) {
-    int n_units, gpf, TPU, nCL;
-    schedule3(HW, T, Dv, &n_units, &gpf, &TPU, &nCL);
+    int n_units, tpf, TPU, nCL;
+    schedule3(HW, T, Dv, &n_units, &tpf, &TPU, &nCL);
     size_t a, b, c;
     const size_t n = part_bytes3(nCL, T, &a, &b, &c, HW);
     if (n > best) best = n;
@@ -940,14 +932,14 @@ size_t long_attn_tc3_workspace(int HW, int HWp, int nslots, int Dv) {
 int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   RMEM_REQUIRE(a.Dk == DK, "long_attn_tc3: Dk=%d (built for 128)", a.Dk);
   RMEM_REQUIRE(a.Dv % DVC == 0 && a.Dv <= 1024, "long_attn_tc3: Dv=%d must be a multiple of 256, <= 1024", a.Dv);
-  RMEM_REQUIRE(a.HWp % BNG == 0 && a.HWp >= a.HW, "long_attn_tc3: HWp=%d must be a multiple of 128", a.HWp);
+  RMEM_REQUIRE(a.HWp % BNS == 0 && a.HWp >= a.HW, "long_attn_tc3: HWp=%d must be a multiple of 64", a.HWp);
   RMEM_REQUIRE(a.T >= 1 && a.T <= kMaxBankFrames && a.T <= a.nslots, "long_attn_tc3: T=%d nslots=%d", a.T, a.nslots);
   RMEM_REQUIRE(a.ldo % 8 == 0 && (!a.gate || a.ldg % 8 == 0), "long_attn_tc3: ldo/ldg alignment");
   RMEM_REQUIRE(a.seed_h * a.seed_w == a.HW || a.seed_h == 0, "long_attn_tc3: seed grid %dx%d != HW=%d", a.seed_h,
                a.seed_w, a.HW);
   Tc3Params p;
   p.HW = a.HW; p.HWp = a.HWp; p.T = a.T; p.Dv = a.Dv; p.n_dv = a.Dv / DVC;
-  schedule3(a.HW, a.T, a.Dv, &p.n_units, &p.gpf, &p.TPU, &p.nCL);
+  schedule3(a.HW, a.T, a.Dv, &p.n_units, &p.tpf, &p.TPU, &p.nCL);
   RMEM_REQUIRE(p.nCL <= kMaxCL, "long_attn_tc3: %d clusters > %d", p.nCL, kMaxCL);
   make_bounds((long long)p.n_units * p.TPU, p.TPU, p.nCL, p.bounds);
   size_t off_ml, off_pieces, off_seed;

@@ -208,6 +208,31 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         return smp["meta"], im, (lb.float() if lb is not None else None)
 
     can_prefetch = use_cuda and hasattr(engine, "prefetch")
+    fast = use_cuda and hasattr(engine, "propagate_label")
+    ring: List = [None] * 4                # (copy event, pinned label buffer, frame index, meta) of the frames in flight
+    ring_bufs: List = [None] * 4
+
+    def emit(frame_idx, meta, lab8):
+        if on_frame is not None:
+            on_frame(frame_idx, lab8)
+        if keep_labels:
+            res.labels.append(lab8.clone())
+        if out_dir is not None:
+            path = os.path.join(out_dir, dataset.seq_name, os.path.splitext(meta["current_name"])[0] + ".png")
+            writers.append(save_mask(lab8.numpy().copy(), path, meta["obj_idx"]))
+            res.paths.append(path)
+
+    def drain(entry):
+        done, buf, fi, mt = entry
+        done.synchronize()
+        emit(fi, mt, buf)
+
+    def flush_ring():
+        for e in sorted((e for e in ring if e is not None), key=lambda e: e[2]):
+            drain(e)
+        for k in range(len(ring)):
+            ring[k] = None
+
     nxt = fetch(0)
     for frame_idx in range(len(dataset)):
         meta, img, label = nxt
@@ -230,6 +255,28 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         else:
             t0 = now()
         out_size = (int(meta["height"]), int(meta["width"]))
+        if fast and label is None:
+            # CUDA engine, ordinary frame: the mask-ID assignment (softmax -> argmax, evaluator.py:430-441) is fused into the
+            # engine's mask head; only the uint8 label map leaves the GPU, through a ring of pinned buffers and without a
+            # per-frame synchronisation (consumers see a frame once its copy event has completed)
+            lab_dev = engine.propagate_label(img, output_size=out_size)
+            cur = lab_dev if out_size == tuple(engine.input_size_2d) else \
+                F.interpolate(lab_dev.float(), size=engine.input_size_2d, mode="nearest")
+            engine.update_memory(cur)
+            ev1.record()
+            timers.append((ev0, ev1))
+            res.frames += 1
+            slot = res.frames % len(ring)
+            if ring[slot] is not None:
+                drain(ring[slot])
+            buf = ring_bufs[slot] if ring_bufs[slot] is not None and ring_bufs[slot].shape == lab_dev.shape[2:] else \
+                torch.empty(lab_dev.shape[2:], dtype=torch.uint8).pin_memory()
+            ring_bufs[slot] = buf
+            buf.copy_(lab_dev[0, 0], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            ring[slot] = (done, buf, frame_idx, meta)
+            continue
         logit = engine.match_propogate_one_frame(img, output_size=out_size)
         prob = torch.softmax(logit, dim=1)
         pred = torch.argmax(prob, dim=1, keepdim=True).float()
@@ -248,15 +295,9 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         else:
             res.seconds += now() - t0
         res.frames += 1
-        lab8 = pred[0, 0].to(torch.uint8).cpu()
-        if on_frame is not None:
-            on_frame(frame_idx, lab8)
-        if keep_labels:
-            res.labels.append(lab8)
-        if out_dir is not None:
-            path = os.path.join(out_dir, dataset.seq_name, os.path.splitext(meta["current_name"])[0] + ".png")
-            writers.append(save_mask(lab8.numpy(), path, meta["obj_idx"]))
-            res.paths.append(path)
+        flush_ring()                                         # keep the output order: frames still in flight first
+        emit(frame_idx, meta, pred[0, 0].to(torch.uint8).cpu())
+    flush_ring()
     if timers:
         torch.cuda.synchronize()
         res.seconds += sum(a.elapsed_time(b) for a, b in timers) / 1e3
