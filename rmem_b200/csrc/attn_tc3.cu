@@ -119,9 +119,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, nullptr, 0); }
 __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity, nullptr, 0); }
 
-// Tried and dropped (profiles/r02_attn3_experiments.txt): a polynomial 2^x on the FMA pipe for a quarter / half of the
-// exponentials (slower: 76-78 vs 73.7 us -- the added issue slots and registers cost more than the MUFU cycles saved), and
-// ex2.approx.f16x2 (two exponentials per MUFU instruction on fp16-rounded exponents: 86 us and 1.6x the error).
+// Tried and dropped (profiles/r02_attn3_experiments.txt): a polynomial 2^x on the FMA pipe for 1/8 .. 1/2 of the
+// exponentials (slower in every version of this kernel: the added issue slots and registers cost more than the MUFU
+// cycles saved), and ex2.approx.f16x2 (two exponentials per MUFU instruction on fp16-rounded exponents: 86 us and 1.6x
+// the error).
 // TMA tile into THIS CTA's shared memory, transaction bytes counted on the LEADER CTA's barrier (peer bit cleared)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -281,7 +282,9 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   cluster_sync_all();           // the peer's barriers are initialised and both TMEM allocations are done
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (cta_times && threadIdx.x == 0) cta_times[7] = clock64();     // set-up done (barriers, TMEM, cluster sync)
   pdl_prologue();   // barriers, TMEM and descriptors are set up; global memory is touched only from here on
+  if (cta_times && threadIdx.x == 0) cta_times[8] = clock64();     // previous kernel complete
 
   if (warp >= kSoftmaxWarps) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
@@ -393,6 +396,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_wait_cl(&p_full[b], (j >> 2) & 1);
         fence_after();
         TRACE3(j, 0);
+        if (cta_times && lane == 0) { if (j == 0) cta_times[9] = clock64(); if (j == ntot - 1) cta_times[10] = clock64(); }
         if (elect_one()) {
           const uint64_t dv = make_desc_sw128(smem_base + OFF_V + sv * SMEM_V);
           const uint32_t pa = tmem + TMEM_P + b * 32;
@@ -611,6 +615,7 @@ long_attn_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       fence_before();
       __syncwarp();
+      if (cta_times && warp == 0 && lane == 0) cta_times[11 + s] = clock64();   // segment epilogue written
       if (lane == 0 && s + 1 < nseg) mbar_arrive_leader(o_drained);
       // the exchange area is reused by the next segment: every group must have read it before anyone writes again
       if (s + 1 < nseg) named_bar_sync(id_ex, kSoftmaxWarps * 32);

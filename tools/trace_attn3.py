@@ -39,6 +39,11 @@ ct = t[600:748]
 g0 = int(ct[:, 0][ct[:, 0] > 0].min())
 rows = [(c, int(ct[c, 0]) - g0, int(ct[c, 1]) - g0, int(ct[c, 2]), int(ct[c, 3]), int(ct[c, 4]), int(ct[c, 6] - ct[c, 5]))
         for c in range(148) if int(ct[c, 0]) > 0]
+print("phase split of even (leader) CTAs, cycles from kernel entry: cta setup_done prev_kernel_done first_PV last_PV epi0 epi1 end")
+for c in list(range(0, 12, 2)) + list(range(60, 72, 2)):
+    if int(ct[c, 0]) > 0:
+        b = int(ct[c, 5])
+        print("  ", c, *[(int(ct[c, k]) - b if int(ct[c, k]) > 0 else "-") for k in (7, 8, 9, 10, 11, 12, 6)])
 print("per-CTA wall time (ns from first start): cta start end groups segs smid cycles")
 for r in rows[:6] + sorted(rows, key=lambda r: -r[2])[:10]:
     print("  ", r)
