@@ -153,6 +153,19 @@ int rmem_idbank_fwd(const uint8_t* label, int H, int W, int use_ignore, const fl
 int rmem_mask_head_fwd(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits,
                        uint8_t* out_label, void* stream);
 
+/* Test-time augmentation (networks/managers/evaluator.py:338-441): every augmentation (scale x flip) runs its own engine;
+ * per output pixel each one's 1/4-res logits are upsampled (bilinear, align_corners), soft-aggregated over its k object
+ * groups, soft-maxed, mirrored back when that augmentation was flipped (flip_tensor(pred_logit, 3)), the probabilities
+ * are averaged over the augmentations and the argmax is taken.  logits4: HOST array [n_aug * k] of device pointers
+ * (augmentation major), each planar [11, h4[a], w4[a]]; h4 / w4 / flip: HOST [n_aug].  out_prob [1+10k, Ho, Wo] nullable. */
+int rmem_tta_head_fwd(const float* const* logits4, int n_aug, int k, const int* h4, const int* w4, const int* flip,
+                      int Ho, int Wo, float* out_prob, uint8_t* out_label, void* stream);
+/* Loader-side preprocessing on the GPU: MultiRestrictSize + MultiToTensor (dataloaders/video_transforms.py:559-682).
+ * img: device uint8 [H, W, 3] as decoded (bgr != 0: cv2.imread order, swapped to RGB); out: fp32 [3, nh, nw] =
+ * ((resize(img) / 255) - mean) / std with OpenCV's INTER_CUBIC rule (a = -0.75, half-pixel centres, clamped taps; no
+ * resize when nh x nw == H x W), mirrored horizontally when flip != 0. */
+int rmem_preprocess_fwd(const uint8_t* img, int H, int W, int bgr, int nh, int nw, int flip, float* out, void* stream);
+
 /* Relevance term of the evict score: fg-prob from the low-res logits (aot_engine.py:355-362) times the layer-0
  * attention mass, summed over tokens (transformer.py:891-906).  rel[T] un-normalised. */
 int rmem_evict_relevance_fwd(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w,

@@ -251,6 +251,21 @@ int rmem_mask_head_fwd(const float* const* logits4, int k, int h4, int w4, int H
   RMEM_API_END
 }
 
+int rmem_tta_head_fwd(const float* const* logits4, int n_aug, int k, const int* h4, const int* w4, const int* flip,
+                      int Ho, int Wo, float* out_prob, uint8_t* out_label, void* stream) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(logits4 && h4 && w4 && flip && (out_prob || out_label), "null argument");
+  return tta_head(logits4, n_aug, k, h4, w4, flip, Ho, Wo, out_prob, out_label, STREAM(stream));
+  RMEM_API_END
+}
+
+int rmem_preprocess_fwd(const uint8_t* img, int H, int W, int bgr, int nh, int nw, int flip, float* out, void* stream) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(img && out, "null argument");
+  return preprocess_frame(img, H, W, bgr, nh, nw, flip, out, STREAM(stream));
+  RMEM_API_END
+}
+
 int rmem_evict_relevance_fwd(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel,
                              void* stream) {
   RMEM_API_BEGIN

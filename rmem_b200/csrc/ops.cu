@@ -714,6 +714,128 @@ __global__ void mask_head_kernel(LogitPtrs lp, int k, int h4, int w4, int Ho, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Test-time augmentation head (evaluator.py:338-441): every augmentation a (scale x flip) has its own engine and its
+// own 1/4-res logits; per output pixel each one is upsampled (bilinear, align_corners), soft-aggregated over its k object
+// groups, soft-maxed, mirrored back if the augmentation was flipped, and the PROBABILITIES are averaged before the argmax.
+struct TtaPtrs { const float* p[8][4]; int h4[8], w4[8], flip[8]; };
+__global__ void tta_head_kernel(TtaPtrs tp, int n_aug, int k, int Ho, int Wo, float* __restrict__ out_prob,
+                                uint8_t* __restrict__ out_label) {
+  pdl_prologue();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ho * Wo) return;
+  const int oy = i / Wo, ox = i - oy * Wo;
+  const int nc = 1 + 10 * k;
+  float mean[41];
+  for (int c = 0; c < nc; ++c) mean[c] = 0.f;
+  for (int a = 0; a < n_aug; ++a) {
+    const int h4 = tp.h4[a], w4 = tp.w4[a];
+    const int sx = tp.flip[a] ? (Wo - 1 - ox) : ox;        // flip_tensor(pred_logit, 3) on the full-size logits
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    src_index(oy, h4, Ho, y0, y1, wy0, wy1);
+    src_index(sx, w4, Wo, x0, x1, wx0, wx1);
+    const size_t plane = (size_t)h4 * w4;
+    const size_t i00 = (size_t)y0 * w4 + x0, i01 = (size_t)y0 * w4 + x1, i10 = (size_t)y1 * w4 + x0,
+                 i11 = (size_t)y1 * w4 + x1;
+    float merged[41];
+    if (k == 1) {
+      float lg[11];
+#pragma unroll
+      for (int c = 0; c < 11; ++c) {
+        const float* pl = tp.p[a][0] + c * plane;
+        lg[c] = bilerp(pl[i00], pl[i01], pl[i10], pl[i11], wy0, wy1, wx0, wx1);
+      }
+      softmax11(lg, merged);
+    } else {
+      float bg = 1.f;
+      for (int e = 0; e < k; ++e) {
+        float lg[11], p[11];
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {
+          const float* pl = tp.p[a][e] + c * plane;
+          lg[c] = bilerp(pl[i00], pl[i01], pl[i10], pl[i11], wy0, wy1, wx0, wx1);
+        }
+        softmax11(lg, p);
+        bg = (e == 0) ? p[0] : __fmul_rn(bg, p[0]);
+        for (int c = 1; c < 11; ++c) merged[1 + e * 10 + (c - 1)] = p[c];
+      }
+      merged[0] = bg;
+      float mx = -INFINITY;
+      for (int c = 0; c < nc; ++c) {
+        float m = fminf(fmaxf(merged[c], 1e-5f), 1.f - 1e-5f);
+        merged[c] = logf(__fdiv_rn(m, __fsub_rn(1.f, m)));
+        mx = fmaxf(mx, merged[c]);
+      }
+      float s = 0.f;
+      for (int c = 0; c < nc; ++c) { merged[c] = expf(__fsub_rn(merged[c], mx)); s = __fadd_rn(s, merged[c]); }
+      for (int c = 0; c < nc; ++c) merged[c] = __fdiv_rn(merged[c], s);
+    }
+    for (int c = 0; c < nc; ++c) mean[c] = __fadd_rn(mean[c], merged[c]);
+  }
+  const float inv = __fdiv_rn(1.f, (float)n_aug);
+  int best = 0;
+  float bp = -1.f;
+  for (int c = 0; c < nc; ++c) {
+    const float p = __fmul_rn(mean[c], inv);
+    if (out_prob) out_prob[(size_t)c * Ho * Wo + i] = p;
+    if (p > bp) { bp = p; best = c; }
+  }
+  if (out_label) out_label[i] = (uint8_t)best;
+}
+
+// Frame preprocessing of the evaluation loader on the GPU (MultiRestrictSize + MultiToTensor,
+// dataloaders/video_transforms.py:559-682): uint8 HWC frame -> fp32 NCHW at the network size, cubic resize with
+// OpenCV's INTER_CUBIC rule (a = -0.75, half-pixel centres, no antialiasing, taps clamped to the image), optional
+// horizontal flip, x / 255, ImageNet mean / std.  `bgr`: the frame is in cv2.imread order and the network wants RGB.
+__device__ __forceinline__ void cubic_w(float t, float* w) {
+  const float A = -0.75f;
+  w[0] = ((A * (t + 1.f) - 5.f * A) * (t + 1.f) + 8.f * A) * (t + 1.f) - 4.f * A;
+  w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  w[2] = ((A + 2.f) * (1.f - t) - (A + 3.f)) * (1.f - t) * (1.f - t) + 1.f;
+  w[3] = 1.f - w[0] - w[1] - w[2];
+}
+__global__ void preprocess_kernel(const uint8_t* __restrict__ img, int H, int W, int bgr, int nh, int nw, int flip,
+                                  float* __restrict__ out) {
+  pdl_prologue();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh * nw) return;
+  const int oy = i / nw, ox0 = i - oy * nw;
+  const int ox = flip ? (nw - 1 - ox0) : ox0;                // tmp[:, ::-1] after the resize
+  float v[3];
+  if (nh == H && nw == W) {
+    const uint8_t* p = img + ((size_t)oy * W + ox) * 3;
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+  } else {
+    const float fy = ((float)oy + 0.5f) * ((float)H / (float)nh) - 0.5f;
+    const float fx = ((float)ox + 0.5f) * ((float)W / (float)nw) - 0.5f;
+    const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+    float wy[4], wx[4];
+    cubic_w(fy - (float)iy, wy);
+    cubic_w(fx - (float)ix, wx);
+    v[0] = v[1] = v[2] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), H - 1);
+      float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), W - 1);
+        const uint8_t* p = img + ((size_t)yy * W + xx) * 3;
+        r[0] += wx[b] * (float)p[0]; r[1] += wx[b] * (float)p[1]; r[2] += wx[b] * (float)p[2];
+      }
+      v[0] += wy[a] * r[0]; v[1] += wy[a] * r[1]; v[2] += wy[a] * r[2];
+    }
+  }
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+  const size_t plane = (size_t)nh * nw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float x = v[bgr ? 2 - c : c];
+    out[c * plane + (size_t)oy * nw + ox0] = (x / 255.f - mean[c]) / sd[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void evict_rel_kernel(const float* __restrict__ mass, int T, const float* __restrict__ logits4, int h4,
                                  int w4, int h, int w, float* __restrict__ rel) {
   pdl_prologue();
@@ -1018,6 +1140,26 @@ int mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo
   LogitPtrs lp;
   for (int e = 0; e < 4; ++e) lp.p[e] = e < k ? logits4[e] : nullptr;
   RMEM_CUDA_CHECK(launch_pdl(mask_head_kernel, dim3(cdiv(Ho * Wo, 128)), dim3(128), 0, s, lp, k, h4, w4, Ho, Wo, out_logits, out_label));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int tta_head(const float* const* logits4, int n_aug, int k, const int* h4, const int* w4, const int* flip, int Ho, int Wo,
+             float* out_prob, uint8_t* out_label, cudaStream_t s) {
+  RMEM_REQUIRE(n_aug >= 1 && n_aug <= 8 && k >= 1 && k <= 4, "tta_head: %d augmentations x %d object groups (max 8 x 4)", n_aug, k);
+  TtaPtrs tp;
+  for (int a = 0; a < 8; ++a) {
+    tp.h4[a] = a < n_aug ? h4[a] : 0; tp.w4[a] = a < n_aug ? w4[a] : 0; tp.flip[a] = a < n_aug ? flip[a] : 0;
+    for (int e = 0; e < 4; ++e) tp.p[a][e] = (a < n_aug && e < k) ? logits4[a * k + e] : nullptr;
+  }
+  RMEM_CUDA_CHECK(launch_pdl(tta_head_kernel, dim3(cdiv(Ho * Wo, 128)), dim3(128), 0, s, tp, n_aug, k, Ho, Wo, out_prob, out_label));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int preprocess_frame(const uint8_t* img, int H, int W, int bgr, int nh, int nw, int flip, float* out, cudaStream_t s) {
+  RMEM_REQUIRE(H > 0 && W > 0 && nh > 0 && nw > 0, "preprocess: empty frame");
+  RMEM_CUDA_CHECK(launch_pdl(preprocess_kernel, dim3(cdiv(nh * nw, 256)), dim3(256), 0, s, img, H, W, bgr, nh, nw, flip, out));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -74,6 +74,12 @@ int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float
 // bilinear(align_corners=True) -> soft aggregation -> out_logits [1+10k, Ho, Wo] (optional) and uint8 label.
 int mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits,
               uint8_t* out_label, cudaStream_t s);
+// Test-time-augmentation head: mean over augmentations of the soft-maxed, (un)flipped, upsampled logits -> argmax.
+// logits4: HOST array [n_aug * k] of device pointers (augmentation major), h4 / w4 / flip: HOST [n_aug].
+int tta_head(const float* const* logits4, int n_aug, int k, const int* h4, const int* w4, const int* flip, int Ho, int Wo,
+             float* out_prob, uint8_t* out_label, cudaStream_t s);
+// uint8 HWC frame -> normalised fp32 NCHW at nh x nw (OpenCV INTER_CUBIC rule), optional horizontal flip.
+int preprocess_frame(const uint8_t* img, int H, int W, int bgr, int nh, int nw, int flip, float* out, cudaStream_t s);
 
 // Relevance part of the evict score (aot_engine.py:355-362, transformer.py:891-906):
 //   fg = 1 - softmax(bilinear(logits4 -> h x w))[0];  rel[t] = sum_i mass[i,t] * fg[i]   (un-normalised)

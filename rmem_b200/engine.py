@@ -247,6 +247,27 @@ class DeAOTInferEngine:
                                               _capi.stream_ptr()))
         return label
 
+    def propagate_only(self, img: torch.Tensor):
+        """Run the propagation of one frame and leave the 1/4-res logits of every object group in the engine
+        (`logits4_views`): the test-time-augmentation head merges several engines' logits itself."""
+        lib = _capi.load()
+        _capi.check(lib.rmem_engine_set_gap(self._h, max(int(self.long_term_mem_gap), 1)))
+        img = self._dev(img, torch.float32)
+        _capi.check(lib.rmem_engine_propagate(self._h, _capi.ptr(img), 0, 0, None, None, _capi.stream_ptr()))
+
+    def logits4_views(self) -> List[torch.Tensor]:
+        """Views (no copy) of the fp32 [11,H/4,W/4] logits of the last decode, one per object group."""
+        lib = _capi.load()
+        out = []
+        for i in range(len(self.aot_engines)):
+            p = C.c_void_p()
+            h4, w4 = C.c_int(), C.c_int()
+            _capi.check(lib.rmem_engine_pred_logits(self._h, i, C.byref(p), C.byref(h4), C.byref(w4)))
+            n = 11 * h4.value * w4.value
+            off = p.value - self._arena.data_ptr()
+            out.append(self._arena[off:off + 4 * n].view(torch.float32).view(11, h4.value, w4.value))
+        return out
+
     def prefetch(self, img: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
         """Encode the NEXT frame on the engine's side stream while the current one is propagated (the image encoder,
         aot.py:116-134, does not depend on the memory bank).  `img` must be a contiguous fp32 CUDA tensor that is ready

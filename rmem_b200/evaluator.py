@@ -13,7 +13,9 @@ Host-side mirror of the reference's production caller:
 The engine is anything with the reference's method surface (`restart_engine`, `add_reference_frame`,
 `match_propogate_one_frame`, `update_memory`, `long_term_mem_gap`, `input_size_2d`): the CUDA engine of
 rmem_b200.engine in production, the CPU oracle in the host-logic tests.  Test-time augmentation (flip / multi-scale
-engines, evaluator.py:338-352) is not part of the measured path and is rejected loudly rather than silently ignored.
+engines with probability averaging, evaluator.py:338-441) is `evaluate_clip_tta`: one engine per augmentation, the
+frames resized / normalised / flipped on the GPU (rmem_preprocess_fwd) and the per-augmentation logits merged by the
+fused TTA head (rmem_tta_head_fwd) when the engines are CUDA engines.
 """
 from __future__ import annotations
 
@@ -122,6 +124,14 @@ class ClipDataset:
                 lut[obj_id] = pos
         return lut[self._read_png(name)]
 
+    def read_image_u8(self, idx: int) -> np.ndarray:
+        """The frame as decoded (uint8, cv2.imread channel order): input of the GPU preprocessing."""
+        import cv2
+        img = cv2.imread(os.path.join(self.image_dir, self.images[idx]))
+        if img is None:
+            raise FileNotFoundError(os.path.join(self.image_dir, self.images[idx]))
+        return img
+
     def read_image(self, idx: int) -> np.ndarray:
         import cv2
         img = cv2.imread(os.path.join(self.image_dir, self.images[idx]))
@@ -129,6 +139,23 @@ class ClipDataset:
             raise FileNotFoundError(os.path.join(self.image_dir, self.images[idx]))
         img = np.array(img, dtype=np.float32)
         return img[:, :, [2, 1, 0]] if self.rgb else img
+
+    def sample_meta(self, idx: int) -> Dict:
+        """`meta` and `current_label` of __getitem__ without the frame itself (the GPU preprocessing reads it raw)."""
+        from PIL import Image
+        with Image.open(os.path.join(self.image_dir, self.images[idx])) as im:      # header only
+            width, height = im.size
+        if self.resolution is not None:
+            width = int(np.ceil(float(width) * self.resolution / float(height)))
+            height = int(self.resolution)
+        sample: Dict = {}
+        lab = os.path.splitext(self.images[idx])[0] + ".png"
+        if lab in self.labels:
+            sample["current_label"] = torch.from_numpy(self.read_label(lab, self.obj_indices[idx])).int()[None, None]
+        sample["meta"] = {"seq_name": self.seq_name, "frame_num": len(self.images), "obj_num": self.obj_nums[idx],
+                          "current_name": self.images[idx], "height": height, "width": width, "flip": False,
+                          "obj_idx": self.obj_indices[idx]}
+        return sample
 
     def __getitem__(self, idx: int) -> Dict:
         img = self.read_image(idx)
@@ -301,6 +328,141 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
     if timers:
         torch.cuda.synchronize()
         res.seconds += sum(a.elapsed_time(b) for a, b in timers) / 1e3
+    for t in writers:
+        if t is not None:
+            t.join()
+    return res
+
+
+def tta_augmentations(flip: bool, multi_scale: Sequence[float]) -> List[Tuple[float, bool]]:
+    """(scale, flipped) in the order MultiRestrictSize emits its samples (video_transforms.py:575-650)."""
+    out: List[Tuple[float, bool]] = []
+    for sc in multi_scale:
+        out.append((float(sc), False))
+        if flip:
+            out.append((float(sc), True))
+    return out
+
+
+def evaluate_clip_tta(engines: Sequence, dataset: ClipDataset, flip: bool = True, multi_scale: Sequence[float] = (1.0,),
+                      out_dir: Optional[str] = None, device=None, keep_labels: bool = False,
+                      gpu_preprocess: Optional[bool] = None, no_memory_gap: bool = False) -> ClipResult:
+    """evaluator.py:300-556 with test-time augmentation: `engines[a]` serves augmentation a of `tta_augmentations`
+    (the reference deep-copies the model per augmentation, :342-352; engines built on one RmemModel share the weight
+    blob).  Per frame every engine propagates its own resized / flipped view, the soft-maxed logits are flipped back
+    and averaged (:426-441), the argmax label (flipped again where needed) refreshes every engine's memory (:484-522)."""
+    augs = tta_augmentations(flip, multi_scale)
+    if len(engines) != len(augs):
+        raise ValueError(f"{len(augs)} augmentations need {len(augs)} engines, got {len(engines)}")
+    res = ClipResult(dataset.seq_name)
+    gap = long_term_gap(len(dataset), no_memory_gap)
+    for e in engines:
+        e.restart_engine()
+        e.long_term_mem_gap = gap
+    use_cuda = device is not None and torch.device(device).type == "cuda"
+    cuda_engines = use_cuda and all(hasattr(e, "propagate_only") for e in engines)
+    if gpu_preprocess is None:
+        gpu_preprocess = cuda_engines
+    if out_dir is not None:
+        os.makedirs(os.path.join(out_dir, dataset.seq_name), exist_ok=True)
+    writers = []
+    t_sum = 0.0
+    timers = []
+
+    def views(idx):
+        """[(img fp32 [1,3,nh,nw] on `device`, flipped)] for every augmentation + (meta, label)."""
+        meta_smp = dataset[idx] if not gpu_preprocess else None
+        out = []
+        if gpu_preprocess:
+            from . import ops as K
+            raw = torch.from_numpy(dataset.read_image_u8(idx)).to(device, non_blocking=True)
+            H0, W0 = raw.shape[:2]
+            for sc, fl in augs:
+                nh, nw = restrict_size(H0, W0, dataset.min_size, dataset.max_size, scale=sc)
+                out.append((K.preprocess(raw, nh, nw, bgr=dataset.rgb, flip=fl), fl))
+            smp = dataset.sample_meta(idx)
+        else:
+            import cv2
+            base = dataset.read_image(idx)
+            H0, W0 = base.shape[:2]
+            for sc, fl in augs:
+                nh, nw = restrict_size(H0, W0, dataset.min_size, dataset.max_size, scale=sc)
+                im = base if (nh, nw) == (H0, W0) else cv2.resize(base, dsize=(nw, nh), interpolation=cv2.INTER_CUBIC)
+                if fl:
+                    im = im[:, ::-1]
+                im = (im / 255. - IMAGENET_MEAN) / IMAGENET_STD
+                t = torch.from_numpy(np.ascontiguousarray(im.transpose(2, 0, 1))).float()[None]
+                out.append((t.to(device) if device is not None else t, fl))
+            smp = {"meta": meta_smp["meta"], "current_label": meta_smp.get("current_label")}
+        lab = smp.get("current_label")
+        if lab is not None:
+            lab = lab.float()
+            if device is not None:
+                lab = lab.to(device)
+        return smp["meta"], out, lab
+
+    def to_engine(label, eng, fl):
+        """Label map [1,1,Ho,Wo] -> the engine's input size, mirrored for a flipped augmentation."""
+        if fl:
+            label = torch.flip(label, dims=(3,))
+        return F.interpolate(label.float(), size=eng.input_size_2d, mode="nearest")
+
+    for frame_idx in range(len(dataset)):
+        meta, imgs, label = views(frame_idx)
+        out_size = (int(meta["height"]), int(meta["width"]))
+        if frame_idx == 0:
+            if label is None:
+                raise ValueError(f"{dataset.seq_name}: the first frame has no label")
+            for (img, fl), eng in zip(imgs, engines):
+                lab = torch.flip(label, dims=(3,)) if fl else label
+                ref = F.interpolate(lab, size=img.shape[2:], mode="nearest").int()
+                eng.add_reference_frame(img, ref, obj_nums=[int(meta["obj_num"])], frame_step=0)
+            continue
+        if use_cuda:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        else:
+            t0 = time.perf_counter()
+        if cuda_engines:
+            from . import ops as K
+            for (img, fl), eng in zip(imgs, engines):
+                eng.propagate_only(img)
+            _, lab8 = K.tta_head([eng.logits4_views() for eng in engines], [fl for _, fl in imgs], *out_size)
+            pred = lab8.float()[None, None]
+        else:
+            probs = []
+            for (img, fl), eng in zip(imgs, engines):
+                lg = eng.match_propogate_one_frame(img, output_size=out_size)
+                if fl:
+                    lg = torch.flip(lg, dims=(3,))
+                probs.append(torch.softmax(lg, dim=1))
+            pred = torch.argmax(torch.mean(torch.cat(probs, dim=0), dim=0, keepdim=True), dim=1, keepdim=True).float()
+        if label is not None:              # a frame that introduces objects: paste them in and re-reference every engine
+            keep = (label == 0).float()
+            pred = pred * keep + label * (1 - keep)
+            new_obj_nums = [int(pred.max().item())]
+            for (img, fl), eng in zip(imgs, engines):
+                eng.add_reference_frame(img, to_engine(pred, eng, fl), obj_nums=new_obj_nums, frame_step=frame_idx)
+        else:
+            for (img, fl), eng in zip(imgs, engines):
+                eng.update_memory(to_engine(pred, eng, fl))
+        if use_cuda:
+            ev1.record()
+            timers.append((ev0, ev1))
+        else:
+            t_sum += time.perf_counter() - t0
+        res.frames += 1
+        lab_host = pred[0, 0].to(torch.uint8).cpu()
+        if keep_labels:
+            res.labels.append(lab_host)
+        if out_dir is not None:
+            path = os.path.join(out_dir, dataset.seq_name, os.path.splitext(meta["current_name"])[0] + ".png")
+            writers.append(save_mask(lab_host.numpy(), path, meta["obj_idx"]))
+            res.paths.append(path)
+    if timers:
+        torch.cuda.synchronize()
+        t_sum += sum(a.elapsed_time(b) for a, b in timers) / 1e3
+    res.seconds = t_sum
     for t in writers:
         if t is not None:
             t.join()

@@ -191,6 +191,34 @@ def mask_head(logits4: Sequence[torch.Tensor], Ho: int, Wo: int, want_logits: bo
     return out, lab
 
 
+def tta_head(logits4: Sequence[Sequence[torch.Tensor]], flips: Sequence[bool], Ho: int, Wo: int, want_prob: bool = False):
+    """Test-time-augmentation head.  logits4[a][e]: fp32 [11,h4_a,w4_a] of augmentation a, object group e.
+    Returns (prob fp32 [1+10k,Ho,Wo] | None, label uint8 [Ho,Wo])."""
+    lib = _capi.load()
+    n_aug, k = len(logits4), len(logits4[0])
+    flat = [t for per in logits4 for t in per]
+    ptrs = (C.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+    h4 = (C.c_int * n_aug)(*[int(per[0].shape[-2]) for per in logits4])
+    w4 = (C.c_int * n_aug)(*[int(per[0].shape[-1]) for per in logits4])
+    fl = (C.c_int * n_aug)(*[int(bool(f)) for f in flips])
+    dev = flat[0].device
+    prob = torch.empty(1 + 10 * k, Ho, Wo, dtype=torch.float32, device=dev) if want_prob else None
+    lab = torch.empty(Ho, Wo, dtype=torch.uint8, device=dev)
+    _capi.check(lib.rmem_tta_head_fwd(ptrs, n_aug, k, h4, w4, fl, Ho, Wo, _capi.ptr(prob), _capi.ptr(lab),
+                                      _capi.stream_ptr()))
+    return prob, lab
+
+
+def preprocess(img_u8: torch.Tensor, nh: int, nw: int, bgr: bool = True, flip: bool = False) -> torch.Tensor:
+    """uint8 [H,W,3] device frame -> normalised fp32 [1,3,nh,nw] (MultiRestrictSize + MultiToTensor on the GPU)."""
+    lib = _capi.load()
+    H, W, _ = img_u8.shape
+    out = torch.empty(1, 3, nh, nw, dtype=torch.float32, device=img_u8.device)
+    _capi.check(lib.rmem_preprocess_fwd(_capi.ptr(img_u8.contiguous()), H, W, int(bgr), nh, nw, int(flip), _capi.ptr(out),
+                                        _capi.stream_ptr()))
+    return out
+
+
 def evict_relevance(mass: torch.Tensor, logits4: torch.Tensor, h: int, w: int) -> torch.Tensor:
     lib = _capi.load()
     T = mass.shape[1]

@@ -186,3 +186,38 @@ def test_evaluator_shell_cuda_engine_vs_oracle_engine(cuda_device, tmp_path):
     assert agree >= 0.97, agree
     out2 = np.array(Image.open(ours.paths[1]))                   # frame 2: dataset ids, new object pasted in
     assert (out2[60:90, 80:120] == 9).all() and set(np.unique(out2)) <= {0, 4, 9}
+
+
+def test_tta_shell_cuda_engines_vs_oracle_engines(cuda_device, tmp_path):
+    """Flip + two-scale test-time augmentation (evaluator.py:338-441) through rmem_b200.evaluator.evaluate_clip_tta: four
+    CUDA engines on one weight blob, frames preprocessed on the GPU, logits merged by the fused TTA head -- against the
+    same shell driving four CPU oracle engines with the cv2 loader.  Free-running; the averaged probabilities make the
+    labels less sensitive to near-ties than the single-engine run."""
+    import cv2
+    from PIL import Image
+    from rmem_b200 import evaluator as E
+    from rmem_b200.engine import RmemModel, RmemConfig, build_engine
+    rng = np.random.RandomState(1)
+    H, W = 97, 129
+    img_dir, lab_dir = tmp_path / "JPEGImages" / "c", tmp_path / "Annotations" / "c"
+    os.makedirs(img_dir), os.makedirs(lab_dir)
+    base = cv2.GaussianBlur(rng.randint(0, 255, (H, W, 3)).astype(np.uint8), (0, 0), 3)
+    for f in range(4):
+        cv2.imwrite(str(img_dir / f"{f:05d}.png"), np.roll(base, 2 * f, axis=1))
+    l0 = np.zeros((H, W), np.uint8); l0[20:60, 20:70] = 4
+    Image.fromarray(l0).save(lab_dir / "00000.png")
+    ds = E.ClipDataset(str(img_dir), str(lab_dir))
+    sd = O.make_state_dict("r50_deaotl", seed=5, sharpen=4.0)
+    model = RmemModel(sd, RmemConfig(model="r50_deaotl", former_mem_len=1, latter_mem_len=2), cuda_device)
+    engines = [build_engine("deaotengine", phase="eval", aot_model=model, gpu_id=0) for _ in range(4)]
+    ours = E.evaluate_clip_tta(engines, ds, flip=True, multi_scale=(1.0, 1.3), device=cuda_device, keep_labels=True)
+    ocfg = O.OracleConfig(model="r50_deaotl", former_mem_len=1, latter_mem_len=2)
+    with torch.no_grad():
+        ref = E.evaluate_clip_tta([O.OracleEngine(sd, ocfg) for _ in range(4)], ds, flip=True, multi_scale=(1.0, 1.3),
+                                  keep_labels=True)
+    assert ours.frames == ref.frames == 3 and ours.seconds > 0
+    assert engines[2].input_size_2d == (129, 161)                 # int(97*1.3) = 126 -> 129, int(129*1.3) = 167 -> 161
+    agree = np.mean([float((a == b).float().mean()) for a, b in zip(ours.labels, ref.labels)])
+    from parity_report import report
+    report("shell/tta_flip_2scales", label_agreement=float(agree), frames=3, vs="same shell with CPU oracle engines + cv2 loader")
+    assert agree >= 0.97, agree

@@ -197,3 +197,26 @@ def test_clip_queue_dynamic_over_gloo_store():
         assert p.exitcode == 0
     allc = sorted(i for _, mine in res for i in mine)
     assert allc == list(range(9))                                # every clip exactly once, drawn from one counter
+
+
+def test_tta_shell_degenerate_equals_plain_and_flip_runs(tmp_path):
+    """evaluate_clip_tta (evaluator.py:338-441) with a single un-flipped, un-scaled augmentation is the plain loop; with
+    flip + two scales it runs one engine per augmentation (MultiRestrictSize order) and merges by probability averaging."""
+    img_dir, lab_dir = write_clip(str(tmp_path), n_frames=4, new_at=2)
+    ds = E.ClipDataset(img_dir, lab_dir)
+    sd = O.make_state_dict("r50_deaotl", seed=1, sharpen=1.0)
+    cfg = O.OracleConfig(model="r50_deaotl", former_mem_len=1, latter_mem_len=2)
+    assert E.tta_augmentations(True, (1.0, 1.3)) == [(1.0, False), (1.0, True), (1.3, False), (1.3, True)]
+    with torch.no_grad():
+        plain = E.evaluate_clip(O.OracleEngine(sd, cfg), ds, keep_labels=True)
+        one = E.evaluate_clip_tta([O.OracleEngine(sd, cfg)], ds, flip=False, multi_scale=(1.0,), keep_labels=True)
+        assert one.frames == plain.frames == 3
+        for a, b in zip(one.labels, plain.labels):
+            assert torch.equal(a, b)
+        engines = [O.OracleEngine(sd, cfg) for _ in range(4)]
+        tta = E.evaluate_clip_tta(engines, ds, flip=True, multi_scale=(1.0, 1.3), keep_labels=True)
+    assert tta.frames == 3 and all(l.shape == plain.labels[0].shape for l in tta.labels)
+    assert engines[0].input_size_2d == (65, 81) and engines[2].input_size_2d == (81, 97)       # int(65*1.3)=84 -> 81, int(81*1.3)=105 -> 97 (np.around(6.5) = 6)
+    assert int(tta.labels[1].max()) == 2 and (tta.labels[1][40:60, 50:70] == 2).all()           # new object pasted in at frame 2
+    with pytest.raises(ValueError):
+        E.evaluate_clip_tta(engines[:3], ds, flip=True, multi_scale=(1.0, 1.3))

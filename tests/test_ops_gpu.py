@@ -245,3 +245,52 @@ def test_evict_relevance(ops, cuda_device):
     ref = (mass * fg.view(-1, 1)).sum(0)
     out = ops.evict_relevance(mass.to(cuda_device), lg[0].contiguous().to(cuda_device), h, w)
     assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_gpu_preprocess_matches_cv2_loader(ops, cuda_device):
+    """rmem_preprocess_fwd against the reference's loader arithmetic (video_transforms.py:559-682): cv2.resize(float32,
+    INTER_CUBIC) -> optional horizontal flip -> /255, ImageNet mean / std, HWC -> CHW.  Tolerance 2e-3 (normalised units)."""
+    import cv2
+    import numpy as np
+    rng = np.random.RandomState(3)
+    img = cv2.GaussianBlur(rng.randint(0, 255, (97, 161, 3)).astype(np.uint8), (0, 0), 1.5)
+    for (nh, nw) in ((97, 161), (129, 209), (65, 113), (113, 97)):
+        for flip in (False, True):
+            for bgr in (True, False):
+                ref = np.array(img, dtype=np.float32)
+                if bgr:
+                    ref = ref[:, :, [2, 1, 0]]
+                if (nh, nw) != ref.shape[:2]:
+                    ref = cv2.resize(ref, dsize=(nw, nh), interpolation=cv2.INTER_CUBIC)
+                if flip:
+                    ref = ref[:, ::-1]
+                ref = (ref / 255. - (0.485, 0.456, 0.406)) / (0.229, 0.224, 0.225)
+                ref = torch.from_numpy(np.ascontiguousarray(ref.transpose(2, 0, 1))).float()
+                out = ops.preprocess(torch.from_numpy(img).to(cuda_device), nh, nw, bgr=bgr, flip=flip)
+                err = float((out[0].cpu() - ref).abs().max())
+                assert out.shape == (1, 3, nh, nw) and err < 2e-3, (nh, nw, flip, bgr, err)
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_tta_head_matches_probability_averaging(ops, cuda_device, k):
+    """rmem_tta_head_fwd against the evaluator's merge (evaluator.py:420-441) written out in torch: upsample each
+    augmentation's logits (bilinear, align_corners), soft-aggregate the object groups, flip back, softmax, mean, argmax."""
+    g = torch.Generator().manual_seed(17 + k)
+    Ho, Wo = 97, 129
+    sizes = [(25, 33), (25, 33), (33, 43), (33, 43)]
+    flips = [False, True, False, True]
+    logits = [[torch.randn(11, h4, w4, generator=g) * 3 for _ in range(k)] for (h4, w4) in sizes]
+    probs = []
+    for per, fl in zip(logits, flips):
+        ups = [F.interpolate(t[None], size=(Ho, Wo), mode="bilinear", align_corners=True) for t in per]
+        lg = O.soft_logit_aggregation(ups)
+        if fl:
+            lg = torch.flip(lg, dims=(3,))
+        probs.append(torch.softmax(lg, dim=1))
+    mean = torch.mean(torch.cat(probs, 0), 0)
+    ref_lab = torch.argmax(mean, 0)
+    prob, lab = ops.tta_head([[t.to(cuda_device) for t in per] for per in logits], flips, Ho, Wo, want_prob=True)
+    assert float((prob.cpu() - mean).abs().max()) < 2e-5
+    top2 = torch.topk(mean, 2, dim=0).values
+    decided = (top2[0] - top2[1]) > 1e-4                         # away from near-ties the label is exact
+    assert bool((lab.cpu().long() == ref_lab)[decided].all()) and float(decided.float().mean()) > 0.99
