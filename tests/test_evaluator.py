@@ -217,6 +217,6 @@ def test_tta_shell_degenerate_equals_plain_and_flip_runs(tmp_path):
         tta = E.evaluate_clip_tta(engines, ds, flip=True, multi_scale=(1.0, 1.3), keep_labels=True)
     assert tta.frames == 3 and all(l.shape == plain.labels[0].shape for l in tta.labels)
     assert engines[0].input_size_2d == (65, 81) and engines[2].input_size_2d == (81, 97)       # int(65*1.3)=84 -> 81, int(81*1.3)=105 -> 97 (np.around(6.5) = 6)
-    assert int(tta.labels[1].max()) == 2 and (tta.labels[1][40:60, 50:70] == 2).all()           # new object pasted in at frame 2
+    assert (tta.labels[1][40:60, 50:70] == 2).all()             # new object pasted in at frame 2 (random weights: any id elsewhere)
     with pytest.raises(ValueError):
         E.evaluate_clip_tta(engines[:3], ds, flip=True, multi_scale=(1.0, 1.3))
