@@ -189,6 +189,15 @@ typedef struct rmem_engine_config {
   int max_engines;      /* ceil(max objects / 10) object groups */
   int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC2 | RMEM_ATTN_TC3 */
   int long_term_mem_gap;
+  /* Ablation knobs of configs/models/r50_deaotl.py:9-28 (all off in the shipped configs):
+   *   no_long_memory  NO_LONG_MEMORY (aot_engine.py:339): never append to the long-term bank (reference frame only).
+   *   reverse_infer   REVERSE_INFER (aot_engine.py:371-396) and
+   *   time_encode     TIME_ENCODE[_NORM] (aot_engine.py:293-303, 413-421): accepted and ignored -- at inference both leave
+   *                   every output of the unmodified reference bit-identical (the reverse pass only feeds a training loss,
+   *                   the sin/cos encoding is stored and never read); checked by oracle/make_golden.py, tests/golden/knobs.json.
+   *   GRU_MEMORY (ConvGRU condensation of evicted frames, transformer.py:35-119, 420-430) is not built: no shipped
+   *   checkpoint carries its weights; rmem_engine_create refuses gru_memory != 0. */
+  int no_long_memory, reverse_infer, time_encode, gru_memory;
 } rmem_engine_config;
 
 typedef struct rmem_weight_entry {

@@ -74,12 +74,14 @@ def import_reference():
     return DefaultEngineConfig, build_vos_model, build_engine, seen
 
 
-def build_reference(model: str, sd, former: int, latter: int, gap: int):
+def build_reference(model: str, sd, former: int, latter: int, gap: int, knobs: dict = None):
     DefaultEngineConfig, build_vos_model, build_engine, seen = import_reference()
     cfg = DefaultEngineConfig("golden", model)
     cfg.MODEL_LINEAR_Q = False
     cfg.MODEL_IGNORE_TOKEN = True
     cfg.FORMER_MEM_LEN, cfg.LATTER_MEM_LEN = former, latter
+    for k, v in (knobs or {}).items():                  # ablation knobs of configs/models/r50_deaotl.py:9-28
+        setattr(cfg, k, v)
     net = build_vos_model(cfg.MODEL_VOS, cfg).eval()
     missing = net.load_state_dict(sd, strict=True)
     seen.clear()
@@ -122,6 +124,14 @@ def run_oracle_clip(sd, cfg, gap, frames, label0, n_obj, out_size, forced_labels
     return rec, eng
 
 
+# Ablation knobs on the deaot_small_xavier clip.  NO_LONG_MEMORY changes the result (fixture
+# deaot_no_long_memory.npz); REVERSE_INFER and TIME_ENCODE are asserted to leave every inference output of the
+# UNMODIFIED reference bit-identical (aot_engine.py:371-396 only feeds a training loss; the sin/cos encoding of
+# aot_engine.py:293-303, 413-421 is stored and never read) -- the result is recorded in tests/golden/knobs.json.
+KNOB_CASE = "deaot_small_xavier"
+KNOBS_IDENTICAL = [{"REVERSE_INFER": True}, {"TIME_ENCODE": True, "TIME_ENCODE_NORM": False},
+                   {"TIME_ENCODE": True, "TIME_ENCODE_NORM": True}]
+
 CASES = {
     # name: (model, seed, sharpen, H, W, n_obj, n_frames, former, latter, gap, out_size)
     "deaot_small_10obj": ("r50_deaotl", 0, 4.0, 257, 321, 10, 14, 1, 3, 2, (256, 320)),
@@ -132,6 +142,47 @@ CASES = {
     # AOT + RMem: restricted bank (1 + 2), eviction active, sharpened attention
     "aot_small_rmem": ("r50_aotl", 4, 4.0, 193, 257, 3, 11, 1, 2, 2, (193, 257)),
 }
+
+
+def check_knobs():
+    import numpy as np
+    model, seed, sharpen, H, W, n_obj, nfr, former, latter, gap, out_size = CASES[KNOB_CASE]
+    sd = O.make_state_dict(model, seed=seed, sharpen=sharpen)
+    frames = O.synthetic_frames(nfr, H, W, seed=seed + 1)
+    label0 = O.synthetic_label(H, W, n_obj)
+    _, eng = build_reference(model, sd, former, latter, gap)
+    base = run_reference_clip(eng, frames, label0, n_obj, out_size)
+    report = {"case": KNOB_CASE, "identical_to_default": []}
+    for knobs in KNOBS_IDENTICAL:
+        _, e2 = build_reference(model, sd, former, latter, gap, knobs)
+        r = run_reference_clip(e2, frames, label0, n_obj, out_size)
+        same = all(torch.equal(a, b) for a, b in zip(base["logits_out"], r["logits_out"])) and base["idx"] == r["idx"]
+        print(f"[knobs] {knobs}: inference outputs identical to the default config = {same}")
+        assert same, knobs
+        report["identical_to_default"].append(knobs)
+    # NO_LONG_MEMORY (aot_engine.py:339): the long-term bank never grows beyond the reference frame
+    knobs = {"NO_LONG_MEMORY": True}
+    _, e3 = build_reference(model, sd, former, latter, gap, knobs)
+    ref = run_reference_clip(e3, frames, label0, n_obj, out_size)
+    cfg = O.OracleConfig(model=model, former_mem_len=former, latter_mem_len=latter, no_long_memory=True)
+    ref_labels = torch.stack([l[0, 0] for l in ref["labels"]])
+    orc, _ = run_oracle_clip(sd, cfg, gap, frames, label0, n_obj, out_size, forced_labels=ref_labels)
+    worst = max((a - b).abs().max().item() for a, b in zip(ref["logits_out"], orc["logits_out"]))
+    print(f"[knobs] NO_LONG_MEMORY: max|logit_ref - logit_oracle| = {worst:.3e}, idx = {ref['idx'][-1]}")
+    assert worst < 2e-4 and ref["idx"] == orc["idx"] and all(i == [[0]] for i in ref["idx"])
+    differs = not all(torch.equal(a, b) for a, b in zip(base["logits_out"], ref["logits_out"]))
+    assert differs, "NO_LONG_MEMORY should change the outputs of a clip that appends long-term frames"
+    meta = dict(case="deaot_no_long_memory", model=model, seed=seed, sharpen=sharpen, H=H, W=W, n_obj=n_obj, n_frames=nfr,
+                former=former, latter=latter, gap=gap, out_size=list(out_size), idx=ref["idx"], keep=[len(ref["logits4"]) - 1],
+                knobs=knobs, reference_commit="431cde18", torch=torch.__version__)
+    k = len(ref["logits4"]) - 1
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "deaot_no_long_memory.npz"), meta=json.dumps(meta),
+                        labels=ref_labels.numpy(),
+                        logits4_sub=torch.stack([x[0, :, ::4, ::4] for x in ref["logits4"]]).numpy(),
+                        ref_logits4=ref["ref_logits4"][0].numpy().astype(np.float16),
+                        **{f"logits4_{k}": ref["logits4"][k][0].numpy().astype(np.float16)})
+    report["changes_outputs"] = [knobs]
+    json.dump(report, open(os.path.join(ROOT, "tests", "golden", "knobs.json"), "w"), indent=1)
 
 
 def main():
@@ -176,6 +227,8 @@ def main():
         for k in keep:
             arrays[f"logits4_{k}"] = ref["logits4"][k][0].numpy().astype(np.float16)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), meta=json.dumps(meta), **arrays)
+    if not only or "knobs" in only:
+        check_knobs()
     print("golden fixtures written")
 
 

@@ -55,6 +55,7 @@ class OracleConfig:
     model: str = "r50_deaotl"           # "r50_deaotl" | "r50_aotl"
     former_mem_len: int = 1
     latter_mem_len: int = 8             # shipped setting (configs/models/r50_deaotl.py:8); the T=8 workloads pass 7
+    no_long_memory: bool = False        # NO_LONG_MEMORY (configs/models/r50_deaotl.py:20, aot_engine.py:339)
     d_model: int = 256                  # MODEL_ENCODER_EMBEDDING_DIM
     n_layers: int = 3                   # MODEL_LSTT_NUM
     max_obj: int = MAX_OBJ
@@ -614,7 +615,7 @@ class OracleSubEngine:
         h, w = self.hw
         oh = one_hot_with_ignore(label, use_ignore=True)
         id_emb = id_embedding(sd, cfg, oh)
-        is_long = self.frame_step - self.last_mem_step >= self.gap
+        is_long = (not cfg.no_long_memory) and self.frame_step - self.last_mem_step >= self.gap
         if is_long:
             self.last_mem_step = self.frame_step
         if cfg.is_deaot:

@@ -38,7 +38,8 @@ class GemmDesc(C.Structure):
 class EngineConfig(C.Structure):
     _fields_ = [("model", C.c_int), ("H", C.c_int), ("W", C.c_int), ("former_mem_len", C.c_int),
                 ("latter_mem_len", C.c_int), ("max_engines", C.c_int), ("attn_impl", C.c_int),
-                ("long_term_mem_gap", C.c_int)]
+                ("long_term_mem_gap", C.c_int), ("no_long_memory", C.c_int), ("reverse_infer", C.c_int),
+                ("time_encode", C.c_int), ("gru_memory", C.c_int)]
 
 
 class WeightEntry(C.Structure):

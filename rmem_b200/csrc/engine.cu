@@ -1040,6 +1040,7 @@ int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(cfg && bytes, "null argument");
   RMEM_REQUIRE(cfg->model == 0 || cfg->model == 1, "model %d: 0 = r50_deaotl, 1 = r50_aotl", cfg->model);
+  RMEM_REQUIRE(cfg->gru_memory == 0, "GRU_MEMORY (ConvGRU memory condensation) is not built");
   RMEM_REQUIRE(cfg->attn_impl == RMEM_ATTN_DENSE || cfg->attn_impl == RMEM_ATTN_TC2 || cfg->attn_impl == RMEM_ATTN_TC3,
                "attn_impl %d: 0 = dense, 2 = tc2, 3 = tc3", cfg->attn_impl);
   RMEM_REQUIRE(cfg->H > 16 && cfg->W > 16 && (cfg->H - 1) % 16 == 0 && (cfg->W - 1) % 16 == 0,
@@ -1220,7 +1221,7 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
     Group& gr = e->groups[gi];
     RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/1, s));
     e->mark("upd.id_embed", s);
-    bool is_long = (gr.frame_step - gr.last_mem_step) >= e->cfg.long_term_mem_gap;
+    bool is_long = !e->cfg.no_long_memory && (gr.frame_step - gr.last_mem_step) >= e->cfg.long_term_mem_gap;
     if (is_long) gr.last_mem_step = gr.frame_step;
     if (e->cfg.model == 1) {
       RMEM_TRY(e->aot_refresh(gr, s));                                     // transformer.py:269-304

@@ -36,6 +36,11 @@ class RmemConfig:
     max_obj_num: int = MAX_OBJ
     attn_impl: int = _capi.ATTN_TC3
     max_engines: int = 4
+    # ablation knobs (configs/models/r50_deaotl.py:9-28; all False in the shipped configs, see include/rmem_b200.h)
+    no_long_memory: bool = False     # NO_LONG_MEMORY: the long-term bank stays at the reference frame
+    reverse_infer: bool = False      # REVERSE_INFER: no effect at inference (training-loss pass only); accepted
+    time_encode: bool = False        # TIME_ENCODE / TIME_ENCODE_NORM: no effect at inference (stored, never read); accepted
+    gru_memory: bool = False         # GRU_MEMORY: not built (refused)
 
 
 MODEL_IDS = {"r50_deaotl": 0, "r50_aotl": 1}
@@ -167,7 +172,8 @@ class DeAOTInferEngine:
         self._destroy()
         lib = _capi.load()
         cc = _capi.EngineConfig(MODEL_IDS[self.cfg.model], H, W, self.cfg.former_mem_len, self.cfg.latter_mem_len, self.cfg.max_engines,
-                                self.cfg.attn_impl, max(int(self.long_term_mem_gap), 1))
+                                self.cfg.attn_impl, max(int(self.long_term_mem_gap), 1), int(self.cfg.no_long_memory),
+                                int(self.cfg.reverse_infer), int(self.cfg.time_encode), int(self.cfg.gru_memory))
         nbytes = C.c_size_t()
         _capi.check(lib.rmem_engine_arena_bytes(C.byref(cc), C.byref(nbytes)))
         self._arena = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)

@@ -41,9 +41,11 @@ def test_errors_are_reported_not_thrown():
     import ctypes as C
     lib = _capi.load()
     nbytes = C.c_size_t()
-    cfg = _capi.EngineConfig(0, 480, 854, 1, 7, 1, 0, 5)          # not 16k+1 -> must be refused with a message
+    cfg = _capi.EngineConfig(0, 480, 854, 1, 7, 1, 0, 5, 0, 0, 0, 0)   # not 16k+1 -> must be refused with a message
     rc = lib.rmem_engine_arena_bytes(C.byref(cfg), C.byref(nbytes))
     assert rc != 0 and b"16k+1" in lib.rmem_last_error()
-    cfg = _capi.EngineConfig(0, 481, 849, 1, 7, 1, 0, 5)
+    cfg = _capi.EngineConfig(0, 481, 849, 1, 7, 1, 0, 5, 0, 0, 0, 1)   # GRU_MEMORY is refused
+    assert lib.rmem_engine_arena_bytes(C.byref(cfg), C.byref(nbytes)) != 0 and b"GRU_MEMORY" in lib.rmem_last_error()
+    cfg = _capi.EngineConfig(0, 481, 849, 1, 7, 1, 0, 5, 0, 0, 0, 0)
     assert lib.rmem_engine_arena_bytes(C.byref(cfg), C.byref(nbytes)) == 0
     assert 100e6 < nbytes.value < 4e9

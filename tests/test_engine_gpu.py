@@ -41,8 +41,10 @@ def run_engine_lockstep(meta, z, device, attn_impl=0):
     H, W, n_obj = meta["H"], meta["W"], meta["n_obj"]
     frames = O.synthetic_frames(meta["n_frames"], H, W, seed=meta["seed"] + 1)
     label0 = O.synthetic_label(H, W, n_obj)
+    knobs = meta.get("knobs", {})
     cfg = RmemConfig(model=meta["model"], former_mem_len=meta["former"], latter_mem_len=meta["latter"],
-                     attn_impl=attn_impl)
+                     attn_impl=attn_impl, no_long_memory=bool(knobs.get("NO_LONG_MEMORY", False)),
+                     reverse_infer=bool(knobs.get("REVERSE_INFER", False)), time_encode=bool(knobs.get("TIME_ENCODE", False)))
     model = RmemModel(sd, cfg, device)
     eng = build_engine("deaotengine" if meta["model"] == "r50_deaotl" else "aotengine", phase="eval", aot_model=model,
                        gpu_id=0, long_term_mem_gap=meta["gap"])
@@ -92,6 +94,24 @@ def test_engine_matches_reference_goldens(cuda_device, name, impl):
     report(f"golden/{name}/attn_impl_{impl}", worst_rel_logit_err=worst, label_agreement=agree, idx_identical=True,
            frames=len(rec["logits4"]), tolerances=dict(logit=LOGIT_TOL, label=LABEL_AGREE), vs="unmodified reference")
     assert agree >= LABEL_AGREE
+
+
+def test_ablation_knobs_match_reference(cuda_device):
+    """NO_LONG_MEMORY against its own reference golden; REVERSE_INFER / TIME_ENCODE are inference no-ops in
+    the reference (tests/golden/knobs.json, asserted by oracle/make_golden.py), so the engine accepts them and must
+    reproduce the default golden bit-for-bit in its integer state and within tolerance in its logits."""
+    test_engine_matches_reference_goldens(cuda_device, "deaot_no_long_memory", 3)
+    kn = json.load(open(os.path.join(GOLD, "knobs.json")))
+    assert {"REVERSE_INFER": True} in kn["identical_to_default"] and {"NO_LONG_MEMORY": True} in kn["changes_outputs"]
+    meta, z = load_case(kn["case"])
+    meta = dict(meta, knobs={"REVERSE_INFER": True, "TIME_ENCODE": True})
+    rec, _ = run_engine_lockstep(meta, z, cuda_device, attn_impl=3)
+    assert rec["idx"] == meta["idx"]
+    from rmem_b200.engine import RmemModel, RmemConfig, build_engine
+    with pytest.raises(Exception):
+        sd = O.make_state_dict("r50_deaotl", seed=1)
+        e = build_engine("deaotengine", aot_model=RmemModel(sd, RmemConfig(gru_memory=True), cuda_device))
+        e.add_reference_frame(torch.zeros(1, 3, 129, 161), torch.zeros(1, 1, 129, 161).int(), obj_nums=[1], frame_step=0)
 
 
 @pytest.mark.parametrize("name", ["aot_c1_256_t1", "aot_small_rmem"])
