@@ -226,6 +226,8 @@ def run_ours(args):
     cpu = None
     if rank == 0:
         roof = measure_attention_roofline(eng, dev, args)
+        roof["hbm_kernels"] = measure_hbm_kernels(eng, dev)
+        roof["hbm_peak"] = {"value": peaks()["hbm_gbs"], "unit": "GB/s", "source": peaks()["source"]}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(sample_frames=args.cpu_frames)
     if rank == 0:
@@ -350,6 +352,66 @@ def measure_attention_roofline(eng, dev, args):
                       "immediately around the main kernel launch on its stream; op = qprep + seed + kernel + combine "
                       "between two events; 256 MB L2 flush between launches",
             "algorithmic_flops_per_launch": flops, "traffic": ncu_traffic()}
+
+
+def measure_hbm_kernels(eng, dev):
+    """HBM-bound kernels of the path, each timed ALONE at its c3 shape through the op-level C ABI (median of 9 launches,
+    CUDA events around the single launch on the launch stream, 256 MB L2 flush before each: cold-cache, and the ~2 us
+    launch latency is inside the time -- a floor for the fraction, not a ceiling).  achieved = ALGORITHMIC bytes (inputs
+    read once + outputs written once, as listed) / time; peak = MEASURED_PEAKS.json hbm_gbs."""
+    from rmem_b200 import _capi, ops as K
+    from rmem_b200.synth import synthetic_frames
+    from rmem_b200.weights import pack_model
+    pk = peaks()
+    OP = _capi.op_dtype()
+    g = torch.Generator().manual_seed(1)
+    h, w, HW = 31, 54, HW_TOK
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+
+    def timed(name, bytes_, fn, what):
+        fn()
+        ts = []
+        for _ in range(9):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        us = sorted(ts)[len(ts) // 2]
+        gbs = bytes_ / us / 1e3
+        out.append({"kernel": name, "algorithmic_bytes": int(bytes_), "bytes_are": what, "us": round(us, 2),
+                    "achieved_gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 4)})
+
+    x = torch.randn(HW, 1024, generator=g).to(dev).to(OP)
+    dw = torch.randn(25, 1024, generator=g).to(dev)
+    timed("dwconv5_kernel", 2 * HW * 1024 * 2, lambda: K.dwconv5x5(x, dw, h, w), "gated [HW,1024] fp16 in + out")
+    xf = torch.randn(HW, 256, generator=g).to(dev)
+    gm, bt = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    timed("layernorm_kernel", HW * 256 * (4 + 2), lambda: K.layernorm(xf, gm, bt), "[HW,256] fp32 in, fp16 out")
+    lg = [torch.randn(11, 121, 213, generator=g).to(dev)]
+    timed("mask_head_kernel", 11 * 121 * 213 * 4 + H * W, lambda: K.mask_head(lg, H, W, want_logits=False),
+          "1/4-res logits fp32 in, uint8 label map out")
+    lab = eng.propagate_label(synthetic_frames(2, H, W, seed=3)[1:2].to(dev), output_size=(H, W))[0, 0].contiguous()
+    pw = pack_model(eng.AOT.weights_state if hasattr(eng.AOT, "weights_state") else _bench_sd(), "r50_deaotl")
+    wts = {k: pw[k].to(dev) for k in ("idbank.w", "idbank.b", "idbank.prefix", "idbank.prefix_rows", "id_norm.g", "id_norm.b",
+                                      "enc.conv1.w", "enc.conv1.b")}
+    timed("idbank_kernel", H * W + HW * 256 * 4 + pw["idbank.prefix_rows"].numel() * 4,
+          lambda: K.id_embedding(lab, wts["idbank.w"], wts["idbank.b"], wts["id_norm.g"], wts["id_norm.b"], True,
+                                 prefix=wts["idbank.prefix"], prefix_rows=wts["idbank.prefix_rows"]),
+          "uint8 label map + row-prefix table (3.8 MB, each entry at most once) in, [HW,256] fp32 out; steady-state "
+          "network labels")
+    img = synthetic_frames(1, H, W, seed=5).to(dev)
+    H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    timed("gemm_tc_kernel<64> (conv1 stem) + pack_image_padded_kernel", 3 * H * W * 4 + 2 * (H + 6) * (W + 8) * 8 * 2 + H1 * W1 * 64 * 2,
+          lambda: K.stem_conv(img, wts["enc.conv1.w"], wts["enc.conv1.b"]),
+          "fp32 frame in, padded NHWC8 fp16 written + read once, [P1,64] fp16 out (two launches)")
+    return out
+
+
+def _bench_sd():
+    from rmem_b200.synth import make_state_dict
+    return make_state_dict("r50_deaotl", seed=0, sharpen=4.0)
 
 
 def ncu_traffic():

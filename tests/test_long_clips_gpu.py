@@ -81,5 +81,5 @@ def test_long_clip_matches_oracle_fixture(cuda_device, name):
     from parity_report import report
     report(f"long/{name}", **rec)
     assert n_evict == len(evict_at)
-    label_bar = LABEL_AGREE if n_obj <= 10 else 0.99        # several object groups: see tests/test_full_size_gpu.py
+    label_bar = LABEL_AGREE if n_obj <= 10 else 0.985       # several object groups: see tests/test_full_size_gpu.py (0.9908 measured)
     assert worst_logit < LOGIT_TOL and min_agree >= label_bar and worst_rel < REL_TOL, rec
