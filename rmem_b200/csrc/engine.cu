@@ -105,6 +105,10 @@ struct Group {       // one AOTEngine: <= 10 objects, own bank (reference + per-
   bool has_ref = false;
   std::vector<float> last_rel;
   int last_drop = -1;
+  // deferred eviction: update_memory leaves the T relevance floats in flight to pinned host memory and returns; the
+  // table edit happens at the next call that reads the tables (rmem_engine::resolve_evict) -- no host sync per append
+  bool evict_pending = false;
+  int evict_T_old = 0;
 };
 
 }  // namespace
@@ -146,6 +150,33 @@ struct rmem_engine {
     RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
     return RMEM_OK;
   }
+  float* rel_pinned = nullptr;             // [max_engines][kMaxBankFrames] pinned host landing zone of the relevance sums
+  cudaEvent_t ev_rel[4] = {nullptr, nullptr, nullptr, nullptr};
+  // transformer.py:891-964 on the host, run lazily: waits for the T floats of the last append (normally long complete),
+  // then EMA / UCB / argmin and the slot-table edit exactly as before.
+  int resolve_evict(int gi) {
+    Group& gr = groups[gi];
+    if (!gr.evict_pending) return RMEM_OK;
+    gr.evict_pending = false;
+    RMEM_CUDA_CHECK(cudaEventSynchronize(ev_rel[gi]));
+    const int T_old = gr.evict_T_old;
+    const int cap = cfg.former_mem_len + cfg.latter_mem_len;
+    int drop = cfg.former_mem_len;
+    gr.last_rel.assign(T_old, 0.f);
+    RMEM_TRY(evict_pick_host(rel_pinned + (size_t)gi * kMaxBankFrames, T_old, gr.long_idx.data(), cfg.former_mem_len, gr.ema,
+                             gr.times, &drop, gr.last_rel.data()));
+    gr.last_drop = drop;
+    if ((int)gr.slots.size() > cap) {
+      gr.free_slots.push_back(gr.slots[drop]);
+      gr.slots.erase(gr.slots.begin() + drop);
+      gr.long_idx.erase(gr.long_idx.begin() + drop);
+    }
+    return RMEM_OK;
+  }
+  int resolve_all() {
+    for (int gi = 0; gi < (int)groups.size(); ++gi) RMEM_TRY(resolve_evict(gi));
+    return RMEM_OK;
+  }
   cudaStream_t enc_stream = nullptr;
   cudaEvent_t ev_img_ready = nullptr, ev_inline = nullptr, ev_done[2] = {nullptr, nullptr}, ev_feat_free[2] = {nullptr, nullptr};
   bool feat_free_valid[2] = {false, false}, inline_valid = false;
@@ -175,6 +206,8 @@ struct rmem_engine {
       RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
       RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_feat_free[i], cudaEventDisableTiming));
     }
+    RMEM_CUDA_CHECK(cudaMallocHost(&rel_pinned, sizeof(float) * 4 * kMaxBankFrames));
+    for (int i = 0; i < 4; ++i) RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_rel[i], cudaEventDisableTiming));
     return RMEM_OK;
   }
   ~rmem_engine() {
@@ -188,6 +221,9 @@ struct rmem_engine {
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    for (int i = 0; i < 4; ++i)
+      if (ev_rel[i]) cudaEventDestroy(ev_rel[i]);
+    if (rel_pinned) cudaFreeHost(rel_pinned);
     if (ev_img_ready) cudaEventDestroy(ev_img_ready);
     if (ev_inline) cudaEventDestroy(ev_inline);
     for (int i = 0; i < 2; ++i) {
@@ -1107,6 +1143,7 @@ int rmem_engine_restart(rmem_engine* e) {
   e->n_groups = 0;
   e->pending[0] = e->pending[1] = false;
   for (auto& gr : e->groups) {
+    gr.evict_pending = false;
     gr.slots.clear(); gr.free_slots.clear(); gr.long_idx.clear(); gr.ema.clear(); gr.times.clear();
     gr.frame_step = 0; gr.last_mem_step = -1; gr.has_ref = false; gr.parity = 0; gr.mass_T = 0;
     gr.last_rel.clear(); gr.last_drop = -1;
@@ -1133,6 +1170,7 @@ int rmem_engine_add_reference_frame(rmem_engine* e, const float* img, const void
   RMEM_REQUIRE(n <= e->cfg.max_engines, "%d objects need %d object groups, engine built for %d", n_objects, n,
                e->cfg.max_engines);
   if (n > e->n_groups) e->n_groups = n;
+  RMEM_TRY(e->resolve_all());
   // zero the bank/state region once per clip (pad columns of the value-major bank must stay finite)
   RMEM_CUDA_CHECK(cudaMemsetAsync(e->arena_base + e->state_begin, 0, e->state_bytes, s));
   RMEM_TRY(e->features(img, s));
@@ -1160,6 +1198,7 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
   RMEM_REQUIRE(e->n_groups >= 1 && e->groups[0].has_ref, "propagate before add_reference_frame");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   RMEM_TRY(e->features(img, s));
+  RMEM_TRY(e->resolve_all());                // a deferred eviction of the previous update_memory edits the slot tables now
   const float* lg[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int gi = 0; gi < e->n_groups; ++gi) {
     Group& gr = e->groups[gi];
@@ -1217,6 +1256,7 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
   const Geo& G = e->g;
   const int cap = e->cfg.former_mem_len + e->cfg.latter_mem_len;
   e->mark("begin", s);
+  RMEM_TRY(e->resolve_all());
   for (int gi = 0; gi < e->n_groups; ++gi) {
     Group& gr = e->groups[gi];
     RMEM_TRY(e->id_embed(gr, gi, label, label_is_f32, /*use_ignore=*/1, s));
@@ -1243,19 +1283,13 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
       RMEM_REQUIRE(T_old + 1 == (int)gr.slots.size(), "attention mass is stale (T_old=%d, bank=%zu)", T_old,
                    gr.slots.size());
       RMEM_TRY(evict_relevance(gr.mass0, T_old, gr.logits4, G.H4, G.W4, G.h, G.w, e->rel_dev, s));
-      float rel_host[kMaxBankFrames];
-      RMEM_CUDA_CHECK(cudaMemcpyAsync(rel_host, e->rel_dev, sizeof(float) * T_old, cudaMemcpyDeviceToHost, s));
-      RMEM_CUDA_CHECK(cudaStreamSynchronize(s));
-      int drop = e->cfg.former_mem_len;
-      gr.last_rel.assign(T_old, 0.f);
-      RMEM_TRY(evict_pick_host(rel_host, T_old, gr.long_idx.data(), e->cfg.former_mem_len, gr.ema, gr.times, &drop,
-                               gr.last_rel.data()));
-      gr.last_drop = drop;
-      if ((int)gr.slots.size() > cap) {
-        gr.free_slots.push_back(gr.slots[drop]);
-        gr.slots.erase(gr.slots.begin() + drop);
-        gr.long_idx.erase(gr.long_idx.begin() + drop);
-      }
+      // no host sync here: the T floats travel to pinned memory behind an event and the EMA / UCB pick + table edit run
+      // at the next call that reads the tables (resolve_evict) -- by then the copy has long completed
+      RMEM_CUDA_CHECK(cudaMemcpyAsync(e->rel_pinned + (size_t)gi * kMaxBankFrames, e->rel_dev, sizeof(float) * T_old,
+                                      cudaMemcpyDeviceToHost, s));
+      RMEM_CUDA_CHECK(cudaEventRecord(e->ev_rel[gi], s));
+      gr.evict_pending = true;
+      gr.evict_T_old = T_old;
     }
     gr.parity ^= 1;   // current frame -> short-term memory
   }
@@ -1270,6 +1304,7 @@ int rmem_engine_num_groups(const rmem_engine* e) { return e ? e->n_groups : 0; }
 int rmem_engine_long_indexes(const rmem_engine* e, int group, int* idx, int* n) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(e && idx && n && group >= 0 && group < e->n_groups, "bad argument");
+  RMEM_TRY(const_cast<rmem_engine*>(e)->resolve_evict(group));
   const Group& gr = e->groups[group];
   // A mid-clip add_reference_frame re-initialises the bank but (like aot_engine.py:321-323) keeps appending to this list,
   // so it can outgrow the bank; the caller's buffer holds kMaxBankFrames + 1 entries: report the NEWEST ones.
@@ -1296,6 +1331,7 @@ int rmem_engine_layer_memory(const rmem_engine* e, int group, int layer, const v
   RMEM_API_BEGIN
   RMEM_REQUIRE(e && group >= 0 && group < e->n_groups && layer >= 0 && layer < kLayers, "bad argument");
   RMEM_REQUIRE(e->cfg.model == 0, "layer memories are exposed for the DeAOT model only");
+  RMEM_TRY(const_cast<rmem_engine*>(e)->resolve_evict(group));
   const Group& gr = e->groups[group];
   const LayerState& L = gr.L[layer];
   // update_memory flipped the parity: the last propagated frame's K / V||ID_V are the "previous frame" buffers now
@@ -1316,6 +1352,7 @@ int rmem_engine_layer_memory(const rmem_engine* e, int group, int layer, const v
 int rmem_engine_last_evict(const rmem_engine* e, int group, float* rel, int* n, int* drop) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(e && rel && n && drop && group >= 0 && group < e->n_groups, "bad argument");
+  RMEM_TRY(const_cast<rmem_engine*>(e)->resolve_evict(group));
   const Group& gr = e->groups[group];
   *n = (int)gr.last_rel.size();
   for (int i = 0; i < *n; ++i) rel[i] = gr.last_rel[i];
