@@ -78,6 +78,16 @@ int rmem_long_attn_grid_fwd(int impl, const void* qt, const float* qbias, const 
                             int nslots, int T, const int* slots /*HOST [T]*/, int HW, int HWp, int Dk, int Dv,
                             float scale, const void* gate, long long ldg, void* out, long long ldo, float* mass,
                             int grid_h, int grid_w, void* workspace, size_t workspace_bytes, void* stream);
+/* Multi-head attention over the bank (AOT model, 8 heads x 32): MultiheadAttention.forward of
+ * networks/layers/attention.py:28-81 as used by SimplifiedTransformerBlock (transformer.py:566-571 self-attention, :632-650
+ * long-term attention over the restricted bank with the temporal PE as a per-head score bias, :656-662 short-term).
+ * q [HW, H*dh] (row stride ldq), kbank [nslots][HWp][H*dh], vtbank [H*dh][nslots*HWp] (value-major), qbias [H][HW][T]
+ * (already multiplied by scale) or NULL, out [HW, H*dh] (row stride ldo), mass [HW, T] = head mean of the per-frame
+ * probability mass or NULL.  impl RMEM_ATTN_DENSE = materialised scores; anything else = the fused tcgen05 kernel. */
+int rmem_mha_workspace_bytes(int impl, int HW, int HWp, int nslots, int H, size_t* bytes);
+int rmem_mha_fwd(int impl, const void* q, long long ldq, const void* kbank, const void* vtbank, int nslots, int T,
+                 const int* slots /*HOST [T]*/, int HW, int HWp, int H, int dh, float scale, const float* qbias,
+                 void* out, long long ldo, float* mass, void* workspace, size_t workspace_bytes, void* stream);
 /* Debug aid (RMEM_ATTN_TC3): device int the kernel increments once per warp-level lazy-rescale event; NULL disables.
  * Thread-local. */
 int rmem_debug_attn_rescale_counter(void* dev_int);

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librmem_b200.so")
-SOURCES = ["capi.cu", "gemm.cu", "gemm_tc.cu", "tma.cu", "ops.cu", "attn_dense.cu", "attn_tc2.cu", "attn_tc3.cu", "local_attn_tc.cu", "engine.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "gemm_tc.cu", "tma.cu", "ops.cu", "attn_dense.cu", "attn_tc2.cu", "attn_tc3.cu", "mha_tc.cu", "local_attn_tc.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]

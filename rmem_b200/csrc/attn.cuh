@@ -53,6 +53,10 @@ struct MhaArgs {
 };
 size_t mha_dense_workspace(int HW, int HWp, int nslots, int H);
 int mha_dense(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
+// Fused tcgen05 version (mha_tc.cu): scores, online softmax and P.V of all 8 heads of a (128-query, 64-key) step in one
+// CTA, P through TMEM, stream-K over the SMs; the engine's AOT path (attn_impl != dense).
+size_t mha_tc_workspace(int HW, int HWp, int nslots, int H);
+int mha_tc(const MhaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 // v2 (attn_tc2.cu): stream-K schedule over the SMs, 8 softmax warps, P through TMEM, fp16 partials.
 size_t long_attn_tc2_workspace(int HW, int HWp, int nslots, int Dv);

@@ -108,6 +108,31 @@ int rmem_long_attn_grid_fwd(int impl, const void* qt, const float* qbias, const 
   RMEM_API_END
 }
 
+int rmem_mha_workspace_bytes(int impl, int HW, int HWp, int nslots, int H, size_t* bytes) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(bytes, "null argument");
+  *bytes = impl == RMEM_ATTN_DENSE ? mha_dense_workspace(HW, HWp, nslots, H) : mha_tc_workspace(HW, HWp, nslots, H);
+  return RMEM_OK;
+  RMEM_API_END
+}
+
+int rmem_mha_fwd(int impl, const void* q, long long ldq, const void* kbank, const void* vtbank, int nslots, int T,
+                 const int* slots, int HW, int HWp, int H, int dh, float scale, const float* qbias, void* out,
+                 long long ldo, float* mass, void* workspace, size_t workspace_bytes, void* stream) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(q && kbank && vtbank && out && slots && workspace, "null argument");
+  RMEM_REQUIRE(T >= 1 && T <= kMaxBankFrames, "T=%d out of range", T);
+  MhaArgs a;
+  a.q = (const t16*)q; a.ldq = ldq; a.kbank = (const t16*)kbank; a.vtbank = (const t16*)vtbank;
+  a.nslots = nslots; a.T = T;
+  for (int t = 0; t < T; ++t) a.slot[t] = slots[t];
+  a.HW = HW; a.HWp = HWp; a.H = H; a.dh = dh; a.scale = scale; a.qbias = qbias;
+  a.out = (t16*)out; a.ldo = ldo; a.mass = mass;
+  if (impl == RMEM_ATTN_DENSE) return mha_dense(a, workspace, workspace_bytes, STREAM(stream));
+  return mha_tc(a, workspace, workspace_bytes, STREAM(stream));
+  RMEM_API_END
+}
+
 int rmem_debug_gemm_trace(void* dev_buf) { return gemm_tc_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 int rmem_debug_attn_events(void* ev0, void* ev1) {
   RMEM_API_BEGIN

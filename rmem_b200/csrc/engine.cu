@@ -358,7 +358,8 @@ struct rmem_engine {
       a_ff2 = a.take<t16>((size_t)G.HW * 4 * kD);
       a_decin = a.take<t16>((size_t)G.HW * 4 * kD);
       a_qt = a.take<t16>((size_t)G.HW * kD);
-      mha_ws_bytes = mha_dense_workspace(G.HW, G.HWp, nslots, 8);
+      mha_ws_bytes = cfg.attn_impl == RMEM_ATTN_DENSE ? mha_dense_workspace(G.HW, G.HWp, nslots, 8)
+                                                      : mha_tc_workspace(G.HW, G.HWp, nslots, 8);
       mha_ws = a.take<char>(mha_ws_bytes);
     }
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
@@ -841,7 +842,9 @@ struct rmem_engine {
   // =============================================================================================
   // AOT (model 1): SimplifiedTransformerBlock / LongShortTermTransformer  (transformer.py:199-267, 553-692)
   // =============================================================================================
-  int mha(const MhaArgs& a, cudaStream_t s) { return mha_dense(a, mha_ws, mha_ws_bytes, s); }
+  int mha(const MhaArgs& a, cudaStream_t s) {
+    return cfg.attn_impl == RMEM_ATTN_DENSE ? mha_dense(a, mha_ws, mha_ws_bytes, s) : mha_tc(a, mha_ws, mha_ws_bytes, s);
+  }
 
   // y[HW,N] (t16 or fp32 accumulate) = x[HW,K] W^T + b
   int lin_t16(const t16* x, long long ldx, int K, const std::string& w, int N, t16* y, long long ldy, cudaStream_t s) {

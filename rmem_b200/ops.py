@@ -346,3 +346,28 @@ def local_attention(q: torch.Tensor, k_prev: torch.Tensor, v_prev: torch.Tensor,
                                         _capi.ptr(out), C.c_longlong(Dv), h, w, Dv, C.c_float(1.0 / math.sqrt(Dk)),
                                         _capi.stream_ptr()))
     return out
+
+
+def multihead_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, slots: Sequence[int], HW: int,
+                        n_head: int = 8, qbias: Optional[torch.Tensor] = None, impl: int = _capi.ATTN_TC3,
+                        want_mass: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """AOT MultiheadAttention over the bank (attention.py:28-81): q t16 [HW, C] (any PE already added), kbank
+    [nslots, HWp, C], vtbank [C, nslots*HWp], qbias fp32 [H, HW, T] (already scaled) or None.
+    Returns (out t16 [HW, C], mass fp32 [HW, T] = head mean of the per-frame probability mass)."""
+    lib = _capi.load()
+    nslots, HWp, Cc = kbank.shape
+    T = len(slots)
+    dh = Cc // n_head
+    dev = q.device
+    scale = 1.0 / math.sqrt(dh)
+    nbytes = C.c_size_t()
+    _capi.check(lib.rmem_mha_workspace_bytes(impl, HW, HWp, nslots, n_head, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    out = torch.empty(HW, Cc, dtype=_capi.op_dtype(), device=dev)
+    mass = torch.empty(HW, T, dtype=torch.float32, device=dev) if want_mass else None
+    sl = (C.c_int * T)(*slots)
+    _capi.check(lib.rmem_mha_fwd(impl, _capi.ptr(q), C.c_longlong(q.stride(0)), _capi.ptr(kbank), _capi.ptr(vtbank),
+                                 nslots, T, sl, HW, HWp, n_head, dh, C.c_float(scale), _capi.ptr(qbias),
+                                 _capi.ptr(out), C.c_longlong(Cc), _capi.ptr(mass), _capi.ptr(ws),
+                                 C.c_size_t(nbytes.value), _capi.stream_ptr()))
+    return out, mass
