@@ -29,6 +29,8 @@ struct LongAttnArgs {
   // RMEM_ATTN_TC3 only: token grid (seed_h * seed_w == HW) for the row-maximum seed (scores against the 3x3 neighbourhood
   // of the query's own position in every bank frame); 0 = no seed (the first key tile seeds the maximum)
   int seed_h = 0, seed_w = 0;
+  // RMEM_ATTN_TC3: seed already computed by qprep_seed_tc3 ([HW] fp32, log2 units); the kernel then launches no seed pass
+  const float* mseed = nullptr;
 };
 
 // Materialised-score implementation (generic GEMM + row softmax).  Workspace: S fp32 + P t16.
@@ -66,6 +68,10 @@ int long_attn_tc2(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
 size_t long_attn_tc3_workspace(int HW, int HWp, int nslots, int Dv);
 int long_attn_tc3_schedule(int HW, int T, int Dv, int* n_units, int* groups_per_unit, int* n_clusters, int* bounds, int cap);
 int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
+// qprep (Qt, qbias: ops.cuh) and the row-maximum seed of the long-term attention in ONE launch (Dk = 128).
+int qprep_seed_tc3(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+                   float scale, const t16* kbank, const int* slot, int HW, int HWp, int h, int w, t16* qt, float* qbias,
+                   float* mseed, cudaStream_t s);
 int long_attn_tc3_set_trace(long long* dev_buf);
 void long_attn_tc3_set_events(void* ev0, void* ev1);
 // Debug: device int incremented once per warp-level lazy-rescale event (null disables).  Thread-local.

@@ -799,6 +799,94 @@ __global__ void __launch_bounds__(256) attn_seed_kernel(const t16* __restrict__ 
   if (lane == 0) mseed[i] = best;
 }
 
+// qprep + seed in one launch (the engine's long-term path): Qt = t16(Q + cur_pos_emb), qbias[i,t] = scale <Qt_i, pe_mem[slot_T(t)]>
+// (transformer.py:1140-1175 as a score bias, see ops.cu qprep_kernel) and the row-maximum seed of attn_seed_kernel above.
+// One warp per query; eight lanes share a 128-channel row (16 channels each); the four 8-lane groups take the bank frames
+// round-robin and issue the loads of all nine neighbour keys of a frame before the first dot product, so a query costs
+// ceil(T / 4) L2 round trips instead of T * 9 / 4 (attn_seed_kernel: 16 us at T = 8).
+struct PeSlots3 { int s[kMaxBankFrames]; };
+__global__ void __launch_bounds__(256) qprep_seed_kernel(const t16* __restrict__ q, long long ldq,
+                                                         const float* __restrict__ pe_cur, const float* __restrict__ pe_mem,
+                                                         PeSlots3 ps, float scale, const t16* __restrict__ kbank, Tc3Params p,
+                                                         int h, int w, t16* __restrict__ qt, float* __restrict__ qbias,
+                                                         float* __restrict__ mseed) {
+  pdl_prologue();
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= p.HW) return;
+  const int sub = lane >> 3, part = lane & 7;
+  float qv[16];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + (long long)i * ldq + part * 16);
+    const uint4 a = qp[0], b = qp[1];
+    const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t r[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 f = unpack2(u[c]);
+      const float x0 = f.x + (pe_cur ? pe_cur[part * 16 + 2 * c] : 0.f);
+      const float x1 = f.y + (pe_cur ? pe_cur[part * 16 + 2 * c + 1] : 0.f);
+      r[c] = pack2(x0, x1);
+      const float2 g = unpack2(r[c]);
+      qv[2 * c] = g.x; qv[2 * c + 1] = g.y;
+    }
+    if (sub == 0) {
+      uint4* op = reinterpret_cast<uint4*>(qt + (long long)i * DK + part * 16);
+      op[0] = make_uint4(r[0], r[1], r[2], r[3]);
+      op[1] = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+  }
+  const int y = i / w, x = i - y * w;
+  float best = -INFINITY;
+  for (int r0 = 0; r0 < p.T; r0 += 4) {                   // uniform trip count: the shuffles below need the whole warp
+    const int t = r0 + sub;
+    const bool live = t < p.T;
+    float bs = 0.f;
+    if (live) {
+      const float4* pm = reinterpret_cast<const float4*>(pe_mem + (long long)ps.s[t] * DK + part * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 e = pm[c];
+        bs = fmaf(qv[4 * c], e.x, bs); bs = fmaf(qv[4 * c + 1], e.y, bs);
+        bs = fmaf(qv[4 * c + 2], e.z, bs); bs = fmaf(qv[4 * c + 3], e.w, bs);
+      }
+    }
+    bs += __shfl_xor_sync(0xffffffffu, bs, 1);
+    bs += __shfl_xor_sync(0xffffffffu, bs, 2);
+    bs += __shfl_xor_sync(0xffffffffu, bs, 4);
+    const float bias = bs * scale;
+    if (live && part == 0) qbias[(long long)i * p.T + t] = bias;
+    uint4 ka[9], kb[9];
+    bool ok[9];
+    const t16* kf = kbank + ((long long)(live ? p.slot[t] : 0) * p.HWp) * DK + part * 16;
+#pragma unroll
+    for (int nb = 0; nb < 9; ++nb) {
+      const int yy = y + nb / 3 - 1, xx = x + nb % 3 - 1;
+      ok[nb] = live && yy >= 0 && yy < h && xx >= 0 && xx < w;
+      if (ok[nb]) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kf + (long long)(yy * w + xx) * DK);
+        ka[nb] = kp[0];
+        kb[nb] = kp[1];
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < 9; ++nb) {
+      float sc = 0.f;
+      if (ok[nb]) {
+        const uint32_t u[8] = {ka[nb].x, ka[nb].y, ka[nb].z, ka[nb].w, kb[nb].x, kb[nb].y, kb[nb].z, kb[nb].w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float2 f = unpack2(u[c]); sc = fmaf(qv[2 * c], f.x, sc); sc = fmaf(qv[2 * c + 1], f.y, sc); }
+      }
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (ok[nb]) best = fmaxf(best, fmaf(sc, p.scale_log2, bias * LOG2E));
+    }
+  }
+  best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 8));
+  best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
+  if (lane == 0) mseed[i] = best;
+}
+
 int sm_count3() {
   static int n = 0;
   if (!n) {
@@ -934,6 +1022,23 @@ size_t long_attn_tc3_workspace(int HW, int HWp, int nslots, int Dv) {
   return best;
 }
 
+int qprep_seed_tc3(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
+                   float scale, const t16* kbank, const int* slot, int HW, int HWp, int h, int w, t16* qt, float* qbias,
+                   float* mseed, cudaStream_t s) {
+  RMEM_REQUIRE(T >= 1 && T <= kMaxBankFrames && h * w == HW, "qprep_seed: T=%d grid %dx%d HW=%d", T, h, w, HW);
+  RMEM_REQUIRE(ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(qt) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(pe_mem) & 15) == 0, "qprep_seed: alignment");
+  Tc3Params p = {};
+  p.HW = HW; p.HWp = HWp; p.T = T;
+  p.scale_log2 = scale * LOG2E;
+  PeSlots3 ps;
+  for (int t = 0; t < kMaxBankFrames; ++t) { ps.s[t] = t < T ? pe_slot[t] : 0; p.slot[t] = t < T ? slot[t] : 0; }
+  RMEM_CUDA_CHECK(launch_pdl(qprep_seed_kernel, dim3(cdiv(HW, 8)), dim3(256), 0, s, q, ldq, pe_cur, pe_mem, ps, scale, kbank,
+                             p, h, w, qt, qbias, mseed));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
 int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   RMEM_REQUIRE(a.Dk == DK, "long_attn_tc3: Dk=%d (built for 128)", a.Dk);
   RMEM_REQUIRE(a.Dv % DVC == 0 && a.Dv <= 1024, "long_attn_tc3: Dv=%d must be a multiple of 256, <= 1024", a.Dv);
@@ -959,7 +1064,7 @@ int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
   p.part_ml = reinterpret_cast<float*>(ws + off_ml);
   p.pieces = a.mass ? reinterpret_cast<float*>(ws + off_pieces) : nullptr;
   float* mseed = reinterpret_cast<float*>(ws + off_seed);
-  p.mseed = a.seed_h > 0 ? mseed : nullptr;
+  p.mseed = a.mseed ? a.mseed : (a.seed_h > 0 ? mseed : nullptr);   // a.mseed: the caller ran qprep_seed_tc3
   p.rescales = g3_rescales;
 
   RMEM_REQUIRE((reinterpret_cast<uintptr_t>(a.qt) & 15) == 0, "long_attn_tc3: q alignment");
@@ -987,7 +1092,7 @@ int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
     RMEM_CUDA_CHECK(cudaFuncSetAttribute(long_attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_done = true;
   }
-  if (p.mseed) {
+  if (p.mseed && !a.mseed) {
     RMEM_CUDA_CHECK(launch_pdl(attn_seed_kernel, dim3(cdiv(a.HW, 8)), dim3(256), 0, s, a.qt, a.qbias, a.kbank, p,
                                a.seed_h, a.seed_w, mseed));
     RMEM_LAUNCH_CHECK();

@@ -200,6 +200,8 @@ struct rmem_engine {
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     { const char* e = getenv("RMEM_AUX_STREAM"); aux_on = !(e && e[0] == '0'); }
     { const char* e = getenv("RMEM_BRANCH_PAR"); branch_par = !(e && e[0] == '0'); }
+    { const char* e = getenv("RMEM_FUSED_SEED"); fused_seed = !(e && e[0] == '0'); }
+    { const char* e = getenv("RMEM_SELF_SEED"); self_seed = !(e && e[0] == '0'); }
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_ready, cudaEventDisableTiming));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_inline, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
@@ -234,7 +236,9 @@ struct rmem_engine {
   float* res;         // [HW,512] tgt || tgt_id residual stream
   t16 *attn_b, *dwo2;
   t16 *t_ln, *qt, *cu, *cu0, *attn_a, *dwo, *z, *qk, *vt_self, *u_self, *gpm_out, *idemb;
-  float *qbias, *rel, *rel_dev;
+  float *qbias, *rel, *rel_dev, *mseed;
+  bool self_seed = true;                   // RMEM_SELF_SEED=0: no seed pass for the T = 1 self-attention (A/B)
+  bool fused_seed = true;                  // RMEM_FUSED_SEED=0: separate qprep + attn_seed launches (A/B)
   t16 *d0, *d1, *d2;
   double* stats;
   uint8_t* label8;
@@ -334,6 +338,7 @@ struct rmem_engine {
     qbias = a.take<float>((size_t)G.HW * kMaxBankFrames);
     rel = a.take<float>((size_t)G.HW * 256);
     rel_dev = a.take<float>(64);
+    mseed = a.take<float>((size_t)G.HW);
     d0 = a.take<t16>((size_t)G.P4 * 128);
     d1 = a.take<t16>((size_t)G.P4 * 128);
     d2 = a.take<t16>((size_t)G.P4 * 128);
@@ -560,9 +565,12 @@ struct rmem_engine {
     const float* lb = cfg.model == 0 ? Wt<float>("id_norm.b", kD, &rc) : nullptr;
     if (rc) return rc;
     RMEM_TRY(separate_label(label, label_is_f32, label8, G.H, G.W, gi, n_groups, s));
-    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s, pf, pr));
-    if (cfg.model == 0)
-      for (int l = 1; l < kLayers; ++l) RMEM_TRY(copy2d_t16(idemb, kD, gr.L[l].cat + kD, 2 * kD, G.HW, kD, s));
+    // DeAOT: layers 1 and 2 read the embedding as the second half of their linear_ID_V input (L.cat): written by the same
+    // launch instead of two copies
+    t16* o2 = cfg.model == 0 ? gr.L[1].cat + kD : nullptr;
+    t16* o3 = cfg.model == 0 ? gr.L[2].cat + kD : nullptr;
+    RMEM_TRY(idbank_embed(label8, G.H, G.W, use_ignore, w, b, lg, lb, idemb, kD, nullptr, G.h, G.w, kD, s, pf, pr, o2, o3,
+                          2 * kD));
     return RMEM_OK;
   }
 
@@ -593,8 +601,8 @@ struct rmem_engine {
     return RMEM_OK;
   }
 
-  int attention(LongAttnArgs& a, cudaStream_t s) {
-    a.seed_h = g.h; a.seed_w = g.w;      // token grid: tc3 seeds the row maximum from the query's own neighbourhood
+  int attention(LongAttnArgs& a, cudaStream_t s, bool seed = true) {
+    if (seed) { a.seed_h = g.h; a.seed_w = g.w; }   // token grid: tc3 seeds the row maximum from the query's own neighbourhood
     if (cfg.attn_impl == RMEM_ATTN_TC3) return long_attn_tc3(a, attn_ws, attn_ws_bytes, s);
     if (cfg.attn_impl == RMEM_ATTN_TC2) return long_attn_tc2(a, attn_ws, attn_ws_bytes, s);
     return long_attn_dense(a, attn_ws, attn_ws_bytes, s);
@@ -701,7 +709,13 @@ struct rmem_engine {
       if (rc) return rc;
       int pe_slot[kMaxBankFrames];
       temporal_pe_slots(T, 4, pe_slot);
-      RMEM_TRY(qprep(L.kc[cur], kDk, pc, pm, pe_slot, T, scale, qt, qbias, G.HW, kDk, s));
+      if (cfg.attn_impl == RMEM_ATTN_TC3 && fused_seed) {
+        RMEM_TRY(qprep_seed_tc3(L.kc[cur], kDk, pc, pm, pe_slot, T, scale, L.kbank, a.slot, G.HW, G.HWp, G.h, G.w, qt, qbias,
+                                mseed, s));
+        a.mseed = mseed;
+      } else {
+        RMEM_TRY(qprep(L.kc[cur], kDk, pc, pm, pe_slot, T, scale, qt, qbias, G.HW, kDk, s));
+      }
     }
     a.qt = qt; a.qbias = qbias;
     a.mass = (l == 0 && !ref_mode) ? gr.mass0 : nullptr;
@@ -778,7 +792,7 @@ struct rmem_engine {
       sa.qt = qk; sa.kbank = qk; sa.vtbank = vt_self; sa.nslots = 1; sa.T = 1; sa.slot[0] = 0;
       sa.gate = u_self; sa.ldg = kDv; sa.out = attn_a; sa.ldo = kDv;
       mark("gpm.self.proj", s);
-      RMEM_TRY(attention(sa, s));
+      RMEM_TRY(attention(sa, s, self_seed));
       mark("gpm.self.attn", s);
       RMEM_TRY(gated_tail(pre + ".self", s));
       mark("gpm.self.tail", s);
@@ -830,11 +844,13 @@ struct rmem_engine {
     RMEM_TRY(upsample_bilinear_t16(d1, d0, G.H8, G.W8, G.H4, G.W4, 128, s));
     RMEM_TRY(conv(feat4, G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, d0, d2, s));
     RMEM_TRY(conv(d2, G.H4, G.W4, 128, "dec.conv_4x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
-    RMEM_TRY(gn("dec.conv_4x", d0, d1, G.P4, 128));
     const t16* wo = Wt<t16>("dec.conv_out.w", (size_t)11 * 128, &rc);
     const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);
+    const float* g4 = Wt<float>("dec.conv_4x.gn.g", 128, &rc);
+    const float* b4 = Wt<float>("dec.conv_4x.gn.b", 128, &rc);
     if (rc) return rc;
-    RMEM_TRY(conv_out_logits(d1, wo, bo, gr.logits4, G.P4, 128, 11, s));
+    // GroupNorm(8) + ReLU of the 1/4-resolution map folded into the conv_out kernel's tile load
+    RMEM_TRY(conv_out_gn_logits(d0, g4, b4, 8, stats, wo, bo, gr.logits4, G.P4, 128, 11, s));
     mark("decoder", s);
     return RMEM_OK;
   }

@@ -399,6 +399,87 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const t16* __restrict__ x
     if (o < Cout) out[(size_t)o * P + p] = acc[o] + b[o];
 }
 
+// Decoder tail in one launch: y = conv_out( relu( GroupNorm(x) ) ) -- fpn.py:62-67.  The GroupNorm statistics come from
+// gn_stats_kernel (`stats`, per-group sum / sum of squares in double); the normalised activation is rounded to t16 when
+// it is staged in shared memory, exactly what gn_apply_kernel would have stored; the logits equal the two-kernel path's
+// up to the fp32 summation order (two half-sums over the input channels instead of one chain) -- minus one 6.6 MB round
+// trip and one launch.  64 pixels per block, two threads per pixel (each takes half of the input channels, one shuffle to
+// add): 403 blocks at P4 = 25.8 k pixels instead of 202 single-warp-per-scheduler blocks.
+__global__ void __launch_bounds__(128) conv_out_gn_kernel(const t16* __restrict__ x, const t16* __restrict__ w,
+                                                          const float* __restrict__ b, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const double* __restrict__ stats,
+                                                          int G, float* __restrict__ out, int P, int Cin, int Cout) {
+  extern __shared__ __align__(16) unsigned char co_smem[];
+  float* sw = reinterpret_cast<float*>(co_smem);                 // [Cin / 8][16][8]
+  const int nch = Cin / 8, pitch = Cin * 2 + 16;
+  float* s_a = sw + (size_t)nch * 16 * 8;                        // [Cin] scale, [Cin] shift of the normalisation
+  float* s_b = s_a + Cin;
+  unsigned char* tile = reinterpret_cast<unsigned char*>(s_b + Cin);
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) {
+    const int o = i / Cin, c = i - o * Cin;
+    sw[((c >> 3) * 16 + o) * 8 + (c & 7)] = t2f(w[i]);
+  }
+  pdl_prologue();
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+    const int g = c / (Cin / G);
+    const double n = (double)P * (Cin / G);
+    const double mean = stats[g * 2] / n;
+    const double var = stats[g * 2 + 1] / n - mean * mean;
+    s_a[c] = (float)mean;                                        // same arithmetic as gn_apply_kernel
+    s_b[c] = rsqrtf(fmaxf((float)var, 0.f) + 1e-5f);
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * nch; i += blockDim.x) {
+    const int pix = i / nch, ch = i - pix * nch;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (p0 + pix < P) {
+      load8(x + (size_t)(p0 + pix) * Cin + ch * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = ch * 8 + k;
+        v[k] = fmaxf((v[k] - s_a[c]) * s_b[c] * gamma[c] + beta[c], 0.f);
+      }
+    }
+    uint4 u;
+    u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + (size_t)pix * pitch + ch * 16) = u;
+  }
+  __syncthreads();
+  const int pix = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int p = p0 + pix;
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+  const unsigned char* row = tile + (size_t)pix * pitch;
+  const int c_lo = half * (nch / 2), c_hi = c_lo + nch / 2;
+  for (int c8 = c_lo; c8 < c_hi; ++c8) {
+    const uint4 r = *reinterpret_cast<const uint4*>(row + c8 * 16);
+    const float2 a = unpack2(r.x), bb = unpack2(r.y), cc = unpack2(r.z), dd = unpack2(r.w);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      if (o < Cout) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[(c8 * 16 + o) * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sw[(c8 * 16 + o) * 8 + 4]);
+        acc[o] += a.x * w0.x + a.y * w0.y + bb.x * w0.z + bb.y * w0.w + cc.x * w1.x + cc.y * w1.y + dd.x * w1.z +
+                  dd.y * w1.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    const float other = __shfl_xor_sync(0xffffffffu, acc[o], 1);
+    acc[o] = half == 0 ? acc[o] + other : other + acc[o];          // low half of the channels first in both threads
+  }
+  if (half == 0 && p < P) {
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+      if (o < Cout) out[(size_t)o * P + p] = acc[o] + b[o];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void transpose_kernel(const t16* __restrict__ x, long long ldx, t16* __restrict__ y, long long ldy, int P,
                                  int C) {
@@ -469,7 +550,8 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
                               const float* __restrict__ wp, const float* __restrict__ prefix,
                               const float* __restrict__ prefix_rows, const float* __restrict__ bias,
                               const float* __restrict__ ln_g, const float* __restrict__ ln_b, t16* __restrict__ out,
-                              long long ldo, float* __restrict__ out_f32, int w, int C) {
+                              long long ldo, float* __restrict__ out_f32, int w, int C, t16* __restrict__ out2,
+                              t16* __restrict__ out3, long long ldo23) {
   pdl_prologue();
   __shared__ int8_t ch[17 * 17];
   __shared__ float red[32];
@@ -629,6 +711,8 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
   }
   if (c < C) {
     if (out) out[(long long)tok * ldo + c] = f2t(o);
+    if (out2) out2[(long long)tok * ldo23 + c] = f2t(o);       // the same embedding, written where later layers read it
+    if (out3) out3[(long long)tok * ldo23 + c] = f2t(o);
     if (out_f32) out_f32[(long long)tok * C + c] = o;
   }
 }
@@ -1096,6 +1180,21 @@ int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int 
   return RMEM_OK;
 }
 
+int conv_out_gn_logits(const t16* x, const float* gamma, const float* beta, int G, double* stats, const t16* w,
+                       const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s) {
+  RMEM_REQUIRE(Cin % 32 == 0 && Cin <= 128 && Cout <= 16 && (Cin / 8) % 2 == 0, "conv_out_gn: unsupported Cin=%d Cout=%d", Cin, Cout);
+  RMEM_REQUIRE(G <= 32 && Cin % G == 0 && (Cin / G) % 8 == 0 && 256 % (Cin / 8) == 0, "conv_out_gn: unsupported C=%d G=%d", Cin, G);
+  const int rows_per_block = 256 / (Cin / 8);
+  const int grid = min(cdiv(P, rows_per_block), kGnMaxBlocks);
+  RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<t16>, dim3(grid), dim3(256), 0, s, x, P, Cin, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
+  RMEM_LAUNCH_CHECK();
+  const size_t smem = (size_t)(Cin / 8) * 16 * 8 * sizeof(float) + (size_t)2 * Cin * sizeof(float) + (size_t)64 * (Cin * 2 + 16);
+  RMEM_CUDA_CHECK(launch_pdl(conv_out_gn_kernel, dim3(cdiv(P, 64)), dim3(128), smem, s, x, w, b, gamma, beta,
+                             static_cast<const double*>(stats), G, out, P, Cin, Cout));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
 int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s) {
   dim3 grid(cdiv(P, 64), cdiv(C, 64)), block(32, 8);
   RMEM_CUDA_CHECK(launch_pdl(transpose_kernel, dim3(grid), dim3(block), 0, s, x, ldx, y, ldy, P, C));
@@ -1126,10 +1225,10 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
-                 cudaStream_t s, const float* prefix, const float* prefix_rows) {
+                 cudaStream_t s, const float* prefix, const float* prefix_rows, t16* out2, t16* out3, long long ldo23) {
   RMEM_REQUIRE(C <= 256 && C % 32 == 0, "idbank: unsupported C=%d", C);
   RMEM_REQUIRE(prefix || !prefix_rows, "idbank: the row-prefix table needs the 2-D prefix table as well");
-  RMEM_CUDA_CHECK(launch_pdl(idbank_kernel, dim3(h * w), dim3(256), 0, s, label, H, W, use_ignore, w_packed, prefix, prefix_rows, bias, ln_g, ln_b, out, ldo, out_f32, w, C));
+  RMEM_CUDA_CHECK(launch_pdl(idbank_kernel, dim3(h * w), dim3(256), 0, s, label, H, W, use_ignore, w_packed, prefix, prefix_rows, bias, ln_g, ln_b, out, ldo, out_f32, w, C, out2, out3, ldo23));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -50,6 +50,9 @@ int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int 
 
 // 1x1 conv to the 11 ID logits, planar fp32 output [11, P].                                (fpn.py:66)
 int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
+// out = conv_out(relu(GroupNorm_G(x))) in two launches (statistics, fused normalise + 1x1 conv): the decoder tail, fpn.py:62-67
+int conv_out_gn_logits(const t16* x, const float* gamma, const float* beta, int G, double* stats, const t16* w,
+                       const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
 
 // [P, C] (row stride ldx) -> [C, ldy] transposed copy.
 int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s);
@@ -68,7 +71,8 @@ int separate_label(const void* label, int label_is_f32, uint8_t* out, int H, int
 // of uniform class be a 4-read rectangle sum.
 int idbank_embed(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
                  const float* ln_g, const float* ln_b, t16* out, long long ldo, float* out_f32, int h, int w, int C,
-                 cudaStream_t s, const float* prefix = nullptr, const float* prefix_rows = nullptr);
+                 cudaStream_t s, const float* prefix = nullptr, const float* prefix_rows = nullptr,
+                 t16* out2 = nullptr, t16* out3 = nullptr, long long ldo23 = 0);
 
 // Mask head (aot_engine.py:457-463, 650-673; evaluator.py:430-441): k engines' planar logits [11,h4,w4] ->
 // bilinear(align_corners=True) -> soft aggregation -> out_logits [1+10k, Ho, Wo] (optional) and uint8 label.
