@@ -20,8 +20,11 @@ SOURCES = ["capi.cu", "gemm.cu", "gemm_tc.cu", "tma.cu", "ops.cu", "attn_dense.c
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
-# --use_fast_math only affects non-parity-critical kernels: the mask head / bilinear paths use explicit
-# __fmul_rn/__fadd_rn/__fdiv_rn and expf is called where exactness matters (see ops.cu).
+# --use_fast_math (approximate exp / log / division, FTZ) is for the tensor-core kernels, whose exponentials are MUFU ex2
+# by design.  ops.cu holds the mask head, the soft aggregation, evict_rel and the TTA head, whose softmax / logit / argmax
+# arithmetic must be the reference's IEEE fp32 (expf, logf, exact division next to the explicit _rn operations): it is
+# compiled WITHOUT the flag.
+EXACT_MATH = {"ops.cu"}
 
 
 def _digest() -> str:
@@ -33,6 +36,7 @@ def _digest() -> str:
     with open(os.path.join(HERE, "..", "include", "rmem_b200.h"), "rb") as fh:
         h.update(fh.read())
     h.update(" ".join(FLAGS).encode())
+    h.update(",".join(sorted(EXACT_MATH)).encode())
     return h.hexdigest()
 
 
@@ -47,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        flags = [f for f in FLAGS if not (src in EXACT_MATH and f == "--use_fast_math")]
+        cmd = [NVCC, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 

@@ -133,6 +133,10 @@ struct rmem_engine {
   // feat4/feat8/feat16/enc_tgt above always point at the set the current frame reads.
   t16 *feat4s[2], *feat8s[2], *feat16s[2];
   float* enc_tgts[2];
+  // The decoder's adapter convolutions (fpn.py:44,50,56: 1x1 convs of the ENCODER features) do not depend on the memory
+  // state either: they are computed with the encoder (prefetch stream) and added by the decoder's GroupNorm / upsample
+  // kernels instead of sitting on the per-frame critical path as three more GEMM launches per object group.
+  t16 *ad16s[2], *ad8s[2], *ad4s[2], *ad16, *ad8, *ad4;
   int fslot = 0;
   // Independent GEMMs of one layer (U / ID_U next to QV, the self-attention projections, the three linear_ID_V of the
   // memory update) are forked onto a second engine-owned stream: each is a ~3 us kernel behind ~5 us of launch latency.
@@ -185,7 +189,10 @@ struct rmem_engine {
   long long pf_seq[2] = {0, 0}, pf_counter = 0;
   int pf_age[2] = {0, 0};                  // features() calls since the prefetch was issued (a live entry is consumed at <= 1)
   int last_enc_slot = -1;                  // last slot encoded on enc_stream (its event orders the encoder temporaries)
-  void use_slot(int sl) { fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl]; }
+  void use_slot(int sl) {
+    fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl];
+    ad16 = ad16s[sl]; ad8 = ad8s[sl]; ad4 = ad4s[sl];
+  }
   int init_streams() {
     // Stream priorities were measured and do not help (c3, 1.335 ms per frame with equal priorities): a low-priority
     // prefetch stream under a high-priority caller stream loses the overlap altogether (1.52 ms), a high-priority second
@@ -317,6 +324,9 @@ struct rmem_engine {
       feat8s[sl] = a.take<t16>((size_t)G.P8 * 512);
       feat16s[sl] = a.take<t16>((size_t)G.HW * 1024);
       enc_tgts[sl] = a.take<float>((size_t)G.HW * kD);
+      ad16s[sl] = a.take<t16>((size_t)G.HW * 256);
+      ad8s[sl] = a.take<t16>((size_t)G.P8 * 256);
+      ad4s[sl] = a.take<t16>((size_t)G.P4 * 128);
     }
     use_slot(0);
     res = a.take<float>((size_t)G.HW * 2 * kD);
@@ -550,6 +560,10 @@ struct rmem_engine {
     p.C = enc_tgts[sl]; p.ldc = kD; p.c_fp32 = 1;
     RMEM_TRY(linear(p, s));
     mark("enc.proj", s);
+    RMEM_TRY(conv(feat16s[sl], G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, nullptr, ad16s[sl], s));
+    RMEM_TRY(conv(feat8s[sl], G.H8, G.W8, 512, "dec.adapter_8x", 256, 1, 1, 0, ACT_NONE, nullptr, ad8s[sl], s));
+    RMEM_TRY(conv(feat4s[sl], G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, nullptr, ad4s[sl], s));
+    mark("enc.adapters", s);
     return RMEM_OK;
   }
 
@@ -825,24 +839,22 @@ struct rmem_engine {
   int fpn_decode(Group& gr, const t16* x16, int cin, cudaStream_t s) {
     const Geo& G = g;
     int rc = RMEM_OK;
-    auto gn = [&](const std::string& n, const t16* x, t16* y, int P, int C) -> int {
+    auto gn = [&](const std::string& n, const t16* x, t16* y, int P, int C, const t16* add) -> int {
       int r2 = RMEM_OK;
       const float* gg = Wt<float>(n + ".gn.g", C, &r2);
       const float* gb = Wt<float>(n + ".gn.b", C, &r2);
       if (r2) return r2;
-      return groupnorm_t16(x, gg, gb, y, P, C, 8, 1, stats, s);
+      return groupnorm_t16(x, gg, gb, y, P, C, 8, 1, stats, s, add);
     };
+    // x = adapter(feature) + x at every scale: the adapter maps (ad16 / ad8 / ad4) were computed with the encoder
     RMEM_TRY(conv(x16, G.h, G.w, cin, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s));
-    RMEM_TRY(gn("dec.conv_in", d0, d1, G.HW, 256));
-    RMEM_TRY(conv(feat16, G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, d1, d0, s));
-    RMEM_TRY(conv(d0, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s));
-    RMEM_TRY(gn("dec.conv_16x", d2, d1, G.HW, 256));
-    RMEM_TRY(upsample_bilinear_t16(d1, d0, G.h, G.w, G.H8, G.W8, 256, s));
-    RMEM_TRY(conv(feat8, G.H8, G.W8, 512, "dec.adapter_8x", 256, 1, 1, 0, ACT_NONE, d0, d2, s));
+    RMEM_TRY(gn("dec.conv_in", d0, d1, G.HW, 256, ad16));                          // relu(GN(conv_in)) + adapter_16x(feat16)
+    RMEM_TRY(conv(d1, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s));
+    RMEM_TRY(gn("dec.conv_16x", d2, d1, G.HW, 256, nullptr));
+    RMEM_TRY(upsample_bilinear_t16(d1, d2, G.h, G.w, G.H8, G.W8, 256, s, ad8));    // up(x) + adapter_8x(feat8)
     RMEM_TRY(conv(d2, G.H8, G.W8, 256, "dec.conv_8x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
-    RMEM_TRY(gn("dec.conv_8x", d0, d1, G.P8, 128));
-    RMEM_TRY(upsample_bilinear_t16(d1, d0, G.H8, G.W8, G.H4, G.W4, 128, s));
-    RMEM_TRY(conv(feat4, G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, d0, d2, s));
+    RMEM_TRY(gn("dec.conv_8x", d0, d1, G.P8, 128, nullptr));
+    RMEM_TRY(upsample_bilinear_t16(d1, d2, G.H8, G.W8, G.H4, G.W4, 128, s, ad4));  // up(x) + adapter_4x(feat4)
     RMEM_TRY(conv(d2, G.H4, G.W4, 128, "dec.conv_4x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
     const t16* wo = Wt<t16>("dec.conv_out.w", (size_t)11 * 128, &rc);
     const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);

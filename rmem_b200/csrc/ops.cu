@@ -205,7 +205,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int P, int C, int G, do
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, t16* __restrict__ y, int P, int C, int G, int relu,
-                                const double* __restrict__ stats) {
+                                const double* __restrict__ stats, const t16* __restrict__ add) {
   pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,6 +225,12 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict
     float o = (v[k] - fm) * rstd * gamma[c] + beta[c];
     v[k] = relu == 1 ? fmaxf(o, 0.f) : (relu == 2 ? 0.5f * o * (1.f + erff(o * 0.70710678118654752f)) : o);
   }
+  if (add) {                                   // e.g. the FPN adapter branch, added to the normalised + activated map
+    float a[8];
+    load8(add + (size_t)r * C + col * 8, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += a[k];
+  }
   store8(y + (size_t)r * C + col * 8, v);
 }
 
@@ -232,7 +238,7 @@ constexpr int kGnMaxBlocks = 148 * 4;
 
 template <typename T>
 int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
-                   double* stats, cudaStream_t s) {
+                   double* stats, cudaStream_t s, const t16* add = nullptr) {
   RMEM_REQUIRE(C % 8 == 0 && G <= 32 && C % G == 0 && (C / G) % 8 == 0 && 256 % (C / 8) == 0,
                "groupnorm: unsupported C=%d G=%d", C, G);
   // scratch layout (doubles): [0,64) stats | [64] counter (zero-initialised once, self re-arming) | [72,..) partials
@@ -241,7 +247,7 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
   RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<T>, dim3(grid), dim3(256), 0, s, x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
   RMEM_LAUNCH_CHECK();
   long long nvec = (long long)P * (C / 8);
-  RMEM_CUDA_CHECK(launch_pdl(gn_apply_kernel<T>, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, s, x, gamma, beta, y, P, C, G, relu, stats));
+  RMEM_CUDA_CHECK(launch_pdl(gn_apply_kernel<T>, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, s, x, gamma, beta, y, P, C, G, relu, static_cast<const double*>(stats), add));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -253,7 +259,8 @@ int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, in
 // global ones, the 25 weight pairs in registers (fetched before the PDL wait: not produced by the preceding kernel).
 // fp32 accumulation in (ky, kx) order.  The register-only versions before it sat at ~13 us for 6.6 MB of traffic
 // (148 registers -> 2.4 waves of L2-latency-bound threads).
-constexpr int DW_TH = 8, DW_TW = 18;
+constexpr int DW_TH = 8;
+template <int DW_TW>
 __global__ void __launch_bounds__(256) dwconv5_kernel(const t16* __restrict__ x, int ldx, const float* __restrict__ w,
                                                       t16* __restrict__ y, int ldy, int h, int wd, int C) {
   __shared__ uint32_t tile[(DW_TH + 4) * (DW_TW + 4)][32];
@@ -329,7 +336,7 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
 }
 
 __global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__ y, int hin, int win, int hout,
-                                     int wout, int C) {
+                                     int wout, int C, const t16* __restrict__ add) {
   pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,6 +354,12 @@ __global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__
   load8(x + ((size_t)y1 * win + x1) * C + c8 * 8, d);
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = bilerp(a[k], b[k], c[k], d[k], wy0, wy1, wx0, wx1);
+  if (add) {                                   // FPN: adapter(feature) + upsample(x), fpn.py:50-60
+    float e[8];
+    load8(add + ((size_t)oy * wout + ox) * C + c8 * 8, e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] += e[k];
+  }
   store8(y + ((size_t)oy * wout + ox) * C + c8 * 8, o);
 }
 
@@ -1144,8 +1157,8 @@ int layernorm_pair(const float* x, long long ldx, const float* g0, const float* 
 }
 
 int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
-                   double* stats, cudaStream_t s) {
-  return groupnorm_impl<t16>(x, gamma, beta, y, P, C, G, relu, stats, s);
+                   double* stats, cudaStream_t s, const t16* add) {
+  return groupnorm_impl<t16>(x, gamma, beta, y, P, C, G, relu, stats, s, add);
 }
 int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s) {
@@ -1157,16 +1170,24 @@ int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaSt
   if (ldx <= 0) ldx = C;
   if (ldy <= 0) ldy = C;
   RMEM_REQUIRE(ldx % 2 == 0 && ldy % 2 == 0 && ldx >= C && ldy >= C, "dwconv: ldx=%d ldy=%d", ldx, ldy);
-  const dim3 grid(C / 64, cdiv(wd, DW_TW), cdiv(h, DW_TH));
-  RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel, grid, dim3(256), 0, s, x, ldx, w, y, ldy, h, wd, C));
+  // tile width: wider tiles re-read less halo, narrower ones give more blocks and a shorter serial chain per warp
+  // (RMEM_DW_TW = 6 | 9 | 18 | 27 for A/B; c3's 31 x 54 token grid: 576 / 384 / 192 / 128 blocks)
+  static const int tw = [] { const char* e = getenv("RMEM_DW_TW"); const int v = e ? atoi(e) : 18;
+                             return (v == 6 || v == 9 || v == 18 || v == 27) ? v : 18; }();
+  const dim3 grid(C / 64, cdiv(wd, tw), cdiv(h, DW_TH));
+  if (tw == 6) RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel<6>, grid, dim3(256), 0, s, x, ldx, w, y, ldy, h, wd, C));
+  else if (tw == 9) RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel<9>, grid, dim3(256), 0, s, x, ldx, w, y, ldy, h, wd, C));
+  else if (tw == 27) RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel<27>, grid, dim3(256), 0, s, x, ldx, w, y, ldy, h, wd, C));
+  else RMEM_CUDA_CHECK(launch_pdl(dwconv5_kernel<18>, grid, dim3(256), 0, s, x, ldx, w, y, ldy, h, wd, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
 
-int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s) {
+int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s,
+                          const t16* add) {
   RMEM_REQUIRE(C % 8 == 0, "upsample: C %% 8");
   long long n = (long long)hout * wout * (C / 8);
-  RMEM_CUDA_CHECK(launch_pdl(upsample_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, y, hin, win, hout, wout, C));
+  RMEM_CUDA_CHECK(launch_pdl(upsample_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, y, hin, win, hout, wout, C, add));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -23,8 +23,9 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
 // GroupNorm over (pixels x C/G) per group, eps 1e-5, optional ReLU.  `stats` = kGnScratchDoubles doubles of
 // scratch whose element [64] (the block counter) must be zero before the first call; it re-arms itself.
 constexpr int kGnScratchDoubles = 72 + 148 * 4 * 64;
+// `add` (optional, [P,C] t16): added to the normalised + activated map before the store
 int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
-                   double* stats, cudaStream_t s);
+                   double* stats, cudaStream_t s, const t16* add = nullptr);
 int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s);
 
@@ -46,7 +47,8 @@ int qprep_heads(const t16* q, long long ldq, const float* pe_cur, const float* p
 int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaStream_t s, int ldx = 0, int ldy = 0);
 
 // Bilinear resize, align_corners=True, NHWC t16.                                         (fpn.py:50,58)
-int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s);
+int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s,
+                          const t16* add = nullptr);   // add: optional [hout*wout, C] t16 added to the interpolated map
 
 // 1x1 conv to the 11 ID logits, planar fp32 output [11, P].                                (fpn.py:66)
 int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);

@@ -18,6 +18,10 @@ CASES = {
     "c2_aotl_480p_1obj_T4": ("r50_aotl", 481, 849, 1, 1, 3, 7, 2.0),
     "c3_deaotl_480p_10obj_T8": ("r50_deaotl", 481, 849, 10, 1, 7, 11, 4.0),
     "c4_deaotl_720p_30obj_3engines": ("r50_deaotl", 721, 1281, 30, 1, 2, 5, 4.0),
+    # the bank depths BASELINE.json / the shipped eval script name: c4 at T = 8 (bank full + one eviction), c3 at
+    # T = 9 (LATTER_MEM_LEN = 8, eval_vost.sh)
+    "c4_deaotl_720p_30obj_3engines_T8": ("r50_deaotl", 721, 1281, 30, 1, 7, 10, 4.0),
+    "c3_deaotl_480p_10obj_T9": ("r50_deaotl", 481, 849, 10, 1, 8, 12, 4.0),
 }
 
 
