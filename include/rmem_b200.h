@@ -205,8 +205,12 @@ typedef struct rmem_engine_config {
    *   time_encode     TIME_ENCODE[_NORM] (aot_engine.py:293-303, 413-421): accepted and ignored -- at inference both leave
    *                   every output of the unmodified reference bit-identical (the reverse pass only feeds a training loss,
    *                   the sin/cos encoding is stored and never read); checked by oracle/make_golden.py, tests/golden/knobs.json.
-   *   GRU_MEMORY (ConvGRU condensation of evicted frames, transformer.py:35-119, 420-430) is not built: no shipped
-   *   checkpoint carries its weights; rmem_engine_create refuses gru_memory != 0. */
+   *   gru_memory      GRU_MEMORY (transformer.py:35-119, 337-338, 395-396, 406-430; model 1 = R50_AOTL only -- DualBranchGPM
+   *                   hard-codes gru_memory = False, :728): on every eviction the dropped frame's K / V memories of each layer
+   *                   go through that layer's ConvGRU cells (K: 2x2, V: 1x1, padding "same"; fp32 hidden state, zeroed by
+   *                   add_reference_frame) and the cells' outputs replace bank position 1, which like position 0 is never
+   *                   dropped.  Needs the `lstt.<l>.gru.<i>.{gates,can,out}` weights (LSTT.layers.<l>.memory_grus.<i>.* of a
+   *                   checkpoint trained with GRU_MEMORY); refused for model 0.  Golden: tests/golden/aot_gru_memory.npz. */
   int no_long_memory, reverse_infer, time_encode, gru_memory;
 } rmem_engine_config;
 

@@ -141,12 +141,15 @@ CASES = {
     "aot_c1_256_t1": ("r50_aotl", 3, 1.0, 257, 257, 1, 3, 1, 1, 9999, (256, 256)),
     # AOT + RMem: restricted bank (1 + 2), eviction active, sharpened attention
     "aot_small_rmem": ("r50_aotl", 4, 4.0, 193, 257, 3, 11, 1, 2, 2, (193, 257)),
+    # GRU_MEMORY ablation (r50_aotl only): bank 1 + 3, an eviction with ConvGRU condensation on every frame
+    # from the fifth on (the ConvGRU weights come from make_state_dict(..., gru_memory=True))
+    "aot_gru_memory": ("r50_aotl", 5, 4.0, 193, 257, 3, 13, 1, 3, 1, (193, 257), {"GRU_MEMORY": True}),
 }
 
 
 def check_knobs():
     import numpy as np
-    model, seed, sharpen, H, W, n_obj, nfr, former, latter, gap, out_size = CASES[KNOB_CASE]
+    model, seed, sharpen, H, W, n_obj, nfr, former, latter, gap, out_size = CASES[KNOB_CASE][:11]
     sd = O.make_state_dict(model, seed=seed, sharpen=sharpen)
     frames = O.synthetic_frames(nfr, H, W, seed=seed + 1)
     label0 = O.synthetic_label(H, W, n_obj)
@@ -189,15 +192,18 @@ def main():
     torch.set_num_threads(8)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     only = sys.argv[1:]
-    for name, (model, seed, sharpen, H, W, n_obj, nfr, former, latter, gap, out_size) in CASES.items():
+    for name, case in CASES.items():
+        model, seed, sharpen, H, W, n_obj, nfr, former, latter, gap, out_size = case[:11]
+        knobs = case[11] if len(case) > 11 else {}
+        gru = bool(knobs.get("GRU_MEMORY", False))
         if only and name not in only:
             continue
-        sd = O.make_state_dict(model, seed=seed, sharpen=sharpen)
+        sd = O.make_state_dict(model, seed=seed, sharpen=sharpen, gru_memory=gru)
         frames = O.synthetic_frames(nfr, H, W, seed=seed + 1)
         label0 = O.synthetic_label(H, W, n_obj)
-        net, eng = build_reference(model, sd, former, latter, gap)
+        net, eng = build_reference(model, sd, former, latter, gap, knobs)
         ref = run_reference_clip(eng, frames, label0, n_obj, out_size)
-        cfg = O.OracleConfig(model=model, former_mem_len=former, latter_mem_len=latter)
+        cfg = O.OracleConfig(model=model, former_mem_len=former, latter_mem_len=latter, gru_memory=gru)
         ref_labels = torch.stack([l[0, 0] for l in ref["labels"]])                # uint8 [F-1,Ho,Wo]
         orc, oeng = run_oracle_clip(sd, cfg, gap, frames, label0, n_obj, out_size, forced_labels=ref_labels)
 
@@ -218,6 +224,8 @@ def main():
         meta = dict(case=name, model=model, seed=seed, sharpen=sharpen, H=H, W=W, n_obj=n_obj, n_frames=nfr,
                     former=former, latter=latter, gap=gap, out_size=list(out_size), idx=ref["idx"],
                     keep=keep, reference_commit="431cde18", torch=torch.__version__)
+        if knobs:
+            meta["knobs"] = knobs
         arrays = dict(
             labels=ref_labels.numpy(),
             # strided sample of every frame's 1/4-res logits (engine 0), fp32

@@ -56,6 +56,7 @@ class OracleConfig:
     former_mem_len: int = 1
     latter_mem_len: int = 8             # shipped setting (configs/models/r50_deaotl.py:8); the T=8 workloads pass 7
     no_long_memory: bool = False        # NO_LONG_MEMORY (configs/models/r50_deaotl.py:20, aot_engine.py:339)
+    gru_memory: bool = False            # GRU_MEMORY (r50_aotl only): ConvGRU condensation of evicted frames into bank slot 1
     d_model: int = 256                  # MODEL_ENCODER_EMBEDDING_DIM
     n_layers: int = 3                   # MODEL_LSTT_NUM
     max_obj: int = MAX_OBJ
@@ -325,9 +326,10 @@ class EvictState:
     times: Dict[int, int] = field(default_factory=dict)
 
 
-def evict_pick(rel: Tensor, idx: List[int], st: EvictState, former: int) -> int:
-    """transformer.py:907-964.  rel [T_old] fp32 relevance, idx = long_memories_indexes AFTER the
-    append (len T_old+1).  Updates st in place and returns the logical index to drop."""
+def evict_pick(rel: Tensor, idx: List[int], st: EvictState, former: int, gru: bool = False) -> int:
+    """transformer.py:907-964 (AOT twin :354-411).  rel [T_old] fp32 relevance, idx = long_memories_indexes AFTER the
+    append (len T_old+1).  Updates st in place and returns the logical index to drop.
+    gru (GRU_MEMORY, :337-338, 395-396, 406-411): bank position 1 holds the condensed memory and is never dropped either."""
     T_old = rel.numel()
     rel = rel.clone().float()
     new_ema = {}
@@ -341,12 +343,29 @@ def evict_pick(rel: Tensor, idx: List[int], st: EvictState, former: int) -> int:
     st.times = {f: 1 + st.times.get(f, 0) for f in idx}
     tt = torch.tensor([float(st.times[f]) for f in idx[:-1]], dtype=torch.float32)
     tt[0] = float(len(tt))
+    if gru and len(tt) > 1:
+        tt[1] = float(len(tt))
     bonus = UCB_MUL * torch.sqrt(torch.log(tt.sum()) / (tt + UCB_ADD))
     score = rel + bonus
-    drop = former
-    if score.numel() > 1:
-        drop = int(torch.argmin(score[1:]).item()) + 1
+    skip = 2 if gru else 1
+    drop = former + (1 if gru else 0)
+    if score.numel() > skip:
+        drop = int(torch.argmin(score[skip:]).item()) + skip
     return drop
+
+
+def conv_gru(sd, p: str, x: Tensor, h_cur: Tensor) -> Tuple[Tensor, Tensor]:
+    """ConvGRUCellOutput.forward (transformer.py:84-118) on [1,C,h,w] maps: returns (h_next, output_conv(h_next)).
+    padding = "same": the 2x2 kernel of the K cell pads one row / column at the bottom / right."""
+    C = h_cur.shape[1]
+    cc = F.conv2d(torch.cat([x, h_cur], 1), sd[p + ".conv_gru_cell.conv_gates.weight"],
+                  sd[p + ".conv_gru_cell.conv_gates.bias"], padding="same")
+    gamma, beta = torch.split(cc, C, dim=1)
+    reset, update = torch.sigmoid(gamma), torch.sigmoid(beta)
+    cnm = torch.tanh(F.conv2d(torch.cat([x, reset * h_cur], 1), sd[p + ".conv_gru_cell.conv_can.weight"],
+                              sd[p + ".conv_gru_cell.conv_can.bias"], padding="same"))
+    h_next = (1 - update) * h_cur + update * cnm
+    return h_next, F.conv2d(h_next, sd[p + ".output_conv.weight"], sd[p + ".output_conv.bias"])
 
 
 # --------------------------------------------------------------------------------------
@@ -369,6 +388,7 @@ class Bank:
     short_next: list = field(default_factory=list)               # AOT: [layer] [linear_QMem(o3), o3] of the last forward
     mass0: Optional[Tensor] = None                               # layer-0 [HW,T]
     evict: EvictState = field(default_factory=EvictState)
+    gru_h: list = field(default_factory=list)                    # GRU_MEMORY: [layer][K|V] hidden state [1,C,h,w]
 
 
 def fuse_id(sd, l: int, curr_ID_V: Optional[Tensor], id_emb: Tensor) -> Tensor:
@@ -600,6 +620,10 @@ class OracleSubEngine:
         oh = one_hot_with_ignore(mask, use_ignore=False)
         id_emb = id_embedding(self.sd, self.cfg, oh)
         self._lstt(feats, id_emb)
+        if self.cfg.gru_memory:                                   # init_memory (transformer.py:444-453, aot_engine.py:322)
+            h, w = self.hw
+            self.bank.gru_h = [[torch.zeros(1, self.cfg.d_model, h, w), torch.zeros(1, self.cfg.d_model, h, w)]
+                               for _ in range(3)]
         self.last_mem_step = frame_step
         self.long_memories_indexes.append(self.frame_step)
 
@@ -639,10 +663,15 @@ class OracleSubEngine:
             lg = F.interpolate(self.pred_id_logits, size=(h, w), mode="bilinear", align_corners=True)
             fg = 1 - torch.softmax(lg, dim=1)[0, 0].flatten()     # aot_engine.py:355-362
             rel = evict_scores(bank.mass0, fg)
-            drop = evict_pick(rel, self.long_memories_indexes, bank.evict, cfg.former_mem_len)
+            drop = evict_pick(rel, self.long_memories_indexes, bank.evict, cfg.former_mem_len, gru=cfg.gru_memory)
             self.last_rel, self.last_drop = rel, drop
             if len(bank.long[0]) > cfg.former_mem_len + cfg.latter_mem_len:
                 for l in range(3):
+                    if cfg.gru_memory:                            # transformer.py:420-430: the dropped frame goes through
+                        for i, nm in enumerate(("K", "V")):       # the layer's ConvGRU, its output replaces bank entry 1
+                            x = tokens_to_map(getattr(bank.long[l][drop], nm), h, w)
+                            bank.gru_h[l][i], out = conv_gru(sd, f"LSTT.layers.{l}.memory_grus.{i}", x, bank.gru_h[l][i])
+                            setattr(bank.long[l][1], nm, out.flatten(2)[0].t().contiguous())
                     del bank.long[l][drop]
                 self.long_memories_indexes.pop(drop)
 

@@ -23,7 +23,7 @@ const char* get_error() { return g_err; }
 long long& launch_counter() { return g_launches; }
 
 int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former, std::map<int, float>& ema,
-                    std::map<int, int>& times, int* drop, float* rel_norm_out);
+                    std::map<int, int>& times, int* drop, float* rel_norm_out, bool gru = false);
 
 }  // namespace rmem
 

@@ -29,7 +29,7 @@
 namespace rmem {
 
 int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former, std::map<int, float>& ema,
-                    std::map<int, int>& times, int* drop, float* rel_norm_out);
+                    std::map<int, int>& times, int* drop, float* rel_norm_out, bool gru = false);
 
 namespace {
 
@@ -87,6 +87,7 @@ struct LayerStateA {  // AOT (SimplifiedTransformerBlock) per-layer memories, tr
   t16* sv[2];       // [HW,256]   short-term V = linear_VMem(o3 + id)
   t16* kbank;       // [nslots][HWp][256]
   t16* vtbank;      // [256][nslots*HWp]
+  float* gru_h[2];  // GRU_MEMORY: fp32 hidden state of the K / V ConvGRU [HW,256] (zeroed per clip with the state region)
 };
 
 struct Group {       // one AOTEngine: <= 10 objects, own bank (reference + per-engine deepcopy)
@@ -158,7 +159,7 @@ struct rmem_engine {
   cudaEvent_t ev_rel[4] = {nullptr, nullptr, nullptr, nullptr};
   // transformer.py:891-964 on the host, run lazily: waits for the T floats of the last append (normally long complete),
   // then EMA / UCB / argmin and the slot-table edit exactly as before.
-  int resolve_evict(int gi) {
+  int resolve_evict(int gi, cudaStream_t s = nullptr) {
     Group& gr = groups[gi];
     if (!gr.evict_pending) return RMEM_OK;
     gr.evict_pending = false;
@@ -168,9 +169,10 @@ struct rmem_engine {
     int drop = cfg.former_mem_len;
     gr.last_rel.assign(T_old, 0.f);
     RMEM_TRY(evict_pick_host(rel_pinned + (size_t)gi * kMaxBankFrames, T_old, gr.long_idx.data(), cfg.former_mem_len, gr.ema,
-                             gr.times, &drop, gr.last_rel.data()));
+                             gr.times, &drop, gr.last_rel.data(), cfg.gru_memory != 0));
     gr.last_drop = drop;
     if ((int)gr.slots.size() > cap) {
+      if (cfg.gru_memory) RMEM_TRY(gru_condense(gr, drop, s));   // GRU_MEMORY resolves inside update_memory (stream known)
       gr.free_slots.push_back(gr.slots[drop]);
       gr.slots.erase(gr.slots.begin() + drop);
       gr.long_idx.erase(gr.long_idx.begin() + drop);
@@ -261,6 +263,9 @@ struct rmem_engine {
   t16 *a_tln, *a_qkpos, *a_q, *a_k, *a_vt, *a_att, *a_o3, *a_sum, *a_n4k, *a_n4v, *a_n4vt, *a_ff1, *a_ff2, *a_decin, *a_qt;
   void* mha_ws = nullptr;
   size_t mha_ws_bytes = 0;
+  // GRU_MEMORY scratch: [x | h] (then [x | reset*h]) t16, gates fp32 [HW,512], candidate fp32, token-major x / h / output
+  t16 *g_comb = nullptr, *g_x = nullptr, *g_h16 = nullptr, *g_out = nullptr;
+  float *g_gates = nullptr, *g_cand = nullptr;
   bool pos_ready = false;
   // optional stage timing (debug / profiling aid): CUDA events between pipeline stages, accumulated per name
   bool timing = false;
@@ -376,6 +381,14 @@ struct rmem_engine {
       mha_ws_bytes = cfg.attn_impl == RMEM_ATTN_DENSE ? mha_dense_workspace(G.HW, G.HWp, nslots, 8)
                                                       : mha_tc_workspace(G.HW, G.HWp, nslots, 8);
       mha_ws = a.take<char>(mha_ws_bytes);
+      if (cfg.gru_memory) {
+        g_comb = a.take<t16>((size_t)G.HW * 2 * kD);
+        g_gates = a.take<float>((size_t)G.HW * 2 * kD);
+        g_cand = a.take<float>((size_t)G.HW * kD);
+        g_x = a.take<t16>((size_t)G.HW * kD);
+        g_h16 = a.take<t16>((size_t)G.HW * kD);
+        g_out = a.take<t16>((size_t)G.HW * kD);
+      }
     }
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
     size_t ws_tc2 = long_attn_tc2_workspace(G.HW, G.HWp, nslots, kDv);
@@ -398,6 +411,7 @@ struct rmem_engine {
         }
         L.kbank = a.take<t16>((size_t)nslots * G.HWp * kD);
         L.vtbank = a.take<t16>((size_t)kD * nslots * G.HWp);
+        for (int i = 0; i < 2; ++i) L.gru_h[i] = cfg.gru_memory ? a.take<float>((size_t)G.HW * kD) : nullptr;
       }
       for (int l = 0; l < kLayers && cfg.model == 0; ++l) {
         LayerState& L = gr.L[l];
@@ -1041,6 +1055,64 @@ struct rmem_engine {
     return RMEM_OK;
   }
 
+  // GRU_MEMORY (transformer.py:420-430, AOT only): the frame about to be dropped goes through the layer's ConvGRU (K: 2x2,
+  // V: 1x1, padding "same" = one zero row / column at the bottom / right for the 2x2 kernel, which is what the implicit
+  // GEMM's out-of-bounds zero fill gives with pad = 0); the cell's output replaces bank position 1.
+  int conv_same(const t16* x, int Cin, const std::string& wname, int Cout, int k, float* out, cudaStream_t s) {
+    const Geo& G = g;
+    int rc = RMEM_OK;
+    const t16* w = Wt<t16>(wname + ".w", (size_t)Cout * k * k * Cin, &rc);
+    const float* b = Wt<float>(wname + ".b", Cout, &rc);
+    if (rc) return rc;
+    GemmParams p;
+    p.A = x; p.B = w; p.ldb = (long long)k * k * Cin;
+    p.M = G.HW; p.N = Cout; p.K = k * k * Cin;
+    if (k == 1) {
+      p.lda = Cin;
+    } else {
+      p.conv = 1; p.Hin = G.h; p.Win = G.w; p.Cin = Cin; p.Wout = G.w; p.kw = k; p.stride = 1; p.pad = 0;
+    }
+    p.bias = b;
+    p.C = out; p.ldc = Cout; p.c_fp32 = 1;
+    return gemm_launch(p, s);
+  }
+  int gru_condense(Group& gr, int drop, cudaStream_t s) {
+    const Geo& G = g;
+    RMEM_REQUIRE(drop >= 2 && drop < (int)gr.slots.size(), "GRU_MEMORY: drop index %d", drop);
+    const int ps_drop = gr.slots[drop], ps_one = gr.slots[1];
+    const long long ldv = (long long)nslots * G.HWp;
+    for (int l = 0; l < kLayers; ++l) {
+      LayerStateA& L = gr.A[l];
+      for (int i = 0; i < 2; ++i) {
+        const std::string pre = "lstt." + std::to_string(l) + ".gru." + std::to_string(i);
+        const int k = i == 0 ? 2 : 1;
+        const t16* x = L.kbank + (size_t)ps_drop * G.HWp * kD;
+        if (i == 1) {                                   // the V bank is value-major: back to token-major
+          RMEM_TRY(transpose_t16(L.vtbank + (size_t)ps_drop * G.HWp, ldv, g_x, kD, kD, G.HW, s));
+          x = g_x;
+        }
+        float* h = L.gru_h[i];
+        RMEM_TRY(copy2d_t16(x, kD, g_comb, 2 * kD, G.HW, kD, s));
+        RMEM_TRY(cvt_f32_t16(h, kD, g_comb + kD, 2 * kD, G.HW, kD, s));
+        RMEM_TRY(conv_same(g_comb, 2 * kD, pre + ".gates", 2 * kD, k, g_gates, s));
+        RMEM_TRY(gru_reset(g_gates, 2 * kD, h, g_comb + kD, 2 * kD, G.HW, kD, s));
+        RMEM_TRY(conv_same(g_comb, 2 * kD, pre + ".can", kD, k, g_cand, s));
+        RMEM_TRY(gru_blend(g_gates + kD, 2 * kD, g_cand, h, g_h16, G.HW, kD, s));
+        Lin p;
+        p.A = g_h16; p.lda = kD; p.M = G.HW; p.K = kD; p.N = kD; p.w = pre + ".out";
+        if (i == 0) {
+          p.C = L.kbank + (size_t)ps_one * G.HWp * kD; p.ldc = kD;
+          RMEM_TRY(linear(p, s));
+        } else {
+          p.C = g_out; p.ldc = kD;
+          RMEM_TRY(linear(p, s));
+          RMEM_TRY(transpose_t16(g_out, kD, L.vtbank + (size_t)ps_one * G.HWp, ldv, G.HW, kD, s));
+        }
+      }
+    }
+    return RMEM_OK;
+  }
+
   int frame_forward(Group& gr, bool ref_mode, cudaStream_t s) {
     return cfg.model == 1 ? lstt_decode_aot(gr, ref_mode, s) : lstt_decode(gr, ref_mode, s);
   }
@@ -1051,7 +1123,7 @@ namespace rmem {
 
 // transformer.py:907-964 -- EMA + UCB bonus + argmin, fp32 host arithmetic on T_old values.
 int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former, std::map<int, float>& ema,
-                    std::map<int, int>& times, int* drop, float* rel_norm_out) {
+                    std::map<int, int>& times, int* drop, float* rel_norm_out, bool gru) {
   float sum = 0.f;
   for (int t = 0; t < T_old; ++t) sum += rel_raw[t];
   std::vector<float> rel(T_old);
@@ -1082,12 +1154,14 @@ int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former,
   float tsum = 0.f;
   for (int t = 0; t < T_old; ++t) tt[t] = (float)times[idx[t]];
   tt[0] = (float)T_old;
+  if (gru && T_old > 1) tt[1] = (float)T_old;   // GRU_MEMORY: position 1 holds the condensed memory (transformer.py:395-396)
   for (int t = 0; t < T_old; ++t) tsum += tt[t];
   const float lg = logf(tsum);
-  int best = former;
-  if (T_old > 1) {
+  const int skip = gru ? 2 : 1;                  // positions never dropped (:406-411)
+  int best = former + (gru ? 1 : 0);
+  if (T_old > skip) {
     float bs = INFINITY;
-    for (int t = 1; t < T_old; ++t) {
+    for (int t = skip; t < T_old; ++t) {
       float q = lg / (tt[t] + 8.0f);
       float bonus = 1.5f * sqrtf(q);
       float score = ema[idx[t]] + bonus;
@@ -1107,7 +1181,10 @@ int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(cfg && bytes, "null argument");
   RMEM_REQUIRE(cfg->model == 0 || cfg->model == 1, "model %d: 0 = r50_deaotl, 1 = r50_aotl", cfg->model);
-  RMEM_REQUIRE(cfg->gru_memory == 0, "GRU_MEMORY (ConvGRU memory condensation) is not built");
+  RMEM_REQUIRE(cfg->gru_memory == 0 || cfg->model == 1,
+               "GRU_MEMORY exists for the AOT model only (DualBranchGPM hard-codes gru_memory = False, transformer.py:728)");
+  RMEM_REQUIRE(cfg->gru_memory == 0 || (cfg->former_mem_len == 1 && cfg->latter_mem_len >= 2),
+               "GRU_MEMORY keeps bank positions 0 and 1: former_mem_len must be 1 and latter_mem_len >= 2");
   RMEM_REQUIRE(cfg->attn_impl == RMEM_ATTN_DENSE || cfg->attn_impl == RMEM_ATTN_TC2 || cfg->attn_impl == RMEM_ATTN_TC3,
                "attn_impl %d: 0 = dense, 2 = tc2, 3 = tc3", cfg->attn_impl);
   RMEM_REQUIRE(cfg->H > 16 && cfg->W > 16 && (cfg->H - 1) % 16 == 0 && (cfg->W - 1) % 16 == 0,
@@ -1321,6 +1398,7 @@ int rmem_engine_update_memory(rmem_engine* e, const void* label, int label_is_f3
       RMEM_CUDA_CHECK(cudaEventRecord(e->ev_rel[gi], s));
       gr.evict_pending = true;
       gr.evict_T_old = T_old;
+      if (e->cfg.gru_memory) RMEM_TRY(e->resolve_evict(gi, s));   // the condensation kernels need this stream: no deferral
     }
     gr.parity ^= 1;   // current frame -> short-term memory
   }

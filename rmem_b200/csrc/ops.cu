@@ -730,6 +730,33 @@ __global__ void idbank_kernel(const uint8_t* __restrict__ label, int H, int W, i
   }
 }
 
+// GRU_MEMORY ablation (ConvGRUCell.forward, transformer.py:84-100), elementwise halves around the two convolutions:
+//   reset:  comb[:, C:2C] = t16( sigmoid(gates[:, 0:C]) * h )            (input of conv_can next to the unchanged x half)
+//   blend:  h = (1 - u) h + u tanh(cand),  u = sigmoid(gates[:, C:2C]);  h16 = t16(h)
+__global__ void gru_reset_kernel(const float* __restrict__ gates, long long ldg, const float* __restrict__ h,
+                                 t16* __restrict__ comb_h, long long ldc, int P, int C) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  const float g = gates[r * ldg + c];
+  const float reset = 1.f / (1.f + expf(-g));
+  comb_h[r * ldc + c] = f2t(reset * h[r * C + c]);
+}
+__global__ void gru_blend_kernel(const float* __restrict__ gates_u, long long ldg, const float* __restrict__ cand,
+                                 float* __restrict__ h, t16* __restrict__ h16, int P, int C) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  const float u = 1.f / (1.f + expf(-gates_u[r * ldg + c]));
+  const float hn = (1.f - u) * h[i] + u * tanhf(cand[i]);
+  h[i] = hn;
+  h16[i] = f2t(hn);
+}
+
 // ------------------------------------------------------------------------------------------------
 struct LogitPtrs { const float* p[4]; };
 
@@ -1212,6 +1239,19 @@ int conv_out_gn_logits(const t16* x, const float* gamma, const float* beta, int 
   const size_t smem = (size_t)(Cin / 8) * 16 * 8 * sizeof(float) + (size_t)2 * Cin * sizeof(float) + (size_t)64 * (Cin * 2 + 16);
   RMEM_CUDA_CHECK(launch_pdl(conv_out_gn_kernel, dim3(cdiv(P, 64)), dim3(128), smem, s, x, w, b, gamma, beta,
                              static_cast<const double*>(stats), G, out, P, Cin, Cout));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
+int gru_reset(const float* gates, long long ldg, const float* h, t16* comb_h, long long ldc, int P, int C, cudaStream_t s) {
+  const long long n = (long long)P * C;
+  RMEM_CUDA_CHECK(launch_pdl(gru_reset_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, gates, ldg, h, comb_h, ldc, P, C));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+int gru_blend(const float* gates_u, long long ldg, const float* cand, float* h, t16* h16, int P, int C, cudaStream_t s) {
+  const long long n = (long long)P * C;
+  RMEM_CUDA_CHECK(launch_pdl(gru_blend_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, gates_u, ldg, cand, h, h16, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -52,6 +52,9 @@ int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int 
 
 // 1x1 conv to the 11 ID logits, planar fp32 output [11, P].                                (fpn.py:66)
 int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
+// GRU_MEMORY ablation: the elementwise halves of ConvGRUCell.forward (transformer.py:84-100), fp32 hidden state
+int gru_reset(const float* gates, long long ldg, const float* h, t16* comb_h, long long ldc, int P, int C, cudaStream_t s);
+int gru_blend(const float* gates_u, long long ldg, const float* cand, float* h, t16* h16, int P, int C, cudaStream_t s);
 // out = conv_out(relu(GroupNorm_G(x))) in two launches (statistics, fused normalise + 1x1 conv): the decoder tail, fpn.py:62-67
 int conv_out_gn_logits(const t16* x, const float* gamma, const float* beta, int G, double* stats, const t16* w,
                        const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);

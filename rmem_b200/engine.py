@@ -40,7 +40,7 @@ class RmemConfig:
     no_long_memory: bool = False     # NO_LONG_MEMORY: the long-term bank stays at the reference frame
     reverse_infer: bool = False      # REVERSE_INFER: no effect at inference (training-loss pass only); accepted
     time_encode: bool = False        # TIME_ENCODE / TIME_ENCODE_NORM: no effect at inference (stored, never read); accepted
-    gru_memory: bool = False         # GRU_MEMORY: not built (refused)
+    gru_memory: bool = False         # GRU_MEMORY (r50_aotl only; needs the memory_grus weights in the state dict)
 
 
 MODEL_IDS = {"r50_deaotl": 0, "r50_aotl": 1}

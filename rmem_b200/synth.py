@@ -30,7 +30,7 @@ def _resnet_blocks():
 
 
 def make_state_dict(model: str = "r50_deaotl", seed: int = 0, sharpen: float = 1.0,
-                    dtype=torch.float32) -> Dict[str, Tensor]:
+                    dtype=torch.float32, gru_memory: bool = False) -> Dict[str, Tensor]:
     """Deterministic synthetic weights under the reference's state_dict names/shapes.
 
     Magnitudes follow the reference initialisers (resnet.py:197-205 He-normal convs,
@@ -160,6 +160,17 @@ def make_state_dict(model: str = "r50_deaotl", seed: int = 0, sharpen: float = 1
     sd["patch_wise_id_bank.bias"] = rand(d, lo=-1.0 / math.sqrt(fan), hi=1.0 / math.sqrt(fan)) * 0.01
     if model == "r50_deaotl":
         norm("id_norm", d)
+    if gru_memory:
+        # GRU_MEMORY ablation (transformer.py:35-119, 529-545; AOT only): per layer a ConvGRU for K (2x2) and V (1x1).
+        # Generated last, so the rest of the dict is identical to the default one of the same seed.
+        if model != "r50_aotl":
+            raise ValueError("GRU_MEMORY exists for r50_aotl only (DualBranchGPM hard-codes gru_memory = False)")
+        for l in range(3):
+            for i, k in ((0, 2), (1, 1)):
+                q = f"LSTT.layers.{l}.memory_grus.{i}"
+                conv(q + ".conv_gru_cell.conv_gates", 2 * d, 2 * d, k, bias=True, he=False)
+                conv(q + ".conv_gru_cell.conv_can", d, 2 * d, k, bias=True, he=False)
+                conv(q + ".output_conv", d, d, 1, bias=True, he=False)
     return sd
 
 

@@ -109,6 +109,13 @@ def pack_model(sd: Dict[str, torch.Tensor], model: str = "r50_deaotl") -> Dict[s
         w = sd[f"{p}.activation.conv.weight"]                               # [C,1,5,5]
         out[f"{q}.act.dw"] = w.view(w.shape[0], 25).t().contiguous()
         norm(f"lstt.dec_norm.{l}", f"LSTT.decoder_norms.{l}")
+        # GRU_MEMORY ablation (transformer.py:529-545): ConvGRU of the K (2x2) and V (1x1) memories, when the checkpoint has it
+        for i in (0, 1):
+            g = f"{p}.memory_grus.{i}"
+            if g + ".conv_gru_cell.conv_gates.weight" in sd:
+                conv(f"{q}.gru.{i}.gates", g + ".conv_gru_cell.conv_gates")
+                conv(f"{q}.gru.{i}.can", g + ".conv_gru_cell.conv_can")
+                linear(f"{q}.gru.{i}.out", g + ".output_conv")
 
     for l in range(3 if deaot else 0):
         p, q = f"LSTT.layers.{l}", f"gpm.{l}"

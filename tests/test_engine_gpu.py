@@ -37,14 +37,16 @@ def load_case(name):
 
 def run_engine_lockstep(meta, z, device, attn_impl=0):
     from rmem_b200.engine import RmemModel, RmemConfig, build_engine
-    sd = O.make_state_dict(meta["model"], seed=meta["seed"], sharpen=meta["sharpen"])
+    knobs = meta.get("knobs", {})
+    sd = O.make_state_dict(meta["model"], seed=meta["seed"], sharpen=meta["sharpen"],
+                           gru_memory=bool(knobs.get("GRU_MEMORY", False)))
     H, W, n_obj = meta["H"], meta["W"], meta["n_obj"]
     frames = O.synthetic_frames(meta["n_frames"], H, W, seed=meta["seed"] + 1)
     label0 = O.synthetic_label(H, W, n_obj)
-    knobs = meta.get("knobs", {})
     cfg = RmemConfig(model=meta["model"], former_mem_len=meta["former"], latter_mem_len=meta["latter"],
                      attn_impl=attn_impl, no_long_memory=bool(knobs.get("NO_LONG_MEMORY", False)),
-                     reverse_infer=bool(knobs.get("REVERSE_INFER", False)), time_encode=bool(knobs.get("TIME_ENCODE", False)))
+                     reverse_infer=bool(knobs.get("REVERSE_INFER", False)), time_encode=bool(knobs.get("TIME_ENCODE", False)),
+                     gru_memory=bool(knobs.get("GRU_MEMORY", False)))
     model = RmemModel(sd, cfg, device)
     eng = build_engine("deaotengine" if meta["model"] == "r50_deaotl" else "aotengine", phase="eval", aot_model=model,
                        gpu_id=0, long_term_mem_gap=meta["gap"])
@@ -114,10 +116,12 @@ def test_ablation_knobs_match_reference(cuda_device):
         e.add_reference_frame(torch.zeros(1, 3, 129, 161), torch.zeros(1, 1, 129, 161).int(), obj_nums=[1], frame_step=0)
 
 
-@pytest.mark.parametrize("name", ["aot_c1_256_t1", "aot_small_rmem"])
+@pytest.mark.parametrize("name", ["aot_c1_256_t1", "aot_small_rmem", "aot_gru_memory"])
 def test_aot_engine_matches_reference_goldens(cuda_device, name):
-    """R50_AOTL (+RMem): BASELINE.json configs[0] (c1) and a restricted-bank clip with eviction."""
+    """R50_AOTL (+RMem): BASELINE.json configs[0] (c1), a restricted-bank clip with eviction, and the GRU_MEMORY ablation
+    (ConvGRU condensation of every evicted frame into bank position 1, transformer.py:420-430) against its own golden."""
     test_engine_matches_reference_goldens(cuda_device, name, 0)
+    test_engine_matches_reference_goldens(cuda_device, name, 3)      # attn_impl != dense: the fused tcgen05 MHA kernel
 
 
 def test_engine_restart_is_deterministic(cuda_device):

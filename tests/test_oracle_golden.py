@@ -13,16 +13,17 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name", ["deaot_small_xavier", "deaot_13obj_2engines", "deaot_small_10obj",
-                                  "aot_c1_256_t1", "aot_small_rmem", "deaot_no_long_memory"])
+                                  "aot_c1_256_t1", "aot_small_rmem", "deaot_no_long_memory", "aot_gru_memory"])
 def test_oracle_reproduces_reference_goldens(name):
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 1))
     z = np.load(os.path.join(GOLD, name + ".npz"))
     meta = json.loads(str(z["meta"]))
-    sd = O.make_state_dict(meta["model"], seed=meta["seed"], sharpen=meta["sharpen"])
+    gru = bool(meta.get("knobs", {}).get("GRU_MEMORY", False))
+    sd = O.make_state_dict(meta["model"], seed=meta["seed"], sharpen=meta["sharpen"], gru_memory=gru)
     frames = O.synthetic_frames(meta["n_frames"], meta["H"], meta["W"], seed=meta["seed"] + 1)
     label0 = O.synthetic_label(meta["H"], meta["W"], meta["n_obj"])
     cfg = O.OracleConfig(model=meta["model"], former_mem_len=meta["former"], latter_mem_len=meta["latter"],
-                         no_long_memory=bool(meta.get("knobs", {}).get("NO_LONG_MEMORY", False)))
+                         no_long_memory=bool(meta.get("knobs", {}).get("NO_LONG_MEMORY", False)), gru_memory=gru)
     eng = O.OracleEngine(sd, cfg, long_term_mem_gap=meta["gap"])
     forced = torch.from_numpy(z["labels"])
     rec = dict(idx=[], logits4=[])
