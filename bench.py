@@ -34,7 +34,7 @@ METRIC = "VOS frames/sec @480p R50_DeAOTL+RMem T=8"
 # long-term attention algorithmic FLOPs per layer at c3 = 2*HW*(T*HW)*(Dk+Dv)
 HW_TOK = 31 * 54
 LT_FLOPS_PER_LAUNCH = 2.0 * HW_TOK * (8 * HW_TOK) * (128 + 1024)
-ATTN_IMPLS = {"dense": 0, "tc2": 2, "tc3": 3}
+ATTN_IMPLS = {"dense": 0, "tc2": 2, "tc3": 3, "tc4": 4}
 
 
 def peaks():
@@ -313,8 +313,8 @@ def measure_attention_roofline(eng, dev, args):
         launch(l)
     torch.cuda.synchronize()
     iters = 12                                                       # per layer
-    per_layer_k, per_layer_op = [], []
-    has_events = impl in (ATTN_IMPLS["tc2"], ATTN_IMPLS["tc3"])
+    per_layer_k, per_layer_op, fallback = [], [], []
+    has_events = impl in (ATTN_IMPLS["tc2"], ATTN_IMPLS["tc3"], ATTN_IMPLS["tc4"])
     for l in range(3):
         ks, ops = [], []
         for _ in range(iters):
@@ -335,10 +335,13 @@ def measure_attention_roofline(eng, dev, args):
                 ks.append(a.elapsed_time(b))
         per_layer_op.append(sorted(ops)[len(ops) // 2])
         per_layer_k.append(sorted(ks)[len(ks) // 2] if ks else per_layer_op[-1])
+        if args.attn == "tc4":                                       # did these operands leave the column kernel's fp16 range?
+            fallback.append(int(ws[:4].view(torch.int32).item()))
     ms = sum(per_layer_k) / 3
     ms_op = sum(per_layer_op) / 3
     ach = flops / (ms * 1e-3) / 1e12
-    kname = {"tc3": "long_attn_tc3_kernel", "tc2": "long_attn_tc2_kernel"}.get(args.attn, "long_term_attention op")
+    kname = {"tc3": "long_attn_tc3_kernel", "tc2": "long_attn_tc2_kernel",
+             "tc4": "long_attn_tc4_kernel + guarded long_attn_tc3_kernel fallback"}.get(args.attn, "long_term_attention op")
     return {"bound": "tensor", "kernel": f"{kname} (c3 GPM layer, T={T}, real operands of layers 0/1/2)",
             "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
             "peak_source": pk["source"] + " burst (kernel timed alone)", "ms_per_launch": round(ms, 4),
@@ -347,6 +350,7 @@ def measure_attention_roofline(eng, dev, args):
             "frac_max": round(flops / (min(per_layer_k) * 1e-3) / 1e12 / pk["tf_burst"], 4),
             "op_ms_per_launch": round(ms_op, 4), "op_ms_per_launch_by_layer": [round(x, 4) for x in per_layer_op],
             "op_frac": round(flops / (ms_op * 1e-3) / 1e12 / pk["tf_burst"], 4),
+            **({"fallback_taken_by_layer": fallback} if fallback else {}),
             "timing": f"median of {iters} launches per layer on the engine's own steady-state Q / K-bank / V-bank of each "
                       "GPM layer (frac = mean over the three layers); kernel = CUDA events recorded by the library "
                       "immediately around the main kernel launch on its stream; op = qprep + seed + kernel + combine "
@@ -499,7 +503,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--attn", default=os.environ.get("RMEM_ATTN", "tc3"), choices=["tc3", "tc2", "dense"])
+    ap.add_argument("--attn", default=os.environ.get("RMEM_ATTN", "tc3"), choices=["tc4", "tc3", "tc2", "dense"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=10)
     ap.add_argument("--ref-max-steps", type=int, default=20)

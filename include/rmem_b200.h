@@ -30,6 +30,9 @@ extern "C" {
 #define RMEM_ATTN_TC2 2   /* stream-K schedule over single CTAs, 8 softmax warps, P through TMEM, fp16 partials */
 #define RMEM_ATTN_TC3 3   /* CTA pairs (tcgen05.mma.cta_group::2) sharing every K / V^T tile, 128-key score MMAs, seeded
                              row maximum (default) */
+#define RMEM_ATTN_TC4 4   /* TC3 + the column kernel for seeded banks of >= 3 frames: scores and exponentials once per (query
+                             pair, sub-tile), probabilities re-read from L2 for the other Dv chunks, fixed softmax reference
+                             from the seed, guarded TC3 fallback; everything else (self-attention, unseeded calls) runs TC3 */
 
 int rmem_version(void);
 const char* rmem_last_error(void);
@@ -197,7 +200,7 @@ typedef struct rmem_engine_config {
   int former_mem_len;   /* FORMER_MEM_LEN */
   int latter_mem_len;   /* LATTER_MEM_LEN */
   int max_engines;      /* ceil(max objects / 10) object groups */
-  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC2 | RMEM_ATTN_TC3 */
+  int attn_impl;        /* RMEM_ATTN_DENSE | RMEM_ATTN_TC2 | RMEM_ATTN_TC3 | RMEM_ATTN_TC4 */
   int long_term_mem_gap;
   /* Ablation knobs of configs/models/r50_deaotl.py:9-28 (all off in the shipped configs):
    *   no_long_memory  NO_LONG_MEMORY (aot_engine.py:339): never append to the long-term bank (reference frame only).

@@ -12,6 +12,7 @@ ATTN_DENSE = 0
 ATTN_TC = 1
 ATTN_TC2 = 2
 ATTN_TC3 = 3
+ATTN_TC4 = 4
 MAX_BANK_FRAMES = 16
 
 

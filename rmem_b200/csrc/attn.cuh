@@ -71,7 +71,13 @@ int long_attn_tc3(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
 // qprep (Qt, qbias: ops.cuh) and the row-maximum seed of the long-term attention in ONE launch (Dk = 128).
 int qprep_seed_tc3(const t16* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T,
                    float scale, const t16* kbank, const int* slot, int HW, int HWp, int h, int w, t16* qt, float* qbias,
-                   float* mseed, cudaStream_t s);
+                   float* mseed, cudaStream_t s, int* zero_flag = nullptr);
+// v4 (attn_tc3.cu, long_attn_tc4_kernel): column kernel -- scores and exponentials once per (query pair, sub-tile), the
+// probabilities re-read from L2 for the other Dv chunks; fixed softmax reference from the seed, guarded tc3 fallback.
+// Falls through to long_attn_tc3 for unseeded calls and banks of fewer than 3 frames.  The first int of the workspace is
+// the overflow flag: qprep_seed_tc3(..., zero_flag = workspace) arms it when the caller provides a.mseed.
+size_t long_attn_tc4_workspace(int HW, int HWp, int nslots, int Dv);
+int long_attn_tc4(const LongAttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int long_attn_tc3_set_trace(long long* dev_buf);
 void long_attn_tc3_set_events(void* ev0, void* ev1);
 // Debug: device int incremented once per warp-level lazy-rescale event (null disables).  Thread-local.

@@ -67,8 +67,10 @@ int rmem_set_gemm_impl(int impl) {
 int rmem_long_attn_workspace_bytes(int impl, int HW, int HWp, int nslots, int Dv, size_t* bytes) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(bytes, "null bytes");
-  RMEM_REQUIRE(impl == RMEM_ATTN_DENSE || impl == RMEM_ATTN_TC2 || impl == RMEM_ATTN_TC3, "attention impl %d", impl);
-  *bytes = impl == RMEM_ATTN_TC3 ? long_attn_tc3_workspace(HW, HWp, nslots, Dv)
+  RMEM_REQUIRE(impl == RMEM_ATTN_DENSE || impl == RMEM_ATTN_TC2 || impl == RMEM_ATTN_TC3 || impl == RMEM_ATTN_TC4,
+               "attention impl %d", impl);
+  *bytes = impl == RMEM_ATTN_TC4 ? long_attn_tc4_workspace(HW, HWp, nslots, Dv)
+           : impl == RMEM_ATTN_TC3 ? long_attn_tc3_workspace(HW, HWp, nslots, Dv)
            : impl == RMEM_ATTN_TC2 ? long_attn_tc2_workspace(HW, HWp, nslots, Dv)
                                    : long_attn_dense_workspace(HW, HWp, nslots);
   return RMEM_OK;
@@ -101,6 +103,7 @@ int rmem_long_attn_grid_fwd(int impl, const void* qt, const float* qbias, const 
   a.HW = HW; a.HWp = HWp; a.Dk = Dk; a.Dv = Dv; a.scale = scale;
   a.gate = (const t16*)gate; a.ldg = ldg; a.out = (t16*)out; a.ldo = ldo; a.mass = mass;
   a.seed_h = grid_h; a.seed_w = grid_w;
+  if (impl == RMEM_ATTN_TC4) return long_attn_tc4(a, workspace, workspace_bytes, STREAM(stream));
   if (impl == RMEM_ATTN_TC3) return long_attn_tc3(a, workspace, workspace_bytes, STREAM(stream));
   if (impl == RMEM_ATTN_TC2) return long_attn_tc2(a, workspace, workspace_bytes, STREAM(stream));
   RMEM_REQUIRE(impl == RMEM_ATTN_DENSE, "attention impl %d (0 dense, 2 tc2, 3 tc3)", impl);

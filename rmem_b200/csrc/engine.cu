@@ -393,7 +393,9 @@ struct rmem_engine {
     size_t ws_dense = long_attn_dense_workspace(G.HW, G.HWp, nslots);
     size_t ws_tc2 = long_attn_tc2_workspace(G.HW, G.HWp, nslots, kDv);
     size_t ws_tc3 = long_attn_tc3_workspace(G.HW, G.HWp, nslots, kDv);
-    attn_ws_bytes = cfg.attn_impl == RMEM_ATTN_TC3 ? ws_tc3 : (cfg.attn_impl == RMEM_ATTN_TC2 ? ws_tc2 : ws_dense);
+    const size_t ws_tc4 = cfg.attn_impl == RMEM_ATTN_TC4 ? long_attn_tc4_workspace(G.HW, G.HWp, nslots, kDv) : 0;
+    attn_ws_bytes = cfg.attn_impl == RMEM_ATTN_TC4 ? ws_tc4
+                    : cfg.attn_impl == RMEM_ATTN_TC3 ? ws_tc3 : (cfg.attn_impl == RMEM_ATTN_TC2 ? ws_tc2 : ws_dense);
     attn_ws = a.take<char>(attn_ws_bytes);
     local_ws_bytes = local_attn_tc_workspace(G.h, G.w, kDv);
     local_ws = a.take<char>(local_ws_bytes);
@@ -631,6 +633,7 @@ struct rmem_engine {
 
   int attention(LongAttnArgs& a, cudaStream_t s, bool seed = true) {
     if (seed) { a.seed_h = g.h; a.seed_w = g.w; }   // token grid: tc3 seeds the row maximum from the query's own neighbourhood
+    if (cfg.attn_impl == RMEM_ATTN_TC4) return long_attn_tc4(a, attn_ws, attn_ws_bytes, s);
     if (cfg.attn_impl == RMEM_ATTN_TC3) return long_attn_tc3(a, attn_ws, attn_ws_bytes, s);
     if (cfg.attn_impl == RMEM_ATTN_TC2) return long_attn_tc2(a, attn_ws, attn_ws_bytes, s);
     return long_attn_dense(a, attn_ws, attn_ws_bytes, s);
@@ -737,9 +740,10 @@ struct rmem_engine {
       if (rc) return rc;
       int pe_slot[kMaxBankFrames];
       temporal_pe_slots(T, 4, pe_slot);
-      if (cfg.attn_impl == RMEM_ATTN_TC3 && fused_seed) {
+      if ((cfg.attn_impl == RMEM_ATTN_TC3 || cfg.attn_impl == RMEM_ATTN_TC4) && fused_seed) {
+        // (TC4: the launch also arms the column kernel's overflow flag, the first int of the attention workspace)
         RMEM_TRY(qprep_seed_tc3(L.kc[cur], kDk, pc, pm, pe_slot, T, scale, L.kbank, a.slot, G.HW, G.HWp, G.h, G.w, qt, qbias,
-                                mseed, s));
+                                mseed, s, cfg.attn_impl == RMEM_ATTN_TC4 ? reinterpret_cast<int*>(attn_ws) : nullptr));
         a.mseed = mseed;
       } else {
         RMEM_TRY(qprep(L.kc[cur], kDk, pc, pm, pe_slot, T, scale, qt, qbias, G.HW, kDk, s));
@@ -1185,8 +1189,9 @@ int rmem_engine_arena_bytes(const rmem_engine_config* cfg, size_t* bytes) {
                "GRU_MEMORY exists for the AOT model only (DualBranchGPM hard-codes gru_memory = False, transformer.py:728)");
   RMEM_REQUIRE(cfg->gru_memory == 0 || (cfg->former_mem_len == 1 && cfg->latter_mem_len >= 2),
                "GRU_MEMORY keeps bank positions 0 and 1: former_mem_len must be 1 and latter_mem_len >= 2");
-  RMEM_REQUIRE(cfg->attn_impl == RMEM_ATTN_DENSE || cfg->attn_impl == RMEM_ATTN_TC2 || cfg->attn_impl == RMEM_ATTN_TC3,
-               "attn_impl %d: 0 = dense, 2 = tc2, 3 = tc3", cfg->attn_impl);
+  RMEM_REQUIRE(cfg->attn_impl == RMEM_ATTN_DENSE || cfg->attn_impl == RMEM_ATTN_TC2 || cfg->attn_impl == RMEM_ATTN_TC3 ||
+                   cfg->attn_impl == RMEM_ATTN_TC4,
+               "attn_impl %d: 0 = dense, 2 = tc2, 3 = tc3, 4 = tc4", cfg->attn_impl);
   RMEM_REQUIRE(cfg->H > 16 && cfg->W > 16 && (cfg->H - 1) % 16 == 0 && (cfg->W - 1) % 16 == 0,
                "input size %dx%d is not 16k+1 (snap with MultiRestrictSize first)", cfg->H, cfg->W);
   RMEM_REQUIRE(cfg->max_engines >= 1 && cfg->max_engines <= 4, "max_engines=%d out of 1..4", cfg->max_engines);

@@ -309,7 +309,13 @@ def long_attention(q: torch.Tensor, kbank: torch.Tensor, vtbank: torch.Tensor, s
                                             C.c_longlong(gate.stride(0) if gate is not None else 0),
                                             _capi.ptr(out), C.c_longlong(Dv), _capi.ptr(mass), int(gh), int(gw),
                                             _capi.ptr(ws), C.c_size_t(nbytes.value), _capi.stream_ptr()))
+    global last_attn_overflow
+    # ATTN_TC4: first int of the workspace = the column kernel's overflow flag (1: the guarded tc3 fallback produced `out`)
+    last_attn_overflow = int(ws[:4].view(torch.int32).item()) if (impl == _capi.ATTN_TC4 and T >= 3 and grid is not None) else None
     return out, mass
+
+
+last_attn_overflow = None
 
 
 def local_attention(q: torch.Tensor, k_prev: torch.Tensor, v_prev: torch.Tensor, rel_w: torch.Tensor,

@@ -76,7 +76,7 @@ def main():
                                       grid=GRIDS[HW] if SEED else None, **args)
             torch.cuda.synchronize()
             _capi.check(_capi.load().rmem_debug_attn_rescale_counter(None))
-            rec.update(ok=True, impl=IMPL, seeded=SEED, rescales=int(cnt.item()), tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
+            rec.update(ok=True, impl=IMPL, seeded=SEED, rescales=int(cnt.item()), fallback=K.last_attn_overflow, tc_vs_oracle=relfro(ot, ref), dense_vs_oracle=relfro(od, ref),
                        tc_vs_dense=relfro(ot, od), mass_err=float((mt.cpu() - ref_mass).abs().max()),
                        mass_sum_err=float((mt.sum(1).cpu() - 1).abs().max()),
                        finite=bool(torch.isfinite(ot.float()).all()))

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("impl,seed", [(3, 1), (3, 0), (2, 0)], ids=["tc3_seeded", "tc3_unseeded", "tc2"])
+@pytest.mark.parametrize("impl,seed", [(4, 1), (3, 1), (3, 0), (2, 0)], ids=["tc4_column", "tc3_seeded", "tc3_unseeded", "tc2"])
 def test_tc_attention_matches_oracle(cuda_device, impl, seed):
     r = subprocess.run([sys.executable, os.path.join(HERE, "tc_attn_check.py")], capture_output=True, text=True,
                        timeout=600, env=dict(os.environ, RMEM_ATTN_IMPL=str(impl), RMEM_ATTN_SEED=str(seed)))

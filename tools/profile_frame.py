@@ -27,13 +27,13 @@ def main():
     ap.add_argument("--objects", type=int, default=10)
     ap.add_argument("--latter", type=int, default=7)
     ap.add_argument("--gap", type=int, default=5)
-    ap.add_argument("--attn", default="tc3", choices=["tc3", "tc2", "dense"])
+    ap.add_argument("--attn", default="tc3", choices=["tc4", "tc3", "tc2", "dense"])
     ap.add_argument("--stages", action="store_true", help="print per-stage CUDA-event times instead of profiling")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     sd = make_state_dict("r50_deaotl", seed=0, sharpen=4.0)
     cfg = RmemConfig(former_mem_len=1, latter_mem_len=a.latter,
-                     attn_impl={"dense": 0, "tc2": 2, "tc3": 3}[a.attn],
+                     attn_impl={"dense": 0, "tc2": 2, "tc3": 3, "tc4": 4}[a.attn],
                      max_engines=(a.objects + 9) // 10)
     eng = build_engine("deaotengine", aot_model=DeAOTModel(sd, cfg, dev), long_term_mem_gap=1)
     frames = synthetic_frames(4, a.H, a.W, seed=1000).to(dev)
