@@ -503,7 +503,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--attn", default=os.environ.get("RMEM_ATTN", "tc3"), choices=["tc4", "tc3", "tc2", "dense"])
+    ap.add_argument("--attn", default=os.environ.get("RMEM_ATTN", "tc4"), choices=["tc4", "tc3", "tc2", "dense"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=10)
     ap.add_argument("--ref-max-steps", type=int, default=20)

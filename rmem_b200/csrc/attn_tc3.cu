@@ -908,6 +908,7 @@ __device__ __forceinline__ void combine3_body(const Tc3Params& p, const t16* __r
 // only then (always-correct fallback), and combine34_kernel merges whichever partial set is valid.
 constexpr int PS = 5;                                    // P ring depth (16 KB stages over the Q tile + K ring)
 static_assert(PS * (BM * BNS * 2) <= SMEM_Q + KS * SMEM_K, "P ring must fit over the Q tile and the K ring");
+constexpr uint32_t kLboP = BM * 16, kSboP = 128;     // P scratch tile: see the store in pass 0
 constexpr float kRefShift = 6.0f;
 constexpr float kOverflowAt = 15.5f;
 constexpr int OFF_BAR4 = OFF_BAR + 512;                  // the column kernel's extra barriers
@@ -944,6 +945,13 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const bool leader = rank == 0;
   const int cl = (int)cluster_id_x();
   const int cta = cl * 2 + (int)rank;
+  // optional per-CTA phase times (tools/trace_attn4.py): rows 600 + cta of the trace buffer
+  long long* const cta_times = (g_trace3 && cta < 148) ? g_trace3 + (600 + cta) * 16 : nullptr;
+  if (cta_times && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cta_times[0] = (long long)gt; cta_times[5] = clock64();
+  }
 
   // this cluster's column: query pair `qp`, sub-tiles [lo, lo + n) of its T * tpf
   const int g_lo = p.bounds[cl], g_hi = p.bounds[cl + 1];
@@ -970,7 +978,9 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   cluster_sync_all();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (cta_times && threadIdx.x == 0) cta_times[7] = clock64();
   pdl_prologue();
+  if (cta_times && threadIdx.x == 0) cta_times[8] = clock64();
 
   if (warp >= kSoftmaxWarps) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
@@ -1104,10 +1114,12 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           fence_after();
           if (elect_one()) {
             const uint64_t dv = make_desc_sw128(smem_base + OFF_V + sv * SMEM_V);
-            const uint64_t dp = make_desc_sw128(smem_base + OFF_Q + sp * (BM * BNS * 2));
+            // P tile = [8 chunks][128 rows][16 B]: core matrices 2048 B apart along K, 128 B apart along M; a k-step of 16
+            // keys = two chunks = 4096 B
+            const uint64_t dp = make_desc_noswz(smem_base + OFF_Q + sp * (BM * BNS * 2), kLboP, kSboP);
 #pragma unroll
             for (int kk = 0; kk < BNS / 16; ++kk)
-              umma2_ss(od, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j == 0 && kk == 0) ? 0u : 1u);
+              umma2_ss(od, dp + (uint64_t)(kk * (4096 >> 4)), dv + (uint64_t)(kk * 2), idesc_o, (j == 0 && kk == 0) ? 0u : 1u);
             commit_pair(&v_empty[sv]);
             commit_pair(&pk_empty[sp]);
             if (j == n - 1) commit_pair(&pass_done[c]);
@@ -1140,7 +1152,7 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         d[1] = l_piece;
       }
     };
-    t16* prow = p.pbuf + ((long long)cta * p.max_sub * BM + row) * BNS;
+    t16* prow = p.pbuf + (long long)cta * p.max_sub * (BM * BNS) + row * 8;     // + j * tile + chunk * (BM * 8) elements
     int t = lo / p.tpf, jt = lo - t * p.tpf;
     for (int j = 0; j < n; ++j, ++jt) {
       if (jt == p.tpf) { jt = 0; ++t; }
@@ -1205,11 +1217,13 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       fence_before();
       __syncwarp();
       if (lane == 0) { if (leader) mbar_arrive(&p_full[b]); else mbar_arrive_leader(&p_full[b]); }
-      // the same probabilities for passes 1-3: this row's 128 bytes of the sub-tile's scratch tile
+      // the same probabilities for passes 1-3.  Scratch tile layout = [8 key chunks][128 rows][16 B] (the UMMA no-swizzle
+      // K-major core-matrix order): store c of a warp covers 32 consecutive rows = 512 contiguous bytes.  (Row-major rows
+      // -- 32 scattered 16-byte pieces per store instruction -- doubled the pass-0 time per sub-tile: 2200 cycles.)
       {
         uint4* dst = reinterpret_cast<uint4*>(prow + (long long)j * (BM * BNS));
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        for (int c = 0; c < 8; ++c) dst[c * BM] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       }
     }
     flush_piece(cur_t);
@@ -1218,6 +1232,7 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(p_ready);
+    if (cta_times && warp == 0 && lane == 0) cta_times[13] = clock64();      // pass-0 softmax done
 
     // ---- row sums of the three groups -> 1 / l (the same for every pass) ----
     lx[grp * BM + row] = l_tot;
@@ -1234,6 +1249,7 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     for (int c = 0; c < p.n_dv; ++c) {
       mbar_wait_b(&pass_done[c], 0);
       fence_after();
+      if (cta_times && warp == 0 && lane == 0) cta_times[9 + c] = clock64();   // pass c complete
       const uint32_t ob = lane_addr + ((c & 1) ? TMEM_S : TMEM_O);
       t16* po = p.part_o + (((long long)(cta * p.n_dv + c) * (DVC / 16)) * BM + row) * 16;
 #pragma unroll 1
@@ -1260,7 +1276,13 @@ long_attn_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
   fence_before();
   __syncthreads();
+  if (cta_times && threadIdx.x == 0) cta_times[14] = clock64();               // last read-out stored
   cluster_sync_all();
+  if (cta_times && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cta_times[1] = (long long)gt; cta_times[2] = n; cta_times[6] = clock64();
+  }
   if (warp == kWarpMmaS) {
     fence_after();
     tmem_dealloc_pair(tmem);
@@ -1785,10 +1807,11 @@ int long_attn_tc4(const LongAttnArgs& a, void* workspace, size_t workspace_bytes
     RMEM_TRY(tma_encode_cached(&mv, a.vtbank, 2, dims, str, box, nullptr));
   }
   {
+    // the scratch tiles are copied verbatim (no swizzle): 128 lines of 128 B per tile
     uint64_t dims[2] = {(uint64_t)BNS, (uint64_t)sc.nCL * 2 * sc.max_sub * BM};
     uint64_t str[1] = {(uint64_t)BNS * 2};
     uint32_t box[2] = {(uint32_t)BNS, (uint32_t)BM};
-    RMEM_TRY(tma_encode_cached(&mp, p.pbuf, 2, dims, str, box, nullptr));
+    RMEM_TRY(tma_encode_cached(&mp, p.pbuf, 2, dims, str, box, nullptr, /*swizzle128=*/0));
   }
   static bool attr_done = false;
   if (!attr_done) {

@@ -7,13 +7,13 @@
 
 namespace rmem {
 
-// ---- host: tensor maps (tma.cu).  fp16/bf16 (t16) tensors, 128B swizzle, zero OOB fill. ----
+// ---- host: tensor maps (tma.cu).  fp16/bf16 (t16) tensors, 128B swizzle (or none: swizzle128 = 0), zero OOB fill. ----
 // dims/strides in elements / bytes, innermost first; strides has rank-1 entries.  `estr` may be null (all 1).
 int tma_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, const uint32_t* estr);
+               const uint32_t* box, const uint32_t* estr, int swizzle128 = 1);
 // Same, memoised per thread on the full argument tuple (the engine re-uses the same few hundred maps every frame).
 int tma_encode_cached(const CUtensorMap** map, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr);
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, int swizzle128 = 1);
 
 #ifdef __CUDACC__
 namespace tc {
@@ -124,6 +124,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
+}
+
+// K-major operand tile WITHOUT swizzle, stored as 8-row x 16-byte core matrices (128 contiguous bytes each):
+// lbo = byte step between core matrices along K, sbo = byte step between 8-row groups along M / N.
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  return d;                                           // swizzle mode 0
 }
 
 // kind::f16 instruction descriptor: fp16/bf16 A/B (K-major), fp32 D.

@@ -41,7 +41,7 @@ struct MapKey {
 }  // namespace
 
 int tma_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, const uint32_t* estr) {
+               const uint32_t* box, const uint32_t* estr, int swizzle128) {
   RMEM_REQUIRE(rank >= 2 && rank <= 5, "tma_encode: rank %d", rank);
   EncodeFn encode = resolve_encode();
   if (!encode) return RMEM_ERR_CUDA;
@@ -54,7 +54,8 @@ int tma_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
     if (i < rank - 1) s[i] = strides_bytes[i];
   }
   CUresult r = encode(map, kTmaType, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank=%d dims=%llu,%llu,%llu stride0=%llu box=%u,%u,%u)", (int)r,
@@ -67,13 +68,13 @@ int tma_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
 }
 
 int tma_encode_cached(const CUtensorMap** out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, int swizzle128) {
   // std::map nodes are stable, so the returned pointer stays valid for the thread's lifetime.
   static thread_local std::map<MapKey, CUtensorMap> cache;
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.v[0] = reinterpret_cast<uint64_t>(base);
-  k.v[1] = (uint64_t)rank;
+  k.v[1] = (uint64_t)rank | ((uint64_t)(swizzle128 ? 1 : 0) << 8);
   for (int i = 0; i < rank; ++i) {
     k.v[2 + i] = dims[i];
     k.v[7 + i] = ((uint64_t)box[i] << 32) | (estr ? estr[i] : 1);
@@ -83,7 +84,7 @@ int tma_encode_cached(const CUtensorMap** out, const void* base, int rank, const
   if (it == cache.end()) {
     if (cache.size() > 8192) cache.clear();
     CUtensorMap m;
-    RMEM_TRY(tma_encode(&m, base, rank, dims, strides_bytes, box, estr));
+    RMEM_TRY(tma_encode(&m, base, rank, dims, strides_bytes, box, estr, swizzle128));
     it = cache.emplace(k, m).first;
   }
   *out = &it->second;

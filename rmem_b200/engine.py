@@ -34,7 +34,7 @@ class RmemConfig:
     # bank capacity 1 + 8 = 9 frames).  BASELINE.json's "T=8" workloads (bench.py, the c3 / c4 tests) pass 7 explicitly.
     latter_mem_len: int = 8
     max_obj_num: int = MAX_OBJ
-    attn_impl: int = _capi.ATTN_TC3
+    attn_impl: int = _capi.ATTN_TC4   # column kernel for the long-term attention, tc3 pair kernel for everything else
     max_engines: int = 4
     # ablation knobs (configs/models/r50_deaotl.py:9-28; all False in the shipped configs, see include/rmem_b200.h)
     no_long_memory: bool = False     # NO_LONG_MEMORY: the long-term bank stays at the reference frame

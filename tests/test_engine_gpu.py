@@ -66,7 +66,7 @@ def run_engine_lockstep(meta, z, device, attn_impl=0):
     return rec, eng
 
 
-@pytest.mark.parametrize("impl", [3, 2, 0], ids=["tcgen05_pair", "tcgen05_v2", "dense"])
+@pytest.mark.parametrize("impl", [4, 3, 2, 0], ids=["tcgen05_column", "tcgen05_pair", "tcgen05_v2", "dense"])
 @pytest.mark.parametrize("name", ["deaot_small_10obj", "deaot_small_xavier", "deaot_13obj_2engines"])
 def test_engine_matches_reference_goldens(cuda_device, name, impl):
     meta, z = load_case(name)
@@ -126,8 +126,8 @@ def test_aot_engine_matches_reference_goldens(cuda_device, name):
 
 def test_engine_restart_is_deterministic(cuda_device):
     meta, z = load_case("deaot_small_xavier")
-    rec1, eng = run_engine_lockstep(meta, z, cuda_device, attn_impl=3)
-    rec2, _ = run_engine_lockstep(meta, z, cuda_device, attn_impl=3)
+    rec1, eng = run_engine_lockstep(meta, z, cuda_device, attn_impl=4)
+    rec2, _ = run_engine_lockstep(meta, z, cuda_device, attn_impl=4)
     assert rec1["idx"] == rec2["idx"]
     for a, b in zip(rec1["labels"], rec2["labels"]):
         assert torch.equal(a, b)

@@ -73,7 +73,7 @@ def test_layer_memories_match_reference_hooks(cuda_device, gold):
     assert logit_err < 1.5e-2
 
 
-@pytest.mark.parametrize("impl", [3, 2, 0], ids=["tc3", "tc2", "dense"])
+@pytest.mark.parametrize("impl", [4, 3, 2, 0], ids=["tc4", "tc3", "tc2", "dense"])
 def test_gated_propagation_matches_reference_module(cuda_device, gold, impl):
     """long_term_attn of layer 1: out = projection(DWConv5x5((softmax(Q K^T / sqrt(128)) V) * U))."""
     from rmem_b200 import _capi, ops as K
@@ -88,7 +88,7 @@ def test_gated_propagation_matches_reference_module(cuda_device, gold, impl):
     T = Kb.shape[0]
     slots = list(range(T))
     kb, vtb, HWp = K.build_bank(Kb, Vb, T + 1, slots)
-    agg, _ = K.long_attention(Q.to(OP), kb, vtb, slots, HW, gate=U, impl=impl, grid=(h, w) if impl == 3 else None)
+    agg, _ = K.long_attention(Q.to(OP), kb, vtb, slots, HW, gate=U, impl=impl, grid=(h, w) if impl in (3, 4) else None)
     p = "LSTT.layers.1.long_term_attn"
     dw = sd[p + ".dw_conv.conv.weight"].view(1024, 25).t().contiguous().to(cuda_device)
     x = K.dwconv5x5(agg, dw, h, w)

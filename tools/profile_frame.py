@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--objects", type=int, default=10)
     ap.add_argument("--latter", type=int, default=7)
     ap.add_argument("--gap", type=int, default=5)
-    ap.add_argument("--attn", default="tc3", choices=["tc4", "tc3", "tc2", "dense"])
+    ap.add_argument("--attn", default="tc4", choices=["tc4", "tc3", "tc2", "dense"])
     ap.add_argument("--stages", action="store_true", help="print per-stage CUDA-event times instead of profiling")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
