@@ -106,6 +106,13 @@ int rmem_debug_attn_schedule(int impl, int HW, int T, int Dv, int* n_units, int*
 int rmem_debug_attn_events(void* ev0, void* ev1);
 /* Same for the tcgen05 GEMM: first 64 CTAs of every launch, [cta][8] int64. */
 int rmem_debug_gemm_trace(void* dev_buf);
+/* Tuning aids for the tcgen05 GEMM (tools/tune_gemm.py), thread-local.  force: tile width bn (0 = auto | 64 | 128 | 256),
+ * split-K factor (0 = auto, 1..4; bn = 64 only), TMA ring depth (0 = auto, 1..6) for every following launch.  log: the
+ * shape of every following tcgen05 GEMM launch is appended to a HOST buffer of 16-int records (M N K conv Hin Win Cin Wout
+ * kw stride pad act has_res has_gate flags n_split); NULL stops logging; log_count = records written so far. */
+int rmem_debug_gemm_force(int bn, int splitk, int stages);
+int rmem_debug_gemm_log(int* host_buf, int cap_records);
+int rmem_debug_gemm_log_count(void);
 
 /* Qt = t16(Q + cur_pos_emb); qbias[i,t] = scale * <Qt_i, pe_mem[t]>          (transformer.py:1140-1175) */
 /* pe_mem = mem_pos_emb [n_slots, C]; pe_slot HOST [T] = slot of each memory frame (rmem_temporal_pe_slots). */

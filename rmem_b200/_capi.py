@@ -49,7 +49,7 @@ class WeightEntry(C.Structure):
 
 # every symbol include/rmem_b200.h declares (tests/test_capi_symbols.py checks header <-> this list <-> .so)
 SYMBOLS = [
-    "rmem_version", "rmem_last_error", "rmem_operand_dtype", "rmem_gemm_fwd", "rmem_set_gemm_impl", "rmem_long_attn_workspace_bytes", "rmem_long_attn_fwd", "rmem_long_attn_grid_fwd", "rmem_mha_workspace_bytes", "rmem_mha_fwd", "rmem_debug_attn_rescale_counter", "rmem_debug_attn_trace", "rmem_debug_attn_schedule", "rmem_debug_attn_events", "rmem_debug_gemm_trace",
+    "rmem_version", "rmem_last_error", "rmem_operand_dtype", "rmem_gemm_fwd", "rmem_set_gemm_impl", "rmem_long_attn_workspace_bytes", "rmem_long_attn_fwd", "rmem_long_attn_grid_fwd", "rmem_mha_workspace_bytes", "rmem_mha_fwd", "rmem_debug_attn_rescale_counter", "rmem_debug_attn_trace", "rmem_debug_attn_schedule", "rmem_debug_attn_events", "rmem_debug_gemm_trace", "rmem_debug_gemm_force", "rmem_debug_gemm_log", "rmem_debug_gemm_log_count",
     "rmem_qprep_fwd", "rmem_temporal_pe_slots", "rmem_local_attn_fwd", "rmem_local_attn_tc_workspace_bytes", "rmem_local_attn_tc_fwd", "rmem_layernorm_fwd", "rmem_groupnorm_fwd",
     "rmem_dwconv5x5_fwd", "rmem_upsample_bilinear_fwd", "rmem_transpose_fwd", "rmem_maxpool3x3s2_fwd",
     "rmem_pack_image_fwd", "rmem_pack_image_padded_fwd", "rmem_idbank_fwd", "rmem_mask_head_fwd", "rmem_tta_head_fwd", "rmem_preprocess_fwd", "rmem_evict_relevance_fwd", "rmem_evict_pick",

@@ -137,6 +137,17 @@ int rmem_mha_fwd(int impl, const void* q, long long ldq, const void* kbank, cons
 }
 
 int rmem_debug_gemm_trace(void* dev_buf) { return gemm_tc_set_trace(reinterpret_cast<long long*>(dev_buf)); }
+int rmem_debug_gemm_force(int bn, int splitk, int stages) {
+  RMEM_API_BEGIN
+  return gemm_tc_set_force(bn, splitk, stages);
+  RMEM_API_END
+}
+int rmem_debug_gemm_log(int* host_buf, int cap_records) {
+  RMEM_API_BEGIN
+  return gemm_tc_set_log(host_buf, cap_records);
+  RMEM_API_END
+}
+int rmem_debug_gemm_log_count(void) { return gemm_tc_log_count(); }
 int rmem_debug_attn_events(void* ev0, void* ev1) {
   RMEM_API_BEGIN
   long_attn_tc2_set_events(ev0, ev1);

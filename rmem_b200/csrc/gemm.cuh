@@ -57,6 +57,12 @@ int gemm_tc_launch(const GemmParams& p, cudaStream_t stream);
 int gemm_legacy_launch(const GemmParams& p, cudaStream_t stream);
 // Debug: clock64 event trace of the first 64 CTAs of every gemm_tc launch ([cta][8] long long); nullptr disables.
 int gemm_tc_set_trace(long long* dev_buf);
+// Tuning aids, thread-local (tools/tune_gemm.py): force the tile width (0 | 64 | 128 | 256), split-K factor (0 = auto;
+// BN = 64 only) and ring depth (0 = auto) of every following tcgen05 launch; log the shapes launched into a HOST buffer
+// of 16-int records (see gemm_tc.cu).
+int gemm_tc_set_force(int bn, int splitk, int stages);
+int gemm_tc_set_log(int* host_buf, int cap_records);
+int gemm_tc_log_count();
 // 0 = auto (tcgen05 when supported), 1 = force the legacy mma.sync kernel (parity tests).  Thread-local.
 int& gemm_impl_switch();
 

@@ -376,6 +376,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 constexpr int kMaxSplitK = 4;
+// Tuning aids (tools/tune_gemm.py), thread-local: a forced (BN, split-K, stages) for every following launch (0 = the
+// launcher's own choice) and a host-side log of the shapes launched.
+struct TcForce { int bn = 0, splitk = 0, stages = 0; };
+TcForce& tc_force() {
+  static thread_local TcForce f;
+  return f;
+}
+struct TcLog { int* buf = nullptr; int cap = 0, n = 0; };
+TcLog& tc_log() {
+  static thread_local TcLog l;
+  return l;
+}
 int tc_sm_count() {
   static int n = 0;
   if (!n) {
@@ -415,10 +427,20 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
     if (S > p.nk / 4) S = p.nk / 4;
     if (S < 2) S = 1;
   }
+  if (BN == 64 && tc_force().splitk > 0) {
+    S = tc_force().splitk;
+    if (S > kMaxSplitK) S = kMaxSplitK;
+    if (S > p.nk) S = p.nk;
+  }
   p.splitk = S;
   // Only as many stages as there are k-blocks: short-K GEMMs (most of the encoder) are latency-bound, and a small
   // shared-memory footprint lets several CTAs share an SM so one CTA's epilogue overlaps another's loads.
   const int nkl = cdiv(p.nk, S);
+  if (tc_force().stages > 0) {
+    max_stages = tc_force().stages;
+    const int cap = BN == 256 ? 4 : (S > 1 ? 4 : kMaxStages);     // what the shared-memory attribute above covers
+    if (max_stages > cap) max_stages = cap;
+  }
   p.stages = nkl < max_stages ? nkl : max_stages;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cdiv(p.N, BN), m_tiles, S);
@@ -443,6 +465,19 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
 }
 
 }  // namespace
+
+int gemm_tc_set_force(int bn, int splitk, int stages) {
+  RMEM_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 256, "gemm_tc force: BN must be 0, 64, 128 or 256 (got %d)", bn);
+  RMEM_REQUIRE(splitk >= 0 && splitk <= kMaxSplitK && stages >= 0 && stages <= kMaxStages,
+               "gemm_tc force: split-K 0..%d, stages 0..%d", kMaxSplitK, kMaxStages);
+  tc_force().bn = bn; tc_force().splitk = splitk; tc_force().stages = stages;
+  return RMEM_OK;
+}
+int gemm_tc_set_log(int* host_buf, int cap_records) {
+  tc_log().buf = host_buf; tc_log().cap = host_buf ? cap_records : 0; tc_log().n = 0;
+  return RMEM_OK;
+}
+int gemm_tc_log_count() { return tc_log().n; }
 
 int gemm_tc_set_trace(long long* dev_buf) {
   RMEM_CUDA_CHECK(cudaMemcpyToSymbol(g_gemm_trace, &dev_buf, sizeof(dev_buf)));
@@ -536,6 +571,15 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
   int BN = 128;
   if (g.N <= 64 || m_tiles * cdiv(g.N, 128) < 120) BN = 64;
   else if (g.N >= 256 && g.K >= 512 && m_tiles * cdiv(g.N, 256) >= 148) BN = 256;
+  if (tc_force().bn) BN = tc_force().bn;
+  if (tc_log().buf && tc_log().n < tc_log().cap) {
+    // record = 16 ints: M N K conv Hin Win Cin Wout kw stride pad | act has_res has_gate c_fp32 n_split<N
+    int* r = tc_log().buf + (size_t)tc_log().n * 16;
+    r[0] = g.M; r[1] = g.N; r[2] = g.K; r[3] = g.conv; r[4] = g.Hin; r[5] = g.Win; r[6] = g.Cin; r[7] = g.Wout;
+    r[8] = g.kw; r[9] = g.stride; r[10] = g.pad; r[11] = g.act; r[12] = g.res != nullptr; r[13] = g.gate != nullptr;
+    r[14] = g.c_fp32 | (g.accumulate << 1) | (g.bias_m << 2); r[15] = g.n_split < g.N ? g.n_split : 0;
+    ++tc_log().n;
+  }
   {
     uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     uint64_t strides[1] = {(uint64_t)g.ldb * 2};

@@ -20,5 +20,5 @@ timeout 900 ncu --profile-from-start off --set full --clock-control none --impor
     -o /tmp/frame python tools/profile_frame.py --frames 1 > gpurun_out/ncu_frame.log 2>&1
 tail -1 gpurun_out/ncu_frame.log
 python tools/ncu_key_metrics.py /tmp/frame.ncu-rep gpurun_out/frame_ncu_key_metrics.txt > /dev/null 2>&1
-python tools/ncu_traffic.py /tmp/frame.ncu-rep long_attn_tc3_kernel gpurun_out/attn_traffic.json > /dev/null 2>&1
+python tools/ncu_traffic.py /tmp/frame.ncu-rep long_attn_tc4_kernel gpurun_out/attn_traffic.json > /dev/null 2>&1
 ls -la gpurun_out | head -40
