@@ -134,11 +134,20 @@ def run_ours(args):
         eng.long_term_mem_gap = GAP
         eng.add_reference_frame(src[0:1], label0.int().to(dev), obj_nums=[N_OBJ], frame_step=0)
 
+    PAIRS = PREFETCH and args.enc_pairs
+
+    def fr(src, k):
+        return src[1 + k % ring: 2 + k % ring]
+
     def step(i, src):
-        # software pipelining across frames: frame i+1 is encoded on the engine's side stream while frame i propagates
-        if PREFETCH:
-            eng.prefetch(src[1 + (i + 1) % ring: 2 + (i + 1) % ring])
-        lab = eng.propagate_label(src[1 + i % ring: 2 + i % ring], output_size=(H, W))
+        # software pipelining across frames: the image encoder runs on the engine's side stream while frame i propagates
+        # -- frame i+1 alone, or (pair mode) frames i+2 and i+3 in one pass every second frame
+        if PAIRS:
+            if i % 2 == 0:
+                eng.prefetch2(fr(src, i + 2), fr(src, i + 3))
+        elif PREFETCH:
+            eng.prefetch(fr(src, i + 1))
+        lab = eng.propagate_label(fr(src, i), output_size=(H, W))
         eng.update_memory(lab)        # 480p -> output size == input size, nearest resize is the identity
         return lab
 
@@ -152,40 +161,55 @@ def run_ours(args):
     # host->device copy of frame i+1 is issued on a copy stream while frame i computes (what a prefetching loader does,
     # evaluator.py:308,372 uses pin_memory + non_blocking); both copies are inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty(1, 3, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
-    staged = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    NS = 4 if PAIRS else 2                                 # staging buffers: frames i .. i+3 are live in pair mode
+    stage = [torch.empty(1, 3, H, W, dtype=torch.float32, device=dev) for _ in range(NS)]
+    staged = [torch.cuda.Event() for _ in range(NS)]
+    consumed = [torch.cuda.Event() for _ in range(NS)]
+    counter = {"dev": 0, "e2e": 0}                         # frame index runs on across the timed blocks
 
     def prefetch(i, src):
-        b = i % 2
+        b = i % NS
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])           # frame i-2 has finished reading this staging buffer
-            stage[b].copy_(src[1 + i % ring: 2 + i % ring], non_blocking=True)
+            copy_stream.wait_event(consumed[b])           # frame i-NS has finished reading this staging buffer
+            stage[b].copy_(fr(src, i), non_blocking=True)
             staged[b].record(copy_stream)
 
     def timed(src, steps, e2e):
         host_lab = torch.empty(2, 1, 1, H, W, dtype=torch.uint8).pin_memory()
         main = torch.cuda.current_stream()
-        for b in range(2):
-            consumed[b].record(main)
+        first = counter["e2e" if e2e else "dev"]
+        if e2e and first == 0:
+            for b in range(NS):
+                consumed[b].record(main)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if e2e:
-            prefetch(0, src)
-        for i in range(steps):
+        if e2e and first == 0:                              # very first e2e frame(s): nothing staged yet
+            for k in range(2 if PAIRS else 1):
+                prefetch(k, src)
+        for i in range(first, first + steps):
             if e2e:
-                if i + 1 < steps:
+                # The copy of a frame and its encoding are issued ahead of its propagate: frame i+1 (single mode), or
+                # frames i+2, i+3 every second frame (pair mode).  The last one or two frames staged by a block are
+                # consumed by the next block (the frame index runs on), so every block copies and encodes exactly
+                # `steps` frames inside its timed region.
+                if PAIRS:
+                    if i % 2 == 0:
+                        prefetch(i + 2, src)
+                        prefetch(i + 3, src)
+                        eng.prefetch2(stage[(i + 2) % NS], stage[(i + 3) % NS], stream=copy_stream)
+                else:
                     prefetch(i + 1, src)
                     if PREFETCH:
-                        eng.prefetch(stage[(i + 1) % 2], stream=copy_stream)   # encode i+1 once its copy has landed
-                main.wait_event(staged[i % 2])
-                lab = eng.propagate_label(stage[i % 2], output_size=(H, W))
-                consumed[i % 2].record(main)
+                        eng.prefetch(stage[(i + 1) % NS], stream=copy_stream)   # encode i+1 once its copy has landed
+                main.wait_event(staged[i % NS])
+                lab = eng.propagate_label(stage[i % NS], output_size=(H, W))
+                consumed[i % NS].record(main)
                 eng.update_memory(lab)
                 host_lab[i % 2].copy_(lab, non_blocking=True)
             else:
                 lab = step(i, src)
+        counter["e2e" if e2e else "dev"] = first + steps
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -205,8 +229,11 @@ def run_ours(args):
         torch.cuda.set_stream(hp)
     # ---- device-resident run ----
     clip_start(frames_dev)
-    for i in range(max(fill, args.warmup)):
+    nwarm = max(fill, args.warmup)
+    nwarm += nwarm % 2                                    # pair mode: blocks start on an even frame index
+    for i in range(nwarm):
         step(i, frames_dev)
+    counter["dev"] = nwarm
     assert len(eng.aot_engines[0].long_memories_indexes) == FORMER + LATTER, "bank not full after warm-up"
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -242,7 +269,7 @@ def run_ours(args):
         fps_e2e = world * args.steps / (ms_e2e / 1e3)
         out = {
             "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(fill, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "warmup": nwarm, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16" if _capi.op_dtype() == torch.float16 else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"clip-sharded x{world}", "attn_impl": args.attn,
@@ -255,8 +282,12 @@ def run_ours(args):
                                "eval script uses 1 + 8 (T=9): bench.py --latter 8 runs that setting",
                        "l2": "per-frame working set (banks 3x37 MB + activations + 150 MB attention workspace) "
                              "exceeds the 126 MB L2; no explicit flush",
-                       "pipeline": ("each step = prefetch(frame i+1: image encoder on the engine's side stream) + "
-                                    "propagate(frame i) + update_memory(frame i); every frame is encoded exactly once"
+                       "pipeline": (("every second step = prefetch2(frames i+2, i+3: ONE pass of the image encoder over both "
+                                     "images on the engine's side stream); each step = propagate(frame i) + "
+                                     "update_memory(frame i); every frame is encoded exactly once, inside the timed region "
+                                     "of the block that issues it") if PAIRS else
+                                    ("each step = prefetch(frame i+1: image encoder on the engine's side stream) + "
+                                     "propagate(frame i) + update_memory(frame i); every frame is encoded exactly once")
                                     if PREFETCH else "no cross-frame prefetch")},
             "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
                     "d2h_bytes_per_step": H * W},
@@ -583,6 +614,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=10)
     ap.add_argument("--ref-max-steps", type=int, default=20)
     ap.add_argument("--repeat", type=int, default=10, help="timed blocks of --steps steps; the median block is reported")
+    ap.add_argument("--enc-pairs", type=int, default=int(os.environ.get("RMEM_BENCH_ENC_PAIRS", "1")),
+                    help="1 = the image encoder runs over two coming frames per pass (rmem_engine_prefetch2); 0 = one frame ahead")
     ap.add_argument("--clips-in-flight", type=int, default=2,
                     help="2 = also time two independent clips per GPU (extra key two_clips_in_flight); 1 = skip that leg")
     ap.add_argument("--latter", type=int, default=LATTER, help="LATTER_MEM_LEN (7 = T=8 as BASELINE.json names it)")

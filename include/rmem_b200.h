@@ -58,6 +58,8 @@ typedef struct rmem_gemm_desc {
   void* C; long long ldc; int c_is_f32;
   void* C2; long long ldc2; int c2_is_f32; int n_split; /* columns >= n_split go to C2 */
   int pad_n_ok;                      /* N % 32 != 0: columns N..round_up(N,32)-1 of C are writable padding */
+  int n_images;                      /* conv != 0 only: images stacked in A ([n][Hin][Win][Cin]) and in C / residual
+                                      * ([n][Hout*Wout][N]), M = n * Hout * Wout; 0 or 1 = a single image */
 } rmem_gemm_desc;
 int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream);
 /* 0 = auto: the tcgen05/TMA kernel whenever its alignment rules hold (K % 64 == 0, 16-byte aligned operands), else the
@@ -263,6 +265,12 @@ long long rmem_engine_launch_count(const rmem_engine* e);
  * engine's side stream while the current frame is propagated.  `img` must be ready on `stream`; the following
  * rmem_engine_propagate must be given the same pointer (otherwise the inline encoder runs).  Bit-identical results. */
 int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream);
+/* Pair prefetch: frames i+2 and i+3 encoded in ONE pass of the image encoder (every GEMM / conv launch covers both
+ * images: the launches are latency-bound at one 480p image, a pair costs ~1.2x one frame).  Issue it every second frame,
+ * two frames ahead (before rmem_engine_propagate of frame i); each image is consumed by the propagate call that passes the
+ * same pointer and must stay untouched until then.  Same math as the single-frame encoder, differently tiled: results agree to
+ * fp16 rounding, not bit for bit. */
+int rmem_engine_prefetch2(rmem_engine* e, const float* img_a, const float* img_b, void* stream);
 /* Profiling aid: CUDA events between pipeline stages (adds a stream sync per call while on).  get_timing writes
  * "stage total_ms count" lines into buf. */
 int rmem_engine_set_timing(rmem_engine* e, int on);

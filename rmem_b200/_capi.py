@@ -32,7 +32,7 @@ class GemmDesc(C.Structure):
         ("accumulate", C.c_int),
         ("C", C.c_void_p), ("ldc", C.c_longlong), ("c_is_f32", C.c_int),
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_is_f32", C.c_int), ("n_split", C.c_int),
-        ("pad_n_ok", C.c_int),
+        ("pad_n_ok", C.c_int), ("n_images", C.c_int),
     ]
 
 
@@ -57,7 +57,7 @@ SYMBOLS = [
     "rmem_engine_set_gap", "rmem_engine_add_reference_frame", "rmem_engine_propagate", "rmem_engine_update_memory",
     "rmem_engine_num_groups", "rmem_engine_long_indexes", "rmem_engine_pred_logits", "rmem_engine_last_evict",
     "rmem_engine_layer_memory",
-    "rmem_engine_launch_count", "rmem_engine_prefetch", "rmem_engine_set_timing", "rmem_engine_get_timing",
+    "rmem_engine_launch_count", "rmem_engine_prefetch", "rmem_engine_prefetch2", "rmem_engine_set_timing", "rmem_engine_get_timing",
 ]
 
 _lib = None

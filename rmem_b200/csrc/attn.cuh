@@ -100,6 +100,11 @@ size_t local_attn_tc_workspace(int h, int w, int Dv);
 int local_attn_tc_set_trace(long long* dev_buf);
 int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, const t16* v, long long ldv,
                   const float* rel, long long ldrel, int rel_pitch, const t16* gate, long long ldg, t16* out, long long ldo, int h,
-                  int w, int Dv, float scale, void* workspace, size_t workspace_bytes, cudaStream_t s);
+                  int w, int Dv, float scale, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                  bool v_prepared = false);
+// The value-major copy alone (same stream order as the attention that reads it): lets a caller whose v is ready early
+// take the transpose off the path between q and the output; pass v_prepared = true to local_attn_tc afterwards.
+int local_attn_tc_prepare_v(const t16* v, long long ldv, int h, int w, int Dv, void* workspace, size_t workspace_bytes,
+                            cudaStream_t s);
 
 }  // namespace rmem

@@ -52,6 +52,7 @@ int rmem_gemm_fwd(const rmem_gemm_desc* d, void* stream) {
   p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_fp32 = d->c2_is_f32;
   p.n_split = d->C2 ? d->n_split : (1 << 30);
   p.pad_n_ok = d->pad_n_ok;
+  p.nimg = d->n_images > 1 ? d->n_images : 1;
   return gemm_launch(p, STREAM(stream));
   RMEM_API_END
 }

@@ -34,6 +34,7 @@ int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former,
 namespace {
 
 constexpr int kLayers = 3;
+constexpr int kFeatSets = 4;   // encoder output sets: two pairs of contiguous members (rmem_engine_prefetch2)
 constexpr int kD = 256;      // d_model
 constexpr int kDk = 128;     // att dim
 constexpr int kDv = 1024;    // V (512) || ID_V (512)
@@ -128,16 +129,20 @@ struct rmem_engine {
 
   // shared scratch
   t16 *img8, *c1, *x0, *x1, *t1, *t2, *ds, *feat4, *feat8, *feat16;
+  size_t img8_elems = 0;
   float* enc_tgt;     // [HW,256] projector output
   // Encoder outputs are double-buffered: the image encoder does not depend on the memory state, so the NEXT frame can be
   // encoded on a side stream (rmem_engine_prefetch) while this frame's propagation / decoder / memory update run.
   // feat4/feat8/feat16/enc_tgt above always point at the set the current frame reads.
-  t16 *feat4s[2], *feat8s[2], *feat16s[2];
-  float* enc_tgts[2];
+  // Four feature sets = two PAIRS whose members are contiguous ([2][pixels][channels]): rmem_engine_prefetch2 encodes two
+  // frames in one pass (every encoder GEMM / conv runs once over both images, M doubled), a single prefetch or the inline
+  // encoder uses one member.
+  t16 *feat4s[kFeatSets], *feat8s[kFeatSets], *feat16s[kFeatSets];
+  float* enc_tgts[kFeatSets];
   // The decoder's adapter convolutions (fpn.py:44,50,56: 1x1 convs of the ENCODER features) do not depend on the memory
   // state either: they are computed with the encoder (prefetch stream) and added by the decoder's GroupNorm / upsample
   // kernels instead of sitting on the per-frame critical path as three more GEMM launches per object group.
-  t16 *ad16s[2], *ad8s[2], *ad4s[2], *ad16, *ad8, *ad4;
+  t16 *ad16s[kFeatSets], *ad8s[kFeatSets], *ad4s[kFeatSets], *ad16, *ad8, *ad4;
   int fslot = 0;
   // Independent GEMMs of one layer (U / ID_U next to QV, the self-attention projections, the three linear_ID_V of the
   // memory update) are forked onto a second engine-owned stream: each is a ~3 us kernel behind ~5 us of launch latency.
@@ -184,12 +189,39 @@ struct rmem_engine {
     return RMEM_OK;
   }
   cudaStream_t enc_stream = nullptr;
-  cudaEvent_t ev_img_ready = nullptr, ev_inline = nullptr, ev_done[2] = {nullptr, nullptr}, ev_feat_free[2] = {nullptr, nullptr};
-  bool feat_free_valid[2] = {false, false}, inline_valid = false;
-  bool pending[2] = {false, false};        // features of pf_img[sl] are (being) produced on enc_stream, not consumed yet
-  const float* pf_img[2] = {nullptr, nullptr};
-  long long pf_seq[2] = {0, 0}, pf_counter = 0;
-  int pf_age[2] = {0, 0};                  // features() calls since the prefetch was issued (a live entry is consumed at <= 1)
+  cudaEvent_t ev_img_ready = nullptr, ev_inline = nullptr, ev_done[kFeatSets] = {}, ev_feat_free[kFeatSets] = {};
+  bool feat_free_valid[kFeatSets] = {}, inline_valid = false;
+  bool pending[kFeatSets] = {};            // features of pf_img[sl] are (being) produced on enc_stream, not consumed yet
+  const float* pf_img[kFeatSets] = {};
+  long long pf_seq[kFeatSets] = {}, pf_counter = 0;
+  int pf_age[kFeatSets] = {};              // features() calls since the prefetch was issued
+  int pf_ttl[kFeatSets] = {};              // ... at which an unconsumed entry is stale (2: single prefetch, 4: pair)
+  // slot for a single frame: not pending, preferably not the current one; all pending -> the oldest (stale) entry
+  int pick_slot() const {
+    for (int k = 1; k <= kFeatSets; ++k) {
+      const int sl = (fslot + k) % kFeatSets;          // k = kFeatSets: the current slot itself (its readers are all issued)
+      if (!pending[sl]) return sl;
+    }
+    int o = 0;
+    for (int sl = 1; sl < kFeatSets; ++sl)
+      if (pf_seq[sl] < pf_seq[o]) o = sl;
+    return o;
+  }
+  // first slot of a pair with no unconsumed prefetch (preferably not the current frame's pair), else of the older pair
+  int pick_pair() const {
+    const int cur_pair = fslot >> 1;
+    for (int k = 1; k <= kFeatSets / 2; ++k) {
+      const int pr = (cur_pair + k) % (kFeatSets / 2);
+      if (!pending[2 * pr] && !pending[2 * pr + 1]) return 2 * pr;
+    }
+    long long best = -1;
+    int o = 0;
+    for (int pr = 0; pr < kFeatSets / 2; ++pr) {
+      const long long newest = pf_seq[2 * pr] > pf_seq[2 * pr + 1] ? pf_seq[2 * pr] : pf_seq[2 * pr + 1];
+      if (best < 0 || newest < best) { best = newest; o = 2 * pr; }
+    }
+    return o;
+  }
   int last_enc_slot = -1;                  // last slot encoded on enc_stream (its event orders the encoder temporaries)
   void use_slot(int sl) {
     fslot = sl; feat4 = feat4s[sl]; feat8 = feat8s[sl]; feat16 = feat16s[sl]; enc_tgt = enc_tgts[sl];
@@ -213,7 +245,7 @@ struct rmem_engine {
     { const char* e = getenv("RMEM_SELF_SEED"); self_seed = !(e && e[0] == '0'); }
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_ready, cudaEventDisableTiming));
     RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_inline, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kFeatSets; ++i) {
       RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
       RMEM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_feat_free[i], cudaEventDisableTiming));
     }
@@ -237,7 +269,7 @@ struct rmem_engine {
     if (rel_pinned) cudaFreeHost(rel_pinned);
     if (ev_img_ready) cudaEventDestroy(ev_img_ready);
     if (ev_inline) cudaEventDestroy(ev_inline);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kFeatSets; ++i) {
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
       if (ev_feat_free[i]) cudaEventDestroy(ev_feat_free[i]);
     }
@@ -317,21 +349,23 @@ struct rmem_engine {
 
   int layout(Arena& a) {
     const Geo& G = g;
-    img8 = a.take<t16>((size_t)(G.H + 6) * (G.W + 8) * 8);   // zero-padded stem input (zeroed once at create)
-    c1 = a.take<t16>((size_t)G.P1 * 64);
-    x0 = a.take<t16>((size_t)G.P4 * 256);
-    x1 = a.take<t16>((size_t)G.P4 * 256);
-    t1 = a.take<t16>((size_t)G.P4 * 128);
-    t2 = a.take<t16>((size_t)G.P4 * 64);
-    ds = a.take<t16>((size_t)G.P4 * 256);
-    for (int sl = 0; sl < 2; ++sl) {
-      feat4s[sl] = a.take<t16>((size_t)G.P4 * 256);
-      feat8s[sl] = a.take<t16>((size_t)G.P8 * 512);
-      feat16s[sl] = a.take<t16>((size_t)G.HW * 1024);
-      enc_tgts[sl] = a.take<float>((size_t)G.HW * kD);
-      ad16s[sl] = a.take<t16>((size_t)G.HW * 256);
-      ad8s[sl] = a.take<t16>((size_t)G.P8 * 256);
-      ad4s[sl] = a.take<t16>((size_t)G.P4 * 128);
+    // encoder temporaries hold two images (pair encoder); every activation is [n][pixels][channels]
+    img8_elems = (size_t)(G.H + 6) * (G.W + 8) * 8;
+    img8 = a.take<t16>(2 * img8_elems);                       // zero-padded stem inputs (zeroed once at create)
+    c1 = a.take<t16>(2 * (size_t)G.P1 * 64);
+    x0 = a.take<t16>(2 * (size_t)G.P4 * 256);
+    x1 = a.take<t16>(2 * (size_t)G.P4 * 256);
+    t1 = a.take<t16>(2 * (size_t)G.P4 * 128);
+    t2 = a.take<t16>(2 * (size_t)G.P4 * 64);
+    ds = a.take<t16>(2 * (size_t)G.P4 * 256);
+    for (int sl = 0; sl < kFeatSets; sl += 2) {
+      feat4s[sl] = a.take<t16>(2 * (size_t)G.P4 * 256);   feat4s[sl + 1] = feat4s[sl] + (size_t)G.P4 * 256;
+      feat8s[sl] = a.take<t16>(2 * (size_t)G.P8 * 512);   feat8s[sl + 1] = feat8s[sl] + (size_t)G.P8 * 512;
+      feat16s[sl] = a.take<t16>(2 * (size_t)G.HW * 1024); feat16s[sl + 1] = feat16s[sl] + (size_t)G.HW * 1024;
+      enc_tgts[sl] = a.take<float>(2 * (size_t)G.HW * kD); enc_tgts[sl + 1] = enc_tgts[sl] + (size_t)G.HW * kD;
+      ad16s[sl] = a.take<t16>(2 * (size_t)G.HW * 256);    ad16s[sl + 1] = ad16s[sl] + (size_t)G.HW * 256;
+      ad8s[sl] = a.take<t16>(2 * (size_t)G.P8 * 256);     ad8s[sl + 1] = ad8s[sl] + (size_t)G.P8 * 256;
+      ad4s[sl] = a.take<t16>(2 * (size_t)G.P4 * 128);     ad4s[sl + 1] = ad4s[sl] + (size_t)G.P4 * 128;
     }
     use_slot(0);
     res = a.take<float>((size_t)G.HW * 2 * kD);
@@ -439,7 +473,7 @@ struct rmem_engine {
   // ---------------------------------------------------------------------------------------------
   // conv / linear helpers over the generic GEMM
   int conv(const t16* x, int Hin, int Win, int Cin, const std::string& wname, int Cout, int k, int stride, int pad,
-           int act, const t16* resid, t16* out, cudaStream_t s) {
+           int act, const t16* resid, t16* out, cudaStream_t s, int nimg = 1) {
     int rc = RMEM_OK;
     const t16* w = Wt<t16>(wname + ".w", (size_t)Cout * k * k * Cin, &rc);
     const float* b = Wt<float>(wname + ".b", Cout, &rc);
@@ -447,11 +481,12 @@ struct rmem_engine {
     int Hout = (Hin + 2 * pad - k) / stride + 1, Wout = (Win + 2 * pad - k) / stride + 1;
     GemmParams p;
     p.A = x; p.B = w; p.ldb = (long long)k * k * Cin;
-    p.M = Hout * Wout; p.N = Cout; p.K = k * k * Cin;
+    p.M = nimg * Hout * Wout; p.N = Cout; p.K = k * k * Cin;     // images are stacked [n][pixels][channels]
     if (k == 1 && stride == 1) {
       p.lda = Cin;
     } else {
       p.conv = 1; p.Hin = Hin; p.Win = Win; p.Cin = Cin; p.Wout = Wout; p.kw = k; p.stride = stride; p.pad = pad;
+      p.nimg = nimg;
     }
     p.bias = b; p.act = act;
     p.res = resid; p.ldr = Cout;
@@ -487,16 +522,16 @@ struct rmem_engine {
   // ---------------------------------------------------------------------------------------------
   // ResNet-50 stem + layer1..3 (FrozenBN folded) + encoder_projector.   resnet.py:178-195, aot.py:116-134
   int bottleneck(const t16* x, int Hin, int Win, int Cin, const std::string& pre, int planes, int stride, bool has_ds,
-                 t16* out, cudaStream_t s) {
+                 t16* out, cudaStream_t s, int nimg = 1) {
     int Hout = (Hin - 1) / stride + 1, Wout = (Win - 1) / stride + 1;
-    RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".conv1", planes, 1, 1, 0, ACT_RELU, nullptr, t1, s));
-    RMEM_TRY(conv(t1, Hin, Win, planes, pre + ".conv2", planes, 3, stride, 1, ACT_RELU, nullptr, t2, s));
+    RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".conv1", planes, 1, 1, 0, ACT_RELU, nullptr, t1, s, nimg));
+    RMEM_TRY(conv(t1, Hin, Win, planes, pre + ".conv2", planes, 3, stride, 1, ACT_RELU, nullptr, t2, s, nimg));
     const t16* idt = x;
     if (has_ds) {
-      RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".ds", planes * 4, 1, stride, 0, ACT_NONE, nullptr, ds, s));
+      RMEM_TRY(conv(x, Hin, Win, Cin, pre + ".ds", planes * 4, 1, stride, 0, ACT_NONE, nullptr, ds, s, nimg));
       idt = ds;
     }
-    RMEM_TRY(conv(t2, Hout, Wout, planes, pre + ".conv3", planes * 4, 1, 1, 0, ACT_RELU, idt, out, s));
+    RMEM_TRY(conv(t2, Hout, Wout, planes, pre + ".conv3", planes * 4, 1, 1, 0, ACT_RELU, idt, out, s, nimg));
     return RMEM_OK;
   }
 
@@ -506,11 +541,12 @@ struct rmem_engine {
     // before the current frame's propagate (bench / evaluator order).  Anything older was never consumed (skipped frame,
     // exception in the caller): drop it, so that a later tensor the allocator places at the same address cannot pick up
     // stale features.
-    for (int sl = 0; sl < 2; ++sl)
-      if (pending[sl] && pf_age[sl] >= 2) pending[sl] = false;
-    for (int sl = 0; sl < 2; ++sl)
+    // (a pair prefetch is issued two frames ahead and its second member is consumed one call later: ttl 4 instead of 2)
+    for (int sl = 0; sl < kFeatSets; ++sl)
+      if (pending[sl] && pf_age[sl] >= pf_ttl[sl]) pending[sl] = false;
+    for (int sl = 0; sl < kFeatSets; ++sl)
       if (pending[sl]) ++pf_age[sl];
-    for (int sl = 0; sl < 2; ++sl)
+    for (int sl = 0; sl < kFeatSets; ++sl)
       if (pending[sl] && pf_img[sl] == img) {
         RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_done[sl], 0));
         pending[sl] = false;
@@ -520,11 +556,12 @@ struct rmem_engine {
     // inline: the encoder's temporaries are shared with the side stream -> order after whatever is queued there; the
     // current slot's readers were all issued on this stream before, so it can be overwritten in stream order
     if (last_enc_slot >= 0) RMEM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_done[last_enc_slot], 0));
-    // a pending entry may be the NEXT frame (prefetch issued before this call): keep it, encode into the other slot
-    const int sl = pending[fslot] ? (fslot ^ 1) : fslot;
+    // a pending entry may be a COMING frame (prefetch issued before this call): keep it, encode into a free slot
+    const int sl = pending[fslot] ? pick_slot() : fslot;
     pending[sl] = false;
     use_slot(sl);
-    RMEM_TRY(encode_into(img, s, sl));
+    const float* one[1] = {img};
+    RMEM_TRY(encode_into(one, 1, s, sl));
     RMEM_CUDA_CHECK(cudaEventRecord(ev_inline, s));
     inline_valid = true;
     return RMEM_OK;
@@ -535,10 +572,13 @@ struct rmem_engine {
     return RMEM_OK;
   }
 
-  int encode_into(const float* img, cudaStream_t s, int sl) {
+  // n = 1: one frame into feature set sl.  n = 2: two frames into the pair (sl, sl + 1), sl even -- every GEMM / conv of the
+  // encoder runs ONCE over both images (M doubled; convolutions with a fourth tensor-map dimension so that padding stays
+  // per image): the launches are latency-bound at one image, so the pair costs ~1.2x one frame, not 2x.
+  int encode_into(const float* const* imgs, int n, cudaStream_t s, int sl) {
     const Geo& G = g;
     mark("begin", s);
-    RMEM_TRY(pack_image_padded(img, img8, G.H, G.W, s));
+    for (int j = 0; j < n; ++j) RMEM_TRY(pack_image_padded(imgs[j], img8 + (size_t)j * img8_elems, G.H, G.W, s));
     {
       // conv1 (7x7, stride 2, pad 3; resnet.py:178-181) on the tcgen05 kernel: one k-block per window row (gemm.cuh conv = 2)
       int rc = RMEM_OK;
@@ -547,13 +587,15 @@ struct rmem_engine {
       if (rc) return rc;
       GemmParams p;
       p.A = img8; p.B = w; p.ldb = 7 * 64;
-      p.M = G.P1; p.N = 64; p.K = 7 * 64;
+      p.M = n * G.P1; p.N = 64; p.K = 7 * 64;
       p.conv = 2; p.Hin = G.H + 6; p.Win = G.W + 8; p.Cin = 8; p.Wout = G.W1; p.kw = 7; p.stride = 2; p.pad = 3;
+      p.nimg = n;
       p.bias = b; p.act = ACT_RELU;
       p.C = c1; p.ldc = 64;
       RMEM_TRY(gemm_launch(p, s));
     }
-    RMEM_TRY(maxpool3x3s2(c1, x0, G.H1, G.W1, 64, G.H4, G.W4, s));
+    for (int j = 0; j < n; ++j)
+      RMEM_TRY(maxpool3x3s2(c1 + (size_t)j * G.P1 * 64, x0 + (size_t)j * G.P4 * 64, G.H1, G.W1, 64, G.H4, G.W4, s));
     mark("enc.stem", s);
     t16* cur = x0;
     int Hc = G.H4, Wc = G.W4, Cc = 64;
@@ -565,20 +607,20 @@ struct rmem_engine {
         bool has_ds = bi == 0;
         t16* out = (bi == nblk[li] - 1) ? feats[li] : ((cur == x0) ? x1 : x0);
         std::string pre = "enc.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
-        RMEM_TRY(bottleneck(cur, Hc, Wc, Cc, pre, planes[li], st, has_ds, out, s));
+        RMEM_TRY(bottleneck(cur, Hc, Wc, Cc, pre, planes[li], st, has_ds, out, s, n));
         Hc = (Hc - 1) / st + 1; Wc = (Wc - 1) / st + 1; Cc = planes[li] * 4;
         cur = out;
       }
       mark(li == 0 ? "enc.layer1" : (li == 1 ? "enc.layer2" : "enc.layer3"), s);
     }
     Lin p;
-    p.A = feat16s[sl]; p.lda = 1024; p.M = G.HW; p.K = 1024; p.N = kD; p.w = "proj";
+    p.A = feat16s[sl]; p.lda = 1024; p.M = n * G.HW; p.K = 1024; p.N = kD; p.w = "proj";
     p.C = enc_tgts[sl]; p.ldc = kD; p.c_fp32 = 1;
     RMEM_TRY(linear(p, s));
     mark("enc.proj", s);
-    RMEM_TRY(conv(feat16s[sl], G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, nullptr, ad16s[sl], s));
-    RMEM_TRY(conv(feat8s[sl], G.H8, G.W8, 512, "dec.adapter_8x", 256, 1, 1, 0, ACT_NONE, nullptr, ad8s[sl], s));
-    RMEM_TRY(conv(feat4s[sl], G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, nullptr, ad4s[sl], s));
+    RMEM_TRY(conv(feat16s[sl], G.h, G.w, 1024, "dec.adapter_16x", 256, 1, 1, 0, ACT_NONE, nullptr, ad16s[sl], s, n));
+    RMEM_TRY(conv(feat8s[sl], G.H8, G.W8, 512, "dec.adapter_8x", 256, 1, 1, 0, ACT_NONE, nullptr, ad8s[sl], s, n));
+    RMEM_TRY(conv(feat4s[sl], G.H4, G.W4, 256, "dec.adapter_4x", 128, 1, 1, 0, ACT_NONE, nullptr, ad4s[sl], s, n));
     mark("enc.adapters", s);
     return RMEM_OK;
   }
@@ -677,11 +719,45 @@ struct rmem_engine {
     int rc = RMEM_OK;
     const float scale = 1.f / sqrtf((float)kDk);
 
-    // t = LN1(tgt); Q|V = linear_QV(t) (silu on V); U = linear_U(t)
+    // t = LN1(tgt); Q|V = linear_QV(t) (silu on V); U = linear_U(t); ti = id_LN1(tgt_id); ID_U = linear_ID_U(ti).
+    // Two chains of equal length (profiles/r02_timeline_*.txt: the main stream used to idle ~28 us per layer at the join):
+    //   this stream:   LN1 + id_LN1 (one launch) -> linear_QV -> relative-bias GEMM of the short-term branch (needs Q only)
+    //   second stream: value-major copy of the short-term V (previous frame: ready since its update_memory) ->
+    //                  linear_U -> linear_ID_U
+    // so that after the long-term attention kernel (which owns every SM) the short-term branch is only its windowed
+    // attention + depthwise conv, the same length as the long-term tail it runs beside.
     const float* n1g = Wt<float>(pre + ".norm1.g", kD, &rc);
     const float* n1b = Wt<float>(pre + ".norm1.b", kD, &rc);
     if (rc) return rc;
-    RMEM_TRY(layernorm(res, 2 * kD, n1g, n1b, t_ln, kD, nullptr, 0, G.HW, kD, s));
+    if (l > 0) {
+      const float* g1 = Wt<float>(pre + ".id_norm1.g", kD, &rc);
+      const float* b1 = Wt<float>(pre + ".id_norm1.b", kD, &rc);
+      if (rc) return rc;
+      // ti -> curr_ID_V (first half of the linear_ID_V input), also A of linear_ID_U
+      RMEM_TRY(layernorm_pair(res, 2 * kD, n1g, n1b, g1, b1, t_ln, kD, G.HW, kD, s, L.cat, 2 * kD));
+    } else {
+      RMEM_TRY(layernorm(res, 2 * kD, n1g, n1b, t_ln, kD, nullptr, 0, G.HW, kD, s));
+    }
+    t16* gate = (l == 0) ? cu0 : cu;
+    const bool par = use_aux();
+    cudaStream_t s2 = par ? aux_stream : s;          // U and ID_U do not depend on QV: second stream
+    const bool tc_local = cfg.attn_impl != RMEM_ATTN_DENSE;
+    const bool v_early = tc_local && !ref_mode;      // reference frame: its own V is only final after fuse_id below
+    if (par) RMEM_TRY(fork(s));
+    if (v_early)
+      RMEM_TRY(local_attn_tc_prepare_v(L.vid[gr.parity ^ 1], kDv, G.h, G.w, kDv, local_ws, local_ws_bytes, s2));
+    {
+      Lin p;
+      p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_U";
+      p.act = ACT_SILU; p.C = gate; p.ldc = kDv;
+      RMEM_TRY(linear(p, s2));
+    }
+    if (l > 0) {
+      Lin p;
+      p.A = L.cat; p.lda = 2 * kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_ID_U";
+      p.act = ACT_SILU; p.C = gate + 512; p.ldc = kDv;
+      RMEM_TRY(linear(p, s2));
+    }
     {
       Lin p;
       p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = kDk + 2 * kD; p.w = pre + ".linear_QV";
@@ -690,26 +766,13 @@ struct rmem_engine {
       p.C2 = L.vid[cur]; p.ldc2 = kDv; p.n_split = kDk;
       RMEM_TRY(linear(p, s));
     }
-    t16* gate = (l == 0) ? cu0 : cu;
-    const bool par = use_aux();
-    cudaStream_t s2 = par ? aux_stream : s;          // U and ID_U do not depend on QV: second stream
-    if (par) RMEM_TRY(fork(s));
     {
+      // relative-position bias of the windowed attention: rel = Q . rel_emb^T
       Lin p;
-      p.A = t_ln; p.lda = kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_U";
-      p.act = ACT_SILU; p.C = gate; p.ldc = kDv;
-      RMEM_TRY(linear(p, s2));
-    }
-    if (l > 0) {
-      const float* g1 = Wt<float>(pre + ".id_norm1.g", kD, &rc);
-      const float* b1 = Wt<float>(pre + ".id_norm1.b", kD, &rc);
-      if (rc) return rc;
-      // ti = id_LN1(tgt_id) -> curr_ID_V (first half of the linear_ID_V input), also A of linear_ID_U
-      RMEM_TRY(layernorm(res + kD, 2 * kD, g1, b1, L.cat, 2 * kD, nullptr, 0, G.HW, kD, s2));
-      Lin p;
-      p.A = L.cat; p.lda = 2 * kD; p.M = G.HW; p.K = kD; p.N = 2 * kD; p.w = pre + ".linear_ID_U";
-      p.act = ACT_SILU; p.C = gate + 512; p.ldc = kDv;
-      RMEM_TRY(linear(p, s2));
+      p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
+      // the tensor-core kernel reads one aligned 16-float line per window row (".short.rel16": rows re-ordered at pack time)
+      p.w = pre + (tc_local ? ".short.rel16" : ".short.rel"); p.C = rel; p.ldc = 256; p.c_fp32 = 1;
+      RMEM_TRY(linear(p, s));
     }
     if (par) RMEM_TRY(join(s));
 
@@ -760,17 +823,11 @@ struct rmem_engine {
     cudaStream_t sb = par2 ? aux_stream : s;
     t16* sh_attn = par2 ? attn_b : attn_a;
     auto short_branch = [&]() -> int {
-      Lin p;
-      p.A = L.kc[cur]; p.lda = kDk; p.M = G.HW; p.K = kDk; p.N = 256; p.n_weight_rows = 256;   // 225 offsets, zero-padded
-      // the tensor-core kernel reads one aligned 16-float line per window row (".short.rel16": rows re-ordered at pack time)
-      p.w = pre + (cfg.attn_impl == RMEM_ATTN_DENSE ? ".short.rel" : ".short.rel16"); p.C = rel; p.ldc = 256; p.c_fp32 = 1;
-      RMEM_TRY(linear(p, sb));
-      mark("gpm.short.rel", sb);
-      if (cfg.attn_impl == RMEM_ATTN_DENSE)
+      if (!tc_local)
         RMEM_TRY(local_attn(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, gate, kDv, sh_attn, kDv, G.h, G.w, kDv, scale, sb));
       else
         RMEM_TRY(local_attn_tc(L.kc[cur], kDk, sk, kDk, sv, kDv, rel, 256, 16, gate, kDv, sh_attn, kDv, G.h, G.w, kDv,
-                               scale, local_ws, local_ws_bytes, sb));
+                               scale, local_ws, local_ws_bytes, sb, v_early));
       mark("gpm.short.attn", sb);
       return gated_tail_dw(pre + ".short", sh_attn, dwo2 + kDv, sb, 2 * kDv);
     };
@@ -1254,7 +1311,7 @@ int rmem_engine_restart(rmem_engine* e) {
   RMEM_API_BEGIN
   RMEM_REQUIRE(e, "null engine");
   e->n_groups = 0;
-  e->pending[0] = e->pending[1] = false;
+  for (int sl = 0; sl < kFeatSets; ++sl) e->pending[sl] = false;
   for (auto& gr : e->groups) {
     gr.evict_pending = false;
     gr.slots.clear(); gr.free_slots.clear(); gr.long_idx.clear(); gr.ema.clear(); gr.times.clear();
@@ -1331,33 +1388,53 @@ int rmem_engine_propagate(rmem_engine* e, const float* img, int Ho, int Wo, floa
 // no dependency on the memory bank; aot.py:116-134 is a pure function of the image).  `img` must be ready on `stream`
 // and stay untouched until the rmem_engine_propagate call that consumes it has been issued; that call must pass the
 // same pointer (anything else falls back to the inline encoder).  Results are bit-identical to the unprefetched path.
-int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream) {
-  RMEM_API_BEGIN
-  RMEM_REQUIRE(e && img, "null argument");
+static int prefetch_n(rmem_engine* e, const float* const* imgs, int n, void* stream) {
   if (e->timing) return RMEM_OK;            // stage timing serialises the frame; keep it on one stream
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // the slot that does not hold an unconsumed prefetch; the current slot's readers have all been issued
-  int sl = e->pending[e->fslot ^ 1] ? e->fslot : (e->fslot ^ 1);
-  if (e->pending[sl]) sl = e->pf_seq[0] < e->pf_seq[1] ? 0 : 1;   // both unconsumed: the older one is stale, replace it
+  // a slot (pair of slots) that holds no unconsumed prefetch; the current slot's readers have all been issued
+  const int sl = n == 2 ? e->pick_pair() : e->pick_slot();
   RMEM_CUDA_CHECK(cudaEventRecord(e->ev_img_ready, s));
   RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_img_ready, 0));
-  if (e->feat_free_valid[sl]) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_feat_free[sl], 0));
+  for (int j = 0; j < n; ++j)
+    if (e->feat_free_valid[sl + j]) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_feat_free[sl + j], 0));
   if (e->inline_valid) RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_inline, 0));
   const bool pdl_was = pdl_enabled();
   {
     static const bool side_pdl = [] { const char* e = getenv("RMEM_SIDE_PDL"); return e && e[0] == '1'; }();
     pdl_enabled() = side_pdl && pdl_was;    // see common.cuh: no early-launched grids on the side stream
   }
-  const int rc = e->encode_into(img, e->enc_stream, sl);
+  const int rc = e->encode_into(imgs, n, e->enc_stream, sl);
   pdl_enabled() = pdl_was;
   if (rc) return rc;
-  RMEM_CUDA_CHECK(cudaEventRecord(e->ev_done[sl], e->enc_stream));
-  e->pending[sl] = true;
-  e->pf_img[sl] = img;
-  e->pf_seq[sl] = ++e->pf_counter;
-  e->pf_age[sl] = 0;
-  e->last_enc_slot = sl;
+  for (int j = 0; j < n; ++j) {
+    RMEM_CUDA_CHECK(cudaEventRecord(e->ev_done[sl + j], e->enc_stream));
+    e->pending[sl + j] = true;
+    e->pf_img[sl + j] = imgs[j];
+    e->pf_seq[sl + j] = ++e->pf_counter;
+    e->pf_age[sl + j] = 0;
+    e->pf_ttl[sl + j] = n == 2 ? 4 : 2;
+  }
+  e->last_enc_slot = sl + n - 1;
   return RMEM_OK;
+}
+
+int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(e && img, "null argument");
+  const float* one[1] = {img};
+  return prefetch_n(e, one, 1, stream);
+  RMEM_API_END
+}
+
+// Two coming frames in ONE encoder pass (see encode_into).  Meant to be issued two frames ahead -- before the propagate of
+// frame i for frames i+2 and i+3, every second frame -- so that the pass has two frame periods to complete; each image
+// is consumed by the rmem_engine_propagate call that passes the same pointer, exactly like a single prefetch.  The pair's
+// results agree with the single-frame encoder to fp16 rounding of a differently tiled GEMM, not bit for bit.
+int rmem_engine_prefetch2(rmem_engine* e, const float* img_a, const float* img_b, void* stream) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(e && img_a && img_b && img_a != img_b, "prefetch2: two distinct images");
+  const float* two[2] = {img_a, img_b};
+  return prefetch_n(e, two, 2, stream);
   RMEM_API_END
 }
 

@@ -263,6 +263,7 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
 
 int gemm_legacy_launch(const GemmParams& p, cudaStream_t stream) {
   RMEM_REQUIRE(p.A && p.B && p.C, "gemm: null operand");
+  RMEM_REQUIRE(p.nimg == 1, "gemm: stacked images (nimg=%d) exist on the tcgen05 kernel only", p.nimg);
   RMEM_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty shape M=%d N=%d K=%d", p.M, p.N, p.K);
   RMEM_REQUIRE(p.K % 8 == 0, "gemm: K=%d must be a multiple of 8", p.K);
   RMEM_REQUIRE(p.ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm: B not 16B aligned");

@@ -21,6 +21,9 @@ struct GemmParams {
   // k-block per window row: the 64 contiguous elements (8 pixels x 8 channels) starting at padded pixel (oy*2 + ky,
   // ox*2); B = [N][kw rows][8 pixels][8 channels] with zero weights for the 8th pixel, K = kw * 64.
   int conv = 0, Hin = 0, Win = 0, Cin = 0, Wout = 0, kw = 1, stride = 1, pad = 0;
+  // conv modes, tcgen05 kernel only: nimg images of [Hin,Win,Cin] stacked in A and [Hout*Wout, N] blocks stacked in C / res
+  // (M = nimg * Hout * Wout); padding and tile edges are handled per image.
+  int nimg = 1;
   // epilogue
   float alpha = 1.f;
   const float* bias = nullptr;  // [N] (or [M] if bias_m)

@@ -37,6 +37,7 @@ struct TcGemmParams {
   int M, N, nk, stages;
   int splitk;                 // CTAs per cluster along K (1 = no split)
   int conv, taps_w, cin_blocks, pad, stride, BW, BH, tiles_x, Hout, Wout;
+  int nimg, tiles_img;        // conv modes: images stacked along M (4-D tensor map), row tiles per image
   int sx, sy;                 // coordinate steps of the A tensor map per output pixel (conv: stride, stride; stem: 1, 2)
   float alpha;
   const float* bias;
@@ -138,9 +139,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   long long* const gtrace = (blockIdx.y * gridDim.x + blockIdx.x) < 64 ? g_gemm_trace : nullptr;
   if (warp == 0) GTRACE(0);
   const int n0 = blockIdx.x * BN;
-  int m0 = blockIdx.y * TBM, x0 = 0, y0 = 0;
+  int m0 = blockIdx.y * TBM, x0 = 0, y0 = 0, img = 0;
   if (p.conv) {
-    const int ty = blockIdx.y / p.tiles_x, tx = blockIdx.y - ty * p.tiles_x;
+    int t = blockIdx.y;
+    if (p.nimg > 1) { img = t / p.tiles_img; t -= img * p.tiles_img; }
+    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
     x0 = tx * p.BW;
     y0 = ty * p.BH;
   }
@@ -179,7 +182,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.conv) {
           const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
           const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
-          tma_load_3d(sa, &map_a, &full[st], cb * TBK, x0 * p.sx - p.pad + kx, y0 * p.sy - p.pad + ky);
+          if (p.nimg > 1)
+            tma_load_4d(sa, &map_a, &full[st], cb * TBK, x0 * p.sx - p.pad + kx, y0 * p.sy - p.pad + ky, img);
+          else
+            tma_load_3d(sa, &map_a, &full[st], cb * TBK, x0 * p.sx - p.pad + kx, y0 * p.sy - p.pad + ky);
         } else {
           tma_load_2d(sa, &map_a, &full[st], kb * TBK, m0);
         }
@@ -225,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (p.conv) {
       const int yy = y0 + r / p.BW, xx = x0 + r % p.BW;
       valid = yy < p.Hout && xx < p.Wout;
-      gm = (long long)yy * p.Wout + xx;
+      gm = ((long long)img * p.Hout + yy) * p.Wout + xx;
     } else {
       gm = m0 + r;
       valid = gm < p.M;
@@ -427,6 +433,15 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
     if (S > p.nk / 4) S = p.nk / 4;
     if (S < 2) S = 1;
   }
+  // One wave at two CTAs per SM: a long-K convolution with more tiles than half the SMs (layer2's 3x3 at 1/8 resolution:
+  // 102 tiles x 36 k-blocks) still halves its per-SM operand ingest with S = 2 when both CTAs of every cluster stay
+  // resident (shallow ring, see below): 20.7 -> 15.5 us (tools/tune_gemm.py).
+  bool shallow = false;
+  if (BN == 64 && S == 1 && gemm_splitk_switch() && p.conv == 1 && p.nk >= 32 && tiles <= tc_sm_count() &&
+      tiles * 2 > tc_sm_count()) {
+    S = 2;
+    shallow = true;
+  }
   if (BN == 64 && tc_force().splitk > 0) {
     S = tc_force().splitk;
     if (S > kMaxSplitK) S = kMaxSplitK;
@@ -436,6 +451,12 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
   // Only as many stages as there are k-blocks: short-K GEMMs (most of the encoder) are latency-bound, and a small
   // shared-memory footprint lets several CTAs share an SM so one CTA's epilogue overlaps another's loads.
   const int nkl = cdiv(p.nk, S);
+  if (shallow) max_stages = 2;
+  // A grid that fits the SMs one CTA each is operand-ingest bound per SM (header): give it the deepest ring -- whose
+  // footprint (> half of the 227 KB) also keeps the block scheduler from stacking two CTAs on one SM while others idle
+  // (K = 2048 tail projection, 112 CTAs: 22.8 -> 16.6 us; tools/tune_gemm.py).
+  static const bool deep = [] { const char* e = getenv("RMEM_GEMM_DEEP"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (deep && S == 1 && tiles <= tc_sm_count() && nkl >= 6) max_stages = BN == 256 ? 4 : kMaxStages;
   if (tc_force().stages > 0) {
     max_stages = tc_force().stages;
     const int cap = BN == 256 ? 4 : (S > 1 ? 4 : kMaxStages);     // what the shared-memory attribute above covers
@@ -500,15 +521,16 @@ bool gemm_tc_supported(const GemmParams& p) {
   if (p.res && ((reinterpret_cast<uintptr_t>(p.res) & 15) || p.ldr % 8 != 0)) return false;
   if (p.gate && ((reinterpret_cast<uintptr_t>(p.gate) & 15) || p.ldg % 8 != 0)) return false;
   if (p.bias && !p.bias_m && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
+  if (p.nimg < 1 || (p.nimg > 1 && !p.conv)) return false;
   if (p.conv == 2) {                       // stem mode (see gemm.cuh): K = kw rows of 64 contiguous elements
     if (p.K != p.kw * TBK || p.stride != 2 || p.Cin != 8) return false;
-    if (p.M % p.Wout != 0) return false;
+    if (p.M % (p.Wout * p.nimg) != 0) return false;
     if ((long long)(p.Wout - 1) * 2 * p.Cin + TBK > (long long)p.Win * p.Cin) return false;   // last window inside the row
   } else if (p.conv) {
     if (p.Cin % TBK != 0) return false;
     if (p.K % (p.kw * p.Cin) != 0) return false;
     if (p.stride < 1 || p.stride > 2) return false;
-    if (p.M % p.Wout != 0) return false;
+    if (p.M % (p.Wout * p.nimg) != 0) return false;
   } else {
     if (p.lda % 8 != 0) return false;
   }
@@ -522,7 +544,7 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
   p.conv = g.conv; p.taps_w = g.kw; p.cin_blocks = g.conv == 1 ? g.Cin / TBK : 1; p.pad = g.pad; p.stride = g.stride;
   p.sx = p.sy = g.stride;
   if (g.conv == 2) { p.taps_w = 1; p.pad = 0; p.sx = 1; p.sy = 2; }   // k-block kb = window row ky; padding is physical
-  p.BW = 128; p.BH = 1; p.tiles_x = 1; p.Hout = 0; p.Wout = g.Wout;
+  p.BW = 128; p.BH = 1; p.tiles_x = 1; p.Hout = 0; p.Wout = g.Wout; p.nimg = g.nimg; p.tiles_img = 0;
   p.alpha = g.alpha; p.bias = g.bias; p.bias_m = g.bias_m; p.act = g.act; p.act_from = g.act_from;
   p.res = g.res; p.ldr = g.ldr; p.gate = g.gate; p.ldg = g.ldg; p.accumulate = g.accumulate;
   p.C = g.C; p.ldc = g.ldc; p.c_fp32 = g.c_fp32; p.C2 = g.C2; p.ldc2 = g.ldc2; p.c2_fp32 = g.c2_fp32;
@@ -533,8 +555,9 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
   int m_tiles;
   const CUtensorMap *ma = nullptr, *mb = nullptr;
   if (g.conv) {
-    const int Hout = g.M / g.Wout;
+    const int Hout = g.M / (g.Wout * g.nimg);
     p.Hout = Hout;
+    const int rank = g.nimg > 1 ? 4 : 3;   // images = a fourth tensor-map dimension (box 1): padding stays per image
     // rectangular 128-pixel patch that wastes the fewest tile slots
     int best = 1 << 30;
     for (int bw = 128; bw >= 8; bw >>= 1) {
@@ -544,22 +567,23 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
       if (n < best) { best = n; p.BW = bw; p.BH = bh; }
     }
     p.tiles_x = cdiv(g.Wout, p.BW);
-    m_tiles = best;
+    p.tiles_img = best;
+    m_tiles = best * g.nimg;
     if (g.conv == 2) {
       // Stem: the A row of output pixel (oy, ox) and window row ky is the 64 contiguous elements (8 pixels x 8 channels,
       // the 8th pixel meets zero weights) that start at padded pixel (oy*2 + ky, ox*2): a tensor map whose second
       // dimension steps by TWO pixels (32 bytes) while the first one spans 64 elements -- overlapping rows.
-      uint64_t dims[3] = {(uint64_t)TBK, (uint64_t)g.Wout, (uint64_t)g.Hin};
-      uint64_t strides[2] = {(uint64_t)2 * g.Cin * 2, (uint64_t)g.Win * g.Cin * 2};
-      uint32_t box[3] = {(uint32_t)TBK, (uint32_t)p.BW, (uint32_t)(p.BH * 2)};
-      uint32_t estr[3] = {1, 1, 2};
-      RMEM_TRY(tma_encode_cached(&ma, g.A, 3, dims, strides, box, estr));
+      uint64_t dims[4] = {(uint64_t)TBK, (uint64_t)g.Wout, (uint64_t)g.Hin, (uint64_t)g.nimg};
+      uint64_t strides[3] = {(uint64_t)2 * g.Cin * 2, (uint64_t)g.Win * g.Cin * 2, (uint64_t)g.Hin * g.Win * g.Cin * 2};
+      uint32_t box[4] = {(uint32_t)TBK, (uint32_t)p.BW, (uint32_t)(p.BH * 2), 1};
+      uint32_t estr[4] = {1, 1, 2, 1};
+      RMEM_TRY(tma_encode_cached(&ma, g.A, rank, dims, strides, box, estr));
     } else {
-    uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Win, (uint64_t)g.Hin};
-    uint64_t strides[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Win * g.Cin * 2};
-    uint32_t box[3] = {(uint32_t)TBK, (uint32_t)(p.BW * g.stride), (uint32_t)(p.BH * g.stride)};
-    uint32_t estr[3] = {1, (uint32_t)g.stride, (uint32_t)g.stride};
-    RMEM_TRY(tma_encode_cached(&ma, g.A, 3, dims, strides, box, estr));
+    uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.Win, (uint64_t)g.Hin, (uint64_t)g.nimg};
+    uint64_t strides[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Win * g.Cin * 2, (uint64_t)g.Hin * g.Win * g.Cin * 2};
+    uint32_t box[4] = {(uint32_t)TBK, (uint32_t)(p.BW * g.stride), (uint32_t)(p.BH * g.stride), 1};
+    uint32_t estr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+    RMEM_TRY(tma_encode_cached(&ma, g.A, rank, dims, strides, box, estr));
     }
   } else {
     m_tiles = cdiv(g.M, TBM);
@@ -569,7 +593,10 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
     RMEM_TRY(tma_encode_cached(&ma, g.A, 2, dims, strides, box, nullptr));
   }
   int BN = 128;
-  if (g.N <= 64 || m_tiles * cdiv(g.N, 128) < 120) BN = 64;
+  // (a wide tile only when it still gives every SM a CTA: N = 1152 x 14 row tiles = 126 wide tiles ran 10.7 us, 252 narrow
+  // ones 8.5 us, and the narrow CTAs share an SM with the other streams' kernels)
+  static const int wide_min = [] { const char* e = getenv("RMEM_GEMM_WIDE_MIN"); return e ? atoi(e) : 148; }();
+  if (g.N <= 64 || m_tiles * cdiv(g.N, 128) < wide_min) BN = 64;
   else if (g.N >= 256 && g.K >= 512 && m_tiles * cdiv(g.N, 256) >= 148) BN = 256;
   if (tc_force().bn) BN = tc_force().bn;
   if (tc_log().buf && tc_log().n < tc_log().cap) {

@@ -501,9 +501,21 @@ size_t local_attn_tc_workspace(int h, int w, int Dv) {
   return (size_t)Dv * h * wp * sizeof(t16) + 256;
 }
 
+int local_attn_tc_prepare_v(const t16* v, long long ldv, int h, int w, int Dv, void* workspace, size_t workspace_bytes,
+                            cudaStream_t s) {
+  RMEM_REQUIRE(workspace && workspace_bytes >= local_attn_tc_workspace(h, w, Dv), "local_attn_tc: workspace too small");
+  RMEM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "local_attn_tc: workspace alignment");
+  const int wp = round_up(w, 8);
+  dim3 grid(cdiv(wp, 64), cdiv(Dv, 64), h), block(32, 8);
+  RMEM_CUDA_CHECK(launch_pdl(transpose_pad_kernel, dim3(grid), dim3(block), 0, s, v, ldv, reinterpret_cast<t16*>(workspace),
+                             h, w, wp, Dv));
+  RMEM_LAUNCH_CHECK();
+  return RMEM_OK;
+}
+
 int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, const t16* v, long long ldv,
                   const float* rel, long long ldrel, int rel_pitch, const t16* gate, long long ldg, t16* out, long long ldo, int h,
-                  int w, int Dv, float scale, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                  int w, int Dv, float scale, void* workspace, size_t workspace_bytes, cudaStream_t s, bool v_prepared) {
   RMEM_REQUIRE(Dv % DVC == 0, "local_attn_tc: Dv=%d must be a multiple of 256", Dv);
   RMEM_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && (!gate || ldg % 8 == 0),
                "local_attn_tc: row strides must keep 16B alignment");
@@ -511,11 +523,7 @@ int local_attn_tc(const t16* q, long long ldq, const t16* k, long long ldk, cons
   RMEM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "local_attn_tc: workspace alignment");
   const int wp = round_up(w, 8);
   t16* vt = reinterpret_cast<t16*>(workspace);
-  {
-    dim3 grid(cdiv(wp, 64), cdiv(Dv, 64), h), block(32, 8);
-    RMEM_CUDA_CHECK(launch_pdl(transpose_pad_kernel, dim3(grid), dim3(block), 0, s, v, ldv, vt, h, w, wp, Dv));
-    RMEM_LAUNCH_CHECK();
-  }
+  if (!v_prepared) RMEM_TRY(local_attn_tc_prepare_v(v, ldv, h, w, Dv, workspace, workspace_bytes, s));
   const CUtensorMap *mq, *mk, *mv;
   {
     uint64_t dims[3] = {(uint64_t)DK, (uint64_t)w, (uint64_t)h};

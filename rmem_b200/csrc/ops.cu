@@ -104,7 +104,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
 // in one launch: warp -> (row, half).
 __global__ void layernorm_pair_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g0,
                                       const float* __restrict__ b0, const float* __restrict__ g1,
-                                      const float* __restrict__ b1, t16* __restrict__ y, long long ldy, int P, int C) {
+                                      const float* __restrict__ b1, t16* __restrict__ y, long long ldy,
+                                      t16* __restrict__ y1, long long ldy1, int P, int C) {
   pdl_prologue();
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -129,7 +130,9 @@ __global__ void layernorm_pair_kernel(const float* __restrict__ x, long long ldx
   for (int j = 0; j < LN_MAXV; ++j)
     if (j < nv) {
       int c = j * 32 + lane;
-      y[(long long)row * ldy + half * C + c] = f2t((v[j] - mean) * rstd * gamma[c] + beta[c]);
+      const float o = (v[j] - mean) * rstd * gamma[c] + beta[c];
+      if (half && y1) y1[(long long)row * ldy1 + c] = f2t(o);     // second half to its own destination
+      else y[(long long)row * ldy + half * C + c] = f2t(o);
     }
 }
 
@@ -1176,9 +1179,10 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
 }
 
 int layernorm_pair(const float* x, long long ldx, const float* g0, const float* b0, const float* g1, const float* b1,
-                   t16* y, long long ldy, int P, int C, cudaStream_t s) {
+                   t16* y, long long ldy, int P, int C, cudaStream_t s, t16* y1, long long ldy1) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm_pair: unsupported C=%d", C);
-  RMEM_CUDA_CHECK(launch_pdl(layernorm_pair_kernel, dim3(cdiv(2 * P, 8)), dim3(256), 0, s, x, ldx, g0, b0, g1, b1, y, ldy, P, C));
+  RMEM_CUDA_CHECK(launch_pdl(layernorm_pair_kernel, dim3(cdiv(2 * P, 8)), dim3(256), 0, s, x, ldx, g0, b0, g1, b1, y, ldy,
+                             y1, ldy1, P, C));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }

@@ -15,8 +15,10 @@ int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wo
 
 // LayerNorm over C (eps 1e-5): x fp32 [P, ldx] -> y t16 [P, ldy] (+ optional second copy y2).
 // `add2` (fp32 [P, C], optional): y2 = t16(LN(x) + add2) instead of a plain copy (AOT sine PE on q, k).
+// layernorm_pair: the two C-wide halves of a [P, 2C] row normalised in one launch; the second half goes to
+// y[:, C:2C] or, when y1 is given, to y1[:, 0:C] (row stride ldy1).
 int layernorm_pair(const float* x, long long ldx, const float* g0, const float* b0, const float* g1, const float* b1,
-                   t16* y, long long ldy, int P, int C, cudaStream_t s);
+                   t16* y, long long ldy, int P, int C, cudaStream_t s, t16* y1 = nullptr, long long ldy1 = 0);
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy,
               t16* y2, long long ldy2, int P, int C, cudaStream_t s, const float* add2 = nullptr);
 

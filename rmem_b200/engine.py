@@ -285,6 +285,18 @@ class DeAOTInferEngine:
         sp = C.c_void_p(stream.cuda_stream) if stream is not None else _capi.stream_ptr()
         _capi.check(_capi.load().rmem_engine_prefetch(self._h, _capi.ptr(img), sp))
 
+    def prefetch2(self, img_a: torch.Tensor, img_b: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """Pair prefetch: the two frames AFTER the next one (i+2, i+3 when issued before frame i is propagated) go through
+        the image encoder in one pass -- every encoder GEMM / conv launch covers both images.  Issue it every second
+        frame; each tensor is passed unchanged to its own propagate call later.  Same math, differently tiled GEMMs:
+        agrees with the single-frame encoder to fp16 rounding, not bit for bit."""
+        if self._h is None:
+            return
+        for img in (img_a, img_b):
+            assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous(), "prefetch needs the engine-ready tensor"
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else _capi.stream_ptr()
+        _capi.check(_capi.load().rmem_engine_prefetch2(self._h, _capi.ptr(img_a), _capi.ptr(img_b), sp))
+
     def update_memory(self, label: torch.Tensor):
         """aot_engine.py:714-720 -> AOTEngine.update_short_term_memory (:327-396)."""
         lib = _capi.load()

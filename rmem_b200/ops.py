@@ -63,15 +63,18 @@ def gemm(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, act: int = ACT_NONE,
                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x t16 [Hin,Win,Cin]; w t16 [Cout,kh,kw,Cin] -> t16 [Hout,Wout,Cout]."""
+    """x t16 [Hin,Win,Cin] (or a stack [n,Hin,Win,Cin]); w t16 [Cout,kh,kw,Cin] -> t16 [(n,)Hout,Wout,Cout]."""
     lib = _capi.load()
-    Hin, Win, Cin = x.shape
+    nimg = x.shape[0] if x.dim() == 4 else 1
+    Hin, Win, Cin = x.shape[-3:]
     Cout, kh, kw, _ = w.shape
     Hout, Wout = (Hin + 2 * pad - kh) // stride + 1, (Win + 2 * pad - kw) // stride + 1
-    out = torch.empty(Hout, Wout, Cout, dtype=_capi.op_dtype(), device=x.device)
+    oshape = (nimg, Hout, Wout, Cout) if x.dim() == 4 else (Hout, Wout, Cout)
+    out = torch.empty(*oshape, dtype=_capi.op_dtype(), device=x.device)
     d = _capi.GemmDesc()
     d.A, d.B, d.ldb = x.data_ptr(), w.data_ptr(), kh * kw * Cin
-    d.M, d.N, d.K = Hout * Wout, Cout, kh * kw * Cin
+    d.M, d.N, d.K = nimg * Hout * Wout, Cout, kh * kw * Cin
+    d.n_images = nimg
     d.conv, d.Hin, d.Win, d.Cin, d.Wout, d.kw, d.stride, d.pad = 1, Hin, Win, Cin, Wout, kw, stride, pad
     d.alpha = 1.0
     d.bias = bias.data_ptr()

@@ -177,6 +177,52 @@ def test_prefetched_encoder_is_bit_identical(cuda_device, model):
         assert idx == idx0, mode
 
 
+@pytest.mark.parametrize("model", ["r50_deaotl", "r50_aotl"])
+def test_pair_prefetch_matches_single_frame_encoder(cuda_device, model):
+    """rmem_engine_prefetch2 encodes frames i+2, i+3 in one pass (every encoder GEMM / conv over both images, 4-D tensor
+    maps): same math, differently tiled, so not bit-identical -- teacher-forced with the inline run's labels, every frame's
+    1/4-res logits must agree within 2e-3 of the logit range (far inside the 1.5e-2 engine tolerance), labels >= 99.9 %,
+    identical eviction indices; frames the pair did not cover (odd clip end, wrong pointer) fall back to the inline encoder."""
+    from rmem_b200.engine import RmemModel, RmemConfig, build_engine
+    H, W, n_obj, gap = 257, 321, 3, 2
+    sd = O.make_state_dict(model, seed=3, sharpen=4.0)
+    frames = O.synthetic_frames(12, H, W, seed=11).to(cuda_device)
+    label0 = O.synthetic_label(H, W, n_obj).int().to(cuda_device)
+    cfg = RmemConfig(model=model, former_mem_len=1, latter_mem_len=2)
+    eng = build_engine("deaotengine" if model == "r50_deaotl" else "aotengine", phase="eval",
+                       aot_model=RmemModel(sd, cfg, cuda_device), gpu_id=0, long_term_mem_gap=gap)
+    n = frames.shape[0]
+
+    def run(pairs, forced=None):
+        eng.restart_engine()
+        eng.long_term_mem_gap = gap
+        eng.add_reference_frame(frames[0:1], label0, obj_nums=[n_obj], frame_step=0)
+        labs, logits, idx = [], [], []
+        for f in range(1, n):
+            if pairs and f % 2 == 1 and f + 3 < n:
+                eng.prefetch2(frames[f + 2:f + 3], frames[f + 3:f + 4])
+            lab = eng.propagate_label(frames[f:f + 1])
+            logits.append(eng.logits4_views()[0].clone())
+            eng.update_memory(forced[f - 1] if forced is not None else lab)
+            labs.append(lab.clone())
+            idx.append(list(eng.aot_engines[0].long_memories_indexes))
+        torch.cuda.synchronize()
+        return labs, logits, idx
+
+    l0 = eng.launch_count
+    base_l, base_g, base_i = run(False)
+    l1 = eng.launch_count
+    pair_l, pair_g, pair_i = run(True, forced=base_l)
+    l2 = eng.launch_count
+    assert pair_i == base_i
+    assert l2 - l1 < l1 - l0 - 100, "the pair encoder did not run"      # 4 pairs = 4 encoder passes (~50 launches each) saved
+    for f in range(n - 1):
+        err = float((pair_g[f] - base_g[f]).abs().max() / base_g[f].abs().max())
+        agree = float((pair_l[f] == base_l[f]).float().mean())
+        assert err < 2e-3 and agree >= 0.999, (f, err, agree)
+    assert torch.equal(pair_g[0], base_g[0])          # frames 1, 2 were never prefetched: the inline encoder, bit for bit
+
+
 def test_evaluator_shell_cuda_engine_vs_oracle_engine(cuda_device, tmp_path):
     """The same clip directory through rmem_b200.evaluator with the CUDA engine and with the CPU oracle engine: decoded
     frames, resize rule, reference frame, propagate / update loop, new-object re-reference and the PNG writer are shared;

@@ -81,6 +81,31 @@ def test_conv_matches_torch_and_legacy(K, cuda_device, cfg):
     assert relfro(tc, leg) < 1.5e-3, cfg
 
 
+@pytest.mark.parametrize("cfg", [(31, 54, 256, 256, 3, 1, 1, 2), (61, 107, 128, 128, 3, 2, 1, 2), (121, 213, 64, 64, 3, 1, 1, 2),
+                                 (121, 213, 256, 512, 1, 2, 0, 2), (17, 17, 64, 64, 3, 1, 1, 3)])
+def test_stacked_image_conv_matches_per_image_conv(K, cuda_device, cfg):
+    """n images stacked along M (4-D tensor map, rmem_gemm_desc.n_images; the pair encoder of rmem_engine_prefetch2): the
+    halo of one image never reads its neighbour, results agree with torch per image and with the single-image launch."""
+    H, W, Cin, Cout, k, stride, pad, n = cfg
+    OP = _capi.op_dtype()
+    g = torch.Generator().manual_seed(H * W + Cin + n)
+    x = torch.randn(n, H, W, Cin, generator=g).to(cuda_device).to(OP)
+    w = (torch.randn(Cout, k, k, Cin, generator=g) / math.sqrt(k * k * Cin)).to(cuda_device).to(OP)
+    b = torch.randn(Cout, generator=g).to(cuda_device)
+    pre = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b, stride=stride, padding=pad)
+    pre = pre.permute(0, 2, 3, 1)
+    ref = torch.relu(pre)
+    res = torch.randn(*ref.shape, generator=g).to(cuda_device).to(OP)
+    out = K.conv2d_nhwc(x, w, b, stride, pad, act=K.ACT_RELU)
+    assert out.shape == ref.shape
+    assert relfro(out, ref) < 1.5e-3, cfg
+    for i in range(n):
+        one = K.conv2d_nhwc(x[i].contiguous(), w, b, stride, pad, act=K.ACT_RELU)
+        assert relfro(out[i], one) < 1e-3, (cfg, i)
+    out2 = K.conv2d_nhwc(x, w, b, stride, pad, act=K.ACT_RELU, residual=res)
+    assert relfro(out2, torch.relu(pre + res.float())) < 1.5e-3, cfg
+
+
 def test_splitk_is_bit_reproducible_and_matches_unsplit(K, cuda_device, monkeypatch):
     """The cluster split-K reduction adds the partial tiles in rank order: two runs give identical bits, and the
     result agrees with torch fp32 like the unsplit kernel does."""

@@ -90,8 +90,8 @@ def main():
     import re
 
     def short(n):
-        n = re.sub(r"\(.*", "", n).replace("(anonymous namespace)::", "").replace("rmem::", "").replace("void ", "")
-        return n[:40]
+        n = n.replace("(anonymous namespace)::", "").replace("rmem::", "").replace("void ", "")
+        return re.sub(r"\(.*", "", n)[:40]
     print(f"# {len(evs)} device activities over {a.frames} frame(s) x {a.clips} clip(s); times in us from the first one")
     print(f"# {'start':>9s} {'dur':>8s} {'stream':>6s}  name")
     for s, e, st, nm, kind in evs:
