@@ -321,7 +321,10 @@ def measure_two_clips(eng, dev, rank, world, args, frames_a, label0, fill, barri
     def step(k, i):
         e, src = engs[k], srcs[k]
         with torch.cuda.stream(streams[k]):
-            if PREFETCH:
+            if PREFETCH and args.enc_pairs:
+                if i % 2 == 0:
+                    e.prefetch2(src[1 + (i + 2) % ring: 2 + (i + 2) % ring], src[1 + (i + 3) % ring: 2 + (i + 3) % ring])
+            elif PREFETCH:
                 e.prefetch(src[1 + (i + 1) % ring: 2 + (i + 1) % ring])
             lab = e.propagate_label(src[1 + i % ring: 2 + i % ring], output_size=(H, W))
             e.update_memory(lab)
@@ -332,10 +335,13 @@ def measure_two_clips(eng, dev, rank, world, args, frames_a, label0, fill, barri
             engs[k].restart_engine()
             engs[k].long_term_mem_gap = GAP
             engs[k].add_reference_frame(srcs[k][0:1], label0.int().to(dev), obj_nums=[N_OBJ], frame_step=0)
-    for i in range(max(fill, args.warmup)):
+    nwarm = max(fill, args.warmup)
+    nwarm += nwarm % 2
+    for i in range(nwarm):
         for k in range(NC):
             step(k, i)
     torch.cuda.synchronize()
+    pos = nwarm                                         # the frame index runs on across the timed blocks
     for e in engs:
         assert len(e.aot_engines[0].long_memories_indexes) == FORMER + LATTER, "bank not full after warm-up"
     blocks = []
@@ -345,9 +351,10 @@ def measure_two_clips(eng, dev, rank, world, args, frames_a, label0, fill, barri
         e0.record(main)
         for k in range(NC):
             streams[k].wait_event(e0)
-        for i in range(args.steps):
+        for i in range(pos, pos + args.steps):
             for k in range(NC):
                 step(k, i)
+        pos += args.steps
         for k in range(NC):
             main.wait_stream(streams[k])
         e1.record(main)

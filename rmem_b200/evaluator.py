@@ -260,14 +260,33 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         for k in range(len(ring)):
             ring[k] = None
 
-    nxt = fetch(0)
+    # Frames are known ahead of time: up to three are fetched (and copied to the device) ahead of the one being propagated,
+    # and their image encoder runs on the engine's side stream meanwhile -- two frames per encoder pass
+    # (engine.prefetch2: frames i+2, i+3, every second frame), a single frame (engine.prefetch) where no pair covers it
+    # (clip start, odd clip end).  Same-size frames only: a size change rebuilds the engine.
+    can_pair = can_prefetch and hasattr(engine, "prefetch2") and os.environ.get("RMEM_EVAL_ENC_PAIRS", "1") != "0"
+    look: List = []                        # fetched frames frame_idx + 1 ..
+    fetched = 0
+    covered = set()                        # frames whose encoding has been issued
+
+    def ensure(n):
+        nonlocal fetched
+        while len(look) < n and fetched < len(dataset):
+            look.append(fetch(fetched))
+            fetched += 1
+
     for frame_idx in range(len(dataset)):
-        meta, img, label = nxt
-        nxt = fetch(frame_idx + 1) if frame_idx + 1 < len(dataset) else None
-        # frames are known ahead of time: the next one is encoded on the engine's side stream while this one propagates
-        # (same-size frames only -- a size change rebuilds the engine)
-        if can_prefetch and frame_idx >= 1 and nxt is not None and nxt[1].shape == img.shape:
-            engine.prefetch(nxt[1])
+        ensure(1)
+        meta, img, label = look.pop(0)
+        ensure(3 if can_pair else 1)
+        if can_prefetch and frame_idx >= 1:
+            if look and frame_idx + 1 not in covered and look[0][1].shape == img.shape:
+                engine.prefetch(look[0][1])
+                covered.add(frame_idx + 1)
+            if can_pair and len(look) >= 3 and frame_idx + 2 not in covered and \
+                    look[1][1].shape == img.shape and look[2][1].shape == img.shape:
+                engine.prefetch2(look[1][1], look[2][1])
+                covered.update((frame_idx + 2, frame_idx + 3))
         if frame_idx == 0:
             if label is None:
                 raise ValueError(f"{dataset.seq_name}: the first frame has no label")

@@ -18,21 +18,29 @@ def main():
         cfg = RmemConfig(model=model, former_mem_len=1, latter_mem_len=latter, max_engines=(n_obj + 9) // 10)
         eng = build_engine("deaotengine" if model == "r50_deaotl" else "aotengine", aot_model=RmemModel(sd, cfg, dev),
                            long_term_mem_gap=1)
-        frames = synthetic_frames(5, H, W, seed=1000).to(dev)
+        frames = synthetic_frames(9, H, W, seed=1000).to(dev)
+        R = 8
+        pairs = os.environ.get("RMEM_BENCH_ENC_PAIRS", "1") != "0"
         eng.add_reference_frame(frames[0:1], synthetic_label(H, W, n_obj).int().to(dev), obj_nums=[n_obj], frame_step=0)
         def step(i):
-            eng.prefetch(frames[1 + (i + 1) % 4:2 + (i + 1) % 4])
-            lab = eng.propagate_label(frames[1 + i % 4:2 + i % 4], output_size=(H, W))
+            if pairs:
+                if i % 2 == 0:
+                    eng.prefetch2(frames[1 + (i + 2) % R:2 + (i + 2) % R], frames[1 + (i + 3) % R:2 + (i + 3) % R])
+            else:
+                eng.prefetch(frames[1 + (i + 1) % R:2 + (i + 1) % R])
+            lab = eng.propagate_label(frames[1 + i % R:2 + i % R], output_size=(H, W))
             eng.update_memory(lab)
-        for i in range(latter + 3):
+        n0 = latter + 3 + (latter + 3) % 2
+        for i in range(n0):
             step(i)
         eng.long_term_mem_gap = 5
-        for i in range(10):
+        for i in range(n0, n0 + 10):
             step(i)
+        n0 += 10
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(a.frames):
+        for i in range(n0, n0 + a.frames):
             step(i)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.frames
