@@ -473,7 +473,7 @@ struct rmem_engine {
   // ---------------------------------------------------------------------------------------------
   // conv / linear helpers over the generic GEMM
   int conv(const t16* x, int Hin, int Win, int Cin, const std::string& wname, int Cout, int k, int stride, int pad,
-           int act, const t16* resid, t16* out, cudaStream_t s, int nimg = 1) {
+           int act, const t16* resid, t16* out, cudaStream_t s, int nimg = 1, double* gn_stats = nullptr, int gn_groups = 0) {
     int rc = RMEM_OK;
     const t16* w = Wt<t16>(wname + ".w", (size_t)Cout * k * k * Cin, &rc);
     const float* b = Wt<float>(wname + ".b", Cout, &rc);
@@ -491,6 +491,7 @@ struct rmem_engine {
     p.bias = b; p.act = act;
     p.res = resid; p.ldr = Cout;
     p.C = out; p.ldc = Cout;
+    p.gn_stats = gn_stats; p.gn_groups = gn_groups;
     return gemm_launch(p, s);
   }
 
@@ -736,7 +737,9 @@ struct rmem_engine {
       // ti -> curr_ID_V (first half of the linear_ID_V input), also A of linear_ID_U
       RMEM_TRY(layernorm_pair(res, 2 * kD, n1g, n1b, g1, b1, t_ln, kD, G.HW, kD, s, L.cat, 2 * kD));
     } else {
-      RMEM_TRY(layernorm(res, 2 * kD, n1g, n1b, t_ln, kD, nullptr, 0, G.HW, kD, s));
+      // first layer: the residual stream starts here -- tgt = projector output, tgt_id = 0 (transformer.py:786-790),
+      // written by the same launch instead of a copy and a memset in front of it
+      RMEM_TRY(layernorm(enc_tgt, kD, n1g, n1b, t_ln, kD, nullptr, 0, G.HW, kD, s, nullptr, res, 2 * kD));
     }
     t16* gate = (l == 0) ? cu0 : cu;
     const bool par = use_aux();
@@ -893,10 +896,7 @@ struct rmem_engine {
   int lstt_decode(Group& gr, bool ref_mode, cudaStream_t s) {
     const Geo& G = g;
     int rc = RMEM_OK;
-    // residual stream: tgt = projector output, tgt_id = 0
-    RMEM_CUDA_CHECK(cudaMemcpy2DAsync(res, 2 * kD * sizeof(float), enc_tgt, kD * sizeof(float), kD * sizeof(float),
-                                      G.HW, cudaMemcpyDeviceToDevice, s));
-    RMEM_CUDA_CHECK(cudaMemset2DAsync(res + kD, 2 * kD * sizeof(float), 0, kD * sizeof(float), G.HW, s));
+    // residual stream: tgt = projector output, tgt_id = 0 -- initialised by layer 0's LayerNorm launch (gpm_layer)
     if (!ones_ready) {
       RMEM_TRY(fill_t16(cu0 + 512, kDv, G.HW, 512, 1.0f, s));
       ones_ready = true;
@@ -914,30 +914,45 @@ struct rmem_engine {
   int fpn_decode(Group& gr, const t16* x16, int cin, cudaStream_t s) {
     const Geo& G = g;
     int rc = RMEM_OK;
+    // The GroupNorm statistics of every decoder convolution come out of that convolution's own epilogue (fp32 results,
+    // GemmParams::gn_stats): four statistics launches less per frame and object group.  RMEM_GN_FUSED=0: separate pass.
+    static const bool fused = [] { const char* e = getenv("RMEM_GN_FUSED"); return !(e && e[0] == '0'); }();
+    double* st = fused ? stats : nullptr;
     auto gn = [&](const std::string& n, const t16* x, t16* y, int P, int C, const t16* add) -> int {
       int r2 = RMEM_OK;
       const float* gg = Wt<float>(n + ".gn.g", C, &r2);
       const float* gb = Wt<float>(n + ".gn.b", C, &r2);
       if (r2) return r2;
-      return groupnorm_t16(x, gg, gb, y, P, C, 8, 1, stats, s, add);
+      return groupnorm_t16(x, gg, gb, y, P, C, 8, 1, stats, s, add, fused);
     };
     // x = adapter(feature) + x at every scale: the adapter maps (ad16 / ad8 / ad4) were computed with the encoder
-    RMEM_TRY(conv(x16, G.h, G.w, cin, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s));
+    RMEM_TRY(conv(x16, G.h, G.w, cin, "dec.conv_in", 256, 1, 1, 0, ACT_NONE, nullptr, d0, s, 1, st, 8));
     RMEM_TRY(gn("dec.conv_in", d0, d1, G.HW, 256, ad16));                          // relu(GN(conv_in)) + adapter_16x(feat16)
-    RMEM_TRY(conv(d1, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s));
-    RMEM_TRY(gn("dec.conv_16x", d2, d1, G.HW, 256, nullptr));
-    RMEM_TRY(upsample_bilinear_t16(d1, d2, G.h, G.w, G.H8, G.W8, 256, s, ad8));    // up(x) + adapter_8x(feat8)
-    RMEM_TRY(conv(d2, G.H8, G.W8, 256, "dec.conv_8x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
-    RMEM_TRY(gn("dec.conv_8x", d0, d1, G.P8, 128, nullptr));
-    RMEM_TRY(upsample_bilinear_t16(d1, d2, G.H8, G.W8, G.H4, G.W4, 128, s, ad4));  // up(x) + adapter_4x(feat4)
-    RMEM_TRY(conv(d2, G.H4, G.W4, 128, "dec.conv_4x", 128, 3, 1, 1, ACT_NONE, nullptr, d0, s));
+    // ... and where the normalised map is only upsampled, relu(GroupNorm) is applied to the taps inside the upsample kernel
+    auto up_gn = [&](const std::string& n, const t16* x, t16* tmp, t16* y, int hin, int win, int hout, int wout, int C,
+                     const t16* add) -> int {
+      if (!fused) {
+        RMEM_TRY(gn(n, x, tmp, hin * win, C, nullptr));
+        return upsample_bilinear_t16(tmp, y, hin, win, hout, wout, C, s, add);
+      }
+      int r2 = RMEM_OK;
+      const float* gg = Wt<float>(n + ".gn.g", C, &r2);
+      const float* gb = Wt<float>(n + ".gn.b", C, &r2);
+      if (r2) return r2;
+      return upsample_bilinear_t16(x, y, hin, win, hout, wout, C, s, add, stats, gg, gb, 8);
+    };
+    RMEM_TRY(conv(d1, G.h, G.w, 256, "dec.conv_16x", 256, 3, 1, 1, ACT_NONE, nullptr, d2, s, 1, st, 8));
+    RMEM_TRY(up_gn("dec.conv_16x", d2, d1, d0, G.h, G.w, G.H8, G.W8, 256, ad8));      // up(relu(GN(x))) + adapter_8x(feat8)
+    RMEM_TRY(conv(d0, G.H8, G.W8, 256, "dec.conv_8x", 128, 3, 1, 1, ACT_NONE, nullptr, d2, s, 1, st, 8));
+    RMEM_TRY(up_gn("dec.conv_8x", d2, d1, d0, G.H8, G.W8, G.H4, G.W4, 128, ad4));     // up(relu(GN(x))) + adapter_4x(feat4)
+    RMEM_TRY(conv(d0, G.H4, G.W4, 128, "dec.conv_4x", 128, 3, 1, 1, ACT_NONE, nullptr, d2, s, 1, st, 8));
     const t16* wo = Wt<t16>("dec.conv_out.w", (size_t)11 * 128, &rc);
     const float* bo = Wt<float>("dec.conv_out.b", 11, &rc);
     const float* g4 = Wt<float>("dec.conv_4x.gn.g", 128, &rc);
     const float* b4 = Wt<float>("dec.conv_4x.gn.b", 128, &rc);
     if (rc) return rc;
     // GroupNorm(8) + ReLU of the 1/4-resolution map folded into the conv_out kernel's tile load
-    RMEM_TRY(conv_out_gn_logits(d0, g4, b4, 8, stats, wo, bo, gr.logits4, G.P4, 128, 11, s));
+    RMEM_TRY(conv_out_gn_logits(d2, g4, b4, 8, stats, wo, bo, gr.logits4, G.P4, 128, 11, s, fused));
     mark("decoder", s);
     return RMEM_OK;
   }

@@ -45,6 +45,11 @@ struct GemmParams {
   // N % 32 != 0 only: columns N .. round_up(N,32)-1 of C may be written with padding values (no residual / gate /
   // per-column bias in that case).  Lets the tcgen05 kernel store whole 32-column chunks.
   int pad_n_ok = 0;
+  // tcgen05 kernel only: GroupNorm statistics of the (t16, single-destination, un-activated) output over gn_groups
+  // channel groups, written to gn_stats[2 * group] = (sum, sum of squares) in double -- the scratch block of
+  // groupnorm_t16 (ops.cuh, kGnScratchDoubles doubles), so that groupnorm_apply_t16 can follow without a statistics pass.
+  double* gn_stats = nullptr;
+  int gn_groups = 0;
   // batched mode (legacy kernel only): blockIdx.z selects a problem; element strides between problems
   int batch = 1;
   long long sA = 0, sB = 0, sC = 0;

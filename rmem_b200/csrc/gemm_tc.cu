@@ -54,6 +54,13 @@ struct TcGemmParams {
   long long ldc2;
   int c2_fp32, n_split;
   int* err;
+  // GroupNorm statistics of the output, produced by the epilogue (the FPN decoder's conv -> GroupNorm pairs): per
+  // (row tile, 32-column chunk, lane quadrant) fp32 partial sums of the fp32 results, folded in a fixed order and in double
+  // by the last CTA to finish -> gn_stats[2 * group] = (sum, sum of squares).  gn_cpg = channels per group (16 | 32).
+  double* gn_stats;
+  float4* gn_part;
+  unsigned int* gn_counter;
+  int gn_cpg;
 };
 
 constexpr int kMaxStages = 6;
@@ -301,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += rv[j * TBM];
       }
-      if (!valid) return;
+      if (!valid && !p.gn_stats) return;             // (statistics: every lane takes part in the warp reductions below)
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(&s_bias[c0 + j]);
@@ -336,6 +343,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           v[j * 8] *= a.x; v[j * 8 + 1] *= a.y; v[j * 8 + 2] *= b.x; v[j * 8 + 3] *= b.y;
           v[j * 8 + 4] *= c.x; v[j * 8 + 5] *= c.y; v[j * 8 + 6] *= d.x; v[j * 8 + 7] *= d.y;
         }
+      }
+      if (p.gn_stats) {
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        if (valid) {
+          if (p.gn_cpg >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); s1 += v[16 + j]; q1 = fmaf(v[16 + j], v[16 + j], q1); }
+          }
+        }
+        s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
+        if (lane == 0)
+          p.gn_part[((size_t)blockIdx.y * (p.N >> 5) + (n >> 5)) * 4 + quad] = make_float4(s0, q0, s1, q1);
+        if (!valid) return;
       }
       if (warp == 2 && c0 == 0) GTRACE(6);
       if (f32) {
@@ -372,12 +395,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int cc = 0; cc < kHalfCols; cc += 32) chunk(cbeg + cc);
     }
     }
+    if (p.gn_stats) __threadfence();                 // this warp's partial sums are visible before the CTA signs off
     fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     fence_after();
     tmem_dealloc<BN>(tmem);
+  }
+  if (p.gn_stats && krank == 0) {
+    // last CTA to finish: fold the partials -- thread -> (output o = (group, sum | sum of squares), slice j); slice j adds
+    // slots j, j + J, ... in order, the J slices are then added in order: a fixed summation order, bit-reproducible
+    __shared__ bool gn_last;
+    __shared__ double gn_sh[kTcThreads];
+    if (threadIdx.x == 0) gn_last = atomicAdd(p.gn_counter, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (gn_last) {
+      __threadfence();
+      const int chunks = p.N >> 5, gpc = p.gn_cpg >= 32 ? 1 : 2;      // groups per 32-column chunk
+      const int n_out = chunks * gpc * 2, J = kTcThreads / n_out;
+      const int o = threadIdx.x % n_out, j = threadIdx.x / n_out;
+      const int grp = o >> 1, which = o & 1;
+      const int chunk = grp / gpc, comp = (grp % gpc) * 2 + which;    // float4 component holding this output
+      double a = 0.0;
+      if (j < J) {
+        const int nslots = (int)gridDim.y * 4;                        // (row tile, quadrant) pairs
+        for (int k = j; k < nslots; k += J) {
+          const float4 f = p.gn_part[((size_t)(k >> 2) * chunks + chunk) * 4 + (k & 3)];
+          a += (double)(comp == 0 ? f.x : comp == 1 ? f.y : comp == 2 ? f.z : f.w);
+        }
+      }
+      gn_sh[threadIdx.x] = a;
+      __syncthreads();
+      if (threadIdx.x < n_out) {
+        double t = 0.0;
+        for (int jj = 0; jj < J; ++jj) t += gn_sh[jj * n_out + threadIdx.x];
+        p.gn_stats[threadIdx.x] = t;
+      }
+      if (threadIdx.x == 0) *p.gn_counter = 0u;                       // re-arm for the next launch on this stream
+    }
   }
 }
 
@@ -550,6 +606,17 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
   p.C = g.C; p.ldc = g.ldc; p.c_fp32 = g.c_fp32; p.C2 = g.C2; p.ldc2 = g.ldc2; p.c2_fp32 = g.c2_fp32;
   p.n_split = g.n_split;
   p.err = nullptr;   // watchdog traps without a flag word (the library never allocates device memory)
+  p.gn_stats = g.gn_stats; p.gn_cpg = 0; p.gn_part = nullptr; p.gn_counter = nullptr;
+  if (g.gn_stats) {
+    RMEM_REQUIRE(g.gn_groups > 0 && g.N % g.gn_groups == 0 && (g.N / g.gn_groups == 16 || g.N / g.gn_groups == 32) &&
+                 g.N % 32 == 0 && g.N <= 256 && !g.c_fp32 && g.n_split >= g.N && g.act == ACT_NONE && !g.gate,
+                 "gemm_tc: GroupNorm statistics need 16 or 32 channels per group, N <= 256, one t16 destination (N=%d G=%d)",
+                 g.N, g.gn_groups);
+    p.gn_cpg = g.N / g.gn_groups;
+    // scratch layout shared with the stand-alone statistics kernel (ops.cuh): [0,64) stats | [64] counter | [72,..) partials
+    p.gn_counter = reinterpret_cast<unsigned int*>(g.gn_stats + 64);
+    p.gn_part = reinterpret_cast<float4*>(g.gn_stats + 72);
+  }
 
   // ---- tile width: fill the 148 SMs, then prefer wide tiles (fewer A re-reads) ----
   int m_tiles;

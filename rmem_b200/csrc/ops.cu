@@ -71,7 +71,8 @@ __global__ void maxpool_kernel(const t16* __restrict__ x, t16* __restrict__ y, i
 constexpr int LN_MAXV = 16;  // C <= 512
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, t16* __restrict__ y, long long ldy,
-                                 t16* __restrict__ y2, long long ldy2, const float* __restrict__ add2, int P, int C) {
+                                 t16* __restrict__ y2, long long ldy2, const float* __restrict__ add2, int P, int C,
+                                 float* __restrict__ init_res, long long ld_init) {
   pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
@@ -97,6 +98,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
       t16 o = f2t(of);
       y[(long long)row * ldy + c] = o;
       if (y2) y2[(long long)row * ldy2 + c] = add2 ? f2t(of + add2[(long long)row * C + c]) : o;
+      if (init_res) {                       // start of a residual stream [x | 0] (DualBranchGPM: tgt = x, tgt_id = 0)
+        init_res[(long long)row * ld_init + c] = v[j];
+        init_res[(long long)row * ld_init + C + c] = 0.f;
+      }
     }
 }
 
@@ -241,14 +246,16 @@ constexpr int kGnMaxBlocks = 148 * 4;
 
 template <typename T>
 int groupnorm_impl(const T* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
-                   double* stats, cudaStream_t s, const t16* add = nullptr) {
+                   double* stats, cudaStream_t s, const t16* add = nullptr, bool stats_ready = false) {
   RMEM_REQUIRE(C % 8 == 0 && G <= 32 && C % G == 0 && (C / G) % 8 == 0 && 256 % (C / 8) == 0,
                "groupnorm: unsupported C=%d G=%d", C, G);
   // scratch layout (doubles): [0,64) stats | [64] counter (zero-initialised once, self re-arming) | [72,..) partials
-  int rows_per_block = 256 / (C / 8);
-  int grid = min(cdiv(P, rows_per_block), kGnMaxBlocks);     // one row group per block until the grid cap: parallelism first
-  RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<T>, dim3(grid), dim3(256), 0, s, x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
-  RMEM_LAUNCH_CHECK();
+  if (!stats_ready) {     // (stats_ready: the producing GEMM's epilogue left them there, GemmParams::gn_stats)
+    int rows_per_block = 256 / (C / 8);
+    int grid = min(cdiv(P, rows_per_block), kGnMaxBlocks);     // one row group per block until the grid cap: parallelism first
+    RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<T>, dim3(grid), dim3(256), 0, s, x, P, C, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
+    RMEM_LAUNCH_CHECK();
+  }
   long long nvec = (long long)P * (C / 8);
   RMEM_CUDA_CHECK(launch_pdl(gn_apply_kernel<T>, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, s, x, gamma, beta, y, P, C, G, relu, static_cast<const double*>(stats), add));
   RMEM_LAUNCH_CHECK();
@@ -338,8 +345,11 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
   return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
 }
 
+// gn_stats != nullptr: x is the un-normalised convolution output; relu(GroupNorm(x)) (statistics given, G groups) is
+// applied to each of the four taps on load, so the normalised map is never written (fpn.py:46-60: up(relu(gn(conv)))).
 __global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__ y, int hin, int win, int hout,
-                                     int wout, int C, const t16* __restrict__ add) {
+                                     int wout, int C, const t16* __restrict__ add, const double* __restrict__ gn_stats,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, int G) {
   pdl_prologue();
   const int cv = C / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +365,21 @@ __global__ void upsample_t16_kernel(const t16* __restrict__ x, t16* __restrict__
   load8(x + ((size_t)y0 * win + x1) * C + c8 * 8, b);
   load8(x + ((size_t)y1 * win + x0) * C + c8 * 8, c);
   load8(x + ((size_t)y1 * win + x1) * C + c8 * 8, d);
+  if (gn_stats) {                              // same arithmetic as gn_apply_kernel (8 channels never straddle a group)
+    const int g = (c8 * 8) / (C / G);
+    const double n = (double)hin * win * (C / G);
+    const double mean = gn_stats[g * 2] / n;
+    const double var = gn_stats[g * 2 + 1] / n - mean * mean;
+    const float fm = (float)mean, rstd = rsqrtf(fmaxf((float)var, 0.f) + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float ga = gamma[c8 * 8 + k], be = beta[c8 * 8 + k];
+      a[k] = fmaxf((a[k] - fm) * rstd * ga + be, 0.f);
+      b[k] = fmaxf((b[k] - fm) * rstd * ga + be, 0.f);
+      c[k] = fmaxf((c[k] - fm) * rstd * ga + be, 0.f);
+      d[k] = fmaxf((d[k] - fm) * rstd * ga + be, 0.f);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = bilerp(a[k], b[k], c[k], d[k], wy0, wy1, wx0, wx1);
   if (add) {                                   // FPN: adapter(feature) + upsample(x), fpn.py:50-60
@@ -1171,9 +1196,11 @@ int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wo
 }
 
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy, t16* y2,
-              long long ldy2, int P, int C, cudaStream_t s, const float* add2) {
+              long long ldy2, int P, int C, cudaStream_t s, const float* add2, float* init_res, long long ld_init) {
   RMEM_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm: unsupported C=%d", C);
-  RMEM_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, x, ldx, gamma, beta, y, ldy, y2, ldy2, add2, P, C));
+  RMEM_REQUIRE(!init_res || ld_init >= 2 * C, "layernorm: init_res needs a row stride >= 2C");
+  RMEM_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3(cdiv(P, 8)), dim3(256), 0, s, x, ldx, gamma, beta, y, ldy, y2, ldy2, add2, P, C,
+                             init_res, ld_init));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -1188,8 +1215,8 @@ int layernorm_pair(const float* x, long long ldx, const float* g0, const float* 
 }
 
 int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
-                   double* stats, cudaStream_t s, const t16* add) {
-  return groupnorm_impl<t16>(x, gamma, beta, y, P, C, G, relu, stats, s, add);
+                   double* stats, cudaStream_t s, const t16* add, bool stats_ready) {
+  return groupnorm_impl<t16>(x, gamma, beta, y, P, C, G, relu, stats, s, add, stats_ready);
 }
 int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s) {
@@ -1215,10 +1242,12 @@ int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaSt
 }
 
 int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s,
-                          const t16* add) {
+                          const t16* add, const double* gn_stats, const float* gamma, const float* beta, int G) {
   RMEM_REQUIRE(C % 8 == 0, "upsample: C %% 8");
+  RMEM_REQUIRE(!gn_stats || (gamma && beta && G > 0 && C % G == 0 && (C / G) % 8 == 0), "upsample: GroupNorm arguments (C=%d G=%d)", C, G);
   long long n = (long long)hout * wout * (C / 8);
-  RMEM_CUDA_CHECK(launch_pdl(upsample_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, y, hin, win, hout, wout, C, add));
+  RMEM_CUDA_CHECK(launch_pdl(upsample_t16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, y, hin, win, hout, wout, C, add,
+                             gn_stats, gamma, beta, G));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -1233,13 +1262,15 @@ int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int 
 }
 
 int conv_out_gn_logits(const t16* x, const float* gamma, const float* beta, int G, double* stats, const t16* w,
-                       const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s) {
+                       const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s, bool stats_ready) {
   RMEM_REQUIRE(Cin % 32 == 0 && Cin <= 128 && Cout <= 16 && (Cin / 8) % 2 == 0, "conv_out_gn: unsupported Cin=%d Cout=%d", Cin, Cout);
   RMEM_REQUIRE(G <= 32 && Cin % G == 0 && (Cin / G) % 8 == 0 && 256 % (Cin / 8) == 0, "conv_out_gn: unsupported C=%d G=%d", Cin, G);
-  const int rows_per_block = 256 / (Cin / 8);
-  const int grid = min(cdiv(P, rows_per_block), kGnMaxBlocks);
-  RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<t16>, dim3(grid), dim3(256), 0, s, x, P, Cin, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
-  RMEM_LAUNCH_CHECK();
+  if (!stats_ready) {
+    const int rows_per_block = 256 / (Cin / 8);
+    const int grid = min(cdiv(P, rows_per_block), kGnMaxBlocks);
+    RMEM_CUDA_CHECK(launch_pdl(gn_stats_kernel<t16>, dim3(grid), dim3(256), 0, s, x, P, Cin, G, stats, stats + 72, reinterpret_cast<unsigned int*>(stats + 64)));
+    RMEM_LAUNCH_CHECK();
+  }
   const size_t smem = (size_t)(Cin / 8) * 16 * 8 * sizeof(float) + (size_t)2 * Cin * sizeof(float) + (size_t)64 * (Cin * 2 + 16);
   RMEM_CUDA_CHECK(launch_pdl(conv_out_gn_kernel, dim3(cdiv(P, 64)), dim3(128), smem, s, x, w, b, gamma, beta,
                              static_cast<const double*>(stats), G, out, P, Cin, Cout));

@@ -20,14 +20,16 @@ int maxpool3x3s2(const t16* x, t16* y, int Hin, int Win, int C, int Hout, int Wo
 int layernorm_pair(const float* x, long long ldx, const float* g0, const float* b0, const float* g1, const float* b1,
                    t16* y, long long ldy, int P, int C, cudaStream_t s, t16* y1 = nullptr, long long ldy1 = 0);
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, t16* y, long long ldy,
-              t16* y2, long long ldy2, int P, int C, cudaStream_t s, const float* add2 = nullptr);
+              t16* y2, long long ldy2, int P, int C, cudaStream_t s, const float* add2 = nullptr,
+              // optional: also start a residual stream from x: init_res[:, 0:C] = x, init_res[:, C:2C] = 0 (fp32, row stride ld_init)
+              float* init_res = nullptr, long long ld_init = 0);
 
 // GroupNorm over (pixels x C/G) per group, eps 1e-5, optional ReLU.  `stats` = kGnScratchDoubles doubles of
 // scratch whose element [64] (the block counter) must be zero before the first call; it re-arms itself.
 constexpr int kGnScratchDoubles = 72 + 148 * 4 * 64;
 // `add` (optional, [P,C] t16): added to the normalised + activated map before the store
 int groupnorm_t16(const t16* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
-                   double* stats, cudaStream_t s, const t16* add = nullptr);
+                   double* stats, cudaStream_t s, const t16* add = nullptr, bool stats_ready = false);
 int groupnorm_f32(const float* x, const float* gamma, const float* beta, t16* y, int P, int C, int G, int relu,
                   double* stats, cudaStream_t s);
 
@@ -50,7 +52,10 @@ int dwconv5x5(const t16* x, const float* w, t16* y, int h, int wd, int C, cudaSt
 
 // Bilinear resize, align_corners=True, NHWC t16.                                         (fpn.py:50,58)
 int upsample_bilinear_t16(const t16* x, t16* y, int hin, int win, int hout, int wout, int C, cudaStream_t s,
-                          const t16* add = nullptr);   // add: optional [hout*wout, C] t16 added to the interpolated map
+                          const t16* add = nullptr,    // add: optional [hout*wout, C] t16 added to the interpolated map
+                          // optional: x is an un-normalised conv output, relu(GroupNorm(x)) with these statistics (the
+                          // stats block of groupnorm_t16 / GemmParams::gn_stats) is applied to the taps on load
+                          const double* gn_stats = nullptr, const float* gamma = nullptr, const float* beta = nullptr, int G = 0);
 
 // 1x1 conv to the 11 ID logits, planar fp32 output [11, P].                                (fpn.py:66)
 int conv_out_logits(const t16* x, const t16* w, const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
@@ -59,7 +64,7 @@ int gru_reset(const float* gates, long long ldg, const float* h, t16* comb_h, lo
 int gru_blend(const float* gates_u, long long ldg, const float* cand, float* h, t16* h16, int P, int C, cudaStream_t s);
 // out = conv_out(relu(GroupNorm_G(x))) in two launches (statistics, fused normalise + 1x1 conv): the decoder tail, fpn.py:62-67
 int conv_out_gn_logits(const t16* x, const float* gamma, const float* beta, int G, double* stats, const t16* w,
-                       const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s);
+                       const float* b, float* out, int P, int Cin, int Cout, cudaStream_t s, bool stats_ready = false);
 
 // [P, C] (row stride ldx) -> [C, ldy] transposed copy.
 int transpose_t16(const t16* x, long long ldx, t16* y, long long ldy, int P, int C, cudaStream_t s);
