@@ -134,7 +134,8 @@ def run_ours(args):
         eng.long_term_mem_gap = GAP
         eng.add_reference_frame(src[0:1], label0.int().to(dev), obj_nums=[N_OBJ], frame_step=0)
 
-    PAIRS = PREFETCH and args.enc_pairs
+    EG = args.enc_group if PREFETCH else 1               # frames per encoder pass (1 = single-frame prefetch)
+    PAIRS = EG > 1
 
     def fr(src, k):
         return src[1 + k % ring: 2 + k % ring]
@@ -143,8 +144,8 @@ def run_ours(args):
         # software pipelining across frames: the image encoder runs on the engine's side stream while frame i propagates
         # -- frame i+1 alone, or (pair mode) frames i+2 and i+3 in one pass every second frame
         if PAIRS:
-            if i % 2 == 0:
-                eng.prefetch2(fr(src, i + 2), fr(src, i + 3))
+            if i % EG == 0:
+                eng.prefetch_n([fr(src, i + EG + j) for j in range(EG)])
         elif PREFETCH:
             eng.prefetch(fr(src, i + 1))
         lab = eng.propagate_label(fr(src, i), output_size=(H, W))
@@ -161,7 +162,7 @@ def run_ours(args):
     # host->device copy of frame i+1 is issued on a copy stream while frame i computes (what a prefetching loader does,
     # evaluator.py:308,372 uses pin_memory + non_blocking); both copies are inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    NS = 4 if PAIRS else 2                                 # staging buffers: frames i .. i+3 are live in pair mode
+    NS = 2 * EG if PAIRS else 2                            # staging buffers: frames i .. i+2*EG-1 are live in group mode
     stage = [torch.empty(1, 3, H, W, dtype=torch.float32, device=dev) for _ in range(NS)]
     staged = [torch.cuda.Event() for _ in range(NS)]
     consumed = [torch.cuda.Event() for _ in range(NS)]
@@ -185,7 +186,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if e2e and first == 0:                              # very first e2e frame(s): nothing staged yet
-            for k in range(2 if PAIRS else 1):
+            for k in range(EG if PAIRS else 1):
                 prefetch(k, src)
         for i in range(first, first + steps):
             if e2e:
@@ -194,10 +195,10 @@ def run_ours(args):
                 # consumed by the next block (the frame index runs on), so every block copies and encodes exactly
                 # `steps` frames inside its timed region.
                 if PAIRS:
-                    if i % 2 == 0:
-                        prefetch(i + 2, src)
-                        prefetch(i + 3, src)
-                        eng.prefetch2(stage[(i + 2) % NS], stage[(i + 3) % NS], stream=copy_stream)
+                    if i % EG == 0:
+                        for j in range(EG):
+                            prefetch(i + EG + j, src)
+                        eng.prefetch_n([stage[(i + EG + j) % NS] for j in range(EG)], stream=copy_stream)
                 else:
                     prefetch(i + 1, src)
                     if PREFETCH:
@@ -230,7 +231,7 @@ def run_ours(args):
     # ---- device-resident run ----
     clip_start(frames_dev)
     nwarm = max(fill, args.warmup)
-    nwarm += nwarm % 2                                    # pair mode: blocks start on an even frame index
+    nwarm += (-nwarm) % 4                                 # group mode: blocks start on a multiple of the group size
     for i in range(nwarm):
         step(i, frames_dev)
     counter["dev"] = nwarm
@@ -282,8 +283,8 @@ def run_ours(args):
                                "eval script uses 1 + 8 (T=9): bench.py --latter 8 runs that setting",
                        "l2": "per-frame working set (banks 3x37 MB + activations + 150 MB attention workspace) "
                              "exceeds the 126 MB L2; no explicit flush",
-                       "pipeline": (("every second step = prefetch2(frames i+2, i+3: ONE pass of the image encoder over both "
-                                     "images on the engine's side stream); each step = propagate(frame i) + "
+                       "pipeline": ((f"every {EG}th step = prefetch_n(frames i+{EG} .. i+{2 * EG - 1}: ONE pass of the image encoder over "
+                                     f"{EG} images on the engine's side stream); each step = propagate(frame i) + "
                                      "update_memory(frame i); every frame is encoded exactly once, inside the timed region "
                                      "of the block that issues it") if PAIRS else
                                     ("each step = prefetch(frame i+1: image encoder on the engine's side stream) + "
@@ -311,6 +312,7 @@ def measure_two_clips(eng, dev, rank, world, args, frames_a, label0, fill, barri
     from rmem_b200.synth import synthetic_frames
     ring = frames_a.shape[0] - 1
     NC = args.clips_in_flight
+    EG = args.enc_group
     engs, srcs = [eng], [frames_a]
     for k in range(1, NC):
         srcs.append(synthetic_frames(ring + 1, H, W, seed=5000 * k + rank).to(dev))
@@ -321,9 +323,9 @@ def measure_two_clips(eng, dev, rank, world, args, frames_a, label0, fill, barri
     def step(k, i):
         e, src = engs[k], srcs[k]
         with torch.cuda.stream(streams[k]):
-            if PREFETCH and args.enc_pairs:
-                if i % 2 == 0:
-                    e.prefetch2(src[1 + (i + 2) % ring: 2 + (i + 2) % ring], src[1 + (i + 3) % ring: 2 + (i + 3) % ring])
+            if PREFETCH and EG > 1:
+                if i % EG == 0:
+                    e.prefetch_n([src[1 + (i + EG + j) % ring: 2 + (i + EG + j) % ring] for j in range(EG)])
             elif PREFETCH:
                 e.prefetch(src[1 + (i + 1) % ring: 2 + (i + 1) % ring])
             lab = e.propagate_label(src[1 + i % ring: 2 + i % ring], output_size=(H, W))
@@ -336,7 +338,7 @@ def measure_two_clips(eng, dev, rank, world, args, frames_a, label0, fill, barri
             engs[k].long_term_mem_gap = GAP
             engs[k].add_reference_frame(srcs[k][0:1], label0.int().to(dev), obj_nums=[N_OBJ], frame_step=0)
     nwarm = max(fill, args.warmup)
-    nwarm += nwarm % 2
+    nwarm += (-nwarm) % 4
     for i in range(nwarm):
         for k in range(NC):
             step(k, i)
@@ -621,8 +623,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=10)
     ap.add_argument("--ref-max-steps", type=int, default=20)
     ap.add_argument("--repeat", type=int, default=10, help="timed blocks of --steps steps; the median block is reported")
-    ap.add_argument("--enc-pairs", type=int, default=int(os.environ.get("RMEM_BENCH_ENC_PAIRS", "1")),
-                    help="1 = the image encoder runs over two coming frames per pass (rmem_engine_prefetch2); 0 = one frame ahead")
+    ap.add_argument("--enc-group", type=int, default=int(os.environ.get("RMEM_BENCH_ENC_GROUP", "2")), choices=[1, 2, 4],
+                    help="frames per pass of the image encoder (rmem_engine_prefetch_n, issued that many frames ahead); "
+                         "1 = single-frame prefetch")
     ap.add_argument("--clips-in-flight", type=int, default=2,
                     help="2 = also time two independent clips per GPU (extra key two_clips_in_flight); 1 = skip that leg")
     ap.add_argument("--latter", type=int, default=LATTER, help="LATTER_MEM_LEN (7 = T=8 as BASELINE.json names it)")

@@ -271,6 +271,9 @@ int rmem_engine_prefetch(rmem_engine* e, const float* img, void* stream);
  * same pointer and must stay untouched until then.  Same math as the single-frame encoder, differently tiled: results agree to
  * fp16 rounding, not bit for bit. */
 int rmem_engine_prefetch2(rmem_engine* e, const float* img_a, const float* img_b, void* stream);
+/* The general form: n = 1, 2 or 4 coming frames (HOST array of n device pointers) in one encoder pass.  A group of n is
+ * meant to be issued n frames ahead -- before rmem_engine_propagate of frame i for frames i+n .. i+2n-1, every n-th frame. */
+int rmem_engine_prefetch_n(rmem_engine* e, const float* const* imgs, int n, void* stream);
 /* Profiling aid: CUDA events between pipeline stages (adds a stream sync per call while on).  get_timing writes
  * "stage total_ms count" lines into buf. */
 int rmem_engine_set_timing(rmem_engine* e, int on);

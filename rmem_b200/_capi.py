@@ -57,7 +57,7 @@ SYMBOLS = [
     "rmem_engine_set_gap", "rmem_engine_add_reference_frame", "rmem_engine_propagate", "rmem_engine_update_memory",
     "rmem_engine_num_groups", "rmem_engine_long_indexes", "rmem_engine_pred_logits", "rmem_engine_last_evict",
     "rmem_engine_layer_memory",
-    "rmem_engine_launch_count", "rmem_engine_prefetch", "rmem_engine_prefetch2", "rmem_engine_set_timing", "rmem_engine_get_timing",
+    "rmem_engine_launch_count", "rmem_engine_prefetch", "rmem_engine_prefetch2", "rmem_engine_prefetch_n", "rmem_engine_set_timing", "rmem_engine_get_timing",
 ]
 
 _lib = None

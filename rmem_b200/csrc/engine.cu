@@ -34,7 +34,8 @@ int evict_pick_host(const float* rel_raw, int T_old, const int* idx, int former,
 namespace {
 
 constexpr int kLayers = 3;
-constexpr int kFeatSets = 4;   // encoder output sets: two pairs of contiguous members (rmem_engine_prefetch2)
+constexpr int kEncGroup = 4;    // most frames one encoder pass covers (rmem_engine_prefetch_n)
+constexpr int kFeatSets = 8;    // encoder output sets: two groups of kEncGroup contiguous members
 constexpr int kD = 256;      // d_model
 constexpr int kDk = 128;     // att dim
 constexpr int kDv = 1024;    // V (512) || ID_V (512)
@@ -134,9 +135,9 @@ struct rmem_engine {
   // Encoder outputs are double-buffered: the image encoder does not depend on the memory state, so the NEXT frame can be
   // encoded on a side stream (rmem_engine_prefetch) while this frame's propagation / decoder / memory update run.
   // feat4/feat8/feat16/enc_tgt above always point at the set the current frame reads.
-  // Four feature sets = two PAIRS whose members are contiguous ([2][pixels][channels]): rmem_engine_prefetch2 encodes two
-  // frames in one pass (every encoder GEMM / conv runs once over both images, M doubled), a single prefetch or the inline
-  // encoder uses one member.
+  // Eight feature sets = two GROUPS of four contiguous members ([4][pixels][channels]): rmem_engine_prefetch_n encodes
+  // two or four frames in one pass (every encoder GEMM / conv runs once over all images, M multiplied) into an aligned
+  // pair / a whole group, a single prefetch or the inline encoder uses one member.
   t16 *feat4s[kFeatSets], *feat8s[kFeatSets], *feat16s[kFeatSets];
   float* enc_tgts[kFeatSets];
   // The decoder's adapter convolutions (fpn.py:44,50,56: 1x1 convs of the ENCODER features) do not depend on the memory
@@ -207,18 +208,24 @@ struct rmem_engine {
       if (pf_seq[sl] < pf_seq[o]) o = sl;
     return o;
   }
-  // first slot of a pair with no unconsumed prefetch (preferably not the current frame's pair), else of the older pair
-  int pick_pair() const {
-    const int cur_pair = fslot >> 1;
-    for (int k = 1; k <= kFeatSets / 2; ++k) {
-      const int pr = (cur_pair + k) % (kFeatSets / 2);
-      if (!pending[2 * pr] && !pending[2 * pr + 1]) return 2 * pr;
+  // first slot of an aligned run of n (2 | 4) slots with no unconsumed prefetch -- preferably outside the current frame's
+  // group -- else of the run whose newest entry is the oldest (stale)
+  int pick_run(int n) const {
+    const int groups = kFeatSets / kEncGroup, cur_group = fslot / kEncGroup;
+    for (int k = 1; k <= groups; ++k) {
+      const int base = ((cur_group + k) % groups) * kEncGroup;
+      for (int r = 0; r + n <= kEncGroup; r += n) {
+        bool free_run = true;
+        for (int j = 0; j < n; ++j) free_run = free_run && !pending[base + r + j];
+        if (free_run) return base + r;
+      }
     }
     long long best = -1;
     int o = 0;
-    for (int pr = 0; pr < kFeatSets / 2; ++pr) {
-      const long long newest = pf_seq[2 * pr] > pf_seq[2 * pr + 1] ? pf_seq[2 * pr] : pf_seq[2 * pr + 1];
-      if (best < 0 || newest < best) { best = newest; o = 2 * pr; }
+    for (int r = 0; r + n <= kFeatSets; r += n) {
+      long long newest = 0;
+      for (int j = 0; j < n; ++j) newest = pf_seq[r + j] > newest ? pf_seq[r + j] : newest;
+      if (best < 0 || newest < best) { best = newest; o = r; }
     }
     return o;
   }
@@ -349,23 +356,33 @@ struct rmem_engine {
 
   int layout(Arena& a) {
     const Geo& G = g;
-    // encoder temporaries hold two images (pair encoder); every activation is [n][pixels][channels]
+    // encoder temporaries hold kEncGroup images; every activation is [n][pixels][channels]
+    constexpr size_t NG = kEncGroup;
     img8_elems = (size_t)(G.H + 6) * (G.W + 8) * 8;
-    img8 = a.take<t16>(2 * img8_elems);                       // zero-padded stem inputs (zeroed once at create)
-    c1 = a.take<t16>(2 * (size_t)G.P1 * 64);
-    x0 = a.take<t16>(2 * (size_t)G.P4 * 256);
-    x1 = a.take<t16>(2 * (size_t)G.P4 * 256);
-    t1 = a.take<t16>(2 * (size_t)G.P4 * 128);
-    t2 = a.take<t16>(2 * (size_t)G.P4 * 64);
-    ds = a.take<t16>(2 * (size_t)G.P4 * 256);
-    for (int sl = 0; sl < kFeatSets; sl += 2) {
-      feat4s[sl] = a.take<t16>(2 * (size_t)G.P4 * 256);   feat4s[sl + 1] = feat4s[sl] + (size_t)G.P4 * 256;
-      feat8s[sl] = a.take<t16>(2 * (size_t)G.P8 * 512);   feat8s[sl + 1] = feat8s[sl] + (size_t)G.P8 * 512;
-      feat16s[sl] = a.take<t16>(2 * (size_t)G.HW * 1024); feat16s[sl + 1] = feat16s[sl] + (size_t)G.HW * 1024;
-      enc_tgts[sl] = a.take<float>(2 * (size_t)G.HW * kD); enc_tgts[sl + 1] = enc_tgts[sl] + (size_t)G.HW * kD;
-      ad16s[sl] = a.take<t16>(2 * (size_t)G.HW * 256);    ad16s[sl + 1] = ad16s[sl] + (size_t)G.HW * 256;
-      ad8s[sl] = a.take<t16>(2 * (size_t)G.P8 * 256);     ad8s[sl + 1] = ad8s[sl] + (size_t)G.P8 * 256;
-      ad4s[sl] = a.take<t16>(2 * (size_t)G.P4 * 128);     ad4s[sl + 1] = ad4s[sl] + (size_t)G.P4 * 128;
+    img8 = a.take<t16>(NG * img8_elems);                      // zero-padded stem inputs (zeroed once at create)
+    c1 = a.take<t16>(NG * (size_t)G.P1 * 64);
+    x0 = a.take<t16>(NG * (size_t)G.P4 * 256);
+    x1 = a.take<t16>(NG * (size_t)G.P4 * 256);
+    t1 = a.take<t16>(NG * (size_t)G.P4 * 128);
+    t2 = a.take<t16>(NG * (size_t)G.P4 * 64);
+    ds = a.take<t16>(NG * (size_t)G.P4 * 256);
+    for (int sl = 0; sl < kFeatSets; sl += kEncGroup) {
+      feat4s[sl] = a.take<t16>(NG * (size_t)G.P4 * 256);
+      feat8s[sl] = a.take<t16>(NG * (size_t)G.P8 * 512);
+      feat16s[sl] = a.take<t16>(NG * (size_t)G.HW * 1024);
+      enc_tgts[sl] = a.take<float>(NG * (size_t)G.HW * kD);
+      ad16s[sl] = a.take<t16>(NG * (size_t)G.HW * 256);
+      ad8s[sl] = a.take<t16>(NG * (size_t)G.P8 * 256);
+      ad4s[sl] = a.take<t16>(NG * (size_t)G.P4 * 128);
+      for (int j = 1; j < kEncGroup; ++j) {
+        feat4s[sl + j] = feat4s[sl] + (size_t)j * G.P4 * 256;
+        feat8s[sl + j] = feat8s[sl] + (size_t)j * G.P8 * 512;
+        feat16s[sl + j] = feat16s[sl] + (size_t)j * G.HW * 1024;
+        enc_tgts[sl + j] = enc_tgts[sl] + (size_t)j * G.HW * kD;
+        ad16s[sl + j] = ad16s[sl] + (size_t)j * G.HW * 256;
+        ad8s[sl + j] = ad8s[sl] + (size_t)j * G.P8 * 256;
+        ad4s[sl + j] = ad4s[sl] + (size_t)j * G.P4 * 128;
+      }
     }
     use_slot(0);
     res = a.take<float>((size_t)G.HW * 2 * kD);
@@ -542,7 +559,7 @@ struct rmem_engine {
     // before the current frame's propagate (bench / evaluator order).  Anything older was never consumed (skipped frame,
     // exception in the caller): drop it, so that a later tensor the allocator places at the same address cannot pick up
     // stale features.
-    // (a pair prefetch is issued two frames ahead and its second member is consumed one call later: ttl 4 instead of 2)
+    // (a group prefetch of n frames is issued n frames ahead and its last member is consumed n - 1 calls later: ttl 2n)
     for (int sl = 0; sl < kFeatSets; ++sl)
       if (pending[sl] && pf_age[sl] >= pf_ttl[sl]) pending[sl] = false;
     for (int sl = 0; sl < kFeatSets; ++sl)
@@ -573,9 +590,9 @@ struct rmem_engine {
     return RMEM_OK;
   }
 
-  // n = 1: one frame into feature set sl.  n = 2: two frames into the pair (sl, sl + 1), sl even -- every GEMM / conv of the
-  // encoder runs ONCE over both images (M doubled; convolutions with a fourth tensor-map dimension so that padding stays
-  // per image): the launches are latency-bound at one image, so the pair costs ~1.2x one frame, not 2x.
+  // n = 1: one frame into feature set sl.  n = 2 | 4: n frames into the aligned run sl .. sl + n - 1 -- every GEMM / conv
+  // of the encoder runs ONCE over all images (M multiplied; convolutions with a fourth tensor-map dimension so that padding
+  // stays per image): the launches are latency-bound at one image, so a pair costs ~1.5x one frame, not 2x.
   int encode_into(const float* const* imgs, int n, cudaStream_t s, int sl) {
     const Geo& G = g;
     mark("begin", s);
@@ -1407,7 +1424,7 @@ static int prefetch_n(rmem_engine* e, const float* const* imgs, int n, void* str
   if (e->timing) return RMEM_OK;            // stage timing serialises the frame; keep it on one stream
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // a slot (pair of slots) that holds no unconsumed prefetch; the current slot's readers have all been issued
-  const int sl = n == 2 ? e->pick_pair() : e->pick_slot();
+  const int sl = n > 1 ? e->pick_run(n) : e->pick_slot();
   RMEM_CUDA_CHECK(cudaEventRecord(e->ev_img_ready, s));
   RMEM_CUDA_CHECK(cudaStreamWaitEvent(e->enc_stream, e->ev_img_ready, 0));
   for (int j = 0; j < n; ++j)
@@ -1427,7 +1444,7 @@ static int prefetch_n(rmem_engine* e, const float* const* imgs, int n, void* str
     e->pf_img[sl + j] = imgs[j];
     e->pf_seq[sl + j] = ++e->pf_counter;
     e->pf_age[sl + j] = 0;
-    e->pf_ttl[sl + j] = n == 2 ? 4 : 2;
+    e->pf_ttl[sl + j] = 2 * n;
   }
   e->last_enc_slot = sl + n - 1;
   return RMEM_OK;
@@ -1450,6 +1467,19 @@ int rmem_engine_prefetch2(rmem_engine* e, const float* img_a, const float* img_b
   RMEM_REQUIRE(e && img_a && img_b && img_a != img_b, "prefetch2: two distinct images");
   const float* two[2] = {img_a, img_b};
   return prefetch_n(e, two, 2, stream);
+  RMEM_API_END
+}
+
+// n = 1, 2 or 4 coming frames in one encoder pass; a group of n is meant to be issued n frames ahead (before the propagate
+// of frame i for frames i+n .. i+2n-1, every n-th frame).
+int rmem_engine_prefetch_n(rmem_engine* e, const float* const* imgs, int n, void* stream) {
+  RMEM_API_BEGIN
+  RMEM_REQUIRE(e && imgs && (n == 1 || n == 2 || n == 4), "prefetch_n: n must be 1, 2 or 4 (got %d)", n);
+  for (int j = 0; j < n; ++j) {
+    RMEM_REQUIRE(imgs[j], "prefetch_n: null image");
+    for (int k = 0; k < j; ++k) RMEM_REQUIRE(imgs[j] != imgs[k], "prefetch_n: the images must be distinct");
+  }
+  return prefetch_n(e, imgs, n, stream);
   RMEM_API_END
 }
 

@@ -297,6 +297,18 @@ class DeAOTInferEngine:
         sp = C.c_void_p(stream.cuda_stream) if stream is not None else _capi.stream_ptr()
         _capi.check(_capi.load().rmem_engine_prefetch2(self._h, _capi.ptr(img_a), _capi.ptr(img_b), sp))
 
+    def prefetch_n(self, imgs, stream: Optional[torch.cuda.Stream] = None):
+        """1, 2 or 4 coming frames through the image encoder in one pass (see prefetch2).  A group of n is issued n frames
+        ahead: before frame i is propagated for frames i+n .. i+2n-1, every n-th frame."""
+        if self._h is None:
+            return
+        n = len(imgs)
+        for img in imgs:
+            assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous(), "prefetch needs the engine-ready tensor"
+        arr = (C.c_void_p * n)(*[img.data_ptr() for img in imgs])
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else _capi.stream_ptr()
+        _capi.check(_capi.load().rmem_engine_prefetch_n(self._h, arr, n, sp))
+
     def update_memory(self, label: torch.Tensor):
         """aot_engine.py:714-720 -> AOTEngine.update_short_term_memory (:327-396)."""
         lib = _capi.load()

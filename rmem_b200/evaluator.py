@@ -260,11 +260,12 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         for k in range(len(ring)):
             ring[k] = None
 
-    # Frames are known ahead of time: up to three are fetched (and copied to the device) ahead of the one being propagated,
-    # and their image encoder runs on the engine's side stream meanwhile -- two frames per encoder pass
-    # (engine.prefetch2: frames i+2, i+3, every second frame), a single frame (engine.prefetch) where no pair covers it
-    # (clip start, odd clip end).  Same-size frames only: a size change rebuilds the engine.
-    can_pair = can_prefetch and hasattr(engine, "prefetch2") and os.environ.get("RMEM_EVAL_ENC_PAIRS", "1") != "0"
+    # Frames are known ahead of time: up to 2G - 1 are fetched (and copied to the device) ahead of the one being propagated,
+    # and their image encoder runs on the engine's side stream meanwhile -- G frames per encoder pass (engine.prefetch_n:
+    # frames i+G .. i+2G-1, every G-th frame; G = 2, RMEM_EVAL_ENC_GROUP = 1 | 2 | 4 -- 4 measured no faster than 2), a single frame (engine.prefetch) where
+    # no group covers it (clip start, clip end).  Same-size frames only: a size change rebuilds the engine.
+    EG = int(os.environ.get("RMEM_EVAL_ENC_GROUP", "2")) if (can_prefetch and hasattr(engine, "prefetch_n")) else 1
+    EG = EG if EG in (2, 4) else 1
     look: List = []                        # fetched frames frame_idx + 1 ..
     fetched = 0
     covered = set()                        # frames whose encoding has been issued
@@ -278,15 +279,15 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
     for frame_idx in range(len(dataset)):
         ensure(1)
         meta, img, label = look.pop(0)
-        ensure(3 if can_pair else 1)
+        ensure(2 * EG - 1 if EG > 1 else 1)
         if can_prefetch and frame_idx >= 1:
             if look and frame_idx + 1 not in covered and look[0][1].shape == img.shape:
                 engine.prefetch(look[0][1])
                 covered.add(frame_idx + 1)
-            if can_pair and len(look) >= 3 and frame_idx + 2 not in covered and \
-                    look[1][1].shape == img.shape and look[2][1].shape == img.shape:
-                engine.prefetch2(look[1][1], look[2][1])
-                covered.update((frame_idx + 2, frame_idx + 3))
+            if EG > 1 and len(look) >= 2 * EG - 1 and frame_idx + EG not in covered and \
+                    all(look[EG - 1 + j][1].shape == img.shape for j in range(EG)):
+                engine.prefetch_n([look[EG - 1 + j][1] for j in range(EG)])
+                covered.update(range(frame_idx + EG, frame_idx + 2 * EG))
         if frame_idx == 0:
             if label is None:
                 raise ValueError(f"{dataset.seq_name}: the first frame has no label")

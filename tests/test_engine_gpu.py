@@ -177,8 +177,8 @@ def test_prefetched_encoder_is_bit_identical(cuda_device, model):
         assert idx == idx0, mode
 
 
-@pytest.mark.parametrize("model", ["r50_deaotl", "r50_aotl"])
-def test_pair_prefetch_matches_single_frame_encoder(cuda_device, model):
+@pytest.mark.parametrize("model,group", [("r50_deaotl", 2), ("r50_aotl", 2), ("r50_deaotl", 4)])
+def test_pair_prefetch_matches_single_frame_encoder(cuda_device, model, group):
     """rmem_engine_prefetch2 encodes frames i+2, i+3 in one pass (every encoder GEMM / conv over both images, 4-D tensor
     maps): same math, differently tiled, so not bit-identical -- teacher-forced with the inline run's labels, every frame's
     1/4-res logits must agree within 5e-3 of the logit range (the fp16 noise floor of the path: 1.4e-3 .. 4.3e-3 against fp32; engine tolerance 1.5e-2), labels >= 99.5 % (argmax near-ties on random frames flip),
@@ -186,7 +186,7 @@ def test_pair_prefetch_matches_single_frame_encoder(cuda_device, model):
     from rmem_b200.engine import RmemModel, RmemConfig, build_engine
     H, W, n_obj, gap = 257, 321, 3, 2
     sd = O.make_state_dict(model, seed=3, sharpen=4.0)
-    frames = O.synthetic_frames(12, H, W, seed=11).to(cuda_device)
+    frames = O.synthetic_frames(12 if group == 2 else 19, H, W, seed=11).to(cuda_device)
     label0 = O.synthetic_label(H, W, n_obj).int().to(cuda_device)
     cfg = RmemConfig(model=model, former_mem_len=1, latter_mem_len=2)
     eng = build_engine("deaotengine" if model == "r50_deaotl" else "aotengine", phase="eval",
@@ -199,8 +199,10 @@ def test_pair_prefetch_matches_single_frame_encoder(cuda_device, model):
         eng.add_reference_frame(frames[0:1], label0, obj_nums=[n_obj], frame_step=0)
         labs, logits, idx = [], [], []
         for f in range(1, n):
-            if pairs and f % 2 == 1 and f + 3 < n:
+            if pairs and group == 2 and f % 2 == 1 and f + 3 < n:
                 eng.prefetch2(frames[f + 2:f + 3], frames[f + 3:f + 4])
+            if pairs and group == 4 and f % 4 == 1 and f + 7 < n:      # frames f+4 .. f+7, four frames ahead
+                eng.prefetch_n([frames[f + 4 + j:f + 5 + j] for j in range(4)])
             lab = eng.propagate_label(frames[f:f + 1])
             logits.append(eng.logits4_views()[0].clone())
             eng.update_memory(forced[f - 1] if forced is not None else lab)
@@ -215,7 +217,7 @@ def test_pair_prefetch_matches_single_frame_encoder(cuda_device, model):
     pair_l, pair_g, pair_i = run(True, forced=base_l)
     l2 = eng.launch_count
     assert pair_i == base_i
-    assert l2 - l1 < l1 - l0 - 100, "the pair encoder did not run"      # 4 pairs = 4 encoder passes (~50 launches each) saved
+    assert l2 - l1 < l1 - l0 - 100, "the group encoder did not run"     # 4 pairs / 3 quads: >= 4 encoder passes (~50 launches each) saved
     for f in range(n - 1):
         err = float((pair_g[f] - base_g[f]).abs().max() / base_g[f].abs().max())
         agree = float((pair_l[f] == base_l[f]).float().mean())

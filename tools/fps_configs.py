@@ -20,17 +20,18 @@ def main():
                            long_term_mem_gap=1)
         frames = synthetic_frames(9, H, W, seed=1000).to(dev)
         R = 8
-        pairs = os.environ.get("RMEM_BENCH_ENC_PAIRS", "1") != "0"
+        EG = int(os.environ.get("RMEM_BENCH_ENC_GROUP", "2"))
+        pairs = EG > 1
         eng.add_reference_frame(frames[0:1], synthetic_label(H, W, n_obj).int().to(dev), obj_nums=[n_obj], frame_step=0)
         def step(i):
             if pairs:
-                if i % 2 == 0:
-                    eng.prefetch2(frames[1 + (i + 2) % R:2 + (i + 2) % R], frames[1 + (i + 3) % R:2 + (i + 3) % R])
+                if i % EG == 0:
+                    eng.prefetch_n([frames[1 + (i + EG + j) % R:2 + (i + EG + j) % R] for j in range(EG)])
             else:
                 eng.prefetch(frames[1 + (i + 1) % R:2 + (i + 1) % R])
             lab = eng.propagate_label(frames[1 + i % R:2 + i % R], output_size=(H, W))
             eng.update_memory(lab)
-        n0 = latter + 3 + (latter + 3) % 2
+        n0 = latter + 3 + (-(latter + 3)) % 4
         for i in range(n0):
             step(i)
         eng.long_term_mem_gap = 5

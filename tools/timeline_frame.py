@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--clips", type=int, default=1, help="clips in flight (one engine + stream each)")
-    ap.add_argument("--pairs", type=int, default=1, help="1 = pair encoder (prefetch2 two frames ahead), 0 = single prefetch")
+    ap.add_argument("--pairs", type=int, default=2, help="frames per encoder pass (prefetch_n, issued that many frames ahead): 2 | 4; 0 = single prefetch")
     ap.add_argument("--json", default="", help="also write the raw records here")
     ap.add_argument("--chrome", default="", help="also export the profiler's chrome trace here")
     a = ap.parse_args()
@@ -47,8 +47,9 @@ def main():
         e, src = engs[k], srcs[k]
         with torch.cuda.stream(streams[k]):
             if a.pairs:
-                if i % 2 == 0:
-                    e.prefetch2(src[1 + (i + 2) % ring: 2 + (i + 2) % ring], src[1 + (i + 3) % ring: 2 + (i + 3) % ring])
+                EG = a.pairs if a.pairs in (2, 4) else 2
+                if i % EG == 0:
+                    e.prefetch_n([src[1 + (i + EG + j) % ring: 2 + (i + EG + j) % ring] for j in range(EG)])
             else:
                 e.prefetch(src[1 + (i + 1) % ring: 2 + (i + 1) % ring])
             lab = e.propagate_label(src[1 + i % ring: 2 + i % ring], output_size=(H, W))
