@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err; echo "bench8 rc=$?"
+tail -1 gpurun_out/r02_bench_8gpu.json | cut -c1-700
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/bench_c5.py --clips 16 --frames 2000 > gpurun_out/r02_c5_8gpu.json 2> gpurun_out/r02_c5_8gpu.err; echo "c5 rc=$?"
+tail -1 gpurun_out/r02_c5_8gpu.json | cut -c1-700
