@@ -162,6 +162,8 @@ def run_ours(args):
     # host->device copy of frame i+1 is issued on a copy stream while frame i computes (what a prefetching loader does,
     # evaluator.py:308,372 uses pin_memory + non_blocking); both copies are inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)             # label maps leave on their own stream: a device->host copy in the
+    lab_ready = [torch.cuda.Event() for _ in range(4)]     # caller's stream would sit between two frames of the chain (~20 us)
     NS = 2 * EG if PAIRS else 2                            # staging buffers: frames i .. i+2*EG-1 are live in group mode
     stage = [torch.empty(1, 3, H, W, dtype=torch.float32, device=dev) for _ in range(NS)]
     staged = [torch.cuda.Event() for _ in range(NS)]
@@ -206,11 +208,17 @@ def run_ours(args):
                 main.wait_event(staged[i % NS])
                 lab = eng.propagate_label(stage[i % NS], output_size=(H, W))
                 consumed[i % NS].record(main)
+                lab_ready[i % 4].record(main)
                 eng.update_memory(lab)
-                host_lab[i % 2].copy_(lab, non_blocking=True)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(lab_ready[i % 4])
+                    host_lab[i % 2].copy_(lab, non_blocking=True)
+                    lab.record_stream(d2h_stream)
             else:
                 lab = step(i, src)
         counter["e2e" if e2e else "dev"] = first + steps
+        if e2e:
+            main.wait_stream(d2h_stream)                    # every label map has landed before the region ends
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

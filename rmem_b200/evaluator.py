@@ -235,6 +235,7 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
         return smp["meta"], im, (lb.float() if lb is not None else None)
 
     can_prefetch = use_cuda and hasattr(engine, "prefetch")
+    d2h_stream = torch.cuda.Stream(device=device) if use_cuda else None
     fast = use_cuda and hasattr(engine, "propagate_label")
     ring: List = [None] * 4                # (copy event, pinned label buffer, frame index, meta) of the frames in flight
     ring_bufs: List = [None] * 4
@@ -319,9 +320,16 @@ def evaluate_clip(engine, dataset: ClipDataset, out_dir: Optional[str] = None, d
             buf = ring_bufs[slot] if ring_bufs[slot] is not None and ring_bufs[slot].shape == lab_dev.shape[2:] else \
                 torch.empty(lab_dev.shape[2:], dtype=torch.uint8).pin_memory()
             ring_bufs[slot] = buf
-            buf.copy_(lab_dev[0, 0], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
+            # the label map leaves on its own stream: a device->host copy in the caller's stream would sit between two
+            # frames of the propagation chain
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ready)
+                buf.copy_(lab_dev[0, 0], non_blocking=True)
+                lab_dev.record_stream(d2h_stream)
+                done = torch.cuda.Event()
+                done.record()
             ring[slot] = (done, buf, frame_idx, meta)
             continue
         logit = engine.match_propogate_one_frame(img, output_size=out_size)

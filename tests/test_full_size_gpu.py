@@ -22,6 +22,9 @@ CASES = {
     # T = 9 (LATTER_MEM_LEN = 8, eval_vost.sh)
     "c4_deaotl_720p_30obj_3engines_T8": ("r50_deaotl", 721, 1281, 30, 1, 7, 10, 4.0),
     "c3_deaotl_480p_10obj_T9": ("r50_deaotl", 481, 849, 10, 1, 8, 12, 4.0),
+    # the production pipeline: frames f+2, f+3 through the image encoder in ONE pass (rmem_engine_prefetch2), two frames ahead
+    "c3_deaotl_480p_10obj_T8_pair_encoder": ("r50_deaotl", 481, 849, 10, 1, 7, 12, 4.0),
+    "c2_aotl_480p_1obj_T4_pair_encoder": ("r50_aotl", 481, 849, 1, 1, 3, 8, 2.0),
 }
 
 
@@ -40,13 +43,17 @@ def test_full_size_lockstep(cuda_device, name):
     orc = O.OracleEngine(sd, O.OracleConfig(model=model, former_mem_len=former, latter_mem_len=latter),
                          long_term_mem_gap=1)
     worst, agree_min = 0.0, 1.0
+    pairs = name.endswith("_pair_encoder")
+    frames_dev = frames.to(cuda_device)
+    l0 = eng.launch_count
     with torch.no_grad():
         eng.restart_engine(); orc.restart_engine()
         eng.add_reference_frame(frames[0:1].to(cuda_device), label0.int().to(cuda_device), obj_nums=[n_obj], frame_step=0)
         orc.add_reference_frame(frames[0:1], label0, obj_nums=[n_obj], frame_step=0)
         for f in range(1, n_frames):
-            lg, lab = eng.match_propogate_one_frame(frames[f:f + 1].to(cuda_device), output_size=(H, W),
-                                                    return_label=True)
+            if pairs and f % 2 == 1 and f + 3 < n_frames:
+                eng.prefetch2(frames_dev[f + 2:f + 3], frames_dev[f + 3:f + 4])
+            lg, lab = eng.match_propogate_one_frame(frames_dev[f:f + 1], output_size=(H, W), return_label=True)
             ref = orc.match_propogate_one_frame(frames[f:f + 1], output_size=(H, W))
             for k, (a, b) in enumerate(zip(eng.aot_engines, orc.aot_engines)):
                 e = float((a.pred_id_logits.cpu() - b.pred_id_logits).abs().max() / b.pred_id_logits.abs().max())
@@ -61,7 +68,8 @@ def test_full_size_lockstep(cuda_device, name):
                 assert idx[0] == 0 and len(idx) <= cap and idx == sorted(idx)
                 if len(idx) > 1:
                     assert idx[-1] == f                                    # gap 1: the newest frame is always kept
-    print(f"[{name}] worst relative 1/4-res logit error {worst:.3e}, min label agreement {agree_min:.5f}")
+    print(f"[{name}] worst relative 1/4-res logit error {worst:.3e}, min label agreement {agree_min:.5f}, "
+          f"launches {eng.launch_count - l0}")
     from parity_report import report
     # label bar: 99.5 % for one object group; 99 % when the labels come from the soft aggregation of several groups
     # (aot_engine.py:650-673: near-ties along three times as many object boundaries, same 4e-3 logit error)
