@@ -57,6 +57,10 @@ struct TcGemmParams {
   // GroupNorm statistics of the output, produced by the epilogue (the FPN decoder's conv -> GroupNorm pairs): per
   // (row tile, 32-column chunk, lane quadrant) fp32 partial sums of the fp32 results, folded in a fixed order and in double
   // by the last CTA to finish -> gn_stats[2 * group] = (sum, sum of squares).  gn_cpg = channels per group (16 | 32).
+  // TMA-store epilogue (one t16 destination): the tile is staged in the (by then idle) operand ring as 64-column panels in
+  // the 128-byte swizzle and leaves as full 128-byte lines through map_c; rows / columns outside the output are dropped by
+  // the tensor map.  Replaces 16-byte stores at a row stride per lane (half-used sectors, partial-line writes).
+  int tma_store;
   double* gn_stats;
   float4* gn_part;
   unsigned int* gn_counter;
@@ -122,7 +126,7 @@ __device__ __forceinline__ void load8h(const t16* p, float* v) {
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, BN <= 128 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcGemmParams p) {
+               const __grid_constant__ CUtensorMap map_c, const TcGemmParams p) {
   using L = TcSmem<BN>;
   const int STAGES = p.stages;
   extern __shared__ unsigned char smem_raw[];
@@ -164,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_c);
   }
   if (warp == 1) tmem_alloc<BN>(tmem_slot);
   __shared__ __align__(16) float s_bias[BN];
@@ -361,6 +366,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (!valid) return;
       }
       if (warp == 2 && c0 == 0) GTRACE(6);
+      if (p.tma_store) {
+        // row r of the 64-column panel c0 / 64: 128 bytes, 16-byte piece q stored at piece q ^ (r & 7) (128-byte swizzle)
+        unsigned char* panel = smem + (size_t)(c0 >> 6) * (TBM * 128) + (size_t)r * 128;
+        const int q0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack2(v[j * 8], v[j * 8 + 1]); u.y = pack2(v[j * 8 + 2], v[j * 8 + 3]);
+          u.z = pack2(v[j * 8 + 4], v[j * 8 + 5]); u.w = pack2(v[j * 8 + 6], v[j * 8 + 7]);
+          *reinterpret_cast<uint4*>(panel + (((q0 + j) ^ (r & 7)) << 4)) = u;
+        }
+        return;
+      }
       if (f32) {
         float* o = reinterpret_cast<float*>(base) + gm * ld + nn;
         if (do_acc) {                                // one batch of 8 loads = one L2 round trip
@@ -393,6 +411,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
 #pragma unroll 1
       for (int cc = 0; cc < kHalfCols; cc += 32) chunk(cbeg + cc);
+    }
+    if (p.tma_store) {
+      fence_async_smem();                              // the panels (generic-proxy writes) are visible to the TMA unit
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (warp == 2 && elect_one()) {
+#pragma unroll
+        for (int pn = 0; pn < BN / 64; ++pn) {
+          if (n0 + pn * 64 >= p.N) break;
+          const unsigned char* src = smem + (size_t)pn * (TBM * 128);
+          if (p.conv) tma_store_4d(&map_c, src, n0 + pn * 64, x0, y0, img);
+          else tma_store_2d(&map_c, src, n0 + pn * 64, m0);
+        }
+        tma_store_commit_and_wait_read();              // the panels are read before this CTA's shared memory goes away
+      }
     }
     }
     if (p.gn_stats) __threadfence();                 // this warp's partial sums are visible before the CTA signs off
@@ -468,8 +500,8 @@ bool gemm_splitk_switch() {
 }
 
 template <int BN>
-int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int m_tiles, int max_stages,
-              cudaStream_t s) {
+int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, const CUtensorMap* mc, TcGemmParams& p, int m_tiles,
+              int max_stages, cudaStream_t s) {
   using L = TcSmem<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -536,7 +568,10 @@ int launch_tc(const CUtensorMap* ma, const CUtensorMap* mb, TcGemmParams& p, int
     attr[1].val.clusterDim.z = (unsigned)S;
     cfg.numAttrs = 2;
   }
-  RMEM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, *ma, *mb, static_cast<const TcGemmParams&>(p)));
+  // the output panels are staged in the operand ring: BN = 256 needs two stages' worth of it
+  if (p.tma_store && BN == 256 && p.stages < 2) p.tma_store = 0;
+  RMEM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, *ma, *mb, *(p.tma_store ? mc : ma),
+                                     static_cast<const TcGemmParams&>(p)));
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
 }
@@ -680,9 +715,28 @@ int gemm_tc_launch(const GemmParams& g, cudaStream_t stream) {
     uint32_t box[2] = {(uint32_t)TBK, (uint32_t)BN};
     RMEM_TRY(tma_encode_cached(&mb, g.B, 2, dims, strides, box, nullptr));
   }
-  if (BN == 64) return launch_tc<64>(ma, mb, p, m_tiles, 4, stream);
-  if (BN == 128) return launch_tc<128>(ma, mb, p, m_tiles, 3, stream);
-  return launch_tc<256>(ma, mb, p, m_tiles, 4, stream);
+  // TMA-store epilogue: one t16 destination, whole 64-column panels inside the allocation (ldc >= round_up(N, 64) or
+  // N % 64 == 0 -- the tensor map drops what lies beyond N anyway, but a panel's box must not straddle the row pitch)
+  static const int tma_store_on = [] { const char* e = getenv("RMEM_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
+  const CUtensorMap* mc = nullptr;
+  p.tma_store = 0;
+  if (tma_store_on && !g.c_fp32 && g.n_split >= g.N && !g.bias_m && g.N % 8 == 0 && (g.ldc * 2) % 16 == 0) {
+    if (g.conv) {
+      uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.Wout, (uint64_t)p.Hout, (uint64_t)g.nimg};
+      uint64_t strides[3] = {(uint64_t)g.ldc * 2, (uint64_t)g.Wout * g.ldc * 2, (uint64_t)p.Hout * g.Wout * g.ldc * 2};
+      uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+      RMEM_TRY(tma_encode_cached(&mc, g.C, 4, dims, strides, box, nullptr));
+    } else {
+      uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+      uint64_t strides[1] = {(uint64_t)g.ldc * 2};
+      uint32_t box[2] = {64, (uint32_t)TBM};
+      RMEM_TRY(tma_encode_cached(&mc, g.C, 2, dims, strides, box, nullptr));
+    }
+    p.tma_store = 1;
+  }
+  if (BN == 64) return launch_tc<64>(ma, mb, mc, p, m_tiles, 4, stream);
+  if (BN == 128) return launch_tc<128>(ma, mb, mc, p, m_tiles, 3, stream);
+  return launch_tc<256>(ma, mb, mc, p, m_tiles, 4, stream);
 }
 
 }  // namespace rmem

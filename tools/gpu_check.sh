@@ -1,6 +1,6 @@
 #!/bin/bash
-# quick visit: selected parity tests + one short bench line
+# quick visit: selected parity tests + short bench lines (A/B of an environment switch: bash tools/gpu_check.sh VAR=value)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_full_size_gpu.py tests/test_engine_gpu.py tests/test_evaluator.py -m gpu -x -q -s 2>&1 | grep -E "^\[|passed|failed|Error|error" | tail -14
-python tools/bench_brief.py e2e_d2h_stream --clips-in-flight 1
-timeout 600 python tools/bench_c5.py --clips 2 --frames 1000 2> /dev/null | tail -1 | cut -c1-300
+timeout 900 python -m pytest tests/test_gemm_tc_gpu.py tests/test_engine_gpu.py tests/test_layer_goldens_gpu.py tests/test_ops_gpu.py -m gpu -x -q 2>&1 | tail -6
+python tools/bench_brief.py default --clips-in-flight 1
+if [ -n "$1" ]; then env "$1" python tools/bench_brief.py "$1" --clips-in-flight 1; python tools/bench_brief.py default_again --clips-in-flight 1; fi
