@@ -164,17 +164,20 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)             # label maps leave on their own stream: a device->host copy in the
     lab_ready = [torch.cuda.Event() for _ in range(4)]     # caller's stream would sit between two frames of the chain (~20 us)
-    NS = 2 * EG if PAIRS else 2                            # staging buffers: frames i .. i+2*EG-1 are live in group mode
+    NS = 3 * EG if PAIRS else 2                            # staging buffers: frames i-1 .. i+2*EG-1 are live in group mode
     stage = [torch.empty(1, 3, H, W, dtype=torch.float32, device=dev) for _ in range(NS)]
     staged = [torch.cuda.Event() for _ in range(NS)]
     consumed = [torch.cuda.Event() for _ in range(NS)]
     counter = {"dev": 0, "e2e": 0}                         # frame index runs on across the timed blocks
 
+    E2E_DEBUG = os.environ.get("RMEM_BENCH_E2E_DEBUG", "")   # "noh2d" / "nod2h": leave one copy out (where does the e2e gap come from?)
+
     def prefetch(i, src):
         b = i % NS
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[b])           # frame i-NS has finished reading this staging buffer
-            stage[b].copy_(fr(src, i), non_blocking=True)
+            if E2E_DEBUG != "noh2d" or i < 2 * NS:
+                stage[b].copy_(fr(src, i), non_blocking=True)
             staged[b].record(copy_stream)
 
     def timed(src, steps, e2e):
@@ -188,7 +191,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if e2e and first == 0:                              # very first e2e frame(s): nothing staged yet
-            for k in range(EG if PAIRS else 1):
+            for k in range(2 * EG if PAIRS else 1):
                 prefetch(k, src)
         for i in range(first, first + steps):
             if e2e:
@@ -197,10 +200,13 @@ def run_ours(args):
                 # consumed by the next block (the frame index runs on), so every block copies and encodes exactly
                 # `steps` frames inside its timed region.
                 if PAIRS:
+                    # the copies of a group are issued one step before its encoder pass, so that the pass (which has to
+                    # be done two steps later) does not start by waiting ~0.2 ms for PCIe
                     if i % EG == 0:
-                        for j in range(EG):
-                            prefetch(i + EG + j, src)
                         eng.prefetch_n([stage[(i + EG + j) % NS] for j in range(EG)], stream=copy_stream)
+                    if (i + 1) % EG == 0:
+                        for j in range(EG):
+                            prefetch(i + 1 + EG + j, src)
                 else:
                     prefetch(i + 1, src)
                     if PREFETCH:
@@ -210,10 +216,11 @@ def run_ours(args):
                 consumed[i % NS].record(main)
                 lab_ready[i % 4].record(main)
                 eng.update_memory(lab)
-                with torch.cuda.stream(d2h_stream):
-                    d2h_stream.wait_event(lab_ready[i % 4])
-                    host_lab[i % 2].copy_(lab, non_blocking=True)
-                    lab.record_stream(d2h_stream)
+                if E2E_DEBUG != "nod2h":
+                    with torch.cuda.stream(d2h_stream):
+                        d2h_stream.wait_event(lab_ready[i % 4])
+                        host_lab[i % 2].copy_(lab, non_blocking=True)
+                        lab.record_stream(d2h_stream)
             else:
                 lab = step(i, src)
         counter["e2e" if e2e else "dev"] = first + steps
