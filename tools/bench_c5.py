@@ -95,58 +95,16 @@ def main():
     # warm-up clip (not counted): first-use costs (tensor maps, lazy allocations)
     from rmem_b200.evaluator import evaluate_clip
     evaluate_clip(eng, SyntheticClip(10_000 + rank, 120), device=dev)
+    # several clips in flight on this GPU: one engine + host thread + CUDA stream per clip, all drawing from the same queue
+    # (rmem_b200.evaluator.evaluate_clips, extra_engines)
+    for e in engines[1:]:                                   # per-engine warm-up (lazy allocations, tensor maps)
+        evaluate_clip(e, SyntheticClip(20_000 + rank * 8 + len(engines), 60), device=dev)
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
     t0 = time.perf_counter()
-    if a.in_flight <= 1:
-        out = evaluate_clips(eng, clips, device=dev, rank=rank, world=world, store=store, log=None)
-    else:
-        # several clips in flight on this GPU: one host thread + CUDA stream + engine per clip, all drawing from the same
-        # queue (the store's atomic counter across ranks, a locked counter inside one process)
-        import threading
-        from rmem_b200.evaluator import ClipQueue
-        from rmem_b200.sharding import gather_stats
-        lock = threading.Lock()
-        shared = ClipQueue(a.clips, rank, world, store)
-        results = []
-
-        def next_clip():
-            with lock:
-                try:
-                    return next(shared)
-                except StopIteration:
-                    return None
-
-        def worker(k):
-            torch.cuda.set_device(dev)
-            st = torch.cuda.Stream(device=dev)
-            with torch.cuda.stream(st):
-                evaluate_clip(engines[k], SyntheticClip(20_000 + rank * 8 + k, 60), device=dev)      # per-thread warm-up
-                st.synchronize()
-                ready.wait()
-                while True:
-                    i = next_clip()
-                    if i is None:
-                        break
-                    r = evaluate_clip(engines[k], clips[i], device=dev)
-                    with lock:
-                        results.append(r)
-            st.synchronize()
-
-        ready = threading.Barrier(a.in_flight + 1)
-        ths = [threading.Thread(target=worker, args=(k,)) for k in range(a.in_flight)]
-        for t in ths:
-            t.start()
-        ready.wait()                    # every thread has warmed its engine up: the timed region starts here
-        t0 = time.perf_counter()
-        for t in ths:
-            t.join()
-        frames = sum(r.frames for r in results)
-        seconds = sum(r.seconds for r in results)
-        stats = gather_stats(frames, seconds, dev, world)
-        out = {"per_rank": stats, "all_frame_fps": sum(f for f, _ in stats) / max(sum(x for _, x in stats), 1e-9)}
+    out = evaluate_clips(eng, clips, device=dev, rank=rank, world=world, store=store, log=None, extra_engines=engines[1:])
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     walls = [wall]
