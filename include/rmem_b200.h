@@ -279,6 +279,28 @@ int rmem_engine_prefetch_n(rmem_engine* e, const float* const* imgs, int n, void
 int rmem_engine_set_timing(rmem_engine* e, int on);
 int rmem_engine_get_timing(rmem_engine* e, char* buf, size_t cap);
 
+/* ---------------------------------------------------------------- training side (first slice) ---- */
+/* Value and gradient of the reference's per-frame training loss with respect to the 1/4-resolution ID logits
+ * (rmem_engine_pred_logits): AOTEngine.calculate_current_loss (networks/engines/aot_engine.py:484-511) =
+ * bilinear align_corners upsampling to the label size, channels 0..obj_num, then
+ *   0.5 * CrossEntropyLoss (networks/layers/loss.py:163-211: per-pixel CE with ignore_index 255, mean of the
+ *         top_k_pixels largest of all H*W values -- the caller computes top_k_pixels from the training step, :190-198)
+ * + 0.5 * SoftJaccordLoss  (loss.py:30-74, 136-160: tversky alpha = beta = 1, eps 1e-6, over the non-255 pixels, mean over
+ *         the classes that own a pixel).
+ * logits4 fp32 [n_logit_ch, h4, w4]; gt uint8 [H, W] (255 = ignore; other ids above obj_num contribute no cross
+ * entropy -- the reference raises there); losses = device float[3] {total, ce, jaccard}; grad_logits4 (nullable) =
+ * grad_scale * d total / d logits4, same shape as logits4 (channels above obj_num: 0).  fp32, IEEE exp / log, every
+ * reduction in a fixed order: bit-reproducible.  workspace: device, 256-byte aligned, rmem_train_loss_workspace_bytes(H, W).
+ * Backward of the layers UNDER the logits (decoder, GPM, encoder) is not built. */
+int rmem_train_loss_workspace_bytes(int H, int W, size_t* bytes);
+int rmem_train_loss_fwd_bwd(const float* logits4, int n_logit_ch, int h4, int w4, const uint8_t* gt, int H, int W,
+                            int obj_num, long long top_k_pixels, float grad_scale, float* losses, float* grad_logits4,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* predict_current_mask of the training engine (aot_engine.py:467-483; decode_current_logits has pushed the channels above
+ * obj_num to -1e10 there, :449-452): label uint8 [H, W] = argmax over channels 0..obj_num of the upsampled logits. */
+int rmem_train_predict_mask(const float* logits4, int n_logit_ch, int h4, int w4, int H, int W, int obj_num,
+                            uint8_t* label, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

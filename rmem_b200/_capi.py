@@ -58,6 +58,7 @@ SYMBOLS = [
     "rmem_engine_num_groups", "rmem_engine_long_indexes", "rmem_engine_pred_logits", "rmem_engine_last_evict",
     "rmem_engine_layer_memory",
     "rmem_engine_launch_count", "rmem_engine_prefetch", "rmem_engine_prefetch2", "rmem_engine_prefetch_n", "rmem_engine_set_timing", "rmem_engine_get_timing",
+    "rmem_train_loss_workspace_bytes", "rmem_train_loss_fwd_bwd", "rmem_train_predict_mask",
 ]
 
 _lib = None
@@ -72,9 +73,12 @@ def load(build_if_missing: bool = True):
         from . import build as _build
         try:
             _build.build()
-        except Exception as e:  # stale/missing .so and no nvcc -> fail loudly below
+        except Exception as e:  # missing or stale .so that cannot be rebuilt (no nvcc, compile error) -> fail loudly
             if not os.path.exists(LIB_PATH):
                 raise RmemError(f"rmem_b200 CUDA extension is missing and could not be built: {e}") from e
+            if not _build.up_to_date() and os.environ.get("RMEM_ALLOW_STALE_LIB") != "1":
+                raise RmemError(f"{LIB_PATH} was built from other sources than the ones in this tree and the rebuild "
+                                f"failed ({e}); set RMEM_ALLOW_STALE_LIB=1 to load it anyway") from e
     if not os.path.exists(LIB_PATH):
         raise RmemError(f"rmem_b200 CUDA extension not found at {LIB_PATH}; run `python -m rmem_b200.build`")
     lib = C.CDLL(LIB_PATH)

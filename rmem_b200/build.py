@@ -16,15 +16,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librmem_b200.so")
-SOURCES = ["capi.cu", "gemm.cu", "gemm_tc.cu", "tma.cu", "ops.cu", "attn_dense.cu", "attn_tc2.cu", "attn_tc3.cu", "mha_tc.cu", "local_attn_tc.cu", "engine.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "gemm_tc.cu", "tma.cu", "ops.cu", "attn_dense.cu", "attn_tc2.cu", "attn_tc3.cu", "mha_tc.cu", "local_attn_tc.cu", "engine.cu", "train_loss.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
 # --use_fast_math (approximate exp / log / division, FTZ) is for the tensor-core kernels, whose exponentials are MUFU ex2
 # by design.  ops.cu holds the mask head, the soft aggregation, evict_rel and the TTA head, whose softmax / logit / argmax
 # arithmetic must be the reference's IEEE fp32 (expf, logf, exact division next to the explicit _rn operations): it is
-# compiled WITHOUT the flag.
-EXACT_MATH = {"ops.cu"}
+# compiled WITHOUT the flag; so is train_loss.cu (the training loss and its gradient: expf / logf / division as torch's).
+EXACT_MATH = {"ops.cu", "train_loss.cu"}
 
 
 def _digest() -> str:
@@ -40,11 +40,17 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def up_to_date() -> bool:
+    """True when the .so in the tree was built from exactly the sources / header / flags of this tree."""
+    stamp = os.path.join(LIBDIR, "build.sha256")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == _digest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.sha256")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    if not force and up_to_date():
         return LIB
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC} and no up-to-date {LIB}; cannot build the CUDA extension")

@@ -1,0 +1,270 @@
+"""CPU: the training-side slice: oracle loss vs the reference's recorded values and gradient
+(tests/golden/train_small.npz, written by oracle/make_train_golden.py from the UNMODIFIED reference), the host logic of
+rmem_b200.training.train_forward driven by the oracle engine, the loss schedules, and a numpy restatement of the exact
+algorithm csrc/train_loss.cu runs (fp32 taps, 3-pass radix select of the k-th largest cross entropy, tie handling,
+Jaccard coefficients, gather-form transpose of the upsampling with its candidate ranges) against autograd -- so that the
+ALGORITHM of the CUDA loss head is checked here and only its transcription is left to tests/test_training_gpu.py."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rmem_oracle as O
+from oracle import train_oracle as TO
+from rmem_b200 import training as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "train_small.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    z = np.load(GOLD)
+    return json.loads(str(z["meta"])), z
+
+
+def test_schedules_match_reference_formulas():
+    cfg = T.TrainConfig(total_steps=20000)
+    P = 129 * 161
+    assert T.top_k_pixels(0, P, cfg) == P                                   # loss.py:190-198: everything at step 0
+    assert T.top_k_pixels(9000, P, cfg) == 4880                             # the golden's recorded k
+    assert T.top_k_pixels(10 ** 6, P, cfg) == int(0.15 * P)
+    assert T.aux_weight(0, cfg) == pytest.approx(1.0)
+    assert T.aux_weight(3000, cfg) == pytest.approx(0.85, abs=1e-6)         # aot_engine.py:53-54
+    assert T.aux_weight(30000, cfg) == 0.0
+    assert T.aux_weight(5000, T.TrainConfig(total_steps=100000, aux_loss_ratio=0.1)) == pytest.approx(0.5, abs=1e-6)
+
+
+def test_oracle_loss_and_gradient_reproduce_reference(gold):
+    meta, z = gold
+    lg = torch.from_numpy(z["lh_logits4"]).unsqueeze(0)
+    for case in meta["loss_head"]:
+        name = case["name"]
+        gt = torch.from_numpy(z[f"lh_gt_{name}"])
+        total, ce, jac, grad = TO.loss_head_with_grad(lg, gt, meta["n_obj"], case["k"])
+        ref = z[f"lh_losses_{name}"]
+        assert abs(total - ref[0]) < 2e-6 and abs(ce - ref[1]) < 2e-6 and abs(jac - ref[2]) < 4e-6, (name, total, ref)
+        rg = torch.from_numpy(z[f"lh_grad_{name}"])
+        assert float((grad[0] - rg).abs().max() / rg.abs().max()) < 1e-4, name
+        assert float(grad[0, meta["n_obj"] + 1:].abs().max()) == 0.0         # unused identities get no gradient
+
+
+def test_train_forward_on_oracle_engine_reproduces_reference(gold):
+    meta, z = gold
+    H, W, n_obj, F_ = meta["H"], meta["W"], meta["n_obj"], meta["n_frames"]
+    sd = O.make_state_dict(meta["model"], seed=meta["seed"], sharpen=meta["sharpen"])
+    frames = O.synthetic_frames(F_, H, W, seed=meta["seed"] + 1)
+    masks = torch.from_numpy(z["masks"]).float().unsqueeze(1)
+    eng = O.OracleEngine(sd, O.OracleConfig(model=meta["model"], former_mem_len=meta["former"],
+                                            latter_mem_len=meta["latter"]), long_term_mem_gap=meta["gap"])
+    cfg = T.TrainConfig(**meta["train_cfg"])
+    with torch.no_grad():
+        loss, pred, fl, boards = T.train_forward(eng, frames, masks, 1, [n_obj], step=meta["step"], cfg=cfg,
+                                                 loss_fn=lambda lg, gt, n, k: TO.loss_head(lg, gt, n, k)[0],
+                                                 mask_fn=TO.predict_mask)
+    assert loss.ndim == 0 and abs(float(loss) - meta["ref_loss"]) < 2e-5
+    assert len(fl) == F_ and all(x.shape == (1,) for x in fl)
+    assert max(abs(float(a) - b) for a, b in zip(fl, meta["ref_frame_losses"])) < 2e-5
+    got = torch.stack([m[0] for m in pred]).to(torch.uint8).numpy()
+    assert got.shape == z["pred_masks"].shape and int((got != z["pred_masks"]).sum()) <= 2
+    assert eng.aot_engines[0].long_memories_indexes == meta["ref_idx"]
+    assert boards == {"image": {}, "scalar": {}}
+
+
+def test_train_forward_batch_and_prev_pred_host_logic():
+    """Frame-major batches and use_prev_pred on a recording fake engine: call order and which label feeds the memory."""
+    H, W, B, F_ = 17, 33, 2, 4
+    calls = []
+
+    class Sub:
+        pred_id_logits = torch.zeros(1, 11, 5, 9)
+
+    class Fake:
+        aot_engines = [Sub()]
+
+        def restart_engine(self):
+            calls.append(("restart",))
+
+        def add_reference_frame(self, img, mask, obj_nums, frame_step):
+            calls.append(("ref", float(img.flatten()[0]), float(mask.flatten()[0]), obj_nums[0], frame_step))
+
+        def match_propogate_one_frame(self, img, output_size=None):
+            calls.append(("prop", float(img.flatten()[0])))
+
+        def update_memory(self, label):
+            assert tuple(label.shape) == (1, 1, H, W)
+            calls.append(("mem", float(label.flatten()[0])))
+
+    frames = torch.arange(F_ * B).float().view(-1, 1, 1, 1).expand(-1, 3, H, W).contiguous()     # value = f * B + b
+    masks = (100 + torch.arange(F_ * B)).float().view(-1, 1, 1, 1).expand(-1, 1, H, W).contiguous()
+    seen_gt = []
+
+    def loss_fn(lg, gt, n, k):
+        seen_gt.append((float(gt.flatten()[0]), n, k))
+        return torch.tensor(float(len(seen_gt)))
+
+    def mask_fn(lg, h, w, n):
+        return torch.full((h, w), 7, dtype=torch.uint8)
+
+    cfg = T.TrainConfig(total_steps=100)
+    for prev_pred in (False, True):
+        calls.clear(); seen_gt.clear()
+        loss, pred, fl, _ = T.train_forward(Fake(), frames, masks, B, [3, 5], step=0, use_prev_pred=prev_pred, cfg=cfg,
+                                            loss_fn=loss_fn, mask_fn=mask_fn)
+        for b in range(B):
+            mem = (lambda f: 7.0) if prev_pred else (lambda f, b=b: 100.0 + f * B + b)
+            assert calls[b * 7:(b + 1) * 7] == [
+                ("restart",), ("ref", float(b), 100.0 + b, [3, 5][b], 0), ("prop", float(B + b)),
+                ("mem", mem(1)), ("prop", float(2 * B + b)), ("mem", mem(2)), ("prop", float(3 * B + b))]
+        assert len(calls) == 7 * B
+        assert [g for g, _, _ in seen_gt] == [100.0 + f * B + b for b in range(B) for f in range(F_)]
+        assert all(k == H * W for _, _, k in seen_gt) and [n for _, n, _ in seen_gt] == [3] * F_ + [5] * F_
+        # loss values were 1..8 in call order (sample-major); aux = mean of frame 0, pred = mean over the other frames
+        per = torch.arange(1, 9).float().view(B, F_)
+        assert float(loss) == pytest.approx(float(per[:, 0].mean() + per[:, 1:].mean()))
+        assert [tuple(x.shape) for x in fl] == [(B,)] * F_ and [tuple(m.shape) for m in pred] == [(B, H, W)] * F_
+        assert pred[0].dtype == torch.long
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# numpy restatement of csrc/train_loss.cu, kernel by kernel
+# ---------------------------------------------------------------------------------------------------------------------
+f32 = np.float32
+
+
+def taps(in_size, out_size):
+    """tl `taps()`: (i0, i1, l0, l1) per destination index, fp32 arithmetic."""
+    scale = f32(in_size - 1) / f32(out_size - 1) if out_size > 1 else f32(0)
+    dst = np.arange(out_size, dtype=f32)
+    real = (scale * dst).astype(f32)
+    i0 = np.minimum(real.astype(np.int32), in_size - 1)
+    lam = np.clip((real - i0.astype(f32)).astype(f32), 0, 1).astype(f32)
+    i1 = i0 + (i0 < in_size - 1)
+    return scale, i0, i1, (f32(1) - lam).astype(f32), lam
+
+
+def radix_select(ce_bits, k):
+    """tl_hist_kernel + tl_scan_kernel x 3: (threshold pattern, ties needed, ties present)."""
+    prefix, k_rem, n_ties = 0, k, 0
+    for ps in range(3):
+        if ps == 0:
+            digits = ce_bits >> 21
+        elif ps == 1:
+            digits = ((ce_bits >> 10) & 2047)[(ce_bits >> 21) == prefix]
+        else:
+            digits = (ce_bits & 1023)[(ce_bits >> 10) == prefix]
+        hist = np.bincount(digits, minlength=2048)
+        per = 8
+        tot = hist.reshape(256, per).sum(1)
+        cum, t = 0, 255
+        while t > 0 and cum + tot[t] < k_rem:
+            cum += tot[t]; t -= 1
+        b = t * per + per - 1
+        while b > t * per and cum + hist[b] < k_rem:
+            cum += hist[b]; b -= 1
+        prefix = b if ps == 0 else (prefix << (11 if ps == 1 else 10)) | b
+        k_rem -= cum
+        n_ties = int(hist[b])
+    return int(prefix), int(k_rem), n_ties
+
+
+def emulate_loss_head(logits4, gt, obj_num, k, grad_scale=1.0):
+    C_all, h4, w4 = logits4.shape
+    H, W = gt.shape
+    n_ch = obj_num + 1
+    sy, y0, y1, wy0, wy1 = taps(h4, H)
+    sx, x0, x1, wx0, wx1 = taps(w4, W)
+    L = logits4[:n_ch].astype(f32)
+    top = (wx0 * L[:, y0][:, :, x0]).astype(f32) + (wx1 * L[:, y0][:, :, x1]).astype(f32)
+    bot = (wx0 * L[:, y1][:, :, x0]).astype(f32) + (wx1 * L[:, y1][:, :, x1]).astype(f32)
+    x = ((wy0[:, None] * top).astype(f32) + (wy1[:, None] * bot).astype(f32)).reshape(n_ch, -1)      # [C, P]
+    g = gt.reshape(-1).astype(np.int64)
+    m = x.max(0)
+    e = np.exp(x - m).astype(f32)
+    s = e.sum(0).astype(f32)
+    p = (e * (f32(1) / s)).astype(f32)
+    in_range = g < n_ch
+    xg = np.where(in_range, x[np.minimum(g, n_ch - 1), np.arange(g.size)], 0)
+    ce = np.where(in_range, np.maximum(np.log(s).astype(f32) - (xg - m), 0), 0).astype(f32)
+    valid = g != 255
+    I = np.array([(p[c] * (valid & (g == c))).sum(dtype=np.float64) for c in range(n_ch)])
+    S = np.array([(p[c] * valid).sum(dtype=np.float64) for c in range(n_ch)])
+    N = np.array([float((valid & (g == c)).sum()) for c in range(n_ch)])
+    bits = ce.view(np.uint32).astype(np.int64)
+    thr, k_rem, n_ties = radix_select(bits, k)
+    thr_val = np.array([thr], np.uint32).view(f32)[0]
+    ce_loss = (ce[bits > thr].sum(dtype=np.float64) + k_rem * float(thr_val)) / k
+    present = int((N > 0).sum())
+    D = S + N - I + 1e-6
+    jac = float(np.where(N > 0, 1 - I / D, 0).sum() / present) if present else 0.0
+    a = np.where(N > 0, -1.0 / (D * max(present, 1)), 0).astype(f32)
+    b = np.where(N > 0, I / (D * D * max(present, 1)), 0).astype(f32)
+    losses = (0.5 * ce_loss + 0.5 * jac, ce_loss, jac)
+    # tl_grad_pixel_kernel
+    w_ce = np.where(valid & in_range, np.where(bits > thr, 1.0, np.where(bits == thr, k_rem / n_ties, 0.0)) / k, 0).astype(f32)
+    onehot = (np.arange(n_ch)[:, None] == g[None, :])
+    q = np.where(valid[None, :], np.where(onehot, a[:, None], b[:, None]), 0).astype(f32)
+    dot = (p * q).sum(0).astype(f32)
+    gup = (f32(grad_scale) * f32(0.5) * (w_ce * (p - onehot) + p * (q - dot))).astype(f32).reshape(n_ch, H, W)
+    # tl_grad_gather_kernel, with its candidate ranges checked against the exact footprints
+    def axis_weights(in_size, out_size, scale, i0, i1, l0, l1):
+        Wm = np.zeros((in_size, out_size), f32)
+        Wm[i0, np.arange(out_size)] += l0
+        Wm[i1, np.arange(out_size)] += l1
+        for c in range(in_size):
+            if scale > 0:
+                lo = max(0, int(math.floor(f32(c - 1) / scale)) - 1)
+                hi = min(out_size - 1, int(math.ceil(f32(c + 1) / scale)) + 1)
+            else:
+                lo, hi = 0, out_size - 1
+            nz = np.nonzero(Wm[c])[0]
+            assert nz.size == 0 or (lo <= nz.min() and nz.max() <= hi), (c, lo, hi, nz.min(), nz.max())
+        return Wm
+    Wy = axis_weights(h4, H, sy, y0, y1, wy0, wy1)
+    Wx = axis_weights(w4, W, sx, x0, x1, wx0, wx1)
+    grad = np.zeros((C_all, h4, w4), f32)
+    grad[:n_ch] = np.einsum("yh,chw,xw->cyx", Wy, gup, Wx)
+    return losses, grad, (thr, k_rem, n_ties)
+
+
+@pytest.mark.parametrize("case", ["golden_ignore", "golden_absent", "random_small_k", "ties_at_zero", "one_object", "same_size"])
+def test_cuda_algorithm_restatement_matches_autograd(gold, case):
+    meta, z = gold
+    g = torch.Generator().manual_seed(11)
+    if case.startswith("golden"):
+        name = "ignore_shrunk" if case == "golden_ignore" else "absent_all"
+        lg = z["lh_logits4"].copy()
+        gt = z[f"lh_gt_{name}"]
+        n_obj = meta["n_obj"]
+        k = [c for c in meta["loss_head"] if c["name"] == name][0]["k"]
+    elif case == "random_small_k":
+        lg = (3 * torch.randn(11, 19, 23, generator=g)).numpy()
+        gt = torch.randint(0, 8, (73, 89), generator=g).to(torch.uint8).numpy()
+        gt[5:20, 30:60] = 255
+        n_obj, k = 7, 100
+    elif case == "ties_at_zero":                       # most pixels ignored: the k-th largest value is the 0 of an ignored pixel
+        lg = (3 * torch.randn(11, 9, 11, generator=g)).numpy()
+        gt = np.full((33, 41), 255, np.uint8)
+        gt[3:9, 4:30] = 1
+        gt[20:22, 5:9] = 0
+        n_obj, k = 2, 600
+    elif case == "one_object":
+        lg = torch.randn(11, 17, 17, generator=g).numpy()
+        gt = (torch.rand(65, 65, generator=g) > 0.7).to(torch.uint8).numpy()
+        n_obj, k = 1, 65 * 65
+    else:                                               # label map at the logits' own size: scale 1, taps collapse
+        lg = torch.randn(11, 21, 25, generator=g).numpy()
+        gt = torch.randint(0, 4, (21, 25), generator=g).to(torch.uint8).numpy()
+        n_obj, k = 3, 200
+    (total, ce, jac), grad, (thr, k_rem, n_ties) = emulate_loss_head(lg.astype(np.float32), gt, n_obj, k)
+    o_total, o_ce, o_jac, o_grad = TO.loss_head_with_grad(torch.from_numpy(lg).float().unsqueeze(0),
+                                                          torch.from_numpy(gt), n_obj, k)
+    assert 1 <= k_rem <= n_ties
+    assert abs(ce - o_ce) < 5e-6 * max(1.0, o_ce) and abs(jac - o_jac) < 5e-6 and abs(total - o_total) < 5e-6 * max(1.0, o_total)
+    og = o_grad[0].numpy()
+    assert np.abs(grad - og).max() <= 2e-5 * np.abs(og).max() + 1e-10, (case, np.abs(grad - og).max(), np.abs(og).max())
+    if case == "ties_at_zero":
+        assert thr == 0 and n_ties > k_rem             # the threshold is an ignored pixel's zero: those carry no gradient
