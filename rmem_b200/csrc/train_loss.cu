@@ -416,8 +416,8 @@ int rmem_train_loss_fwd_bwd(const float* logits4, int n_logit_ch, int h4, int w4
   if (grad_logits4) {
     tl_grad_pixel_kernel<<<L.nb, kThreads, 0, s>>>(logits4, h4, w4, gt, H, W, n_ch, ce, coef, grad_scale, gup);
     RMEM_LAUNCH_CHECK();
-    tl_grad_gather_kernel<<<cdiv(n_logit_ch * h4 * w4, kThreads), kThreads, 0, s>>>(gup, H, W, h4, w4, n_ch,
-                                                                                    n_logit_ch, grad_logits4);
+    const int gather_grid = cdiv(n_logit_ch * h4 * w4, kThreads);
+    tl_grad_gather_kernel<<<gather_grid, kThreads, 0, s>>>(gup, H, W, h4, w4, n_ch, n_logit_ch, grad_logits4);
     RMEM_LAUNCH_CHECK();
   }
   return RMEM_OK;
@@ -431,8 +431,9 @@ int rmem_train_predict_mask(const float* logits4, int n_logit_ch, int h4, int w4
   RMEM_REQUIRE(H > 0 && W > 0 && h4 > 0 && w4 > 0 && (long long)H * W < (1ll << 30), "train_predict_mask: bad size");
   RMEM_REQUIRE(obj_num >= 0 && obj_num + 1 <= kMaxCh && obj_num + 1 <= n_logit_ch,
                "train_predict_mask: obj_num=%d needs 1..%d logit channels, got %d", obj_num, kMaxCh, n_logit_ch);
-  tl_predict_mask_kernel<<<cdiv(H * W, kThreads), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits4, h4, w4, H, W, obj_num + 1, label);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = cdiv(H * W, kThreads);
+  tl_predict_mask_kernel<<<grid, kThreads, 0, s>>>(logits4, h4, w4, H, W, obj_num + 1, label);
   RMEM_LAUNCH_CHECK();
   return RMEM_OK;
   RMEM_API_END

@@ -268,3 +268,126 @@ def test_cuda_algorithm_restatement_matches_autograd(gold, case):
     assert np.abs(grad - og).max() <= 2e-5 * np.abs(og).max() + 1e-10, (case, np.abs(grad - og).max(), np.abs(og).max())
     if case == "ties_at_zero":
         assert thr == 0 and n_ties > k_rem             # the threshold is an ignored pixel's zero: those carry no gradient
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the ACTUAL kernels of csrc/train_loss.cu, executed on the CPU by the host emulation of tests/cuda_emu (real threads per
+# block, barriers for __syncthreads and the warp primitives): the transcription of the algorithm above is checked here
+# too, before the code ever sees a GPU.  "Device" pointers are numpy arrays.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("cuda_emu_build", os.path.join(ROOT, "tests", "cuda_emu", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build("train_loss.cu")
+
+
+def emu_loss_head(lib, lg, gt, n_obj, k, want_grad=True, grad_scale=1.0):
+    import ctypes as C
+    lg = np.ascontiguousarray(lg, np.float32)
+    gt = np.ascontiguousarray(gt, np.uint8)
+    Cn, h4, w4 = lg.shape
+    H, W = gt.shape
+    n = C.c_size_t(0)
+    assert lib.rmem_train_loss_workspace_bytes(H, W, C.byref(n)) == 0
+    raw = np.full(n.value + 256, 0xCD, np.uint8)                   # poisoned: the kernels must not read what they did not write
+    off = (-raw.ctypes.data) % 256
+    ws = raw[off:off + n.value]
+    losses = np.full(3, np.nan, np.float32)
+    grad = np.full_like(lg, np.nan) if want_grad else None
+    vp = lambda a: C.c_void_p(None if a is None else a.ctypes.data)   # noqa: E731
+    rc = lib.rmem_train_loss_fwd_bwd(vp(lg), Cn, h4, w4, vp(gt), H, W, int(n_obj), C.c_longlong(int(k)),
+                                     C.c_float(grad_scale), vp(losses), vp(grad), vp(ws), C.c_size_t(n.value), None)
+    return rc, losses, grad
+
+
+# (the two golden label maps run in the next test, once each: the emulation spends ~1 s per call at 129 x 161)
+EMU_CASES = ["random_small_k", "ties_at_zero", "one_object", "same_size", "no_objects"]
+
+
+def emu_case(gold, case):
+    meta, z = gold
+    g = torch.Generator().manual_seed(11)
+    if case.startswith("golden"):
+        name = "ignore_shrunk" if case == "golden_ignore" else "absent_all"
+        k = [c for c in meta["loss_head"] if c["name"] == name][0]["k"]
+        return z["lh_logits4"].copy(), z[f"lh_gt_{name}"], meta["n_obj"], k
+    if case == "random_small_k":
+        lg = (3 * torch.randn(11, 19, 23, generator=g)).numpy()
+        gt = torch.randint(0, 8, (73, 89), generator=g).to(torch.uint8).numpy()
+        gt[5:20, 30:60] = 255
+        return lg, gt, 7, 100
+    if case == "ties_at_zero":
+        lg = (3 * torch.randn(11, 9, 11, generator=g)).numpy()
+        gt = np.full((33, 41), 255, np.uint8)
+        gt[3:9, 4:30] = 1
+        gt[20:22, 5:9] = 0
+        return lg, gt, 2, 600
+    if case == "one_object":
+        lg = torch.randn(11, 17, 17, generator=g).numpy()
+        return lg, (torch.rand(65, 65, generator=g) > 0.7).to(torch.uint8).numpy(), 1, 65 * 65
+    if case == "same_size":
+        lg = torch.randn(11, 21, 25, generator=g).numpy()
+        return lg, torch.randint(0, 4, (21, 25), generator=g).to(torch.uint8).numpy(), 3, 200
+    lg = torch.randn(11, 9, 9, generator=g).numpy()                # no_objects: one channel, everything is exactly zero
+    return lg, np.zeros((33, 33), np.uint8), 0, 33 * 33
+
+
+@pytest.mark.parametrize("case", EMU_CASES)
+def test_cuda_kernels_on_host_emulation_vs_oracle(gold, emu_lib, case):
+    lg, gt, n_obj, k = emu_case(gold, case)
+    rc, losses, grad = emu_loss_head(emu_lib, lg, gt, n_obj, k)
+    assert rc == 0, emu_lib.rmem_last_error()
+    total, ce, jac, og = TO.loss_head_with_grad(torch.from_numpy(lg).float().unsqueeze(0), torch.from_numpy(gt), n_obj, k)
+    for got, want in zip(losses.astype(np.float64), (total, ce, jac)):
+        assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (case, losses, (total, ce, jac))
+    og = og[0].numpy()
+    assert np.isfinite(grad).all()
+    assert np.abs(grad - og).max() <= 1e-4 * np.abs(og).max() + 1e-10, (case, np.abs(grad - og).max(), np.abs(og).max())
+    assert not grad[n_obj + 1:].any()
+    # the numpy restatement above is the same algorithm: threshold handling included, they agree far below the tolerance
+    (t2, c2, j2), g2, _ = emulate_loss_head(lg.astype(np.float32), gt, n_obj, k)
+    assert abs(losses[1] - c2) <= 2e-6 * max(1.0, c2) and np.abs(grad - g2).max() <= 2e-6 * np.abs(g2).max() + 1e-12
+    if case not in ("ties_at_zero", "no_objects"):
+        return
+    # run to run bit-identical; forward-only leaves the losses unchanged; grad_scale is exact for a power of two
+    rc, losses2, grad2 = emu_loss_head(emu_lib, lg, gt, n_obj, k)
+    assert rc == 0 and np.array_equal(losses2, losses) and np.array_equal(grad2, grad)
+    rc, losses3, none = emu_loss_head(emu_lib, lg, gt, n_obj, k, want_grad=False)
+    assert rc == 0 and none is None and np.array_equal(losses3, losses)
+    rc, _, grad4 = emu_loss_head(emu_lib, lg, gt, n_obj, k, grad_scale=0.25)
+    assert rc == 0 and np.array_equal(grad4 * 4, grad)
+
+
+def test_cuda_kernels_on_host_emulation_reference_golden_and_mask(gold, emu_lib):
+    import ctypes as C
+    meta, z = gold
+    for case in meta["loss_head"]:
+        name = case["name"]
+        rc, losses, grad = emu_loss_head(emu_lib, z["lh_logits4"], z[f"lh_gt_{name}"], meta["n_obj"], case["k"])
+        assert rc == 0
+        ref = z[f"lh_losses_{name}"]
+        assert np.abs(losses - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+        rg = z[f"lh_grad_{name}"]
+        assert np.abs(grad - rg).max() <= 1e-4 * np.abs(rg).max()
+    # rmem_train_predict_mask against the reference's recorded masks would need the engine; against the oracle's argmax:
+    g = torch.Generator().manual_seed(5)
+    for (h4, w4, H, W, n_obj) in [(19, 23, 73, 89, 7), (21, 25, 21, 25, 3), (9, 9, 33, 33, 1)]:
+        lg = (3 * torch.randn(11, h4, w4, generator=g)).numpy()
+        lab = np.full((H, W), 99, np.uint8)
+        rc = emu_lib.rmem_train_predict_mask(C.c_void_p(lg.ctypes.data), 11, h4, w4, H, W, n_obj,
+                                             C.c_void_p(lab.ctypes.data), None)
+        assert rc == 0
+        want = TO.predict_mask(torch.from_numpy(lg), H, W, n_obj).numpy()
+        assert int((lab != want).sum()) <= 1 and lab.max() <= n_obj
+
+
+def test_cuda_entry_points_reject_bad_arguments_on_host_emulation(emu_lib):
+    lg, gt = np.zeros((11, 9, 9), np.float32), np.zeros((33, 33), np.uint8)
+    for n_obj, k in ((11, 10), (3, 0), (3, 33 * 33 + 1)):
+        rc, _, _ = emu_loss_head(emu_lib, lg, gt, n_obj, k)
+        assert rc == -1 and emu_lib.rmem_last_error()
+    rc, _, _ = emu_loss_head(emu_lib, lg[:3], gt, 5, 10)
+    assert rc == -1
