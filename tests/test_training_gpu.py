@@ -7,7 +7,8 @@ recorded training forward.
 
 Tolerances: the loss head is fp32 with IEEE exp / log (no 16-bit operands): loss values within 2e-5 relative, gradient
 within 1e-4 of its largest entry.  train_forward inherits the engine's fp16-operand logits (<= 1.5e-2 of the largest
-logit, tests/test_engine_gpu.py): per-frame losses within 3e-2 absolute of the reference's, masks >= 98 % identical."""
+logit, tests/test_engine_gpu.py): per-frame losses within 3e-3 absolute of the reference's (achieved 2e-4 on B200,
+profiles/r02_train_pytest_gpu.log), masks >= 99.9 % identical (achieved 99.998 %)."""
 import json
 import os
 
@@ -144,12 +145,12 @@ def test_train_forward_on_cuda_engine_vs_reference(T, gold, cuda_device):
     got_fl = [float(x) for x in fl]
     print(f"train_forward on the CUDA engine: loss {float(loss):.5f} (reference {meta['ref_loss']:.5f}), frame losses "
           f"{[round(x, 5) for x in got_fl]} vs {[round(x, 5) for x in meta['ref_frame_losses']]}")
-    assert max(abs(a - b) for a, b in zip(got_fl, meta["ref_frame_losses"])) < 3e-2
-    assert abs(float(loss) - meta["ref_loss"]) < 5e-2
+    assert max(abs(a - b) for a, b in zip(got_fl, meta["ref_frame_losses"])) < 3e-3
+    assert abs(float(loss) - meta["ref_loss"]) < 5e-3
     got = torch.stack([m[0] for m in pred]).to(torch.uint8).cpu().numpy()
     agree = float((got == z["pred_masks"]).mean())
     print(f"  predicted masks identical to the reference's on {agree:.4%} of the pixels")
-    assert agree >= 0.98
+    assert agree >= 0.999
     assert eng.aot_engines[0].long_memories_indexes == meta["ref_idx"]
     # same sample with the previous prediction fed to the memory (use_prev_pred): runs, finite, close to the GT-fed loss
     loss2, _, _, _ = T.train_forward(eng, frames, masks, 1, [n_obj], step=meta["step"], cfg=tcfg, use_prev_pred=True)
