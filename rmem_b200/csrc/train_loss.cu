@@ -14,13 +14,18 @@
 // top-k selection), so the loss and the gradient are bit-reproducible from run to run.
 //
 //   tl_pixel_kernel     per output pixel: 4-tap upsample, softmax, cross entropy -> ce[P]; per-block class sums
-//                       (I_c = sum p_c [g = c], S_c = sum p_c, N_c = #[g = c] over the valid pixels)
-//   tl_hist / tl_scan   exact k-th largest of ce[] by a 3-pass radix select on the fp32 bit patterns (11 + 11 + 10 bits;
-//                       ce >= 0, so the patterns order like the values)
-//   tl_topk_sum_kernel  sum of the values above the threshold (ties at the threshold enter as k_rem * threshold)
-//   tl_finalize_kernel  losses, Jaccard coefficients per class, tie weight
+//                       (I_c = sum p_c [g = c], S_c = sum p_c, N_c = #[g = c] over the valid pixels); histogram of the
+//                       leading 11 bits of ce.  Last block: class sums folded, first digit of the threshold picked.
+//   tl_hist_kernel x 2  the other two passes of an exact radix select of the k-th largest ce on the fp32 bit patterns
+//                       (11 + 11 + 10 bits; ce >= 0, so the patterns order like the values); warp-aggregated
+//                       shared-memory histograms, integer atomics only.  Last block: next digit (scan_select).
+//   tl_topk_sum_kernel  sum of the values above the threshold (ties at the threshold enter as k_rem * threshold).
+//                       Last block: losses, Jaccard coefficients per class, tie weight.
 //   tl_grad_pixel       d loss / d upsampled logits per pixel (softmax recomputed), channel-major scratch
 //   tl_grad_gather      transpose of the upsampling as a GATHER per 1/4-res logit (fixed order; no float atomics)
+// "Last block": the block that takes the last ticket of a per-launch counter folds what all blocks left in global memory
+// (__threadfence + atomic ticket, as gn_stats_kernel in ops.cu): 4 launches for the value, 6 with the gradient, where
+// the first version needed 9 / 11 (a one-block scan after each histogram, a finalising launch).
 #include "../../include/rmem_b200.h"
 #include "common.cuh"
 
@@ -46,7 +51,7 @@ struct Coef {                     // written by tl_finalize_kernel, read by tl_g
 };
 
 struct Layout {
-  size_t ce, gup, part, tpart, hist, state, coef, total;
+  size_t ce, gup, part, tpart, hist, state, counters, coef, cls, total;   // [hist, coef) is zeroed at the start of a call
   int P, nb;
 };
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -61,7 +66,9 @@ inline Layout make_layout(int H, int W) {
   L.tpart = o; o = align256(o + (size_t)L.nb * 8);
   L.hist = o; o = align256(o + (size_t)3 * kBins * 4);
   L.state = o; o = align256(o + sizeof(SelectState));
+  L.counters = o; o = align256(o + 4 * sizeof(unsigned int));
   L.coef = o; o = align256(o + sizeof(Coef));
+  L.cls = o; o = align256(o + kPartStride * sizeof(double));
   L.total = o;
   return L;
 }
@@ -116,10 +123,81 @@ __device__ __forceinline__ void pixel_softmax(const float* __restrict__ lg, int 
   for (int c = 0; c < kMaxCh; ++c) p[c] *= inv;
 }
 
+// ---- pieces shared by the selection kernels ----
+// Ticket of the calling block on `counter`; true for the block that arrives last, after which everything the other
+// blocks wrote to global memory before their ticket is visible to it (read it with __ldcg).
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// One histogram vote per lane, aggregated over the lanes of the warp that vote for the same bin (ce values cluster in a
+// few exponent bins: unaggregated shared-memory atomics would serialise 32 deep).  Every lane of the warp must call it;
+// vote = false keeps a lane out.
+__device__ __forceinline__ void hist_vote(unsigned int* sh, bool vote, unsigned int digit) {
+  const unsigned int key = vote ? digit : 0xffffffffu;
+  const unsigned int peers = __match_any_sync(0xffffffffu, key);
+  if (vote && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&sh[digit], (unsigned int)__popc(peers));
+}
+__device__ __forceinline__ void hist_flush(const unsigned int* sh, unsigned int* hist) {
+  for (int i = threadIdx.x; i < kBins; i += kThreads)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// The bin, counted from the top, in which rank k_rem falls -- by the whole (last) block: thread t owns bins
+// [8t, 8t + 8), a suffix sum over the threads (warp shuffles + 8 warp totals) gives the count above each thread's bins,
+// and the one thread whose bins straddle the rank walks its eight bins.
+__device__ __forceinline__ void scan_select(const unsigned int* hist, int pass, SelectState* st, unsigned int k) {
+  __shared__ unsigned int wtot[kThreads / 32];
+  constexpr int per = kBins / kThreads;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  unsigned int h[per], s = 0;
+#pragma unroll
+  for (int j = 0; j < per; ++j) { h[j] = __ldcg(&hist[t * per + j]); s += h[j]; }
+  const unsigned int k_rem = pass ? st->k_rem : k;
+  const unsigned int prev = pass ? st->prefix : 0u;
+  unsigned int v = s;                                      // -> sum over the lanes >= this one
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int n = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += n;
+  }
+  if (lane == 0) wtot[warp] = v;
+  __syncthreads();                                         // also: every thread has read st before one of them writes it
+  unsigned int above = v - s;
+  for (int w = warp + 1; w < kThreads / 32; ++w) above += wtot[w];
+  if (above < k_rem && k_rem <= above + s) {
+    unsigned int cum = above, hit = h[0];
+    int bin = 0;
+    bool found = false;
+#pragma unroll
+    for (int j = per - 1; j >= 0; --j) {
+      if (!found) {
+        if (j == 0 || cum + h[j] >= k_rem) { found = true; bin = j; hit = h[j]; }
+        else cum += h[j];
+      }
+    }
+    const unsigned int b = (unsigned int)(t * per + bin);
+    st->prefix = pass == 0 ? b : (prev << (pass == 1 ? 11 : 10)) | b;
+    st->k_rem = k_rem - cum;
+    st->n_ties = hit;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) tl_pixel_kernel(const float* __restrict__ lg, int h4, int w4,
                                                             const uint8_t* __restrict__ gt, int H, int W, int n_ch,
-                                                            float* __restrict__ ce, float* __restrict__ part) {
+                                                            float* __restrict__ ce, float* part, unsigned int* hist,
+                                                            unsigned int* counter, double* cls, SelectState* st,
+                                                            unsigned int k) {
   __shared__ float sm[kThreads / 32][kPartStride];
+  __shared__ unsigned int sh[kBins];
+  __shared__ double fold[kThreads];
+  for (int i = threadIdx.x; i < kBins; i += kThreads) sh[i] = 0u;
   const int P = H * W;
   const int pix = blockIdx.x * kThreads + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -140,6 +218,8 @@ __global__ void __launch_bounds__(kThreads) tl_pixel_kernel(const float* __restr
     }
     ce[pix] = loss;                                // 255 (ignored) and ids above obj_num: 0
   }
+  __syncthreads();                                 // sh is zeroed
+  hist_vote(sh, in, __float_as_uint(loss) >> 21);
   const bool valid = in && g != 255;               // flatten_probas keeps everything but 255
 #pragma unroll
   for (int c = 0; c < kMaxCh; ++c) {
@@ -161,54 +241,50 @@ __global__ void __launch_bounds__(kThreads) tl_pixel_kernel(const float* __restr
     for (int w = 0; w < kThreads / 32; ++w) acc += sm[w][threadIdx.x];
     part[(size_t)blockIdx.x * kPartStride + threadIdx.x] = acc;
   }
+  hist_flush(sh, hist);
+  if (!last_block_done(counter)) return;
+  // class sums: thread -> (column o, slice j); slice j adds blocks j, j + J, ... in order, then the J slices in order
+  constexpr int J = kThreads / kPartStride;
+  const int o = threadIdx.x % kPartStride, j = threadIdx.x / kPartStride;
+  double a = 0.0;
+  if (j < J)
+    for (unsigned int b = j; b < gridDim.x; b += J) a += (double)__ldcg(&part[(size_t)b * kPartStride + o]);
+  fold[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < kPartStride) {
+    double tsum = 0.0;
+    for (int jj = 0; jj < J; ++jj) tsum += fold[jj * kPartStride + threadIdx.x];
+    cls[threadIdx.x] = tsum;
+  }
+  scan_select(hist, 0, st, k);
 }
 
-// pass 0: bits 31..21, pass 1: bits 20..10 of the values whose bits 31..21 equal the prefix, pass 2: bits 9..0
+// pass 1: bits 20..10 of the values whose bits 31..21 equal the prefix, pass 2: bits 9..0 of those whose bits 31..10 do
 __global__ void __launch_bounds__(kThreads) tl_hist_kernel(const float* __restrict__ ce, int P, int pass,
-                                                           const SelectState* __restrict__ st,
-                                                           unsigned int* __restrict__ hist) {
+                                                           SelectState* st, unsigned int* hist, unsigned int* counter,
+                                                           unsigned int k) {
   __shared__ unsigned int sh[kBins];
   for (int i = threadIdx.x; i < kBins; i += kThreads) sh[i] = 0u;
   __syncthreads();
-  const unsigned int prefix = pass ? st->prefix : 0u;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
-    const unsigned int b = __float_as_uint(ce[i]);
-    if (pass == 0) atomicAdd(&sh[b >> 21], 1u);
-    else if (pass == 1) { if ((b >> 21) == prefix) atomicAdd(&sh[(b >> 10) & 2047u], 1u); }
-    else { if ((b >> 10) == prefix) atomicAdd(&sh[b & 1023u], 1u); }
+  const unsigned int prefix = st->prefix;
+  for (int base = blockIdx.x * kThreads; base < P; base += gridDim.x * kThreads) {   // warp-uniform trip count
+    const int i = base + threadIdx.x;
+    const unsigned int b = i < P ? __float_as_uint(ce[i]) : 0u;
+    if (pass == 1) hist_vote(sh, i < P && (b >> 21) == prefix, (b >> 10) & 2047u);
+    else hist_vote(sh, i < P && (b >> 10) == prefix, b & 1023u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kBins; i += kThreads)
-    if (sh[i]) atomicAdd(&hist[i], sh[i]);
-}
-
-// one block: the bin, counted from the top, in which the rank k_rem falls
-__global__ void __launch_bounds__(kThreads) tl_scan_kernel(const unsigned int* __restrict__ hist, int pass,
-                                                           SelectState* __restrict__ st, unsigned int k) {
-  __shared__ unsigned int tot[kThreads];
-  constexpr int per = kBins / kThreads;
-  unsigned int s = 0;
-  for (int j = 0; j < per; ++j) s += hist[threadIdx.x * per + j];
-  tot[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int k_rem = pass ? st->k_rem : k;
-    unsigned int cum = 0;
-    int t = kThreads - 1;
-    while (t > 0 && cum + tot[t] < k_rem) { cum += tot[t]; --t; }
-    int b = t * per + per - 1;
-    while (b > t * per && cum + hist[b] < k_rem) { cum += hist[b]; --b; }
-    const unsigned int prev = pass ? st->prefix : 0u;
-    st->prefix = pass == 0 ? (unsigned int)b : (prev << (pass == 1 ? 11 : 10)) | (unsigned int)b;
-    st->k_rem = k_rem - cum;
-    st->n_ties = hist[b];
-  }
+  hist_flush(sh, hist);
+  if (!last_block_done(counter)) return;
+  scan_select(hist, pass, st, k);
 }
 
 __global__ void __launch_bounds__(kThreads) tl_topk_sum_kernel(const float* __restrict__ ce, int P,
-                                                               const SelectState* __restrict__ st,
-                                                               double* __restrict__ tpart) {
-  __shared__ double red[kThreads / 32];
+                                                               const SelectState* __restrict__ st, double* tpart,
+                                                               unsigned int* counter, const double* __restrict__ cls,
+                                                               int n_ch, unsigned int k, Coef* __restrict__ coef,
+                                                               float* __restrict__ losses) {
+  __shared__ double red[kThreads];
   const int i = blockIdx.x * kThreads + threadIdx.x;
   const unsigned int thr = st->prefix;
   double v = 0.0;
@@ -225,21 +301,9 @@ __global__ void __launch_bounds__(kThreads) tl_topk_sum_kernel(const float* __re
     for (int w = 0; w < kThreads / 32; ++w) acc += red[w];
     tpart[blockIdx.x] = acc;
   }
-}
-
-__global__ void __launch_bounds__(kThreads) tl_finalize_kernel(const float* __restrict__ part,
-                                                               const double* __restrict__ tpart, int nb, int n_ch,
-                                                               unsigned int k, const SelectState* __restrict__ st,
-                                                               Coef* __restrict__ coef, float* __restrict__ losses) {
-  __shared__ double cls[kPartStride];
-  __shared__ double red[kThreads];
-  if (threadIdx.x < kPartStride) {
-    double acc = 0.0;
-    for (int b = 0; b < nb; ++b) acc += (double)part[(size_t)b * kPartStride + threadIdx.x];
-    cls[threadIdx.x] = acc;
-  }
-  double v = 0.0;
-  for (int b = threadIdx.x; b < nb; b += kThreads) v += tpart[b];
+  if (!last_block_done(counter)) return;
+  v = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) v += __ldcg(&tpart[b]);
   red[threadIdx.x] = v;
   __syncthreads();
   for (int o = kThreads / 2; o > 0; o >>= 1) {
@@ -263,13 +327,13 @@ __global__ void __launch_bounds__(kThreads) tl_finalize_kernel(const float* __re
       coef->b[c] = b;
     }
     if (present) jac /= present;
-    const float thr = __uint_as_float(st->prefix);
-    const double ce = (red[0] + (double)st->k_rem * (double)thr) / (double)k;
+    const float thr_val = __uint_as_float(thr);
+    const double ce_loss = (red[0] + (double)st->k_rem * (double)thr_val) / (double)k;
     coef->inv_k = (float)(1.0 / (double)k);
     coef->tie_w = (float)((double)st->k_rem / (double)st->n_ties);
-    coef->thr_bits = st->prefix;
-    losses[0] = (float)(0.5 * ce + 0.5 * jac);
-    losses[1] = (float)ce;
+    coef->thr_bits = thr;
+    losses[0] = (float)(0.5 * ce_loss + 0.5 * jac);
+    losses[1] = (float)ce_loss;
     losses[2] = (float)jac;
   }
 }
@@ -399,19 +463,17 @@ int rmem_train_loss_fwd_bwd(const float* logits4, int n_logit_ch, int h4, int w4
   const int n_ch = obj_num + 1;
   const unsigned int k = (unsigned int)top_k_pixels;
 
-  RMEM_CUDA_CHECK(cudaMemsetAsync(ws + L.hist, 0, L.coef - L.hist, s));      // histograms + select state
-  tl_pixel_kernel<<<L.nb, kThreads, 0, s>>>(logits4, h4, w4, gt, H, W, n_ch, ce, part);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws + L.counters);
+  double* cls = reinterpret_cast<double*>(ws + L.cls);
+  RMEM_CUDA_CHECK(cudaMemsetAsync(ws + L.hist, 0, L.coef - L.hist, s));      // histograms, select state, tickets
+  tl_pixel_kernel<<<L.nb, kThreads, 0, s>>>(logits4, h4, w4, gt, H, W, n_ch, ce, part, hist, counters, cls, st, k);
   RMEM_LAUNCH_CHECK();
   const int hist_grid = min(L.nb, 148 * 4);
-  for (int pass = 0; pass < 3; ++pass) {
-    tl_hist_kernel<<<hist_grid, kThreads, 0, s>>>(ce, L.P, pass, st, hist + pass * kBins);
-    RMEM_LAUNCH_CHECK();
-    tl_scan_kernel<<<1, kThreads, 0, s>>>(hist + pass * kBins, pass, st, k);
+  for (int pass = 1; pass < 3; ++pass) {
+    tl_hist_kernel<<<hist_grid, kThreads, 0, s>>>(ce, L.P, pass, st, hist + pass * kBins, counters + pass, k);
     RMEM_LAUNCH_CHECK();
   }
-  tl_topk_sum_kernel<<<L.nb, kThreads, 0, s>>>(ce, L.P, st, tpart);
-  RMEM_LAUNCH_CHECK();
-  tl_finalize_kernel<<<1, kThreads, 0, s>>>(part, tpart, L.nb, n_ch, k, st, coef, losses);
+  tl_topk_sum_kernel<<<L.nb, kThreads, 0, s>>>(ce, L.P, st, tpart, counters + 3, cls, n_ch, k, coef, losses);
   RMEM_LAUNCH_CHECK();
   if (grad_logits4) {
     tl_grad_pixel_kernel<<<L.nb, kThreads, 0, s>>>(logits4, h4, w4, gt, H, W, n_ch, ce, coef, grad_scale, gup);

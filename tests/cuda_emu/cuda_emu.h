@@ -78,6 +78,33 @@ inline unsigned int __ballot_sync(unsigned, int pred) {
   w->bar.arrive_and_wait();
   return b;
 }
+template <typename T>
+inline T __shfl_down_sync(unsigned, T v, int o) {
+  static_assert(sizeof(T) <= 8, "shuffle of up to 8 bytes");
+  emu::Warp* w = emu::ctx.warp;
+  uint64_t raw = 0;
+  std::memcpy(&raw, &v, sizeof(T));
+  w->buf[emu::ctx.lane] = raw;
+  w->bar.arrive_and_wait();
+  const int src = emu::ctx.lane + o;
+  uint64_t got = src < emu::ctx.warp_lanes ? w->buf[src] : raw;
+  w->bar.arrive_and_wait();
+  T out;
+  std::memcpy(&out, &got, sizeof(T));
+  return out;
+}
+inline unsigned int __match_any_sync(unsigned, unsigned int v) {
+  emu::Warp* w = emu::ctx.warp;
+  w->buf[emu::ctx.lane] = v;
+  w->bar.arrive_and_wait();
+  unsigned int peers = 0;
+  for (int l = 0; l < emu::ctx.warp_lanes; ++l) peers |= (unsigned int)(w->buf[l] == (uint64_t)v) << l;
+  w->bar.arrive_and_wait();
+  return peers;
+}
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __popc(unsigned int v) { return __builtin_popcount(v); }
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

@@ -1,5 +1,5 @@
 """Time the training-side loss head (csrc/train_loss.cu) at the c3 geometry (481 x 849 label map, 121 x 213 logits, 10
-objects) with CUDA events on the launching stream; one JSON line.  The chain is 12 small launches over ~20 MB of scratch:
+objects) with CUDA events on the launching stream; one JSON line.  The chain is 6 small launches (4 without the gradient) over ~20 MB of scratch:
 latency-bound, not bandwidth-bound -- the line says so instead of quoting a roofline fraction for it."""
 import json
 import os
@@ -39,10 +39,10 @@ def main():
         "fwd_bwd_us": round(timed(lambda: head(lg, gt, n_obj, k)), 2),
         "fwd_only_us": round(timed(lambda: head(lg, gt, n_obj, k, want_grad=False)), 2),
         "predict_mask_us": round(timed(lambda: T.predict_mask(lg, H, W, n_obj)), 2),
-        "launches_fwd_bwd": 11, "launches_fwd_only": 9,
+        "launches_fwd_bwd": 6, "launches_fwd_only": 4,
         "algorithmic_bytes": {"logits_read": 11 * h4 * w4 * 4, "labels_read": H * W, "grad_written": 11 * h4 * w4 * 4},
         "scratch_bytes": {"ce": H * W * 4, "grad_upsampled": 11 * H * W * 4},
-        "bound": "launch latency (11 dependent launches incl. 3 histogram passes + 3 one-block scans); 2.6 MB algorithmic",
+        "bound": "launch latency (6 dependent launches: pixel + 2 histogram passes + top-k sum, each folded by its last block, + 2 gradient kernels); 2.6 MB algorithmic",
         "gpu": torch.cuda.get_device_name(0),
     }
     losses, grad = head(lg, gt, n_obj, k)
