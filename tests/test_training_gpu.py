@@ -37,14 +37,19 @@ def T(cuda_device):
     return training
 
 
-def check_against(head, lg, gt, n_obj, k, ref_losses, ref_grad, dev):
+def check_against(head, lg, gt, n_obj, k, ref_losses, ref_grad, dev, tag=None):
     losses, grad = head(lg.to(dev), gt.to(dev), n_obj, k)
     losses, grad = losses.cpu().double().numpy(), grad.cpu()
     for got, want in zip(losses, ref_losses):
         assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (losses, ref_losses)
     scale = float(ref_grad.abs().max())
-    assert float((grad.reshape(ref_grad.shape) - ref_grad).abs().max()) <= 1e-4 * scale + 1e-10
+    gerr = float((grad.reshape(ref_grad.shape) - ref_grad).abs().max())
+    assert gerr <= 1e-4 * scale + 1e-10
     assert torch.isfinite(grad).all()
+    if tag:
+        from parity_report import report
+        report("training/loss_head/" + tag, losses=[float(x) for x in losses], ref_losses=[float(x) for x in ref_losses],
+               grad_err_rel_to_max=gerr / scale if scale else 0.0, tolerances={"loss_rel": 2e-5, "grad_rel_to_max": 1e-4})
     return losses, grad
 
 
@@ -55,7 +60,8 @@ def test_loss_head_reproduces_reference_values_and_gradient(T, gold, cuda_device
     for case in meta["loss_head"]:
         name = case["name"]
         check_against(head, lg, torch.from_numpy(z[f"lh_gt_{name}"]), meta["n_obj"], case["k"],
-                      z[f"lh_losses_{name}"], torch.from_numpy(z[f"lh_grad_{name}"]), cuda_device)
+                      z[f"lh_losses_{name}"], torch.from_numpy(z[f"lh_grad_{name}"]), cuda_device,
+                      tag="reference_" + name)
 
 
 CASES = ["random_small_k", "ties_at_zero", "one_object", "same_size", "no_objects", "c3_geometry"]
@@ -94,7 +100,7 @@ def test_loss_head_vs_oracle(T, cuda_device, case):
     lg, gt, n_obj, k = make_case(case)
     total, ce, jac, grad = TO.loss_head_with_grad(lg.unsqueeze(0), gt, n_obj, k)
     head = T.LossHead(cuda_device)
-    losses, g1 = check_against(head, lg, gt, n_obj, k, [total, ce, jac], grad[0], cuda_device)
+    losses, g1 = check_against(head, lg, gt, n_obj, k, [total, ce, jac], grad[0], cuda_device, tag="oracle_" + case)
     # channels above obj_num carry no gradient; a second run is bit-identical (fixed-order reductions, no float atomics)
     assert float(g1[n_obj + 1:].abs().max()) == 0.0 if n_obj < 10 else True
     losses2, g2 = head(lg.to(cuda_device), gt.to(cuda_device), n_obj, k)
@@ -150,6 +156,11 @@ def test_train_forward_on_cuda_engine_vs_reference(T, gold, cuda_device):
     got = torch.stack([m[0] for m in pred]).to(torch.uint8).cpu().numpy()
     agree = float((got == z["pred_masks"]).mean())
     print(f"  predicted masks identical to the reference's on {agree:.4%} of the pixels")
+    from parity_report import report
+    report("training/train_small_forward", vs="the reference's training engine (eval mode, identity shuffle off)",
+           loss=float(loss), ref_loss=meta["ref_loss"],
+           worst_frame_loss_diff=max(abs(a - b) for a, b in zip(got_fl, meta["ref_frame_losses"])),
+           mask_agreement=agree, tolerances={"frame_loss": 3e-3, "loss": 5e-3, "mask": 0.999})
     assert agree >= 0.999
     assert eng.aot_engines[0].long_memories_indexes == meta["ref_idx"]
     # same sample with the previous prediction fed to the memory (use_prev_pred): runs, finite, close to the GT-fed loss
