@@ -31,13 +31,22 @@ extern "C" const char* rmem_last_error(void) { return rmem::get_error(); }
 """
 
 
-def build(source: str) -> ctypes.CDLL:
+DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];")
+
+
+def build(source: str, extra: str = "") -> ctypes.CDLL:
+    """`extra`: C++ appended to the translation unit (extern "C" shims over its host functions for the tests)."""
     src = open(os.path.join(CSRC, source)).read()
     out, n = LAUNCH.subn(r"emu::launch(\1, dim3(\2), dim3(\3), ", src)
-    assert n == src.count("<<<") and n > 0, f"{source}: {n} of {src.count('<<<')} launches rewritten"
+    assert n == src.count("<<<"), f"{source}: {n} of {src.count('<<<')} launches rewritten"
+    out = DYN_SMEM.sub(r"unsigned char* \1 = emu::ctx.dyn_smem;", out)
+    out = out.replace('#include "ops.cuh"', f'#include "{CSRC}/ops.cuh"')
     out = out.replace('#include "../../include/rmem_b200.h"', f'#include "{ROOT}/include/rmem_b200.h"')
     out = out.replace('#include "common.cuh"', f'#include "{CSRC}/common.cuh"')
-    tag = hashlib.sha256((out + SUPPORT + open(os.path.join(HERE, "cuda_emu.h")).read()).encode()).hexdigest()[:16]
+    out += extra
+    hdrs = "".join(open(os.path.join(d, f)).read() for d in (HERE, os.path.join(HERE, "stubs")) for f in sorted(os.listdir(d))
+                   if f.endswith(".h"))
+    tag = hashlib.sha256((out + SUPPORT + hdrs).encode()).hexdigest()[:16]
     cache = os.path.join(tempfile.gettempdir(), "rmem_cuda_emu")
     os.makedirs(cache, exist_ok=True)
     so = os.path.join(cache, f"{source}.{tag}.so")

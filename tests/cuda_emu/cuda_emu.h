@@ -34,6 +34,13 @@ struct dim3 {
   dim3(unsigned int x_ = 1, unsigned int y_ = 1, unsigned int z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) uint4 { unsigned int x, y, z, w; };
+struct alignas(8) uint2 { unsigned int x, y; };
+inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+#define __align__(n) alignas(n)
 
 namespace emu {
 struct Warp {
@@ -45,6 +52,7 @@ struct Ctx {
   std::barrier<>* block = nullptr;
   Warp* warp = nullptr;
   int lane = 0, warp_lanes = 32;
+  unsigned char* dyn_smem = nullptr;      // `extern __shared__` of the running block (build.py rewrites the declaration)
 };
 inline thread_local Ctx ctx;
 }  // namespace emu
@@ -119,13 +127,19 @@ inline float __expf(float x) { return expf(x); }
 inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 template <typename T> inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> inline T max(T a, T b) { return a > b ? a : b; }
+inline long long min(long long a, int b) { return a < b ? a : b; }
+inline long long min(int a, long long b) { return a < b ? a : b; }
+inline unsigned int min(unsigned int a, int b) { return a < (unsigned int)b ? a : (unsigned int)b; }
+inline unsigned int min(int a, unsigned int b) { return (unsigned int)a < b ? (unsigned int)a : b; }
 
 namespace emu {
 // One pool of block-size threads per launch; the blocks of the grid run one after the other on it.  The block / warp
 // barriers are rebuilt between two blocks (a thread that returned early has dropped out of them), framed by a pool-wide
 // barrier that nobody ever leaves.
 template <typename... KArgs, typename... Args>
-inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+inline void launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+  std::vector<unsigned char> dyn(smem_bytes + 16);
+  unsigned char* dyn_base = dyn.data() + ((16 - reinterpret_cast<uintptr_t>(dyn.data()) % 16) % 16);
   const int nthreads = (int)(block.x * block.y * block.z);
   const int nwarps = (nthreads + 31) / 32;
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
@@ -146,6 +160,7 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args
       gridDim = grid;
       ctx.lane = t % 32;
       ctx.warp_lanes = std::min(32, nthreads - 32 * (t / 32));
+      ctx.dyn_smem = dyn_base;
       for (long long b = 0; b < nblocks; ++b) {
         blockIdx = {(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y))};
         ctx.block = block_bar.get();
@@ -160,4 +175,19 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args
     });
   for (auto& x : th) x.join();
 }
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+  launch_smem(kernel, grid, block, 0, args...);
+}
 }  // namespace emu
+
+// the launcher of common.cuh (programmatic dependent launch) and its device-side prologue: plain launches here
+namespace rmem {
+inline void pdl_prologue() {}
+inline bool& pdl_enabled() { static thread_local bool on = true; return on; }
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void*, Args&&... args) {
+  emu::launch_smem(kernel, grid, block, smem, static_cast<KArgs>(args)...);
+  return 0;
+}
+}  // namespace rmem

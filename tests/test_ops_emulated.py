@@ -1,0 +1,146 @@
+"""CPU: the integer / exact-arithmetic kernels of rmem_b200/csrc/ops.cu -- the mask head (bit-exact label
+target), the per-engine label split (a1), the ID bank with its four decompositions (a5) and the evict relevance (a12) --
+compiled UNMODIFIED for the host emulation of tests/cuda_emu and run against the same torch / oracle references the GPU
+tests use (tests/test_ops_gpu.py).  The GPU tests stay the parity tests proper; these make the same kernels checkable in
+the build container, which has no GPU.  Sizes are small: an emulated block is 128-256 real threads."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rmem_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SHIMS = """
+extern "C" {
+int emu_mask_head(const float* const* logits4, int k, int h4, int w4, int Ho, int Wo, float* out_logits, uint8_t* out_label) {
+  return rmem::mask_head(logits4, k, h4, w4, Ho, Wo, out_logits, out_label, nullptr);
+}
+int emu_separate_label(const void* label, int is_f32, uint8_t* out, int H, int W, int engine, int n_engines) {
+  return rmem::separate_label(label, is_f32, out, H, W, engine, n_engines, nullptr);
+}
+int emu_idbank(const uint8_t* label, int H, int W, int use_ignore, const float* w_packed, const float* bias,
+               const float* ln_g, const float* ln_b, float* out_f32, int h, int w, int Cc, const float* prefix,
+               const float* prefix_rows) {
+  return rmem::idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_g, ln_b, nullptr, 0, out_f32, h, w, Cc, nullptr,
+                            prefix, prefix_rows);
+}
+int emu_evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel) {
+  return rmem::evict_relevance(mass, T, logits4, h4, w4, h, w, rel, nullptr);
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def lib():
+    spec = importlib.util.spec_from_file_location("cuda_emu_build", os.path.join(ROOT, "tests", "cuda_emu", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build("ops.cu", extra=SHIMS)
+
+
+def vp(a):
+    return C.c_void_p(None if a is None else a.ctypes.data)
+
+
+def npf(t):
+    return np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
+
+
+def test_mask_head_bit_exact_labels_on_host_emulation(lib):
+    """tests/test_ops_gpu.py::test_mask_head_bit_exact_labels at emulation-friendly sizes: 0 label mismatches."""
+    g = torch.Generator().manual_seed(7)
+    for k, (h4, w4, Ho, Wo) in [(1, (17, 21, 65, 81)), (2, (13, 17, 49, 65)), (3, (9, 11, 33, 41)), (1, (17, 21, 17, 21)),
+                                (1, (13, 17, 48, 70))]:
+        lgs = [torch.randn(1, 11, h4, w4, generator=g) * 3 for _ in range(k)]
+        up = [F.interpolate(l, size=(Ho, Wo), mode="bilinear", align_corners=True) for l in lgs]
+        ref_logit = O.soft_logit_aggregation(up)
+        ref_label = O.logits_to_label(ref_logit)[0, 0].to(torch.uint8).numpy()
+        arrs = [npf(l[0]) for l in lgs]
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in arrs])
+        out = np.full((1 + 10 * k, Ho, Wo), np.nan, np.float32)
+        lab = np.full((Ho, Wo), 99, np.uint8)
+        assert lib.emu_mask_head(ptrs, k, h4, w4, Ho, Wo, vp(out), vp(lab)) == 0, lib.rmem_last_error()
+        if k == 1:
+            assert float(np.abs(out - ref_logit[0].numpy()).max()) < 2e-5
+        else:
+            sig = lambda a: 1 / (1 + np.exp(-a.astype(np.float64)))   # noqa: E731
+            assert float(np.abs(sig(out) - sig(ref_logit[0].numpy())).max()) < 2e-6
+        assert int((lab != ref_label).sum()) == 0, (k, h4, w4, Ho, Wo)
+        lab2 = np.full((Ho, Wo), 99, np.uint8)                        # label-only call (no full-resolution logits)
+        assert lib.emu_mask_head(ptrs, k, h4, w4, Ho, Wo, None, vp(lab2)) == 0
+        assert np.array_equal(lab2, lab)
+
+
+def test_separate_label_on_host_emulation(lib):
+    """aot_engine.py:604-628: engine e keeps ids 10e+1 .. 10e+10 renumbered from 1; a single engine passes ids through."""
+    g = torch.Generator().manual_seed(3)
+    H, W = 37, 45
+    lab = torch.randint(0, 31, (H, W), generator=g)
+    lab[3:6, 4:9] = 255
+    for is_f32, src in ((0, lab.to(torch.uint8).numpy()), (1, lab.float().numpy())):
+        src = np.ascontiguousarray(src)
+        for n_eng in (1, 3):
+            want = O.separate_mask(lab.view(1, 1, H, W).float(), n_eng)
+            for e in range(n_eng):
+                out = np.full((H, W), 77, np.uint8)
+                assert lib.emu_separate_label(vp(src), is_f32, vp(out), H, W, e, n_eng) == 0
+                w = want[e][0, 0].numpy()
+                if n_eng == 1:
+                    assert np.array_equal(out, lab.to(torch.uint8).numpy())
+                else:
+                    assert np.array_equal(out.astype(np.int64), w.astype(np.int64)), (is_f32, n_eng, e)
+
+
+def test_id_bank_decompositions_on_host_emulation(lib):
+    """tests/test_ops_gpu.py::test_id_embedding_matches_conv_of_one_hot: tap loop / rectangle + dominant class / row runs
+    against Conv2d(one-hot) + LayerNorm of the oracle, on a blocky and a noisy label map, with and without ignore."""
+    from rmem_b200.weights import pack_deaot
+    sd = O.make_state_dict("r50_deaotl", seed=0)
+    cfg = O.OracleConfig()
+    pk = pack_deaot(sd)
+    H, W = 97, 129
+    h, w = (H - 1) // 16 + 1, (W - 1) // 16 + 1
+    lab = O.synthetic_label(H, W, 10)
+    lab[0, 0, 5:30, 7:50] = 255
+    g = torch.Generator().manual_seed(9)
+    noisy = lab.clone()
+    m = torch.rand(lab.shape, generator=g) < 0.12
+    noisy[m] = torch.randint(0, 14, lab.shape, generator=g)[m].to(noisy.dtype)
+    noisy[0, 0, 40:70, 60:100] = torch.randint(0, 11, (30, 40), generator=g).to(noisy.dtype)
+    noisy[0, 0, 80:90, 10:40] = 255
+    wp, b, lg_, lb_ = npf(pk["idbank.w"]), npf(pk["idbank.b"]), npf(pk["id_norm.g"]), npf(pk["id_norm.b"])
+    prefix, rows = npf(pk["idbank.prefix"]), npf(pk["idbank.prefix_rows"])
+    Cc = b.size
+    for which, lb in (("blocks", lab), ("noisy", noisy)):
+        l8 = np.ascontiguousarray(lb[0, 0].to(torch.uint8).numpy())
+        for use_ignore in (False, True):
+            ref = O.id_embedding(sd, cfg, O.one_hot_with_ignore(lb, use_ignore)).numpy()
+            for pf, pr in ((None, None), (prefix, None), (prefix, rows)):
+                out = np.full((h * w, Cc), np.nan, np.float32)
+                rc = lib.emu_idbank(vp(l8), H, W, int(use_ignore), vp(wp), vp(b), vp(lg_), vp(lb_), vp(out), h, w, Cc,
+                                    vp(pf), vp(pr))
+                assert rc == 0, lib.rmem_last_error()
+                err = float(np.linalg.norm(out - ref) / np.linalg.norm(ref))
+                assert err < 2e-4, (which, use_ignore, pf is not None, pr is not None, err)
+
+
+def test_evict_relevance_on_host_emulation(lib):
+    """tests/test_ops_gpu.py::test_evict_relevance (aot_engine.py:355-362, transformer.py:891-906)."""
+    g = torch.Generator().manual_seed(8)
+    h, w, T = 17, 21, 5
+    mass = torch.rand(h * w, T, generator=g)
+    mass = mass / mass.sum(1, keepdim=True)
+    lg = torch.randn(1, 11, 65, 81, generator=g) * 2
+    fg = 1 - torch.softmax(F.interpolate(lg, size=(h, w), mode="bilinear", align_corners=True), 1)[0, 0].flatten()
+    ref = (mass * fg.view(-1, 1)).sum(0).numpy()
+    rel = np.full(T, np.nan, np.float32)
+    mass_np, lg_np = npf(mass), npf(lg[0])                 # kept alive across the call: vp() only carries the address
+    assert lib.emu_evict_relevance(vp(mass_np), T, vp(lg_np), 65, 81, h, w, vp(rel)) == 0, lib.rmem_last_error()
+    assert float(np.abs(rel - ref).max() / np.abs(ref).max()) < 1e-5
