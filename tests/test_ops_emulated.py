@@ -30,6 +30,28 @@ int emu_idbank(const uint8_t* label, int H, int W, int use_ignore, const float* 
   return rmem::idbank_embed(label, H, W, use_ignore, w_packed, bias, ln_g, ln_b, nullptr, 0, out_f32, h, w, Cc, nullptr,
                             prefix, prefix_rows);
 }
+int emu_layernorm(const float* x, const float* g, const float* b, void* y, int P, int Cc) {
+  return rmem::layernorm(x, Cc, g, b, (t16*)y, Cc, nullptr, 0, P, Cc, nullptr);
+}
+int emu_groupnorm(const void* x, int x_is_f32, const float* g, const float* b, void* y, int P, int Cc, int G, int relu,
+                  double* stats) {
+  return x_is_f32 ? rmem::groupnorm_f32((const float*)x, g, b, (t16*)y, P, Cc, G, relu, stats, nullptr)
+                  : rmem::groupnorm_t16((const t16*)x, g, b, (t16*)y, P, Cc, G, relu, stats, nullptr);
+}
+int emu_dwconv(const void* x, const float* w, void* y, int h, int wd, int Cc) {
+  return rmem::dwconv5x5((const t16*)x, w, (t16*)y, h, wd, Cc, nullptr);
+}
+int emu_upsample(const void* x, void* y, int hin, int win, int hout, int wout, int Cc) {
+  return rmem::upsample_bilinear_t16((const t16*)x, (t16*)y, hin, win, hout, wout, Cc, nullptr);
+}
+int emu_maxpool(const void* x, void* y, int Hin, int Win, int Cc, int Hout, int Wout) {
+  return rmem::maxpool3x3s2((const t16*)x, (t16*)y, Hin, Win, Cc, Hout, Wout, nullptr);
+}
+int emu_transpose(const void* x, long long ldx, void* y, long long ldy, int P, int Cc) {
+  return rmem::transpose_t16((const t16*)x, ldx, (t16*)y, ldy, P, Cc, nullptr);
+}
+int emu_gn_scratch_doubles() { return rmem::kGnScratchDoubles; }
+const char* emu_operand() { return RMEM_OPERAND_NAME; }
 int emu_evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel) {
   return rmem::evict_relevance(mass, T, logits4, h4, w4, h, w, rel, nullptr);
 }
@@ -144,3 +166,73 @@ def test_evict_relevance_on_host_emulation(lib):
     mass_np, lg_np = npf(mass), npf(lg[0])                 # kept alive across the call: vp() only carries the address
     assert lib.emu_evict_relevance(vp(mass_np), T, vp(lg_np), 65, 81, h, w, vp(rel)) == 0, lib.rmem_last_error()
     assert float(np.abs(rel - ref).max() / np.abs(ref).max()) < 1e-5
+
+
+def relfro(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-12))
+
+
+def h16(t):
+    """fp16 operand-rounded copy of a tensor as (numpy float16 array, rounded fp32 torch tensor)."""
+    a = np.ascontiguousarray(t.detach().numpy().astype(np.float16))
+    return a, torch.from_numpy(a.astype(np.float32))
+
+
+def test_norms_on_host_emulation(lib):
+    """tests/test_ops_gpu.py::test_layernorm_groupnorm at small sizes: LayerNorm, fp32- and fp16-input GroupNorm (two-level
+    deterministic statistics with the last-block fold) against torch / the oracle; 16-bit outputs: rel-Frobenius 4e-3."""
+    lib.emu_operand.restype = C.c_char_p
+    assert lib.emu_operand() == b"fp16"
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(90, 256, generator=g) * 2 + 0.3
+    gm, bt = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    ref = F.layer_norm(x, (256,), gm, bt, 1e-5).numpy()
+    xa, ga, ba = npf(x), npf(gm), npf(bt)
+    y = np.zeros((90, 256), np.float16)
+    assert lib.emu_layernorm(vp(xa), vp(ga), vp(ba), vp(y), 90, 256) == 0, lib.rmem_last_error()
+    assert relfro(y, ref) < 4e-3
+    stats = np.zeros(lib.emu_gn_scratch_doubles(), np.float64)          # element [64] = block counter, zero before first use
+    x = torch.randn(130, 512, generator=g) * 1.5 + 0.2
+    gm, bt = torch.rand(512, generator=g) + 0.5, torch.randn(512, generator=g)
+    ref = O.group_norm_tokens(x, gm, bt, 2).numpy()
+    xa, ga, ba = npf(x), npf(gm), npf(bt)
+    y = np.zeros((130, 512), np.float16)
+    assert lib.emu_groupnorm(vp(xa), 1, vp(ga), vp(ba), vp(y), 130, 512, 2, 0, vp(stats)) == 0, lib.rmem_last_error()
+    assert relfro(y, ref) < 4e-3
+    x16, xr = h16(torch.randn(11 * 13, 128, generator=g) + 0.1)
+    gm, bt = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    ref = F.relu(O.group_norm_tokens(xr, gm, bt, 8)).numpy()
+    ga, ba = npf(gm), npf(bt)
+    y = np.zeros((11 * 13, 128), np.float16)
+    for _ in range(2):                                                   # the counter re-arms itself: a second call works
+        assert lib.emu_groupnorm(vp(x16), 0, vp(ga), vp(ba), vp(y), 11 * 13, 128, 8, 1, vp(stats)) == 0, lib.rmem_last_error()
+        assert relfro(y, ref) < 4e-3
+
+
+def test_dwconv_upsample_maxpool_transpose_on_host_emulation(lib):
+    """tests/test_ops_gpu.py::test_dwconv_upsample_maxpool_transpose at small sizes (ragged tiles included)."""
+    g = torch.Generator().manual_seed(4)
+    for (h, w, Cc) in [(9, 20, 64), (5, 3, 64), (8, 18, 128)]:
+        x16, xr = h16(torch.randn(h * w, Cc, generator=g))
+        wt = torch.randn(Cc, 1, 5, 5, generator=g) / 5
+        ref = O.dwconv5(xr, wt, h, w).numpy()
+        wa = npf(wt.view(Cc, 25).t().contiguous())
+        y = np.zeros((h * w, Cc), np.float16)
+        assert lib.emu_dwconv(vp(x16), vp(wa), vp(y), h, w, Cc) == 0, lib.rmem_last_error()
+        assert relfro(y, ref) < 4e-3, (h, w, Cc)
+    h, w = 7, 10
+    x16, xr = h16(torch.randn(h, w, 64, generator=g))
+    ref = F.interpolate(xr.permute(2, 0, 1)[None], size=(13, 19), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
+    y = np.zeros((13, 19, 64), np.float16)
+    assert lib.emu_upsample(vp(x16), vp(y), h, w, 13, 19, 64) == 0, lib.rmem_last_error()
+    assert relfro(y, ref.numpy()) < 4e-3
+    x16, xr = h16(torch.randn(17, 21, 64, generator=g))
+    ref = F.max_pool2d(xr.permute(2, 0, 1)[None], 3, 2, 1)[0].permute(1, 2, 0).numpy()
+    y = np.zeros((9, 11, 64), np.float16)
+    assert lib.emu_maxpool(vp(x16), vp(y), 17, 21, 64, 9, 11) == 0, lib.rmem_last_error()
+    assert np.array_equal(y.astype(np.float32), ref)
+    x16, xr = h16(torch.randn(70, 128, generator=g))
+    y = np.full((128, 96), 1, np.float16)
+    assert lib.emu_transpose(vp(x16), 128, vp(y), 96, 70, 128) == 0, lib.rmem_last_error()
+    assert np.array_equal(y[:, :70].astype(np.float32), xr.t().numpy())
