@@ -97,6 +97,8 @@ class LossHead:
 
 LossFn = Callable[[torch.Tensor, torch.Tensor, int, int], torch.Tensor]     # (logits4, gt [H,W], obj_num, top_k) -> 0-d loss
 MaskFn = Callable[[torch.Tensor, int, int, int], torch.Tensor]              # (logits4, H, W, obj_num) -> label [H,W]
+# (logits4, gt, obj_num, top_k, scale) -> (0-d loss, scale * d loss / d logits4)
+LossGradFn = Callable[[torch.Tensor, torch.Tensor, int, int, float], Tuple[torch.Tensor, torch.Tensor]]
 
 
 def predict_mask(logits4: torch.Tensor, H: int, W: int, obj_num: int) -> torch.Tensor:
@@ -137,7 +139,8 @@ def _logits4(engine) -> torch.Tensor:
 def train_forward(engine, all_frames: torch.Tensor, all_masks: torch.Tensor, batch_size: int, obj_nums: Sequence[int],
                   step: int = 0, tf_board: bool = False, use_prev_pred: bool = False,
                   cfg: Optional[TrainConfig] = None, loss_fn: Optional[LossFn] = None,
-                  mask_fn: Optional[MaskFn] = None):
+                  mask_fn: Optional[MaskFn] = None, logit_grads: Optional[list] = None,
+                  loss_grad_fn: Optional[LossGradFn] = None):
     """AOTEngine.forward (aot_engine.py:40-128) over an engine with the reference's inference surface.
 
     all_frames [(F * B), 3, H, W] and all_masks [(F * B), 1, H, W] are frame-major as the trainer builds them
@@ -146,7 +149,13 @@ def train_forward(engine, all_frames: torch.Tensor, all_masks: torch.Tensor, bat
     (loss 0-d, all_pred_mask: F tensors [B, H, W], all_frame_loss: F tensors [B], boards).
 
     loss_fn / mask_fn default to the CUDA loss head and mask kernel (csrc/train_loss.cu); the CPU tests pass the
-    oracle's."""
+    oracle's.
+
+    logit_grads: pass an empty list to also get the head of the backward pass -- it is filled with F tensors
+    [B, C, h4, w4], d loss / d pred_id_logits of every frame (the engine overwrites its logits with the next frame, so
+    the gradient is taken when the frame's loss is: rmem_train_loss_fwd_bwd with grad_scale = the frame's weight in
+    `loss`, w_aux / B for the reference frame and 1 / ((F - 1) B) for the others).  Nothing below the logits is
+    differentiated (module docstring)."""
     cfg = cfg or TrainConfig()
     B = int(batch_size)
     assert all_frames.shape[0] % B == 0 and all_frames.shape[0] == all_masks.shape[0], "frame-major [(F*B), ...] inputs"
@@ -161,12 +170,20 @@ def train_forward(engine, all_frames: torch.Tensor, all_masks: torch.Tensor, bat
         mask_fn = predict_mask
     w_aux = aux_weight(step, cfg)
     k = top_k_pixels(step, H * W, cfg)
+    want_grads = logit_grads is not None
+    if want_grads and loss_grad_fn is None:
+        head = LossHead(all_frames.device if all_frames.is_cuda else "cuda:0")
+
+        def loss_grad_fn(lg, gt, n, kk, scale):
+            losses3, grad = head(lg, gt, n, kk, want_grad=True, grad_scale=scale)
+            return losses3[0], grad
+    per_sample_grads: List[List[torch.Tensor]] = []
 
     per_sample_losses: List[List[torch.Tensor]] = []     # [b][f]: aux loss of the reference frame, then the frames' losses
     per_sample_masks: List[List[torch.Tensor]] = []
     for b in range(B):
         n_obj = obj_nums[b]
-        losses, masks = [], []
+        losses, masks, grads = [], [], []
 
         def frame(f, b=b):
             return all_frames[f * B + b: f * B + b + 1]
@@ -176,7 +193,13 @@ def train_forward(engine, all_frames: torch.Tensor, all_masks: torch.Tensor, bat
 
         def loss_and_mask(f, n_obj=n_obj):          # generate_loss_mask (:513-521) on the logits the engine decoded last
             lg = _logits4(engine)
-            losses.append(loss_fn(lg, mask(f)[0, 0], n_obj, k))
+            if want_grads:
+                weight = w_aux / B if f == 0 else 1.0 / ((F_ - 1) * B)
+                l, g = loss_grad_fn(lg, mask(f)[0, 0], n_obj, k, weight)
+                losses.append(l)
+                grads.append(g.reshape(g.shape[-3:]))
+            else:
+                losses.append(loss_fn(lg, mask(f)[0, 0], n_obj, k))
             masks.append(mask_fn(lg, H, W, n_obj))
 
         engine.restart_engine()
@@ -190,6 +213,7 @@ def train_forward(engine, all_frames: torch.Tensor, all_masks: torch.Tensor, bat
             loss_and_mask(f)                                                                # :83-86, :99-102
         per_sample_losses.append(losses)
         per_sample_masks.append(masks)
+        per_sample_grads.append(grads)
 
     all_frame_loss = [torch.stack([torch.as_tensor(per_sample_losses[b][f]).float().reshape(()) for b in range(B)])
                       for f in range(F_)]
@@ -198,5 +222,7 @@ def train_forward(engine, all_frames: torch.Tensor, all_masks: torch.Tensor, bat
     aux_loss = all_frame_loss[0].mean(dim=0)                    # :104 torch.cat of one [B] tensor, mean over it
     pred_loss = torch.cat(all_frame_loss[1:], dim=0).mean(dim=0)    # :105 mean over every frame of every sample
     loss = w_aux * aux_loss + pred_loss                             # :109 (0-d; the trainer's torch.mean is a no-op)
+    if want_grads:
+        logit_grads[:] = [torch.stack([per_sample_grads[b][f] for b in range(B)], dim=0) for f in range(F_)]
     boards = {"image": {}, "scalar": {}}
     return loss, all_pred_mask, all_frame_loss, boards

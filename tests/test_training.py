@@ -391,3 +391,58 @@ def test_cuda_entry_points_reject_bad_arguments_on_host_emulation(emu_lib):
         assert rc == -1 and emu_lib.rmem_last_error()
     rc, _, _ = emu_loss_head(emu_lib, lg[:3], gt, 5, 10)
     assert rc == -1
+
+
+def test_train_forward_logit_grads_are_the_gradient_of_the_returned_loss():
+    """logit_grads: F tensors [B, C, h4, w4] = d loss / d pred_id_logits per frame, with the frame weights of
+    aot_engine.py:104-109 (w_aux / B for the reference frame, 1 / ((F - 1) B) for the others).  Checked against autograd
+    through the whole aggregation on a fake engine that serves fixed logits per (sample, frame)."""
+    H, W, B, F_, n_obj = 33, 41, 2, 3, 3
+    g = torch.Generator().manual_seed(2)
+    logits = [[(2 * torch.randn(1, 11, 9, 11, generator=g)).requires_grad_(True) for _ in range(F_)] for _ in range(B)]
+    gts = torch.randint(0, n_obj + 1, (F_ * B, 1, H, W), generator=g).float()
+    gts[:, :, 3:9, 5:15] = 255
+    frames = torch.zeros(F_ * B, 3, H, W)
+
+    class Sub:
+        pred_id_logits = None
+
+    class Fake:
+        def __init__(self):
+            self.aot_engines = [Sub()]
+            self.b, self.f = -1, 0
+
+        def restart_engine(self):
+            self.b += 1
+            self.f = 0
+
+        def add_reference_frame(self, img, mask, obj_nums, frame_step):
+            self.aot_engines[0].pred_id_logits = logits[self.b][0]
+
+        def match_propogate_one_frame(self, img, output_size=None):
+            self.f += 1
+            self.aot_engines[0].pred_id_logits = logits[self.b][self.f]
+
+        def update_memory(self, label):
+            pass
+
+    cfg = T.TrainConfig(total_steps=1000)
+    step = 300
+    # autograd through train_forward itself (differentiable oracle loss)
+    loss, _, fl, _ = T.train_forward(Fake(), frames, gts, B, [n_obj] * B, step=step, cfg=cfg,
+                                     loss_fn=lambda lg, gt, n, k: TO.loss_head(lg, gt, n, k)[0], mask_fn=TO.predict_mask)
+    loss.backward()
+    want = [torch.stack([logits[b][f].grad[0] for b in range(B)]) for f in range(F_)]
+
+    def loss_grad_fn(lg, gt, n, k, scale):
+        total, _, _, grad = TO.loss_head_with_grad(lg.detach(), gt, n, k)
+        return torch.tensor(total), scale * grad
+
+    got = []
+    loss2, _, fl2, _ = T.train_forward(Fake(), frames, gts, B, [n_obj] * B, step=step, cfg=cfg, mask_fn=TO.predict_mask,
+                                       logit_grads=got, loss_grad_fn=loss_grad_fn)
+    assert abs(float(loss2) - float(loss.detach())) < 1e-6 and len(got) == F_
+    for f in range(F_):
+        assert got[f].shape == (B, 11, 9, 11)
+        assert float((got[f] - want[f]).abs().max()) <= 1e-5 * float(want[f].abs().max()) + 1e-12
+    assert T.aux_weight(step, cfg) == pytest.approx(0.7, abs=1e-6)
