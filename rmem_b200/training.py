@@ -15,6 +15,10 @@ built: the backward of the layers under those logits (decoder, GPM / LSTT, encod
 gradient stops at `grad_logits4`.  The stochastic parts of the reference's training mode (dropout / drop-path, the
 random identity shuffle of `restart_engine(batch_size, True)`, aot_engine.py:515-547) are not reproduced: the forward
 is the eval-mode arithmetic of the same ops, which is what oracle/make_train_golden.py pins against the reference.
+One more eval / train difference matters only for sequences long enough to overflow the bank (the shipped training
+samples never are: <= 8 frames at TRAIN_LONG_TERM_MEM_GAP 4 against a capacity of 1 + 8): in training mode the reference
+evicts first-in-first-out (restrict_long_memories with use_atten_weight = False, transformer.py:888-890, 964-991), the
+engine always applies the inference rule (attention relevance, transformer.py:891-964).
 
 The product path has no CPU fallback: LossHead raises without the CUDA extension.  `train_forward` itself is host
 logic over the reference's engine surface and takes the loss as a callable, so the CPU tests drive it with the oracle
