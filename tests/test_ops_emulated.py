@@ -52,6 +52,13 @@ int emu_transpose(const void* x, long long ldx, void* y, long long ldy, int P, i
 }
 int emu_gn_scratch_doubles() { return rmem::kGnScratchDoubles; }
 const char* emu_operand() { return RMEM_OPERAND_NAME; }
+int emu_tta_head(const float* const* logits4, int n_aug, int k, const int* h4, const int* w4, const int* flip, int Ho, int Wo,
+                 float* out_prob, uint8_t* out_label) {
+  return rmem::tta_head(logits4, n_aug, k, h4, w4, flip, Ho, Wo, out_prob, out_label, nullptr);
+}
+int emu_preprocess(const uint8_t* img, int H, int W, int bgr, int nh, int nw, int flip, float* out) {
+  return rmem::preprocess_frame(img, H, W, bgr, nh, nw, flip, out, nullptr);
+}
 int emu_evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel) {
   return rmem::evict_relevance(mass, T, logits4, h4, w4, h, w, rel, nullptr);
 }
@@ -236,3 +243,55 @@ def test_dwconv_upsample_maxpool_transpose_on_host_emulation(lib):
     y = np.full((128, 96), 1, np.float16)
     assert lib.emu_transpose(vp(x16), 128, vp(y), 96, 70, 128) == 0, lib.rmem_last_error()
     assert np.array_equal(y[:, :70].astype(np.float32), xr.t().numpy())
+
+
+def test_tta_head_and_preprocess_on_host_emulation(lib):
+    """tests/test_ops_gpu.py::test_tta_head_matches_probability_averaging / test_gpu_preprocess_matches_cv2_loader at small
+    sizes (evaluator.py:420-441; video_transforms.py:559-682)."""
+    for k in (1, 2):
+        g = torch.Generator().manual_seed(17 + k)
+        Ho, Wo = 41, 53
+        sizes = [(11, 14), (11, 14), (14, 18), (14, 18)]
+        flips = [False, True, False, True]
+        logits = [[torch.randn(11, h4, w4, generator=g) * 3 for _ in range(k)] for (h4, w4) in sizes]
+        probs = []
+        for per, fl in zip(logits, flips):
+            ups = [F.interpolate(t[None], size=(Ho, Wo), mode="bilinear", align_corners=True) for t in per]
+            lg = O.soft_logit_aggregation(ups)
+            if fl:
+                lg = torch.flip(lg, dims=(3,))
+            probs.append(torch.softmax(lg, dim=1))
+        mean = torch.mean(torch.cat(probs, 0), 0)
+        ref_lab = torch.argmax(mean, 0).numpy()
+        arrs = [npf(t) for per in logits for t in per]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        n_aug = len(sizes)
+        h4 = (C.c_int * n_aug)(*[s[0] for s in sizes])
+        w4 = (C.c_int * n_aug)(*[s[1] for s in sizes])
+        fl = (C.c_int * n_aug)(*[int(f) for f in flips])
+        prob = np.full((1 + 10 * k, Ho, Wo), np.nan, np.float32)
+        lab = np.full((Ho, Wo), 99, np.uint8)
+        assert lib.emu_tta_head(ptrs, n_aug, k, h4, w4, fl, Ho, Wo, vp(prob), vp(lab)) == 0, lib.rmem_last_error()
+        assert float(np.abs(prob - mean.numpy()).max()) < 2e-5
+        top2 = torch.topk(mean, 2, dim=0).values
+        decided = ((top2[0] - top2[1]) > 1e-4).numpy()
+        assert bool((lab.astype(np.int64) == ref_lab)[decided].all()) and decided.mean() > 0.99
+    import cv2
+    rng = np.random.RandomState(3)
+    img = cv2.GaussianBlur(rng.randint(0, 255, (33, 57, 3)).astype(np.uint8), (0, 0), 1.5)
+    for (nh, nw) in ((33, 57), (49, 81), (17, 33)):
+        for flip in (False, True):
+            for bgr in (True, False):
+                ref = np.array(img, dtype=np.float32)
+                if bgr:
+                    ref = ref[:, :, [2, 1, 0]]
+                if (nh, nw) != ref.shape[:2]:
+                    ref = cv2.resize(ref, dsize=(nw, nh), interpolation=cv2.INTER_CUBIC)
+                if flip:
+                    ref = ref[:, ::-1]
+                ref = (ref / 255. - (0.485, 0.456, 0.406)) / (0.229, 0.224, 0.225)
+                ref = np.ascontiguousarray(ref.transpose(2, 0, 1)).astype(np.float32)
+                out = np.full((3, nh, nw), np.nan, np.float32)
+                src = np.ascontiguousarray(img)
+                assert lib.emu_preprocess(vp(src), 33, 57, int(bgr), nh, nw, int(flip), vp(out)) == 0, lib.rmem_last_error()
+                assert float(np.abs(out - ref).max()) < 2e-3, (nh, nw, flip, bgr)
