@@ -59,6 +59,10 @@ int emu_tta_head(const float* const* logits4, int n_aug, int k, const int* h4, c
 int emu_preprocess(const uint8_t* img, int H, int W, int bgr, int nh, int nw, int flip, float* out) {
   return rmem::preprocess_frame(img, H, W, bgr, nh, nw, flip, out, nullptr);
 }
+int emu_qprep(const void* q, long long ldq, const float* pe_cur, const float* pe_mem, const int* pe_slot, int T, float scale,
+              void* qt, float* qbias, int P, int Cc) {
+  return rmem::qprep((const t16*)q, ldq, pe_cur, pe_mem, pe_slot, T, scale, (t16*)qt, qbias, P, Cc, nullptr);
+}
 int emu_evict_relevance(const float* mass, int T, const float* logits4, int h4, int w4, int h, int w, float* rel) {
   return rmem::evict_relevance(mass, T, logits4, h4, w4, h, w, rel, nullptr);
 }
@@ -295,3 +299,29 @@ def test_tta_head_and_preprocess_on_host_emulation(lib):
                 src = np.ascontiguousarray(img)
                 assert lib.emu_preprocess(vp(src), 33, 57, int(bgr), nh, nw, int(flip), vp(out)) == 0, lib.rmem_last_error()
                 assert float(np.abs(out - ref).max()) < 2e-3, (nh, nw, flip, bgr)
+
+
+def test_temporal_pe_as_score_bias_on_host_emulation(lib):
+    """a11 (transformer.py:1140-1175): K[t] += mem_pos_emb[slot(t)], Q += cur_pos_emb.  The engine never rewrites the K bank:
+    qprep_kernel emits Qt = t16(Q + pe_cur) and the per-(query, frame) bias scale * <Qt_i, pe_mem[slot(t)]>, which the
+    attention kernels add to the scores -- algebraically <Qt_i, K_j + pe> = <Qt_i, K_j> + <Qt_i, pe>.  Checked against the
+    oracle's slot table and the explicit sums."""
+    g = torch.Generator().manual_seed(6)
+    P, Cc = 75, 128
+    for T in (1, 4, 7, 9):
+        slots = [lo for lo, hi, fr in O.temporal_pe_slots(T)]
+        assert all(fr == 0.0 for _, _, fr in O.temporal_pe_slots(T))
+        q16, qr = h16(torch.randn(P, Cc, generator=g))
+        pe_cur = torch.randn(Cc, generator=g) * 0.1
+        pe_mem = torch.randn(4, Cc, generator=g) * 0.5
+        scale = 1.0 / (Cc ** 0.5)
+        qt_ref = (qr + pe_cur).numpy().astype(np.float16)
+        bias_ref = scale * (torch.from_numpy(qt_ref.astype(np.float32)) @ O.temporal_pe(pe_mem, T).view(T, Cc).t())
+        pc, pm = npf(pe_cur), npf(pe_mem)
+        sl = (C.c_int * T)(*slots)
+        qt = np.zeros((P, Cc), np.float16)
+        qb = np.full((P, T), np.nan, np.float32)
+        assert lib.emu_qprep(vp(q16), C.c_longlong(Cc), vp(pc), vp(pm), sl, T, C.c_float(scale), vp(qt), vp(qb), P, Cc) == 0, \
+            lib.rmem_last_error()
+        assert np.array_equal(qt, qt_ref)
+        assert float(np.abs(qb - bias_ref.numpy()).max()) < 1e-5 * max(1.0, float(bias_ref.abs().max()))
