@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from oracle import rmem_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(900)        # an emulated block is real threads on barriers: fail, never hang
 
 SHIMS = """
 extern "C" {

@@ -18,6 +18,7 @@ from rmem_b200 import training as T
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden", "train_small.npz")
+pytestmark = pytest.mark.timeout(900)        # the emulated kernels are real threads on barriers: fail, never hang
 
 
 @pytest.fixture(scope="module")
