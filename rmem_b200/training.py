@@ -64,7 +64,9 @@ def aux_weight(step: int, cfg: TrainConfig) -> float:
 
 class LossHead:
     """0.5 * bootstrapped cross entropy + 0.5 * soft Jaccard of one frame and its gradient with respect to the 1/4-res
-    logits, on the GPU (rmem_train_loss_fwd_bwd).  Returns device tensors; nothing synchronises."""
+    logits, on the GPU (rmem_train_loss_fwd_bwd).  Returns device tensors; nothing synchronises.  One LossHead owns one
+    workspace (histograms, tickets, scratch): use it from one stream at a time -- one head per stream, like one engine per
+    stream."""
 
     def __init__(self, device="cuda:0"):
         self.device = torch.device(device)
